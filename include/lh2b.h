@@ -1,0 +1,108 @@
+/* lh2b.h - C ABI of the B200 Lighthouse 2 render core (libRenderCore_B200.so).
+
+   One opaque handle, plain pointers and sizes, int return codes (0 = ok, nonzero = failed,
+   message via lh2b_last_error()). Nothing is thrown across this boundary and no call aborts the
+   process (the reference cores call FatalError/exit; a library that other languages bind
+   should not).
+
+   Each entry point replaces one member of the reference's CoreAPI_Base
+   (lib/RenderSystem/core_api_base.h:81-119) as implemented by the Optix7 core
+   (lib/rendercore_optix7/rendercore.cpp). Struct arguments are passed as const void* to the
+   reference's own PODs (layouts restated in include/lh2_core_api.h). The C++ class behind
+   CreateCore() (csrc/core_api.cpp) forwards 1:1 to these functions.
+*/
+#ifndef LH2B_H
+#define LH2B_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LH2B_API __attribute__( ( visibility( "default" ) ) )
+
+typedef struct lh2b_core lh2b_core;
+
+/* CoreAPI_Base::Init (core_api_base.h:89, rendercore.cpp:219-278). device < 0: use LOCAL_RANK or 0. */
+LH2B_API int lh2b_create( lh2b_core** out, int device );
+/* CoreAPI_Base::Shutdown (core_api_base.h:101, rendercore.cpp:985-994). */
+LH2B_API int lh2b_destroy( lh2b_core* core );
+/* Last error message of the calling thread ("" if none). */
+LH2B_API const char* lh2b_last_error( void );
+
+/* CoreAPI_Base::SetTarget (core_api_base.h:93, rendercore.cpp:284-326): only width/height of the
+   GLTexture are used; the image is presented in a linear RGBA32F device buffer (lh2b_read_pixels). */
+LH2B_API int lh2b_set_target( lh2b_core* core, int width, int height, int spp );
+/* CoreAPI_Base::Setting (core_api_base.h:95, rendercore.cpp:746-760). Unknown names are ignored. */
+LH2B_API int lh2b_setting( lh2b_core* core, const char* name, float value );
+/* CoreAPI_Base::SetProbePos (core_api_base.h:91, rendercore.cpp:85-88). */
+LH2B_API int lh2b_set_probe_pos( lh2b_core* core, int x, int y );
+/* CoreAPI_Base::SetTextures (core_api_base.h:103, rendercore.cpp:438-502). tex: CoreTexDesc[count]. */
+LH2B_API int lh2b_set_textures( lh2b_core* core, const void* tex, int count );
+/* CoreAPI_Base::SetMaterials (core_api_base.h:105, rendercore.cpp:508-565). mat: CoreMaterial[count]. */
+LH2B_API int lh2b_set_materials( lh2b_core* core, const void* mat, int count );
+/* CoreAPI_Base::SetLights (core_api_base.h:107-110, rendercore.cpp:698-710). */
+LH2B_API int lh2b_set_lights( lh2b_core* core, const void* triLights, int triLightCount,
+	const void* pointLights, int pointLightCount, const void* spotLights, int spotLightCount,
+	const void* directionalLights, int directionalLightCount );
+/* CoreAPI_Base::SetSkyData (core_api_base.h:112, rendercore.cpp:716-740). pixels: float3[w*h]; worldToLight: 16 floats row major. */
+LH2B_API int lh2b_set_sky( lh2b_core* core, const float* pixels, int width, int height, const float* worldToLight );
+/* CoreAPI_Base::SetGeometry (core_api_base.h:114, rendercore.cpp:332-340, core_mesh.cpp:34-61).
+   vertexData: float4[vertexCount] (3 per triangle, not indexed); triangles: CoreTri[triangleCount]. */
+LH2B_API int lh2b_set_geometry( lh2b_core* core, int meshIdx, const float* vertexData, int vertexCount,
+	int triangleCount, const void* triangles );
+/* CoreAPI_Base::SetInstance (core_api_base.h:116, rendercore.cpp:346-376). transform: 16 floats row major;
+   meshIdx == -1 truncates the instance list at instanceIdx. */
+LH2B_API int lh2b_set_instance( lh2b_core* core, int instanceIdx, int meshIdx, const float* transform );
+/* CoreAPI_Base::FinalizeInstances (core_api_base.h:118, rendercore.cpp:382-432). */
+LH2B_API int lh2b_finalize_instances( lh2b_core* core );
+/* CoreAPI_Base::Render (core_api_base.h:97, rendercore.cpp:819-938). view: ViewPyramid (68 bytes);
+   converge: 0 = Converge, 1 = Restart. */
+LH2B_API int lh2b_render( lh2b_core* core, const void* view, int converge, int async );
+/* CoreAPI_Base::WaitForRender (core_api_base.h:99, rendercore.cpp:945-957). */
+LH2B_API int lh2b_wait_for_render( lh2b_core* core );
+/* CoreAPI_Base::GetCoreStats (core_api_base.h:87, rendercore.cpp:1000-1003). out: CoreStats (120 bytes). */
+LH2B_API int lh2b_get_stats( lh2b_core* core, void* outCoreStats );
+
+/* ---- headless extras (no reference counterpart: the reference presents through OpenGL) ---- */
+
+/* Copy the finalized image (accumulator / samplesTaken, finalize_shared.h:29-45) to host: float4[w*h]. */
+LH2B_API int lh2b_read_pixels( lh2b_core* core, float* rgbaOut );
+/* Copy the raw accumulator to host: float4[w*h]. */
+LH2B_API int lh2b_read_accumulator( lh2b_core* core, float* rgbaOut );
+/* Device pointer of the accumulator (float4[w*h]) for zero-copy collectives; samples taken so far. */
+LH2B_API int lh2b_accumulator_device_ptr( lh2b_core* core, void** ptrOut, int* samplesTakenOut );
+/* Multi-GPU sample sharding: this core renders sample indices [first, first+spp) of each pass and
+   seeds as if it were part of a 'total'-spp frame. Default: first 0, total = spp. */
+LH2B_API int lh2b_set_sample_shard( lh2b_core* core, int firstSample, int totalSpp );
+
+/* Closest-hit query over the current scene with HOST buffers (the traversal-only parity and
+   benchmark entry; same semantics as setupSecondaryRay, .optix.cu:131-140).
+   origins/directions: float4[n] (w ignored); hitsOut: float4[n] = (u16|v16<<16, inst, prim, t) bit
+   patterns, prim = -1 on a miss. */
+LH2B_API int lh2b_trace_rays( lh2b_core* core, const float* origins, const float* directions, int n, float* hitsOut );
+/* Occlusion query (generateShadowRay, .optix.cu:142-154): directions.w = tmax; occludedOut[i] = 1 if blocked. */
+LH2B_API int lh2b_trace_shadow_rays( lh2b_core* core, const float* origins, const float* directions, int n, uint8_t* occludedOut );
+/* Same queries on DEVICE buffers, asynchronous on the core's stream; msOut (optional) receives the
+   kernel time of 'repeat' back-to-back launches measured with CUDA events on that stream. */
+LH2B_API int lh2b_trace_rays_device( lh2b_core* core, const void* dOrigins, const void* dDirections, int n, void* dHitsOut, int repeat, float* msOut );
+LH2B_API int lh2b_trace_shadow_rays_device( lh2b_core* core, const void* dOrigins, const void* dDirections, int n, void* dOccludedOut, int repeat, float* msOut );
+/* The CUDA stream the core launches on (cudaStream_t as void*). */
+LH2B_API int lh2b_stream( lh2b_core* core, void** streamOut );
+/* Per-stage device times of the last Render in ms and ray counts; see lh2b_frame_stats below. */
+typedef struct lh2b_frame_stats
+{
+	float generateExtendMs, extendMs, shadeMs, connectMs, finalizeMs, buildMs, filterMs, totalMs;
+	uint32_t primaryRays, extensionRays, shadowRays, kernelLaunches;
+	uint32_t pathLengthReached, reserved[3];
+} lh2b_frame_stats;
+LH2B_API int lh2b_get_frame_stats( lh2b_core* core, lh2b_frame_stats* out );
+/* Acceleration-structure statistics of a mesh (meshIdx >= 0) or the top level (meshIdx = -1). */
+typedef struct lh2b_bvh_stats { uint32_t nodes, triangles, bytes; float buildMs; float sahCost; uint32_t reserved[3]; } lh2b_bvh_stats;
+LH2B_API int lh2b_get_bvh_stats( lh2b_core* core, int meshIdx, lh2b_bvh_stats* out );
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,177 @@
+"""Python host mirror of the reference's CoreAPI_Base (lib/RenderSystem/core_api_base.h:81-119):
+same method names, argument meaning and call-order contract, forwarding to the C ABI.
+Errors surface as CoreError (the reference cores call FatalError and exit)."""
+import ctypes
+import numpy as np
+
+from . import abi
+from .capi import load_library
+
+Converge, Restart = 0, 1
+
+
+class CoreError(RuntimeError):
+    pass
+
+
+def _ptr(a):
+    return None if a is None else ctypes.c_void_p(a.ctypes.data)
+
+
+def _arr(a, dtype):
+    if a is None:
+        return None
+    a = np.ascontiguousarray(a, dtype=dtype)
+    return a
+
+
+class RenderCore:
+    """One render core on one CUDA device (CoreAPI_Base::CreateCoreAPI + Init)."""
+
+    def __init__(self, device=-1):
+        self._lib = load_library()
+        self._h = ctypes.c_void_p()
+        self._check(self._lib.lh2b_create(ctypes.byref(self._h), device))
+        self.width = self.height = self.spp = 0
+
+    # -- plumbing ---------------------------------------------------------------------------
+    def _check(self, rc):
+        if rc != 0:
+            raise CoreError(self._lib.lh2b_last_error().decode())
+
+    def Shutdown(self):
+        if self._h:
+            self._lib.lh2b_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.Shutdown()
+        except Exception:
+            pass
+
+    # -- CoreAPI_Base -----------------------------------------------------------------------
+    def SetTarget(self, width, height, spp=1):
+        self._check(self._lib.lh2b_set_target(self._h, width, height, spp))
+        self.width, self.height, self.spp = width, height, spp
+
+    def Setting(self, name, value):
+        self._check(self._lib.lh2b_setting(self._h, name.encode(), float(value)))
+
+    def SetProbePos(self, x, y):
+        self._check(self._lib.lh2b_set_probe_pos(self._h, x, y))
+
+    def SetTextures(self, texels_list):
+        """texels_list: list of (array, storage) with array uint8[h,w,4] (ARGB32/NRM32) or float32[h,w,4] (ARGB128);
+        each may already contain its MIP chain appended (reference layout). Returns the CoreTexDesc array."""
+        n = len(texels_list)
+        descs = np.zeros(max(n, 1), dtype=abi.CoreTexDesc)
+        self._tex_keepalive = []
+        for i, (tex, storage, w, h, mips) in enumerate(texels_list):
+            tex = np.ascontiguousarray(tex)
+            self._tex_keepalive.append(tex)
+            descs[i]["data"] = tex.ctypes.data
+            descs[i]["width"], descs[i]["height"] = w, h
+            descs[i]["pixelCount"] = tex.size // 4
+            descs[i]["MIPlevels"] = mips
+            descs[i]["storage"] = storage
+        self._check(self._lib.lh2b_set_textures(self._h, _ptr(descs), n))
+        return descs[:n]
+
+    def SetMaterials(self, materials):
+        m = _arr(materials, abi.CoreMaterial)
+        self._check(self._lib.lh2b_set_materials(self._h, _ptr(m), len(m)))
+
+    def SetLights(self, tri=None, point=None, spot=None, directional=None):
+        t, p = _arr(tri, abi.CoreLightTri), _arr(point, abi.CorePointLight)
+        s, d = _arr(spot, abi.CoreSpotLight), _arr(directional, abi.CoreDirectionalLight)
+        n = [0 if x is None else len(x) for x in (t, p, s, d)]
+        self._check(self._lib.lh2b_set_lights(self._h, _ptr(t), n[0], _ptr(p), n[1], _ptr(s), n[2], _ptr(d), n[3]))
+
+    def SetSkyData(self, pixels, width, height, world_to_light=None):
+        px = _arr(pixels, np.float32)
+        m = _arr(np.eye(4) if world_to_light is None else world_to_light, np.float32)
+        self._check(self._lib.lh2b_set_sky(self._h, _ptr(px), width, height, _ptr(m)))
+
+    def SetGeometry(self, mesh_idx, vertex_data, triangles=None):
+        v = _arr(vertex_data, np.float32).reshape(-1, 4)
+        tri_count = v.shape[0] // 3
+        t = None if triangles is None else _arr(triangles, abi.CoreTri)
+        self._check(self._lib.lh2b_set_geometry(self._h, mesh_idx, _ptr(v), v.shape[0], tri_count, _ptr(t)))
+
+    def SetInstance(self, instance_idx, mesh_idx, transform=None):
+        m = _arr(np.eye(4) if transform is None else transform, np.float32)
+        self._check(self._lib.lh2b_set_instance(self._h, instance_idx, mesh_idx, _ptr(m)))
+
+    def FinalizeInstances(self):
+        self._check(self._lib.lh2b_finalize_instances(self._h))
+
+    def Render(self, view, converge=Restart, async_=False):
+        v = _arr(view, abi.ViewPyramid)
+        self._check(self._lib.lh2b_render(self._h, _ptr(v), int(converge), int(async_)))
+
+    def WaitForRender(self):
+        self._check(self._lib.lh2b_wait_for_render(self._h))
+
+    def GetCoreStats(self):
+        s = np.zeros(1, dtype=abi.CoreStats)
+        self._check(self._lib.lh2b_get_stats(self._h, _ptr(s)))
+        return s[0]
+
+    # -- headless extras --------------------------------------------------------------------
+    def ReadPixels(self, out=None):
+        out = np.empty((self.height, self.width, 4), np.float32) if out is None else out
+        self._check(self._lib.lh2b_read_pixels(self._h, _ptr(out)))
+        return out
+
+    def ReadAccumulator(self):
+        out = np.empty((self.height, self.width, 4), np.float32)
+        self._check(self._lib.lh2b_read_accumulator(self._h, _ptr(out)))
+        return out
+
+    def AccumulatorDevicePtr(self):
+        p, n = ctypes.c_void_p(), ctypes.c_int()
+        self._check(self._lib.lh2b_accumulator_device_ptr(self._h, ctypes.byref(p), ctypes.byref(n)))
+        return p.value, n.value
+
+    def SetSampleShard(self, first_sample, total_spp):
+        self._check(self._lib.lh2b_set_sample_shard(self._h, first_sample, total_spp))
+
+    def TraceRays(self, origins, directions):
+        o, d = _arr(origins, np.float32).reshape(-1, 4), _arr(directions, np.float32).reshape(-1, 4)
+        hits = np.empty((o.shape[0], 4), np.uint32)
+        self._check(self._lib.lh2b_trace_rays(self._h, _ptr(o), _ptr(d), o.shape[0], _ptr(hits)))
+        return hits
+
+    def TraceShadowRays(self, origins, directions):
+        o, d = _arr(origins, np.float32).reshape(-1, 4), _arr(directions, np.float32).reshape(-1, 4)
+        occ = np.empty(o.shape[0], np.uint8)
+        self._check(self._lib.lh2b_trace_shadow_rays(self._h, _ptr(o), _ptr(d), o.shape[0], _ptr(occ)))
+        return occ
+
+    def TraceRaysDevice(self, d_origins, d_directions, n, d_hits, repeat=1, timed=True):
+        ms = ctypes.c_float(0)
+        self._check(self._lib.lh2b_trace_rays_device(self._h, d_origins, d_directions, n, d_hits, repeat,
+                                                     ctypes.byref(ms) if timed else None))
+        return ms.value
+
+    def TraceShadowRaysDevice(self, d_origins, d_directions, n, d_occ, repeat=1, timed=True):
+        ms = ctypes.c_float(0)
+        self._check(self._lib.lh2b_trace_shadow_rays_device(self._h, d_origins, d_directions, n, d_occ, repeat,
+                                                            ctypes.byref(ms) if timed else None))
+        return ms.value
+
+    def Stream(self):
+        p = ctypes.c_void_p()
+        self._check(self._lib.lh2b_stream(self._h, ctypes.byref(p)))
+        return p.value
+
+    def GetFrameStats(self):
+        s = np.zeros(1, dtype=abi.FrameStats)
+        self._check(self._lib.lh2b_get_frame_stats(self._h, _ptr(s)))
+        return s[0]
+
+    def GetBvhStats(self, mesh_idx=-1):
+        s = np.zeros(1, dtype=abi.BvhStats)
+        self._check(self._lib.lh2b_get_bvh_stats(self._h, mesh_idx, _ptr(s)))
+        return s[0]

@@ -1,0 +1,311 @@
+/* bvh_build_cpu.cpp - host-side BVH construction: binned-SAH binary build, greedy collapse
+   to 8-wide, CWBVH node encoding.
+
+   Replaces optixAccelBuild (reference call sites: lib/rendercore_optix7/core_mesh.cpp:105,123 for
+   triangle meshes, lib/rendercore_optix7/rendercore.cpp:795 for the instance level). The GPU LBVH
+   builder (bvh_gpu.cu) emits the same Bvh2Node array and uses the same encoding rules; this host
+   builder is the quality yardstick and the path for "build once" static meshes when the caller asks
+   for it (Setting("bvhBuilder", 1)).
+*/
+#include "bvh.h"
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstring>
+#include <future>
+#include <cfloat>
+
+namespace lh2b
+{
+
+static inline float HalfArea( const float* lo, const float* hi )
+{
+	const float ex = hi[0] - lo[0], ey = hi[1] - lo[1], ez = hi[2] - lo[2];
+	return ex * ey + ey * ez + ez * ex;
+}
+
+static inline void GrowBox( float* lo, float* hi, const float* blo, const float* bhi )
+{
+	for (int a = 0; a < 3; a++) lo[a] = std::min( lo[a], blo[a] ), hi[a] = std::max( hi[a], bhi[a] );
+}
+
+struct BuildCtx
+{
+	const Aabb* boxes;
+	std::vector<float> cent;		// 3 per primitive
+	uint32_t* idx;
+	Bvh2Node* nodes;
+	std::atomic<int> nodePtr;
+	int maxLeaf;
+};
+
+static const int BINS = 16;
+
+static void Subdivide( BuildCtx& c, const int nodeIdx, const int first, const int count, const int depth )
+{
+	Bvh2Node& node = c.nodes[nodeIdx];
+	float lo[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, hi[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
+	float clo[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, chi[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
+	for (int i = 0; i < count; i++)
+	{
+		const uint32_t p = c.idx[first + i];
+		GrowBox( lo, hi, c.boxes[p].lo, c.boxes[p].hi );
+		for (int a = 0; a < 3; a++) clo[a] = std::min( clo[a], c.cent[p * 3 + a] ), chi[a] = std::max( chi[a], c.cent[p * 3 + a] );
+	}
+	memcpy( node.lo, lo, 12 ), memcpy( node.hi, hi, 12 );
+	auto makeLeaf = [&]() { node.left = ~first; node.right = count; };
+	if (count == 1) { makeLeaf(); return; }
+	// binned SAH over the three axes
+	float bestCost = FLT_MAX;
+	int bestAxis = -1, bestSplit = 0;
+	for (int a = 0; a < 3; a++)
+	{
+		const float ext = chi[a] - clo[a];
+		if (!(ext > 0)) continue;
+		const float scale = BINS / ext;
+		int cnt[BINS] = {};
+		float blo[BINS][3], bhi[BINS][3];
+		for (int b = 0; b < BINS; b++) for (int k = 0; k < 3; k++) blo[b][k] = FLT_MAX, bhi[b][k] = -FLT_MAX;
+		for (int i = 0; i < count; i++)
+		{
+			const uint32_t p = c.idx[first + i];
+			const int b = std::min( BINS - 1, (int)((c.cent[p * 3 + a] - clo[a]) * scale) );
+			cnt[b]++;
+			GrowBox( blo[b], bhi[b], c.boxes[p].lo, c.boxes[p].hi );
+		}
+		float rightArea[BINS];
+		int rightCnt[BINS];
+		float rlo[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, rhi[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
+		int rc = 0;
+		for (int b = BINS - 1; b > 0; b--)
+		{
+			if (cnt[b]) GrowBox( rlo, rhi, blo[b], bhi[b] );
+			rc += cnt[b];
+			rightCnt[b] = rc, rightArea[b] = rc ? HalfArea( rlo, rhi ) : 0;
+		}
+		float llo[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, lhi[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
+		int lc = 0;
+		for (int b = 0; b < BINS - 1; b++)
+		{
+			if (cnt[b]) GrowBox( llo, lhi, blo[b], bhi[b] );
+			lc += cnt[b];
+			if (lc == 0 || rightCnt[b + 1] == 0) continue;
+			const float cost = HalfArea( llo, lhi ) * lc + rightArea[b + 1] * rightCnt[b + 1];
+			if (cost < bestCost) bestCost = cost, bestAxis = a, bestSplit = b + 1;
+		}
+	}
+	const float nodeArea = HalfArea( lo, hi );
+	if (count <= c.maxLeaf)
+	{
+		// a leaf is legal: keep it unless the split is clearly cheaper (node visit ~ 0.5 tri tests in an 8-wide tree)
+		const float leafCost = nodeArea * count;
+		if (bestAxis < 0 || bestCost + 0.5f * nodeArea >= leafCost) { makeLeaf(); return; }
+	}
+	int mid;
+	if (bestAxis >= 0)
+	{
+		const float scale = BINS / (chi[bestAxis] - clo[bestAxis]);
+		const float base = clo[bestAxis];
+		uint32_t* b = c.idx + first, * e = c.idx + first + count;
+		uint32_t* m = std::partition( b, e, [&]( uint32_t p ) {
+			return std::min( BINS - 1, (int)((c.cent[p * 3 + bestAxis] - base) * scale) ) < bestSplit; } );
+		mid = (int)(m - b);
+	}
+	else mid = 0;
+	if (mid == 0 || mid == count)
+	{
+		// degenerate (coincident centroids): median split on index order
+		mid = count / 2;
+	}
+	const int l = c.nodePtr.fetch_add( 2 );
+	node.left = l, node.right = l + 1;
+	if (count > 32768 && depth < 6)
+	{
+		auto fut = std::async( std::launch::async, [&c, l, first, mid, depth]() { Subdivide( c, l, first, mid, depth + 1 ); } );
+		Subdivide( c, l + 1, first + mid, count - mid, depth + 1 );
+		fut.get();
+	}
+	else
+	{
+		Subdivide( c, l, first, mid, depth + 1 );
+		Subdivide( c, l + 1, first + mid, count - mid, depth + 1 );
+	}
+}
+
+void BuildBvh2FromBoxes( const Aabb* boxes, int count, int maxLeaf, std::vector<Bvh2Node>& nodes, std::vector<uint32_t>& primIdx )
+{
+	nodes.assign( count > 0 ? 2 * count : 1, Bvh2Node{} );
+	primIdx.resize( count );
+	if (count == 0)
+	{
+		Bvh2Node& n = nodes[0];
+		for (int a = 0; a < 3; a++) n.lo[a] = 0, n.hi[a] = 0;
+		n.left = ~0, n.right = 0;
+		nodes.resize( 1 );
+		return;
+	}
+	BuildCtx c;
+	c.boxes = boxes, c.idx = primIdx.data(), c.nodes = nodes.data(), c.maxLeaf = maxLeaf;
+	c.cent.resize( (size_t)count * 3 );
+	for (int i = 0; i < count; i++)
+	{
+		primIdx[i] = i;
+		for (int a = 0; a < 3; a++) c.cent[i * 3 + a] = 0.5f * (boxes[i].lo[a] + boxes[i].hi[a]);
+	}
+	c.nodePtr = 1;
+	Subdivide( c, 0, 0, count, 0 );
+	nodes.resize( c.nodePtr.load() );
+}
+
+void BuildBvh2SAH( const float* verts4, int triCount, std::vector<Bvh2Node>& nodes, std::vector<uint32_t>& primIdx )
+{
+	std::vector<Aabb> boxes( triCount );
+	for (int i = 0; i < triCount; i++)
+	{
+		const float* v = verts4 + (size_t)i * 12;
+		for (int a = 0; a < 3; a++)
+			boxes[i].lo[a] = std::min( v[a], std::min( v[4 + a], v[8 + a] ) ),
+			boxes[i].hi[a] = std::max( v[a], std::max( v[4 + a], v[8 + a] ) );
+	}
+	BuildBvh2FromBoxes( boxes.data(), triCount, 3, nodes, primIdx );
+}
+
+/* ---- collapse + encode ------------------------------------------------------------------ */
+
+static inline bool IsLeaf( const Bvh2Node& n ) { return n.left < 0; }
+
+/* Assign up to 8 children to slots 0..7 so that slot bits match the side of the node the child sits on. */
+static void AssignSlots( const Bvh2Node* bvh2, const int* child, int n, const float* nodeLo, const float* nodeHi, int* slotOf )
+{
+	float score[8][8];
+	const float cx = 0.5f * (nodeLo[0] + nodeHi[0]), cy = 0.5f * (nodeLo[1] + nodeHi[1]), cz = 0.5f * (nodeLo[2] + nodeHi[2]);
+	for (int i = 0; i < n; i++)
+	{
+		const Bvh2Node& c = bvh2[child[i]];
+		const float dx = 0.5f * (c.lo[0] + c.hi[0]) - cx, dy = 0.5f * (c.lo[1] + c.hi[1]) - cy, dz = 0.5f * (c.lo[2] + c.hi[2]) - cz;
+		for (int s = 0; s < 8; s++)
+			score[i][s] = ((s & 4) ? dx : -dx) + ((s & 2) ? dy : -dy) + ((s & 1) ? dz : -dz);
+	}
+	bool slotUsed[8] = {}, childDone[8] = {};
+	for (int i = 0; i < n; i++) slotOf[i] = -1;
+	for (int round = 0; round < n; round++)
+	{
+		float best = -FLT_MAX;
+		int bi = -1, bs = -1;
+		for (int i = 0; i < n; i++) if (!childDone[i]) for (int s = 0; s < 8; s++) if (!slotUsed[s])
+			if (score[i][s] > best) best = score[i][s], bi = i, bs = s;
+		slotOf[bi] = bs, slotUsed[bs] = true, childDone[bi] = true;
+	}
+}
+
+void CollapseToCwBvh( const std::vector<Bvh2Node>& bvh2v, const std::vector<uint32_t>& primIdx, const float* verts4, CwBvh& out )
+{
+	const Bvh2Node* bvh2 = bvh2v.data();
+	out.nodes.clear(), out.tris.clear(), out.leafIds.clear();
+	memcpy( out.bounds.lo, bvh2[0].lo, 12 ), memcpy( out.bounds.hi, bvh2[0].hi, 12 );
+	struct Task { int bvh2Node, cwNode; };
+	std::vector<Task> queue;
+	out.nodes.push_back( CwNode{} );
+	queue.push_back( { 0, 0 } );
+	size_t head = 0;
+	auto emitLeafPrim = [&]( uint32_t prim ) {
+		if (verts4)
+		{
+			const float* v = verts4 + (size_t)prim * 12;
+			CwTri t;
+			for (int a = 0; a < 3; a++) t.v0[a] = v[a], t.e1[a] = v[4 + a] - v[a], t.e2[a] = v[8 + a] - v[a];
+			t.prim = (int32_t)prim, t.pad1 = 0, t.pad2 = 0;
+			out.tris.push_back( t );
+		}
+		else out.leafIds.push_back( prim );
+	};
+	while (head < queue.size())
+	{
+		const Task task = queue[head++];
+		const Bvh2Node& root = bvh2[task.bvh2Node];
+		// gather up to 8 children by repeatedly opening the internal child with the largest area
+		int child[8], n = 0;
+		if (IsLeaf( root )) child[n++] = task.bvh2Node;
+		else
+		{
+			child[n++] = root.left, child[n++] = root.right;
+			while (n < 8)
+			{
+				float bestA = -1;
+				int bi = -1;
+				for (int i = 0; i < n; i++) if (!IsLeaf( bvh2[child[i]] ))
+				{
+					const float a = HalfArea( bvh2[child[i]].lo, bvh2[child[i]].hi );
+					if (a > bestA) bestA = a, bi = i;
+				}
+				if (bi < 0) break;
+				const Bvh2Node& open = bvh2[child[bi]];
+				child[bi] = open.left, child[n++] = open.right;
+			}
+		}
+		int slotOf[8];
+		AssignSlots( bvh2, child, n, root.lo, root.hi, slotOf );
+		int childInSlot[8];
+		for (int s = 0; s < 8; s++) childInSlot[s] = -1;
+		for (int i = 0; i < n; i++) childInSlot[slotOf[i]] = child[i];
+		// node header
+		uint8_t bytes[80] = {};
+		float p[3] = { root.lo[0], root.lo[1], root.lo[2] };
+		uint8_t e[3];
+		float quantum[3];
+		for (int a = 0; a < 3; a++)
+		{
+			const float ext = root.hi[a] - root.lo[a];
+			int ex = ext > 0 ? (int)ceilf( log2f( ext / 255.0f ) ) : -126;
+			ex = std::max( -126, std::min( 127, ex ) );
+			// make sure 255 quanta really cover the extent (log2f rounding)
+			while (ex < 127 && ldexpf( 255.0f, ex ) < ext) ex++;
+			e[a] = (uint8_t)(ex + 127), quantum[a] = ldexpf( 1.0f, ex );
+		}
+		memcpy( bytes, p, 12 );
+		bytes[12] = e[0], bytes[13] = e[1], bytes[14] = e[2];
+		uint8_t imask = 0;
+		int internalCount = 0, triCount = 0;
+		for (int s = 0; s < 8; s++) if (childInSlot[s] >= 0 && !IsLeaf( bvh2[childInSlot[s]] )) imask |= 1 << s, internalCount++;
+		bytes[15] = imask;
+		const uint32_t childBase = (uint32_t)out.nodes.size();
+		const uint32_t triBase = (uint32_t)(verts4 ? out.tris.size() : out.leafIds.size());
+		memcpy( bytes + 16, &childBase, 4 ), memcpy( bytes + 20, &triBase, 4 );
+		int nextInternal = 0;
+		for (int s = 0; s < 8; s++)
+		{
+			const int ci = childInSlot[s];
+			if (ci < 0) continue; // meta 0, boxes 0
+			const Bvh2Node& c = bvh2[ci];
+			if (IsLeaf( c ))
+			{
+				const int first = ~c.left, count = c.right;
+				// count is 1..3 by construction; unary encode
+				bytes[24 + s] = (uint8_t)((((1 << count) - 1) << 5) | triCount);
+				for (int k = 0; k < count; k++) emitLeafPrim( primIdx[first + k] );
+				triCount += count;
+			}
+			else
+			{
+				bytes[24 + s] = (uint8_t)((1 << 5) | (24 + s));
+				queue.push_back( { ci, (int)childBase + nextInternal } );
+				nextInternal++;
+			}
+			for (int a = 0; a < 3; a++)
+			{
+				// conservative quantisation: floor for lo, ceil for hi, checked against float rounding of p + q * 2^e
+				int qlo = (int)floorf( (c.lo[a] - p[a]) / quantum[a] );
+				int qhi = (int)ceilf( (c.hi[a] - p[a]) / quantum[a] );
+				qlo = std::max( 0, std::min( 255, qlo ) ), qhi = std::max( 0, std::min( 255, qhi ) );
+				while (qlo > 0 && p[a] + qlo * quantum[a] > c.lo[a]) qlo--;
+				while (qhi < 255 && p[a] + qhi * quantum[a] < c.hi[a]) qhi++;
+				bytes[32 + a * 8 + s] = (uint8_t)qlo;
+				bytes[56 + a * 8 + s] = (uint8_t)qhi;
+			}
+		}
+		for (int k = 0; k < internalCount; k++) out.nodes.push_back( CwNode{} );
+		memcpy( &out.nodes[task.cwNode], bytes, 80 );
+	}
+}
+
+} // namespace lh2b

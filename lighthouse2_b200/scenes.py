@@ -1,0 +1,184 @@
+"""Synthetic scenes and cameras for the configurations named in BASELINE.json.
+
+Everything here produces the *inputs* the reference RenderSystem would hand to a core through
+CoreAPI_Base: float4 positions, CoreTri records, CoreMaterial records, CoreLightTri records and a
+ViewPyramid. The arithmetic of those host-side producers is restated from:
+  Camera::GetView ................. lib/RenderSystem/camera.cpp:107-128
+  mat4::LookAt .................... lib/RenderSystem/common_types.h:514-538
+  HostTriLight::HostTriLight ...... lib/RenderSystem/host_light.cpp:25-42
+  CoreTri fields .................. lib/RenderSystem/common_classes.h:57-97
+"""
+import math
+import numpy as np
+
+from . import abi
+
+f32 = np.float32
+
+
+def _normalize(v):
+    v = np.asarray(v, dtype=np.float64)
+    return v / np.linalg.norm(v, axis=-1, keepdims=True)
+
+
+def view_pyramid(pos, target, fov_deg=40.0, width=1920, height=1080, focal_distance=5.0, aperture=0.0, distortion=0.0):
+    """ViewPyramid as Camera::GetView builds it (p1 top-left, p2 top-right, p3 bottom-left of the focal plane)."""
+    pos, target = np.asarray(pos, np.float64), np.asarray(target, np.float64)
+    z = _normalize(target - pos)
+    x = _normalize(np.cross(z, [0.0, 1.0, 0.0]))
+    y = np.cross(x, z)
+    aspect = width / height
+    screen = math.tan(fov_deg / 2 / (180 / math.pi))
+    c = pos + focal_distance * z
+    v = np.zeros(1, dtype=abi.ViewPyramid)
+    v["pos"] = pos
+    v["p1"] = c - screen * x * focal_distance * aspect + screen * focal_distance * y
+    v["p2"] = c + screen * x * focal_distance * aspect + screen * focal_distance * y
+    v["p3"] = c - screen * x * focal_distance * aspect - screen * focal_distance * y
+    v["aperture"], v["focalDistance"], v["distortion"] = aperture, focal_distance, distortion
+    v["spreadAngle"] = (fov_deg * math.pi / 180) / height
+    up1 = c - screen * x * aspect + screen * y
+    up2 = c + screen * x * aspect + screen * y
+    up3 = c - screen * x * aspect - screen * y
+    v["imagePlane"] = np.linalg.norm(up1 - up2) * np.linalg.norm(up1 - up3)
+    return v
+
+
+def core_tris_from_verts(verts4, material=0, smooth_normals=None):
+    """Fill CoreTri records for non-indexed float4 positions (3 per triangle)."""
+    v = np.asarray(verts4, f32).reshape(-1, 3, 4)[:, :, :3]
+    n = v.shape[0]
+    t = np.zeros(n, dtype=abi.CoreTri)
+    e1, e2 = v[:, 1] - v[:, 0], v[:, 2] - v[:, 0]
+    N = np.cross(e1.astype(np.float64), e2.astype(np.float64))
+    ln = np.linalg.norm(N, axis=1, keepdims=True)
+    N = np.where(ln > 0, N / np.maximum(ln, 1e-30), [0.0, 1.0, 0.0])
+    t["Nx"], t["Ny"], t["Nz"] = N[:, 0], N[:, 1], N[:, 2]
+    if smooth_normals is None:
+        t["vN0"] = t["vN1"] = t["vN2"] = N
+    else:
+        sn = np.asarray(smooth_normals, f32).reshape(-1, 3, 3)
+        t["vN0"], t["vN1"], t["vN2"] = sn[:, 0], sn[:, 1], sn[:, 2]
+    T = _normalize(np.where(np.linalg.norm(e1, axis=1, keepdims=True) > 0, e1, [1.0, 0.0, 0.0]))
+    B = np.cross(N, T)
+    t["T"], t["B"] = T, B
+    a = np.linalg.norm(v[:, 1] - v[:, 0], axis=1).astype(f32)
+    b = np.linalg.norm(v[:, 2] - v[:, 1], axis=1).astype(f32)
+    c = np.linalg.norm(v[:, 0] - v[:, 2], axis=1).astype(f32)
+    s = (a + b + c) * f32(0.5)
+    area = np.sqrt(np.maximum(s * (s - a) * (s - b) * (s - c), 0)).astype(f32)
+    t["area"] = area
+    t["invArea"] = np.where(area > 0, 1.0 / np.maximum(area, 1e-30), 0)
+    t["vertex0"], t["vertex1"], t["vertex2"] = v[:, 0], v[:, 1], v[:, 2]
+    t["material"] = material
+    t["ltriIdx"] = -1
+    t["u"] = [0.0, 1.0, 0.0]
+    t["v"] = [0.0, 0.0, 1.0]
+    return t
+
+
+def quad(center, normal, width, depth):
+    """Two triangles forming a quad like HostScene::AddQuad (facing 'normal')."""
+    n = _normalize(normal)
+    helper = np.array([1.0, 0.0, 0.0]) if abs(n[0]) < 0.9 else np.array([0.0, 0.0, 1.0])
+    t = _normalize(np.cross(n, helper)) * (width * 0.5)
+    b = _normalize(np.cross(n, t)) * (depth * 0.5)
+    c = np.asarray(center, np.float64)
+    p = [c - t - b, c + t - b, c + t + b, c - t + b]
+    tri = np.array([p[0], p[1], p[2], p[0], p[2], p[3]])
+    # make the winding agree with the requested normal
+    if np.dot(np.cross(tri[1] - tri[0], tri[2] - tri[0]), n) < 0:
+        tri = tri[[0, 2, 1, 3, 5, 4]]
+    v = np.zeros((6, 4), f32)
+    v[:, :3] = tri
+    return v
+
+
+def tri_lights(verts4, tris, materials, inst_idx=0, transform=None, first_ltri=0):
+    """CoreLightTri records for the emissive triangles of a mesh instance; also sets tris['ltriIdx'].
+    A material is emissive when a colour channel exceeds 1 (HostMaterial::IsEmissive)."""
+    v = np.asarray(verts4, f32).reshape(-1, 3, 4)[:, :, :3].astype(np.float64)
+    lights = []
+    for i in range(v.shape[0]):
+        col = materials[int(tris[i]["material"])]["color"]["value"]
+        if not (col > 1.0).any():
+            continue
+        p = v[i]
+        if transform is not None:
+            m = np.asarray(transform, np.float64).reshape(4, 4)
+            p = p @ m[:3, :3].T + m[:3, 3]
+        l = np.zeros(1, dtype=abi.CoreLightTri)
+        p32 = p.astype(f32)
+        l["vertex0"], l["vertex1"], l["vertex2"] = p32[0], p32[1], p32[2]
+        l["centre"] = f32(0.333333) * (p32[0] + p32[1] + p32[2])
+        n = np.cross(p[1] - p[0], p[2] - p[0])
+        l["N"] = n / np.linalg.norm(n)
+        a = f32(np.linalg.norm(p32[1] - p32[0])); b = f32(np.linalg.norm(p32[2] - p32[1])); c = f32(np.linalg.norm(p32[0] - p32[2]))
+        s = (a + b + c) * f32(0.5)
+        area = f32(math.sqrt(max(float(s * (s - a) * (s - b) * (s - c)), 0.0)))
+        l["area"], l["radiance"] = area, col
+        l["energy"] = float((col * area).sum())
+        l["triIdx"], l["instIdx"] = i, inst_idx
+        tris[i]["ltriIdx"] = first_ltri + len(lights)
+        lights.append(l)
+    return np.concatenate(lights) if lights else np.zeros(0, dtype=abi.CoreLightTri)
+
+
+def terrain(nx=1000, nz=500, extent=50.0, seed=0x12345678, floaters=0):
+    """Jittered-grid height field over [-extent, extent]^2 with 2 triangles per cell (nx * nz * 2 triangles),
+    plus 'floaters' random small triangles above it. Returns float4[3 * T]."""
+    rng = np.random.default_rng(seed)
+    gx, gz = np.meshgrid(np.arange(nx + 1), np.arange(nz + 1), indexing="ij")
+    jx = (rng.random(gx.shape) - 0.5) * 0.6
+    jz = (rng.random(gx.shape) - 0.5) * 0.6
+    jx[[0, -1], :] = 0; jz[:, [0, -1]] = 0
+    x = ((gx + jx) / nx * 2 - 1) * extent
+    z = ((gz + jz) / nz * 2 - 1) * extent
+    y = (3.0 * np.sin(x * 0.21) * np.cos(z * 0.17) + 1.5 * np.sin(x * 0.63 + 1.3) * np.sin(z * 0.71)
+         + 0.5 * np.sin(x * 1.9) * np.cos(z * 2.3) + 0.15 * rng.standard_normal(gx.shape))
+    p = np.stack([x, y, z], axis=-1)
+    p00, p10, p01, p11 = p[:-1, :-1], p[1:, :-1], p[:-1, 1:], p[1:, 1:]
+    t1 = np.stack([p00, p01, p10], axis=2)  # upward facing
+    t2 = np.stack([p10, p01, p11], axis=2)
+    tris = np.concatenate([t1.reshape(-1, 3, 3), t2.reshape(-1, 3, 3)], axis=0)
+    if floaters > 0:
+        c = np.stack([(rng.random(floaters) * 2 - 1) * extent, 6 + rng.random(floaters) * 10, (rng.random(floaters) * 2 - 1) * extent], axis=1)
+        d = (rng.random((floaters, 3, 3)) - 0.5) * 0.6
+        tris = np.concatenate([tris, c[:, None, :] + d], axis=0)
+    v = np.zeros((tris.shape[0] * 3, 4), f32)
+    v[:, :3] = tris.reshape(-1, 3)
+    return v
+
+
+def random_soup(n, extent=10.0, size=1.0, seed=1):
+    """n random triangles in a cube; the parity workhorse (lots of overlaps and near misses)."""
+    rng = np.random.default_rng(seed)
+    c = (rng.random((n, 1, 3)) * 2 - 1) * extent
+    d = (rng.random((n, 3, 3)) - 0.5) * size
+    v = np.zeros((n * 3, 4), f32)
+    v[:, :3] = (c + d).reshape(-1, 3)
+    return v
+
+
+def camera_rays(view, width, height, sub=(0.5, 0.5)):
+    """Pinhole primary rays through pixel centres (distortion 0, aperture 0): float4 O, float4 D."""
+    v = view[0]
+    pos, p1, p2, p3 = (np.asarray(v[k], np.float64) for k in ("pos", "p1", "p2", "p3"))
+    right, up = p2 - p1, p3 - p1
+    sx, sy = np.meshgrid(np.arange(width), np.arange(height), indexing="xy")
+    u = (sx + sub[0]) / width
+    w = (sy + sub[1]) / height
+    target = p1 + u[..., None] * right + w[..., None] * up
+    d = _normalize(target - pos).reshape(-1, 3)
+    O = np.zeros((width * height, 4), f32); D = np.zeros((width * height, 4), f32)
+    O[:, :3] = pos; D[:, :3] = d
+    return O, D
+
+
+def random_rays(n, extent=12.0, seed=2):
+    rng = np.random.default_rng(seed)
+    O = np.zeros((n, 4), f32); D = np.zeros((n, 4), f32)
+    O[:, :3] = (rng.random((n, 3)) * 2 - 1) * extent
+    t = (rng.random((n, 3)) * 2 - 1) * extent * 0.5
+    D[:, :3] = _normalize(t - O[:, :3])
+    return O, D

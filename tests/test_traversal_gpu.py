@@ -1,0 +1,98 @@
+"""GPU parity of extend / connect (hand-written CWBVH traversal) against the brute-force CPU oracle.
+Bit-exact: hit record = (u16|v16<<16, instance, primitive, t bits); occlusion flag."""
+import numpy as np
+import pytest
+
+from lighthouse2_b200 import RenderCore, scenes
+from oracle import binding as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _rot(axis, angle, t=(0, 0, 0), s=1.0):
+    axis = np.asarray(axis, np.float64) / np.linalg.norm(axis)
+    x, y, z = axis
+    c, si = np.cos(angle), np.sin(angle)
+    r = np.array([[c + x * x * (1 - c), x * y * (1 - c) - z * si, x * z * (1 - c) + y * si],
+                  [y * x * (1 - c) + z * si, c + y * y * (1 - c), y * z * (1 - c) - x * si],
+                  [z * x * (1 - c) - y * si, z * y * (1 - c) + x * si, c + z * z * (1 - c)]])
+    m = np.eye(4)
+    m[:3, :3] = r * s
+    m[:3, 3] = t
+    return m.astype(np.float32)
+
+
+def _check(meshes, instances, O, D, shadow_tmax=None):
+    core = RenderCore()
+    for i, m in enumerate(meshes):
+        core.SetGeometry(i, m)
+    for i, (mi, xf) in enumerate(instances):
+        core.SetInstance(i, mi, xf)
+    core.SetInstance(len(instances), -1)
+    core.FinalizeInstances()
+    got = core.TraceRays(O, D)
+    want = orc.closest_hits(meshes, instances, O, D)
+    miss_g, miss_w = got[:, 2] == 0xFFFFFFFF, want[:, 2] == 0xFFFFFFFF
+    assert np.array_equal(miss_g, miss_w), f"{(miss_g != miss_w).sum()} rays disagree on hit/miss"
+    h = ~miss_w
+    bad = np.nonzero((got[h] != want[h]).any(axis=1))[0]
+    assert bad.size == 0, f"{bad.size} of {h.sum()} hit records differ, first: got {got[h][bad[:3]]} want {want[h][bad[:3]]}"
+    if shadow_tmax is not None:
+        D2 = D.copy()
+        D2[:, 3] = shadow_tmax
+        og = core.TraceShadowRays(O, D2)
+        ow = orc.occluded(meshes, instances, O, D2)
+        assert np.array_equal(og, ow), f"{(og != ow).sum()} occlusion flags differ"
+    core.Shutdown()
+    return int(h.sum())
+
+
+def test_single_mesh_soup():
+    mesh = scenes.random_soup(20000, extent=10, size=1.5, seed=3)
+    O, D = scenes.random_rays(20000, extent=14, seed=4)
+    hits = _check([mesh], [(0, None)], O, D, shadow_tmax=9.0)
+    assert hits > 2000
+
+
+def test_terrain_primary_rays():
+    mesh = scenes.terrain(60, 40, extent=50, seed=7, floaters=500)
+    view = scenes.view_pyramid((0, 30, -80), (0, 0, 0), 40, 160, 90)
+    O, D = scenes.camera_rays(view, 160, 90)
+    hits = _check([mesh], [(0, None)], O, D, shadow_tmax=60.0)
+    assert hits > 160 * 90 // 4
+
+
+def test_instances_two_level():
+    m0 = scenes.random_soup(3000, extent=3, size=0.8, seed=11)
+    m1 = scenes.terrain(20, 20, extent=4, seed=12)
+    inst = [(0, _rot((0, 1, 0), 0.3, (5, 0, 0))), (1, _rot((1, 0, 0), -0.7, (-4, 1, 2), 1.5)),
+            (0, _rot((1, 1, 0), 1.1, (0, -3, -5), 0.5)), (1, None), (0, _rot((0, 0, 1), 2.0, (1, 6, 1)))]
+    O, D = scenes.random_rays(20000, extent=12, seed=13)
+    hits = _check([m0, m1], inst, O, D, shadow_tmax=7.5)
+    assert hits > 2000
+
+
+def test_axis_aligned_and_degenerate():
+    # floor quads (zero-thickness boxes), a sliver, a zero-area triangle, axis-parallel rays
+    q = [scenes.quad((0, 0, 0), (0, 1, 0), 20, 20), scenes.quad((0, 5, 0), (0, -1, 0), 4, 4),
+         scenes.quad((3, 2, 0), (1, 0, 0), 6, 6)]
+    deg = np.zeros((6, 4), np.float32)
+    deg[0:3, :3] = [[1, 1, 1], [1, 1, 1], [1, 1, 1]]
+    deg[3:6, :3] = [[-2, 1, -2], [2, 1.000001, 2], [0, 1.0000005, 0]]
+    mesh = np.concatenate(q + [deg])
+    rng = np.random.default_rng(5)
+    n = 4096
+    O = np.zeros((n, 4), np.float32); D = np.zeros((n, 4), np.float32)
+    O[:, :3] = (rng.random((n, 3)) * 2 - 1) * [9, 0, 9] + [0, 8, 0]
+    D[:, 1] = -1  # straight down, dx = dz = 0
+    O2, D2 = scenes.random_rays(4096, extent=9, seed=6)
+    O = np.concatenate([O, O2]); D = np.concatenate([D, D2])
+    _check([mesh], [(0, None)], O, D, shadow_tmax=6.0)
+
+
+def test_empty_and_tiny():
+    tri = np.zeros((3, 4), np.float32)
+    tri[:, :3] = [[-1, 0, -1], [1, 0, -1], [0, 0, 1]]
+    O, D = scenes.random_rays(512, extent=3, seed=8)
+    _check([tri], [(0, None)], O, D, shadow_tmax=2.0)
+    _check([tri], [(0, _rot((1, 0, 0), 0.5, (0, 1, 0)))], O, D, shadow_tmax=2.0)
