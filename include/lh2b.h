@@ -73,6 +73,9 @@ LH2B_API int lh2b_read_pixels( lh2b_core* core, float* rgbaOut );
 LH2B_API int lh2b_read_accumulator( lh2b_core* core, float* rgbaOut );
 /* Device pointer of the accumulator (float4[w*h]) for zero-copy collectives; samples taken so far. */
 LH2B_API int lh2b_accumulator_device_ptr( lh2b_core* core, void** ptrOut, int* samplesTakenOut );
+/* Finalize an externally reduced accumulator (float4[w*h] on this device, e.g. the NCCL sum over the
+   shards) into this core's pixel buffer: pixels = accum / samples. */
+LH2B_API int lh2b_finalize_external( lh2b_core* core, const void* dAccumulator, int samples );
 /* Multi-GPU sample sharding: this core renders sample indices [first, first+spp) of each pass and
    seeds as if it were part of a 'total'-spp frame. Default: first 0, total = spp. */
 LH2B_API int lh2b_set_sample_shard( lh2b_core* core, int firstSample, int totalSpp );

@@ -34,6 +34,7 @@ SIGNATURES = {
     "lh2b_read_pixels": ([_vp, _vp], _ip),
     "lh2b_read_accumulator": ([_vp, _vp], _ip),
     "lh2b_accumulator_device_ptr": ([_vp, _c.POINTER(_vp), _c.POINTER(_ip)], _ip),
+    "lh2b_finalize_external": ([_vp, _vp, _ip], _ip),
     "lh2b_set_sample_shard": ([_vp, _ip, _ip], _ip),
     "lh2b_trace_rays": ([_vp, _vp, _vp, _ip, _vp], _ip),
     "lh2b_trace_shadow_rays": ([_vp, _vp, _vp, _ip, _vp], _ip),

@@ -14,6 +14,9 @@
 namespace lh2b
 {
 
+void InitRenderState( lh2b_core* core );
+void ReleaseRenderState( lh2b_core* core );
+
 static thread_local std::string g_lastError;
 void SetLastError( const std::string& msg ) { g_lastError = msg; }
 
@@ -90,6 +93,7 @@ void UpdateAccelerationStructures( lh2b_core* core )
 	const double t0 = NowMs();
 	const int n = (int)core->instances.size();
 	std::vector<InstTrav> trav( n > 0 ? n : 1 );
+	std::vector<lh2abi::CoreInstanceDesc> desc( n > 0 ? n : 1 );
 	std::vector<Aabb> boxes( n );
 	for (int i = 0; i < n; i++)
 	{
@@ -101,6 +105,10 @@ void UpdateAccelerationStructures( lh2b_core* core )
 		trav[i].r1 = make_float4( inv[4], inv[5], inv[6], inv[7] );
 		trav[i].r2 = make_float4( inv[8], inv[9], inv[10], inv[11] );
 		trav[i].nodes = mesh.nodes.ptr, trav[i].tris = mesh.cwTris.ptr;
+		// shading-side descriptor: triangle array + inverse transform (rendercore.cpp:403-417)
+		desc[i].triangles = mesh.coreTris.ptr, desc[i].dummy1 = desc[i].dummy2 = 0;
+		desc[i].invTransform.A = { inv[0], inv[1], inv[2], inv[3] }, desc[i].invTransform.B = { inv[4], inv[5], inv[6], inv[7] };
+		desc[i].invTransform.C = { inv[8], inv[9], inv[10], inv[11] }, desc[i].invTransform.D = { 0, 0, 0, 1 };
 		TransformBounds( mesh.bounds, inst.xform, boxes[i] );
 	}
 	std::vector<Bvh2Node> bvh2;
@@ -113,6 +121,7 @@ void UpdateAccelerationStructures( lh2b_core* core )
 	core->tlasNodes.Upload( (const uint4*)cw.nodes.data(), cw.nodes.size() * 5, core->stream );
 	core->tlasLeafIds.Upload( cw.leafIds.data(), cw.leafIds.size(), core->stream );
 	core->instTrav.Upload( trav.data(), trav.size(), core->stream );
+	core->instDesc.Upload( desc.data(), desc.size(), core->stream );
 	CUDA_CHECK( cudaStreamSynchronize( core->stream ) );
 	core->scene.tlasNodes = core->tlasNodes.ptr;
 	core->scene.tlasLeafIds = core->tlasLeafIds.ptr;
@@ -164,6 +173,7 @@ int lh2b_create( lh2b_core** out, int device )
 		core->stats.deviceName = new char[strlen( prop.name ) + 1];
 		strcpy( core->stats.deviceName, prop.name );
 		core->stats.probedTriid = -1;
+		InitRenderState( core.get() );
 		*out = core.release();
 	}
 	catch (const std::exception& e) { SetLastError( e.what() ); return 1; }
@@ -175,6 +185,7 @@ int lh2b_destroy( lh2b_core* core )
 	if (!core) return 0;
 	cudaSetDevice( core->device );
 	cudaStreamSynchronize( core->stream );
+	ReleaseRenderState( core );
 	cudaEventDestroy( core->evA ), cudaEventDestroy( core->evB );
 	cudaStreamDestroy( core->stream );
 	delete[] core->stats.deviceName;

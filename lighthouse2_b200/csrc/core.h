@@ -10,6 +10,7 @@
 #include "bvh.h"
 #include "common.cuh"
 #include "traverse.cuh"
+#include "render_types.h"
 #include <memory>
 #include <vector>
 
@@ -55,4 +56,35 @@ struct lh2b_core
 	lh2b::DevBuf<uint8_t> qOcc;
 	// settings
 	int bvhBuilder = 0;				// 0: GPU LBVH (default), 1: host binned SAH
+	float geometryEpsilon = 1e-4f, clampValue = 10.0f;	// reference defaults: stageClampValue(10) at rendercore.cpp:243; epsilon comes from RenderSystem (rendersystem.h:65-72)
+	int maxPathLength = 3;			// reference MAXPATHLENGTH (core_settings.h:25)
+	uint32_t enoughBounces = S_BOUNCED;	// reference ENOUGH_BOUNCES (pathtracer.h:33)
+	// render target + wavefront buffers (rendercore.cpp:284-326)
+	int width = 0, height = 0, spp = 1;
+	size_t maxPixels = 0; int allocatedSpp = 0;
+	lh2b::DevBuf<float4> pathBuf[2][3];		// ping-pong O/D/T
+	lh2b::DevBuf<float4> hitBuf, connBuf[3], accumulator, pixels;
+	lh2b::DevBuf<lh2b::DevCounters> counters;
+	lh2b::DevCounters* hostCounters = nullptr;	// pinned
+	int samplesTaken = 0;
+	int sampleShardFirst = 0, sampleShardTotal = 0;	// 0 total = not sharded
+	bool firstConvergingFrame = true, frameInFlight = false;
+	uint32_t camRNGseed = 0x12345678u, shiftSeed = 0x11331445u;	// rendercore.h:122-123
+	int probeX = 0, probeY = 0;
+	// scene tables
+	lh2b::DevBuf<lh2abi::CoreInstanceDesc> instDesc;
+	lh2b::DevBuf<lh2b::DevMaterial> materials;
+	lh2b::DevBuf<float4> triLights, pointLights, spotLights, dirLights;
+	int lightCounts[4] = { 0, 0, 0, 0 };
+	lh2b::DevBuf<uchar4> argb32, nrm32;
+	lh2b::DevBuf<float4> argb128, skyPixels;
+	std::vector<lh2abi::CoreTexDesc> texDescs;
+	int skyW = 0, skyH = 0;
+	float worldToSky[12] = { 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0 };
+	lh2b::DevBuf<uint32_t> blueNoise;
+	// timing
+	std::vector<cudaEvent_t> events;	// per frame: see render.cu
+	lh2b_frame_stats frameStats = {};
+	double renderStartMs = 0, lastFrameEndMs = 0;
+	lh2abi::ViewPyramid lastView = {};
 };

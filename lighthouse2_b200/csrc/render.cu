@@ -1,21 +1,450 @@
-/* render.cu - placeholder entry points; replaced by the wavefront loop. */
+/* render.cu - the render-target, scene-table and frame entry points of the C ABI, and the wavefront
+   loop: generate+extend, shade, connect per path length, finalize. No host read-back happens between
+   bounces (the reference blocks on a 48-byte counter copy per bounce, rendercore.cpp:903): every stage
+   takes its ray count from device counters, so a frame is one fixed sequence of launches on one stream.
+
+   Reference behaviour restated here: lib/rendercore_optix7/rendercore.cpp
+     SetTarget :284-326 | SetTextures/SyncStorageType :438-502 | SetMaterials :508-565 | SetLights :698-710
+     SetSkyData :716-740 | Setting :746-760 | Render/RenderImpl :819-938 | WaitForRender :945-957
+     FinalizeRender :963-979 | GetCoreStats :1000-1003 | Init (blue noise expansion) :247-256
+*/
 #include "core.h"
-using namespace lh2b;
-#define NOTYET( name ) { (void)core; SetLastError( name ": not implemented yet" ); return 1; }
-extern "C" {
-int lh2b_set_target( lh2b_core* core, int, int, int ) NOTYET( "SetTarget" )
-int lh2b_setting( lh2b_core* core, const char*, float ) NOTYET( "Setting" )
-int lh2b_set_probe_pos( lh2b_core* core, int, int ) NOTYET( "SetProbePos" )
-int lh2b_set_textures( lh2b_core* core, const void*, int ) NOTYET( "SetTextures" )
-int lh2b_set_materials( lh2b_core* core, const void*, int ) NOTYET( "SetMaterials" )
-int lh2b_set_lights( lh2b_core* core, const void*, int, const void*, int, const void*, int, const void*, int ) NOTYET( "SetLights" )
-int lh2b_set_sky( lh2b_core* core, const float*, int, int, const float* ) NOTYET( "SetSkyData" )
-int lh2b_render( lh2b_core* core, const void*, int, int ) NOTYET( "Render" )
-int lh2b_wait_for_render( lh2b_core* core ) NOTYET( "WaitForRender" )
-int lh2b_get_stats( lh2b_core* core, void* ) NOTYET( "GetCoreStats" )
-int lh2b_read_pixels( lh2b_core* core, float* ) NOTYET( "ReadPixels" )
-int lh2b_read_accumulator( lh2b_core* core, float* ) NOTYET( "ReadAccumulator" )
-int lh2b_accumulator_device_ptr( lh2b_core* core, void**, int* ) NOTYET( "AccumulatorDevicePtr" )
-int lh2b_set_sample_shard( lh2b_core* core, int, int ) NOTYET( "SetSampleShard" )
-int lh2b_get_frame_stats( lh2b_core* core, lh2b_frame_stats* ) NOTYET( "GetFrameStats" )
+#include "kernels.h"
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <cuda_fp16.h>
+
+extern "C" const unsigned char lh2b_bluenoise_bytes[];
+
+namespace lh2b
+{
+
+static double NowMs()
+{
+	return std::chrono::duration<double, std::milli>( std::chrono::steady_clock::now().time_since_epoch() ).count();
 }
+
+static uint32_t RandomUInt( uint32_t& seed ) { seed ^= seed << 13, seed ^= seed >> 17, seed ^= seed << 5; return seed; }	// lib/platform/system.cpp:51
+
+void InitRenderState( lh2b_core* core )
+{
+	// blue noise: three byte tables expanded to one uint per entry at offsets 0 / 65536 / 3*65536 (rendercore.cpp:247-254)
+	std::vector<uint32_t> bn( 65536 * 5, 0 );
+	const unsigned char* b = lh2b_bluenoise_bytes;
+	for (int i = 0; i < 65536; i++) bn[i] = b[i];
+	for (int i = 0; i < 128 * 128 * 8; i++) bn[i + 65536] = b[65536 + i];
+	for (int i = 0; i < 128 * 128 * 8; i++) bn[i + 3 * 65536] = b[65536 + 131072 + i];
+	core->blueNoise.Upload( bn.data(), bn.size(), core->stream );
+	core->counters.Resize( 1 );
+	CUDA_CHECK( cudaMemsetAsync( core->counters.ptr, 0, sizeof( DevCounters ), core->stream ) );
+	CUDA_CHECK( cudaMallocHost( &core->hostCounters, sizeof( DevCounters ) ) );
+	memset( core->hostCounters, 0, sizeof( DevCounters ) );
+	// events: 0 frame start, then per path length L (1-based): 4 * L + {0: trace start, 1: trace end/shade start, 2: shade end/connect start, 3: connect end}
+	core->events.resize( 4 * (LH2B_MAXPATHLENGTH + 1) + 4 );
+	for (auto& e : core->events) CUDA_CHECK( cudaEventCreate( &e ) );
+	// one-texel placeholders so table pointers are never null
+	const uchar4 z4 = make_uchar4( 0, 0, 0, 0 );
+	const float4 zf = make_float4( 0, 0, 0, 0 );
+	core->argb32.Upload( &z4, 1, core->stream ), core->nrm32.Upload( &z4, 1, core->stream );
+	core->argb128.Upload( &zf, 1, core->stream ), core->skyPixels.Upload( &zf, 1, core->stream );
+	core->triLights.Upload( &zf, 1, core->stream ), core->pointLights.Upload( &zf, 1, core->stream );
+	core->spotLights.Upload( &zf, 1, core->stream ), core->dirLights.Upload( &zf, 1, core->stream );
+	CUDA_CHECK( cudaStreamSynchronize( core->stream ) );
+}
+
+void ReleaseRenderState( lh2b_core* core )
+{
+	for (auto& e : core->events) cudaEventDestroy( e );
+	core->events.clear();
+	if (core->hostCounters) cudaFreeHost( core->hostCounters ), core->hostCounters = nullptr;
+}
+
+static void FinishFrame( lh2b_core* core )
+{
+	if (!core->frameInFlight) return;
+	CUDA_CHECK( cudaStreamSynchronize( core->stream ) );
+	core->frameInFlight = false;
+	const DevCounters& c = *core->hostCounters;
+	const int maxLen = core->maxPathLength;
+	lh2abi::CoreStats& st = core->stats;
+	lh2b_frame_stats& fs = core->frameStats;
+	const uint32_t stride = (uint32_t)core->width * core->height * core->spp;
+	st.primaryRayCount = stride;
+	st.bounce1RayCount = maxLen >= 2 ? c.extensionRays[1] : 0;
+	st.deepRayCount = 0;
+	for (int L = 2; L < maxLen; L++) st.deepRayCount += c.extensionRays[L];
+	st.totalExtensionRays = st.primaryRayCount + st.bounce1RayCount + st.deepRayCount;
+	st.totalShadowRays = 0;
+	for (int L = 1; L <= maxLen; L++) st.totalShadowRays += c.shadowRays[L];
+	st.totalRays = st.totalExtensionRays + st.totalShadowRays;
+	auto elapsed = [&]( int a, int b ) { float ms = 0; cudaEventElapsedTime( &ms, core->events[a], core->events[b] ); return ms; };
+	st.traceTime0 = elapsed( 4, 5 );
+	st.traceTime1 = maxLen >= 2 ? elapsed( 8, 9 ) : 0;
+	st.traceTimeX = 0, st.shadeTime = 0, st.shadowTraceTime = 0;
+	for (int L = 3; L <= maxLen; L++) st.traceTimeX += elapsed( 4 * L, 4 * L + 1 );
+	for (int L = 1; L <= maxLen; L++) st.shadeTime += elapsed( 4 * L + 1, 4 * L + 2 ), st.shadowTraceTime += elapsed( 4 * L + 2, 4 * L + 3 );
+	st.probedInstid = c.probedInstid, st.probedTriid = c.probedTriid, st.probedDist = c.probedDist;
+	// probe world position (rendercore.cpp:935-937)
+	{
+		const lh2abi::ViewPyramid& v = core->lastView;
+		const float rx = v.p2.x - v.p1.x, ry = v.p2.y - v.p1.y, rz = v.p2.z - v.p1.z;
+		const float ux = v.p3.x - v.p1.x, uy = v.p3.y - v.p1.y, uz = v.p3.z - v.p1.z;
+		const float fu = (core->probeX + 0.5f) / core->width, fv = (core->probeY + 0.5f) / core->height;
+		float dx = v.p1.x + fu * rx + fv * ux - v.pos.x, dy = v.p1.y + fu * ry + fv * uy - v.pos.y, dz = v.p1.z + fu * rz + fv * uz - v.pos.z;
+		const float il = 1.0f / sqrtf( dx * dx + dy * dy + dz * dz );
+		st.probedWorldPos.x = v.pos.x + c.probedDist * dx * il, st.probedWorldPos.y = v.pos.y + c.probedDist * dy * il, st.probedWorldPos.z = v.pos.z + c.probedDist * dz * il;
+	}
+	// FinalizeRender (rendercore.cpp:963-979)
+	const int total = core->sampleShardTotal > 0 ? core->sampleShardTotal : core->spp;
+	core->samplesTaken += total;
+	const int localSamples = (int)((long long)core->samplesTaken * core->spp / total);
+	const int finEv = (int)core->events.size() - 2;
+	CUDA_CHECK( cudaEventRecord( core->events[finEv], core->stream ) );
+	LaunchFinalize( core->accumulator.ptr, core->pixels.ptr, core->width * core->height, localSamples, core->stream );
+	CUDA_CHECK( cudaEventRecord( core->events[finEv + 1], core->stream ) );
+	CUDA_CHECK( cudaStreamSynchronize( core->stream ) );
+	const double now = NowMs();
+	st.renderTime = (float)((now - core->renderStartMs) * 0.001);	// the reference Timer reports seconds
+	st.frameOverhead = core->lastFrameEndMs > 0 ? fmaxf( 0.0f, (float)((core->renderStartMs - core->lastFrameEndMs) * 0.001) ) : 0;
+	core->lastFrameEndMs = now;
+	fs.generateExtendMs = st.traceTime0, fs.extendMs = st.traceTime1 + st.traceTimeX, fs.shadeMs = st.shadeTime, fs.connectMs = st.shadowTraceTime;
+	fs.finalizeMs = elapsed( finEv, finEv + 1 );
+	fs.totalMs = elapsed( 0, finEv + 1 );
+	fs.primaryRays = st.primaryRayCount, fs.extensionRays = st.totalExtensionRays, fs.shadowRays = st.totalShadowRays;
+	fs.kernelLaunches = 3 * maxLen + 1;
+	fs.pathLengthReached = 1;
+	for (int L = 1; L < maxLen; L++) if (c.extensionRays[L] > 0) fs.pathLengthReached = L + 1;
+	// traversal statistics are per second in the reference apps (times in seconds there); we keep milliseconds in frame stats
+	st.traceTime0 *= 0.001f, st.traceTime1 *= 0.001f, st.traceTimeX *= 0.001f, st.shadeTime *= 0.001f, st.shadowTraceTime *= 0.001f;
+}
+
+static void RenderFrame( lh2b_core* core, const lh2abi::ViewPyramid& view )
+{
+	cudaStream_t s = core->stream;
+	const uint32_t stride = (uint32_t)core->width * core->height * core->spp;
+	core->lastView = view;
+	CUDA_CHECK( cudaEventRecord( core->events[0], s ) );
+	if (core->samplesTaken == 0) CUDA_CHECK( cudaMemsetAsync( core->accumulator.ptr, 0, (size_t)core->width * core->height * sizeof( float4 ), s ) );
+	CUDA_CHECK( cudaMemsetAsync( core->counters.ptr, 0, sizeof( DevCounters ), s ) );
+	RandomUInt( core->shiftSeed );
+	RenderParams p = {};
+	p.posLensSize = make_float4( view.pos.x, view.pos.y, view.pos.z, view.aperture );
+	p.right = make_float3( view.p2.x - view.p1.x, view.p2.y - view.p1.y, view.p2.z - view.p1.z );
+	p.up = make_float3( view.p3.x - view.p1.x, view.p3.y - view.p1.y, view.p3.z - view.p1.z );
+	p.p1 = make_float3( view.p1.x, view.p1.y, view.p1.z );
+	p.distortion = view.distortion, p.spreadAngle = view.spreadAngle;
+	p.w = core->width, p.h = core->height, p.spp = core->spp;
+	p.pass = core->samplesTaken, p.shift = core->shiftSeed;
+	p.sampleBase = core->sampleShardTotal > 0 ? core->sampleShardFirst : 0;
+	p.stride = stride;
+	p.geometryEpsilon = core->geometryEpsilon, p.clampValue = core->clampValue;
+	p.probePixelIdx = core->probeX + core->width * core->probeY;
+	p.maxPathLength = core->maxPathLength, p.enoughBounces = core->enoughBounces;
+	p.instDesc = core->instDesc.ptr, p.materials = core->materials.ptr;
+	p.triLights = core->triLights.ptr, p.pointLights = core->pointLights.ptr, p.spotLights = core->spotLights.ptr, p.dirLights = core->dirLights.ptr;
+	p.lightCounts = make_int4( core->lightCounts[0], core->lightCounts[1], core->lightCounts[2], core->lightCounts[3] );
+	p.argb32 = core->argb32.ptr, p.argb128 = core->argb128.ptr, p.nrm32 = core->nrm32.ptr;
+	p.skyPixels = core->skyPixels.ptr, p.skyW = core->skyW, p.skyH = core->skyH;
+	memcpy( p.worldToSky, core->worldToSky, sizeof( p.worldToSky ) );
+	p.blueNoise = core->blueNoise.ptr, p.accumulator = core->accumulator.ptr, p.counters = core->counters.ptr;
+	const bool useNEE = (core->lightCounts[0] + core->lightCounts[1] + core->lightCounts[2] + core->lightCounts[3]) > 0;
+	const PathSet conn = { core->connBuf[0].ptr, core->connBuf[1].ptr, core->connBuf[2].ptr };
+	const int sm = (int)core->stats.SMcount;
+	for (int L = 1; L <= core->maxPathLength; L++)
+	{
+		const PathSet in = { core->pathBuf[(L - 1) & 1][0].ptr, core->pathBuf[(L - 1) & 1][1].ptr, core->pathBuf[(L - 1) & 1][2].ptr };
+		const PathSet out = { core->pathBuf[L & 1][0].ptr, core->pathBuf[L & 1][1].ptr, core->pathBuf[L & 1][2].ptr };
+		CUDA_CHECK( cudaEventRecord( core->events[4 * L], s ) );
+		if (L == 1) LaunchGenerateExtend( core->scene, p, in, core->hitBuf.ptr, sm, s );
+		else LaunchExtendCounted( core->scene, in, core->hitBuf.ptr, &core->counters.ptr->extensionRays[L - 1], stride, sm, s );
+		CUDA_CHECK( cudaEventRecord( core->events[4 * L + 1], s ) );
+		const uint32_t R0 = RandomUInt( core->camRNGseed ) + L * 91771;
+		LaunchShade( p, in, out, core->hitBuf.ptr, conn, L, R0, useNEE, stride, sm, s );
+		CUDA_CHECK( cudaEventRecord( core->events[4 * L + 2], s ) );
+		if (useNEE) LaunchConnect( core->scene, conn, core->accumulator.ptr, &core->counters.ptr->shadowRays[L], stride, sm, s );
+		CUDA_CHECK( cudaEventRecord( core->events[4 * L + 3], s ) );
+	}
+	CUDA_CHECK( cudaGetLastError() );
+	CUDA_CHECK( cudaMemcpyAsync( core->hostCounters, core->counters.ptr, sizeof( DevCounters ), cudaMemcpyDeviceToHost, s ) );
+	core->frameInFlight = true;
+}
+
+} // namespace lh2b
+
+using namespace lh2b;
+
+#define API_BEGIN if (!core) { SetLastError( "null core handle" ); return 1; } try { CUDA_CHECK( cudaSetDevice( core->device ) );
+#define API_END } catch (const std::exception& e) { SetLastError( e.what() ); return 1; } return 0;
+
+static uint32_t ToChar( float a ) { return (uint32_t)(a * 255.0f); }	// truncation, as TOCHAR (rendercore.cpp:510)
+static uint32_t Pack4( float a, float b, float c, float d ) { return ToChar( a ) + (ToChar( b ) << 8) + (ToChar( c ) << 16) + (ToChar( d ) << 24); }
+static uint32_t HalfBits( float f ) { const __half h = __float2half_rn( f ); unsigned short u; memcpy( &u, &h, 2 ); return u; }
+
+template <typename V> static uint4 MakeMap( const lh2b_core* core, const V& v )
+{
+	// CUDAMaterial::Map { short width, height; half uscale, vscale, uoffs, voffs; uint addr } (core_settings.h:141, rendercore.h:78-85)
+	if (v.textureID < 0 || v.textureID >= (int)core->texDescs.size()) throw CoreError( "SetMaterials: texture id out of range (call SetTextures first)" );
+	const lh2abi::CoreTexDesc& t = core->texDescs[v.textureID];
+	uint4 m;
+	m.x = (t.width & 0xffff) | ((t.height & 0xffff) << 16);
+	m.y = HalfBits( v.uvscale.x ) | (HalfBits( v.uvscale.y ) << 16);
+	m.z = HalfBits( v.uvoffset.x ) | (HalfBits( v.uvoffset.y ) << 16);
+	m.w = t.firstPixel;
+	return m;
+}
+
+extern "C" {
+
+int lh2b_set_target( lh2b_core* core, int width, int height, int spp )
+{
+	API_BEGIN
+	if (width <= 0 || height <= 0 || spp <= 0) throw CoreError( "SetTarget: width, height and spp must be positive" );
+	if ((unsigned long long)width * height * spp >= (1ull << 26)) throw CoreError( "SetTarget: w*h*spp must stay below 2^26 (path index is packed above 6 flag bits)" );
+	FinishFrame( core );
+	core->width = width, core->height = height, core->spp = spp;
+	const size_t pixels = (size_t)width * height;
+	if (pixels > core->maxPixels || spp != core->allocatedSpp)
+	{
+		core->maxPixels = pixels + (pixels >> 4);	// slack against frequent reallocation (rendercore.cpp:298-299)
+		core->allocatedSpp = spp;
+		const size_t rays = core->maxPixels * spp;
+		for (int b = 0; b < 2; b++) for (int k = 0; k < 3; k++) core->pathBuf[b][k].Free(), core->pathBuf[b][k].Resize( rays );
+		for (int k = 0; k < 3; k++) core->connBuf[k].Free(), core->connBuf[k].Resize( rays );
+		core->hitBuf.Free(), core->hitBuf.Resize( rays );
+		core->accumulator.Free(), core->accumulator.Resize( core->maxPixels );
+		core->pixels.Free(), core->pixels.Resize( core->maxPixels );
+	}
+	CUDA_CHECK( cudaMemsetAsync( core->accumulator.ptr, 0, pixels * sizeof( float4 ), core->stream ) );
+	CUDA_CHECK( cudaMemsetAsync( core->pixels.ptr, 0, pixels * sizeof( float4 ), core->stream ) );
+	core->samplesTaken = 0;
+	API_END
+}
+
+int lh2b_setting( lh2b_core* core, const char* name, float value )
+{
+	API_BEGIN
+	if (!name) throw CoreError( "Setting: null name" );
+	if (!strcmp( name, "epsilon" )) core->geometryEpsilon = value;
+	else if (!strcmp( name, "clampValue" )) core->clampValue = value;
+	else if (!strcmp( name, "noiseShift" )) { /* accepted and unused, as in the reference (rendercore.cpp:756-759) */ }
+	// extensions of this core (the reference fixes these at compile time: core_settings.h:25, pathtracer.h:33)
+	else if (!strcmp( name, "maxPathLength" )) core->maxPathLength = value < 1 ? 1 : (value > LH2B_MAXPATHLENGTH ? LH2B_MAXPATHLENGTH : (int)value);
+	else if (!strcmp( name, "maxDiffuseBounces" )) core->enoughBounces = value <= 0 ? 0 : (value < 2 ? S_BOUNCED : S_BOUNCEDTWICE);
+	else if (!strcmp( name, "bvhBuilder" )) core->bvhBuilder = (int)value;
+	// unknown names are ignored
+	API_END
+}
+
+int lh2b_set_probe_pos( lh2b_core* core, int x, int y )
+{
+	API_BEGIN
+	core->probeX = x, core->probeY = y;
+	API_END
+}
+
+int lh2b_set_textures( lh2b_core* core, const void* tex, int count )
+{
+	API_BEGIN
+	FinishFrame( core );
+	core->texDescs.assign( (const lh2abi::CoreTexDesc*)tex, (const lh2abi::CoreTexDesc*)tex + (count > 0 ? count : 0) );
+	for (int storage = 0; storage < 3; storage++)
+	{
+		size_t total = 0;
+		for (auto& t : core->texDescs) if ((int)t.storage == storage) total += t.pixelCount;
+		const size_t alloc = total > 16 ? total : 16;
+		if (storage == lh2abi::ARGB128)
+		{
+			std::vector<float4> host( alloc, make_float4( 0, 0, 0, 0 ) );
+			size_t at = 0;
+			for (auto& t : core->texDescs) if ((int)t.storage == storage)
+				memcpy( host.data() + at, t.fdata, (size_t)t.pixelCount * sizeof( float4 ) ), t.firstPixel = (uint32_t)at, at += t.pixelCount;
+			core->argb128.Upload( host.data(), alloc, core->stream );
+			core->stats.argb128TexelCount = (uint32_t)alloc;
+		}
+		else
+		{
+			std::vector<uchar4> host( alloc, make_uchar4( 0, 0, 0, 0 ) );
+			size_t at = 0;
+			for (auto& t : core->texDescs) if ((int)t.storage == storage)
+				memcpy( host.data() + at, t.idata, (size_t)t.pixelCount * sizeof( uchar4 ) ), t.firstPixel = (uint32_t)at, at += t.pixelCount;
+			(storage == lh2abi::ARGB32 ? core->argb32 : core->nrm32).Upload( host.data(), alloc, core->stream );
+			(storage == lh2abi::ARGB32 ? core->stats.argb32TexelCount : core->stats.nrm32TexelCount) = (uint32_t)alloc;
+		}
+		CUDA_CHECK( cudaStreamSynchronize( core->stream ) );
+	}
+	API_END
+}
+
+int lh2b_set_materials( lh2b_core* core, const void* matPtr, int count )
+{
+	API_BEGIN
+	FinishFrame( core );
+	const lh2abi::CoreMaterial* mat = (const lh2abi::CoreMaterial*)matPtr;
+	std::vector<DevMaterial> host( count > 0 ? count : 1 );
+	memset( host.data(), 0, host.size() * sizeof( DevMaterial ) );
+	for (int i = 0; i < count; i++)
+	{
+		const lh2abi::CoreMaterial& m = mat[i];
+		DevMaterial& g = host[i];
+		const float tr = 1 - m.absorption.value.x, tg = 1 - m.absorption.value.y, tb = 1 - m.absorption.value.z;
+		uint32_t flags = (m.eta.value < 1 ? 1u : 0) + (m.color.textureID != -1 ? (1u << 2) : 0) + (m.normals.textureID != -1 ? (1u << 3) : 0) +
+			(m.specular.textureID != -1 ? (1u << 4) : 0) + (m.roughness.textureID != -1 ? (1u << 5) : 0) +
+			(m.detailNormals.textureID != -1 ? (1u << 7) : 0) + (m.detailColor.textureID != -1 ? (1u << 9) : 0) +
+			((m.flags & 1) ? (1u << 11) : 0) + ((m.flags & 2) ? (1u << 12) : 0);
+		if (m.color.textureID != -1 && m.color.textureID < (int)core->texDescs.size() && (core->texDescs[m.color.textureID].flags & 8)) flags += 1u << 1;
+		g.q[0].x = HalfBits( m.color.value.x ) | (HalfBits( m.color.value.y ) << 16);
+		g.q[0].y = HalfBits( m.color.value.z ) | (HalfBits( tr ) << 16);
+		g.q[0].z = HalfBits( tg ) | (HalfBits( tb ) << 16);
+		g.q[0].w = flags;
+		g.q[1].x = Pack4( m.metallic.value, m.subsurface.value, m.specular.value, m.roughness.value );
+		g.q[1].y = Pack4( m.specularTint.value, m.anisotropic.value, m.sheen.value, m.sheenTint.value );
+		g.q[1].z = Pack4( m.clearcoat.value, m.clearcoatGloss.value, m.transmission.value, 0 );
+		memcpy( &g.q[1].w, &m.eta.value, 4 );
+		if (m.color.textureID != -1) g.q[2] = MakeMap( core, m.color );
+		if (m.detailColor.textureID != -1) g.q[3] = MakeMap( core, m.detailColor );
+		if (m.normals.textureID != -1) g.q[4] = MakeMap( core, m.normals );
+		if (m.detailNormals.textureID != -1) g.q[5] = MakeMap( core, m.detailNormals );
+		if (m.specular.textureID != -1) g.q[6] = MakeMap( core, m.specular );
+		if (m.roughness.textureID != -1) g.q[7] = MakeMap( core, m.roughness );
+	}
+	core->materials.Upload( host.data(), host.size(), core->stream );
+	CUDA_CHECK( cudaStreamSynchronize( core->stream ) );
+	API_END
+}
+
+static void UploadLights( lh2b_core* core, DevBuf<float4>& buf, const void* src, int count, int float4sPer )
+{
+	if (count > 0) buf.Upload( (const float4*)src, (size_t)count * float4sPer, core->stream );
+}
+
+int lh2b_set_lights( lh2b_core* core, const void* tri, int nTri, const void* point, int nPoint, const void* spot, int nSpot, const void* dir, int nDir )
+{
+	API_BEGIN
+	FinishFrame( core );
+	if (nTri + nPoint + nSpot + nDir > 64) throw CoreError( "SetLights: at most 64 lights are importance sampled (MAXISLIGHTS, lights_shared.h:26)" );
+	UploadLights( core, core->triLights, tri, nTri, 6 ), UploadLights( core, core->pointLights, point, nPoint, 2 );
+	UploadLights( core, core->spotLights, spot, nSpot, 3 ), UploadLights( core, core->dirLights, dir, nDir, 2 );
+	core->lightCounts[0] = nTri, core->lightCounts[1] = nPoint, core->lightCounts[2] = nSpot, core->lightCounts[3] = nDir;
+	CUDA_CHECK( cudaStreamSynchronize( core->stream ) );
+	API_END
+}
+
+int lh2b_set_sky( lh2b_core* core, const float* pixels, int width, int height, const float* worldToLight )
+{
+	API_BEGIN
+	FinishFrame( core );
+	const int w = width >> 6, h = height >> 6;
+	std::vector<float4> host( (size_t)width * height + (size_t)w * h + 1 );
+	for (size_t i = 0; i < (size_t)width * height; i++) host[i] = make_float4( pixels[i * 3], pixels[i * 3 + 1], pixels[i * 3 + 2], 0 );
+	float4* scaled = host.data() + (size_t)width * height;
+	for (int y = 0; y < h; y++) for (int x = 0; x < w; x++)
+	{
+		// 64x64 box filter (rendercore.cpp:727-737)
+		float4 total = make_float4( 0, 0, 0, 0 );
+		const float4* tile = host.data() + x * 64 + (size_t)y * 64 * width;
+		for (int v = 0; v < 64; v++) for (int u = 0; u < 64; u++)
+		{
+			const float4 t = tile[u + (size_t)v * width];
+			total.x += t.x, total.y += t.y, total.z += t.z, total.w += t.w;
+		}
+		const float r = 1.0f / (64 * 64);
+		scaled[x + y * w] = make_float4( total.x * r, total.y * r, total.z * r, total.w * r );
+	}
+	core->skyPixels.Upload( host.data(), host.size(), core->stream );
+	core->skyW = width, core->skyH = height;
+	if (worldToLight) memcpy( core->worldToSky, worldToLight, 12 * sizeof( float ) );
+	CUDA_CHECK( cudaStreamSynchronize( core->stream ) );
+	API_END
+}
+
+int lh2b_render( lh2b_core* core, const void* viewPtr, int converge, int async )
+{
+	API_BEGIN
+	if (!core->sceneReady) return 0;	// silent no-op before the first FinalizeInstances (rendercore.cpp:821)
+	if (core->width == 0) throw CoreError( "Render: SetTarget has not been called" );
+	if (core->materials.count == 0) throw CoreError( "Render: SetMaterials has not been called" );
+	FinishFrame( core );
+	if (converge == 1 || core->firstConvergingFrame)
+	{
+		core->samplesTaken = 0;
+		core->firstConvergingFrame = true;
+		core->camRNGseed = 0x12345678u;
+	}
+	if (converge == 0) core->firstConvergingFrame = false;
+	core->renderStartMs = NowMs();
+	RenderFrame( core, *(const lh2abi::ViewPyramid*)viewPtr );
+	if (!async) FinishFrame( core );
+	API_END
+}
+
+int lh2b_wait_for_render( lh2b_core* core )
+{
+	API_BEGIN
+	FinishFrame( core );
+	API_END
+}
+
+int lh2b_get_stats( lh2b_core* core, void* out )
+{
+	API_BEGIN
+	core->stats.bvhBuildTime = 0;
+	for (auto& m : core->meshes) core->stats.bvhBuildTime += m->buildMs * 0.001f;
+	memcpy( out, &core->stats, sizeof( lh2abi::CoreStats ) );
+	API_END
+}
+
+int lh2b_get_frame_stats( lh2b_core* core, lh2b_frame_stats* out )
+{
+	API_BEGIN
+	core->frameStats.buildMs = core->tlasBuildMs;
+	*out = core->frameStats;
+	API_END
+}
+
+int lh2b_read_pixels( lh2b_core* core, float* rgbaOut )
+{
+	API_BEGIN
+	FinishFrame( core );
+	CUDA_CHECK( cudaMemcpyAsync( rgbaOut, core->pixels.ptr, (size_t)core->width * core->height * sizeof( float4 ), cudaMemcpyDeviceToHost, core->stream ) );
+	CUDA_CHECK( cudaStreamSynchronize( core->stream ) );
+	API_END
+}
+
+int lh2b_read_accumulator( lh2b_core* core, float* rgbaOut )
+{
+	API_BEGIN
+	FinishFrame( core );
+	CUDA_CHECK( cudaMemcpyAsync( rgbaOut, core->accumulator.ptr, (size_t)core->width * core->height * sizeof( float4 ), cudaMemcpyDeviceToHost, core->stream ) );
+	CUDA_CHECK( cudaStreamSynchronize( core->stream ) );
+	API_END
+}
+
+int lh2b_accumulator_device_ptr( lh2b_core* core, void** ptrOut, int* samplesTakenOut )
+{
+	API_BEGIN
+	FinishFrame( core );
+	if (ptrOut) *ptrOut = core->accumulator.ptr;
+	if (samplesTakenOut) *samplesTakenOut = core->samplesTaken;
+	API_END
+}
+
+int lh2b_finalize_external( lh2b_core* core, const void* dAccumulator, int samples )
+{
+	API_BEGIN
+	FinishFrame( core );
+	if (samples <= 0) throw CoreError( "finalize_external: samples must be positive" );
+	LaunchFinalize( (const float4*)dAccumulator, core->pixels.ptr, core->width * core->height, samples, core->stream );
+	CUDA_CHECK( cudaStreamSynchronize( core->stream ) );
+	API_END
+}
+
+int lh2b_set_sample_shard( lh2b_core* core, int firstSample, int totalSpp )
+{
+	API_BEGIN
+	if (firstSample < 0 || totalSpp < 0) throw CoreError( "set_sample_shard: negative argument" );
+	core->sampleShardFirst = firstSample, core->sampleShardTotal = totalSpp;
+	API_END
+}
+
+} // extern "C"

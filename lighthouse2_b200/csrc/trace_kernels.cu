@@ -5,6 +5,7 @@
    Both read O4/D4 as float4 (32 B per ray) and write 16 B (hit) or 1 B (flag).
 */
 #include "kernels.h"
+#include "render_types.h"
 #include "traverse.cuh"
 
 namespace lh2b
@@ -36,6 +37,123 @@ __global__ void __launch_bounds__( 128 ) occludeKernel( const DevScene scene, co
 	const float4 o = O4[i], d = D4[i];
 	TraceResult r;
 	occluded[i] = Traverse<true>( scene, make_float3( o.x, o.y, o.z ), make_float3( d.x, d.y, d.z ), 0.0f, d.w, r ) ? 1 : 0;
+}
+
+/* ---- wavefront stages ------------------------------------------------------------------- */
+
+__device__ __forceinline__ uint32_t WangHashT( uint32_t s ) { s = (s ^ 61) ^ (s >> 16), s *= 9, s = s ^ (s >> 4), s *= 0x27d4eb2d, s = s ^ (s >> 15); return s; }
+__device__ __forceinline__ float RandomFloatT( uint32_t& s ) { s ^= s << 13, s ^= s >> 17, s ^= s << 5; return s * 2.3283064365387e-10f; }
+
+/* generate + extend for path length 1: setupPrimaryRay (.optix.cu:112-129) with generateEyeRay (:85-104),
+   RandomPointOnLens (:71-83), blueNoiseSampler4 (:56-69) and RayTarget (lib/RenderSystem/common_functions.h:29-50).
+   One thread per path, grid-stride over the w*h*spp paths of this core. */
+__global__ void __launch_bounds__( 128 ) generateExtendKernel( const DevScene scene, const RenderParams p, const PathSet out, float4* __restrict__ hits )
+{
+	const uint32_t pixels = p.w * p.h;
+	for (uint32_t pathIdx = blockIdx.x * blockDim.x + threadIdx.x; pathIdx < p.stride; pathIdx += gridDim.x * blockDim.x)
+	{
+		const uint32_t pixelIdx = pathIdx % pixels;
+		const uint32_t seedIdx = pathIdx + p.sampleBase * pixels;
+		const uint32_t sampleIdx = seedIdx / pixels + p.pass;
+		uint32_t seed = WangHashT( seedIdx * 16789 + p.pass * 1791 );
+		const int sx = pixelIdx % p.w, sy = pixelIdx / p.w;
+		float4 r4;
+		if (sampleIdx < 64)
+		{
+			const int x = (sx + (p.shift & 127)) & 127, y = (sy + (p.shift >> 24)) & 127;
+			const uint32_t* bn = p.blueNoise;
+			const uint4 rank = *(const uint4*)(bn + (x + y * 128) * 8 + 65536 * 3);
+			const uint32_t v0 = bn[0 + ((sampleIdx ^ rank.x) & 255) * 256], v1 = bn[1 + ((sampleIdx ^ rank.y) & 255) * 256];
+			const uint32_t v2 = bn[2 + ((sampleIdx ^ rank.z) & 255) * 256], v3 = bn[3 + ((sampleIdx ^ rank.w) & 255) * 256];
+			const uint4 scr = *(const uint4*)(bn + (x + y * 128) * 8 + 65536);
+			r4 = make_float4( (0.5f + (int)(v0 ^ scr.x)) * (1.0f / 256.0f), (0.5f + (int)(v1 ^ scr.y)) * (1.0f / 256.0f),
+				(0.5f + (int)(v2 ^ scr.z)) * (1.0f / 256.0f), (0.5f + (int)(v3 ^ scr.w)) * (1.0f / 256.0f) );
+		}
+		else r4.x = RandomFloatT( seed ), r4.y = RandomFloatT( seed ), r4.z = RandomFloatT( seed ), r4.w = RandomFloatT( seed );
+		// lens: 9-blade aperture
+		const float blade = (float)(int)(r4.x * 9);
+		float r1 = r4.z, r2 = (r4.x - blade * (1.0f / 9.0f)) * 9.0f;
+		float x1, y1, x2, y2;
+		const float PI_T = 3.14159265358979323846264f;
+		__sincosf( blade * PI_T / 4.5f, &x1, &y1 );
+		__sincosf( (blade + 1.0f) * PI_T / 4.5f, &x2, &y2 );
+		if ((r1 + r2) > 1) r1 = 1.0f - r1, r2 = 1.0f - r2;
+		const float xr = x1 * r1 + x2 * r2, yr = y1 * r1 + y2 * r2;
+		const float ap = p.posLensSize.w;
+		const float3 O = make_float3( p.posLensSize.x + ap * (p.right.x * xr + p.up.x * yr), p.posLensSize.y + ap * (p.right.y * xr + p.up.y * yr),
+			p.posLensSize.z + ap * (p.right.z * xr + p.up.z * yr) );
+		// point on the pixel
+		float fu, fv;
+		if (p.distortion == 0) fu = ((float)sx + r4.y) * (1.0f / p.w), fv = ((float)sy + r4.w) * (1.0f / p.h);
+		else
+		{
+			const float tx = sx / (float)p.w - 0.5f, ty = sy / (float)p.h - 0.5f;
+			const float rr = tx * tx + ty * ty;
+			const float rq = sqrtf( rr ) * (1.0f + p.distortion * rr + p.distortion * rr * rr);
+			const float theta = atan2f( tx, ty );
+			const float bx = (sinf( theta ) * rq + 0.5f) * p.w, by = (cosf( theta ) * rq + 0.5f) * p.h;
+			fu = (bx + r4.y) / (float)p.w, fv = (by + r4.w) / (float)p.h;
+		}
+		float3 D = make_float3( p.p1.x + fu * p.right.x + fv * p.up.x - O.x, p.p1.y + fu * p.right.y + fv * p.up.y - O.y, p.p1.z + fu * p.right.z + fv * p.up.z - O.z );
+		const float il = rsqrtf( D.x * D.x + D.y * D.y + D.z * D.z );
+		D.x *= il, D.y *= il, D.z *= il;
+		out.O[pathIdx] = make_float4( O.x, O.y, O.z, __uint_as_float( (pathIdx << 6) + 1 /* S_SPECULAR */ ) );
+		out.D[pathIdx] = make_float4( D.x, D.y, D.z, 0 );
+		TraceResult r;
+		const bool hit = Traverse<false>( scene, O, D, 0.0f, 1e34f, r );
+		hits[pathIdx] = PackHit( hit, r );
+	}
+}
+
+/* extend for path length > 1 (setupSecondaryRay, .optix.cu:131-140): ray count comes from the device counter. */
+__global__ void __launch_bounds__( 128 ) extendCountedKernel( const DevScene scene, const PathSet in, float4* __restrict__ hits,
+	const uint32_t* __restrict__ countPtr )
+{
+	const uint32_t n = *countPtr;
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+	{
+		const float4 o = in.O[i], d = in.D[i];
+		TraceResult r;
+		const bool hit = Traverse<false>( scene, make_float3( o.x, o.y, o.z ), make_float3( d.x, d.y, d.z ), 0.0f, 1e34f, r );
+		hits[i] = PackHit( hit, r );
+	}
+}
+
+/* connect (generateShadowRay, .optix.cu:142-154): unoccluded shadow rays deposit their potential contribution. */
+__global__ void __launch_bounds__( 128 ) connectKernel( const DevScene scene, const PathSet conn, float4* __restrict__ accumulator,
+	const uint32_t* __restrict__ countPtr )
+{
+	const uint32_t n = *countPtr;
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+	{
+		const float4 o = conn.O[i], d = conn.D[i];
+		TraceResult r;
+		if (Traverse<true>( scene, make_float3( o.x, o.y, o.z ), make_float3( d.x, d.y, d.z ), 0.0f, d.w, r )) continue;
+		const float4 e = conn.T[i];
+		atomicAdd( accumulator + __float_as_int( e.w ), make_float4( e.x, e.y, e.z, 1 ) );
+	}
+}
+
+static uint32_t GridFor( uint32_t maxItems, int smCount )
+{
+	uint32_t blocks = (maxItems + 127) / 128;
+	const uint32_t cap = (uint32_t)smCount * 8 * 8;
+	return blocks > cap ? cap : (blocks ? blocks : 1);
+}
+
+void LaunchGenerateExtend( const DevScene& scene, const RenderParams& p, const PathSet& out, float4* hits, int smCount, cudaStream_t s )
+{
+	generateExtendKernel<<<GridFor( p.stride, smCount ), 128, 0, s>>>( scene, p, out, hits );
+}
+
+void LaunchExtendCounted( const DevScene& scene, const PathSet& in, float4* hits, const uint32_t* countPtr, uint32_t maxRays, int smCount, cudaStream_t s )
+{
+	extendCountedKernel<<<GridFor( maxRays, smCount ), 128, 0, s>>>( scene, in, hits, countPtr );
+}
+
+void LaunchConnect( const DevScene& scene, const PathSet& conn, float4* accumulator, const uint32_t* countPtr, uint32_t maxRays, int smCount, cudaStream_t s )
+{
+	connectKernel<<<GridFor( maxRays, smCount ), 128, 0, s>>>( scene, conn, accumulator, countPtr );
 }
 
 void LaunchExtend( const DevScene& scene, const float4* O4, const float4* D4, float4* hits, int n, cudaStream_t s )

@@ -182,3 +182,97 @@ def random_rays(n, extent=12.0, seed=2):
     t = (rng.random((n, 3)) * 2 - 1) * extent * 0.5
     D[:, :3] = _normalize(t - O[:, :3])
     return O, D
+
+
+# ---- scene descriptions -------------------------------------------------------------------------
+
+class SceneDesc:
+    """Plain container of everything a core (or the oracle) is fed through the CoreAPI_Base calls."""
+
+    def __init__(self):
+        self.meshes = []        # list of (verts4 float32[3T,4], CoreTri[T])
+        self.instances = []     # list of (meshIdx, 4x4 float32 or None)
+        self.materials = None   # CoreMaterial[]
+        self.tri_lights = np.zeros(0, dtype=abi.CoreLightTri)
+        self.point_lights = np.zeros(0, dtype=abi.CorePointLight)
+        self.spot_lights = np.zeros(0, dtype=abi.CoreSpotLight)
+        self.dir_lights = np.zeros(0, dtype=abi.CoreDirectionalLight)
+        self.sky = None         # (float32[h,w,3], w, h)
+        self.textures = []      # list of (texels, storage, w, h, mips)
+
+    def upload(self, core):
+        """Issue the calls in the order RenderSystem::SynchronizeSceneData does (rendersystem.cpp:203-211)."""
+        if self.sky is not None:
+            core.SetSkyData(self.sky[0], self.sky[1], self.sky[2])
+        if self.textures:
+            core.SetTextures(self.textures)
+        core.SetMaterials(self.materials)
+        for i, (v, t) in enumerate(self.meshes):
+            core.SetGeometry(i, v, t)
+        core.SetLights(self.tri_lights, self.point_lights, self.spot_lights, self.dir_lights)
+        for i, (m, xf) in enumerate(self.instances):
+            core.SetInstance(i, m, xf)
+        core.SetInstance(len(self.instances), -1)
+        core.FinalizeInstances()
+
+
+def gradient_sky(w=512, h=256, zenith=(0.35, 0.5, 0.9), horizon=(0.9, 0.9, 0.85), scale=1.0):
+    """Equirect sky with a vertical gradient; rows follow theta = acos(D.z) like SampleSkydome (tools_shared.h:196-203)."""
+    t = np.linspace(0, 1, h, dtype=np.float32)[:, None, None]
+    g = 1.0 - np.abs(2 * t - 1)     # brightest at the middle rows (theta = pi/2)
+    sky = (np.asarray(zenith, f32) * (1 - g) + np.asarray(horizon, f32) * g) * scale
+    return np.ascontiguousarray(np.broadcast_to(sky, (h, w, 3)).astype(f32)), w, h
+
+
+def make_materials(specs):
+    """specs: list of dicts with optional keys color, roughness, transmission, eta, absorption, smooth."""
+    m = abi.default_material(len(specs))
+    for i, s in enumerate(specs):
+        m[i]["color"]["value"] = s.get("color", (0.8, 0.8, 0.8))
+        m[i]["roughness"]["value"] = s.get("roughness", 1.0)
+        m[i]["transmission"]["value"] = s.get("transmission", 0.0)
+        m[i]["eta"]["value"] = s.get("eta", 1.0)
+        m[i]["absorption"]["value"] = s.get("absorption", (0.0, 0.0, 0.0))
+        m[i]["flags"] = 1 if s.get("smooth", False) else 0
+    return m
+
+
+def config2_scene(nx=1000, nz=500, n_materials=1, light_quads=1, seed=0x12345678, floaters=0):
+    """BASELINE.json configs[1]/[2]: height-field terrain + emissive quads.
+    n_materials > 1 assigns diffuse/specular materials with roughness in {0, 0.3, 1} to terrain patches."""
+    sd = SceneDesc()
+    rng = np.random.default_rng(seed ^ 0x9E3779B9)
+    specs = []
+    for i in range(max(1, n_materials)):
+        col = 0.35 + 0.6 * rng.random(3)
+        rough = (1.0, 0.3, 0.0)[i % 3] if n_materials > 1 else 1.0
+        specs.append(dict(color=tuple(col), roughness=rough))
+    light_mat = len(specs)
+    specs.append(dict(color=(100.0, 100.0, 80.0)))
+    sd.materials = make_materials(specs)
+    tv = terrain(nx, nz, 50.0, seed, floaters)
+    tt = core_tris_from_verts(tv)
+    if n_materials > 1:
+        c = tv.reshape(-1, 3, 4)[:, :, :3].mean(axis=1)
+        patch = (np.floor((c[:, 0] + 50) / 12.5).astype(np.int64) * 8 + np.floor((c[:, 2] + 50) / 12.5).astype(np.int64))
+        tt["material"] = (patch * 2654435761 % (2 ** 32) >> 8) % n_materials
+    sd.meshes.append((tv, tt))
+    sd.instances.append((0, None))
+    lights = []
+    for k in range(light_quads):
+        if light_quads == 1:
+            center = (0.0, 26.0, 0.0)
+        else:
+            a = 2 * math.pi * k / light_quads
+            center = (30.0 * math.cos(a), 22.0 + 3.0 * (k % 3), 30.0 * math.sin(a))
+        qv = quad(center, (0, -1, 0), 6.9, 6.9)
+        qt = core_tris_from_verts(qv, material=light_mat)
+        mesh_idx = len(sd.meshes)
+        inst_idx = len(sd.instances)
+        lt = tri_lights(qv, qt, sd.materials, inst_idx=inst_idx, first_ltri=sum(len(l) for l in lights))
+        lights.append(lt)
+        sd.meshes.append((qv, qt))
+        sd.instances.append((mesh_idx, None))
+    sd.tri_lights = np.concatenate(lights)
+    sd.sky = gradient_sky()
+    return sd
