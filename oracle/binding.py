@@ -65,3 +65,138 @@ def occluded(meshes, instances, O4, D4, threads=None):
     lib().orc_occluded(cm, len(keep), ci, len(instances), ctypes.c_void_p(O4.ctypes.data), ctypes.c_void_p(D4.ctypes.data),
                        n, ctypes.c_void_p(occ.ctypes.data), threads or os.cpu_count())
     return occ
+
+
+# ---- full frame -----------------------------------------------------------------------------------
+
+class OrcTexDesc(ctypes.Structure):
+    _fields_ = [("data", ctypes.c_void_p), ("width", ctypes.c_uint), ("height", ctypes.c_uint), ("flags", ctypes.c_uint),
+                ("pixelCount", ctypes.c_uint), ("firstPixel", ctypes.c_uint), ("mipLevels", ctypes.c_uint),
+                ("storage", ctypes.c_int), ("pad", ctypes.c_uint)]
+
+
+class OrcMaterialIn(ctypes.Structure):
+    _fields_ = [("color", ctypes.c_float * 3), ("absorption", ctypes.c_float * 3), ("params", ctypes.c_float * 12),
+                ("flags", ctypes.c_uint), ("tex", ctypes.c_int * 6), ("uvscale", (ctypes.c_float * 2) * 6),
+                ("uvoffset", (ctypes.c_float * 2) * 6)]
+
+
+class OrcFrameIn(ctypes.Structure):
+    _fields_ = [("meshes", ctypes.c_void_p), ("coreTris", ctypes.c_void_p), ("meshCount", ctypes.c_int),
+                ("instances", ctypes.c_void_p), ("instanceCount", ctypes.c_int),
+                ("materials", ctypes.c_void_p), ("materialCount", ctypes.c_int),
+                ("textures", ctypes.c_void_p), ("textureCount", ctypes.c_int),
+                ("triLights", ctypes.c_void_p), ("triLightCount", ctypes.c_int),
+                ("pointLights", ctypes.c_void_p), ("pointLightCount", ctypes.c_int),
+                ("spotLights", ctypes.c_void_p), ("spotLightCount", ctypes.c_int),
+                ("dirLights", ctypes.c_void_p), ("dirLightCount", ctypes.c_int),
+                ("skyPixels", ctypes.c_void_p), ("skyW", ctypes.c_int), ("skyH", ctypes.c_int),
+                ("worldToSky", ctypes.c_float * 16), ("blueNoiseBytes", ctypes.c_void_p),
+                ("w", ctypes.c_int), ("h", ctypes.c_int), ("spp", ctypes.c_int), ("pass_", ctypes.c_int),
+                ("sampleBase", ctypes.c_uint), ("shiftSeed", ctypes.c_uint), ("camRNGseed", ctypes.c_uint),
+                ("geometryEpsilon", ctypes.c_float), ("clampValue", ctypes.c_float),
+                ("maxPathLength", ctypes.c_int), ("enoughBounces", ctypes.c_uint),
+                ("view", ctypes.c_float * 17), ("threads", ctypes.c_int)]
+
+
+PathRecord = np.dtype([("hit", np.uint32, 4), ("firstShadow", np.float32, 8)])
+_PARAM_NAMES = ("metallic", "subsurface", "specular", "roughness", "specularTint", "anisotropic", "sheen", "sheenTint",
+                "clearcoat", "clearcoatGloss", "transmission", "eta")
+_TEX_NAMES = ("color", "detailColor", "normals", "detailNormals", "specular", "roughness")
+_BLUENOISE = os.path.join(os.path.dirname(_HERE), "lighthouse2_b200", "data", "heitz_bluenoise_256spp.bin")
+
+
+class FrameOracle:
+    """Stateful CPU counterpart of one render core: keeps samplesTaken and the two host RNG states
+    (rendercore.h:122-123) so consecutive Render calls can be mirrored frame by frame."""
+
+    def __init__(self, scene, width, height, spp=1, epsilon=1e-4, clamp=10.0, max_path_length=3, max_diffuse_bounces=1,
+                 threads=None, sample_base=0, total_spp=0):
+        self.sd, self.w, self.h, self.spp = scene, width, height, spp
+        self.eps, self.clamp, self.maxlen = epsilon, clamp, max_path_length
+        self.enough = 0 if max_diffuse_bounces <= 0 else (2 if max_diffuse_bounces < 2 else 8)
+        self.threads = threads or os.cpu_count()
+        self.sample_base, self.total_spp = sample_base, total_spp
+        self.samples_taken = 0
+        self.shift_seed, self.cam_seed = 0x11331445, 0x12345678
+        self.first_converging = True
+        self.accum = np.zeros((height, width, 4), np.float32)
+        self.ray_counts = (0, 0)
+
+    def render(self, view, converge=1, records=False):
+        sd = self.sd
+        if converge == 1 or self.first_converging:
+            self.samples_taken, self.first_converging, self.cam_seed = 0, True, 0x12345678
+        if converge == 0:
+            self.first_converging = False
+        if self.samples_taken == 0:
+            self.accum[:] = 0
+        keep = []
+        verts = [np.ascontiguousarray(v, np.float32).reshape(-1, 4) for v, _ in sd.meshes]
+        tris = [np.ascontiguousarray(t) for _, t in sd.meshes]
+        keep += verts + tris
+        cm = (OrcMesh * len(verts))()
+        ct = (ctypes.c_void_p * len(verts))()
+        for i, (v, t) in enumerate(zip(verts, tris)):
+            cm[i].verts4, cm[i].triCount = v.ctypes.data, v.shape[0] // 3
+            ct[i] = t.ctypes.data
+        ci = (OrcInstance * max(len(sd.instances), 1))()
+        for i, (mi, xf) in enumerate(sd.instances):
+            ci[i].mesh = mi
+            x = np.eye(4, dtype=np.float32) if xf is None else np.asarray(xf, np.float32).reshape(4, 4)
+            for k in range(12):
+                ci[i].xform[k] = float(x.flat[k])
+        mats = (OrcMaterialIn * len(sd.materials))()
+        for i, m in enumerate(sd.materials):
+            mats[i].color[:] = [float(x) for x in m["color"]["value"]]
+            mats[i].absorption[:] = [float(x) for x in m["absorption"]["value"]]
+            mats[i].params[:] = [float(m[n]["value"]) for n in _PARAM_NAMES]
+            mats[i].flags = int(m["flags"])
+            for k, n in enumerate(_TEX_NAMES):
+                mats[i].tex[k] = int(m[n]["textureID"])
+                mats[i].uvscale[k][:] = [float(x) for x in m[n]["uvscale"]]
+                mats[i].uvoffset[k][:] = [float(x) for x in m[n]["uvoffset"]]
+        texs = (OrcTexDesc * max(len(sd.textures), 1))()
+        for i, (tex, storage, w, h, mips) in enumerate(sd.textures):
+            tex = np.ascontiguousarray(tex)
+            keep.append(tex)
+            texs[i].data, texs[i].width, texs[i].height = tex.ctypes.data, w, h
+            texs[i].pixelCount, texs[i].mipLevels, texs[i].storage = tex.size // 4, mips, storage
+        f = OrcFrameIn()
+        f.meshes, f.coreTris, f.meshCount = ctypes.addressof(cm), ctypes.addressof(ct), len(verts)
+        f.instances, f.instanceCount = ctypes.addressof(ci), len(sd.instances)
+        f.materials, f.materialCount = ctypes.addressof(mats), len(sd.materials)
+        f.textures, f.textureCount = ctypes.addressof(texs), len(sd.textures)
+        lights = [np.ascontiguousarray(a) for a in (sd.tri_lights, sd.point_lights, sd.spot_lights, sd.dir_lights)]
+        keep += lights
+        f.triLights, f.triLightCount = lights[0].ctypes.data, len(lights[0])
+        f.pointLights, f.pointLightCount = lights[1].ctypes.data, len(lights[1])
+        f.spotLights, f.spotLightCount = lights[2].ctypes.data, len(lights[2])
+        f.dirLights, f.dirLightCount = lights[3].ctypes.data, len(lights[3])
+        if sd.sky is not None:
+            sky = np.ascontiguousarray(sd.sky[0], np.float32)
+            keep.append(sky)
+            f.skyPixels, f.skyW, f.skyH = sky.ctypes.data, sd.sky[1], sd.sky[2]
+        f.worldToSky[:] = [float(x) for x in np.eye(4, dtype=np.float32).flat]
+        bn = np.fromfile(_BLUENOISE, dtype=np.uint8)
+        keep.append(bn)
+        f.blueNoiseBytes = bn.ctypes.data
+        f.w, f.h, f.spp, f.pass_ = self.w, self.h, self.spp, self.samples_taken
+        f.sampleBase = self.sample_base
+        f.shiftSeed, f.camRNGseed = self.shift_seed, self.cam_seed
+        f.geometryEpsilon, f.clampValue = self.eps, self.clamp
+        f.maxPathLength, f.enoughBounces = self.maxlen, self.enough
+        f.view[:] = [float(x) for x in np.frombuffer(np.ascontiguousarray(view).tobytes(), np.float32)]
+        f.threads = self.threads
+        counts = (ctypes.c_uint64 * 2)()
+        seeds = (ctypes.c_uint * 2)()
+        rec = np.zeros(self.w * self.h * self.spp, dtype=PathRecord) if records else None
+        lib().orc_render_frame(ctypes.byref(f), ctypes.c_void_p(self.accum.ctypes.data), counts, seeds,
+                               ctypes.c_void_p(rec.ctypes.data) if records else None)
+        self.shift_seed, self.cam_seed = seeds[0], seeds[1]
+        self.ray_counts = (int(counts[0]), int(counts[1]))
+        total = self.total_spp if self.total_spp > 0 else self.spp
+        self.samples_taken += total
+        local = self.samples_taken * self.spp // total
+        self.pixels = self.accum / np.float32(local)
+        return (self.pixels, rec) if records else self.pixels

@@ -49,3 +49,162 @@ ORC_API void orc_occluded( const orc::Mesh* meshes, int meshCount, const orc::In
 	} );
 	s.Release();
 }
+
+/* ---- full frame ---------------------------------------------------------------------------- */
+#include "lh2_oracle_render.h"
+
+struct OrcMaterialIn
+{
+	float color[3], absorption[3];
+	float params[12];		// metallic, subsurface, specular, roughness, specularTint, anisotropic, sheen, sheenTint, clearcoat, clearcoatGloss, transmission, eta
+	uint32_t flags;			// CoreMaterial::flags (bit 0 smooth normals, bit 1 alpha)
+	int32_t tex[6];			// texture ids: color, detailColor, normals, detailNormals, specular, roughness (-1 = none)
+	float uvscale[6][2], uvoffset[6][2];
+};
+
+struct OrcFrameIn
+{
+	const orc::Mesh* meshes; const float* const* coreTris; int meshCount;
+	const orc::Instance* instances; int instanceCount;
+	const OrcMaterialIn* materials; int materialCount;
+	const orc::TexDesc* textures; int textureCount;
+	const float* triLights; int triLightCount;
+	const float* pointLights; int pointLightCount;
+	const float* spotLights; int spotLightCount;
+	const float* dirLights; int dirLightCount;
+	const float* skyPixels; int skyW, skyH;		// float3 pixels
+	float worldToSky[16];
+	const uint8_t* blueNoiseBytes;				// sob | scr | rnk byte tables (327680 bytes)
+	int w, h, spp, pass;
+	uint32_t sampleBase;
+	uint32_t shiftSeed, camRNGseed;				// generator states BEFORE this frame (rendercore.h:122-123)
+	float geometryEpsilon, clampValue;
+	int maxPathLength; uint32_t enoughBounces;
+	float view[17];
+	int threads;
+};
+
+static uint32_t XorShift( uint32_t& s ) { s ^= s << 13, s ^= s >> 17, s ^= s << 5; return s; }
+
+static void ConvertMaterials( const OrcFrameIn& in, std::vector<orc::TexDesc>& tex, orc::RenderScene& sc )
+{
+	// texture packing per storage class (rendercore.cpp:458-502), then material conversion (rendercore.cpp:508-549)
+	tex.assign( in.textures, in.textures + in.textureCount );
+	for (int storage = 0; storage < 3; storage++)
+	{
+		size_t at = 0;
+		for (auto& t : tex) if (t.storage == storage)
+		{
+			t.firstPixel = (uint32_t)at;
+			if (storage == 1) sc.argb128.insert( sc.argb128.end(), (const float*)t.data, (const float*)t.data + (size_t)t.pixelCount * 4 );
+			else (storage == 0 ? sc.argb32 : sc.nrm32).insert( (storage == 0 ? sc.argb32 : sc.nrm32).end(), (const uint8_t*)t.data, (const uint8_t*)t.data + (size_t)t.pixelCount * 4 );
+			at += t.pixelCount;
+		}
+	}
+	sc.argb32.resize( sc.argb32.size() + 64, 0 ), sc.nrm32.resize( sc.nrm32.size() + 64, 0 ), sc.argb128.resize( sc.argb128.size() + 64, 0 );
+	auto toChar = []( float a ) { return (uint32_t)orc::F2U( a * 255.0f ); };
+	for (int i = 0; i < in.materialCount; i++)
+	{
+		const OrcMaterialIn& m = in.materials[i];
+		orc::Material g;
+		memset( &g, 0, sizeof( g ) );
+		uint16_t th[3];
+		for (int k = 0; k < 3; k++)
+		{
+			g.color[k] = orc::HalfToFloat( orc::FloatToHalf( m.color[k] ) );
+			th[k] = orc::FloatToHalf( 1 - m.absorption[k] );
+			g.transmittance[k] = orc::HalfToFloat( th[k] );
+		}
+		g.baseZ = (uint32_t)th[1] | ((uint32_t)th[2] << 16);
+		const float* p = m.params;
+		g.params[0] = toChar( p[0] ) + (toChar( p[1] ) << 8) + (toChar( p[2] ) << 16) + (toChar( p[3] ) << 24);
+		g.params[1] = toChar( p[4] ) + (toChar( p[5] ) << 8) + (toChar( p[6] ) << 16) + (toChar( p[7] ) << 24);
+		g.params[2] = toChar( p[8] ) + (toChar( p[9] ) << 8) + (toChar( p[10] ) << 16);
+		g.params[3] = orc::FBits( p[11] );
+		const int bit[6] = { 2, 9, 3, 7, 4, 5 };
+		orc::Material::Map* maps[6] = { &g.tex0, &g.tex1, &g.nmap0, &g.nmap1, &g.smap, &g.rmap };
+		g.flags = (p[11] < 1 ? 1u : 0) + ((m.flags & 1) ? (1u << 11) : 0) + ((m.flags & 2) ? (1u << 12) : 0);
+		for (int k = 0; k < 6; k++) if (m.tex[k] != -1)
+		{
+			g.flags += 1u << bit[k];
+			const orc::TexDesc& t = tex[m.tex[k]];
+			maps[k]->w = (int16_t)t.width, maps[k]->h = (int16_t)t.height;
+			maps[k]->uscale = orc::HalfToFloat( orc::FloatToHalf( m.uvscale[k][0] ) ), maps[k]->vscale = orc::HalfToFloat( orc::FloatToHalf( m.uvscale[k][1] ) );
+			maps[k]->uoffs = orc::HalfToFloat( orc::FloatToHalf( m.uvoffset[k][0] ) ), maps[k]->voffs = orc::HalfToFloat( orc::FloatToHalf( m.uvoffset[k][1] ) );
+			maps[k]->addr = t.firstPixel;
+		}
+		if (m.tex[0] != -1 && (tex[m.tex[0]].flags & 8)) g.flags += 1u << 1;
+		sc.materials.push_back( g );
+	}
+}
+
+/* Renders one frame exactly as RenderCore::Render(view, converge) + FinalizeRender would; accumulates into
+   accum (float4 per pixel; caller zeroes it for a Restart frame). rayCounts[0] = extension rays, [1] = shadow rays.
+   seedsOut[0] = shiftSeed after, seedsOut[1] = camRNGseed after. records (optional): one PathRecord per path. */
+ORC_API void orc_render_frame( const OrcFrameIn* inp, float* accum, uint64_t* rayCounts, uint32_t* seedsOut, orc::PathRecord* records )
+{
+	const OrcFrameIn& in = *inp;
+	orc::RenderScene sc;
+	sc.geo = orc::Scene{ in.meshes, in.meshCount, in.instances, in.instanceCount, nullptr };
+	sc.geo.Prepare();
+	sc.coreTris = in.coreTris;
+	std::vector<orc::TexDesc> tex;
+	ConvertMaterials( in, tex, sc );
+	sc.triLights = in.triLights, sc.triLightCount = in.triLightCount;
+	sc.pointLights = in.pointLights, sc.pointLightCount = in.pointLightCount;
+	sc.spotLights = in.spotLights, sc.spotLightCount = in.spotLightCount;
+	sc.dirLights = in.dirLights, sc.dirLightCount = in.dirLightCount;
+	// sky: float3 -> float4 plus the 64x64 box-filtered copy (rendercore.cpp:716-737)
+	sc.skyW = in.skyW, sc.skyH = in.skyH;
+	const int sw = in.skyW >> 6, sh = in.skyH >> 6;
+	sc.sky.assign( ((size_t)in.skyW * in.skyH + (size_t)sw * sh + 1) * 4, 0.0f );
+	for (size_t i = 0; i < (size_t)in.skyW * in.skyH; i++) for (int k = 0; k < 3; k++) sc.sky[i * 4 + k] = in.skyPixels[i * 3 + k];
+	for (int y = 0; y < sh; y++) for (int x = 0; x < sw; x++)
+	{
+		float total[4] = { 0, 0, 0, 0 };
+		for (int v = 0; v < 64; v++) for (int u = 0; u < 64; u++)
+		{
+			const float* t = sc.sky.data() + 4 * ((size_t)(x * 64 + u) + (size_t)(y * 64 + v) * in.skyW);
+			for (int k = 0; k < 4; k++) total[k] += t[k];
+		}
+		float* o = sc.sky.data() + 4 * ((size_t)in.skyW * in.skyH + x + (size_t)y * sw);
+		for (int k = 0; k < 4; k++) o[k] = total[k] * (1.0f / (64 * 64));
+	}
+	memcpy( sc.worldToSky, in.worldToSky, sizeof( sc.worldToSky ) );
+	std::vector<uint32_t> bn( 65536 * 5, 0 );
+	for (int i = 0; i < 65536; i++) bn[i] = in.blueNoiseBytes[i];
+	for (int i = 0; i < 128 * 128 * 8; i++) bn[i + 65536] = in.blueNoiseBytes[65536 + i], bn[i + 3 * 65536] = in.blueNoiseBytes[65536 + 131072 + i];
+	sc.blueNoise = bn.data();
+	orc::Settings st;
+	memset( &st, 0, sizeof( st ) );
+	st.w = in.w, st.h = in.h, st.spp = in.spp, st.pass = in.pass, st.sampleBase = in.sampleBase;
+	uint32_t shiftSeed = in.shiftSeed, camSeed = in.camRNGseed;
+	XorShift( shiftSeed );
+	st.shift = shiftSeed;
+	for (int L = 1; L <= in.maxPathLength; L++) st.R0[L] = XorShift( camSeed ) + L * 91771;
+	st.geometryEpsilon = in.geometryEpsilon, st.clampValue = in.clampValue;
+	st.maxPathLength = in.maxPathLength, st.enoughBounces = in.enoughBounces;
+	memcpy( st.view, in.view, sizeof( st.view ) );
+	if (seedsOut) seedsOut[0] = shiftSeed, seedsOut[1] = camSeed;
+	const int pixels = in.w * in.h;
+	std::vector<double> acc( (size_t)pixels * 4, 0.0 );
+	const int threads = in.threads > 0 ? in.threads : 1;
+	std::vector<uint64_t> counts( (size_t)threads * 2, 0 );
+	std::vector<std::thread> pool;
+	// interleave rows over threads: cost varies smoothly over the image
+	for (int t = 0; t < threads; t++) pool.emplace_back( [&, t]() {
+		uint32_t rc[2] = { 0, 0 };
+		for (int y = t; y < in.h; y += threads) for (int x = 0; x < in.w; x++) for (int s = 0; s < in.spp; s++)
+		{
+			const uint32_t pathIdx = (uint32_t)(x + y * in.w) + (uint32_t)s * pixels;
+			orc::PathRecord* rec = records ? records + pathIdx : nullptr;
+			if (rec) memset( rec, 0, sizeof( *rec ) );
+			orc::TracePath( sc, st, pathIdx, acc.data(), rc, rec );
+			counts[t * 2] += rc[0], counts[t * 2 + 1] += rc[1], rc[0] = rc[1] = 0;
+		}
+	} );
+	for (auto& th : pool) th.join();
+	for (size_t i = 0; i < (size_t)pixels * 4; i++) accum[i] += (float)acc[i];
+	if (rayCounts) { rayCounts[0] = rayCounts[1] = 0; for (int t = 0; t < threads; t++) rayCounts[0] += counts[t * 2], rayCounts[1] += counts[t * 2 + 1]; }
+	sc.geo.Release();
+}
