@@ -105,6 +105,17 @@ LH2B_API int lh2b_get_frame_stats( lh2b_core* core, lh2b_frame_stats* out );
 typedef struct lh2b_bvh_stats { uint32_t nodes, triangles, bytes; float buildMs; float sahCost; uint32_t reserved[3]; } lh2b_bvh_stats;
 LH2B_API int lh2b_get_bvh_stats( lh2b_core* core, int meshIdx, lh2b_bvh_stats* out );
 
+/* Parity hook: run the shade stage alone (shadeKernel, lib/rendercore_optix7/kernels/pathtracer.h:54-238) on HOST
+   buffers of n paths at the given path length, with explicit per-frame random state (R0, shift, pass). Outputs: the
+   compacted extension rays and shadow rays (order unspecified; match by the path / pixel index they carry) and the
+   accumulator (float4[w*h], in/out). Uses the current target, scene tables and settings. */
+LH2B_API int lh2b_shade_paths( lh2b_core* core, int pathLength, int n, const float* O4, const float* D4, const float* T4, const float* hits,
+	uint32_t R0, uint32_t shift, int pass, float* extO, float* extD, float* extT, int* extCount,
+	float* shO, float* shD, float* shE, int* shCount, float* accumulator );
+
+/* The C handle behind a CoreAPI_Base* obtained from CreateCore() (for headless read-back and statistics). */
+LH2B_API lh2b_core* lh2b_handle_of( void* coreApiBase );
+
 #ifdef __cplusplus
 }
 #endif

@@ -161,6 +161,21 @@ class RenderCore:
                                                             ctypes.byref(ms) if timed else None))
         return ms.value
 
+    def ShadePaths(self, path_length, O4, D4, T4, hits, R0, shift, pass_, accumulator):
+        """Parity hook (lh2b_shade_paths): the shade stage alone on host buffers. Returns (ext dict, shadow dict, accumulator)."""
+        O4, D4, T4 = (_arr(a, np.float32).reshape(-1, 4) for a in (O4, D4, T4))
+        hits = np.ascontiguousarray(hits).view(np.float32).reshape(-1, 4)
+        n = O4.shape[0]
+        out = [np.zeros((n, 4), np.float32) for _ in range(6)]
+        acc = np.ascontiguousarray(accumulator, np.float32).copy()
+        ne, ns = ctypes.c_int(0), ctypes.c_int(0)
+        self._check(self._lib.lh2b_shade_paths(self._h, path_length, n, _ptr(O4), _ptr(D4), _ptr(T4), _ptr(hits), R0, shift, pass_,
+                                               _ptr(out[0]), _ptr(out[1]), _ptr(out[2]), ctypes.byref(ne),
+                                               _ptr(out[3]), _ptr(out[4]), _ptr(out[5]), ctypes.byref(ns), _ptr(acc)))
+        ext = dict(O=out[0][:ne.value], D=out[1][:ne.value], T=out[2][:ne.value])
+        sh = dict(O=out[3][:ns.value], D=out[4][:ns.value], E=out[5][:ns.value])
+        return ext, sh, acc
+
     def Stream(self):
         p = ctypes.c_void_p()
         self._check(self._lib.lh2b_stream(self._h, ctypes.byref(p)))

@@ -119,15 +119,9 @@ static void FinishFrame( lh2b_core* core )
 	st.traceTime0 *= 0.001f, st.traceTime1 *= 0.001f, st.traceTimeX *= 0.001f, st.shadeTime *= 0.001f, st.shadowTraceTime *= 0.001f;
 }
 
-static void RenderFrame( lh2b_core* core, const lh2abi::ViewPyramid& view )
+static RenderParams BuildParams( lh2b_core* core, const lh2abi::ViewPyramid& view )
 {
-	cudaStream_t s = core->stream;
 	const uint32_t stride = (uint32_t)core->width * core->height * core->spp;
-	core->lastView = view;
-	CUDA_CHECK( cudaEventRecord( core->events[0], s ) );
-	if (core->samplesTaken == 0) CUDA_CHECK( cudaMemsetAsync( core->accumulator.ptr, 0, (size_t)core->width * core->height * sizeof( float4 ), s ) );
-	CUDA_CHECK( cudaMemsetAsync( core->counters.ptr, 0, sizeof( DevCounters ), s ) );
-	RandomUInt( core->shiftSeed );
 	RenderParams p = {};
 	p.posLensSize = make_float4( view.pos.x, view.pos.y, view.pos.z, view.aperture );
 	p.right = make_float3( view.p2.x - view.p1.x, view.p2.y - view.p1.y, view.p2.z - view.p1.z );
@@ -148,6 +142,19 @@ static void RenderFrame( lh2b_core* core, const lh2abi::ViewPyramid& view )
 	p.skyPixels = core->skyPixels.ptr, p.skyW = core->skyW, p.skyH = core->skyH;
 	memcpy( p.worldToSky, core->worldToSky, sizeof( p.worldToSky ) );
 	p.blueNoise = core->blueNoise.ptr, p.accumulator = core->accumulator.ptr, p.counters = core->counters.ptr;
+	return p;
+}
+
+static void RenderFrame( lh2b_core* core, const lh2abi::ViewPyramid& view )
+{
+	cudaStream_t s = core->stream;
+	const uint32_t stride = (uint32_t)core->width * core->height * core->spp;
+	core->lastView = view;
+	CUDA_CHECK( cudaEventRecord( core->events[0], s ) );
+	if (core->samplesTaken == 0) CUDA_CHECK( cudaMemsetAsync( core->accumulator.ptr, 0, (size_t)core->width * core->height * sizeof( float4 ), s ) );
+	CUDA_CHECK( cudaMemsetAsync( core->counters.ptr, 0, sizeof( DevCounters ), s ) );
+	RandomUInt( core->shiftSeed );
+	RenderParams p = BuildParams( core, view );
 	const bool useNEE = (core->lightCounts[0] + core->lightCounts[1] + core->lightCounts[2] + core->lightCounts[3]) > 0;
 	const PathSet conn = { core->connBuf[0].ptr, core->connBuf[1].ptr, core->connBuf[2].ptr };
 	const int sm = (int)core->stats.SMcount;
@@ -436,6 +443,52 @@ int lh2b_finalize_external( lh2b_core* core, const void* dAccumulator, int sampl
 	if (samples <= 0) throw CoreError( "finalize_external: samples must be positive" );
 	LaunchFinalize( (const float4*)dAccumulator, core->pixels.ptr, core->width * core->height, samples, core->stream );
 	CUDA_CHECK( cudaStreamSynchronize( core->stream ) );
+	API_END
+}
+
+int lh2b_shade_paths( lh2b_core* core, int pathLength, int n, const float* O4, const float* D4, const float* T4, const float* hits,
+	uint32_t R0, uint32_t shift, int pass, float* extO, float* extD, float* extT, int* extCount,
+	float* shO, float* shD, float* shE, int* shCount, float* accumulator )
+{
+	API_BEGIN
+	FinishFrame( core );
+	if (!core->sceneReady || core->width == 0) throw CoreError( "shade_paths: scene and target must be set" );
+	const uint32_t stride = (uint32_t)core->width * core->height * core->spp;
+	if (n < 0 || (uint32_t)n > stride) throw CoreError( "shade_paths: n exceeds w*h*spp" );
+	if (pathLength < 1 || pathLength > core->maxPathLength) throw CoreError( "shade_paths: pathLength out of range" );
+	cudaStream_t s = core->stream;
+	const size_t bytes = (size_t)n * sizeof( float4 ), accBytes = (size_t)core->width * core->height * sizeof( float4 );
+	CUDA_CHECK( cudaMemcpyAsync( core->pathBuf[0][0].ptr, O4, bytes, cudaMemcpyHostToDevice, s ) );
+	CUDA_CHECK( cudaMemcpyAsync( core->pathBuf[0][1].ptr, D4, bytes, cudaMemcpyHostToDevice, s ) );
+	CUDA_CHECK( cudaMemcpyAsync( core->pathBuf[0][2].ptr, T4, bytes, cudaMemcpyHostToDevice, s ) );
+	CUDA_CHECK( cudaMemcpyAsync( core->hitBuf.ptr, hits, bytes, cudaMemcpyHostToDevice, s ) );
+	CUDA_CHECK( cudaMemcpyAsync( core->accumulator.ptr, accumulator, accBytes, cudaMemcpyHostToDevice, s ) );
+	DevCounters hc;
+	memset( &hc, 0, sizeof( hc ) );
+	hc.extensionRays[pathLength - 1] = (uint32_t)n;
+	CUDA_CHECK( cudaMemcpyAsync( core->counters.ptr, &hc, sizeof( hc ), cudaMemcpyHostToDevice, s ) );
+	lh2abi::ViewPyramid view = core->lastView;
+	RenderParams p = BuildParams( core, view );
+	p.stride = pathLength == 1 ? (uint32_t)n : stride;
+	p.shift = shift, p.pass = pass;
+	const bool useNEE = (core->lightCounts[0] + core->lightCounts[1] + core->lightCounts[2] + core->lightCounts[3]) > 0;
+	const PathSet in = { core->pathBuf[0][0].ptr, core->pathBuf[0][1].ptr, core->pathBuf[0][2].ptr };
+	const PathSet out = { core->pathBuf[1][0].ptr, core->pathBuf[1][1].ptr, core->pathBuf[1][2].ptr };
+	const PathSet conn = { core->connBuf[0].ptr, core->connBuf[1].ptr, core->connBuf[2].ptr };
+	LaunchShade( p, in, out, core->hitBuf.ptr, conn, pathLength, R0, useNEE, (uint32_t)n, (int)core->stats.SMcount, s );
+	CUDA_CHECK( cudaGetLastError() );
+	CUDA_CHECK( cudaMemcpyAsync( &hc, core->counters.ptr, sizeof( hc ), cudaMemcpyDeviceToHost, s ) );
+	CUDA_CHECK( cudaStreamSynchronize( s ) );
+	const uint32_t ne = hc.extensionRays[pathLength], ns = hc.shadowRays[pathLength];
+	*extCount = (int)ne, *shCount = (int)ns;
+	CUDA_CHECK( cudaMemcpyAsync( extO, out.O, ne * sizeof( float4 ), cudaMemcpyDeviceToHost, s ) );
+	CUDA_CHECK( cudaMemcpyAsync( extD, out.D, ne * sizeof( float4 ), cudaMemcpyDeviceToHost, s ) );
+	CUDA_CHECK( cudaMemcpyAsync( extT, out.T, ne * sizeof( float4 ), cudaMemcpyDeviceToHost, s ) );
+	CUDA_CHECK( cudaMemcpyAsync( shO, conn.O, ns * sizeof( float4 ), cudaMemcpyDeviceToHost, s ) );
+	CUDA_CHECK( cudaMemcpyAsync( shD, conn.D, ns * sizeof( float4 ), cudaMemcpyDeviceToHost, s ) );
+	CUDA_CHECK( cudaMemcpyAsync( shE, conn.T, ns * sizeof( float4 ), cudaMemcpyDeviceToHost, s ) );
+	CUDA_CHECK( cudaMemcpyAsync( accumulator, core->accumulator.ptr, accBytes, cudaMemcpyDeviceToHost, s ) );
+	CUDA_CHECK( cudaStreamSynchronize( s ) );
 	API_END
 }
 

@@ -131,6 +131,23 @@ class FrameOracle:
             self.first_converging = False
         if self.samples_taken == 0:
             self.accum[:] = 0
+        f, keep = self.frame_in(view)
+        counts = (ctypes.c_uint64 * 2)()
+        seeds = (ctypes.c_uint * 2)()
+        rec = np.zeros(self.w * self.h * self.spp, dtype=PathRecord) if records else None
+        lib().orc_render_frame(ctypes.byref(f), ctypes.c_void_p(self.accum.ctypes.data), counts, seeds,
+                               ctypes.c_void_p(rec.ctypes.data) if records else None)
+        self.shift_seed, self.cam_seed = seeds[0], seeds[1]
+        self.ray_counts = (int(counts[0]), int(counts[1]))
+        total = self.total_spp if self.total_spp > 0 else self.spp
+        self.samples_taken += total
+        local = self.samples_taken * self.spp // total
+        self.pixels = self.accum / np.float32(local)
+        return (self.pixels, rec) if records else self.pixels
+
+    def frame_in(self, view):
+        """OrcFrameIn for the current state plus the list of arrays that must stay alive while it is used."""
+        sd = self.sd
         keep = []
         verts = [np.ascontiguousarray(v, np.float32).reshape(-1, 4) for v, _ in sd.meshes]
         tris = [np.ascontiguousarray(t) for _, t in sd.meshes]
@@ -188,15 +205,119 @@ class FrameOracle:
         f.maxPathLength, f.enoughBounces = self.maxlen, self.enough
         f.view[:] = [float(x) for x in np.frombuffer(np.ascontiguousarray(view).tobytes(), np.float32)]
         f.threads = self.threads
-        counts = (ctypes.c_uint64 * 2)()
-        seeds = (ctypes.c_uint * 2)()
-        rec = np.zeros(self.w * self.h * self.spp, dtype=PathRecord) if records else None
-        lib().orc_render_frame(ctypes.byref(f), ctypes.c_void_p(self.accum.ctypes.data), counts, seeds,
-                               ctypes.c_void_p(rec.ctypes.data) if records else None)
-        self.shift_seed, self.cam_seed = seeds[0], seeds[1]
-        self.ray_counts = (int(counts[0]), int(counts[1]))
-        total = self.total_spp if self.total_spp > 0 else self.spp
-        self.samples_taken += total
-        local = self.samples_taken * self.spp // total
-        self.pixels = self.accum / np.float32(local)
-        return (self.pixels, rec) if records else self.pixels
+        keep += [cm, ct, ci, mats, texs]
+        return f, keep
+
+    def shade_paths(self, view, path_length, O4, D4, T4, hits, R0, shift, pass_):
+        """Stage-level oracle: shadeKernel on n paths. Returns dict of per-path (uncompacted) outputs + flags."""
+        f, keep = self.frame_in(view)
+        n = O4.shape[0]
+        arrs = {k: np.zeros((n, 4), np.float32) for k in ("extO", "extD", "extT", "shO", "shD", "shE", "deposit")}
+        flags = np.zeros(n, np.uint8)
+        O4, D4, T4 = (np.ascontiguousarray(a, np.float32) for a in (O4, D4, T4))
+        hits = np.ascontiguousarray(hits, np.uint32)
+        p = lambda a: ctypes.c_void_p(a.ctypes.data)
+        lib().orc_shade_paths(ctypes.byref(f), path_length, n, p(O4), p(D4), p(T4), p(hits), ctypes.c_uint(R0), ctypes.c_uint(shift), pass_,
+                              p(arrs["extO"]), p(arrs["extD"]), p(arrs["extT"]), p(arrs["shO"]), p(arrs["shD"]), p(arrs["shE"]),
+                              p(arrs["deposit"]), p(flags))
+        arrs["flags"] = flags
+        return arrs
+
+    def reference_tables(self, view):
+        """Converted materials (CUDAMaterial, 128 B each), packed texel arrays, sky table and instance inverses - the
+        device-side tables of the reference core, produced by the oracle's restatement of rendercore.cpp:438-565,716-737."""
+        f, keep = self.frame_in(view)
+        mats = np.zeros((len(self.sd.materials), 32), np.uint32)
+        lib().orc_convert_materials(ctypes.byref(f), ctypes.c_void_p(mats.ctypes.data))
+        cnt = [ctypes.c_uint(0) for _ in range(4)]
+        lib().orc_scene_tables(ctypes.byref(f), None, ctypes.byref(cnt[0]), None, ctypes.byref(cnt[1]), None, ctypes.byref(cnt[2]), None,
+                               ctypes.byref(cnt[3]), None)
+        a32 = np.zeros((cnt[0].value, 4), np.uint8); a128 = np.zeros((cnt[1].value, 4), np.float32)
+        n32 = np.zeros((cnt[2].value, 4), np.uint8); sky = np.zeros((cnt[3].value, 4), np.float32)
+        inv = np.zeros((max(len(self.sd.instances), 1), 16), np.float32)
+        p = lambda a: ctypes.c_void_p(a.ctypes.data)
+        lib().orc_scene_tables(ctypes.byref(f), p(a32), ctypes.byref(cnt[0]), p(a128), ctypes.byref(cnt[1]), p(n32), ctypes.byref(cnt[2]),
+                               p(sky), ctypes.byref(cnt[3]), p(inv))
+        return dict(materials=mats, argb32=a32, argb128=a128, nrm32=n32, sky=sky, inverses=inv)
+
+
+# ---- the reference's own shadeKernel, compiled for sm_100a from /root/reference (oracle/_ref) -------------
+
+class RefShadeIn(ctypes.Structure):
+    _fields_ = [("meshCount", ctypes.c_int), ("coreTris", ctypes.c_void_p), ("triCounts", ctypes.c_void_p),
+                ("instanceCount", ctypes.c_int), ("instMesh", ctypes.c_void_p), ("instInverse16", ctypes.c_void_p),
+                ("materials128", ctypes.c_void_p), ("materialCount", ctypes.c_int),
+                ("triLights", ctypes.c_void_p), ("triLightCount", ctypes.c_int), ("pointLights", ctypes.c_void_p), ("pointLightCount", ctypes.c_int),
+                ("spotLights", ctypes.c_void_p), ("spotLightCount", ctypes.c_int), ("dirLights", ctypes.c_void_p), ("dirLightCount", ctypes.c_int),
+                ("argb32", ctypes.c_void_p), ("argb32Count", ctypes.c_int), ("argb128", ctypes.c_void_p), ("argb128Count", ctypes.c_int),
+                ("nrm32", ctypes.c_void_p), ("nrm32Count", ctypes.c_int),
+                ("skyPixels4", ctypes.c_void_p), ("skyPixelCount", ctypes.c_int), ("skyW", ctypes.c_int), ("skyH", ctypes.c_int),
+                ("worldToSky", ctypes.c_float * 16), ("blueNoise", ctypes.c_void_p),
+                ("geometryEpsilon", ctypes.c_float), ("clampValue", ctypes.c_float),
+                ("pathCount", ctypes.c_int), ("stride", ctypes.c_int),
+                ("pathStates", ctypes.c_void_p), ("hits", ctypes.c_void_p), ("connections", ctypes.c_void_p), ("accumulator", ctypes.c_void_p),
+                ("R0", ctypes.c_uint), ("shift", ctypes.c_uint), ("pass_", ctypes.c_int), ("probePixelIdx", ctypes.c_int),
+                ("pathLength", ctypes.c_int), ("w", ctypes.c_int), ("h", ctypes.c_int), ("spreadAngle", ctypes.c_float), ("useNEE", ctypes.c_int),
+                ("countersOut", ctypes.c_uint * 12)]
+
+
+REF_SHADE_GPU = os.path.join(_HERE, "_ref", "libref_shade_gpu.so")
+
+
+def have_ref_shade_gpu():
+    return os.path.exists(REF_SHADE_GPU)
+
+
+def ref_shade_gpu(oracle, view, path_length, O4, D4, T4, hits, R0, shift, pass_, accumulator):
+    """Run the REFERENCE shadeKernel (unmodified source, sm_100a build) on n paths. Returns compacted extension rays,
+    shadow rays, the accumulator and the counters, like lh2b_shade_paths."""
+    sd = oracle.sd
+    rl = ctypes.CDLL(REF_SHADE_GPU)
+    tb = oracle.reference_tables(view)
+    n = O4.shape[0]
+    stride = 2 * n
+    ps = np.zeros((3 * stride, 4), np.float32)
+    ps[0:n], ps[stride:stride + n], ps[2 * stride:2 * stride + n] = O4, D4, T4
+    hb = np.zeros((stride, 4), np.float32)
+    hb[:n] = np.ascontiguousarray(hits).view(np.float32)
+    conn = np.zeros((6 * stride, 4), np.float32)
+    acc = np.ascontiguousarray(accumulator, np.float32).reshape(-1, 4).copy()
+    tris = [np.ascontiguousarray(t) for _, t in sd.meshes]
+    tp = (ctypes.c_void_p * len(tris))(*[t.ctypes.data for t in tris])
+    tc = np.array([len(t) for t in tris], np.int32)
+    im = np.array([m for m, _ in sd.instances], np.int32)
+    bn8 = np.fromfile(_BLUENOISE, dtype=np.uint8)
+    bn = np.zeros(65536 * 5, np.uint32)
+    bn[:65536] = bn8[:65536]; bn[65536:65536 + 131072] = bn8[65536:65536 + 131072]; bn[3 * 65536:3 * 65536 + 131072] = bn8[65536 + 131072:]
+    lights = [np.ascontiguousarray(a) for a in (sd.tri_lights, sd.point_lights, sd.spot_lights, sd.dir_lights)]
+    r = RefShadeIn()
+    p = lambda a: a.ctypes.data if a.size else None
+    r.meshCount, r.coreTris, r.triCounts = len(tris), ctypes.addressof(tp), tc.ctypes.data
+    r.instanceCount, r.instMesh, r.instInverse16 = len(sd.instances), im.ctypes.data, tb["inverses"].ctypes.data
+    r.materials128, r.materialCount = tb["materials"].ctypes.data, len(sd.materials)
+    r.triLights, r.triLightCount = p(lights[0]), len(lights[0])
+    r.pointLights, r.pointLightCount = p(lights[1]), len(lights[1])
+    r.spotLights, r.spotLightCount = p(lights[2]), len(lights[2])
+    r.dirLights, r.dirLightCount = p(lights[3]), len(lights[3])
+    r.argb32, r.argb32Count = tb["argb32"].ctypes.data, len(tb["argb32"])
+    r.argb128, r.argb128Count = tb["argb128"].ctypes.data, len(tb["argb128"])
+    r.nrm32, r.nrm32Count = tb["nrm32"].ctypes.data, len(tb["nrm32"])
+    r.skyPixels4, r.skyPixelCount = tb["sky"].ctypes.data, len(tb["sky"])
+    r.skyW, r.skyH = (sd.sky[1], sd.sky[2]) if sd.sky is not None else (0, 0)
+    r.worldToSky[:] = [float(x) for x in np.eye(4, dtype=np.float32).flat]
+    r.blueNoise = bn.ctypes.data
+    r.geometryEpsilon, r.clampValue = oracle.eps, oracle.clamp
+    r.pathCount, r.stride = n, stride
+    r.pathStates, r.hits, r.connections, r.accumulator = ps.ctypes.data, hb.ctypes.data, conn.ctypes.data, acc.ctypes.data
+    r.R0, r.shift, r.pass_, r.probePixelIdx, r.pathLength = R0, shift, pass_, -1, path_length
+    r.w, r.h = oracle.w, oracle.h
+    r.spreadAngle = float(np.ascontiguousarray(view)[0]["spreadAngle"])
+    r.useNEE = int(sum(len(l) for l in lights) > 0)
+    rc = rl.refshade_run(ctypes.byref(r))
+    if rc != 0:
+        raise RuntimeError("refshade_run failed")
+    cnt = list(r.countersOut)
+    n_ext, n_sh = cnt[5] - n, cnt[6]          # Counters.extensionRays started at n (see ref_shade_gpu.cu), shadowRays at 0
+    ext = dict(O=ps[n:n + n_ext], D=ps[stride + n:stride + n + n_ext], T=ps[2 * stride + n:2 * stride + n + n_ext])
+    sh = dict(O=conn[0:n_sh], D=conn[2 * stride:2 * stride + n_sh], E=conn[4 * stride:4 * stride + n_sh])
+    return ext, sh, acc.reshape(oracle.h, oracle.w, 4), cnt

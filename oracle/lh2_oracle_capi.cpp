@@ -141,14 +141,16 @@ static void ConvertMaterials( const OrcFrameIn& in, std::vector<orc::TexDesc>& t
 /* Renders one frame exactly as RenderCore::Render(view, converge) + FinalizeRender would; accumulates into
    accum (float4 per pixel; caller zeroes it for a Restart frame). rayCounts[0] = extension rays, [1] = shadow rays.
    seedsOut[0] = shiftSeed after, seedsOut[1] = camRNGseed after. records (optional): one PathRecord per path. */
-ORC_API void orc_render_frame( const OrcFrameIn* inp, float* accum, uint64_t* rayCounts, uint32_t* seedsOut, orc::PathRecord* records )
+struct FrameCtx { orc::RenderScene sc; std::vector<orc::TexDesc> tex; std::vector<uint32_t> bn; };
+
+static void SetupScene( const OrcFrameIn& in, FrameCtx& ctx )
 {
-	const OrcFrameIn& in = *inp;
-	orc::RenderScene sc;
+	orc::RenderScene& sc = ctx.sc;
+	std::vector<orc::TexDesc>& tex = ctx.tex;
+	std::vector<uint32_t>& bn = ctx.bn;
 	sc.geo = orc::Scene{ in.meshes, in.meshCount, in.instances, in.instanceCount, nullptr };
 	sc.geo.Prepare();
 	sc.coreTris = in.coreTris;
-	std::vector<orc::TexDesc> tex;
 	ConvertMaterials( in, tex, sc );
 	sc.triLights = in.triLights, sc.triLightCount = in.triLightCount;
 	sc.pointLights = in.pointLights, sc.pointLightCount = in.pointLightCount;
@@ -171,10 +173,18 @@ ORC_API void orc_render_frame( const OrcFrameIn* inp, float* accum, uint64_t* ra
 		for (int k = 0; k < 4; k++) o[k] = total[k] * (1.0f / (64 * 64));
 	}
 	memcpy( sc.worldToSky, in.worldToSky, sizeof( sc.worldToSky ) );
-	std::vector<uint32_t> bn( 65536 * 5, 0 );
+	bn.assign( 65536 * 5, 0 );
 	for (int i = 0; i < 65536; i++) bn[i] = in.blueNoiseBytes[i];
 	for (int i = 0; i < 128 * 128 * 8; i++) bn[i + 65536] = in.blueNoiseBytes[65536 + i], bn[i + 3 * 65536] = in.blueNoiseBytes[65536 + 131072 + i];
 	sc.blueNoise = bn.data();
+}
+
+ORC_API void orc_render_frame( const OrcFrameIn* inp, float* accum, uint64_t* rayCounts, uint32_t* seedsOut, orc::PathRecord* records )
+{
+	const OrcFrameIn& in = *inp;
+	FrameCtx ctx;
+	SetupScene( in, ctx );
+	orc::RenderScene& sc = ctx.sc;
 	orc::Settings st;
 	memset( &st, 0, sizeof( st ) );
 	st.w = in.w, st.h = in.h, st.spp = in.spp, st.pass = in.pass, st.sampleBase = in.sampleBase;
@@ -207,4 +217,93 @@ ORC_API void orc_render_frame( const OrcFrameIn* inp, float* accum, uint64_t* ra
 	for (size_t i = 0; i < (size_t)pixels * 4; i++) accum[i] += (float)acc[i];
 	if (rayCounts) { rayCounts[0] = rayCounts[1] = 0; for (int t = 0; t < threads; t++) rayCounts[0] += counts[t * 2], rayCounts[1] += counts[t * 2 + 1]; }
 	sc.geo.Release();
+}
+
+
+/* CUDAMaterial records (128 bytes each, core_settings.h:136-150) as the reference host code would build them
+   (rendercore.cpp:508-549); used to feed the reference shadeKernel harness. */
+ORC_API void orc_convert_materials( const OrcFrameIn* inp, uint32_t* out32PerMaterial )
+{
+	FrameCtx ctx;
+	SetupScene( *inp, ctx );
+	for (size_t i = 0; i < ctx.sc.materials.size(); i++)
+	{
+		const orc::Material& g = ctx.sc.materials[i];
+		uint32_t* o = out32PerMaterial + i * 32;
+		memset( o, 0, 128 );
+		o[0] = orc::FloatToHalf( g.color[0] ) | ((uint32_t)orc::FloatToHalf( g.color[1] ) << 16);
+		o[1] = orc::FloatToHalf( g.color[2] ) | ((uint32_t)orc::FloatToHalf( g.transmittance[0] ) << 16);
+		o[2] = g.baseZ, o[3] = g.flags;
+		memcpy( o + 4, g.params, 16 );
+		const orc::Material::Map* maps[6] = { &g.tex0, &g.tex1, &g.nmap0, &g.nmap1, &g.smap, &g.rmap };
+		for (int k = 0; k < 6; k++)
+		{
+			uint32_t* m = o + 8 + k * 4;
+			m[0] = ((uint32_t)maps[k]->w & 0xffff) | (((uint32_t)maps[k]->h & 0xffff) << 16);
+			m[1] = orc::FloatToHalf( maps[k]->uscale ) | ((uint32_t)orc::FloatToHalf( maps[k]->vscale ) << 16);
+			m[2] = orc::FloatToHalf( maps[k]->uoffs ) | ((uint32_t)orc::FloatToHalf( maps[k]->voffs ) << 16);
+			m[3] = maps[k]->addr;
+		}
+	}
+	ctx.sc.geo.Release();
+}
+
+/* The packed texel arrays and sky table exactly as the core keeps them, for the reference harness. */
+ORC_API void orc_scene_tables( const OrcFrameIn* inp, uint8_t* argb32, uint32_t* argb32Count, float* argb128, uint32_t* argb128Count,
+	uint8_t* nrm32, uint32_t* nrm32Count, float* sky4, uint32_t* skyCount, float* inverses16 )
+{
+	FrameCtx ctx;
+	SetupScene( *inp, ctx );
+	const orc::RenderScene& sc = ctx.sc;
+	*argb32Count = (uint32_t)(sc.argb32.size() / 4), *argb128Count = (uint32_t)(sc.argb128.size() / 4), *nrm32Count = (uint32_t)(sc.nrm32.size() / 4);
+	*skyCount = (uint32_t)(sc.sky.size() / 4);
+	if (argb32) memcpy( argb32, sc.argb32.data(), sc.argb32.size() );
+	if (argb128) memcpy( argb128, sc.argb128.data(), sc.argb128.size() * 4 );
+	if (nrm32) memcpy( nrm32, sc.nrm32.data(), sc.nrm32.size() );
+	if (sky4) memcpy( sky4, sc.sky.data(), sc.sky.size() * 4 );
+	if (inverses16) for (int i = 0; i < inp->instanceCount; i++)
+	{
+		float* o = inverses16 + i * 16;
+		memcpy( o, sc.geo.inverses + i * 12, 48 );
+		o[12] = o[13] = o[14] = 0, o[15] = 1;
+	}
+	ctx.sc.geo.Release();
+}
+
+/* shadeKernel on n paths (the stage-level oracle). Inputs/outputs mirror lh2b_shade_paths, except that outputs are
+   NOT compacted: slot i belongs to input path i, flags[i] bit0 = extension ray, bit1 = shadow ray, bit2 = deposit. */
+ORC_API void orc_shade_paths( const OrcFrameIn* inp, int pathLength, int n, const float* O4, const float* D4, const float* T4, const uint32_t* hits,
+	uint32_t R0, uint32_t shift, int pass, float* extO, float* extD, float* extT, float* shO, float* shD, float* shE, float* deposit4, uint8_t* flags )
+{
+	const OrcFrameIn& in = *inp;
+	FrameCtx ctx;
+	SetupScene( in, ctx );
+	orc::Settings st;
+	memset( &st, 0, sizeof( st ) );
+	st.w = in.w, st.h = in.h, st.spp = in.spp, st.pass = pass, st.sampleBase = in.sampleBase, st.shift = shift;
+	st.R0[pathLength] = R0;
+	st.geometryEpsilon = in.geometryEpsilon, st.clampValue = in.clampValue;
+	st.maxPathLength = in.maxPathLength, st.enoughBounces = in.enoughBounces;
+	memcpy( st.view, in.view, sizeof( st.view ) );
+	ParallelFor( n, in.threads, [&]( int a, int b ) {
+		for (int i = a; i < b; i++)
+		{
+			orc::PathState ps;
+			ps.O = orc::v3( O4[i * 4], O4[i * 4 + 1], O4[i * 4 + 2] ), ps.data = orc::FBits( O4[i * 4 + 3] );
+			ps.D = orc::v3( D4[i * 4], D4[i * 4 + 1], D4[i * 4 + 2] ), ps.packedN = orc::FBits( D4[i * 4 + 3] );
+			ps.T = orc::v3( T4[i * 4], T4[i * 4 + 1], T4[i * 4 + 2] ), ps.bsdfPdf = T4[i * 4 + 3];
+			orc::ShadeOut so;
+			orc::ShadeStep( ctx.sc, st, pathLength, ps, hits + i * 4, -1, so );
+			flags[i] = (so.extend ? 1 : 0) | (so.shadow ? 2 : 0) | (so.deposit ? 4 : 0);
+			float* o;
+			o = extO + i * 4, o[0] = so.next.O.x, o[1] = so.next.O.y, o[2] = so.next.O.z, o[3] = orc::BitsF( so.next.data );
+			o = extD + i * 4, o[0] = so.next.D.x, o[1] = so.next.D.y, o[2] = so.next.D.z, o[3] = orc::BitsF( so.next.packedN );
+			o = extT + i * 4, o[0] = so.next.T.x, o[1] = so.next.T.y, o[2] = so.next.T.z, o[3] = so.next.bsdfPdf;
+			o = shO + i * 4, o[0] = so.sO.x, o[1] = so.sO.y, o[2] = so.sO.z, o[3] = 0;
+			o = shD + i * 4, o[0] = so.sD.x, o[1] = so.sD.y, o[2] = so.sD.z, o[3] = so.sTmax;
+			o = shE + i * 4, o[0] = so.E.x, o[1] = so.E.y, o[2] = so.E.z, o[3] = orc::BitsF( so.pixelIdx );
+			o = deposit4 + i * 4, o[0] = so.contribution.x, o[1] = so.contribution.y, o[2] = so.contribution.z, o[3] = orc::BitsF( so.pixelIdx );
+		}
+	} );
+	ctx.sc.geo.Release();
 }

@@ -547,131 +547,169 @@ struct PathRecord		// optional per-path trace for path-by-path comparison with t
 	float firstShadow[8];	// first NEE connection: origin.xyz, valid flag, L.xyz, tmax
 };
 
-/* Trace one complete path; deposits into accum (float4 per pixel, double precision accumulate). */
-static inline void TracePath( const RenderScene& sc, const Settings& st, uint32_t pathIdx, double* accum, uint32_t* rayCounts /* [0]=extension, [1]=shadow */, PathRecord* rec )
+/* One path vertex, exactly the content of the device buffers. */
+struct PathState { V3 O; uint32_t data; V3 D; uint32_t packedN; V3 T; float bsdfPdf; };
+struct ShadeOut
 {
+	bool deposit; V3 contribution; uint32_t pixelIdx;		// direct accumulator write (sky / emissive)
+	bool shadow; V3 sO, sD; float sTmax; V3 E;				// NEE connection (pathtracer.h:206-209)
+	bool extend; PathState next;							// extension ray (pathtracer.h:234-237)
+	bool probe; int probeInst, probePrim; float probeDist;
+};
+
+/* shadeKernel for one path (pathtracer.h:54-238). hit = (u16|v16<<16, instance, primitive, t bits). */
+static inline void ShadeStep( const RenderScene& sc, const Settings& st, int pathLength, const PathState& in, const uint32_t* hit, int probePixelIdx, ShadeOut& out )
+{
+	memset( &out, 0, sizeof( out ) );
 	const uint32_t pixels = (uint32_t)st.w * st.h;
+	uint32_t data = in.data;
+	const uint32_t pathIdx = data >> 6;
 	const uint32_t pixelIdx = pathIdx % pixels, seedIdx = pathIdx + st.sampleBase * pixels;
 	const uint32_t sampleIdx = seedIdx / pixels + st.pass;
 	const bool useNEE = LightTotal( sc ) > 0;
-	V3 O, D;
-	GeneratePrimary( sc, st, pathIdx, O, D );
-	uint32_t data = (pathIdx << 6) + S_SPECULAR;
-	V3 throughput = v3( 1 );
-	float bsdfPdf = 1;
-	uint32_t packedLastN = 0;
-	double* px = accum + (size_t)pixelIdx * 4;
-	auto deposit = [&]( V3 c, double w ) { px[0] += c.x, px[1] += c.y, px[2] += c.z, px[3] += w; };
+	const V3 O = in.O, D = in.D;
+	V3 throughput = pathLength == 1 ? v3( 1 ) : in.T;
+	const float bsdfPdf = pathLength == 1 ? 1.0f : in.bsdfPdf;
+	out.pixelIdx = pixelIdx;
+	const int prim = (int)hit[2], instIdx = (int)hit[1];
+	if (prim == -1)
+	{
+		const float* m = sc.worldToSky;
+		const V3 tD = v3( -(m[0] * D.x + m[1] * D.y + m[2] * D.z), -(m[4] * D.x + m[5] * D.y + m[6] * D.z), -(m[8] * D.x + m[9] * D.y + m[10] * D.z) );
+		V3 contribution = throughput * SampleSky( sc, tD, (data & S_BOUNCED) != 0 ) * (1.0f / bsdfPdf);
+		ClampIntensity( contribution, st.clampValue );
+		FixNan( contribution );
+		out.deposit = true, out.contribution = contribution;
+		return;
+	}
+	const float hu = (float)(hit[0] & 65535) * (1.0f / 65535.0f), hv = (float)(hit[0] >> 16) * (1.0f / 65535.0f);
+	const float ht = BitsF( hit[3] );
+	if ((int)pixelIdx == probePixelIdx && pathLength == 1) out.probe = true, out.probeInst = instIdx, out.probePrim = prim, out.probeDist = ht;
+	const float* tri = sc.coreTris[sc.geo.instances[instIdx].mesh] + (size_t)prim * 52;
+	const float* invT = sc.geo.inverses + instIdx * 12;
+	Shading sh;
+	V3 N, iN, fN, T;
+	const V3 I = O + ht * D;
+	const float spreadAngle = st.view[13];
+	GetShadingData( sc, D, hu, hv, spreadAngle * ht, tri, invT, sh, N, iN, fN, T );
+	uint32_t seed = WangHash( seedIdx * 17 + st.R0[pathLength] );
+	if (sh.flags & 1)
+	{
+		if (pathLength < st.maxPathLength)
+		{
+			out.extend = true, out.next = in;
+			out.next.O = I + D * st.geometryEpsilon;
+			if (pathLength == 1) out.next.T = v3( 1 ), out.next.bsdfPdf = 1;
+			if (!isfinite( out.next.T.x + out.next.T.y + out.next.T.z )) out.next.T = v3( 0 );
+		}
+		return;
+	}
+	if (sh.color.x > 1.0f || sh.color.y > 1.0f || sh.color.z > 1.0f)
+	{
+		const float DdotNL = -dot( D, N );
+		if (DdotNL > 0)
+		{
+			V3 contribution = v3( 0 );
+			if (pathLength == 1 || (data & S_SPECULAR) || !useNEE) contribution = sh.color;
+			else
+			{
+				const V3 lastN = UnpackNormal( in.packedN );
+				const float area = tri[23];
+				const int ltriIdx = (int)FBits( tri[3] );
+				const float lightPdf = (ht * ht) / (fabsf( dot( D, N ) ) * area);
+				const float pickProb = LightPickProb( sc, ltriIdx, O, lastN, I );
+				if ((bsdfPdf + lightPdf * pickProb) > 0) contribution = throughput * sh.color * (1.0f / (bsdfPdf + lightPdf * pickProb));
+			}
+			ClampIntensity( contribution, st.clampValue );
+			FixNan( contribution );
+			out.deposit = true, out.contribution = contribution;
+		}
+		return;
+	}
+	if (data & S_BOUNCED) sh.params[0] |= 255u << 24;
+	const float roughness = Roughness( sh );
+	if (roughness <= 0.001f || Transmission( sh ) > 0.5f) data |= S_SPECULAR; else data &= ~(uint32_t)S_SPECULAR;
+	const float faceDir = (dot( D, N ) > 0) ? -1.0f : 1.0f;
+	if (faceDir == 1) sh.transmittance = v3( 0 );
+	throughput = throughput * (1.0f / bsdfPdf);
+	float r4[4];
+	if (sampleIdx < 64)
+		BlueNoise4( sc.blueNoise, ((seedIdx % st.w) + (st.shift & 127)) & 127, ((seedIdx / st.w) + (st.shift >> 24)) & 127, sampleIdx, 4 * pathLength - 4, r4 );
+	else r4[0] = RandomFloat( seed ), r4[1] = RandomFloat( seed ), r4[2] = RandomFloat( seed ), r4[3] = RandomFloat( seed );
+	if ((data & S_SPECULAR) == 0 && useNEE)
+	{
+		float pickProb = 0, lightPdf = 0;
+		V3 lightColor = v3( 0 );
+		V3 L = RandomPointOnLight( sc, r4[0], r4[1], I, fN * faceDir, pickProb, lightPdf, lightColor ) - I;
+		const float dist = sqrtf( dot( L, L ) );
+		L = L * (1.0f / dist);
+		const float NdotL = dot( L, fN * faceDir );
+		if (NdotL > 0 && lightPdf > 0)
+		{
+			float lobePdf;
+			const V3 f = EvaluateBSDF( sh, fN, L, lobePdf ) * roughness;
+			if (lobePdf > 0)
+			{
+				V3 contribution = throughput * f * lightColor * (NdotL / (pickProb * lightPdf + lobePdf));
+				FixNan( contribution );
+				ClampIntensity( contribution, st.clampValue );
+				out.shadow = true, out.sO = SafeOrigin( I, L, N, st.geometryEpsilon ), out.sD = L;
+				out.sTmax = dist - 2 * st.geometryEpsilon, out.E = contribution;
+			}
+		}
+	}
+	if ((data & st.enoughBounces) || pathLength == st.maxPathLength) return;
+	V3 R;
+	float newPdf;
+	bool specular = false;
+	(void)RandomFloat( seed );	// r5 argument of the reference SampleBSDF call (unused by the Lambert model)
+	const V3 bsdf = SampleBSDF( sh, fN, N, D * -1.0f, ht, r4[2], r4[3], R, newPdf, specular );
+	if (newPdf < 0.0001f || newPdf != newPdf) return;
+	if (specular) data |= S_SPECULAR;
+	const float p = ((data & S_SPECULAR) || ((data & S_BOUNCED) == 0)) ? 1 : fminf( 1.0f, fmaxf( fmaxf( bsdf.x, bsdf.y ), bsdf.z ) );
+	if (p < RandomFloat( seed )) return;
+	throughput = throughput * (1 / p);
+	const uint32_t packedNormal = PackNormal( fN * faceDir );
+	if (!(data & S_SPECULAR)) data |= (data & S_BOUNCED) ? S_BOUNCEDTWICE : S_BOUNCED; else data |= S_VIASPECULAR;
+	out.extend = true;
+	out.next.O = SafeOrigin( I, R, N, st.geometryEpsilon ), out.next.data = data;
+	out.next.D = R, out.next.packedN = packedNormal;
+	FixNan( throughput );
+	out.next.T = throughput * bsdf * fabsf( dot( fN, R ) ), out.next.bsdfPdf = newPdf;
+}
+
+/* Trace one complete path: generate, then (closest hit, shade, connect) per path length. Deposits into accum
+   (4 doubles per pixel). rayCounts[0] += extension rays, [1] += shadow rays. */
+static inline void TracePath( const RenderScene& sc, const Settings& st, uint32_t pathIdx, double* accum, uint32_t* rayCounts, PathRecord* rec )
+{
+	PathState ps;
+	memset( &ps, 0, sizeof( ps ) );
+	GeneratePrimary( sc, st, pathIdx, ps.O, ps.D );
+	ps.data = (pathIdx << 6) + S_SPECULAR, ps.T = v3( 1 ), ps.bsdfPdf = 1;
 	for (int pathLength = 1; pathLength <= st.maxPathLength; pathLength++)
 	{
 		Hit h;
-		const float o[3] = { O.x, O.y, O.z }, d[3] = { D.x, D.y, D.z };
+		const float o[3] = { ps.O.x, ps.O.y, ps.O.z }, d[3] = { ps.D.x, ps.D.y, ps.D.z };
 		const bool hit = ClosestHit( sc.geo, o, d, 0.0f, 1e34f, h );
 		rayCounts[0]++;
-		if (rec && pathLength == 1) PackHit( hit, h, rec->hit );
-		if (!hit)
+		uint32_t rec4[4];
+		PackHit( hit, h, rec4 );
+		if (rec && pathLength == 1) memcpy( rec->hit, rec4, 16 );
+		ShadeOut so;
+		ShadeStep( sc, st, pathLength, ps, rec4, -1, so );
+		double* px = accum + (size_t)so.pixelIdx * 4;
+		if (so.deposit) px[0] += so.contribution.x, px[1] += so.contribution.y, px[2] += so.contribution.z;
+		if (so.shadow)
 		{
-			const float* m = sc.worldToSky;
-			const V3 tD = v3( -(m[0] * D.x + m[1] * D.y + m[2] * D.z), -(m[4] * D.x + m[5] * D.y + m[6] * D.z), -(m[8] * D.x + m[9] * D.y + m[10] * D.z) );
-			V3 contribution = throughput * SampleSky( sc, tD, (data & S_BOUNCED) != 0 ) * (1.0f / bsdfPdf);
-			ClampIntensity( contribution, st.clampValue );
-			FixNan( contribution );
-			deposit( contribution, 0 );
-			return;
+			rayCounts[1]++;
+			const float s3[3] = { so.sO.x, so.sO.y, so.sO.z }, l3[3] = { so.sD.x, so.sD.y, so.sD.z };
+			if (rec && rec->firstShadow[3] == 0)
+				rec->firstShadow[0] = s3[0], rec->firstShadow[1] = s3[1], rec->firstShadow[2] = s3[2], rec->firstShadow[3] = 1,
+				rec->firstShadow[4] = l3[0], rec->firstShadow[5] = l3[1], rec->firstShadow[6] = l3[2], rec->firstShadow[7] = so.sTmax;
+			if (!Occluded( sc.geo, s3, l3, 0.0f, so.sTmax )) px[0] += so.E.x, px[1] += so.E.y, px[2] += so.E.z, px[3] += 1;
 		}
-		// the device path quantises the barycentrics to 16 bit in the hit record (.optix.cu:180, pathtracer.h:38-39)
-		const float hu = (float)(F2U( 65535.0f * h.u ) & 65535) * (1.0f / 65535.0f), hv = (float)(F2U( 65535.0f * h.v ) & 65535) * (1.0f / 65535.0f);
-		const float* tri = sc.coreTris[sc.geo.instances[h.inst].mesh] + (size_t)h.prim * 52;
-		const float* invT = sc.geo.inverses + h.inst * 12;
-		Shading sh;
-		V3 N, iN, fN, T;
-		const V3 I = O + h.t * D;
-		const float spreadAngle = st.view[13];
-		GetShadingData( sc, D, hu, hv, spreadAngle * h.t, tri, invT, sh, N, iN, fN, T );
-		uint32_t seed = WangHash( seedIdx * 17 + st.R0[pathLength] );
-		if (sh.flags & 1)
-		{
-			if (pathLength < st.maxPathLength) { O = I + D * st.geometryEpsilon; continue; }	// same direction, same state (pathtracer.h:113-124)
-			return;
-		}
-		if (sh.color.x > 1.0f || sh.color.y > 1.0f || sh.color.z > 1.0f)
-		{
-			const float DdotNL = -dot( D, N );
-			if (DdotNL > 0)
-			{
-				V3 contribution = v3( 0 );
-				if (pathLength == 1 || (data & S_SPECULAR) || !useNEE) contribution = sh.color;
-				else
-				{
-					const V3 lastN = UnpackNormal( packedLastN );
-					const float area = tri[23];
-					const int ltriIdx = (int)FBits( tri[3] );
-					const float lightPdf = (h.t * h.t) / (fabsf( dot( D, N ) ) * area);
-					const float pickProb = LightPickProb( sc, ltriIdx, O, lastN, I );
-					if ((bsdfPdf + lightPdf * pickProb) > 0) contribution = throughput * sh.color * (1.0f / (bsdfPdf + lightPdf * pickProb));
-				}
-				ClampIntensity( contribution, st.clampValue );
-				FixNan( contribution );
-				deposit( contribution, 0 );
-			}
-			return;
-		}
-		if (data & S_BOUNCED) sh.params[0] |= 255u << 24;
-		const float roughness = Roughness( sh );
-		if (roughness <= 0.001f || Transmission( sh ) > 0.5f) data |= S_SPECULAR; else data &= ~(uint32_t)S_SPECULAR;
-		const float faceDir = (dot( D, N ) > 0) ? -1.0f : 1.0f;
-		if (faceDir == 1) sh.transmittance = v3( 0 );
-		throughput = throughput * (1.0f / bsdfPdf);
-		float r4[4];
-		if (sampleIdx < 64)
-			BlueNoise4( sc.blueNoise, ((seedIdx % st.w) + (st.shift & 127)) & 127, ((seedIdx / st.w) + (st.shift >> 24)) & 127, sampleIdx, 4 * pathLength - 4, r4 );
-		else r4[0] = RandomFloat( seed ), r4[1] = RandomFloat( seed ), r4[2] = RandomFloat( seed ), r4[3] = RandomFloat( seed );
-		if ((data & S_SPECULAR) == 0 && useNEE)
-		{
-			float pickProb = 0, lightPdf = 0;
-			V3 lightColor = v3( 0 );
-			V3 L = RandomPointOnLight( sc, r4[0], r4[1], I, fN * faceDir, pickProb, lightPdf, lightColor ) - I;
-			const float dist = sqrtf( dot( L, L ) );
-			L = L * (1.0f / dist);
-			const float NdotL = dot( L, fN * faceDir );
-			if (NdotL > 0 && lightPdf > 0)
-			{
-				float lobePdf;
-				const V3 f = EvaluateBSDF( sh, fN, L, lobePdf ) * roughness;
-				if (lobePdf > 0)
-				{
-					V3 contribution = throughput * f * lightColor * (NdotL / (pickProb * lightPdf + lobePdf));
-					FixNan( contribution );
-					ClampIntensity( contribution, st.clampValue );
-					const V3 so = SafeOrigin( I, L, N, st.geometryEpsilon );
-					const float so3[3] = { so.x, so.y, so.z }, l3[3] = { L.x, L.y, L.z };
-					const float tmax = dist - 2 * st.geometryEpsilon;
-					rayCounts[1]++;
-					if (rec && rec->firstShadow[3] == 0)
-						rec->firstShadow[0] = so.x, rec->firstShadow[1] = so.y, rec->firstShadow[2] = so.z, rec->firstShadow[3] = 1,
-						rec->firstShadow[4] = L.x, rec->firstShadow[5] = L.y, rec->firstShadow[6] = L.z, rec->firstShadow[7] = tmax;
-					if (!Occluded( sc.geo, so3, l3, 0.0f, tmax )) deposit( contribution, 1 );
-				}
-			}
-		}
-		if ((data & st.enoughBounces) || pathLength == st.maxPathLength) return;
-		V3 R;
-		float newPdf;
-		bool specular = false;
-		(void)RandomFloat( seed );	// r5 argument of the reference SampleBSDF call (unused by the Lambert model)
-		const V3 bsdf = SampleBSDF( sh, fN, N, D * -1.0f, h.t, r4[2], r4[3], R, newPdf, specular );
-		if (newPdf < 0.0001f || newPdf != newPdf) return;
-		if (specular) data |= S_SPECULAR;
-		const float p = ((data & S_SPECULAR) || ((data & S_BOUNCED) == 0)) ? 1 : fminf( 1.0f, fmaxf( fmaxf( bsdf.x, bsdf.y ), bsdf.z ) );
-		if (p < RandomFloat( seed )) return;
-		throughput = throughput * (1 / p);
-		packedLastN = PackNormal( fN * faceDir );
-		if (!(data & S_SPECULAR)) data |= (data & S_BOUNCED) ? S_BOUNCEDTWICE : S_BOUNCED; else data |= S_VIASPECULAR;
-		O = SafeOrigin( I, R, N, st.geometryEpsilon );
-		D = R;
-		FixNan( throughput );
-		throughput = throughput * bsdf * fabsf( dot( fN, R ) );
-		bsdfPdf = newPdf;
+		if (!so.extend) return;
+		ps = so.next;
 	}
 }
 

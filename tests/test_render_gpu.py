@@ -90,10 +90,10 @@ def test_probe_and_stats():
     core.SetProbePos(W // 2, H // 2)
     core.Render(view, 1)
     st = core.GetCoreStats()
-    O, D = scenes.camera_rays(view, W, H)
-    i = W // 2 + (H // 2) * W
-    want = orc.closest_hits([m for m, _ in sd.meshes], sd.instances, O[i:i + 1], D[i:i + 1])[0]
+    oracle = orc.FrameOracle(sd, W, H, 1, 1e-3, 10.0, 3, 1)
+    _, rec = oracle.render(view, 1, records=True)
+    want = rec[W // 2 + (H // 2) * W]["hit"]       # primary hit record of the probed pixel (same jittered ray)
     assert (int(st["probedInstid"]), int(st["probedTriid"])) == (int(want[1]), int(want[2]))
-    assert abs(float(st["probedDist"]) - float(want[3:4].view(np.float32)[0])) < 0.05
+    assert abs(float(st["probedDist"]) / float(want[3:4].view(np.float32)[0]) - 1) < 1e-4
     assert st["primaryRayCount"] == W * H and st["totalRays"] == st["totalExtensionRays"] + st["totalShadowRays"]
     core.Shutdown()

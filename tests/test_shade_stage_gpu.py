@@ -1,0 +1,126 @@
+"""Stage-level parity of the CUDA shade kernel, path by path, against
+  (1) the REFERENCE's own shadeKernel compiled for sm_100a from /root/reference (oracle/_ref/libref_shade_gpu.so), and
+  (2) the CPU oracle's ShadeStep,
+on identical path states and hit records. Extension rays are matched by the path index they carry (O.w >> 6),
+shadow rays by pixel index (E.w). Both GPU kernels are fast-math builds, so values agree to a few ulp-scale
+relative error; discrete decisions may flip for isolated paths (bounded below)."""
+import numpy as np
+import pytest
+
+from lighthouse2_b200 import RenderCore, scenes
+from oracle import binding as orc
+
+pytestmark = pytest.mark.gpu
+W, H = 128, 72
+FLIP_TOL = 0.002     # fraction of paths allowed to take a different discrete branch
+VAL_TOL = 2e-3       # relative tolerance on ray / radiance values of matched paths (fast-math vs libm)
+
+
+def _setup(n_mat=6, lights=3):
+    sd = scenes.config2_scene(48, 32, n_materials=n_mat, light_quads=lights, floaters=300)
+    core = RenderCore()
+    core.SetTarget(W, H, 1)
+    core.Setting("epsilon", 1e-3)
+    sd.upload(core)
+    view = scenes.view_pyramid((0, 14, -60), (0, 0, 0), 45, W, H)
+    core.Render(view, 1)      # fixes spreadAngle for the hook
+    oracle = orc.FrameOracle(sd, W, H, 1, 1e-3, 10.0, 3, 1)
+    return sd, core, oracle, view
+
+
+def _primary_state(view):
+    O, D = scenes.camera_rays(view, W, H)
+    n = W * H
+    O4, D4 = O.copy(), D.copy()
+    O4[:, 3] = ((np.arange(n, dtype=np.uint32) << 6) | 1).view(np.float32)
+    T4 = np.ones((n, 4), np.float32)
+    return O4, D4, T4
+
+
+def _key(a):
+    return a[:, 3].view(np.uint32) >> 6
+
+
+def _match(a, b, key_a, key_b, fields, n_total, what):
+    ia, ib = np.argsort(key_a), np.argsort(key_b)
+    ka, kb = key_a[ia], key_b[ib]
+    common, pa, pb = np.intersect1d(ka, kb, return_indices=True)
+    flips = (len(ka) - len(common)) + (len(kb) - len(common))
+    assert flips <= max(4, FLIP_TOL * n_total), f"{what}: {flips} paths emitted by only one side ({len(ka)} vs {len(kb)})"
+    worst = 0.0
+    for f in fields:
+        xa, xb = a[f][ia][pa][:, :3].astype(np.float64), b[f][ib][pb][:, :3].astype(np.float64)
+        err = np.abs(xa - xb) / (1e-3 + np.abs(xb))
+        bad = (err > VAL_TOL).any(axis=1)
+        assert bad.mean() <= FLIP_TOL, f"{what}.{f}: {bad.sum()} of {len(bad)} matched rays differ by more than {VAL_TOL}"
+        worst = max(worst, float(np.median(err)))
+    return len(common), worst
+
+
+def _run_all(core, oracle, view, L, O4, D4, T4, hits, R0, shift):
+    acc0 = np.zeros((H, W, 4), np.float32)
+    got = core.ShadePaths(L, O4, D4, T4, hits, R0, shift, 0, acc0)
+    want = oracle.shade_paths(view, L, O4, D4, T4, hits, R0, shift, 0)
+    ref = orc.ref_shade_gpu(oracle, view, L, O4, D4, T4, hits, R0, shift, 0, acc0) if orc.have_ref_shade_gpu() else None
+    return got, want, ref
+
+
+def _check_level(core, oracle, view, L, O4, D4, T4, hits, R0, shift):
+    n = O4.shape[0]
+    (ext, sh, acc), want, ref = _run_all(core, oracle, view, L, O4, D4, T4, hits, R0, shift)
+    # (2) CPU oracle: uncompacted outputs + flags
+    fl = want["flags"]
+    oe = dict(O=want["extO"][(fl & 1) > 0], D=want["extD"][(fl & 1) > 0], T=want["extT"][(fl & 1) > 0])
+    os_ = dict(O=want["shO"][(fl & 2) > 0], D=want["shD"][(fl & 2) > 0], E=want["shE"][(fl & 2) > 0])
+    _match(ext, oe, _key(ext["O"]), _key(oe["O"]), ("O", "D", "T"), n, f"L{L} ext vs oracle")
+    _match(sh, os_, sh["E"][:, 3].view(np.uint32), os_["E"][:, 3].view(np.uint32), ("O", "D", "E"), n, f"L{L} shadow vs oracle")
+    dep = np.zeros((H * W, 4), np.float64)
+    d = want["deposit"][(fl & 4) > 0]
+    np.add.at(dep, d[:, 3].view(np.uint32), np.concatenate([d[:, :3], np.zeros((len(d), 1))], axis=1))
+    err = np.abs(acc.reshape(-1, 4)[:, :3] - dep[:, :3]) / (1e-3 + np.abs(dep[:, :3]))
+    assert ((err > VAL_TOL).any(axis=1)).mean() <= FLIP_TOL, f"L{L} accumulator vs oracle"
+    # (1) the reference kernel itself
+    if ref is not None:
+        rext, rsh, racc, cnt = ref
+        _match(ext, rext, _key(ext["O"]), _key(rext["O"]), ("O", "D", "T"), n, f"L{L} ext vs reference kernel")
+        _match(sh, rsh, sh["E"][:, 3].view(np.uint32), rsh["E"][:, 3].view(np.uint32), ("O", "D", "E"), n, f"L{L} shadow vs reference kernel")
+        err = np.abs(acc[..., :3] - racc[..., :3]) / (1e-3 + np.abs(racc[..., :3]))
+        assert ((err > VAL_TOL).any(axis=-1)).mean() <= FLIP_TOL, f"L{L} accumulator vs reference kernel"
+        # packed state words (flags, packed normal) must agree exactly on matched rays
+        ia, ib = np.argsort(_key(ext["O"])), np.argsort(_key(rext["O"]))
+        _, pa, pb = np.intersect1d(_key(ext["O"])[ia], _key(rext["O"])[ib], return_indices=True)
+        same_flags = ext["O"][ia][pa][:, 3].view(np.uint32) == rext["O"][ib][pb][:, 3].view(np.uint32)
+        assert same_flags.mean() > 1 - FLIP_TOL
+    return ext, sh
+
+
+def test_shade_three_path_lengths():
+    sd, core, oracle, view = _setup()
+    O4, D4, T4 = _primary_state(view)
+    shift = 0x5A17C3E1
+    for L in (1, 2, 3):
+        hits = core.TraceRays(O4, D4)
+        R0 = (0x9E3779B9 * L + L * 91771) & 0xFFFFFFFF
+        ext, sh = _check_level(core, oracle, view, L, O4, D4, T4, hits, R0, shift)
+        if L == 1:
+            assert len(ext["O"]) > W * H // 4 and len(sh["O"]) > W * H // 4
+        O4, D4, T4 = ext["O"], ext["D"], ext["T"]
+        if len(O4) == 0:
+            break
+    core.Shutdown()
+
+
+def test_shade_point_spot_directional_lights():
+    sd, core, oracle, view = _setup(3, 1)
+    from lighthouse2_b200 import abi
+    pl = np.zeros(2, abi.CorePointLight); pl["position"] = [(10, 12, 5), (-20, 9, -10)]; pl["radiance"] = [(300, 280, 250), (80, 120, 200)]
+    pl["energy"] = pl["radiance"].sum(axis=1)
+    sl = np.zeros(1, abi.CoreSpotLight); sl["position"] = (0, 25, -20); sl["direction"] = (0, -0.8, 0.6); sl["radiance"] = (900, 900, 700)
+    sl["cosInner"], sl["cosOuter"] = 0.95, 0.8
+    dl = np.zeros(1, abi.CoreDirectionalLight); dl["direction"] = (0.3, -0.9, 0.316); dl["radiance"] = (1.5, 1.4, 1.2); dl["energy"] = 4.1
+    sd.point_lights, sd.spot_lights, sd.dir_lights = pl, sl, dl
+    core.SetLights(sd.tri_lights, pl, sl, dl)
+    O4, D4, T4 = _primary_state(view)
+    hits = core.TraceRays(O4, D4)
+    _check_level(core, oracle, view, 1, O4, D4, T4, hits, 0x1234567, 0x0BADF00D)
+    core.Shutdown()
