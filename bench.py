@@ -1,0 +1,300 @@
+#!/usr/bin/env python
+"""bench.py - BASELINE.json headline metric on its configs[1] workload: a synthetic 1M-triangle static scene,
+1920x1080, primary + shadow rays only (path length 1: generate+extend, shade with NEE, connect, finalize),
+reported as Mrays/s (extend + shadow).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+ours:       a "step" is one Render() of the workload on every rank. `value` = rays of all ranks / max-over-ranks
+            device time of K steps (CUDA events on the core's launch stream, inputs resident in HBM).
+            `e2e` = the same metric through the public API with host buffers: the ViewPyramid goes in from host
+            memory and the finished RGBA32F frame is read back into pinned host memory every step.
+            N > 1 (torchrun, one process per GPU): every rank renders the full frame for its own sample index
+            (sample sharding, scene replicated, weak scaling) and the accumulators are summed on rank 0 with an
+            NCCL reduce - the only exchange the path has.
+reference:  the reference has no CPU (or any runnable) implementation of this path here (OptiX is closed and absent),
+            so this arm times the CPU oracle port of the path (oracle/, brute-force ray queries) on all host cores
+            over a bounded pixel crop of the same frame per step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H, SPP = 1920, 1080, 1
+NX, NZ = 1000, 500                     # 1000 x 500 cells x 2 = 1,000,000 terrain triangles (+ 2 light triangles)
+CAM_POS, CAM_TARGET, FOV = (0.0, 30.0, -80.0), (0.0, 0.0, 0.0), 40.0
+WORKLOAD = "synthetic 1M-triangle static scene, 1920x1080, primary+shadow rays only (configs[1])"
+METRIC, UNIT = "Mrays/s (extend+shadow)", "Mrays/s"
+EXTEND_BYTES_PER_RAY = 48              # 32 B ray (O4+D4) + 16 B hit record per extension ray
+
+
+def build_scene():
+    from lighthouse2_b200 import scenes
+    sd = scenes.config2_scene(NX, NZ, n_materials=1, light_quads=1, seed=0x12345678)
+    view = scenes.view_pyramid(CAM_POS, CAM_TARGET, FOV, W, H)
+    return sd, view
+
+
+class ClockSampler:
+    """nvidia-smi sampled every 200 ms while the timed region runs (recipe: /opt/skills/guides/B200_PROFILING.md)."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 - 0.05 <= t <= t1 + 0.15] or [r for _, r in self.rows]
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[0])), mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def oracle_crop_run(sd, view, crop_w, crop_h, threads):
+    """One pass of the CPU oracle over a centred crop_w x crop_h pixel crop of the 1080p frame (same rays as the GPU
+    frame for those pixels). Returns (rays, seconds)."""
+    import numpy as np
+    from oracle import binding as orc
+    # a crop keeps the pixel footprint: render the sub-window by shifting the view corners
+    v = view.copy()
+    p1, p2, p3 = (np.asarray(view[0][k], np.float64) for k in ("p1", "p2", "p3"))
+    right, up = (p2 - p1) / W, (p3 - p1) / H
+    x0, y0 = (W - crop_w) // 2, (H - crop_h) // 2
+    n1 = p1 + right * x0 + up * y0
+    v["p1"], v["p2"], v["p3"] = n1, n1 + right * crop_w, n1 + up * crop_h
+    o = orc.FrameOracle(sd, crop_w, crop_h, 1, 1e-3, 10.0, 1, 1, threads=threads)
+    t0 = time.perf_counter()
+    o.render(v, 1)
+    dt = time.perf_counter() - t0
+    return sum(o.ray_counts), dt
+
+
+def calibrate_crop(sd, view, threads, target_seconds):
+    """Pick a crop whose oracle pass takes about target_seconds on this host."""
+    rays, dt = oracle_crop_run(sd, view, 16, 8, threads)
+    per_pixel = dt / (16 * 8)
+    pixels = max(64, int(target_seconds / max(per_pixel, 1e-9)))
+    ch = max(4, int((pixels * 9 / 16) ** 0.5))
+    cw = max(8, ch * 16 // 9)
+    return min(cw, W), min(ch, H)
+
+
+def run_reference(args, rank, world):
+    """--impl reference: CPU oracle port on all host cores, bounded crop per step. Rank 0 only."""
+    if rank != 0:
+        return
+    from oracle import binding as orc
+    orc.build()
+    sd, view = build_scene()
+    threads = os.cpu_count() or 1
+    budget = 150.0 / max(1, args.steps + args.warmup)
+    cw, ch = calibrate_crop(sd, view, threads, min(max(budget, 0.5), 8.0))
+    for _ in range(args.warmup):
+        oracle_crop_run(sd, view, cw, ch, threads)
+    rays, secs = 0, 0.0
+    for _ in range(args.steps):
+        r, dt = oracle_crop_run(sd, view, cw, ch, threads)
+        rays, secs = rays + r, secs + dt
+    value = rays / secs / 1e6
+    sample = f"{cw}x{ch}-pixel centre crop of the 1920x1080 frame per step ({rays // max(1, args.steps)} rays), brute-force closest hit over 1,000,002 triangles"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "the reference ships no runnable implementation of this path (OptiX closed, no CPU tracer): "
+                   "CPU oracle port timed instead", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+def run_ours(args, rank, world, local_rank):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from lighthouse2_b200 import RenderCore
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the core has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    sd, view = build_scene()
+    core = RenderCore(local_rank)
+    core.SetTarget(W, H, SPP)
+    core.Setting("epsilon", 1e-3)
+    core.Setting("clampValue", 10.0)
+    core.Setting("maxPathLength", 1)            # primary + shadow rays only
+    sd.upload(core)
+    bvh = core.GetBvhStats(0)
+    if world > 1:
+        core.SetSampleShard(rank * SPP, world * SPP)
+
+    class _Cai:
+        def __init__(self, ptr, shape):
+            self.__cuda_array_interface__ = {"shape": shape, "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+    acc_ptr, _ = core.AccumulatorDevicePtr()
+    acc_t = torch.as_tensor(_Cai(acc_ptr, (H, W, 4)), device=f"cuda:{local_rank}") if world > 1 else None
+    host_img = torch.empty((H, W, 4), dtype=torch.float32, pin_memory=True)
+    host_np = host_img.numpy()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        core.Render(view, 1)                     # Restart: clears the accumulator, renders, finalizes, synchronises
+        if world > 1:
+            dist.reduce(acc_t, dst=0, op=dist.ReduceOp.SUM)
+            torch.cuda.current_stream().synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    # ---- device-timed run -----------------------------------------------------------------------------
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stream = torch.cuda.ExternalStream(core.Stream(), device=f"cuda:{local_rank}")
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    rays = 0
+    stage = {"generateExtendMs": 0.0, "shadeMs": 0.0, "connectMs": 0.0, "finalizeMs": 0.0}
+    barrier()
+    t0 = time.time()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+        fs = core.GetFrameStats()
+        rays += int(fs["primaryRays"]) + int(fs["shadowRays"])
+        for k in stage:
+            stage[k] += float(fs[k])
+    ev1.record(stream)
+    barrier()
+    t1 = time.time()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop(t0, t1) if sampler else None
+    # ---- end-to-end run through the public API with host buffers -----------------------------------------
+    barrier()
+    e0 = time.perf_counter()
+    e_rays = 0
+    for _ in range(args.steps):
+        step()
+        if rank == 0:
+            if world > 1:
+                core._check(core._lib.lh2b_finalize_external(core._h, acc_ptr, world * SPP))
+            core.ReadPixels(host_np)            # device -> pinned host, 33 MB
+        fs = core.GetFrameStats()
+        e_rays += int(fs["primaryRays"]) + int(fs["shadowRays"])
+    barrier()
+    e_secs = time.perf_counter() - e0
+    if world > 1:
+        t = torch.tensor([ms, e_secs, float(rays), float(e_rays)], dtype=torch.float64, device=f"cuda:{local_rank}")
+        mx = t.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = t.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        ms, e_secs, rays, e_rays = mx[0].item(), mx[1].item(), sm[2].item(), sm[3].item()
+    if rank != 0:
+        core.Shutdown()
+        return
+    value = rays / (ms * 1e-3) / 1e6
+    e2e = e_rays / e_secs / 1e6
+    # ---- roofline of the dominant kernel (generate+extend), live per-launch time from CUDA events on the launch stream
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    ge_ms = stage["generateExtendMs"] / args.steps
+    achieved = W * H * SPP * EXTEND_BYTES_PER_RAY / (ge_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("generateExtendKernel_dram_bytes_per_launch")
+    roofline = {"kernel": "generateExtendKernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src, "ms_per_launch": ge_ms, "mrays_per_s": W * H * SPP / ge_ms / 1e3,
+                "note": "BVH traversal is latency/issue-bound, not HBM-bound (SURVEY.md 8d): the 67 MB CWBVH is L2-resident; "
+                        "see profiles/ for issue-slot and L1/L2 hit-rate evidence"}
+    # ---- CPU baseline: oracle port on this box's host cores, bounded crop (rank 0, N = 1 only) ------------------
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import binding as orc
+        orc.build()
+        threads = os.cpu_count() or 1
+        cw, ch = calibrate_crop(sd, view, threads, 12.0)
+        r, dt = oracle_crop_run(sd, view, cw, ch, threads)
+        cpu = {"value": r / dt / 1e6, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"{cw}x{ch}-pixel centre crop of the same frame ({r} rays, {dt:.1f} s), brute-force closest hit over 1,000,002 triangles"}
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "triangles": int(bvh["triangles"]) + 2, "resolution": [W, H], "spp_per_gpu": SPP,
+                   "path_length": 1, "bvh": "CWBVH (8-wide, quantised)", "bvh_nodes": int(bvh["nodes"]),
+                   "parallelism": "1 GPU" if world == 1 else f"sample-sharded x{world}, scene replicated, NCCL reduce of the accumulator to rank 0",
+                   "l2": "no explicit flush: per-step working set (path state 0.2 GB + scene 0.3 GB) exceeds the 126 MB L2; the 67 MB BVH "
+                         "staying L2-resident across frames is the steady state of the renderer"},
+        "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()},
+        "rays_per_step": rays / args.steps,
+        "roofline": roofline, "cpu_baseline": cpu,
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 68, "d2h_bytes_per_step": W * H * 16, "ms_per_step": e_secs / args.steps * 1e3},
+        "gpu_launches": 4 * args.steps, "clocks": clocks}
+    print(json.dumps(out))
+    core.Shutdown()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank, world, local_rank = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -48,6 +48,8 @@ def _match(a, b, key_a, key_b, fields, n_total, what):
     flips = (len(ka) - len(common)) + (len(kb) - len(common))
     assert flips <= max(4, FLIP_TOL * n_total), f"{what}: {flips} paths emitted by only one side ({len(ka)} vs {len(kb)})"
     worst = 0.0
+    if len(common) == 0:
+        return 0, 0.0
     for f in fields:
         xa, xb = a[f][ia][pa][:, :3].astype(np.float64), b[f][ib][pb][:, :3].astype(np.float64)
         err = np.abs(xa - xb) / (1e-3 + np.abs(xb))
