@@ -173,6 +173,7 @@ int lh2b_create( lh2b_core** out, int device )
 		core->stats.deviceName = new char[strlen( prop.name ) + 1];
 		strcpy( core->stats.deviceName, prop.name );
 		core->stats.probedTriid = -1;
+		core->queryCounter.Resize( 4 );
 		InitRenderState( core.get() );
 		*out = core.release();
 	}
@@ -248,7 +249,7 @@ int lh2b_trace_rays_device( lh2b_core* core, const void* dO, const void* dD, int
 	if (!core->sceneReady) throw CoreError( "trace: FinalizeInstances has not been called" );
 	if (repeat < 1) repeat = 1;
 	if (msOut) CUDA_CHECK( cudaEventRecord( core->evA, core->stream ) );
-	for (int r = 0; r < repeat; r++) LaunchExtend( core->scene, (const float4*)dO, (const float4*)dD, (float4*)dHits, n, core->stream );
+	for (int r = 0; r < repeat; r++) LaunchExtend( core->scene, (const float4*)dO, (const float4*)dD, (float4*)dHits, n, core->queryCounter.ptr, (int)core->stats.SMcount, core->stream );
 	CUDA_CHECK( cudaGetLastError() );
 	if (msOut)
 	{
@@ -265,7 +266,7 @@ int lh2b_trace_shadow_rays_device( lh2b_core* core, const void* dO, const void* 
 	if (!core->sceneReady) throw CoreError( "trace: FinalizeInstances has not been called" );
 	if (repeat < 1) repeat = 1;
 	if (msOut) CUDA_CHECK( cudaEventRecord( core->evA, core->stream ) );
-	for (int r = 0; r < repeat; r++) LaunchOcclude( core->scene, (const float4*)dO, (const float4*)dD, (uint8_t*)dOcc, n, core->stream );
+	for (int r = 0; r < repeat; r++) LaunchOcclude( core->scene, (const float4*)dO, (const float4*)dD, (uint8_t*)dOcc, n, core->queryCounter.ptr, (int)core->stats.SMcount, core->stream );
 	CUDA_CHECK( cudaGetLastError() );
 	if (msOut)
 	{
@@ -283,7 +284,7 @@ int lh2b_trace_rays( lh2b_core* core, const float* origins, const float* directi
 	core->qO.Upload( (const float4*)origins, n, core->stream );
 	core->qD.Upload( (const float4*)directions, n, core->stream );
 	core->qHits.Resize( n );
-	LaunchExtend( core->scene, core->qO.ptr, core->qD.ptr, core->qHits.ptr, n, core->stream );
+	LaunchExtend( core->scene, core->qO.ptr, core->qD.ptr, core->qHits.ptr, n, core->queryCounter.ptr, (int)core->stats.SMcount, core->stream );
 	CUDA_CHECK( cudaGetLastError() );
 	CUDA_CHECK( cudaMemcpyAsync( hitsOut, core->qHits.ptr, (size_t)n * 16, cudaMemcpyDeviceToHost, core->stream ) );
 	CUDA_CHECK( cudaStreamSynchronize( core->stream ) );
@@ -297,7 +298,7 @@ int lh2b_trace_shadow_rays( lh2b_core* core, const float* origins, const float* 
 	core->qO.Upload( (const float4*)origins, n, core->stream );
 	core->qD.Upload( (const float4*)directions, n, core->stream );
 	core->qOcc.Resize( n );
-	LaunchOcclude( core->scene, core->qO.ptr, core->qD.ptr, core->qOcc.ptr, n, core->stream );
+	LaunchOcclude( core->scene, core->qO.ptr, core->qD.ptr, core->qOcc.ptr, n, core->queryCounter.ptr, (int)core->stats.SMcount, core->stream );
 	CUDA_CHECK( cudaGetLastError() );
 	CUDA_CHECK( cudaMemcpyAsync( occludedOut, core->qOcc.ptr, (size_t)n, cudaMemcpyDeviceToHost, core->stream ) );
 	CUDA_CHECK( cudaStreamSynchronize( core->stream ) );

@@ -54,6 +54,7 @@ struct lh2b_core
 	// scratch for the host-buffer query entry points
 	lh2b::DevBuf<float4> qO, qD, qHits;
 	lh2b::DevBuf<uint8_t> qOcc;
+	lh2b::DevBuf<uint32_t> queryCounter;	// work counter of the persistent query kernels
 	// settings
 	int bvhBuilder = 0;				// 0: GPU LBVH (default), 1: host binned SAH
 	float geometryEpsilon = 1e-4f, clampValue = 10.0f;	// reference defaults: stageClampValue(10) at rendercore.cpp:243; epsilon comes from RenderSystem (rendersystem.h:65-72)

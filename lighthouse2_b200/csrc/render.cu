@@ -163,13 +163,13 @@ static void RenderFrame( lh2b_core* core, const lh2abi::ViewPyramid& view )
 		const PathSet in = { core->pathBuf[(L - 1) & 1][0].ptr, core->pathBuf[(L - 1) & 1][1].ptr, core->pathBuf[(L - 1) & 1][2].ptr };
 		const PathSet out = { core->pathBuf[L & 1][0].ptr, core->pathBuf[L & 1][1].ptr, core->pathBuf[L & 1][2].ptr };
 		CUDA_CHECK( cudaEventRecord( core->events[4 * L], s ) );
-		if (L == 1) LaunchGenerateExtend( core->scene, p, in, core->hitBuf.ptr, sm, s );
-		else LaunchExtendCounted( core->scene, in, core->hitBuf.ptr, &core->counters.ptr->extensionRays[L - 1], stride, sm, s );
+		if (L == 1) LaunchGenerateExtend( core->scene, p, in, core->hitBuf.ptr, &core->counters.ptr->workFetch[2 * L], sm, s );
+		else LaunchExtendCounted( core->scene, in, core->hitBuf.ptr, &core->counters.ptr->extensionRays[L - 1], &core->counters.ptr->workFetch[2 * L], stride, sm, s );
 		CUDA_CHECK( cudaEventRecord( core->events[4 * L + 1], s ) );
 		const uint32_t R0 = RandomUInt( core->camRNGseed ) + L * 91771;
 		LaunchShade( p, in, out, core->hitBuf.ptr, conn, L, R0, useNEE, stride, sm, s );
 		CUDA_CHECK( cudaEventRecord( core->events[4 * L + 2], s ) );
-		if (useNEE) LaunchConnect( core->scene, conn, core->accumulator.ptr, &core->counters.ptr->shadowRays[L], stride, sm, s );
+		if (useNEE) LaunchConnect( core->scene, conn, core->accumulator.ptr, &core->counters.ptr->shadowRays[L], &core->counters.ptr->workFetch[2 * L + 1], stride, sm, s );
 		CUDA_CHECK( cudaEventRecord( core->events[4 * L + 3], s ) );
 	}
 	CUDA_CHECK( cudaGetLastError() );
@@ -239,6 +239,11 @@ int lh2b_setting( lh2b_core* core, const char* name, float value )
 	else if (!strcmp( name, "maxPathLength" )) core->maxPathLength = value < 1 ? 1 : (value > LH2B_MAXPATHLENGTH ? LH2B_MAXPATHLENGTH : (int)value);
 	else if (!strcmp( name, "maxDiffuseBounces" )) core->enoughBounces = value <= 0 ? 0 : (value < 2 ? S_BOUNCED : S_BOUNCEDTWICE);
 	else if (!strcmp( name, "bvhBuilder" )) core->bvhBuilder = (int)value;
+	else if (!strcmp( name, "traversalVariant" )) g_traversalVariant = (int)value;
+	else if (!strcmp( name, "wideBlocksPerSM" )) g_wideBlocksPerSM = value < 1 ? 1 : (int)value;
+	else if (!strcmp( name, "triThreshold" )) g_triThreshold = (int)value;
+	else if (!strcmp( name, "triThresholdShadow" )) g_triThresholdShadow = (int)value;
+	else if (!strcmp( name, "refillThreshold" )) g_refillThreshold = (int)value;
 	// unknown names are ignored
 	API_END
 }

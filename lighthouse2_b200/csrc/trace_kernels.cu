@@ -7,6 +7,7 @@
 #include "kernels.h"
 #include "render_types.h"
 #include "traverse.cuh"
+#include "traverse_wide.cuh"
 
 namespace lh2b
 {
@@ -134,6 +135,167 @@ __global__ void __launch_bounds__( 128 ) connectKernel( const DevScene scene, co
 	}
 }
 
+/* ---- persistent warp-cooperative variants (single identity instance: no top level) ------------------------- */
+
+struct BufferRaySource
+{
+	const float4* __restrict__ O4; const float4* __restrict__ D4; bool shadow;
+	__device__ __forceinline__ bool Load( const uint32_t i, WideRay& r ) const
+	{
+		const float4 o = O4[i], d = D4[i];
+		r.O = make_float3( o.x, o.y, o.z ), r.D = make_float3( d.x, d.y, d.z );
+		r.tmin = 0.0f, r.tmax = shadow ? d.w : 1e34f;
+		return true;
+	}
+};
+
+struct HitBufferSink
+{
+	float4* __restrict__ hits;
+	__device__ __forceinline__ void Closest( const uint32_t i, const bool hit, const TraceResult& r ) const { hits[i] = PackHit( hit, r ); }
+	__device__ __forceinline__ void AnyHit( const uint32_t, const bool ) const {}
+};
+
+struct OccludedFlagSink
+{
+	uint8_t* __restrict__ flags;
+	__device__ __forceinline__ void Closest( const uint32_t, const bool, const TraceResult& ) const {}
+	__device__ __forceinline__ void AnyHit( const uint32_t i, const bool occluded ) const { flags[i] = occluded ? 1 : 0; }
+};
+
+struct ConnectSink
+{
+	const float4* __restrict__ E4; float4* __restrict__ accumulator;
+	__device__ __forceinline__ void Closest( const uint32_t, const bool, const TraceResult& ) const {}
+	__device__ __forceinline__ void AnyHit( const uint32_t i, const bool occluded ) const
+	{
+		if (occluded) return;
+		const float4 e = E4[i];
+		atomicAdd( accumulator + __float_as_int( e.w ), make_float4( e.x, e.y, e.z, 1 ) );
+	}
+};
+
+/* Primary rays: work items are 8x4 pixel tiles per warp (coherent rays per warp), per sample. */
+__device__ __forceinline__ void GeneratePrimary( const RenderParams& p, const uint32_t pathIdx, float3& O, float3& D )
+{
+	const uint32_t pixels = p.w * p.h;
+	const uint32_t pixelIdx = pathIdx % pixels;
+	const uint32_t seedIdx = pathIdx + p.sampleBase * pixels;
+	const uint32_t sampleIdx = seedIdx / pixels + p.pass;
+	uint32_t seed = WangHashT( seedIdx * 16789 + p.pass * 1791 );
+	const int sx = pixelIdx % p.w, sy = pixelIdx / p.w;
+	float4 r4;
+	if (sampleIdx < 64)
+	{
+		const int x = (sx + (p.shift & 127)) & 127, y = (sy + (p.shift >> 24)) & 127;
+		const uint32_t* bn = p.blueNoise;
+		const uint4 rank = *(const uint4*)(bn + (x + y * 128) * 8 + 65536 * 3);
+		const uint32_t v0 = bn[0 + ((sampleIdx ^ rank.x) & 255) * 256], v1 = bn[1 + ((sampleIdx ^ rank.y) & 255) * 256];
+		const uint32_t v2 = bn[2 + ((sampleIdx ^ rank.z) & 255) * 256], v3 = bn[3 + ((sampleIdx ^ rank.w) & 255) * 256];
+		const uint4 scr = *(const uint4*)(bn + (x + y * 128) * 8 + 65536);
+		r4 = make_float4( (0.5f + (int)(v0 ^ scr.x)) * (1.0f / 256.0f), (0.5f + (int)(v1 ^ scr.y)) * (1.0f / 256.0f),
+			(0.5f + (int)(v2 ^ scr.z)) * (1.0f / 256.0f), (0.5f + (int)(v3 ^ scr.w)) * (1.0f / 256.0f) );
+	}
+	else r4.x = RandomFloatT( seed ), r4.y = RandomFloatT( seed ), r4.z = RandomFloatT( seed ), r4.w = RandomFloatT( seed );
+	const float blade = (float)(int)(r4.x * 9);
+	float r1 = r4.z, r2 = (r4.x - blade * (1.0f / 9.0f)) * 9.0f;
+	float x1, y1, x2, y2;
+	const float PI_T = 3.14159265358979323846264f;
+	__sincosf( blade * PI_T / 4.5f, &x1, &y1 );
+	__sincosf( (blade + 1.0f) * PI_T / 4.5f, &x2, &y2 );
+	if ((r1 + r2) > 1) r1 = 1.0f - r1, r2 = 1.0f - r2;
+	const float xr = x1 * r1 + x2 * r2, yr = y1 * r1 + y2 * r2;
+	const float ap = p.posLensSize.w;
+	O = make_float3( p.posLensSize.x + ap * (p.right.x * xr + p.up.x * yr), p.posLensSize.y + ap * (p.right.y * xr + p.up.y * yr),
+		p.posLensSize.z + ap * (p.right.z * xr + p.up.z * yr) );
+	float fu, fv;
+	if (p.distortion == 0) fu = ((float)sx + r4.y) * (1.0f / p.w), fv = ((float)sy + r4.w) * (1.0f / p.h);
+	else
+	{
+		const float tx = sx / (float)p.w - 0.5f, ty = sy / (float)p.h - 0.5f;
+		const float rr = tx * tx + ty * ty;
+		const float rq = sqrtf( rr ) * (1.0f + p.distortion * rr + p.distortion * rr * rr);
+		const float theta = atan2f( tx, ty );
+		const float bx = (sinf( theta ) * rq + 0.5f) * p.w, by = (cosf( theta ) * rq + 0.5f) * p.h;
+		fu = (bx + r4.y) / (float)p.w, fv = (by + r4.w) / (float)p.h;
+	}
+	D = make_float3( p.p1.x + fu * p.right.x + fv * p.up.x - O.x, p.p1.y + fu * p.right.y + fv * p.up.y - O.y, p.p1.z + fu * p.right.z + fv * p.up.z - O.z );
+	const float il = rsqrtf( D.x * D.x + D.y * D.y + D.z * D.z );
+	D.x *= il, D.y *= il, D.z *= il;
+}
+
+struct TiledPrimarySource
+{
+	const RenderParams* p; float4* __restrict__ outO; float4* __restrict__ outD; uint32_t* __restrict__ pathOf;	// pathOf: smem-free mapping kept in registers by the sink
+	uint32_t tilesX, itemsPerSample;
+	__device__ __forceinline__ uint32_t PathOf( const uint32_t work ) const
+	{
+		const uint32_t s = work / itemsPerSample, w = work - s * itemsPerSample;
+		const uint32_t tile = w >> 5, l = w & 31;
+		const uint32_t x = (tile % tilesX) * 8 + (l & 7), y = (tile / tilesX) * 4 + (l >> 3);
+		if (x >= (uint32_t)p->w || y >= (uint32_t)p->h) return 0xffffffffu;
+		return x + y * p->w + s * (p->w * p->h);
+	}
+	__device__ __forceinline__ bool Load( const uint32_t work, WideRay& r ) const
+	{
+		const uint32_t pathIdx = PathOf( work );
+		if (pathIdx == 0xffffffffu) return false;
+		GeneratePrimary( *p, pathIdx, r.O, r.D );
+		r.tmin = 0.0f, r.tmax = 1e34f;
+		outO[pathIdx] = make_float4( r.O.x, r.O.y, r.O.z, __uint_as_float( (pathIdx << 6) + 1 /* S_SPECULAR */ ) );
+		outD[pathIdx] = make_float4( r.D.x, r.D.y, r.D.z, 0 );
+		return true;
+	}
+};
+
+struct TiledHitSink
+{
+	const TiledPrimarySource* src; float4* __restrict__ hits;
+	__device__ __forceinline__ void Closest( const uint32_t work, const bool hit, const TraceResult& r ) const { hits[src->PathOf( work )] = PackHit( hit, r ); }
+	__device__ __forceinline__ void AnyHit( const uint32_t, const bool ) const {}
+};
+
+__global__ void __launch_bounds__( WIDE_BLOCK ) wideGenerateExtendKernel( const DevScene scene, const RenderParams p, const PathSet out, float4* __restrict__ hits,
+	uint32_t* workCounter, const WideTuning tune )
+{
+	TiledPrimarySource src;
+	src.p = &p, src.outO = out.O, src.outD = out.D, src.pathOf = nullptr;
+	src.tilesX = (p.w + 7) / 8;
+	src.itemsPerSample = src.tilesX * ((p.h + 3) / 4) * 32;
+	TiledHitSink sink = { &src, hits };
+	TraverseWide<false>( scene.instances[0], src, sink, src.itemsPerSample * p.spp, workCounter, tune );
+}
+
+__global__ void __launch_bounds__( WIDE_BLOCK ) wideExtendKernel( const DevScene scene, const float4* __restrict__ O4, const float4* __restrict__ D4,
+	float4* __restrict__ hits, const uint32_t* __restrict__ countPtr, const uint32_t fixedCount, uint32_t* workCounter, const WideTuning tune )
+{
+	BufferRaySource src = { O4, D4, false };
+	HitBufferSink sink = { hits };
+	TraverseWide<false>( scene.instances[0], src, sink, countPtr ? *countPtr : fixedCount, workCounter, tune );
+}
+
+__global__ void __launch_bounds__( WIDE_BLOCK ) wideOccludeKernel( const DevScene scene, const float4* __restrict__ O4, const float4* __restrict__ D4,
+	uint8_t* __restrict__ flags, const uint32_t fixedCount, uint32_t* workCounter, const WideTuning tune )
+{
+	BufferRaySource src = { O4, D4, true };
+	OccludedFlagSink sink = { flags };
+	TraverseWide<true>( scene.instances[0], src, sink, fixedCount, workCounter, tune );
+}
+
+__global__ void __launch_bounds__( WIDE_BLOCK ) wideConnectKernel( const DevScene scene, const PathSet conn, float4* __restrict__ accumulator,
+	const uint32_t* __restrict__ countPtr, uint32_t* workCounter, const WideTuning tune )
+{
+	BufferRaySource src = { conn.O, conn.D, true };
+	ConnectSink sink = { conn.T, accumulator };
+	TraverseWide<true>( scene.instances[0], src, sink, *countPtr, workCounter, tune );
+}
+
+static uint32_t PersistentGrid( uint32_t maxItems, int smCount, int blocksPerSM )
+{
+	const uint32_t need = (maxItems + WIDE_BLOCK - 1) / WIDE_BLOCK, cap = (uint32_t)(smCount * blocksPerSM);
+	return need < cap ? (need ? need : 1) : cap;
+}
+
 static uint32_t GridFor( uint32_t maxItems, int smCount )
 {
 	uint32_t blocks = (maxItems + 127) / 128;
@@ -141,31 +303,56 @@ static uint32_t GridFor( uint32_t maxItems, int smCount )
 	return blocks > cap ? cap : (blocks ? blocks : 1);
 }
 
-void LaunchGenerateExtend( const DevScene& scene, const RenderParams& p, const PathSet& out, float4* hits, int smCount, cudaStream_t s )
+int g_traversalVariant = 1;	// 1: persistent warp-cooperative kernels for single-instance scenes, 0: per-thread while-while everywhere
+int g_wideBlocksPerSM = 8;
+int g_triThreshold = WIDE_TRI_THRESHOLD, g_refillThreshold = WIDE_REFILL_THRESHOLD, g_triThresholdShadow = WIDE_TRI_THRESHOLD;
+#define TUNE WideTuning{ g_triThreshold, g_refillThreshold }
+#define TUNE_SHADOW WideTuning{ g_triThresholdShadow, g_refillThreshold }
+
+void LaunchGenerateExtend( const DevScene& scene, const RenderParams& p, const PathSet& out, float4* hits, uint32_t* workCounter, int smCount, cudaStream_t s )
 {
-	generateExtendKernel<<<GridFor( p.stride, smCount ), 128, 0, s>>>( scene, p, out, hits );
+	if (scene.singleIdentity && g_traversalVariant == 1)
+	{
+		const uint32_t items = ((p.w + 7) / 8) * ((p.h + 3) / 4) * 32 * p.spp;
+		wideGenerateExtendKernel<<<PersistentGrid( items, smCount, g_wideBlocksPerSM ), WIDE_BLOCK, 0, s>>>( scene, p, out, hits, workCounter, TUNE );
+	}
+	else generateExtendKernel<<<GridFor( p.stride, smCount ), 128, 0, s>>>( scene, p, out, hits );
 }
 
-void LaunchExtendCounted( const DevScene& scene, const PathSet& in, float4* hits, const uint32_t* countPtr, uint32_t maxRays, int smCount, cudaStream_t s )
+void LaunchExtendCounted( const DevScene& scene, const PathSet& in, float4* hits, const uint32_t* countPtr, uint32_t* workCounter, uint32_t maxRays, int smCount, cudaStream_t s )
 {
-	extendCountedKernel<<<GridFor( maxRays, smCount ), 128, 0, s>>>( scene, in, hits, countPtr );
+	if (scene.singleIdentity && g_traversalVariant == 1)
+		wideExtendKernel<<<PersistentGrid( maxRays, smCount, g_wideBlocksPerSM ), WIDE_BLOCK, 0, s>>>( scene, in.O, in.D, hits, countPtr, 0, workCounter, TUNE );
+	else extendCountedKernel<<<GridFor( maxRays, smCount ), 128, 0, s>>>( scene, in, hits, countPtr );
 }
 
-void LaunchConnect( const DevScene& scene, const PathSet& conn, float4* accumulator, const uint32_t* countPtr, uint32_t maxRays, int smCount, cudaStream_t s )
+void LaunchConnect( const DevScene& scene, const PathSet& conn, float4* accumulator, const uint32_t* countPtr, uint32_t* workCounter, uint32_t maxRays, int smCount, cudaStream_t s )
 {
-	connectKernel<<<GridFor( maxRays, smCount ), 128, 0, s>>>( scene, conn, accumulator, countPtr );
+	if (scene.singleIdentity && g_traversalVariant == 1)
+		wideConnectKernel<<<PersistentGrid( maxRays, smCount, g_wideBlocksPerSM ), WIDE_BLOCK, 0, s>>>( scene, conn, accumulator, countPtr, workCounter, TUNE_SHADOW );
+	else connectKernel<<<GridFor( maxRays, smCount ), 128, 0, s>>>( scene, conn, accumulator, countPtr );
 }
 
-void LaunchExtend( const DevScene& scene, const float4* O4, const float4* D4, float4* hits, int n, cudaStream_t s )
+void LaunchExtend( const DevScene& scene, const float4* O4, const float4* D4, float4* hits, int n, uint32_t* workCounter, int smCount, cudaStream_t s )
 {
 	if (n <= 0) return;
-	extendKernel<<<(n + 127) / 128, 128, 0, s>>>( scene, O4, D4, hits, n );
+	if (scene.singleIdentity && g_traversalVariant == 1)
+	{
+		cudaMemsetAsync( workCounter, 0, sizeof( uint32_t ), s );
+		wideExtendKernel<<<PersistentGrid( (uint32_t)n, smCount, g_wideBlocksPerSM ), WIDE_BLOCK, 0, s>>>( scene, O4, D4, hits, nullptr, (uint32_t)n, workCounter, TUNE );
+	}
+	else extendKernel<<<(n + 127) / 128, 128, 0, s>>>( scene, O4, D4, hits, n );
 }
 
-void LaunchOcclude( const DevScene& scene, const float4* O4, const float4* D4, uint8_t* occluded, int n, cudaStream_t s )
+void LaunchOcclude( const DevScene& scene, const float4* O4, const float4* D4, uint8_t* occluded, int n, uint32_t* workCounter, int smCount, cudaStream_t s )
 {
 	if (n <= 0) return;
-	occludeKernel<<<(n + 127) / 128, 128, 0, s>>>( scene, O4, D4, occluded, n );
+	if (scene.singleIdentity && g_traversalVariant == 1)
+	{
+		cudaMemsetAsync( workCounter, 0, sizeof( uint32_t ), s );
+		wideOccludeKernel<<<PersistentGrid( (uint32_t)n, smCount, g_wideBlocksPerSM ), WIDE_BLOCK, 0, s>>>( scene, O4, D4, occluded, (uint32_t)n, workCounter, TUNE_SHADOW );
+	}
+	else occludeKernel<<<(n + 127) / 128, 128, 0, s>>>( scene, O4, D4, occluded, n );
 }
 
 } // namespace lh2b

@@ -1,0 +1,247 @@
+/* traverse_wide.cuh - persistent, warp-cooperative CWBVH traversal (sm_100a).
+
+   Same contract and bit-identical results as traverse.cuh (see there for the reference call sites it replaces);
+   this is the throughput path. What the first ncu profile (profiles/r1_v0_generateExtend_full.txt) showed for the
+   per-thread while-while loop: triangle tests ran with 3 of 32 lanes, node steps with 15 of 32, and the byte->float
+   conversions (48 I2F.U8 per node step, quarter-rate XU pipe) dominated the stall samples. Hence:
+
+   1. The warp, not the thread, owns the loop. Every iteration all 32 lanes vote (ballot) on what they could do
+      next and the warp executes ONE phase: a node step for the lanes holding a node group, or a triangle test for
+      the lanes holding a triangle group. Triangle groups found while a lane still has node work are parked
+      (per-lane deferred stack) until enough lanes have triangles (TRI_THRESHOLD) or no lane has node work.
+   2. Persistent threads: lanes whose ray is finished fetch the next ray index from a global counter with one
+      warp-aggregated atomicAdd, so the warp stays full until the launch runs out of rays.
+   3. Quantised plane bytes are turned into floats with one PRMT each (byte dropped into the mantissa of 65536.0f:
+      value 65536 + 2q), folded into the slab FMA; the 2^-9-quantum rounding this adds is covered by separate,
+      outward-rounded near/far offsets.
+   4. The node stack head lives in shared memory ([entry][thread] layout: conflict-free for any per-lane depth),
+      overflow and the deferred-triangle stack in local memory.
+
+   Closest-hit order independence (tie-break on (instance, primitive)) is what makes deferring legal: the result
+   does not depend on the order in which triangles are tested.
+*/
+#pragma once
+#include "traverse.cuh"
+
+namespace lh2b
+{
+
+#define WIDE_BLOCK 128
+#define WIDE_SMEM_STACK 12		// node-stack entries per thread kept in shared memory
+#define WIDE_LOCAL_STACK 40		// overflow entries in local memory
+#define WIDE_TRI_STACK 12		// deferred triangle groups per lane
+#define WIDE_TRI_THRESHOLD 12	// lanes with pending triangles that trigger a triangle phase
+#define WIDE_REFILL_THRESHOLD 8	// idle lanes that trigger fetching new rays
+
+__device__ __forceinline__ float ByteFloat( const uint32_t word, const uint32_t selector )
+{
+	// 0x47800000 = 65536.0f; dropping a byte into mantissa bits 8..15 gives exactly 65536 + 2 * byte
+	return __uint_as_float( __byte_perm( word, 0x47800000u, selector ) );
+}
+
+struct WideRay
+{
+	float3 O, D;
+	float tmin, tmax;
+};
+
+/* RaySource: bool Load( uint32_t workIdx, WideRay& ) (false: nothing to trace for this index)
+   HitSink:   void Closest( uint32_t workIdx, bool hit, const TraceResult& ) / void AnyHit( uint32_t workIdx, bool occluded ) */
+struct WideTuning { int triThreshold, refillThreshold; };
+
+template <bool ANYHIT, class RaySource, class HitSink>
+__device__ __forceinline__ void TraverseWide( const InstTrav& blas, RaySource& src, HitSink& sink, const uint32_t rayCount, uint32_t* workCounter,
+	const WideTuning tune )
+{
+	__shared__ uint2 smemStack[WIDE_SMEM_STACK][WIDE_BLOCK];
+	uint2 localStack[WIDE_LOCAL_STACK];
+	uint2 triStack[WIDE_TRI_STACK];
+	const uint32_t lane = threadIdx.x & 31;
+	const uint4* __restrict__ nodes = blas.nodes;
+	const float4* __restrict__ tris = blas.tris;
+	// lane state
+	bool active = false;
+	uint32_t workIdx = 0;
+	float3 O = make_float3( 0, 0, 0 ), D = make_float3( 0, 0, 1 );
+	float idx = 0, idy = 0, idz = 0, tmin = 0, tmax = 0;
+	uint32_t octinv = 0;
+	uint2 ng = make_uint2( 0, 0 ), tg = make_uint2( 0, 0 );
+	int sp = 0, tsp = 0;
+	uint32_t bestPrim = 0xffffffffu;
+	float bestU = 0, bestV = 0;
+	bool exhausted = false;	// no more rays in the launch
+	while (true)
+	{
+		// ---- lanes without a node group take the next one from their stack; finished rays retire -------------
+		if (active)
+		{
+			if (ng.y <= 0x00ffffffu && sp > 0)
+			{
+				--sp;
+				ng = sp < WIDE_SMEM_STACK ? smemStack[sp][threadIdx.x] : localStack[sp - WIDE_SMEM_STACK];
+			}
+			if (tg.y == 0 && tsp > 0) tg = triStack[--tsp];
+			if (ng.y <= 0x00ffffffu && tg.y == 0)
+			{
+				// nothing left for this ray
+				if (ANYHIT) sink.AnyHit( workIdx, false );
+				else
+				{
+					TraceResult r;
+					r.t = tmax, r.inst = 0, r.prim = bestPrim, r.u = bestU, r.v = bestV;
+					sink.Closest( workIdx, bestPrim != 0xffffffffu, r );
+				}
+				active = false;
+			}
+		}
+		// ---- refill idle lanes -------------------------------------------------------------------------
+		const uint32_t idleMask = __ballot_sync( 0xffffffffu, !active );
+		if (!exhausted && __popc( idleMask ) >= tune.refillThreshold)
+		{
+			const int leader = __ffs( idleMask ) - 1;
+			uint32_t base = 0;
+			if (lane == leader) base = atomicAdd( workCounter, (uint32_t)__popc( idleMask ) );
+			base = __shfl_sync( 0xffffffffu, base, leader );
+			if (base >= rayCount) exhausted = true;
+			if (!active)
+			{
+				const uint32_t mine = base + __popc( idleMask & ((1u << lane) - 1) );
+				WideRay ray;
+				if (mine < rayCount && src.Load( mine, ray ))
+				{
+					workIdx = mine, active = true;
+					O = ray.O, D = ray.D, tmin = ray.tmin, tmax = ray.tmax;
+					idx = SafeRcpDir( D.x ), idy = SafeRcpDir( D.y ), idz = SafeRcpDir( D.z );
+					octinv = (D.x < 0 ? 0 : 4) | (D.y < 0 ? 0 : 2) | (D.z < 0 ? 0 : 1);
+					ng = make_uint2( 0, 0x80000000u ), tg = make_uint2( 0, 0 );
+					sp = 0, tsp = 0, bestPrim = 0xffffffffu, bestU = bestV = 0;
+				}
+			}
+		}
+		// ---- vote ------------------------------------------------------------------------------------
+		const bool hasNode = active && ng.y > 0x00ffffffu, hasTri = active && tg.y != 0;
+		const uint32_t nodeMask = __ballot_sync( 0xffffffffu, hasNode ), triMask = __ballot_sync( 0xffffffffu, hasTri );
+		const uint32_t fullMask = __ballot_sync( 0xffffffffu, tsp >= WIDE_TRI_STACK - 1 );
+		if ((nodeMask | triMask) == 0)
+		{
+			// no active lane is left (active lanes always hold a node or a triangle group here)
+			if (exhausted) break;
+			if (idleMask != 0xffffffffu) continue;	// cannot happen; keeps the loop safe
+			continue;
+		}
+		const bool triPhase = triMask != 0 && (nodeMask == 0 || __popc( triMask ) >= tune.triThreshold || fullMask != 0);
+		if (triPhase)
+		{
+			if (hasTri)
+			{
+				const int bit = 31 - __clz( tg.y );
+				tg.y &= ~(1u << bit);
+				const float4* tp = tris + (size_t)(tg.x + bit) * 3;
+				const float4 v0 = __ldg( tp ), e1 = __ldg( tp + 1 ), e2 = __ldg( tp + 2 );
+				const float pvx = CROSS_X( D.x, D.y, D.z, e2.x, e2.y, e2.z );
+				const float pvy = CROSS_Y( D.x, D.y, D.z, e2.x, e2.y, e2.z );
+				const float pvz = CROSS_Z( D.x, D.y, D.z, e2.x, e2.y, e2.z );
+				const float det = Dot3( e1.x, e1.y, e1.z, pvx, pvy, pvz );
+				if (det != 0.0f)
+				{
+					const float inv = __frcp_rn( det );
+					const float tvx = __fsub_rn( O.x, v0.x ), tvy = __fsub_rn( O.y, v0.y ), tvz = __fsub_rn( O.z, v0.z );
+					const float u = __fmul_rn( Dot3( tvx, tvy, tvz, pvx, pvy, pvz ), inv );
+					if (u >= 0.0f && u <= 1.0f)
+					{
+						const float qvx = CROSS_X( tvx, tvy, tvz, e1.x, e1.y, e1.z );
+						const float qvy = CROSS_Y( tvx, tvy, tvz, e1.x, e1.y, e1.z );
+						const float qvz = CROSS_Z( tvx, tvy, tvz, e1.x, e1.y, e1.z );
+						const float v = __fmul_rn( Dot3( D.x, D.y, D.z, qvx, qvy, qvz ), inv );
+						if (v >= 0.0f && __fadd_rn( u, v ) <= 1.0f)
+						{
+							const float t = __fmul_rn( Dot3( e2.x, e2.y, e2.z, qvx, qvy, qvz ), inv );
+							if (ANYHIT)
+							{
+								if (t > tmin && t < tmax)
+								{
+									sink.AnyHit( workIdx, true );
+									active = false, ng.y = 0, tg.y = 0, sp = 0, tsp = 0;
+								}
+							}
+							else if (t > tmin)
+							{
+								const uint32_t prim = __float_as_uint( v0.w );
+								if (t < tmax || (t == tmax && prim < bestPrim)) tmax = t, bestPrim = prim, bestU = u, bestV = v;
+							}
+						}
+					}
+				}
+			}
+			continue;
+		}
+		// ---- node phase --------------------------------------------------------------------------------
+		if (hasNode)
+		{
+			const uint32_t hits = ng.y;
+			const int bit = 31 - __clz( hits );
+			ng.y &= ~(1u << bit);
+			if (ng.y > 0x00ffffffu)
+			{
+				if (sp < WIDE_SMEM_STACK) smemStack[sp][threadIdx.x] = ng; else localStack[sp - WIDE_SMEM_STACK] = ng;
+				sp++;
+			}
+			const uint32_t slot = (uint32_t)(bit - 24) ^ octinv;
+			const uint32_t rel = __popc( hits & ~(0xffffffffu << slot) & 0xffu );
+			const uint4* np = nodes + (size_t)(ng.x + rel) * 5;
+			const uint4 n0 = __ldg( np ), n1 = __ldg( np + 1 ), n2 = __ldg( np + 2 ), n3 = __ldg( np + 3 ), n4 = __ldg( np + 4 );
+			// t(q) = (p + q * 2^e - o) * idir = (65536 + 2q) * (2^e * idir / 2) + ((p - o) * idir - 32768 * 2^e * idir)
+			const float sx = __uint_as_float( (n0.w & 255u) << 23 ) * idx, sy = __uint_as_float( ((n0.w >> 8) & 255u) << 23 ) * idy;
+			const float sz = __uint_as_float( ((n0.w >> 16) & 255u) << 23 ) * idz;
+			const float hx = 0.5f * sx, hy = 0.5f * sy, hz = 0.5f * sz;
+			const float cx = fmaf( -32768.0f, sx, (__uint_as_float( n0.x ) - O.x) * idx );
+			const float cy = fmaf( -32768.0f, sy, (__uint_as_float( n0.y ) - O.y) * idy );
+			const float cz = fmaf( -32768.0f, sz, (__uint_as_float( n0.z ) - O.z) * idz );
+			// outward slack of 2^-8 quantum on both sides covers the rounding of the shifted offset
+			const float ex = 0.00390625f * fabsf( sx ), ey = 0.00390625f * fabsf( sy ), ez = 0.00390625f * fabsf( sz );
+			const float cnx = cx - ex, cfx = cx + ex, cny = cy - ey, cfy = cy + ey, cnz = cz - ez, cfz = cz + ez;
+			const uint32_t octinv4 = octinv * 0x01010101u;
+			ng.x = n1.x;
+			uint2 ntg = make_uint2( n1.y, 0 );
+			uint32_t hitmask = 0;
+#pragma unroll
+			for (int half = 0; half < 2; half++)
+			{
+				const uint32_t meta4 = half ? n1.w : n1.z;
+				const uint32_t isInner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+				const uint32_t innerMask4 = SignExtendS8x4( isInner4 << 3 );
+				const uint32_t bitIndex4 = (meta4 ^ (octinv4 & innerMask4)) & 0x1f1f1f1fu;
+				const uint32_t childBits4 = (meta4 >> 5) & 0x07070707u;
+				const uint32_t qlox = half ? n2.y : n2.x, qloy = half ? n2.w : n2.z, qloz = half ? n3.y : n3.x;
+				const uint32_t qhix = half ? n3.w : n3.z, qhiy = half ? n4.y : n4.x, qhiz = half ? n4.w : n4.z;
+				const uint32_t nx = D.x < 0 ? qhix : qlox, fx = D.x < 0 ? qlox : qhix;
+				const uint32_t ny = D.y < 0 ? qhiy : qloy, fy = D.y < 0 ? qloy : qhiy;
+				const uint32_t nz = D.z < 0 ? qhiz : qloz, fz = D.z < 0 ? qloz : qhiz;
+#pragma unroll
+				for (int j = 0; j < 4; j++)
+				{
+					const uint32_t sel = 0x7604u | (uint32_t)(j << 4);
+					const float t0x = fmaf( ByteFloat( nx, sel ), hx, cnx ), t1x = fmaf( ByteFloat( fx, sel ), hx, cfx );
+					const float t0y = fmaf( ByteFloat( ny, sel ), hy, cny ), t1y = fmaf( ByteFloat( fy, sel ), hy, cfy );
+					const float t0z = fmaf( ByteFloat( nz, sel ), hz, cnz ), t1z = fmaf( ByteFloat( fz, sel ), hz, cfz );
+					const float cmin = fmaxf( fmaxf( t0x, t0y ), fmaxf( t0z, tmin ) );
+					const float cmax = fminf( fminf( t1x, t1y ), fminf( t1z, tmax ) ) * 1.0000005f;
+					if (cmin <= cmax)
+					{
+						const uint32_t cb = (childBits4 >> (8 * j)) & 255u, bi = (bitIndex4 >> (8 * j)) & 255u;
+						hitmask |= cb << bi;
+					}
+				}
+			}
+			ng.y = (hitmask & 0xff000000u) | (n0.w >> 24);
+			ntg.y = hitmask & 0x00ffffffu;
+			if (ntg.y != 0)
+			{
+				if (tg.y == 0) tg = ntg;
+				else triStack[tsp++] = ntg;
+			}
+		}
+	}
+}
+
+} // namespace lh2b

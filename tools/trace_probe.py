@@ -10,6 +10,9 @@ t0 = time.time()
 mesh = scenes.terrain(nx, nz, extent=50, seed=0x12345678)
 print("scene: %d tris, gen %.1fs" % (mesh.shape[0] // 3, time.time() - t0))
 core = RenderCore(0)
+for k, v in os.environ.items():
+    if k.startswith("LH2B_SET_"):
+        core.Setting(k[9:], float(v)); print("setting", k[9:], v)
 t0 = time.time()
 core.SetGeometry(0, mesh)
 core.SetInstance(0, 0); core.SetInstance(1, -1)
