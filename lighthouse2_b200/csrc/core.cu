@@ -48,6 +48,44 @@ static bool IsIdentity( const float* m )
 	return memcmp( m, id, sizeof( id ) ) == 0;
 }
 
+/* Arena slots: bump allocation with 25% slack; a mesh that outgrows its slot gets a new one at the top
+   (the old slot is not recycled - meshes that change triangle count every frame should be rare). */
+static uint32_t ArenaAllocNodes( lh2b_core* core, uint32_t count, uint32_t& cap )
+{
+	cap = count + count / 4 + 4;
+	const uint32_t off = core->arenaNodeTop;
+	core->arenaNodeTop += cap;
+	const size_t need = (size_t)core->arenaNodeTop * 5;
+	if (need > core->arenaNodes.capacity)
+	{
+		core->arenaNodes.count = core->arenaNodes.capacity;
+		core->arenaNodes.Reserve( need + need / 2, true );
+	}
+	core->arenaNodes.count = need;
+	return off;
+}
+
+static uint32_t ArenaAllocTris( lh2b_core* core, uint32_t count, uint32_t& cap )
+{
+	cap = count + count / 4 + 4;
+	const uint32_t off = core->arenaTriTop;
+	core->arenaTriTop += cap;
+	const size_t need = (size_t)core->arenaTriTop * 3;
+	if (need > core->arenaTris.capacity)
+	{
+		core->arenaTris.count = core->arenaTris.capacity;
+		core->arenaTris.Reserve( need + need / 2, true );
+	}
+	core->arenaTris.count = need;
+	return off;
+}
+
+/* childBase / triBase of every node become absolute arena indices. */
+static void BakeOffsets( std::vector<CwNode>& nodes, uint32_t nodeOff, uint32_t triOff )
+{
+	for (auto& n : nodes) n.w[4] += nodeOff, n.w[5] += triOff;
+}
+
 static void RebuildMeshHost( lh2b_core* core, Mesh& mesh )
 {
 	const double t0 = NowMs();
@@ -58,10 +96,12 @@ static void RebuildMeshHost( lh2b_core* core, Mesh& mesh )
 	CollapseToCwBvh( bvh2, primIdx, mesh.hostVerts.data(), cw );
 	mesh.bounds = cw.bounds;
 	mesh.nodeCount = (uint32_t)cw.nodes.size();
-	mesh.nodes.Upload( (const uint4*)cw.nodes.data(), cw.nodes.size() * 5, core->stream );
-	// keep at least one triangle slot so the pointer is never null
 	if (cw.tris.empty()) cw.tris.push_back( CwTri{} );
-	mesh.cwTris.Upload( (const float4*)cw.tris.data(), cw.tris.size() * 3, core->stream );
+	if (mesh.nodeCount > mesh.nodeCap) mesh.nodeOff = ArenaAllocNodes( core, mesh.nodeCount, mesh.nodeCap );
+	if (cw.tris.size() > mesh.triCap) mesh.triOff = ArenaAllocTris( core, (uint32_t)cw.tris.size(), mesh.triCap );
+	BakeOffsets( cw.nodes, mesh.nodeOff, mesh.triOff );
+	CUDA_CHECK( cudaMemcpyAsync( core->arenaNodes.ptr + (size_t)mesh.nodeOff * 5, cw.nodes.data(), cw.nodes.size() * sizeof( CwNode ), cudaMemcpyHostToDevice, core->stream ) );
+	CUDA_CHECK( cudaMemcpyAsync( core->arenaTris.ptr + (size_t)mesh.triOff * 3, cw.tris.data(), cw.tris.size() * sizeof( CwTri ), cudaMemcpyHostToDevice, core->stream ) );
 	CUDA_CHECK( cudaStreamSynchronize( core->stream ) );
 	mesh.buildMs = (float)(NowMs() - t0);
 	mesh.dirty = false;
@@ -104,7 +144,7 @@ void UpdateAccelerationStructures( lh2b_core* core )
 		trav[i].r0 = make_float4( inv[0], inv[1], inv[2], inv[3] );
 		trav[i].r1 = make_float4( inv[4], inv[5], inv[6], inv[7] );
 		trav[i].r2 = make_float4( inv[8], inv[9], inv[10], inv[11] );
-		trav[i].nodes = mesh.nodes.ptr, trav[i].tris = mesh.cwTris.ptr;
+		trav[i].rootNode = mesh.nodeOff, trav[i].flags = IsIdentity( inst.xform ) ? 1u : 0u, trav[i].pad0 = trav[i].pad1 = 0;
 		// shading-side descriptor: triangle array + inverse transform (rendercore.cpp:403-417)
 		desc[i].triangles = mesh.coreTris.ptr, desc[i].dummy1 = desc[i].dummy2 = 0;
 		desc[i].invTransform.A = { inv[0], inv[1], inv[2], inv[3] }, desc[i].invTransform.B = { inv[4], inv[5], inv[6], inv[7] };
@@ -118,12 +158,16 @@ void UpdateAccelerationStructures( lh2b_core* core )
 	CollapseToCwBvh( bvh2, primIdx, nullptr, cw );
 	if (cw.leafIds.empty()) cw.leafIds.push_back( 0 );
 	core->tlasNodeCount = (uint32_t)cw.nodes.size();
-	core->tlasNodes.Upload( (const uint4*)cw.nodes.data(), cw.nodes.size() * 5, core->stream );
+	if (core->tlasNodeCount > core->tlasCap) core->tlasOff = ArenaAllocNodes( core, core->tlasNodeCount, core->tlasCap );
+	BakeOffsets( cw.nodes, core->tlasOff, 0 );
+	CUDA_CHECK( cudaMemcpyAsync( core->arenaNodes.ptr + (size_t)core->tlasOff * 5, cw.nodes.data(), cw.nodes.size() * sizeof( CwNode ), cudaMemcpyHostToDevice, core->stream ) );
 	core->tlasLeafIds.Upload( cw.leafIds.data(), cw.leafIds.size(), core->stream );
 	core->instTrav.Upload( trav.data(), trav.size(), core->stream );
 	core->instDesc.Upload( desc.data(), desc.size(), core->stream );
 	CUDA_CHECK( cudaStreamSynchronize( core->stream ) );
-	core->scene.tlasNodes = core->tlasNodes.ptr;
+	core->scene.nodes = core->arenaNodes.ptr, core->scene.tris = core->arenaTris.ptr;
+	core->scene.tlasRoot = core->tlasOff;
+	core->scene.singleRoot = n > 0 ? core->meshes[core->instances[0].mesh]->nodeOff : 0;
 	core->scene.tlasLeafIds = core->tlasLeafIds.ptr;
 	core->scene.instances = core->instTrav.ptr;
 	core->scene.instanceCount = n;
@@ -312,7 +356,7 @@ int lh2b_get_bvh_stats( lh2b_core* core, int meshIdx, lh2b_bvh_stats* out )
 	if (meshIdx == -1)
 	{
 		out->nodes = core->tlasNodeCount, out->triangles = (uint32_t)core->instances.size();
-		out->bytes = (uint32_t)(core->tlasNodes.Bytes() + core->tlasLeafIds.Bytes() + core->instTrav.Bytes());
+		out->bytes = (uint32_t)(core->tlasNodeCount * 80 + core->tlasLeafIds.Bytes() + core->instTrav.Bytes());
 		out->buildMs = core->tlasBuildMs;
 	}
 	else
@@ -320,7 +364,7 @@ int lh2b_get_bvh_stats( lh2b_core* core, int meshIdx, lh2b_bvh_stats* out )
 		if (meshIdx < 0 || meshIdx >= (int)core->meshes.size()) throw CoreError( "unknown mesh" );
 		const Mesh& m = *core->meshes[meshIdx];
 		out->nodes = m.nodeCount, out->triangles = m.triCount;
-		out->bytes = (uint32_t)(m.nodes.Bytes() + m.cwTris.Bytes());
+		out->bytes = (uint32_t)(m.nodeCount * 80 + (size_t)m.triCount * 48);
 		out->buildMs = m.buildMs, out->sahCost = m.sahCost;
 	}
 	API_END

@@ -22,8 +22,8 @@ struct Mesh
 	int triCount = 0;
 	DevBuf<float4> coreTris;		// CoreTri4 view: 13 float4 per triangle (shading data)
 	DevBuf<float4> verts;			// float4[3 * triCount] positions as passed to SetGeometry
-	DevBuf<uint4> nodes;			// CWBVH nodes, 5 uint4 each
-	DevBuf<float4> cwTris;			// traversal triangles, 3 float4 each
+	uint32_t nodeOff = 0, nodeCap = 0;	// slot in the node arena (in nodes)
+	uint32_t triOff = 0, triCap = 0;	// slot in the triangle arena (in triangles)
 	std::vector<float> hostVerts;	// kept for host rebuilds
 	Aabb bounds = {};
 	bool dirty = true;
@@ -45,7 +45,10 @@ struct lh2b_core
 	std::vector<lh2b::Instance> instances;
 	bool sceneReady = false;
 	// top level
-	lh2b::DevBuf<uint4> tlasNodes;
+	lh2b::DevBuf<uint4> arenaNodes;			// every BLAS + the TLAS, 5 uint4 per node
+	lh2b::DevBuf<float4> arenaTris;			// every BLAS triangle, 3 float4 each
+	uint32_t arenaNodeTop = 0, arenaTriTop = 0;
+	uint32_t tlasOff = 0, tlasCap = 0;
 	lh2b::DevBuf<uint32_t> tlasLeafIds;
 	lh2b::DevBuf<lh2b::InstTrav> instTrav;
 	lh2b::DevScene scene = {};

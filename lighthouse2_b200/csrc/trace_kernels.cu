@@ -147,6 +147,11 @@ struct BufferRaySource
 		r.tmin = 0.0f, r.tmax = shadow ? d.w : 1e34f;
 		return true;
 	}
+	__device__ __forceinline__ void Reload( const uint32_t i, float3& O, float3& D ) const
+	{
+		const float4 o = O4[i], d = D4[i];
+		O = make_float3( o.x, o.y, o.z ), D = make_float3( d.x, d.y, d.z );
+	}
 };
 
 struct HitBufferSink
@@ -246,6 +251,12 @@ struct TiledPrimarySource
 		outD[pathIdx] = make_float4( r.D.x, r.D.y, r.D.z, 0 );
 		return true;
 	}
+	__device__ __forceinline__ void Reload( const uint32_t work, float3& O, float3& D ) const
+	{
+		const uint32_t pathIdx = PathOf( work );
+		const float4 o = outO[pathIdx], d = outD[pathIdx];	// written by this thread in Load
+		O = make_float3( o.x, o.y, o.z ), D = make_float3( d.x, d.y, d.z );
+	}
 };
 
 struct TiledHitSink
@@ -255,7 +266,7 @@ struct TiledHitSink
 	__device__ __forceinline__ void AnyHit( const uint32_t, const bool ) const {}
 };
 
-__global__ void __launch_bounds__( WIDE_BLOCK ) wideGenerateExtendKernel( const DevScene scene, const RenderParams p, const PathSet out, float4* __restrict__ hits,
+template <bool TWO_LEVEL> __global__ void __launch_bounds__( WIDE_BLOCK ) wideGenerateExtendKernel( const DevScene scene, const RenderParams p, const PathSet out, float4* __restrict__ hits,
 	uint32_t* workCounter, const WideTuning tune )
 {
 	TiledPrimarySource src;
@@ -263,31 +274,31 @@ __global__ void __launch_bounds__( WIDE_BLOCK ) wideGenerateExtendKernel( const 
 	src.tilesX = (p.w + 7) / 8;
 	src.itemsPerSample = src.tilesX * ((p.h + 3) / 4) * 32;
 	TiledHitSink sink = { &src, hits };
-	TraverseWide<false>( scene.instances[0], src, sink, src.itemsPerSample * p.spp, workCounter, tune );
+	TraverseWide<false, TWO_LEVEL>( scene, src, sink, src.itemsPerSample * p.spp, workCounter, tune );
 }
 
-__global__ void __launch_bounds__( WIDE_BLOCK ) wideExtendKernel( const DevScene scene, const float4* __restrict__ O4, const float4* __restrict__ D4,
+template <bool TWO_LEVEL> __global__ void __launch_bounds__( WIDE_BLOCK ) wideExtendKernel( const DevScene scene, const float4* __restrict__ O4, const float4* __restrict__ D4,
 	float4* __restrict__ hits, const uint32_t* __restrict__ countPtr, const uint32_t fixedCount, uint32_t* workCounter, const WideTuning tune )
 {
 	BufferRaySource src = { O4, D4, false };
 	HitBufferSink sink = { hits };
-	TraverseWide<false>( scene.instances[0], src, sink, countPtr ? *countPtr : fixedCount, workCounter, tune );
+	TraverseWide<false, TWO_LEVEL>( scene, src, sink, countPtr ? *countPtr : fixedCount, workCounter, tune );
 }
 
-__global__ void __launch_bounds__( WIDE_BLOCK ) wideOccludeKernel( const DevScene scene, const float4* __restrict__ O4, const float4* __restrict__ D4,
+template <bool TWO_LEVEL> __global__ void __launch_bounds__( WIDE_BLOCK ) wideOccludeKernel( const DevScene scene, const float4* __restrict__ O4, const float4* __restrict__ D4,
 	uint8_t* __restrict__ flags, const uint32_t fixedCount, uint32_t* workCounter, const WideTuning tune )
 {
 	BufferRaySource src = { O4, D4, true };
 	OccludedFlagSink sink = { flags };
-	TraverseWide<true>( scene.instances[0], src, sink, fixedCount, workCounter, tune );
+	TraverseWide<true, TWO_LEVEL>( scene, src, sink, fixedCount, workCounter, tune );
 }
 
-__global__ void __launch_bounds__( WIDE_BLOCK ) wideConnectKernel( const DevScene scene, const PathSet conn, float4* __restrict__ accumulator,
+template <bool TWO_LEVEL> __global__ void __launch_bounds__( WIDE_BLOCK ) wideConnectKernel( const DevScene scene, const PathSet conn, float4* __restrict__ accumulator,
 	const uint32_t* __restrict__ countPtr, uint32_t* workCounter, const WideTuning tune )
 {
 	BufferRaySource src = { conn.O, conn.D, true };
 	ConnectSink sink = { conn.T, accumulator };
-	TraverseWide<true>( scene.instances[0], src, sink, *countPtr, workCounter, tune );
+	TraverseWide<true, TWO_LEVEL>( scene, src, sink, *countPtr, workCounter, tune );
 }
 
 static uint32_t PersistentGrid( uint32_t maxItems, int smCount, int blocksPerSM )
@@ -311,35 +322,46 @@ int g_triThreshold = WIDE_TRI_THRESHOLD, g_refillThreshold = WIDE_REFILL_THRESHO
 
 void LaunchGenerateExtend( const DevScene& scene, const RenderParams& p, const PathSet& out, float4* hits, uint32_t* workCounter, int smCount, cudaStream_t s )
 {
-	if (scene.singleIdentity && g_traversalVariant == 1)
+	if (g_traversalVariant == 1)
 	{
-		const uint32_t items = ((p.w + 7) / 8) * ((p.h + 3) / 4) * 32 * p.spp;
-		wideGenerateExtendKernel<<<PersistentGrid( items, smCount, g_wideBlocksPerSM ), WIDE_BLOCK, 0, s>>>( scene, p, out, hits, workCounter, TUNE );
+		const uint32_t items = ((p.w + 7) / 8) * ((p.h + 3) / 4) * 32 * p.spp, grid = PersistentGrid( items, smCount, g_wideBlocksPerSM );
+		if (scene.singleIdentity) wideGenerateExtendKernel<false><<<grid, WIDE_BLOCK, 0, s>>>( scene, p, out, hits, workCounter, TUNE );
+		else wideGenerateExtendKernel<true><<<grid, WIDE_BLOCK, 0, s>>>( scene, p, out, hits, workCounter, TUNE );
 	}
 	else generateExtendKernel<<<GridFor( p.stride, smCount ), 128, 0, s>>>( scene, p, out, hits );
 }
 
 void LaunchExtendCounted( const DevScene& scene, const PathSet& in, float4* hits, const uint32_t* countPtr, uint32_t* workCounter, uint32_t maxRays, int smCount, cudaStream_t s )
 {
-	if (scene.singleIdentity && g_traversalVariant == 1)
-		wideExtendKernel<<<PersistentGrid( maxRays, smCount, g_wideBlocksPerSM ), WIDE_BLOCK, 0, s>>>( scene, in.O, in.D, hits, countPtr, 0, workCounter, TUNE );
+	if (g_traversalVariant == 1)
+	{
+		const uint32_t grid = PersistentGrid( maxRays, smCount, g_wideBlocksPerSM );
+		if (scene.singleIdentity) wideExtendKernel<false><<<grid, WIDE_BLOCK, 0, s>>>( scene, in.O, in.D, hits, countPtr, 0, workCounter, TUNE );
+		else wideExtendKernel<true><<<grid, WIDE_BLOCK, 0, s>>>( scene, in.O, in.D, hits, countPtr, 0, workCounter, TUNE );
+	}
 	else extendCountedKernel<<<GridFor( maxRays, smCount ), 128, 0, s>>>( scene, in, hits, countPtr );
 }
 
 void LaunchConnect( const DevScene& scene, const PathSet& conn, float4* accumulator, const uint32_t* countPtr, uint32_t* workCounter, uint32_t maxRays, int smCount, cudaStream_t s )
 {
-	if (scene.singleIdentity && g_traversalVariant == 1)
-		wideConnectKernel<<<PersistentGrid( maxRays, smCount, g_wideBlocksPerSM ), WIDE_BLOCK, 0, s>>>( scene, conn, accumulator, countPtr, workCounter, TUNE_SHADOW );
+	if (g_traversalVariant == 1)
+	{
+		const uint32_t grid = PersistentGrid( maxRays, smCount, g_wideBlocksPerSM );
+		if (scene.singleIdentity) wideConnectKernel<false><<<grid, WIDE_BLOCK, 0, s>>>( scene, conn, accumulator, countPtr, workCounter, TUNE_SHADOW );
+		else wideConnectKernel<true><<<grid, WIDE_BLOCK, 0, s>>>( scene, conn, accumulator, countPtr, workCounter, TUNE_SHADOW );
+	}
 	else connectKernel<<<GridFor( maxRays, smCount ), 128, 0, s>>>( scene, conn, accumulator, countPtr );
 }
 
 void LaunchExtend( const DevScene& scene, const float4* O4, const float4* D4, float4* hits, int n, uint32_t* workCounter, int smCount, cudaStream_t s )
 {
 	if (n <= 0) return;
-	if (scene.singleIdentity && g_traversalVariant == 1)
+	if (g_traversalVariant == 1)
 	{
 		cudaMemsetAsync( workCounter, 0, sizeof( uint32_t ), s );
-		wideExtendKernel<<<PersistentGrid( (uint32_t)n, smCount, g_wideBlocksPerSM ), WIDE_BLOCK, 0, s>>>( scene, O4, D4, hits, nullptr, (uint32_t)n, workCounter, TUNE );
+		const uint32_t grid = PersistentGrid( (uint32_t)n, smCount, g_wideBlocksPerSM );
+		if (scene.singleIdentity) wideExtendKernel<false><<<grid, WIDE_BLOCK, 0, s>>>( scene, O4, D4, hits, nullptr, (uint32_t)n, workCounter, TUNE );
+		else wideExtendKernel<true><<<grid, WIDE_BLOCK, 0, s>>>( scene, O4, D4, hits, nullptr, (uint32_t)n, workCounter, TUNE );
 	}
 	else extendKernel<<<(n + 127) / 128, 128, 0, s>>>( scene, O4, D4, hits, n );
 }
@@ -347,10 +369,12 @@ void LaunchExtend( const DevScene& scene, const float4* O4, const float4* D4, fl
 void LaunchOcclude( const DevScene& scene, const float4* O4, const float4* D4, uint8_t* occluded, int n, uint32_t* workCounter, int smCount, cudaStream_t s )
 {
 	if (n <= 0) return;
-	if (scene.singleIdentity && g_traversalVariant == 1)
+	if (g_traversalVariant == 1)
 	{
 		cudaMemsetAsync( workCounter, 0, sizeof( uint32_t ), s );
-		wideOccludeKernel<<<PersistentGrid( (uint32_t)n, smCount, g_wideBlocksPerSM ), WIDE_BLOCK, 0, s>>>( scene, O4, D4, occluded, (uint32_t)n, workCounter, TUNE_SHADOW );
+		const uint32_t grid = PersistentGrid( (uint32_t)n, smCount, g_wideBlocksPerSM );
+		if (scene.singleIdentity) wideOccludeKernel<false><<<grid, WIDE_BLOCK, 0, s>>>( scene, O4, D4, occluded, (uint32_t)n, workCounter, TUNE_SHADOW );
+		else wideOccludeKernel<true><<<grid, WIDE_BLOCK, 0, s>>>( scene, O4, D4, occluded, (uint32_t)n, workCounter, TUNE_SHADOW );
 	}
 	else occludeKernel<<<(n + 127) / 128, 128, 0, s>>>( scene, O4, D4, occluded, n );
 }

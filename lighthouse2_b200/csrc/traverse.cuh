@@ -20,20 +20,26 @@
 namespace lh2b
 {
 
+/* All BLASes and the TLAS live in ONE node arena and ONE triangle arena; child / triangle base indices inside the
+   nodes are absolute arena indices (baked at build time), so traversal needs no per-ray pointers. */
 struct InstTrav
 {
 	float4 r0, r1, r2;		// rows of the world->object 3x4
-	const uint4* nodes;		// BLAS nodes (5 x uint4 per node)
-	const float4* tris;		// BLAS triangles (3 x float4 per triangle)
+	uint32_t rootNode;		// arena index of the BLAS root node
+	uint32_t flags;			// bit 0: identity transform
+	uint32_t pad0, pad1;
 };
 
 struct DevScene
 {
-	const uint4* tlasNodes;
-	const uint32_t* tlasLeafIds;
+	const uint4* nodes;				// node arena (5 x uint4 per node)
+	const float4* tris;				// triangle arena (3 x float4 per triangle)
+	const uint32_t* tlasLeafIds;	// instance index per top-level leaf slot
 	const InstTrav* instances;
+	uint32_t tlasRoot;				// arena index of the top-level root node
 	int instanceCount;
-	int singleIdentity;		// 1: exactly one instance with identity transform -> skip the top level
+	int singleIdentity;				// 1: exactly one instance with identity transform -> skip the top level
+	uint32_t singleRoot;			// its BLAS root
 };
 
 #define LH2B_STACK 48
@@ -74,19 +80,14 @@ __device__ __forceinline__ bool Traverse( const DevScene& scene, const float3 wO
 	uint2 stack[LH2B_STACK];
 	int sp = 0;
 	float3 O = wO, D = wD;
-	const uint4* nodes = scene.tlasNodes;
-	const float4* tris = nullptr;
-	bool inBlas = false;
+	const uint4* __restrict__ nodes = scene.nodes;
+	const float4* __restrict__ tris = scene.tris;
+	bool inBlas = scene.singleIdentity != 0;
 	uint32_t curInst = 0;
-	if (scene.singleIdentity)
-	{
-		const InstTrav& it = scene.instances[0];
-		nodes = it.nodes, tris = it.tris, inBlas = true;
-	}
 	float idx = SafeRcpDir( D.x ), idy = SafeRcpDir( D.y ), idz = SafeRcpDir( D.z );
 	uint32_t octinv = (D.x < 0 ? 0 : 4) | (D.y < 0 ? 0 : 2) | (D.z < 0 ? 0 : 1);
 	uint32_t octinv4 = octinv * 0x01010101u;
-	uint2 ng = make_uint2( 0, 0x80000000u ), tg = make_uint2( 0, 0 );
+	uint2 ng = make_uint2( scene.singleIdentity ? scene.singleRoot : scene.tlasRoot, 0x80000000u ), tg = make_uint2( 0, 0 );
 	uint32_t bestInst = 0xffffffffu, bestPrim = 0xffffffffu;
 	float bestU = 0, bestV = 0;
 	while (true)
@@ -204,8 +205,8 @@ __device__ __forceinline__ bool Traverse( const DevScene& scene, const float3 wO
 				idx = SafeRcpDir( D.x ), idy = SafeRcpDir( D.y ), idz = SafeRcpDir( D.z );
 				octinv = (D.x < 0 ? 0 : 4) | (D.y < 0 ? 0 : 2) | (D.z < 0 ? 0 : 1);
 				octinv4 = octinv * 0x01010101u;
-				nodes = it.nodes, tris = it.tris, curInst = inst, inBlas = true;
-				ng = make_uint2( 0, 0x80000000u ), tg = make_uint2( 0, 0 );
+				curInst = inst, inBlas = true;
+				ng = make_uint2( it.rootNode, 0x80000000u ), tg = make_uint2( 0, 0 );
 				break;
 			}
 		}
@@ -222,7 +223,7 @@ __device__ __forceinline__ bool Traverse( const DevScene& scene, const float3 wO
 				idx = SafeRcpDir( D.x ), idy = SafeRcpDir( D.y ), idz = SafeRcpDir( D.z );
 				octinv = (D.x < 0 ? 0 : 4) | (D.y < 0 ? 0 : 2) | (D.z < 0 ? 0 : 1);
 				octinv4 = octinv * 0x01010101u;
-				nodes = scene.tlasNodes, inBlas = false;
+				inBlas = false;
 			}
 			if (done) break;
 		}

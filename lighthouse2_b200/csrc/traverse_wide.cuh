@@ -45,20 +45,27 @@ struct WideRay
 	float tmin, tmax;
 };
 
-/* RaySource: bool Load( uint32_t workIdx, WideRay& ) (false: nothing to trace for this index)
-   HitSink:   void Closest( uint32_t workIdx, bool hit, const TraceResult& ) / void AnyHit( uint32_t workIdx, bool occluded ) */
+/* RaySource: bool Load( uint32_t workIdx, WideRay& ) (false: nothing to trace for this index);
+              void Reload( uint32_t workIdx, float3& O, float3& D ) (world-space ray again, after leaving an instance)
+   HitSink:   void Closest( uint32_t workIdx, bool hit, const TraceResult& ) / void AnyHit( uint32_t workIdx, bool occluded )
+
+   TWO_LEVEL: the lane is either in the top level (curInst == ~0: node groups index TLAS nodes, leaf groups are
+   instances) or inside one instance. Entering an instance transforms the ray, pushes the remaining top-level work and
+   a sentinel; the sentinel is only popped once every triangle of that instance (pending group + deferred stack) has
+   been tested, because deferred triangle groups are meaningless outside their instance. */
 struct WideTuning { int triThreshold, refillThreshold; };
 
-template <bool ANYHIT, class RaySource, class HitSink>
-__device__ __forceinline__ void TraverseWide( const InstTrav& blas, RaySource& src, HitSink& sink, const uint32_t rayCount, uint32_t* workCounter,
+template <bool ANYHIT, bool TWO_LEVEL, class RaySource, class HitSink>
+__device__ __forceinline__ void TraverseWide( const DevScene& scene, RaySource& src, HitSink& sink, const uint32_t rayCount, uint32_t* workCounter,
 	const WideTuning tune )
 {
 	__shared__ uint2 smemStack[WIDE_SMEM_STACK][WIDE_BLOCK];
 	uint2 localStack[WIDE_LOCAL_STACK];
 	uint2 triStack[WIDE_TRI_STACK];
 	const uint32_t lane = threadIdx.x & 31;
-	const uint4* __restrict__ nodes = blas.nodes;
-	const float4* __restrict__ tris = blas.tris;
+	const uint4* __restrict__ nodes = scene.nodes;
+	const float4* __restrict__ tris = scene.tris;
+	const uint32_t NO_INST = 0xffffffffu;
 	// lane state
 	bool active = false;
 	uint32_t workIdx = 0;
@@ -67,28 +74,77 @@ __device__ __forceinline__ void TraverseWide( const InstTrav& blas, RaySource& s
 	uint32_t octinv = 0;
 	uint2 ng = make_uint2( 0, 0 ), tg = make_uint2( 0, 0 );
 	int sp = 0, tsp = 0;
-	uint32_t bestPrim = 0xffffffffu;
+	uint32_t curInst = TWO_LEVEL ? NO_INST : 0u;
+	uint32_t bestPrim = 0xffffffffu, bestInst = 0xffffffffu;
 	float bestU = 0, bestV = 0;
 	bool exhausted = false;	// no more rays in the launch
+#define WIDE_PUSH( e ) do { if (sp < WIDE_SMEM_STACK) smemStack[sp][threadIdx.x] = (e); else localStack[sp - WIDE_SMEM_STACK] = (e); sp++; } while (0)
+#define WIDE_TOP() (sp <= WIDE_SMEM_STACK ? smemStack[sp - 1][threadIdx.x] : localStack[sp - 1 - WIDE_SMEM_STACK])
 	while (true)
 	{
 		// ---- lanes without a node group take the next one from their stack; finished rays retire -------------
 		if (active)
 		{
-			if (ng.y <= 0x00ffffffu && sp > 0)
+			if (!TWO_LEVEL)
 			{
-				--sp;
-				ng = sp < WIDE_SMEM_STACK ? smemStack[sp][threadIdx.x] : localStack[sp - WIDE_SMEM_STACK];
+				if (ng.y <= 0x00ffffffu && sp > 0) { ng = WIDE_TOP(); sp--; }
+				if (tg.y == 0 && tsp > 0) tg = triStack[--tsp];
 			}
-			if (tg.y == 0 && tsp > 0) tg = triStack[--tsp];
+			else
+			{
+				if (curInst != NO_INST && tg.y == 0 && tsp > 0) tg = triStack[--tsp];
+				if (ng.y <= 0x00ffffffu) while (sp > 0)
+				{
+					const uint2 top = WIDE_TOP();
+					if (top.y > 0x00ffffffu) { ng = top, sp--; break; }	// node group
+					if (top.y != 0)
+					{
+						// top-level leaf group (instances): only reachable in the top level
+						if (tg.y == 0) tg = top, sp--;
+						break;
+					}
+					// sentinel: leave the instance once all of its triangles are done
+					if (tg.y != 0 || tsp > 0) break;
+					sp--, curInst = NO_INST;
+					src.Reload( workIdx, O, D );
+					idx = SafeRcpDir( D.x ), idy = SafeRcpDir( D.y ), idz = SafeRcpDir( D.z );
+					octinv = (D.x < 0 ? 0 : 4) | (D.y < 0 ? 0 : 2) | (D.z < 0 ? 0 : 1);
+				}
+				if (curInst == NO_INST && tg.y != 0)
+				{
+					// enter one instance of the pending top-level leaf group
+					const int bit = 31 - __clz( tg.y );
+					tg.y &= ~(1u << bit);
+					const uint32_t inst = __ldg( scene.tlasLeafIds + tg.x + bit );
+					if (tg.y != 0) WIDE_PUSH( tg );
+					if (ng.y > 0x00ffffffu) WIDE_PUSH( ng );
+					WIDE_PUSH( make_uint2( 0, 0 ) );
+					const InstTrav& it = scene.instances[inst];
+					if (!(it.flags & 1u))
+					{
+						const float4 r0 = it.r0, r1 = it.r1, r2 = it.r2;
+						const float3 wO = O, wD = D;
+						O.x = __fmaf_rn( r0.x, wO.x, __fmaf_rn( r0.y, wO.y, __fmaf_rn( r0.z, wO.z, r0.w ) ) );
+						O.y = __fmaf_rn( r1.x, wO.x, __fmaf_rn( r1.y, wO.y, __fmaf_rn( r1.z, wO.z, r1.w ) ) );
+						O.z = __fmaf_rn( r2.x, wO.x, __fmaf_rn( r2.y, wO.y, __fmaf_rn( r2.z, wO.z, r2.w ) ) );
+						D.x = __fmaf_rn( r0.x, wD.x, __fmaf_rn( r0.y, wD.y, __fmul_rn( r0.z, wD.z ) ) );
+						D.y = __fmaf_rn( r1.x, wD.x, __fmaf_rn( r1.y, wD.y, __fmul_rn( r1.z, wD.z ) ) );
+						D.z = __fmaf_rn( r2.x, wD.x, __fmaf_rn( r2.y, wD.y, __fmul_rn( r2.z, wD.z ) ) );
+						idx = SafeRcpDir( D.x ), idy = SafeRcpDir( D.y ), idz = SafeRcpDir( D.z );
+						octinv = (D.x < 0 ? 0 : 4) | (D.y < 0 ? 0 : 2) | (D.z < 0 ? 0 : 1);
+					}
+					curInst = inst;
+					ng = make_uint2( it.rootNode, 0x80000000u ), tg = make_uint2( 0, 0 );
+				}
+			}
 			if (ng.y <= 0x00ffffffu && tg.y == 0)
 			{
-				// nothing left for this ray
+				// nothing left for this ray (two-level: the stack is empty here, the loop above ran dry)
 				if (ANYHIT) sink.AnyHit( workIdx, false );
 				else
 				{
 					TraceResult r;
-					r.t = tmax, r.inst = 0, r.prim = bestPrim, r.u = bestU, r.v = bestV;
+					r.t = tmax, r.inst = TWO_LEVEL ? bestInst : 0u, r.prim = bestPrim, r.u = bestU, r.v = bestV;
 					sink.Closest( workIdx, bestPrim != 0xffffffffu, r );
 				}
 				active = false;
@@ -113,20 +169,22 @@ __device__ __forceinline__ void TraverseWide( const InstTrav& blas, RaySource& s
 					O = ray.O, D = ray.D, tmin = ray.tmin, tmax = ray.tmax;
 					idx = SafeRcpDir( D.x ), idy = SafeRcpDir( D.y ), idz = SafeRcpDir( D.z );
 					octinv = (D.x < 0 ? 0 : 4) | (D.y < 0 ? 0 : 2) | (D.z < 0 ? 0 : 1);
-					ng = make_uint2( 0, 0x80000000u ), tg = make_uint2( 0, 0 );
-					sp = 0, tsp = 0, bestPrim = 0xffffffffu, bestU = bestV = 0;
+					ng = make_uint2( TWO_LEVEL ? scene.tlasRoot : scene.singleRoot, 0x80000000u ), tg = make_uint2( 0, 0 );
+					sp = 0, tsp = 0, bestPrim = 0xffffffffu, bestInst = 0xffffffffu, bestU = bestV = 0;
+					curInst = TWO_LEVEL ? NO_INST : 0u;
 				}
 			}
 		}
 		// ---- vote ------------------------------------------------------------------------------------
-		const bool hasNode = active && ng.y > 0x00ffffffu, hasTri = active && tg.y != 0;
+		const bool hasNode = active && ng.y > 0x00ffffffu;
+		const bool hasTri = active && tg.y != 0 && (!TWO_LEVEL || curInst != NO_INST);
 		const uint32_t nodeMask = __ballot_sync( 0xffffffffu, hasNode ), triMask = __ballot_sync( 0xffffffffu, hasTri );
 		const uint32_t fullMask = __ballot_sync( 0xffffffffu, tsp >= WIDE_TRI_STACK - 1 );
 		if ((nodeMask | triMask) == 0)
 		{
-			// no active lane is left (active lanes always hold a node or a triangle group here)
-			if (exhausted) break;
-			if (idleMask != 0xffffffffu) continue;	// cannot happen; keeps the loop safe
+			// no lane can do a node or a triangle step: either nothing is active, or (two-level) lanes are about to
+			// enter an instance at the top of the next iteration
+			if (exhausted && __ballot_sync( 0xffffffffu, active ) == 0) break;
 			continue;
 		}
 		const bool triPhase = triMask != 0 && (nodeMask == 0 || __popc( triMask ) >= tune.triThreshold || fullMask != 0);
@@ -167,7 +225,8 @@ __device__ __forceinline__ void TraverseWide( const InstTrav& blas, RaySource& s
 							else if (t > tmin)
 							{
 								const uint32_t prim = __float_as_uint( v0.w );
-								if (t < tmax || (t == tmax && prim < bestPrim)) tmax = t, bestPrim = prim, bestU = u, bestV = v;
+								const bool closer = t < tmax || (t == tmax && (curInst < bestInst || (curInst == bestInst && prim < bestPrim)));
+								if (closer) tmax = t, bestPrim = prim, bestInst = curInst, bestU = u, bestV = v;
 							}
 						}
 					}
@@ -181,11 +240,7 @@ __device__ __forceinline__ void TraverseWide( const InstTrav& blas, RaySource& s
 			const uint32_t hits = ng.y;
 			const int bit = 31 - __clz( hits );
 			ng.y &= ~(1u << bit);
-			if (ng.y > 0x00ffffffu)
-			{
-				if (sp < WIDE_SMEM_STACK) smemStack[sp][threadIdx.x] = ng; else localStack[sp - WIDE_SMEM_STACK] = ng;
-				sp++;
-			}
+			if (ng.y > 0x00ffffffu) WIDE_PUSH( ng );
 			const uint32_t slot = (uint32_t)(bit - 24) ^ octinv;
 			const uint32_t rel = __popc( hits & ~(0xffffffffu << slot) & 0xffu );
 			const uint4* np = nodes + (size_t)(ng.x + rel) * 5;
@@ -242,6 +297,8 @@ __device__ __forceinline__ void TraverseWide( const InstTrav& blas, RaySource& s
 			}
 		}
 	}
+#undef WIDE_PUSH
+#undef WIDE_TOP
 }
 
 } // namespace lh2b
