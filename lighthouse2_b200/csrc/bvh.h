@@ -39,7 +39,7 @@ static_assert( sizeof( CwNode ) == 80, "CwNode must be 80 bytes" );
 
 /* Leaf triangle record used by traversal: 48 bytes, Moeller-Trumbore form.
    v0.w holds the primitive index (triangle index in the mesh) as int bits. */
-struct CwTri { float v0[3]; int32_t prim; float e1[3]; float pad1; float e2[3]; float pad2; };
+struct CwTri { float v0[3]; int32_t prim; float e1[3]; uint32_t inst; float e2[3]; float pad2; };	// inst: owning instance in flat scenes (see core.cu)
 static_assert( sizeof( CwTri ) == 48, "CwTri must be 48 bytes" );
 
 /* Plain binary BVH used as the builder intermediate (host SAH builder and GPU LBVH both emit this). */
@@ -62,7 +62,10 @@ struct CwBvh
 /* Host builders (bvh_build_cpu.cpp). */
 void BuildBvh2SAH( const float* verts4, int triCount, std::vector<Bvh2Node>& nodes, std::vector<uint32_t>& primIdx );
 void BuildBvh2FromBoxes( const Aabb* boxes, int count, int maxLeaf, std::vector<Bvh2Node>& nodes, std::vector<uint32_t>& primIdx );
+/* linkedRoots (top level only): when given, leaf 'prim' is emitted as an INTERNAL child holding a copy of
+   linkedRoots[prim] (the root node of that instance's BLAS, indices already absolute) - the flat-scene layout. */
 void CollapseToCwBvh( const std::vector<Bvh2Node>& bvh2, const std::vector<uint32_t>& primIdx,
-	const float* verts4 /* null for TLAS */, CwBvh& out );
+	const float* verts4 /* null for TLAS */, CwBvh& out, uint32_t nodeOffset = 0, uint32_t triOffset = 0, const CwNode* linkedRoots = nullptr );
+/* nodeOffset / triOffset are added to every childBase / triBase this call writes (absolute arena indices). */
 
 } // namespace lh2b

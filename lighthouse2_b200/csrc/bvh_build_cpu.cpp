@@ -198,12 +198,14 @@ static void AssignSlots( const Bvh2Node* bvh2, const int* child, int n, const fl
 	}
 }
 
-void CollapseToCwBvh( const std::vector<Bvh2Node>& bvh2v, const std::vector<uint32_t>& primIdx, const float* verts4, CwBvh& out )
+void CollapseToCwBvh( const std::vector<Bvh2Node>& bvh2v, const std::vector<uint32_t>& primIdx, const float* verts4, CwBvh& out, uint32_t nodeOffset, uint32_t triOffset, const CwNode* linkedRoots )
 {
 	const Bvh2Node* bvh2 = bvh2v.data();
 	out.nodes.clear(), out.tris.clear(), out.leafIds.clear();
 	memcpy( out.bounds.lo, bvh2[0].lo, 12 ), memcpy( out.bounds.hi, bvh2[0].hi, 12 );
 	struct Task { int bvh2Node, cwNode; };
+	struct Link { int cwNode; uint32_t prim; };
+	std::vector<Link> links;
 	std::vector<Task> queue;
 	out.nodes.push_back( CwNode{} );
 	queue.push_back( { 0, 0 } );
@@ -214,7 +216,7 @@ void CollapseToCwBvh( const std::vector<Bvh2Node>& bvh2v, const std::vector<uint
 			const float* v = verts4 + (size_t)prim * 12;
 			CwTri t;
 			for (int a = 0; a < 3; a++) t.v0[a] = v[a], t.e1[a] = v[4 + a] - v[a], t.e2[a] = v[8 + a] - v[a];
-			t.prim = (int32_t)prim, t.pad1 = 0, t.pad2 = 0;
+			t.prim = (int32_t)prim, t.inst = 0, t.pad2 = 0;
 			out.tris.push_back( t );
 		}
 		else out.leafIds.push_back( prim );
@@ -266,18 +268,26 @@ void CollapseToCwBvh( const std::vector<Bvh2Node>& bvh2v, const std::vector<uint
 		bytes[12] = e[0], bytes[13] = e[1], bytes[14] = e[2];
 		uint8_t imask = 0;
 		int internalCount = 0, triCount = 0;
-		for (int s = 0; s < 8; s++) if (childInSlot[s] >= 0 && !IsLeaf( bvh2[childInSlot[s]] )) imask |= 1 << s, internalCount++;
+		for (int s = 0; s < 8; s++) if (childInSlot[s] >= 0 && (linkedRoots || !IsLeaf( bvh2[childInSlot[s]] ))) imask |= 1 << s, internalCount++;
 		bytes[15] = imask;
 		const uint32_t childBase = (uint32_t)out.nodes.size();
 		const uint32_t triBase = (uint32_t)(verts4 ? out.tris.size() : out.leafIds.size());
-		memcpy( bytes + 16, &childBase, 4 ), memcpy( bytes + 20, &triBase, 4 );
+		const uint32_t childBaseAbs = childBase + nodeOffset, triBaseAbs = triBase + triOffset;
+		memcpy( bytes + 16, &childBaseAbs, 4 ), memcpy( bytes + 20, &triBaseAbs, 4 );
 		int nextInternal = 0;
 		for (int s = 0; s < 8; s++)
 		{
 			const int ci = childInSlot[s];
 			if (ci < 0) continue; // meta 0, boxes 0
 			const Bvh2Node& c = bvh2[ci];
-			if (IsLeaf( c ))
+			if (IsLeaf( c ) && linkedRoots)
+			{
+				// flat scene: the instance's BLAS root is copied in as an internal child
+				bytes[24 + s] = (uint8_t)((1 << 5) | (24 + s));
+				links.push_back( { (int)childBase + nextInternal, primIdx[~c.left] } );
+				nextInternal++;
+			}
+			else if (IsLeaf( c ))
 			{
 				const int first = ~c.left, count = c.right;
 				// count is 1..3 by construction; unary encode
@@ -306,6 +316,7 @@ void CollapseToCwBvh( const std::vector<Bvh2Node>& bvh2v, const std::vector<uint
 		for (int k = 0; k < internalCount; k++) out.nodes.push_back( CwNode{} );
 		memcpy( &out.nodes[task.cwNode], bytes, 80 );
 	}
+	for (const Link& l : links) out.nodes[l.cwNode] = linkedRoots[l.prim];
 }
 
 } // namespace lh2b

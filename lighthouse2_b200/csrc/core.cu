@@ -99,7 +99,8 @@ static void RebuildMeshHost( lh2b_core* core, Mesh& mesh )
 	if (cw.tris.empty()) cw.tris.push_back( CwTri{} );
 	if (mesh.nodeCount > mesh.nodeCap) mesh.nodeOff = ArenaAllocNodes( core, mesh.nodeCount, mesh.nodeCap );
 	if (cw.tris.size() > mesh.triCap) mesh.triOff = ArenaAllocTris( core, (uint32_t)cw.tris.size(), mesh.triCap );
-	BakeOffsets( cw.nodes, mesh.nodeOff, mesh.triOff );
+	BakeOffsets( cw.nodes, mesh.nodeOff, mesh.triOff );	// slots are known only after the build: bake now
+	mesh.rootNode = cw.nodes[0], mesh.taggedInst = 0;	// triangle records are emitted with inst = 0
 	CUDA_CHECK( cudaMemcpyAsync( core->arenaNodes.ptr + (size_t)mesh.nodeOff * 5, cw.nodes.data(), cw.nodes.size() * sizeof( CwNode ), cudaMemcpyHostToDevice, core->stream ) );
 	CUDA_CHECK( cudaMemcpyAsync( core->arenaTris.ptr + (size_t)mesh.triOff * 3, cw.tris.data(), cw.tris.size() * sizeof( CwTri ), cudaMemcpyHostToDevice, core->stream ) );
 	CUDA_CHECK( cudaStreamSynchronize( core->stream ) );
@@ -151,15 +152,40 @@ void UpdateAccelerationStructures( lh2b_core* core )
 		desc[i].invTransform.C = { inv[8], inv[9], inv[10], inv[11] }, desc[i].invTransform.D = { 0, 0, 0, 1 };
 		TransformBounds( mesh.bounds, inst.xform, boxes[i] );
 	}
+	// flat scene: every instance has the identity transform and no mesh is instanced twice. Then no ray ever needs
+	// transforming: the top level links copies of the BLAS roots as internal children and traversal is single-level;
+	// the instance index of a hit comes from the triangle record.
+	bool flat = n > 0;
+	{
+		std::vector<int> uses( core->meshes.size(), 0 );
+		for (int i = 0; i < n; i++) if (!IsIdentity( core->instances[i].xform ) || ++uses[core->instances[i].mesh] > 1) flat = false;
+	}
+	std::vector<CwNode> linked;
+	if (flat)
+	{
+		linked.resize( n );
+		for (int i = 0; i < n; i++)
+		{
+			Mesh& mesh = *core->meshes[core->instances[i].mesh];
+			linked[i] = mesh.rootNode;
+			if (mesh.taggedInst != i)
+			{
+				LaunchTagTriangles( core->arenaTris.ptr + (size_t)mesh.triOff * 3, mesh.triCount, (uint32_t)i, core->stream );
+				mesh.taggedInst = i;
+			}
+		}
+	}
 	std::vector<Bvh2Node> bvh2;
 	std::vector<uint32_t> primIdx;
 	BuildBvh2FromBoxes( boxes.data(), n, 1, bvh2, primIdx );
+	// the top level's slot must exist before encoding (linked roots are absolute already and must not be re-based)
+	const uint32_t tlasNeed = (uint32_t)(2 * n + 2);
+	if (tlasNeed > core->tlasCap) core->tlasOff = ArenaAllocNodes( core, tlasNeed, core->tlasCap );
 	CwBvh cw;
-	CollapseToCwBvh( bvh2, primIdx, nullptr, cw );
+	CollapseToCwBvh( bvh2, primIdx, nullptr, cw, core->tlasOff, 0, flat ? linked.data() : nullptr );
 	if (cw.leafIds.empty()) cw.leafIds.push_back( 0 );
 	core->tlasNodeCount = (uint32_t)cw.nodes.size();
-	if (core->tlasNodeCount > core->tlasCap) core->tlasOff = ArenaAllocNodes( core, core->tlasNodeCount, core->tlasCap );
-	BakeOffsets( cw.nodes, core->tlasOff, 0 );
+	if (core->tlasNodeCount > core->tlasCap) throw CoreError( "internal: top-level node estimate too small" );
 	CUDA_CHECK( cudaMemcpyAsync( core->arenaNodes.ptr + (size_t)core->tlasOff * 5, cw.nodes.data(), cw.nodes.size() * sizeof( CwNode ), cudaMemcpyHostToDevice, core->stream ) );
 	core->tlasLeafIds.Upload( cw.leafIds.data(), cw.leafIds.size(), core->stream );
 	core->instTrav.Upload( trav.data(), trav.size(), core->stream );
@@ -167,11 +193,12 @@ void UpdateAccelerationStructures( lh2b_core* core )
 	CUDA_CHECK( cudaStreamSynchronize( core->stream ) );
 	core->scene.nodes = core->arenaNodes.ptr, core->scene.tris = core->arenaTris.ptr;
 	core->scene.tlasRoot = core->tlasOff;
-	core->scene.singleRoot = n > 0 ? core->meshes[core->instances[0].mesh]->nodeOff : 0;
+	// flat scenes start at the top-level root (whose children are BLAS-root copies), or directly at the BLAS root
+	core->scene.singleRoot = !flat ? 0 : (n == 1 ? core->meshes[core->instances[0].mesh]->nodeOff : core->tlasOff);
 	core->scene.tlasLeafIds = core->tlasLeafIds.ptr;
 	core->scene.instances = core->instTrav.ptr;
 	core->scene.instanceCount = n;
-	core->scene.singleIdentity = (n == 1 && IsIdentity( core->instances[0].xform )) ? 1 : 0;
+	core->scene.singleIdentity = flat ? 1 : 0;
 	core->tlasBuildMs = (float)(NowMs() - t0);
 }
 

@@ -29,6 +29,8 @@ struct Mesh
 	bool dirty = true;
 	float buildMs = 0, sahCost = 0;
 	uint32_t nodeCount = 0;
+	CwNode rootNode = {};			// host copy of the BLAS root (absolute indices), linked into flat top levels
+	int taggedInst = -1;			// instance index currently written into the triangle records (flat scenes)
 };
 
 struct Instance { int mesh = 0; float xform[12] = { 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0 }; };

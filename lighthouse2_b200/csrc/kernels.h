@@ -18,6 +18,7 @@ void LaunchExtendCounted( const DevScene& scene, const PathSet& in, float4* hits
 void LaunchConnect( const DevScene& scene, const PathSet& conn, float4* accumulator, const uint32_t* countPtr, uint32_t* workCounter, uint32_t maxRays, int smCount, cudaStream_t s );
 void LaunchShade( const RenderParams& p, const PathSet& in, const PathSet& out, const float4* hits, const PathSet& conn,
 	int pathLength, uint32_t R0, bool useNEE, uint32_t maxPaths, int smCount, cudaStream_t s );
+void LaunchTagTriangles( float4* tris, int triCount, uint32_t inst, cudaStream_t s );
 void LaunchFinalize( const float4* accumulator, float4* out, int n, int samplesTaken, cudaStream_t s );
 
 } // namespace lh2b

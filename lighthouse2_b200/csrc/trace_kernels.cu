@@ -140,17 +140,13 @@ __global__ void __launch_bounds__( 128 ) connectKernel( const DevScene scene, co
 struct BufferRaySource
 {
 	const float4* __restrict__ O4; const float4* __restrict__ D4; bool shadow;
-	__device__ __forceinline__ bool Load( const uint32_t i, WideRay& r ) const
+	__device__ __forceinline__ bool Load( const uint32_t i, WideRay& r, uint32_t& tag ) const
 	{
 		const float4 o = O4[i], d = D4[i];
 		r.O = make_float3( o.x, o.y, o.z ), r.D = make_float3( d.x, d.y, d.z );
 		r.tmin = 0.0f, r.tmax = shadow ? d.w : 1e34f;
+		tag = i;
 		return true;
-	}
-	__device__ __forceinline__ void Reload( const uint32_t i, float3& O, float3& D ) const
-	{
-		const float4 o = O4[i], d = D4[i];
-		O = make_float3( o.x, o.y, o.z ), D = make_float3( d.x, d.y, d.z );
 	}
 };
 
@@ -241,28 +237,23 @@ struct TiledPrimarySource
 		if (x >= (uint32_t)p->w || y >= (uint32_t)p->h) return 0xffffffffu;
 		return x + y * p->w + s * (p->w * p->h);
 	}
-	__device__ __forceinline__ bool Load( const uint32_t work, WideRay& r ) const
+	__device__ __forceinline__ bool Load( const uint32_t work, WideRay& r, uint32_t& tag ) const
 	{
 		const uint32_t pathIdx = PathOf( work );
 		if (pathIdx == 0xffffffffu) return false;
+		tag = pathIdx;
 		GeneratePrimary( *p, pathIdx, r.O, r.D );
 		r.tmin = 0.0f, r.tmax = 1e34f;
 		outO[pathIdx] = make_float4( r.O.x, r.O.y, r.O.z, __uint_as_float( (pathIdx << 6) + 1 /* S_SPECULAR */ ) );
 		outD[pathIdx] = make_float4( r.D.x, r.D.y, r.D.z, 0 );
 		return true;
 	}
-	__device__ __forceinline__ void Reload( const uint32_t work, float3& O, float3& D ) const
-	{
-		const uint32_t pathIdx = PathOf( work );
-		const float4 o = outO[pathIdx], d = outD[pathIdx];	// written by this thread in Load
-		O = make_float3( o.x, o.y, o.z ), D = make_float3( d.x, d.y, d.z );
-	}
 };
 
 struct TiledHitSink
 {
 	const TiledPrimarySource* src; float4* __restrict__ hits;
-	__device__ __forceinline__ void Closest( const uint32_t work, const bool hit, const TraceResult& r ) const { hits[src->PathOf( work )] = PackHit( hit, r ); }
+	__device__ __forceinline__ void Closest( const uint32_t pathIdx, const bool hit, const TraceResult& r ) const { hits[pathIdx] = PackHit( hit, r ); }
 	__device__ __forceinline__ void AnyHit( const uint32_t, const bool ) const {}
 };
 
@@ -299,6 +290,18 @@ template <bool TWO_LEVEL> __global__ void __launch_bounds__( WIDE_BLOCK ) wideCo
 	BufferRaySource src = { conn.O, conn.D, true };
 	ConnectSink sink = { conn.T, accumulator };
 	TraverseWide<true, TWO_LEVEL>( scene, src, sink, *countPtr, workCounter, tune );
+}
+
+/* flat scenes: write the owning instance index into the spare word of every traversal triangle */
+__global__ void tagTrianglesKernel( float4* tris, const int triCount, const uint32_t inst )
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < triCount) tris[(size_t)i * 3 + 1].w = __uint_as_float( inst );
+}
+
+void LaunchTagTriangles( float4* tris, int triCount, uint32_t inst, cudaStream_t s )
+{
+	if (triCount > 0) tagTrianglesKernel<<<(triCount + 255) / 256, 256, 0, s>>>( tris, triCount, inst );
 }
 
 static uint32_t PersistentGrid( uint32_t maxItems, int smCount, int blocksPerSM )

@@ -180,8 +180,9 @@ __device__ __forceinline__ bool Traverse( const DevScene& scene, const float3 wO
 							else if (t > tmin)
 							{
 								const uint32_t prim = __float_as_uint( v0.w );
-								const bool closer = t < tmax || (t == tmax && (curInst < bestInst || (curInst == bestInst && prim < bestPrim)));
-								if (closer) tmax = t, bestInst = curInst, bestPrim = prim, bestU = u, bestV = v;
+								const uint32_t inst = scene.singleIdentity ? __float_as_uint( e1.w ) : curInst;	// flat scenes: from the triangle record
+								const bool closer = t < tmax || (t == tmax && (inst < bestInst || (inst == bestInst && prim < bestPrim)));
+								if (closer) tmax = t, bestInst = inst, bestPrim = prim, bestU = u, bestV = v;
 							}
 						}
 					}

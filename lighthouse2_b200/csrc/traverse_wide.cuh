@@ -45,9 +45,9 @@ struct WideRay
 	float tmin, tmax;
 };
 
-/* RaySource: bool Load( uint32_t workIdx, WideRay& ) (false: nothing to trace for this index);
-              void Reload( uint32_t workIdx, float3& O, float3& D ) (world-space ray again, after leaving an instance)
-   HitSink:   void Closest( uint32_t workIdx, bool hit, const TraceResult& ) / void AnyHit( uint32_t workIdx, bool occluded )
+/* RaySource: bool Load( uint32_t workIdx, WideRay&, uint32_t& tag ) (false: nothing to trace for this index; tag is
+              an opaque per-ray word handed back to the sink, e.g. the path index)
+   HitSink:   void Closest( uint32_t tag, bool hit, const TraceResult& ) / void AnyHit( uint32_t tag, bool occluded )
 
    TWO_LEVEL: the lane is either in the top level (curInst == ~0: node groups index TLAS nodes, leaf groups are
    instances) or inside one instance. Entering an instance transforms the ray, pushes the remaining top-level work and
@@ -60,6 +60,7 @@ __device__ __forceinline__ void TraverseWide( const DevScene& scene, RaySource& 
 	const WideTuning tune )
 {
 	__shared__ uint2 smemStack[WIDE_SMEM_STACK][WIDE_BLOCK];
+	__shared__ float worldRay[TWO_LEVEL ? 6 : 1][WIDE_BLOCK];	// world-space O, D while the lane is inside a transformed instance
 	uint2 localStack[WIDE_LOCAL_STACK];
 	uint2 triStack[WIDE_TRI_STACK];
 	const uint32_t lane = threadIdx.x & 31;
@@ -106,9 +107,14 @@ __device__ __forceinline__ void TraverseWide( const DevScene& scene, RaySource& 
 					// sentinel: leave the instance once all of its triangles are done
 					if (tg.y != 0 || tsp > 0) break;
 					sp--, curInst = NO_INST;
-					src.Reload( workIdx, O, D );
-					idx = SafeRcpDir( D.x ), idy = SafeRcpDir( D.y ), idz = SafeRcpDir( D.z );
-					octinv = (D.x < 0 ? 0 : 4) | (D.y < 0 ? 0 : 2) | (D.z < 0 ? 0 : 1);
+					if (top.x != 0)
+					{
+						// the instance had a transform: restore the world-space ray
+						O = make_float3( worldRay[0][threadIdx.x], worldRay[1][threadIdx.x], worldRay[2][threadIdx.x] );
+						D = make_float3( worldRay[3][threadIdx.x], worldRay[4][threadIdx.x], worldRay[5][threadIdx.x] );
+						idx = SafeRcpDir( D.x ), idy = SafeRcpDir( D.y ), idz = SafeRcpDir( D.z );
+						octinv = (D.x < 0 ? 0 : 4) | (D.y < 0 ? 0 : 2) | (D.z < 0 ? 0 : 1);
+					}
 				}
 				if (curInst == NO_INST && tg.y != 0)
 				{
@@ -118,12 +124,15 @@ __device__ __forceinline__ void TraverseWide( const DevScene& scene, RaySource& 
 					const uint32_t inst = __ldg( scene.tlasLeafIds + tg.x + bit );
 					if (tg.y != 0) WIDE_PUSH( tg );
 					if (ng.y > 0x00ffffffu) WIDE_PUSH( ng );
-					WIDE_PUSH( make_uint2( 0, 0 ) );
 					const InstTrav& it = scene.instances[inst];
-					if (!(it.flags & 1u))
+					const bool transformed = !(it.flags & 1u);
+					WIDE_PUSH( make_uint2( transformed ? 1u : 0u, 0 ) );	// sentinel; x tells whether the ray must be restored
+					if (transformed)
 					{
 						const float4 r0 = it.r0, r1 = it.r1, r2 = it.r2;
 						const float3 wO = O, wD = D;
+						worldRay[0][threadIdx.x] = O.x, worldRay[1][threadIdx.x] = O.y, worldRay[2][threadIdx.x] = O.z;
+						worldRay[3][threadIdx.x] = D.x, worldRay[4][threadIdx.x] = D.y, worldRay[5][threadIdx.x] = D.z;
 						O.x = __fmaf_rn( r0.x, wO.x, __fmaf_rn( r0.y, wO.y, __fmaf_rn( r0.z, wO.z, r0.w ) ) );
 						O.y = __fmaf_rn( r1.x, wO.x, __fmaf_rn( r1.y, wO.y, __fmaf_rn( r1.z, wO.z, r1.w ) ) );
 						O.z = __fmaf_rn( r2.x, wO.x, __fmaf_rn( r2.y, wO.y, __fmaf_rn( r2.z, wO.z, r2.w ) ) );
@@ -144,7 +153,7 @@ __device__ __forceinline__ void TraverseWide( const DevScene& scene, RaySource& 
 				else
 				{
 					TraceResult r;
-					r.t = tmax, r.inst = TWO_LEVEL ? bestInst : 0u, r.prim = bestPrim, r.u = bestU, r.v = bestV;
+					r.t = tmax, r.inst = bestInst, r.prim = bestPrim, r.u = bestU, r.v = bestV;
 					sink.Closest( workIdx, bestPrim != 0xffffffffu, r );
 				}
 				active = false;
@@ -163,9 +172,9 @@ __device__ __forceinline__ void TraverseWide( const DevScene& scene, RaySource& 
 			{
 				const uint32_t mine = base + __popc( idleMask & ((1u << lane) - 1) );
 				WideRay ray;
-				if (mine < rayCount && src.Load( mine, ray ))
+				if (mine < rayCount && src.Load( mine, ray, workIdx ))
 				{
-					workIdx = mine, active = true;
+					active = true;
 					O = ray.O, D = ray.D, tmin = ray.tmin, tmax = ray.tmax;
 					idx = SafeRcpDir( D.x ), idy = SafeRcpDir( D.y ), idz = SafeRcpDir( D.z );
 					octinv = (D.x < 0 ? 0 : 4) | (D.y < 0 ? 0 : 2) | (D.z < 0 ? 0 : 1);
@@ -225,8 +234,9 @@ __device__ __forceinline__ void TraverseWide( const DevScene& scene, RaySource& 
 							else if (t > tmin)
 							{
 								const uint32_t prim = __float_as_uint( v0.w );
-								const bool closer = t < tmax || (t == tmax && (curInst < bestInst || (curInst == bestInst && prim < bestPrim)));
-								if (closer) tmax = t, bestPrim = prim, bestInst = curInst, bestU = u, bestV = v;
+								const uint32_t inst = TWO_LEVEL ? curInst : __float_as_uint( e1.w );	// flat scenes: from the triangle record
+								const bool closer = t < tmax || (t == tmax && (inst < bestInst || (inst == bestInst && prim < bestPrim)));
+								if (closer) tmax = t, bestPrim = prim, bestInst = inst, bestU = u, bestV = v;
 							}
 						}
 					}
