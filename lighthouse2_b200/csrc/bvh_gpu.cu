@@ -1,0 +1,497 @@
+/* bvh_gpu.cu - GPU construction of the acceleration structures: Morton-code LBVH (Karras 2012) -> bottom-up bounds ->
+   greedy collapse to 8-wide -> CWBVH encoding, all on the core's stream without host round trips. Also the "refit"
+   path (same topology, new bounds, re-collapse) and the per-frame top level over instance boxes.
+
+   Replaces the closed OptiX builders: optixAccelBuild on triangles (lib/rendercore_optix7/core_mesh.cpp:67-129, always
+   a full rebuild there) and on instances (lib/rendercore_optix7/rendercore.cpp:767-797, every Render).
+
+   Stages (n primitives; triangles for a BLAS, instances for the TLAS):
+     1. boundsKernel ......... primitive boxes + scene box (block reduce + float atomics)             24n B read
+     2. mortonKernel ......... 63-bit Morton code of the box centre                                     8n B written
+     3. cub::DeviceRadixSort . (code, primitive index) pairs - the one library call in the builder
+     4. radixTreeKernel ...... Karras' binary radix tree over the sorted codes (ties broken by index)
+     5. fitKernel ............ leaf boxes, then parents bottom-up (second arrival continues)            = refit
+     6. collapseKernel ....... persistent cooperative kernel, one BFS level per grid.sync(): each task turns one binary
+                               subtree root into one 80-byte CWBVH node (<= 8 children, octant slots, quantised boxes),
+                               emits leaf triangles in Moeller-Trumbore form and queues the internal children.
+   Encoding rules are identical to the host builder (bvh_build_cpu.cpp); both are checked against the brute-force oracle.
+*/
+#include "core.h"
+#include "kernels.h"
+#include <cooperative_groups.h>
+#include <cub/device/device_radix_sort.cuh>
+#include <cfloat>
+
+namespace cg = cooperative_groups;
+
+namespace lh2b
+{
+
+struct BuildTask { int bvh2Node; uint32_t cwNode; };
+
+struct GpuBuildScratch
+{
+	DevBuf<float4> primLo, primHi;			// primitive boxes
+	DevBuf<uint64_t> keys, keysAlt;
+	DevBuf<uint32_t> idx, idxAlt;
+	DevBuf<uint8_t> cubTemp;
+	DevBuf<float4> nodeLo, nodeHi;			// 2n-1 binary nodes: internal [0, n-1), leaves [n-1, 2n-1)
+	DevBuf<int2> children;					// per internal node
+	DevBuf<int2> range;						// per internal node: first/last sorted position
+	DevBuf<int> parent;						// per binary node
+	DevBuf<uint32_t> visit;					// per internal node arrival counter
+	DevBuf<BuildTask> queue;
+	DevBuf<uint32_t> ctrl;					// [0] node counter, [1] leaf counter, [2] queue tail, [3..8] scene box as ordered ints, [9] error flag
+};
+
+/* ---- float atomics through order-preserving integer keys ---- */
+__device__ __forceinline__ int FloatOrdered( const float f ) { const int i = __float_as_int( f ); return i >= 0 ? i : i ^ 0x7fffffff; }
+__device__ __forceinline__ float OrderedFloat( const int i ) { return __int_as_float( i >= 0 ? i : i ^ 0x7fffffff ); }
+
+__global__ void initCtrlKernel( uint32_t* ctrl )
+{
+	ctrl[0] = 1, ctrl[1] = 0, ctrl[2] = 1, ctrl[9] = 0;
+	int* box = (int*)(ctrl + 3);
+	box[0] = box[1] = box[2] = FloatOrdered( FLT_MAX ), box[3] = box[4] = box[5] = FloatOrdered( -FLT_MAX );
+}
+
+/* stage 1 for triangles */
+__global__ void triBoundsKernel( const float4* __restrict__ verts, const int n, float4* __restrict__ lo, float4* __restrict__ hi, uint32_t* ctrl )
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	float3 a = make_float3( FLT_MAX, FLT_MAX, FLT_MAX ), b = make_float3( -FLT_MAX, -FLT_MAX, -FLT_MAX );
+	if (i < n)
+	{
+		const float4 v0 = verts[i * 3], v1 = verts[i * 3 + 1], v2 = verts[i * 3 + 2];
+		a = make_float3( fminf( v0.x, fminf( v1.x, v2.x ) ), fminf( v0.y, fminf( v1.y, v2.y ) ), fminf( v0.z, fminf( v1.z, v2.z ) ) );
+		b = make_float3( fmaxf( v0.x, fmaxf( v1.x, v2.x ) ), fmaxf( v0.y, fmaxf( v1.y, v2.y ) ), fmaxf( v0.z, fmaxf( v1.z, v2.z ) ) );
+		lo[i] = make_float4( a.x, a.y, a.z, 0 ), hi[i] = make_float4( b.x, b.y, b.z, 0 );
+	}
+	// warp reduce, one atomic set per warp
+	for (int o = 16; o > 0; o >>= 1)
+	{
+		a.x = fminf( a.x, __shfl_xor_sync( 0xffffffffu, a.x, o ) ), a.y = fminf( a.y, __shfl_xor_sync( 0xffffffffu, a.y, o ) ), a.z = fminf( a.z, __shfl_xor_sync( 0xffffffffu, a.z, o ) );
+		b.x = fmaxf( b.x, __shfl_xor_sync( 0xffffffffu, b.x, o ) ), b.y = fmaxf( b.y, __shfl_xor_sync( 0xffffffffu, b.y, o ) ), b.z = fmaxf( b.z, __shfl_xor_sync( 0xffffffffu, b.z, o ) );
+	}
+	if ((threadIdx.x & 31) == 0)
+	{
+		int* box = (int*)(ctrl + 3);
+		atomicMin( box + 0, FloatOrdered( a.x ) ), atomicMin( box + 1, FloatOrdered( a.y ) ), atomicMin( box + 2, FloatOrdered( a.z ) );
+		atomicMax( box + 3, FloatOrdered( b.x ) ), atomicMax( box + 4, FloatOrdered( b.y ) ), atomicMax( box + 5, FloatOrdered( b.z ) );
+	}
+}
+
+/* stage 1 for instances: world box of the transformed mesh box (8 corners), padded like the host path */
+struct InstBuildIn { float xform[12]; const float4* bounds; uint64_t pad; };	// bounds: the mesh's device-resident {lo, hi}
+__global__ void instBoundsKernel( const InstBuildIn* __restrict__ inst, const int n, float4* __restrict__ lo, float4* __restrict__ hi, uint32_t* ctrl )
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const InstBuildIn in = inst[i];
+	const float4 mlo = in.bounds[0], mhi = in.bounds[1];
+	float a[3] = { 1e34f, 1e34f, 1e34f }, b[3] = { -1e34f, -1e34f, -1e34f };
+	for (int k = 0; k < 8; k++)
+	{
+		const float x = (k & 1) ? mhi.x : mlo.x, y = (k & 2) ? mhi.y : mlo.y, z = (k & 4) ? mhi.z : mlo.z;
+		for (int c = 0; c < 3; c++)
+		{
+			const float v = in.xform[c * 4] * x + in.xform[c * 4 + 1] * y + in.xform[c * 4 + 2] * z + in.xform[c * 4 + 3];
+			a[c] = fminf( a[c], v ), b[c] = fmaxf( b[c], v );
+		}
+	}
+	for (int c = 0; c < 3; c++)
+	{
+		const float pad = 1e-5f * fmaxf( fabsf( a[c] ), fabsf( b[c] ) ) + 1e-30f;
+		a[c] -= pad, b[c] += pad;
+	}
+	lo[i] = make_float4( a[0], a[1], a[2], 0 ), hi[i] = make_float4( b[0], b[1], b[2], 0 );
+	int* box = (int*)(ctrl + 3);
+	atomicMin( box + 0, FloatOrdered( a[0] ) ), atomicMin( box + 1, FloatOrdered( a[1] ) ), atomicMin( box + 2, FloatOrdered( a[2] ) );
+	atomicMax( box + 3, FloatOrdered( b[0] ) ), atomicMax( box + 4, FloatOrdered( b[1] ) ), atomicMax( box + 5, FloatOrdered( b[2] ) );
+}
+
+/* stage 2 */
+__device__ __forceinline__ uint64_t Spread21( uint64_t x )
+{
+	x &= 0x1fffffull;
+	x = (x | x << 32) & 0x1f00000000ffffull;
+	x = (x | x << 16) & 0x1f0000ff0000ffull;
+	x = (x | x << 8) & 0x100f00f00f00f00full;
+	x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+	x = (x | x << 2) & 0x1249249249249249ull;
+	return x;
+}
+__global__ void mortonKernel( const float4* __restrict__ lo, const float4* __restrict__ hi, const int n, const uint32_t* __restrict__ ctrl,
+	uint64_t* __restrict__ keys, uint32_t* __restrict__ idx )
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const int* box = (const int*)(ctrl + 3);
+	const float3 smin = make_float3( OrderedFloat( box[0] ), OrderedFloat( box[1] ), OrderedFloat( box[2] ) );
+	const float3 smax = make_float3( OrderedFloat( box[3] ), OrderedFloat( box[4] ), OrderedFloat( box[5] ) );
+	const float4 a = lo[i], b = hi[i];
+	const float sx = smax.x > smin.x ? 2097151.0f / (smax.x - smin.x) : 0, sy = smax.y > smin.y ? 2097151.0f / (smax.y - smin.y) : 0;
+	const float sz = smax.z > smin.z ? 2097151.0f / (smax.z - smin.z) : 0;
+	const uint64_t x = (uint64_t)fminf( fmaxf( (0.5f * (a.x + b.x) - smin.x) * sx, 0.0f ), 2097151.0f );
+	const uint64_t y = (uint64_t)fminf( fmaxf( (0.5f * (a.y + b.y) - smin.y) * sy, 0.0f ), 2097151.0f );
+	const uint64_t z = (uint64_t)fminf( fmaxf( (0.5f * (a.z + b.z) - smin.z) * sz, 0.0f ), 2097151.0f );
+	keys[i] = (Spread21( x ) << 2) | (Spread21( y ) << 1) | Spread21( z );
+	idx[i] = i;
+}
+
+/* stage 4 */
+__device__ __forceinline__ int Delta( const uint64_t* __restrict__ keys, const int n, const int i, const int j )
+{
+	if (j < 0 || j >= n) return -1;
+	const uint64_t a = keys[i], b = keys[j];
+	if (a == b) return 64 + __clz( i ^ j );
+	return __clzll( a ^ b );
+}
+__global__ void radixTreeKernel( const uint64_t* __restrict__ keys, const int n, int2* __restrict__ children, int2* __restrict__ range,
+	int* __restrict__ parent, uint32_t* __restrict__ visit )
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n - 1) return;
+	const int d = Delta( keys, n, i, i + 1 ) - Delta( keys, n, i, i - 1 ) >= 0 ? 1 : -1;
+	const int deltaMin = Delta( keys, n, i, i - d );
+	int lmax = 2;
+	while (Delta( keys, n, i, i + lmax * d ) > deltaMin) lmax *= 2;
+	int l = 0;
+	for (int t = lmax / 2; t >= 1; t /= 2) if (Delta( keys, n, i, i + (l + t) * d ) > deltaMin) l += t;
+	const int j = i + l * d;
+	const int deltaNode = Delta( keys, n, i, j );
+	int s = 0, t = l;
+	do
+	{
+		t = (t + 1) >> 1;
+		if (Delta( keys, n, i, i + (s + t) * d ) > deltaNode) s += t;
+	} while (t > 1);
+	const int gamma = i + s * d + min( d, 0 );
+	const int first = min( i, j ), last = max( i, j );
+	const int left = first == gamma ? (n - 1) + gamma : gamma;
+	const int right = last == gamma + 1 ? (n - 1) + gamma + 1 : gamma + 1;
+	children[i] = make_int2( left, right );
+	range[i] = make_int2( first, last );
+	parent[left] = i, parent[right] = i;
+	visit[i] = 0;
+	if (i == 0) parent[0] = -1;
+}
+
+/* stage 5: leaf boxes from the (possibly updated) primitive boxes, parents bottom-up */
+__global__ void fitKernel( const float4* __restrict__ primLo, const float4* __restrict__ primHi, const uint32_t* __restrict__ idx, const int n,
+	const int2* __restrict__ children, const int* __restrict__ parent, uint32_t* __restrict__ visit, float4* __restrict__ nodeLo, float4* __restrict__ nodeHi )
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const uint32_t p = idx[i];
+	int node = (n - 1) + i;
+	float4 lo = primLo[p], hi = primHi[p];
+	nodeLo[node] = lo, nodeHi[node] = hi;
+	if (n == 1) return;
+	int cur = parent[node];
+	while (cur >= 0)
+	{
+		__threadfence();
+		if (atomicAdd( visit + cur, 1u ) == 0) return;	// first child to arrive: the sibling will carry on
+		const int2 c = children[cur];
+		const int other = c.x == node ? c.y : c.x;
+		const float4 olo = __ldcg( nodeLo + other ), ohi = __ldcg( nodeHi + other );	// written by another SM: bypass L1
+		lo = make_float4( fminf( lo.x, olo.x ), fminf( lo.y, olo.y ), fminf( lo.z, olo.z ), 0 );
+		hi = make_float4( fmaxf( hi.x, ohi.x ), fmaxf( hi.y, ohi.y ), fmaxf( hi.z, ohi.z ), 0 );
+		nodeLo[cur] = lo, nodeHi[cur] = hi;
+		node = cur, cur = parent[cur];
+	}
+}
+
+__global__ void resetVisitKernel( uint32_t* visit, const int n )
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) visit[i] = 0;
+}
+
+/* stage 6 */
+struct CollapseArgs
+{
+	int n, maxLeaf;
+	const int2* children; const int2* range; const float4* nodeLo; const float4* nodeHi; const uint32_t* idx;
+	const float4* verts;			// BLAS: triangle vertices; null for the TLAS
+	uint4* outNodes;				// arena base
+	float4* outTris;				// arena base (BLAS)
+	uint32_t* outLeafIds;			// TLAS
+	const uint32_t* linkedRootOf;	// TLAS, flat scenes: arena index of the BLAS root to copy per instance; null otherwise
+	uint32_t nodeOffset, triOffset, nodeCapacity, triCapacity;
+	BuildTask* queue; uint32_t* ctrl;
+	float4* boundsOut;				// [0] = lo, [1] = hi of the root (kept on the device for the top-level build)
+	uint32_t* countsOut;			// [0] node count, [1] leaf count, [2] overflow flag
+};
+
+__device__ __forceinline__ float HalfAreaD( const float4 lo, const float4 hi )
+{
+	const float ex = hi.x - lo.x, ey = hi.y - lo.y, ez = hi.z - lo.z;
+	return ex * ey + ey * ez + ez * ex;
+}
+
+__device__ void CollapseTask( const CollapseArgs& a, const BuildTask task )
+{
+	const int n = a.n;
+	auto leafLike = [&]( const int node ) -> bool {
+		if (node >= n - 1) return true;
+		if (a.linkedRootOf) return false;
+		const int2 r = a.range[node];
+		return r.y - r.x + 1 <= a.maxLeaf;
+	};
+	int child[8], cnt = 0;
+	const int root = task.bvh2Node;
+	if (leafLike( root )) child[cnt++] = root;
+	else
+	{
+		const int2 c = a.children[root];
+		child[cnt++] = c.x, child[cnt++] = c.y;
+		while (cnt < 8)
+		{
+			float bestA = -1;
+			int bi = -1;
+			for (int i = 0; i < cnt; i++) if (!leafLike( child[i] ))
+			{
+				const float ar = HalfAreaD( a.nodeLo[child[i]], a.nodeHi[child[i]] );
+				if (ar > bestA) bestA = ar, bi = i;
+			}
+			if (bi < 0) break;
+			const int2 c2 = a.children[child[bi]];
+			child[bi] = c2.x, child[cnt++] = c2.y;
+		}
+	}
+	const float4 rlo = a.nodeLo[root], rhi = a.nodeHi[root];
+	// octant slot assignment (same greedy rule as the host builder)
+	int slotChild[8];
+	for (int s = 0; s < 8; s++) slotChild[s] = -1;
+	{
+		const float cx = 0.5f * (rlo.x + rhi.x), cy = 0.5f * (rlo.y + rhi.y), cz = 0.5f * (rlo.z + rhi.z);
+		float dx[8], dy[8], dz[8];
+		for (int i = 0; i < cnt; i++)
+		{
+			const float4 lo = a.nodeLo[child[i]], hi = a.nodeHi[child[i]];
+			dx[i] = 0.5f * (lo.x + hi.x) - cx, dy[i] = 0.5f * (lo.y + hi.y) - cy, dz[i] = 0.5f * (lo.z + hi.z) - cz;
+		}
+		uint32_t slotUsed = 0, childDone = 0;
+		for (int round = 0; round < cnt; round++)
+		{
+			float best = -FLT_MAX;
+			int bi = -1, bs = -1;
+			for (int i = 0; i < cnt; i++) if (!(childDone >> i & 1)) for (int s = 0; s < 8; s++) if (!(slotUsed >> s & 1))
+			{
+				const float sc = ((s & 4) ? dx[i] : -dx[i]) + ((s & 2) ? dy[i] : -dy[i]) + ((s & 1) ? dz[i] : -dz[i]);
+				if (sc > best) best = sc, bi = i, bs = s;
+			}
+			slotChild[bs] = child[bi], slotUsed |= 1u << bs, childDone |= 1u << bi;
+		}
+	}
+	// counts and allocation
+	int internalCount = 0, leafPrims = 0;
+	uint32_t imask = 0;
+	for (int s = 0; s < 8; s++) if (slotChild[s] >= 0)
+	{
+		const int c = slotChild[s];
+		const bool isLeaf = leafLike( c ) && !a.linkedRootOf;
+		if (!isLeaf) imask |= 1u << s, internalCount++;
+		else leafPrims += c >= n - 1 ? 1 : a.range[c].y - a.range[c].x + 1;
+	}
+	const uint32_t childBase = internalCount ? atomicAdd( a.ctrl + 0, (uint32_t)internalCount ) : 0;
+	const uint32_t leafBase = leafPrims ? atomicAdd( a.ctrl + 1, (uint32_t)leafPrims ) : 0;
+	if (childBase + internalCount > a.nodeCapacity || leafBase + leafPrims > a.triCapacity) { a.ctrl[9] = 1; return; }
+	uint32_t queueBase = 0;
+	{
+		int realInternal = 0;
+		for (int s = 0; s < 8; s++) if (slotChild[s] >= 0 && (imask >> s & 1) && !(a.linkedRootOf && slotChild[s] >= n - 1)) realInternal++;
+		if (realInternal) queueBase = atomicAdd( a.ctrl + 2, (uint32_t)realInternal );
+	}
+	// header
+	float quantum[3];
+	uint32_t e[3];
+	const float ext[3] = { rhi.x - rlo.x, rhi.y - rlo.y, rhi.z - rlo.z };
+	for (int k = 0; k < 3; k++)
+	{
+		int ex = ext[k] > 0 ? (int)ceilf( log2f( ext[k] / 255.0f ) ) : -126;
+		ex = max( -126, min( 127, ex ) );
+		while (ex < 127 && ldexpf( 255.0f, ex ) < ext[k]) ex++;
+		e[k] = (uint32_t)(ex + 127), quantum[k] = ldexpf( 1.0f, ex );
+	}
+	uint32_t meta[8], qlo[3][8], qhi[3][8];
+	for (int s = 0; s < 8; s++) { meta[s] = 0; for (int k = 0; k < 3; k++) qlo[k][s] = qhi[k][s] = 0; }
+	int nextInternal = 0, nextQueued = 0, triCursor = 0;
+	const float p[3] = { rlo.x, rlo.y, rlo.z };
+	for (int s = 0; s < 8; s++)
+	{
+		const int c = slotChild[s];
+		if (c < 0) continue;
+		const float4 clo = a.nodeLo[c], chi = a.nodeHi[c];
+		if (imask >> s & 1)
+		{
+			meta[s] = (1u << 5) | (24u + s);
+			const uint32_t dst = childBase + nextInternal;
+			if (a.linkedRootOf && c >= n - 1)
+			{
+				// flat scene: copy the BLAS root of this instance in as the child node
+				const uint32_t inst = a.idx[c - (n - 1)];
+				const uint4* src = a.outNodes + (size_t)a.linkedRootOf[inst] * 5;
+				uint4* d = a.outNodes + (size_t)(a.nodeOffset + dst) * 5;
+				for (int k = 0; k < 5; k++) d[k] = src[k];
+			}
+			else a.queue[queueBase + nextQueued++] = BuildTask{ c, dst };
+			nextInternal++;
+		}
+		else
+		{
+			const int first = c >= n - 1 ? c - (n - 1) : a.range[c].x, count = c >= n - 1 ? 1 : a.range[c].y - a.range[c].x + 1;
+			meta[s] = (((1u << count) - 1) << 5) | (uint32_t)triCursor;
+			for (int k = 0; k < count; k++)
+			{
+				const uint32_t prim = a.idx[first + k];
+				const uint32_t at = leafBase + triCursor + k;
+				if (a.verts)
+				{
+					const float4 v0 = a.verts[prim * 3], v1 = a.verts[prim * 3 + 1], v2 = a.verts[prim * 3 + 2];
+					float4* t = a.outTris + (size_t)(a.triOffset + at) * 3;
+					t[0] = make_float4( v0.x, v0.y, v0.z, __uint_as_float( prim ) );
+					t[1] = make_float4( v1.x - v0.x, v1.y - v0.y, v1.z - v0.z, __uint_as_float( 0u ) );
+					t[2] = make_float4( v2.x - v0.x, v2.y - v0.y, v2.z - v0.z, 0 );
+				}
+				else a.outLeafIds[at] = prim;
+			}
+			triCursor += count;
+		}
+		const float cl[3] = { clo.x, clo.y, clo.z }, ch[3] = { chi.x, chi.y, chi.z };
+		for (int k = 0; k < 3; k++)
+		{
+			int ql = (int)floorf( (cl[k] - p[k]) / quantum[k] ), qh = (int)ceilf( (ch[k] - p[k]) / quantum[k] );
+			ql = max( 0, min( 255, ql ) ), qh = max( 0, min( 255, qh ) );
+			while (ql > 0 && p[k] + ql * quantum[k] > cl[k]) ql--;
+			while (qh < 255 && p[k] + qh * quantum[k] < ch[k]) qh++;
+			qlo[k][s] = (uint32_t)ql, qhi[k][s] = (uint32_t)qh;
+		}
+	}
+	auto pack4 = []( const uint32_t* b ) { return b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24); };
+	uint4* out = a.outNodes + (size_t)(a.nodeOffset + task.cwNode) * 5;
+	out[0] = make_uint4( __float_as_uint( p[0] ), __float_as_uint( p[1] ), __float_as_uint( p[2] ), e[0] | (e[1] << 8) | (e[2] << 16) | (imask << 24) );
+	out[1] = make_uint4( a.nodeOffset + childBase, a.triOffset + leafBase, pack4( meta ), pack4( meta + 4 ) );
+	out[2] = make_uint4( pack4( qlo[0] ), pack4( qlo[0] + 4 ), pack4( qlo[1] ), pack4( qlo[1] + 4 ) );
+	out[3] = make_uint4( pack4( qlo[2] ), pack4( qlo[2] + 4 ), pack4( qhi[0] ), pack4( qhi[0] + 4 ) );
+	out[4] = make_uint4( pack4( qhi[1] ), pack4( qhi[1] + 4 ), pack4( qhi[2] ), pack4( qhi[2] + 4 ) );
+}
+
+__global__ void __launch_bounds__( 128 ) collapseKernel( const CollapseArgs a )
+{
+	cg::grid_group grid = cg::this_grid();
+	const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+	if (tid == 0)
+	{
+		a.queue[0] = BuildTask{ 0, 0 };
+		if (a.boundsOut) a.boundsOut[0] = a.nodeLo[0], a.boundsOut[1] = a.nodeHi[0];
+	}
+	grid.sync();
+	uint32_t head = 0, tail = 1;
+	while (head < tail)
+	{
+		for (uint32_t t = head + tid; t < tail; t += stride) CollapseTask( a, a.queue[t] );
+		grid.sync();
+		head = tail;
+		tail = *((volatile uint32_t*)(a.ctrl + 2));
+		grid.sync();
+	}
+	if (tid == 0 && a.countsOut) a.countsOut[0] = a.ctrl[0], a.countsOut[1] = a.ctrl[1], a.countsOut[2] = a.ctrl[9];
+}
+
+static GpuBuildScratch& Scratch( lh2b_core* core )
+{
+	if (!core->gpuBuild) core->gpuBuild = new GpuBuildScratch();
+	return *(GpuBuildScratch*)core->gpuBuild;
+}
+
+void ReleaseGpuBuildScratch( lh2b_core* core )
+{
+	delete (GpuBuildScratch*)core->gpuBuild;
+	core->gpuBuild = nullptr;
+}
+
+static int CollapseGrid( lh2b_core* core )
+{
+	static int blocksPerSM = 0;
+	if (!blocksPerSM) CUDA_CHECK( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &blocksPerSM, collapseKernel, 128, 0 ) );
+	return (int)core->stats.SMcount * (blocksPerSM > 0 ? blocksPerSM : 1);
+}
+
+/* Shared tail of BLAS and TLAS builds: stages 2-6 over n primitive boxes already in scratch.primLo/primHi.
+   sortTopology = false: keep the sorted order and the radix tree of the previous build (refit). */
+static void BuildFromBoxes( lh2b_core* core, GpuBuildScratch& s, const int n, const bool sortTopology, CollapseArgs args )
+{
+	cudaStream_t st = core->stream;
+	const int blocks = (n + 255) / 256;
+	if (sortTopology)
+	{
+		s.keys.Resize( n ), s.keysAlt.Resize( n ), s.idx.Resize( n ), s.idxAlt.Resize( n );
+		mortonKernel<<<blocks, 256, 0, st>>>( s.primLo.ptr, s.primHi.ptr, n, s.ctrl.ptr, s.keys.ptr, s.idx.ptr );
+		size_t tempBytes = 0;
+		cub::DeviceRadixSort::SortPairs( nullptr, tempBytes, s.keys.ptr, s.keysAlt.ptr, s.idx.ptr, s.idxAlt.ptr, n, 0, 63, st );
+		s.cubTemp.Resize( tempBytes + 16 );
+		cub::DeviceRadixSort::SortPairs( s.cubTemp.ptr, tempBytes, s.keys.ptr, s.keysAlt.ptr, s.idx.ptr, s.idxAlt.ptr, n, 0, 63, st );
+		s.children.Resize( n ), s.range.Resize( n ), s.parent.Resize( 2 * n ), s.visit.Resize( n );
+		if (n > 1) radixTreeKernel<<<blocks, 256, 0, st>>>( s.keysAlt.ptr, n, s.children.ptr, s.range.ptr, s.parent.ptr, s.visit.ptr );
+	}
+	else if (n > 1) resetVisitKernel<<<blocks, 256, 0, st>>>( s.visit.ptr, n - 1 );
+	s.nodeLo.Resize( 2 * n ), s.nodeHi.Resize( 2 * n );
+	fitKernel<<<blocks, 256, 0, st>>>( s.primLo.ptr, s.primHi.ptr, s.idxAlt.ptr, n, s.children.ptr, s.parent.ptr, s.visit.ptr, s.nodeLo.ptr, s.nodeHi.ptr );
+	s.queue.Resize( (size_t)n + 8 );
+	args.n = n, args.children = s.children.ptr, args.range = s.range.ptr, args.nodeLo = s.nodeLo.ptr, args.nodeHi = s.nodeHi.ptr;
+	args.idx = s.idxAlt.ptr, args.queue = s.queue.ptr, args.ctrl = s.ctrl.ptr;
+	void* params[] = { &args };
+	CUDA_CHECK( cudaLaunchCooperativeKernel( (void*)collapseKernel, dim3( CollapseGrid( core ) ), dim3( 128 ), params, 0, st ) );
+}
+
+/* BLAS build (or refit) of one mesh from its device-resident vertices. Per-mesh topology (sorted order + radix tree) is
+   kept in the mesh so that a later SetGeometry with the same triangle count can refit. */
+void GpuBuildMesh( lh2b_core* core, Mesh& mesh, const bool refit )
+{
+	GpuBuildScratch& s = Scratch( core );
+	cudaStream_t st = core->stream;
+	const int n = mesh.triCount;
+	s.ctrl.Resize( 16 );
+	initCtrlKernel<<<1, 1, 0, st>>>( s.ctrl.ptr );
+	if (n == 0)
+	{
+		// empty mesh: one node without children, zero box
+		CUDA_CHECK( cudaMemsetAsync( core->arenaNodes.ptr + (size_t)mesh.nodeOff * 5, 0, 80, st ) );
+		CUDA_CHECK( cudaMemsetAsync( mesh.devBounds.ptr, 0, 32, st ) );
+		CUDA_CHECK( cudaMemsetAsync( mesh.devCounts.ptr, 0, 16, st ) );
+		return;
+	}
+	s.primLo.Resize( n ), s.primHi.Resize( n );
+	triBoundsKernel<<<(n + 255) / 256, 256, 0, st>>>( mesh.verts.ptr, n, s.primLo.ptr, s.primHi.ptr, s.ctrl.ptr );
+	// per-mesh topology lives in the mesh's own buffers: swap them into the scratch for the duration of the build
+	s.idxAlt.Swap( mesh.topoIdx ), s.children.Swap( mesh.topoChildren ), s.range.Swap( mesh.topoRange );
+	s.parent.Swap( mesh.topoParent ), s.visit.Swap( mesh.topoVisit );
+	CollapseArgs a = {};
+	a.maxLeaf = 3, a.verts = mesh.verts.ptr, a.outNodes = core->arenaNodes.ptr, a.outTris = core->arenaTris.ptr;
+	a.nodeOffset = mesh.nodeOff, a.triOffset = mesh.triOff, a.nodeCapacity = mesh.nodeCap, a.triCapacity = mesh.triCap;
+	a.boundsOut = mesh.devBounds.ptr, a.countsOut = mesh.devCounts.ptr;
+	BuildFromBoxes( core, s, n, !refit, a );
+	s.idxAlt.Swap( mesh.topoIdx ), s.children.Swap( mesh.topoChildren ), s.range.Swap( mesh.topoRange );
+	s.parent.Swap( mesh.topoParent ), s.visit.Swap( mesh.topoVisit );
+}
+
+/* TLAS build over instance boxes; everything stays on the device. */
+void GpuBuildTlas( lh2b_core* core, const void* dInstIn, const int n, const uint32_t* dLinkedRoots )
+{
+	GpuBuildScratch& s = Scratch( core );
+	cudaStream_t st = core->stream;
+	s.ctrl.Resize( 16 );
+	initCtrlKernel<<<1, 1, 0, st>>>( s.ctrl.ptr );
+	if (n == 0) return;
+	s.primLo.Resize( n ), s.primHi.Resize( n );
+	instBoundsKernel<<<(n + 127) / 128, 128, 0, st>>>( (const InstBuildIn*)dInstIn, n, s.primLo.ptr, s.primHi.ptr, s.ctrl.ptr );
+	CollapseArgs a = {};
+	a.maxLeaf = 1, a.verts = nullptr, a.outNodes = core->arenaNodes.ptr, a.outLeafIds = core->tlasLeafIds.ptr, a.linkedRootOf = dLinkedRoots;
+	a.nodeOffset = core->tlasOff, a.triOffset = 0, a.nodeCapacity = core->tlasCap, a.triCapacity = (uint32_t)core->tlasLeafIds.capacity;
+	BuildFromBoxes( core, s, n, true, a );
+}
+
+} // namespace lh2b

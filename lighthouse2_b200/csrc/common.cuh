@@ -43,6 +43,7 @@ template <typename T> struct DevBuf
 		if (n) CUDA_CHECK( cudaMemcpyAsync( ptr, src, n * sizeof( T ), cudaMemcpyHostToDevice, s ) );
 	}
 	void Free() { if (ptr) cudaFree( ptr ); ptr = nullptr, count = capacity = 0; }
+	void Swap( DevBuf& o ) { T* p = ptr; ptr = o.ptr, o.ptr = p; size_t t = count; count = o.count, o.count = t; t = capacity; capacity = o.capacity, o.capacity = t; }
 	size_t Bytes() const { return count * sizeof( T ); }
 };
 

@@ -48,98 +48,124 @@ static bool IsIdentity( const float* m )
 	return memcmp( m, id, sizeof( id ) ) == 0;
 }
 
-/* Arena slots: bump allocation with 25% slack; a mesh that outgrows its slot gets a new one at the top
-   (the old slot is not recycled - meshes that change triangle count every frame should be rare). */
-static uint32_t ArenaAllocNodes( lh2b_core* core, uint32_t count, uint32_t& cap )
+void GpuBuildMesh( lh2b_core* core, Mesh& mesh, const bool refit );
+void GpuBuildTlas( lh2b_core* core, const void* dInstIn, const int n, const uint32_t* dLinkedRoots );
+void ReleaseGpuBuildScratch( lh2b_core* core );
+
+/* Arena slots: bump allocation; a mesh that outgrows its slot gets a new one at the top (the old slot is not
+   recycled - meshes that change triangle count every frame should be rare). Growing the arena drains the stream
+   first: builds in flight write through the old pointer. */
+template <typename T> static void GrowArena( lh2b_core* core, DevBuf<T>& buf, size_t need )
 {
-	cap = count + count / 4 + 4;
+	if (need <= buf.capacity) { buf.count = need; return; }
+	CUDA_CHECK( cudaStreamSynchronize( core->stream ) );
+	const size_t newCap = need + need / 2;
+	T* np = nullptr;
+	CUDA_CHECK( cudaMalloc( &np, newCap * sizeof( T ) ) );
+	if (buf.ptr && buf.capacity) CUDA_CHECK( cudaMemcpy( np, buf.ptr, buf.capacity * sizeof( T ), cudaMemcpyDeviceToDevice ) );
+	if (buf.ptr) cudaFree( buf.ptr );
+	buf.ptr = np, buf.capacity = newCap, buf.count = need;
+}
+
+static uint32_t ArenaAllocNodes( lh2b_core* core, uint32_t cap )
+{
 	const uint32_t off = core->arenaNodeTop;
 	core->arenaNodeTop += cap;
-	const size_t need = (size_t)core->arenaNodeTop * 5;
-	if (need > core->arenaNodes.capacity)
-	{
-		core->arenaNodes.count = core->arenaNodes.capacity;
-		core->arenaNodes.Reserve( need + need / 2, true );
-	}
-	core->arenaNodes.count = need;
+	GrowArena( core, core->arenaNodes, (size_t)core->arenaNodeTop * 5 );
 	return off;
 }
 
-static uint32_t ArenaAllocTris( lh2b_core* core, uint32_t count, uint32_t& cap )
+static uint32_t ArenaAllocTris( lh2b_core* core, uint32_t cap )
 {
-	cap = count + count / 4 + 4;
 	const uint32_t off = core->arenaTriTop;
 	core->arenaTriTop += cap;
-	const size_t need = (size_t)core->arenaTriTop * 3;
-	if (need > core->arenaTris.capacity)
-	{
-		core->arenaTris.count = core->arenaTris.capacity;
-		core->arenaTris.Reserve( need + need / 2, true );
-	}
-	core->arenaTris.count = need;
+	GrowArena( core, core->arenaTris, (size_t)core->arenaTriTop * 3 );
 	return off;
 }
 
-/* childBase / triBase of every node become absolute arena indices. */
-static void BakeOffsets( std::vector<CwNode>& nodes, uint32_t nodeOff, uint32_t triOff )
+static void EnsureMeshSlots( lh2b_core* core, Mesh& mesh, uint32_t nodesNeeded, uint32_t trisNeeded )
 {
-	for (auto& n : nodes) n.w[4] += nodeOff, n.w[5] += triOff;
+	if (nodesNeeded > mesh.nodeCap) mesh.nodeCap = nodesNeeded + nodesNeeded / 8 + 4, mesh.nodeOff = ArenaAllocNodes( core, mesh.nodeCap );
+	if (trisNeeded > mesh.triCap) mesh.triCap = trisNeeded + 4, mesh.triOff = ArenaAllocTris( core, mesh.triCap );
+	if (mesh.devBounds.count == 0) mesh.devBounds.Resize( 2 ), mesh.devCounts.Resize( 4 );
 }
 
+/* Host builder (Setting "bvhBuilder" = 1): binned SAH on the CPU, uploaded into the arena. */
 static void RebuildMeshHost( lh2b_core* core, Mesh& mesh )
 {
 	const double t0 = NowMs();
 	std::vector<Bvh2Node> bvh2;
 	std::vector<uint32_t> primIdx;
 	BuildBvh2SAH( mesh.hostVerts.data(), mesh.triCount, bvh2, primIdx );
-	CwBvh cw;
-	CollapseToCwBvh( bvh2, primIdx, mesh.hostVerts.data(), cw );
-	mesh.bounds = cw.bounds;
-	mesh.nodeCount = (uint32_t)cw.nodes.size();
-	if (cw.tris.empty()) cw.tris.push_back( CwTri{} );
-	if (mesh.nodeCount > mesh.nodeCap) mesh.nodeOff = ArenaAllocNodes( core, mesh.nodeCount, mesh.nodeCap );
-	if (cw.tris.size() > mesh.triCap) mesh.triOff = ArenaAllocTris( core, (uint32_t)cw.tris.size(), mesh.triCap );
-	BakeOffsets( cw.nodes, mesh.nodeOff, mesh.triOff );	// slots are known only after the build: bake now
-	mesh.rootNode = cw.nodes[0], mesh.taggedInst = 0;	// triangle records are emitted with inst = 0
-	CUDA_CHECK( cudaMemcpyAsync( core->arenaNodes.ptr + (size_t)mesh.nodeOff * 5, cw.nodes.data(), cw.nodes.size() * sizeof( CwNode ), cudaMemcpyHostToDevice, core->stream ) );
-	CUDA_CHECK( cudaMemcpyAsync( core->arenaTris.ptr + (size_t)mesh.triOff * 3, cw.tris.data(), cw.tris.size() * sizeof( CwTri ), cudaMemcpyHostToDevice, core->stream ) );
+	CwBvh probe;
+	CollapseToCwBvh( bvh2, primIdx, mesh.hostVerts.data(), probe );	// sizes first: the slot must exist before indices can be absolute
+	EnsureMeshSlots( core, mesh, (uint32_t)probe.nodes.size(), (uint32_t)std::max<size_t>( probe.tris.size(), 1 ) );
+	for (auto& n : probe.nodes) n.w[4] += mesh.nodeOff, n.w[5] += mesh.triOff;
+	if (probe.tris.empty()) probe.tris.push_back( CwTri{} );
+	mesh.nodeCount = (uint32_t)probe.nodes.size(), mesh.taggedInst = 0, mesh.hasTopology = false;
+	const float4 b[2] = { make_float4( probe.bounds.lo[0], probe.bounds.lo[1], probe.bounds.lo[2], 0 ), make_float4( probe.bounds.hi[0], probe.bounds.hi[1], probe.bounds.hi[2], 0 ) };
+	CUDA_CHECK( cudaMemcpyAsync( core->arenaNodes.ptr + (size_t)mesh.nodeOff * 5, probe.nodes.data(), probe.nodes.size() * sizeof( CwNode ), cudaMemcpyHostToDevice, core->stream ) );
+	CUDA_CHECK( cudaMemcpyAsync( core->arenaTris.ptr + (size_t)mesh.triOff * 3, probe.tris.data(), probe.tris.size() * sizeof( CwTri ), cudaMemcpyHostToDevice, core->stream ) );
+	CUDA_CHECK( cudaMemcpyAsync( mesh.devBounds.ptr, b, sizeof( b ), cudaMemcpyHostToDevice, core->stream ) );
 	CUDA_CHECK( cudaStreamSynchronize( core->stream ) );
 	mesh.buildMs = (float)(NowMs() - t0);
 	mesh.dirty = false;
 }
 
-static void TransformBounds( const Aabb& b, const float* m, Aabb& out )
+/* GPU builder (default): LBVH + collapse, or a refit when only the vertex positions changed. Returns false if the
+   node slot overflowed (the caller grows it and retries). */
+static void RebuildMeshGpu( lh2b_core* core, Mesh& mesh )
 {
-	for (int a = 0; a < 3; a++) out.lo[a] = 1e34f, out.hi[a] = -1e34f;
-	for (int k = 0; k < 8; k++)
+	const bool refit = core->bvhRefit && mesh.hasTopology && mesh.builtTriCount == mesh.triCount;
+	uint32_t nodeGuess = std::max( mesh.nodeCap, (uint32_t)(mesh.triCount / 2 + 64) );
+	for (int attempt = 0; attempt < 4; attempt++)
 	{
-		const float x = (k & 1) ? b.hi[0] : b.lo[0], y = (k & 2) ? b.hi[1] : b.lo[1], z = (k & 4) ? b.hi[2] : b.lo[2];
-		for (int a = 0; a < 3; a++)
+		EnsureMeshSlots( core, mesh, nodeGuess, (uint32_t)std::max( mesh.triCount, 1 ) );
+		CUDA_CHECK( cudaEventRecord( core->evA, core->stream ) );
+		GpuBuildMesh( core, mesh, refit );
+		CUDA_CHECK( cudaEventRecord( core->evB, core->stream ) );
+		uint32_t counts[4] = { 0, 0, 0, 0 };
+		CUDA_CHECK( cudaMemcpyAsync( counts, mesh.devCounts.ptr, 16, cudaMemcpyDeviceToHost, core->stream ) );
+		CUDA_CHECK( cudaStreamSynchronize( core->stream ) );
+		CUDA_CHECK( cudaGetLastError() );
+		if (counts[2] == 0)
 		{
-			const float v = m[a * 4] * x + m[a * 4 + 1] * y + m[a * 4 + 2] * z + m[a * 4 + 3];
-			out.lo[a] = fminf( out.lo[a], v ), out.hi[a] = fmaxf( out.hi[a], v );
+			mesh.nodeCount = mesh.triCount ? counts[0] : 1;
+			CUDA_CHECK( cudaEventElapsedTime( &mesh.buildMs, core->evA, core->evB ) );
+			mesh.hasTopology = mesh.triCount > 0, mesh.builtTriCount = mesh.triCount, mesh.taggedInst = 0, mesh.dirty = false;
+			return;
 		}
+		nodeGuess = mesh.nodeCap * 2;	// slot too small for this tree: take a bigger one and rebuild
 	}
-	// pad: the object-space traversal re-derives the ray with rounding, keep the world box conservative
-	for (int a = 0; a < 3; a++)
-	{
-		const float pad = 1e-5f * fmaxf( fabsf( out.lo[a] ), fabsf( out.hi[a] ) ) + 1e-30f;
-		out.lo[a] -= pad, out.hi[a] += pad;
-	}
+	throw CoreError( "GPU BVH build: node slot overflow persists" );
 }
+
+struct InstBuildHost { float xform[12]; const float4* bounds; uint64_t pad; };
 
 void UpdateAccelerationStructures( lh2b_core* core )
 {
-	for (auto& m : core->meshes) if (m->dirty) RebuildMeshHost( core, *m );
-	const double t0 = NowMs();
+	for (auto& m : core->meshes) if (m->dirty)
+	{
+		if (core->bvhBuilder == 1) RebuildMeshHost( core, *m ); else RebuildMeshGpu( core, *m );
+	}
+	CUDA_CHECK( cudaEventRecord( core->evA, core->stream ) );
 	const int n = (int)core->instances.size();
 	std::vector<InstTrav> trav( n > 0 ? n : 1 );
 	std::vector<lh2abi::CoreInstanceDesc> desc( n > 0 ? n : 1 );
-	std::vector<Aabb> boxes( n );
+	std::vector<InstBuildHost> buildIn( n > 0 ? n : 1 );
+	std::vector<uint32_t> linked( n > 0 ? n : 1, 0 );
+	// flat scene: every instance has the identity transform and no mesh is instanced twice. Then no ray ever needs
+	// transforming: the top level links copies of the BLAS roots as internal children and traversal is single-level;
+	// the instance index of a hit comes from the triangle record.
+	bool flat = n > 0;
+	{
+		std::vector<int> uses( core->meshes.size(), 0 );
+		for (int i = 0; i < n; i++) if (!IsIdentity( core->instances[i].xform ) || ++uses[core->instances[i].mesh] > 1) flat = false;
+	}
 	for (int i = 0; i < n; i++)
 	{
 		const Instance& inst = core->instances[i];
-		const Mesh& mesh = *core->meshes[inst.mesh];
+		Mesh& mesh = *core->meshes[inst.mesh];
 		float inv[12];
 		InvertAffine( inst.xform, inv );
 		trav[i].r0 = make_float4( inv[0], inv[1], inv[2], inv[3] );
@@ -150,47 +176,29 @@ void UpdateAccelerationStructures( lh2b_core* core )
 		desc[i].triangles = mesh.coreTris.ptr, desc[i].dummy1 = desc[i].dummy2 = 0;
 		desc[i].invTransform.A = { inv[0], inv[1], inv[2], inv[3] }, desc[i].invTransform.B = { inv[4], inv[5], inv[6], inv[7] };
 		desc[i].invTransform.C = { inv[8], inv[9], inv[10], inv[11] }, desc[i].invTransform.D = { 0, 0, 0, 1 };
-		TransformBounds( mesh.bounds, inst.xform, boxes[i] );
-	}
-	// flat scene: every instance has the identity transform and no mesh is instanced twice. Then no ray ever needs
-	// transforming: the top level links copies of the BLAS roots as internal children and traversal is single-level;
-	// the instance index of a hit comes from the triangle record.
-	bool flat = n > 0;
-	{
-		std::vector<int> uses( core->meshes.size(), 0 );
-		for (int i = 0; i < n; i++) if (!IsIdentity( core->instances[i].xform ) || ++uses[core->instances[i].mesh] > 1) flat = false;
-	}
-	std::vector<CwNode> linked;
-	if (flat)
-	{
-		linked.resize( n );
-		for (int i = 0; i < n; i++)
+		memcpy( buildIn[i].xform, inst.xform, 48 ), buildIn[i].bounds = mesh.devBounds.ptr, buildIn[i].pad = 0;
+		linked[i] = mesh.nodeOff;
+		if (flat && mesh.taggedInst != i)
 		{
-			Mesh& mesh = *core->meshes[core->instances[i].mesh];
-			linked[i] = mesh.rootNode;
-			if (mesh.taggedInst != i)
-			{
-				LaunchTagTriangles( core->arenaTris.ptr + (size_t)mesh.triOff * 3, mesh.triCount, (uint32_t)i, core->stream );
-				mesh.taggedInst = i;
-			}
+			LaunchTagTriangles( core->arenaTris.ptr + (size_t)mesh.triOff * 3, mesh.triCount, (uint32_t)i, core->stream );
+			mesh.taggedInst = i;
 		}
 	}
-	std::vector<Bvh2Node> bvh2;
-	std::vector<uint32_t> primIdx;
-	BuildBvh2FromBoxes( boxes.data(), n, 1, bvh2, primIdx );
-	// the top level's slot must exist before encoding (linked roots are absolute already and must not be re-based)
+	// top level: slot for 2n+2 nodes (n internal at most, n linked copies, root), leaf ids for n instances
 	const uint32_t tlasNeed = (uint32_t)(2 * n + 2);
-	if (tlasNeed > core->tlasCap) core->tlasOff = ArenaAllocNodes( core, tlasNeed, core->tlasCap );
-	CwBvh cw;
-	CollapseToCwBvh( bvh2, primIdx, nullptr, cw, core->tlasOff, 0, flat ? linked.data() : nullptr );
-	if (cw.leafIds.empty()) cw.leafIds.push_back( 0 );
-	core->tlasNodeCount = (uint32_t)cw.nodes.size();
-	if (core->tlasNodeCount > core->tlasCap) throw CoreError( "internal: top-level node estimate too small" );
-	CUDA_CHECK( cudaMemcpyAsync( core->arenaNodes.ptr + (size_t)core->tlasOff * 5, cw.nodes.data(), cw.nodes.size() * sizeof( CwNode ), cudaMemcpyHostToDevice, core->stream ) );
-	core->tlasLeafIds.Upload( cw.leafIds.data(), cw.leafIds.size(), core->stream );
+	if (tlasNeed > core->tlasCap) core->tlasCap = tlasNeed + tlasNeed / 2, core->tlasOff = ArenaAllocNodes( core, core->tlasCap );
+	core->tlasLeafIds.Reserve( (size_t)n + 8 ), core->tlasLeafIds.count = (size_t)n + 8;
 	core->instTrav.Upload( trav.data(), trav.size(), core->stream );
 	core->instDesc.Upload( desc.data(), desc.size(), core->stream );
-	CUDA_CHECK( cudaStreamSynchronize( core->stream ) );
+	core->instBuildIn.Upload( (const uint8_t*)buildIn.data(), buildIn.size() * sizeof( InstBuildHost ), core->stream );
+	core->linkedRoots.Upload( linked.data(), linked.size(), core->stream );
+	if (n == 0) CUDA_CHECK( cudaMemsetAsync( core->arenaNodes.ptr + (size_t)core->tlasOff * 5, 0, 80, core->stream ) );
+	else GpuBuildTlas( core, core->instBuildIn.ptr, n, flat ? core->linkedRoots.ptr : nullptr );
+	CUDA_CHECK( cudaEventRecord( core->evB, core->stream ) );
+	CUDA_CHECK( cudaStreamSynchronize( core->stream ) );	// the host vectors above were the copy sources
+	CUDA_CHECK( cudaGetLastError() );
+	CUDA_CHECK( cudaEventElapsedTime( &core->tlasBuildMs, core->evA, core->evB ) );
+	core->tlasNodeCount = 0;
 	core->scene.nodes = core->arenaNodes.ptr, core->scene.tris = core->arenaTris.ptr;
 	core->scene.tlasRoot = core->tlasOff;
 	// flat scenes start at the top-level root (whose children are BLAS-root copies), or directly at the BLAS root
@@ -199,7 +207,6 @@ void UpdateAccelerationStructures( lh2b_core* core )
 	core->scene.instances = core->instTrav.ptr;
 	core->scene.instanceCount = n;
 	core->scene.singleIdentity = flat ? 1 : 0;
-	core->tlasBuildMs = (float)(NowMs() - t0);
 }
 
 } // namespace lh2b
@@ -258,6 +265,7 @@ int lh2b_destroy( lh2b_core* core )
 	cudaSetDevice( core->device );
 	cudaStreamSynchronize( core->stream );
 	ReleaseRenderState( core );
+	ReleaseGpuBuildScratch( core );
 	cudaEventDestroy( core->evA ), cudaEventDestroy( core->evB );
 	cudaStreamDestroy( core->stream );
 	delete[] core->stats.deviceName;
@@ -280,7 +288,7 @@ int lh2b_set_geometry( lh2b_core* core, int meshIdx, const float* vertexData, in
 	if (meshIdx == (int)core->meshes.size()) core->meshes.emplace_back( new Mesh() );
 	Mesh& mesh = *core->meshes[meshIdx];
 	mesh.triCount = triangleCount;
-	mesh.hostVerts.assign( vertexData, vertexData + (size_t)vertexCount * 4 );
+	if (core->bvhBuilder == 1) mesh.hostVerts.assign( vertexData, vertexData + (size_t)vertexCount * 4 );
 	mesh.verts.Upload( (const float4*)vertexData, (size_t)vertexCount, core->stream );
 	if (triangles) mesh.coreTris.Upload( (const float4*)triangles, (size_t)triangleCount * 13, core->stream );
 	CUDA_CHECK( cudaStreamSynchronize( core->stream ) ); // caller may free its arrays on return
@@ -382,8 +390,8 @@ int lh2b_get_bvh_stats( lh2b_core* core, int meshIdx, lh2b_bvh_stats* out )
 	memset( out, 0, sizeof( *out ) );
 	if (meshIdx == -1)
 	{
-		out->nodes = core->tlasNodeCount, out->triangles = (uint32_t)core->instances.size();
-		out->bytes = (uint32_t)(core->tlasNodeCount * 80 + core->tlasLeafIds.Bytes() + core->instTrav.Bytes());
+		out->nodes = (uint32_t)core->instances.size() + 1, out->triangles = (uint32_t)core->instances.size();
+		out->bytes = (uint32_t)(core->tlasCap * 80 + core->tlasLeafIds.Bytes() + core->instTrav.Bytes());
 		out->buildMs = core->tlasBuildMs;
 	}
 	else

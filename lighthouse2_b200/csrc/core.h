@@ -24,13 +24,19 @@ struct Mesh
 	DevBuf<float4> verts;			// float4[3 * triCount] positions as passed to SetGeometry
 	uint32_t nodeOff = 0, nodeCap = 0;	// slot in the node arena (in nodes)
 	uint32_t triOff = 0, triCap = 0;	// slot in the triangle arena (in triangles)
-	std::vector<float> hostVerts;	// kept for host rebuilds
-	Aabb bounds = {};
+	std::vector<float> hostVerts;	// kept only when the host builder is selected
 	bool dirty = true;
 	float buildMs = 0, sahCost = 0;
 	uint32_t nodeCount = 0;
-	CwNode rootNode = {};			// host copy of the BLAS root (absolute indices), linked into flat top levels
 	int taggedInst = -1;			// instance index currently written into the triangle records (flat scenes)
+	// GPU builder state: topology of the last full build (sorted order + binary radix tree) for refits
+	DevBuf<uint32_t> topoIdx, topoVisit;
+	DevBuf<int2> topoChildren, topoRange;
+	DevBuf<int> topoParent;
+	DevBuf<float4> devBounds;		// {lo, hi} of the mesh, device resident (feeds the top-level build)
+	DevBuf<uint32_t> devCounts;		// node count, leaf count, overflow flag of the last build
+	bool hasTopology = false;
+	int builtTriCount = -1;
 };
 
 struct Instance { int mesh = 0; float xform[12] = { 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0 }; };
@@ -59,7 +65,11 @@ struct lh2b_core
 	// scratch for the host-buffer query entry points
 	lh2b::DevBuf<float4> qO, qD, qHits;
 	lh2b::DevBuf<uint8_t> qOcc;
-	lh2b::DevBuf<uint32_t> queryCounter;	// work counter of the persistent query kernels
+	lh2b::DevBuf<uint32_t> queryCounter;
+	void* gpuBuild = nullptr;				// GpuBuildScratch (bvh_gpu.cu)
+	lh2b::DevBuf<uint8_t> instBuildIn;		// per-frame top-level build input
+	lh2b::DevBuf<uint32_t> linkedRoots;
+	int bvhRefit = 1;						// refit (keep topology) when a mesh is re-sent with the same triangle count	// work counter of the persistent query kernels
 	// settings
 	int bvhBuilder = 0;				// 0: GPU LBVH (default), 1: host binned SAH
 	float geometryEpsilon = 1e-4f, clampValue = 10.0f;	// reference defaults: stageClampValue(10) at rendercore.cpp:243; epsilon comes from RenderSystem (rendersystem.h:65-72)

@@ -238,7 +238,8 @@ int lh2b_setting( lh2b_core* core, const char* name, float value )
 	// extensions of this core (the reference fixes these at compile time: core_settings.h:25, pathtracer.h:33)
 	else if (!strcmp( name, "maxPathLength" )) core->maxPathLength = value < 1 ? 1 : (value > LH2B_MAXPATHLENGTH ? LH2B_MAXPATHLENGTH : (int)value);
 	else if (!strcmp( name, "maxDiffuseBounces" )) core->enoughBounces = value <= 0 ? 0 : (value < 2 ? S_BOUNCED : S_BOUNCEDTWICE);
-	else if (!strcmp( name, "bvhBuilder" )) core->bvhBuilder = (int)value;
+	else if (!strcmp( name, "bvhBuilder" )) core->bvhBuilder = (int)value;	// 0: GPU LBVH (default), 1: host binned SAH
+	else if (!strcmp( name, "bvhRefit" )) core->bvhRefit = (int)value;
 	else if (!strcmp( name, "traversalVariant" )) g_traversalVariant = (int)value;
 	else if (!strcmp( name, "wideBlocksPerSM" )) g_wideBlocksPerSM = value < 1 ? 1 : (int)value;
 	else if (!strcmp( name, "triThreshold" )) g_triThreshold = (int)value;

@@ -22,8 +22,23 @@ def _rot(axis, angle, t=(0, 0, 0), s=1.0):
     return m.astype(np.float32)
 
 
+BUILDER = {"gpu-lbvh": 0, "host-sah": 1}
+
+
+@pytest.fixture(params=list(BUILDER), autouse=True)
+def builder(request):
+    """Every parity case runs with the GPU LBVH builder (default) and with the host SAH builder."""
+    global _builder
+    _builder = BUILDER[request.param]
+    yield request.param
+
+
+_builder = 0
+
+
 def _check(meshes, instances, O, D, shadow_tmax=None):
     core = RenderCore()
+    core.Setting("bvhBuilder", _builder)
     for i, m in enumerate(meshes):
         core.SetGeometry(i, m)
     for i, (mi, xf) in enumerate(instances):
@@ -96,3 +111,38 @@ def test_empty_and_tiny():
     O, D = scenes.random_rays(512, extent=3, seed=8)
     _check([tri], [(0, None)], O, D, shadow_tmax=2.0)
     _check([tri], [(0, _rot((1, 0, 0), 0.5, (0, 1, 0)))], O, D, shadow_tmax=2.0)
+
+
+def test_refit_after_deformation():
+    """SetGeometry with the same triangle count: the GPU builder keeps the topology (refit) - results must still be exact."""
+    base = scenes.terrain(50, 40, extent=20, seed=21)
+    O, D = scenes.random_rays(20000, extent=24, seed=22)
+    core = RenderCore()
+    core.Setting("bvhBuilder", _builder)
+    core.SetGeometry(0, base)
+    core.SetInstance(0, 0)
+    core.SetInstance(1, -1)
+    core.FinalizeInstances()
+    rng = np.random.default_rng(23)
+    for step in range(3):
+        mesh = base.copy()
+        mesh[:, 1] += (np.sin(mesh[:, 0] * 0.7 + step) * 1.5 + rng.standard_normal(len(mesh)) * 0.2 * step).astype(np.float32)
+        core.SetGeometry(0, mesh)
+        core.FinalizeInstances()
+        got = core.TraceRays(O, D)
+        want = orc.closest_hits([mesh], [(0, None)], O, D)
+        assert np.array_equal(got, want), f"refit step {step}: {(got != want).any(axis=1).sum()} records differ"
+    core.Shutdown()
+
+
+def test_many_instances():
+    m0 = scenes.random_soup(400, extent=1.0, size=0.5, seed=31)
+    m1 = scenes.terrain(8, 8, extent=1.5, seed=32)
+    rng = np.random.default_rng(33)
+    inst = []
+    for i in range(150):
+        t = (rng.random(3) * 2 - 1) * 12
+        inst.append((i % 2, _rot(rng.standard_normal(3), rng.random() * 6.28, t, 0.5 + rng.random())))
+    O, D = scenes.random_rays(8000, extent=16, seed=34)
+    hits = _check([m0, m1], inst, O, D, shadow_tmax=10.0)
+    assert hits > 500
