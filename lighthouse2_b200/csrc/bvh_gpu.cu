@@ -37,7 +37,9 @@ struct GpuBuildScratch
 	DevBuf<uint8_t> cubTemp;
 	DevBuf<float4> nodeLo, nodeHi;			// 2n-1 binary nodes: internal [0, n-1), leaves [n-1, 2n-1)
 	DevBuf<int2> children;					// per internal node
-	DevBuf<int2> range;						// per internal node: first/last sorted position
+	DevBuf<uint32_t> subtree;				// per internal node: number of primitives below it
+	DevBuf<int> clusterA, clusterB, mergeTmp;	// PLOC working sets
+	DevBuf<uint32_t> blockCount;
 	DevBuf<int> parent;						// per binary node
 	DevBuf<uint32_t> visit;					// per internal node arrival counter
 	DevBuf<BuildTask> queue;
@@ -147,7 +149,7 @@ __device__ __forceinline__ int Delta( const uint64_t* __restrict__ keys, const i
 	if (a == b) return 64 + __clz( i ^ j );
 	return __clzll( a ^ b );
 }
-__global__ void radixTreeKernel( const uint64_t* __restrict__ keys, const int n, int2* __restrict__ children, int2* __restrict__ range,
+__global__ void radixTreeKernel( const uint64_t* __restrict__ keys, const int n, int2* __restrict__ children, uint32_t* __restrict__ subtree,
 	int* __restrict__ parent, uint32_t* __restrict__ visit )
 {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -171,7 +173,7 @@ __global__ void radixTreeKernel( const uint64_t* __restrict__ keys, const int n,
 	const int left = first == gamma ? (n - 1) + gamma : gamma;
 	const int right = last == gamma + 1 ? (n - 1) + gamma + 1 : gamma + 1;
 	children[i] = make_int2( left, right );
-	range[i] = make_int2( first, last );
+	subtree[i] = (uint32_t)(last - first + 1);
 	parent[left] = i, parent[right] = i;
 	visit[i] = 0;
 	if (i == 0) parent[0] = -1;
@@ -213,7 +215,7 @@ __global__ void resetVisitKernel( uint32_t* visit, const int n )
 struct CollapseArgs
 {
 	int n, maxLeaf;
-	const int2* children; const int2* range; const float4* nodeLo; const float4* nodeHi; const uint32_t* idx;
+	const int2* children; const uint32_t* subtree; const float4* nodeLo; const float4* nodeHi; const uint32_t* idx;
 	const float4* verts;			// BLAS: triangle vertices; null for the TLAS
 	uint4* outNodes;				// arena base
 	float4* outTris;				// arena base (BLAS)
@@ -237,8 +239,7 @@ __device__ void CollapseTask( const CollapseArgs& a, const BuildTask task )
 	auto leafLike = [&]( const int node ) -> bool {
 		if (node >= n - 1) return true;
 		if (a.linkedRootOf) return false;
-		const int2 r = a.range[node];
-		return r.y - r.x + 1 <= a.maxLeaf;
+		return a.subtree[node] <= (uint32_t)a.maxLeaf;
 	};
 	int child[8], cnt = 0;
 	const int root = task.bvh2Node;
@@ -294,7 +295,7 @@ __device__ void CollapseTask( const CollapseArgs& a, const BuildTask task )
 		const int c = slotChild[s];
 		const bool isLeaf = leafLike( c ) && !a.linkedRootOf;
 		if (!isLeaf) imask |= 1u << s, internalCount++;
-		else leafPrims += c >= n - 1 ? 1 : a.range[c].y - a.range[c].x + 1;
+		else leafPrims += c >= n - 1 ? 1 : (int)a.subtree[c];
 	}
 	const uint32_t childBase = internalCount ? atomicAdd( a.ctrl + 0, (uint32_t)internalCount ) : 0;
 	const uint32_t leafBase = leafPrims ? atomicAdd( a.ctrl + 1, (uint32_t)leafPrims ) : 0;
@@ -342,11 +343,19 @@ __device__ void CollapseTask( const CollapseArgs& a, const BuildTask task )
 		}
 		else
 		{
-			const int first = c >= n - 1 ? c - (n - 1) : a.range[c].x, count = c >= n - 1 ? 1 : a.range[c].y - a.range[c].x + 1;
+			// the (at most maxLeaf) primitives below this child: tiny depth-first walk
+			int leafPos[4], count = 0, walk[4], wsp = 0;
+			walk[wsp++] = c;
+			while (wsp > 0)
+			{
+				const int nd = walk[--wsp];
+				if (nd >= n - 1) leafPos[count++] = nd - (n - 1);
+				else { const int2 cc = a.children[nd]; walk[wsp++] = cc.y, walk[wsp++] = cc.x; }
+			}
 			meta[s] = (((1u << count) - 1) << 5) | (uint32_t)triCursor;
 			for (int k = 0; k < count; k++)
 			{
-				const uint32_t prim = a.idx[first + k];
+				const uint32_t prim = a.idx[leafPos[k]];
 				const uint32_t at = leafBase + triCursor + k;
 				if (a.verts)
 				{
@@ -401,6 +410,148 @@ __global__ void __launch_bounds__( 128 ) collapseKernel( const CollapseArgs a )
 	if (tid == 0 && a.countsOut) a.countsOut[0] = a.ctrl[0], a.countsOut[1] = a.ctrl[1], a.countsOut[2] = a.ctrl[9];
 }
 
+
+/* ---- stage 4': PLOC (parallel locally-ordered clustering, Meister & Bittner 2018) instead of the radix tree ------------
+   Clusters start as the Morton-sorted leaves. Each round every cluster looks PLOC_RADIUS positions left and right for the
+   neighbour whose union box has the smallest area; mutual nearest neighbours merge into a new binary node; the cluster
+   array is compacted in order. One persistent cooperative kernel runs all rounds (three grid.sync() per round).
+   Internal node ids are handed out downwards from n-2, so the last merge - the root - is node 0, like the radix tree. */
+#define PLOC_BLOCK 256
+
+struct PlocArgs
+{
+	int n, radius;
+	int* clusterA; int* clusterB; int* nn; int* mergeTmp;
+	float4* nodeLo; float4* nodeHi; int2* children; int* parent; uint32_t* subtree; uint32_t* visit;
+	uint32_t* blockCount;	// per block valid count
+	uint32_t* ctrl;			// [10] next internal id + 1, [11] current cluster count
+};
+
+__global__ void __launch_bounds__( PLOC_BLOCK ) plocKernel( const PlocArgs a )
+{
+	cg::grid_group grid = cg::this_grid();
+	__shared__ uint32_t warpSums[PLOC_BLOCK / 32];
+	__shared__ uint32_t blockBase;
+	const int n = a.n;
+	const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+	int* in = a.clusterA;
+	int* out = a.clusterB;
+	for (uint32_t i = tid; i < (uint32_t)n; i += stride) in[i] = (n - 1) + i;
+	if (tid == 0) a.ctrl[10] = n - 1, a.ctrl[11] = n, a.parent[0] = -1;
+	grid.sync();
+	int m = n;
+	while (m > 1)
+	{
+		// phase 1: nearest neighbour within the window
+		for (int i = tid; i < m; i += stride)
+		{
+			const int ci = in[i];
+			const float4 lo = a.nodeLo[ci], hi = a.nodeHi[ci];
+			float best = FLT_MAX;
+			int bj = -1;
+			const int j0 = max( 0, i - a.radius ), j1 = min( m - 1, i + a.radius );
+			for (int j = j0; j <= j1; j++) if (j != i)
+			{
+				const int cj = in[j];
+				const float4 l2 = a.nodeLo[cj], h2 = a.nodeHi[cj];
+				const float ex = fmaxf( hi.x, h2.x ) - fminf( lo.x, l2.x ), ey = fmaxf( hi.y, h2.y ) - fminf( lo.y, l2.y ), ez = fmaxf( hi.z, h2.z ) - fminf( lo.z, l2.z );
+				const float area = ex * ey + ey * ez + ez * ex;
+				if (area < best) best = area, bj = j;
+			}
+			a.nn[i] = bj;
+		}
+		grid.sync();
+		// phase 2: mutual pairs merge; every block owns a contiguous chunk of positions so that compaction keeps the order
+		const int chunk = (m + gridDim.x - 1) / gridDim.x;
+		const int c0 = blockIdx.x * chunk, c1 = min( m, c0 + chunk );
+		uint32_t blockTotal = 0;
+		for (int base = c0; base < c1; base += PLOC_BLOCK)
+		{
+			const int i = base + threadIdx.x;
+			int result = -1;	// -1: this position disappears
+			if (i < c1)
+			{
+				const int j = a.nn[i];
+				if (a.nn[j] == i)
+				{
+					if (i < j)
+					{
+						const int ci = in[i], cj = in[j];
+						const int id = (int)atomicSub( a.ctrl + 10, 1u ) - 1;
+						const float4 l1 = a.nodeLo[ci], h1 = a.nodeHi[ci], l2 = a.nodeLo[cj], h2 = a.nodeHi[cj];
+						a.nodeLo[id] = make_float4( fminf( l1.x, l2.x ), fminf( l1.y, l2.y ), fminf( l1.z, l2.z ), 0 );
+						a.nodeHi[id] = make_float4( fmaxf( h1.x, h2.x ), fmaxf( h1.y, h2.y ), fmaxf( h1.z, h2.z ), 0 );
+						a.children[id] = make_int2( ci, cj );
+						a.parent[ci] = id, a.parent[cj] = id;
+						a.subtree[id] = (ci >= n - 1 ? 1u : a.subtree[ci]) + (cj >= n - 1 ? 1u : a.subtree[cj]);
+						a.visit[id] = 0;
+						result = id;
+					}
+				}
+				else result = in[i];
+				a.mergeTmp[i] = result;
+			}
+			blockTotal += __syncthreads_count( result >= 0 );
+		}
+		if (threadIdx.x == 0) a.blockCount[blockIdx.x] = blockTotal;
+		grid.sync();
+		// phase 3: ordered compaction. Block offset = sum of the counts of the blocks before it.
+		{
+			uint32_t partial = 0;
+			for (uint32_t b = threadIdx.x; b < blockIdx.x; b += PLOC_BLOCK) partial += a.blockCount[b];
+			for (int o = 16; o > 0; o >>= 1) partial += __shfl_xor_sync( 0xffffffffu, partial, o );
+			if ((threadIdx.x & 31) == 0) warpSums[threadIdx.x >> 5] = partial;
+			__syncthreads();
+			if (threadIdx.x == 0)
+			{
+				uint32_t t = 0;
+				for (int w = 0; w < PLOC_BLOCK / 32; w++) t += warpSums[w];
+				blockBase = t;
+			}
+			__syncthreads();
+		}
+		uint32_t running = blockBase;
+		for (int base = c0; base < c1; base += PLOC_BLOCK)
+		{
+			const int i = base + threadIdx.x;
+			const int v = i < c1 ? a.mergeTmp[i] : -1;
+			const bool keep = v >= 0;
+			const uint32_t ballot = __ballot_sync( 0xffffffffu, keep );
+			const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+			__syncthreads();
+			if (lane == 0) warpSums[warp] = __popc( ballot );
+			__syncthreads();
+			uint32_t before = 0, total = 0;
+			for (int w = 0; w < PLOC_BLOCK / 32; w++) { const uint32_t c = warpSums[w]; if (w < (int)warp) before += c; total += c; }
+			if (keep) out[running + before + __popc( ballot & ((1u << lane) - 1) )] = v;
+			running += total;
+		}
+		// new cluster count
+		uint32_t total = 0;
+		{
+			uint32_t partial = 0;
+			for (uint32_t b = threadIdx.x; b < gridDim.x; b += PLOC_BLOCK) partial += a.blockCount[b];
+			for (int o = 16; o > 0; o >>= 1) partial += __shfl_xor_sync( 0xffffffffu, partial, o );
+			__syncthreads();
+			if ((threadIdx.x & 31) == 0) warpSums[threadIdx.x >> 5] = partial;
+			__syncthreads();
+			for (int w = 0; w < PLOC_BLOCK / 32; w++) total += warpSums[w];
+		}
+		grid.sync();
+		m = (int)total;
+		int* t = in; in = out, out = t;
+	}
+}
+
+static int PlocGrid( lh2b_core* core )
+{
+	static int blocksPerSM = 0;
+	if (!blocksPerSM) CUDA_CHECK( cudaOccupancyMaxActiveBlocksPerMultiprocessor( &blocksPerSM, plocKernel, PLOC_BLOCK, 0 ) );
+	return (int)core->stats.SMcount * (blocksPerSM > 0 ? blocksPerSM : 1);
+}
+
+static void BuildPloc( lh2b_core* core, GpuBuildScratch& s, const int n );
+
 static GpuBuildScratch& Scratch( lh2b_core* core )
 {
 	if (!core->gpuBuild) core->gpuBuild = new GpuBuildScratch();
@@ -422,7 +573,7 @@ static int CollapseGrid( lh2b_core* core )
 
 /* Shared tail of BLAS and TLAS builds: stages 2-6 over n primitive boxes already in scratch.primLo/primHi.
    sortTopology = false: keep the sorted order and the radix tree of the previous build (refit). */
-static void BuildFromBoxes( lh2b_core* core, GpuBuildScratch& s, const int n, const bool sortTopology, CollapseArgs args )
+static void BuildFromBoxes( lh2b_core* core, GpuBuildScratch& s, const int n, const bool sortTopology, const bool usePloc, CollapseArgs args )
 {
 	cudaStream_t st = core->stream;
 	const int blocks = (n + 255) / 256;
@@ -434,17 +585,43 @@ static void BuildFromBoxes( lh2b_core* core, GpuBuildScratch& s, const int n, co
 		cub::DeviceRadixSort::SortPairs( nullptr, tempBytes, s.keys.ptr, s.keysAlt.ptr, s.idx.ptr, s.idxAlt.ptr, n, 0, 63, st );
 		s.cubTemp.Resize( tempBytes + 16 );
 		cub::DeviceRadixSort::SortPairs( s.cubTemp.ptr, tempBytes, s.keys.ptr, s.keysAlt.ptr, s.idx.ptr, s.idxAlt.ptr, n, 0, 63, st );
-		s.children.Resize( n ), s.range.Resize( n ), s.parent.Resize( 2 * n ), s.visit.Resize( n );
-		if (n > 1) radixTreeKernel<<<blocks, 256, 0, st>>>( s.keysAlt.ptr, n, s.children.ptr, s.range.ptr, s.parent.ptr, s.visit.ptr );
+		s.children.Resize( n ), s.subtree.Resize( n ), s.parent.Resize( 2 * n ), s.visit.Resize( n );
+		if (n > 1 && usePloc) BuildPloc( core, s, n );
+		else if (n > 1) radixTreeKernel<<<blocks, 256, 0, st>>>( s.keysAlt.ptr, n, s.children.ptr, s.subtree.ptr, s.parent.ptr, s.visit.ptr );
 	}
 	else if (n > 1) resetVisitKernel<<<blocks, 256, 0, st>>>( s.visit.ptr, n - 1 );
 	s.nodeLo.Resize( 2 * n ), s.nodeHi.Resize( 2 * n );
 	fitKernel<<<blocks, 256, 0, st>>>( s.primLo.ptr, s.primHi.ptr, s.idxAlt.ptr, n, s.children.ptr, s.parent.ptr, s.visit.ptr, s.nodeLo.ptr, s.nodeHi.ptr );
 	s.queue.Resize( (size_t)n + 8 );
-	args.n = n, args.children = s.children.ptr, args.range = s.range.ptr, args.nodeLo = s.nodeLo.ptr, args.nodeHi = s.nodeHi.ptr;
+	args.n = n, args.children = s.children.ptr, args.subtree = s.subtree.ptr, args.nodeLo = s.nodeLo.ptr, args.nodeHi = s.nodeHi.ptr;
 	args.idx = s.idxAlt.ptr, args.queue = s.queue.ptr, args.ctrl = s.ctrl.ptr;
 	void* params[] = { &args };
 	CUDA_CHECK( cudaLaunchCooperativeKernel( (void*)collapseKernel, dim3( CollapseGrid( core ) ), dim3( 128 ), params, 0, st ) );
+}
+
+__global__ void leafBoxKernel( const float4* __restrict__ primLo, const float4* __restrict__ primHi, const uint32_t* __restrict__ idx, const int n,
+	float4* __restrict__ nodeLo, float4* __restrict__ nodeHi )
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const uint32_t p = idx[i];
+	nodeLo[(n - 1) + i] = primLo[p], nodeHi[(n - 1) + i] = primHi[p];
+}
+
+static void BuildPloc( lh2b_core* core, GpuBuildScratch& s, const int n )
+{
+	cudaStream_t st = core->stream;
+	s.nodeLo.Resize( 2 * n ), s.nodeHi.Resize( 2 * n );
+	s.clusterA.Resize( n ), s.clusterB.Resize( n ), s.mergeTmp.Resize( 2 * (size_t)n );
+	const int grid = PlocGrid( core );
+	s.blockCount.Resize( grid );
+	leafBoxKernel<<<(n + 255) / 256, 256, 0, st>>>( s.primLo.ptr, s.primHi.ptr, s.idxAlt.ptr, n, s.nodeLo.ptr, s.nodeHi.ptr );
+	PlocArgs a;
+	a.n = n, a.radius = core->plocRadius, a.clusterA = s.clusterA.ptr, a.clusterB = s.clusterB.ptr, a.nn = s.mergeTmp.ptr + n, a.mergeTmp = s.mergeTmp.ptr;
+	a.nodeLo = s.nodeLo.ptr, a.nodeHi = s.nodeHi.ptr, a.children = s.children.ptr, a.parent = s.parent.ptr, a.subtree = s.subtree.ptr, a.visit = s.visit.ptr;
+	a.blockCount = s.blockCount.ptr, a.ctrl = s.ctrl.ptr;
+	void* params[] = { &a };
+	CUDA_CHECK( cudaLaunchCooperativeKernel( (void*)plocKernel, dim3( grid ), dim3( PLOC_BLOCK ), params, 0, st ) );
 }
 
 /* BLAS build (or refit) of one mesh from its device-resident vertices. Per-mesh topology (sorted order + radix tree) is
@@ -467,14 +644,14 @@ void GpuBuildMesh( lh2b_core* core, Mesh& mesh, const bool refit )
 	s.primLo.Resize( n ), s.primHi.Resize( n );
 	triBoundsKernel<<<(n + 255) / 256, 256, 0, st>>>( mesh.verts.ptr, n, s.primLo.ptr, s.primHi.ptr, s.ctrl.ptr );
 	// per-mesh topology lives in the mesh's own buffers: swap them into the scratch for the duration of the build
-	s.idxAlt.Swap( mesh.topoIdx ), s.children.Swap( mesh.topoChildren ), s.range.Swap( mesh.topoRange );
+	s.idxAlt.Swap( mesh.topoIdx ), s.children.Swap( mesh.topoChildren ), s.subtree.Swap( mesh.topoSubtree );
 	s.parent.Swap( mesh.topoParent ), s.visit.Swap( mesh.topoVisit );
 	CollapseArgs a = {};
-	a.maxLeaf = 3, a.verts = mesh.verts.ptr, a.outNodes = core->arenaNodes.ptr, a.outTris = core->arenaTris.ptr;
+	a.maxLeaf = core->bvhMaxLeaf, a.verts = mesh.verts.ptr, a.outNodes = core->arenaNodes.ptr, a.outTris = core->arenaTris.ptr;
 	a.nodeOffset = mesh.nodeOff, a.triOffset = mesh.triOff, a.nodeCapacity = mesh.nodeCap, a.triCapacity = mesh.triCap;
 	a.boundsOut = mesh.devBounds.ptr, a.countsOut = mesh.devCounts.ptr;
-	BuildFromBoxes( core, s, n, !refit, a );
-	s.idxAlt.Swap( mesh.topoIdx ), s.children.Swap( mesh.topoChildren ), s.range.Swap( mesh.topoRange );
+	BuildFromBoxes( core, s, n, !refit, core->bvhBuilder != 2, a );
+	s.idxAlt.Swap( mesh.topoIdx ), s.children.Swap( mesh.topoChildren ), s.subtree.Swap( mesh.topoSubtree );
 	s.parent.Swap( mesh.topoParent ), s.visit.Swap( mesh.topoVisit );
 }
 
@@ -491,7 +668,7 @@ void GpuBuildTlas( lh2b_core* core, const void* dInstIn, const int n, const uint
 	CollapseArgs a = {};
 	a.maxLeaf = 1, a.verts = nullptr, a.outNodes = core->arenaNodes.ptr, a.outLeafIds = core->tlasLeafIds.ptr, a.linkedRootOf = dLinkedRoots;
 	a.nodeOffset = core->tlasOff, a.triOffset = 0, a.nodeCapacity = core->tlasCap, a.triCapacity = (uint32_t)core->tlasLeafIds.capacity;
-	BuildFromBoxes( core, s, n, true, a );
+	BuildFromBoxes( core, s, n, true, false, a );
 }
 
 } // namespace lh2b

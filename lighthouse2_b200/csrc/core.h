@@ -31,7 +31,8 @@ struct Mesh
 	int taggedInst = -1;			// instance index currently written into the triangle records (flat scenes)
 	// GPU builder state: topology of the last full build (sorted order + binary radix tree) for refits
 	DevBuf<uint32_t> topoIdx, topoVisit;
-	DevBuf<int2> topoChildren, topoRange;
+	DevBuf<int2> topoChildren;
+	DevBuf<uint32_t> topoSubtree;
 	DevBuf<int> topoParent;
 	DevBuf<float4> devBounds;		// {lo, hi} of the mesh, device resident (feeds the top-level build)
 	DevBuf<uint32_t> devCounts;		// node count, leaf count, overflow flag of the last build
@@ -69,6 +70,7 @@ struct lh2b_core
 	void* gpuBuild = nullptr;				// GpuBuildScratch (bvh_gpu.cu)
 	lh2b::DevBuf<uint8_t> instBuildIn;		// per-frame top-level build input
 	lh2b::DevBuf<uint32_t> linkedRoots;
+	int plocRadius = 16, bvhMaxLeaf = 2;	// swept on the 1M-triangle terrain (tools/quality_sweep.py)
 	int bvhRefit = 1;						// refit (keep topology) when a mesh is re-sent with the same triangle count	// work counter of the persistent query kernels
 	// settings
 	int bvhBuilder = 0;				// 0: GPU LBVH (default), 1: host binned SAH

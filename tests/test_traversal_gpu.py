@@ -22,12 +22,12 @@ def _rot(axis, angle, t=(0, 0, 0), s=1.0):
     return m.astype(np.float32)
 
 
-BUILDER = {"gpu-lbvh": 0, "host-sah": 1}
+BUILDER = {"gpu-ploc": 0, "host-sah": 1, "gpu-lbvh": 2}
 
 
 @pytest.fixture(params=list(BUILDER), autouse=True)
 def builder(request):
-    """Every parity case runs with the GPU LBVH builder (default) and with the host SAH builder."""
+    """Every parity case runs with each builder: GPU PLOC (default), host binned SAH, GPU LBVH (radix tree)."""
     global _builder
     _builder = BUILDER[request.param]
     yield request.param
