@@ -156,15 +156,9 @@ def run_ours(args, rank, world, local_rank):
     core.Setting("maxPathLength", 1)            # primary + shadow rays only
     sd.upload(core)
     bvh = core.GetBvhStats(0)
-    if world > 1:
-        core.SetSampleShard(rank * SPP, world * SPP)
-
-    class _Cai:
-        def __init__(self, ptr, shape):
-            self.__cuda_array_interface__ = {"shape": shape, "typestr": "<f4", "data": (ptr, False), "version": 2}
-
-    acc_ptr, _ = core.AccumulatorDevicePtr()
-    acc_t = torch.as_tensor(_Cai(acc_ptr, (H, W, 4)), device=f"cuda:{local_rank}") if world > 1 else None
+    from lighthouse2_b200.distributed import ShardedRenderer, accumulator_tensor
+    acc_t = accumulator_tensor(core, f"cuda:{local_rank}")
+    sharded = ShardedRenderer(core, SPP, rank, world, acc_t)
     host_img = torch.empty((H, W, 4), dtype=torch.float32, pin_memory=True)
     host_np = host_img.numpy()
 
@@ -174,10 +168,7 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize()
 
     def step():
-        core.Render(view, 1)                     # Restart: clears the accumulator, renders, finalizes, synchronises
-        if world > 1:
-            dist.reduce(acc_t, dst=0, op=dist.ReduceOp.SUM)
-            torch.cuda.current_stream().synchronize()
+        sharded.render(view, 1)                  # Restart frame on every rank (+ NCCL reduce of the accumulator for N > 1)
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -209,7 +200,7 @@ def run_ours(args, rank, world, local_rank):
         step()
         if rank == 0:
             if world > 1:
-                core._check(core._lib.lh2b_finalize_external(core._h, acc_ptr, world * SPP))
+                sharded.finalize()
             core.ReadPixels(host_np)            # device -> pinned host, 33 MB
         fs = core.GetFrameStats()
         e_rays += int(fs["primaryRays"]) + int(fs["shadowRays"])

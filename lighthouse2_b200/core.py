@@ -134,6 +134,15 @@ class RenderCore:
         self._check(self._lib.lh2b_accumulator_device_ptr(self._h, ctypes.byref(p), ctypes.byref(n)))
         return p.value, n.value
 
+    def SamplesTaken(self):
+        """Samples accumulated per pixel so far, counted over the whole (possibly sharded) frame."""
+        return self.AccumulatorDevicePtr()[1]
+
+    def FinalizeExternal(self, accumulator, samples):
+        """pixels = accumulator / samples for an externally reduced accumulator (torch CUDA tensor or raw device pointer)."""
+        ptr = accumulator.data_ptr() if hasattr(accumulator, "data_ptr") else int(accumulator)
+        self._check(self._lib.lh2b_finalize_external(self._h, ctypes.c_void_p(ptr), int(samples)))
+
     def SetSampleShard(self, first_sample, total_spp):
         self._check(self._lib.lh2b_set_sample_shard(self._h, first_sample, total_spp))
 
