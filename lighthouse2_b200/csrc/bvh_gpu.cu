@@ -132,8 +132,9 @@ __global__ void mortonKernel( const float4* __restrict__ lo, const float4* __res
 	const float3 smin = make_float3( OrderedFloat( box[0] ), OrderedFloat( box[1] ), OrderedFloat( box[2] ) );
 	const float3 smax = make_float3( OrderedFloat( box[3] ), OrderedFloat( box[4] ), OrderedFloat( box[5] ) );
 	const float4 a = lo[i], b = hi[i];
-	const float sx = smax.x > smin.x ? 2097151.0f / (smax.x - smin.x) : 0, sy = smax.y > smin.y ? 2097151.0f / (smax.y - smin.y) : 0;
-	const float sz = smax.z > smin.z ? 2097151.0f / (smax.z - smin.z) : 0;
+	// one scale for all axes (the largest extent): code bits then measure real distance, which matters for flat scenes
+	const float ext = fmaxf( smax.x - smin.x, fmaxf( smax.y - smin.y, smax.z - smin.z ) );
+	const float sx = ext > 0 ? 2097151.0f / ext : 0, sy = sx, sz = sx;
 	const uint64_t x = (uint64_t)fminf( fmaxf( (0.5f * (a.x + b.x) - smin.x) * sx, 0.0f ), 2097151.0f );
 	const uint64_t y = (uint64_t)fminf( fmaxf( (0.5f * (a.y + b.y) - smin.y) * sy, 0.0f ), 2097151.0f );
 	const uint64_t z = (uint64_t)fminf( fmaxf( (0.5f * (a.z + b.z) - smin.z) * sz, 0.0f ), 2097151.0f );
