@@ -113,6 +113,22 @@ LH2B_API int lh2b_shade_paths( lh2b_core* core, int pathLength, int n, const flo
 	uint32_t R0, uint32_t shift, int pass, float* extO, float* extD, float* extT, int* extCount,
 	float* shO, float* shD, float* shE, int* shCount, float* accumulator );
 
+/* Parity hook: run the SVGF / TAA chain alone on HOST buffers, exactly as the filter core's FinalizeRender does
+   (lib/RenderCore_Optix7Filter/rendercore.cpp:897-948): prepareFilter, applyFilter phases 1-3, then TAApass + unsharpenTAA
+   (taa = 1) or finalizeNoTAA. All image buffers are float4[w*h] except accumulator (float4[2*w*h]: direct, indirect),
+   features (uint4[w*h]) and motion (float2[w*h]). Every stage's output is returned. */
+typedef struct lh2b_filter_io
+{
+	int w, h, samplesTaken, camIsStationary, taa;
+	float directClamp, indirectClamp, j0, j1, prevj0, prevj1;
+	float prevView[17];
+	const float* accumulator; const uint32_t* features; const float* worldPos; const float* prevWorldPos; const float* deltaDepth;
+	const float* prevMoments; const float* filteredIN; const float* prevPixels;
+	uint32_t* featuresOut; float* shadingAfterPrepare; float* motion; float* moments;
+	float* phase1; float* phase2; float* phase3; float* taaPixels; float* target;
+} lh2b_filter_io;
+LH2B_API int lh2b_filter_chain( lh2b_core* core, lh2b_filter_io* io );
+
 /* The C handle behind a CoreAPI_Base* obtained from CreateCore() (for headless read-back and statistics). */
 LH2B_API lh2b_core* lh2b_handle_of( void* coreApiBase );
 

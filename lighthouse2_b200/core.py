@@ -185,6 +185,10 @@ class RenderCore:
         sh = dict(O=out[3][:ns.value], D=out[4][:ns.value], E=out[5][:ns.value])
         return ext, sh, acc
 
+    def FilterChain(self, io):
+        """Parity hook (lh2b_filter_chain): io is a ctypes structure laid out like lh2b_filter_io."""
+        self._check(self._lib.lh2b_filter_chain(self._h, ctypes.byref(io)))
+
     def Stream(self):
         p = ctypes.c_void_p()
         self._check(self._lib.lh2b_stream(self._h, ctypes.byref(p)))

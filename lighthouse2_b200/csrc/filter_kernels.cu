@@ -1,0 +1,511 @@
+/* filter_kernels.cu - the SVGF temporal + a-trous filter and the TAA pass as shared-memory-tiled kernels (sm_100a, built
+   with --use_fast_math like the reference).
+
+   Restates lib/CUDA/shared_kernel_code/finalize_shared.h of the reference's Optix7Filter core:
+     prepareFilterKernel :217-314 (albedo demodulation, clamps, reprojection incl. the 25-step diamond search for
+                                   specular pixels, luminance moments with history)         -> prepareKernel
+     applyFilterKernel   :320-484 (5x5-minus-corners a-trous at step 1,2,4 with normal^128, depth-gradient, luminance
+                                   variance and albedo/material weights; phase 1 adds the temporal blend with a YCoCg
+                                   neighbourhood clamp; the last pass remodulates and takes the square root)  -> atrousKernel
+     TAApassKernel       :498-548 (Mitchell-Netravali history fetch, variance clip, 0.1/0.9 blend)  -> taaKernel
+     unsharpenTAAKernel  :554-583 / finalizeNoTAAKernel :589-600                                     -> presentKernel
+   plus the helpers they use from sampling_shared.h:111-215 and tools_shared.h:122-177,237-262.
+   The reference reads every tap from global memory (its block is 32x2). Here each block stages its tile plus the
+   a-trous halo (2 * step pixels on every side) of the shading and feature buffers in shared memory once, so the
+   21 taps per pixel come from on-chip memory; history lookups stay gathers.
+   Parity is checked stage by stage against the reference's own kernels (oracle/ref_filter_gpu.cu).
+*/
+#include "kernels.h"
+#include "common.cuh"
+
+namespace lh2b
+{
+
+__device__ __forceinline__ float3 min3f( const float3 a, const float b ) { return make_float3( fminf( a.x, b ), fminf( a.y, b ), fminf( a.z, b ) ); }
+__device__ __forceinline__ float3 max3v( const float3 a, const float3 b ) { return make_float3( fmaxf( a.x, b.x ), fmaxf( a.y, b.y ), fmaxf( a.z, b.z ) ); }
+__device__ __forceinline__ float3 clamp3( const float3 v, const float3 lo, const float3 hi ) { return make_float3( fminf( fmaxf( v.x, lo.x ), hi.x ), fminf( fmaxf( v.y, lo.y ), hi.y ), fminf( fmaxf( v.z, lo.z ), hi.z ) ); }
+__device__ __forceinline__ float sqrLen( const float3 a ) { return dot( a, a ); }
+__device__ __forceinline__ float sqrf( const float x ) { return x * x; }
+__device__ __forceinline__ float4 operator-( const float4 a, const float4 b ) { return make_float4( a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w ); }
+__device__ __forceinline__ float4 operator+( const float4 a, const float4 b ) { return make_float4( a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w ); }
+__device__ __forceinline__ float4 operator*( const float4 a, const float s ) { return make_float4( a.x * s, a.y * s, a.z * s, a.w * s ); }
+__device__ __forceinline__ float4 operator*( const float s, const float4 a ) { return make_float4( a.x * s, a.y * s, a.z * s, a.w * s ); }
+
+/* tools_shared.h:122-177 */
+__device__ __forceinline__ float3 UnpackNormal2( const uint32_t pi )
+{
+	const uint32_t x = (pi >> 2u) & 1023u, y = (pi >> 12u) & 1023u, z = pi >> 22u;
+	return make_float3( x * (1.0f / 511.0f) - 1, y * (1.0f / 511.0f) - 1, z * (1.0f / 511.0f) - 1 );
+}
+__device__ __forceinline__ float3 RGBToYCoCg( const float3 RGB )
+{
+	const float3 rgb = min3f( RGB, 4.0f );
+	const float Y = (rgb.x + 2 * rgb.y + rgb.z) * 0.25f;
+	const float Co = (2 * rgb.x - 2 * rgb.z) * 0.25f + (0.5f * 256.0f / 255.0f);
+	const float Cg = (-rgb.x + 2 * rgb.y - rgb.z) * 0.25f + (0.5f * 256.0f / 255.0f);
+	return make_float3( Y, Co, Cg );
+}
+__device__ __forceinline__ float3 YCoCgToRGB( const float3 c )
+{
+	const float Y = c.x, Co = c.y - (0.5f * 256.0f / 255.0f), Cg = c.z - (0.5f * 256.0f / 255.0f);
+	return make_float3( Y + Co - Cg, Y + Cg, Y - Co - Cg );
+}
+__device__ __forceinline__ float Luminance( const float3 rgb ) { return 0.299f * fminf( rgb.x, 10.0f ) + 0.587f * fminf( rgb.y, 10.0f ) + 0.114f * fminf( rgb.z, 10.0f ); }
+__device__ __forceinline__ float3 RGB32toHDR( const uint32_t c )
+{
+	return make_float3( (float)(c >> 22) * (1.0f / 1023.0f), (float)((c >> 11) & 2047) * (1.0f / 2047.0f), (float)(c & 2047) * (1.0f / 2047.0f) );
+}
+__device__ __forceinline__ float3 RGB32toHDRmin1( const uint32_t c )
+{
+	return make_float3( (float)max( 1u, c >> 22 ) * (1.0f / 1023.0f), (float)max( 1u, (c >> 11) & 2047 ) * (1.0f / 2047.0f), (float)max( 1u, c & 2047 ) * (1.0f / 2047.0f) );
+}
+/* tools_shared.h:237-262: two rgb triples in 5.11 fixed point */
+__device__ __forceinline__ float4 CombineToFloat4( const float3 A, const float3 B )
+{
+	const uint32_t Ar = (uint32_t)(fminf( A.x, 31.999f ) * 2048.0f), Ag = (uint32_t)(fminf( A.y, 31.999f ) * 2048.0f), Ab = (uint32_t)(fminf( A.z, 31.999f ) * 2048.0f);
+	const uint32_t Br = (uint32_t)(fminf( B.x, 31.999f ) * 2048.0f), Bg = (uint32_t)(fminf( B.y, 31.999f ) * 2048.0f), Bb = (uint32_t)(fminf( B.z, 31.999f ) * 2048.0f);
+	return make_float4( __uint_as_float( (Ar << 16) + Ag ), __uint_as_float( Ab ), __uint_as_float( (Br << 16) + Bg ), __uint_as_float( Bb ) );
+}
+__device__ __forceinline__ float3 DirectOf( const float4 X )
+{
+	const uint32_t v0 = __float_as_uint( X.x ), v1 = __float_as_uint( X.y );
+	return make_float3( (float)(v0 >> 16) * (1.0f / 2048.0f), (float)(v0 & 65535) * (1.0f / 2048.0f), (float)v1 * (1.0f / 2048.0f) );
+}
+__device__ __forceinline__ float3 IndirectOf( const float4 X )
+{
+	const uint32_t v2 = __float_as_uint( X.z ), v3 = __float_as_uint( X.w );
+	return make_float3( (float)(v2 >> 16) * (1.0f / 2048.0f), (float)(v2 & 65535) * (1.0f / 2048.0f), (float)v3 * (1.0f / 2048.0f) );
+}
+__device__ __forceinline__ float OneOverPow2( const int p ) { return __uint_as_float( (uint32_t)(127 - p) << 23 ); }
+__device__ __forceinline__ float MitchellNetravali( const float v )
+{
+	const float B = 1.0f / 3.0f, C = 1.0f / 3.0f, x = fabsf( v ), x2 = x * x, x3 = x2 * x;
+	if (x < 1) return (1.0f / 6.0f) * ((12 - 9 * B - 6 * C) * x3 + (-18 + 12 * B + 6 * C) * x2 + (6 - 2 * B));
+	else if (x < 2) return 1.0f / 6.0f * ((-B - 6 * C) * x3 + (6 * B + 30 * C) * x2 + (-12 * B - 48 * C) * x + (8 * B + 24 * C));
+	return 0.0f;
+}
+
+/* sampling_shared.h:111-215 */
+__device__ __forceinline__ float4 ReadWorldPos( const float4* __restrict__ buffer, const int x, const int y, const int w, const int h )
+{
+	if (x >= 0 && y >= 0 && x < w && y < h) return buffer[x + y * w];
+	return make_float4( 1e20f, 1e20f, 1e20f, __uint_as_float( 0 ) );
+}
+__device__ __forceinline__ float4 ReadTexelConsistent( const float4* __restrict__ buffer, const float4* __restrict__ prevWorldPos, const float4 localPos,
+	const float3 localNormal, const float u, const float v, const int w, const int h )
+{
+	const int iu1 = (int)floorf( u ), iv1 = (int)floorf( v ), iu0 = max( 0, iu1 - 1 ), iv0 = max( 0, iv1 - 1 );
+	if (iu1 >= w || iv1 >= h || iu1 < 0 || iv1 < 0) return make_float4( -1, -1, -1, -1 );
+	const float fx = u - floorf( u ), fy = v - floorf( v );
+	const float4 p0 = buffer[iu0 + iv0 * w], p1 = buffer[iu1 + iv0 * w], p2 = buffer[iu0 + iv1 * w], p3 = buffer[iu1 + iv1 * w];
+	const uint32_t n0 = __float_as_uint( prevWorldPos[iu0 + iv0 * w].w ), n1 = __float_as_uint( prevWorldPos[iu1 + iv0 * w].w );
+	const uint32_t n2 = __float_as_uint( prevWorldPos[iu0 + iv1 * w].w ), n3 = __float_as_uint( prevWorldPos[iu1 + iv1 * w].w );
+	const uint32_t spec = __float_as_uint( localPos.w ) & 3;
+	float w0 = (1 - fx) * (1 - fy), w1 = fx * (1 - fy), w2 = (1 - fx) * fy, w3 = 1 - (w0 + w1 + w2);
+	if (dot( UnpackNormal2( n0 ), localNormal ) < 0.95f || (n0 & 3) != spec) w0 = 0;
+	if (dot( UnpackNormal2( n1 ), localNormal ) < 0.95f || (n1 & 3) != spec) w1 = 0;
+	if (dot( UnpackNormal2( n2 ), localNormal ) < 0.95f || (n2 & 3) != spec) w2 = 0;
+	if (dot( UnpackNormal2( n3 ), localNormal ) < 0.95f || (n3 & 3) != spec) w3 = 0;
+	const float sum = w0 + w1 + w2 + w3;
+	if (sum == 0) return make_float4( -1, -1, -1, -1 );
+	return (w0 * p0 + w1 * p1 + w2 * p2 + w3 * p3) * (1.0f / sum);
+}
+__device__ __forceinline__ void ReadTexelConsistent2( const float4* __restrict__ buffer, const float4* __restrict__ prevWorldPos, const float4 localPos,
+	const float3 localNormal, const float u, const float v, const int w, const int h, float3& direct, float3& indirect )
+{
+	direct.x = -1;
+	const int iu1 = (int)floorf( u ), iv1 = (int)floorf( v ), iu0 = max( 0, iu1 - 1 ), iv0 = max( 0, iv1 - 1 );
+	if (iu1 >= w || iv1 >= h || iu1 < 0 || iv1 < 0) return;
+	const float fx = u - floorf( u ), fy = v - floorf( v );
+	const float4 p0 = buffer[iu0 + iv0 * w], p1 = buffer[iu1 + iv0 * w], p2 = buffer[iu0 + iv1 * w], p3 = buffer[iu1 + iv1 * w];
+	const uint32_t n0 = __float_as_uint( prevWorldPos[iu0 + iv0 * w].w ), n1 = __float_as_uint( prevWorldPos[iu1 + iv0 * w].w );
+	const uint32_t n2 = __float_as_uint( prevWorldPos[iu0 + iv1 * w].w ), n3 = __float_as_uint( prevWorldPos[iu1 + iv1 * w].w );
+	const uint32_t spec = __float_as_uint( localPos.w ) & 3;
+	float w0 = (1 - fx) * (1 - fy), w1 = fx * (1 - fy), w2 = (1 - fx) * fy, w3 = 1 - (w0 + w1 + w2);
+	if (dot( UnpackNormal2( n0 ), localNormal ) < 0.975f || (n0 & 3) != spec) w0 = 0;
+	if (dot( UnpackNormal2( n1 ), localNormal ) < 0.975f || (n1 & 3) != spec) w1 = 0;
+	if (dot( UnpackNormal2( n2 ), localNormal ) < 0.975f || (n2 & 3) != spec) w2 = 0;
+	if (dot( UnpackNormal2( n3 ), localNormal ) < 0.975f || (n3 & 3) != spec) w3 = 0;
+	const float sum = w0 + w1 + w2 + w3;
+	if (sum == 0) return;
+	const float r = 1.0f / sum;
+	direct = (w0 * DirectOf( p0 ) + w1 * DirectOf( p1 ) + w2 * DirectOf( p2 ) + w3 * DirectOf( p3 )) * r;
+	indirect = (w0 * IndirectOf( p0 ) + w1 * IndirectOf( p1 ) + w2 * IndirectOf( p2 ) + w3 * IndirectOf( p3 )) * r;
+}
+
+/* ---- prepare (finalize_shared.h:169-314) ------------------------------------------------------------------------ */
+__device__ __forceinline__ float WorldDistance( const int x, const int y, const float4 cur, const float4* __restrict__ prevWorldPos, const int w, const int h )
+{
+	const float4 p = ReadWorldPos( prevWorldPos, x, y, w, h );
+	if ((__float_as_uint( p.w ) & 3) != 1) return 1e21f;
+	if (dot( UnpackNormal2( __float_as_uint( cur.w ) ), UnpackNormal2( __float_as_uint( p.w ) ) ) < 0.85f) return 1e21f;
+	return sqrtf( sqrLen( make_float3( cur.x - p.x, cur.y - p.y, cur.z - p.z ) ) );
+}
+__device__ __forceinline__ float FineWorldDistance( const float px, const float py, const float4 cur, const float4* __restrict__ prevWorldPos, const int w, const int h )
+{
+	const int x0 = (int)px, y0 = (int)py;
+	const float fx = px - floorf( px ), fy = py - floorf( py );
+	const float w0 = (1 - fx) * (1 - fy), w1 = fx * (1 - fy), w2 = (1 - fx) * fy, w3 = fx * fy;
+	const float d0 = WorldDistance( x0, y0, cur, prevWorldPos, w, h ), d1 = WorldDistance( x0 + 1, y0, cur, prevWorldPos, w, h );
+	const float d2 = WorldDistance( x0, y0 + 1, cur, prevWorldPos, w, h ), d3 = WorldDistance( x0 + 1, y0 + 1, cur, prevWorldPos, w, h );
+	float totalWeight = 0, totalDist = 0;
+	if (d0 < 1e20f) totalDist += d0 * w0, totalWeight += w0;
+	if (d1 < 1e20f) totalDist += d1 * w1, totalWeight += w1;
+	if (d2 < 1e20f) totalDist += d2 * w2, totalWeight += w2;
+	if (d3 < 1e20f) totalDist += d3 * w3, totalWeight += w3;
+	return totalWeight == 0 ? 1e20f : totalDist / totalWeight;
+}
+
+struct PrepareArgs
+{
+	const float4* accumulator; uint4* features; const float4* worldPos; const float4* prevWorldPos;
+	float4* shading; float2* motion; float4* moments; const float4* prevMoments; const float4* deltaDepth;
+	float4 prevPos, prevE, prevRight, prevUp;
+	float j0, j1, prevj0, prevj1;
+	int w, h; float pixelValueScale, directClamp, indirectClamp; int camIsStationary;
+};
+
+__global__ void __launch_bounds__( 256 ) prepareKernel( const PrepareArgs a )
+{
+	const int x = threadIdx.x + blockIdx.x * blockDim.x, y = threadIdx.y + blockIdx.y * blockDim.y;
+	if (x >= a.w || y >= a.h) return;
+	const int pixelIdx = x + y * a.w;
+	const float3 direct = xyz( a.accumulator[pixelIdx] ) * a.pixelValueScale;
+	const uint4 feat = a.features[pixelIdx];
+	const float4 lwp = a.worldPos[pixelIdx];
+	const float3 albedo = RGB32toHDRmin1( feat.x );
+	const float3 indirect = xyz( a.accumulator[pixelIdx + a.w * a.h] ) * a.pixelValueScale;
+	const float3 reci = make_float3( 1.0f / albedo.x, 1.0f / albedo.y, 1.0f / albedo.z );
+	const float3 directLight = min3f( direct * reci, a.directClamp ), indirectLight = min3f( indirect * reci, a.indirectClamp );
+	a.shading[pixelIdx] = CombineToFloat4( directLight, indirectLight );
+	float lumDirect = Luminance( directLight ), lumDirect2 = lumDirect * lumDirect;
+	float lumIndirect = Luminance( indirectLight ), lumIndirect2 = lumIndirect * lumIndirect;
+	float2 prev;
+	if (((feat.w >> 4) & 3) == 0)
+	{
+		// diffuse: analytic reprojection into the previous view
+		const float3 D = xyz( lwp ) - xyz( a.prevPos );
+		const float il = rsqrtf( dot( D, D ) );
+		const float3 Dn = D * il;
+		const float t = a.prevPos.w / dot( xyz( a.prevE ), Dn );
+		const float3 S = xyz( a.prevPos ) + Dn * t;
+		prev = make_float2( dot( S, xyz( a.prevRight ) ) - a.prevRight.w - a.j0, dot( S, xyz( a.prevUp ) ) - a.prevUp.w - a.j1 );
+	}
+	else
+	{
+		prev = make_float2( (float)x, (float)y );
+		if (!a.camIsStationary)
+		{
+			// specular: diamond search for the world position of this pixel in the previous frame
+			const float4 pw = a.prevWorldPos[pixelIdx];
+			float bestDist = sqrtf( sqrLen( make_float3( lwp.x - pw.x, lwp.y - pw.y, lwp.z - pw.z ) ) ), stepSize = 5.0f;
+			const float ox = a.j0 - a.prevj0, oy = a.j1 - a.prevj1;
+			int iter = 0;
+			while (1)
+			{
+				int tap = 0;
+				const float cx = prev.x, cy = prev.y;
+				float d;
+				d = FineWorldDistance( cx - stepSize + ox, cy + oy, lwp, a.prevWorldPos, a.w, a.h );
+				if (d < bestDist) bestDist = d, prev = make_float2( cx - stepSize, cy ), tap = 1;
+				d = FineWorldDistance( cx + stepSize + ox, cy + oy, lwp, a.prevWorldPos, a.w, a.h );
+				if (d < bestDist) bestDist = d, prev = make_float2( cx + stepSize, cy ), tap = 2;
+				d = FineWorldDistance( cx + ox, cy - stepSize + oy, lwp, a.prevWorldPos, a.w, a.h );
+				if (d < bestDist) bestDist = d, prev = make_float2( cx, cy - stepSize ), tap = 3;
+				d = FineWorldDistance( cx + ox, cy + stepSize + oy, lwp, a.prevWorldPos, a.w, a.h );
+				if (d < bestDist) bestDist = d, prev = make_float2( cx, cy + stepSize ), tap = 4;
+				if (tap == 0) { stepSize *= 0.45f; if (stepSize < 0.05f) break; }
+				if (++iter == 25) break;
+			}
+		}
+	}
+	prev.x += 0.5f, prev.y += 0.5f;
+	uint32_t fw = feat.w;
+	if (prev.x >= 0 && prev.x < a.w && prev.y >= 0 && prev.y < a.h)
+	{
+		const float4 history = ReadTexelConsistent( a.prevMoments, a.prevWorldPos, lwp, UnpackNormal2( feat.y ), prev.x, prev.y, a.w, a.h );
+		if (history.x > -1)
+		{
+			lumDirect = 0.2f * lumDirect + 0.8f * history.x, lumDirect2 = 0.2f * lumDirect2 + 0.8f * history.y;
+			lumIndirect = 0.2f * lumIndirect + 0.8f * history.z, lumIndirect2 = 0.2f * lumIndirect2 + 0.8f * history.w;
+			if ((fw & 15) < 15) fw++;
+		}
+		else fw &= 0xfffffff0u;
+	}
+	else fw &= 0xfffffff0u;
+	if (fw != feat.w) a.features[pixelIdx].w = fw;
+	a.motion[pixelIdx] = prev;
+	a.moments[pixelIdx] = make_float4( lumDirect, lumDirect2, lumIndirect, lumIndirect2 );
+}
+
+/* ---- a-trous (finalize_shared.h:320-484) ------------------------------------------------------------------------ */
+#define AT_BX 32
+#define AT_BY 8
+struct AtrousArgs
+{
+	const uint4* features; const float4* prevWorldPos; const float4* worldPos; const float4* deltaDepth; const float2* motion; const float4* moments;
+	const float4* A; const float4* B; float4* C;
+	int w, h, phase, lastPass;
+};
+
+template <int STEP> __global__ void __launch_bounds__( AT_BX * AT_BY ) atrousKernel( const AtrousArgs a )
+{
+	constexpr int HALO = 2 * STEP, TW = AT_BX + 2 * HALO, TH = AT_BY + 2 * HALO;
+	extern __shared__ float4 tile[];			// [TH][TW] shading, then [TH][TW] features (as float4 bit patterns)
+	float4* tShade = tile;
+	uint4* tFeat = (uint4*)(tile + TW * TH);
+	const int x0 = blockIdx.x * AT_BX, y0 = blockIdx.y * AT_BY;
+	for (int i = threadIdx.y * AT_BX + threadIdx.x; i < TW * TH; i += AT_BX * AT_BY)
+	{
+		const int ty = i / TW, tx = i - ty * TW;
+		const int gx = min( max( x0 - HALO + tx, 0 ), a.w - 1 ), gy = y0 - HALO + ty;
+		if (gy >= 0 && gy < a.h) tShade[i] = a.A[gx + gy * a.w], tFeat[i] = a.features[gx + gy * a.w];
+	}
+	__syncthreads();
+	const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+	if (x >= a.w || y >= a.h) return;
+	const int pixelIdx = x + y * a.w, phase = a.phase;
+	const int cx = threadIdx.x + HALO, cy = threadIdx.y + HALO;
+	const uint4 lf = tFeat[cx + cy * TW];
+	const float3 localNormal = UnpackNormal2( lf.y ), localColor = RGB32toHDR( lf.x );
+	const int localMatID = lf.w >> 4;
+	const float4 combined = tShade[cx + cy * TW];
+	float dirW = 1, indW = 1;
+	float3 dirSum = DirectOf( combined ), indSum = IndirectOf( combined );
+	const float localDirect = Luminance( dirSum ), localIndirect = Luminance( indSum );
+	const float localDepth = __uint_as_float( lf.z );
+	const float4 dd = a.deltaDepth[pixelIdx];
+	const float localDdx = dd.z, localDdy = dd.w;
+	const float sigma = 10.0f * OneOverPow2( phase - 1 );
+	const float factor = (lf.w & 15) == 0 ? 400.0f : 1.0f;
+	const float4 m = a.moments[pixelIdx];
+	const float var_dir = m.y - m.x * m.x, var_ind = m.w - m.z * m.z;
+	const float rdir = -1.0f / (sigma * factor * sqrtf( var_dir + 0.00001f ) + 0.00001f);
+	const float rind = -1.0f / (sigma * factor * sqrtf( var_ind + 0.00001f ) + 0.00001f);
+	for (int vv = -2; vv <= 2; vv++)
+	{
+		const int v = vv * STEP + y;
+		const int r = abs( vv ) == 2 ? 1 : 2;
+		if (v >= 0 && v < a.h) for (int uu = -r; uu <= r; uu++) if (uu != 0 || vv != 0)
+		{
+			// columns are clamped to the image by the tile loader, like the reference clamps u
+			const int ti = (cx + uu * STEP) + (cy + vv * STEP) * TW;
+			const float4 nc = tShade[ti];
+			const uint4 nf = tFeat[ti];
+			const float w_dist = (uu * uu + vv * vv) * (-1.0f / 7.5f);
+			const float3 nDirect = DirectOf( nc ), nIndirect = IndirectOf( nc );
+			float w_normal = powf( fmaxf( 0.0f, dot( UnpackNormal2( nf.y ), localNormal ) ), 128 );
+			const float expected = localDepth + localDdx * (float)(uu * STEP) + localDdy * (float)(vv * STEP);
+			const float depthError = fabsf( expected - __uint_as_float( nf.z ) );
+			const float expectedDiff = fabsf( expected - localDepth );
+			const float w_depth = depthError / fmaxf( 0.00001f, (0.5f + phase * 0.5f) * expectedDiff );
+			w_normal *= ((int)(nf.w >> 4) != localMatID) ? 0.0001f : dot( localColor, RGB32toHDR( nf.x ) );
+			float wd = w_normal * __expf( fabsf( localDirect - Luminance( nDirect ) ) * rdir + w_dist - w_depth );
+			float wi = w_normal * __expf( fabsf( localIndirect - Luminance( nIndirect ) ) * rind + w_dist - w_depth );
+			if (!isfinite( wd )) wd = 0;
+			if (!isfinite( wi )) wi = 0;
+			dirSum += nDirect * wd, dirW += wd;
+			indSum += nIndirect * wi, indW += wi;
+		}
+	}
+	float3 dirF = dirSum * (1.0f / fmaxf( 0.0001f, dirW )), indF = indSum * (1.0f / fmaxf( 0.0001f, indW ));
+	if (STEP == 1 && phase == 1)
+	{
+		// temporal blend with the previous frame's phase-1 output, clamped to the 3x3 YCoCg neighbourhood
+		const float2 pp = a.motion[pixelIdx];
+		const int px = (int)pp.x, py = (int)pp.y;
+		if (px >= 0 && px < a.w && py >= 0 && py < a.h)
+		{
+			float3 prevDirect, prevIndirect;
+			const float4 localPos = a.worldPos[pixelIdx];
+			ReadTexelConsistent2( a.B, a.prevWorldPos, localPos, localNormal, pp.x, pp.y, a.w, a.h, prevDirect, prevIndirect );
+			if (prevDirect.x != -1)
+			{
+				prevDirect = RGBToYCoCg( prevDirect ), prevIndirect = RGBToYCoCg( prevIndirect );
+				float3 dirAvg = RGBToYCoCg( dirF ), dirVar = dirAvg * dirAvg, indAvg = RGBToYCoCg( indF ), indVar = indAvg * indAvg;
+				auto tap = [&]( const int ox, const int oy ) {
+					const float4 c4 = tShade[(cx + ox) + (cy + oy) * TW];
+					const float3 f = RGBToYCoCg( DirectOf( c4 ) ), g = RGBToYCoCg( IndirectOf( c4 ) );
+					dirAvg += f, dirVar += f * f, indAvg += g, indVar += g * g;
+				};
+				if (x > 1)
+				{
+					if (y > 1) tap( -1, -1 );
+					tap( -1, 0 );
+					if (y < a.h - 1) tap( -1, 1 );
+				}
+				if (y > 1) tap( 0, -1 );
+				if (y < a.h - 1) tap( 0, 1 );
+				if (x < a.w - 1)
+				{
+					if (y > 1) tap( 1, -1 );
+					tap( 1, 0 );
+					if (y < a.h - 1) tap( 1, 1 );
+				}
+				dirAvg *= 1.0f / 9.0f, dirVar *= 1.0f / 9.0f, indAvg *= 1.0f / 9.0f, indVar *= 1.0f / 9.0f;
+				float3 sDir = max3v( f3( 0 ), dirVar - dirAvg * dirAvg ), sInd = max3v( f3( 0 ), indVar - indAvg * indAvg );
+				sDir = make_float3( sqrtf( sDir.x ), sqrtf( sDir.y ), sqrtf( sDir.z ) ), sInd = make_float3( sqrtf( sInd.x ), sqrtf( sInd.y ), sqrtf( sInd.z ) );
+				prevDirect = clamp3( prevDirect, dirAvg - 0.75f * sDir, dirAvg + 0.75f * sDir );
+				prevIndirect = clamp3( prevIndirect, indAvg - 0.75f * sInd, indAvg + 0.75f * sInd );
+				dirF = dirF * 0.1f + YCoCgToRGB( prevDirect ) * 0.9f;
+				indF = indF * 0.1f + YCoCgToRGB( prevIndirect ) * 0.9f;
+			}
+		}
+	}
+	if (a.lastPass)
+	{
+		const float3 c = (dirF + indF) * RGB32toHDR( lf.x );
+		a.C[pixelIdx] = make_float4( sqrtf( c.x ), sqrtf( c.y ), sqrtf( c.z ), 1 );
+	}
+	else a.C[pixelIdx] = CombineToFloat4( dirF, indF );
+}
+
+/* ---- TAA (finalize_shared.h:498-548) ------------------------------------------------------------------------------ */
+__global__ void __launch_bounds__( 256 ) taaKernel( const float4* __restrict__ pixelsIn, float4* __restrict__ pixelsOut, const float4* __restrict__ prevPixels,
+	const float2* __restrict__ motion, const int w, const int h )
+{
+	__shared__ float4 tile[10][34];
+	const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 8;
+	for (int i = threadIdx.y * 32 + threadIdx.x; i < 340; i += 256)
+	{
+		const int ty = i / 34, tx = i - ty * 34;
+		const int gx = min( max( x0 - 1 + tx, 0 ), w - 1 ), gy = min( max( y0 - 1 + ty, 0 ), h - 1 );
+		tile[ty][tx] = pixelsIn[gx + gy * w];
+	}
+	__syncthreads();
+	const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+	if (x >= w || y >= h) return;
+	const int pixelIdx = x + y * w, cx = threadIdx.x + 1, cy = threadIdx.y + 1;
+	float3 pixel = xyz( tile[cy][cx] );
+	const float2 mv = motion[pixelIdx];
+	const float pu = mv.x - 0.5f, pv = mv.y - 0.5f;
+	if (pu >= 0 && pu < w && pv >= 0 && pv < h)
+	{
+		const float3 newPixel = RGBToYCoCg( pixel );
+		// Mitchell-Netravali history fetch (sampling_shared.h:117-134)
+		float3 hist;
+		{
+			const int x1 = (int)(pu - 2.0f), y1 = (int)(pv - 2.0f);
+			float totalWeight = 0;
+			float4 total = make_float4( 0, 0, 0, 0 );
+			for (int yy = y1; yy < y1 + 4; yy++) for (int xx = x1; xx < x1 + 4; xx++) if (xx >= 0 && yy > 0 && xx < w && yy < h)
+			{
+				const float weight = MitchellNetravali( (float)xx - pu ) * MitchellNetravali( (float)yy - pv );
+				total = total + prevPixels[xx + yy * w] * weight, totalWeight += weight;
+			}
+			hist = xyz( total * (1.0f / totalWeight) );
+		}
+		float3 history = RGBToYCoCg( hist );
+		float3 avg = newPixel, var = newPixel * newPixel;
+		auto tap = [&]( const int ox, const int oy ) { const float3 f = RGBToYCoCg( xyz( tile[cy + oy][cx + ox] ) ); avg += f, var += f * f; };
+		if (x > 1)
+		{
+			if (y > 1) tap( -1, -1 );
+			tap( -1, 0 );
+			if (y < h - 1) tap( -1, 1 );
+		}
+		if (y > 1) tap( 0, -1 );
+		if (y < h - 1) tap( 0, 1 );
+		if (x < w - 1)
+		{
+			if (y > 1) tap( 1, -1 );
+			tap( 1, 0 );
+			if (y < h - 1) tap( 1, 1 );
+		}
+		avg *= 1.0f / 9.0f, var *= 1.0f / 9.0f;
+		float3 sigma = max3v( f3( 0 ), var - avg * avg );
+		sigma = make_float3( sqrtf( sigma.x ), sqrtf( sigma.y ), sqrtf( sigma.z ) );
+		history = clamp3( history, avg - 1.25f * sigma, avg + 1.25f * sigma );
+		pixel = YCoCgToRGB( newPixel * 0.1f + history * 0.9f );
+		if (isnan( pixel.x + pixel.y + pixel.z )) pixel = YCoCgToRGB( newPixel );
+	}
+	const float3 o = min3f( pixel, 10.0f );
+	pixelsOut[pixelIdx] = make_float4( o.x, o.y, o.z, 0 );
+}
+
+/* ---- present: unsharpenTAAKernel (:554-583) or finalizeNoTAAKernel (:589-600); border pixels are left untouched ---- */
+__global__ void __launch_bounds__( 256 ) presentKernel( const float4* __restrict__ pixels, float4* __restrict__ target, const int w, const int h, const int taa )
+{
+	__shared__ float4 tile[10][34];
+	const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 8;
+	for (int i = threadIdx.y * 32 + threadIdx.x; i < 340; i += 256)
+	{
+		const int ty = i / 34, tx = i - ty * 34;
+		const int gx = min( max( x0 - 1 + tx, 0 ), w - 1 ), gy = min( max( y0 - 1 + ty, 0 ), h - 1 );
+		tile[ty][tx] = pixels[gx + gy * w];
+	}
+	__syncthreads();
+	const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+	if (x == 0 || y == 0 || x >= w - 1 || y >= h - 1) return;
+	const int cx = threadIdx.x + 1, cy = threadIdx.y + 1;
+	const float4 c = tile[cy][cx];
+	if (!taa)
+	{
+		target[x + y * w] = make_float4( sqrtf( c.x ), sqrtf( c.y ), sqrtf( c.z ), 0 );
+		return;
+	}
+	const float4 p0 = tile[cy - 1][cx - 1], p1 = tile[cy - 1][cx], p2 = tile[cy - 1][cx + 1], p3 = tile[cy][cx + 1];
+	const float4 p4 = tile[cy + 1][cx + 1], p5 = tile[cy + 1][cx], p6 = tile[cy + 1][cx - 1], p7 = tile[cy][cx - 1];
+	const float4 blur = 0.35f * p0 + 0.5f * p1 + 0.35f * p2 + 0.5f * p3 + 0.35f * p4 + 0.5f * p5 + 0.35f * p6 + 0.5f * p7;
+	const float4 sharp = c * 2.7f - 0.5f * blur;
+	const float4 px = make_float4( fmaxf( c.x, sharp.x ), fmaxf( c.y, sharp.y ), fmaxf( c.z, sharp.z ), fmaxf( c.w, sharp.w ) );
+	target[x + y * w] = make_float4( px.x * px.x, px.y * px.y, px.z * px.z, 0 );
+}
+
+/* ---- host side --------------------------------------------------------------------------------------------------- */
+static void FilterChainImpl( const FilterBuffers& b, const FilterSettings& s, cudaStream_t st, float* hPrepare, float* hP1, float* hP2, float* hP3 )
+{
+	auto snap = [&]( float* dst, const float4* src ) { if (dst) cudaMemcpyAsync( dst, src, (size_t)s.w * s.h * 16, cudaMemcpyDeviceToHost, st ); };
+	const int w = s.w, h = s.h;
+	const dim3 grid( (w + 31) / 32, (h + 7) / 8 ), block( 32, 8 );
+	// reprojection constants of the previous view (finalize_shared.h:301-313)
+	const float* pv = s.prevView;
+	const float3 pos = make_float3( pv[0], pv[1], pv[2] ), p1 = make_float3( pv[3], pv[4], pv[5] ), p2 = make_float3( pv[6], pv[7], pv[8] ), p3 = make_float3( pv[9], pv[10], pv[11] );
+	auto norm = []( const float3 v ) { const float l = 1.0f / sqrtf( v.x * v.x + v.y * v.y + v.z * v.z ); return v * l; };
+	auto len = []( const float3 v ) { return sqrtf( v.x * v.x + v.y * v.y + v.z * v.z ); };
+	const float3 centre = 0.5f * (p2 + p3), direction = norm( centre - pos ), right = norm( p2 - p1 ), up = norm( p3 - p1 );
+	const float lenReci = h / len( p3 - p1 );
+	PrepareArgs pa;
+	pa.accumulator = b.accumulator, pa.features = b.features, pa.worldPos = b.worldPos, pa.prevWorldPos = b.prevWorldPos;
+	pa.shading = b.shading, pa.motion = b.motion, pa.moments = b.moments, pa.prevMoments = b.prevMoments, pa.deltaDepth = b.deltaDepth;
+	pa.prevPos = f4( pos, -(dot( pos, direction ) - dot( centre, direction )) ), pa.prevE = f4( direction, 0 );
+	pa.prevRight = f4( right * lenReci, dot( p1, right ) * lenReci ), pa.prevUp = f4( up * lenReci, dot( p1, up ) * lenReci );
+	pa.j0 = s.j0, pa.j1 = s.j1, pa.prevj0 = s.prevj0, pa.prevj1 = s.prevj1;
+	pa.w = w, pa.h = h, pa.pixelValueScale = 1.0f / (float)s.samplesTaken, pa.directClamp = s.directClamp, pa.indirectClamp = s.indirectClamp;
+	pa.camIsStationary = s.camIsStationary;
+	prepareKernel<<<grid, block, 0, st>>>( pa );
+	snap( hPrepare, b.shading );
+	AtrousArgs aa;
+	aa.features = b.features, aa.prevWorldPos = b.prevWorldPos, aa.worldPos = b.worldPos, aa.deltaDepth = b.deltaDepth, aa.motion = b.motion, aa.moments = b.moments;
+	aa.w = w, aa.h = h;
+	auto smem = []( int step ) { return (size_t)(AT_BX + 4 * step) * (AT_BY + 4 * step) * 32; };
+	static bool attr = false;
+	if (!attr)
+	{
+		cudaFuncSetAttribute( atrousKernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem( 4 ) );
+		attr = true;
+	}
+	aa.A = b.shading, aa.B = b.filteredIN, aa.C = b.filteredOUT, aa.phase = 1, aa.lastPass = 0;
+	atrousKernel<1><<<grid, block, smem( 1 ), st>>>( aa );
+	snap( hP1, b.filteredOUT );
+	aa.A = b.filteredOUT, aa.B = nullptr, aa.C = b.filteredIN, aa.phase = 2;
+	atrousKernel<2><<<grid, block, smem( 2 ), st>>>( aa );
+	snap( hP2, b.filteredIN );
+	aa.A = b.filteredIN, aa.C = b.shading, aa.phase = 3, aa.lastPass = 1;
+	atrousKernel<4><<<grid, block, smem( 4 ), st>>>( aa );
+	snap( hP3, b.shading );
+	if (s.taa)
+	{
+		taaKernel<<<grid, block, 0, st>>>( b.shading, b.taaOut, b.prevPixels, b.motion, w, h );
+		presentKernel<<<grid, block, 0, st>>>( b.taaOut, b.target, w, h, 1 );
+	}
+	else presentKernel<<<grid, block, 0, st>>>( b.shading, b.target, w, h, 0 );
+}
+
+void LaunchFilterChain( const FilterBuffers& b, const FilterSettings& s, cudaStream_t st ) { FilterChainImpl( b, s, st, nullptr, nullptr, nullptr, nullptr ); }
+void LaunchFilterChainStaged( const FilterBuffers& b, const FilterSettings& s, cudaStream_t st, float* hPrepare, float* hP1, float* hP2, float* hP3 )
+{
+	FilterChainImpl( b, s, st, hPrepare, hP1, hP2, hP3 );
+}
+
+} // namespace lh2b

@@ -18,6 +18,23 @@ void LaunchExtendCounted( const DevScene& scene, const PathSet& in, float4* hits
 void LaunchConnect( const DevScene& scene, const PathSet& conn, float4* accumulator, const uint32_t* countPtr, uint32_t* workCounter, uint32_t maxRays, int smCount, cudaStream_t s );
 void LaunchShade( const RenderParams& p, const PathSet& in, const PathSet& out, const float4* hits, const PathSet& conn,
 	int pathLength, uint32_t R0, bool useNEE, uint32_t maxPaths, int smCount, cudaStream_t s );
+/* SVGF / TAA chain (filter_kernels.cu). Buffers are float4[w*h] unless noted. */
+struct FilterBuffers
+{
+	const float4* accumulator;	// [2*w*h]: direct, then indirect
+	uint4* features; const float4* worldPos; const float4* prevWorldPos; const float4* deltaDepth;
+	float4* shading; float2* motion; float4* moments; const float4* prevMoments;
+	float4* filteredIN; float4* filteredOUT;	// IN holds last frame's phase-1 output on entry and this frame's phase-2 output on exit
+	const float4* prevPixels; float4* taaOut; float4* target;
+};
+struct FilterSettings
+{
+	int w, h, samplesTaken, camIsStationary, taa;
+	float directClamp, indirectClamp, j0, j1, prevj0, prevj1;
+	float prevView[17];
+};
+void LaunchFilterChain( const FilterBuffers& b, const FilterSettings& s, cudaStream_t st );
+void LaunchFilterChainStaged( const FilterBuffers& b, const FilterSettings& s, cudaStream_t st, float* hPrepare, float* hP1, float* hP2, float* hP3 );
 void LaunchTagTriangles( float4* tris, int triCount, uint32_t inst, cudaStream_t s );
 void LaunchFinalize( const float4* accumulator, float4* out, int n, int samplesTaken, cudaStream_t s );
 

@@ -500,6 +500,38 @@ int lh2b_shade_paths( lh2b_core* core, int pathLength, int n, const float* O4, c
 	API_END
 }
 
+int lh2b_filter_chain( lh2b_core* core, lh2b_filter_io* io )
+{
+	API_BEGIN
+	FinishFrame( core );
+	const int w = io->w, h = io->h;
+	const size_t px = (size_t)w * h;
+	cudaStream_t s = core->stream;
+	DevBuf<float4> acc, wp, pwp, dd, shading, moments, pmom, fIN, fOUT, prevPixels, taaOut, target;
+	DevBuf<uint4> feat;
+	DevBuf<float2> motion;
+	acc.Upload( (const float4*)io->accumulator, 2 * px, s ), feat.Upload( (const uint4*)io->features, px, s );
+	wp.Upload( (const float4*)io->worldPos, px, s ), pwp.Upload( (const float4*)io->prevWorldPos, px, s ), dd.Upload( (const float4*)io->deltaDepth, px, s );
+	pmom.Upload( (const float4*)io->prevMoments, px, s ), fIN.Upload( (const float4*)io->filteredIN, px, s ), prevPixels.Upload( (const float4*)io->prevPixels, px, s );
+	shading.Resize( px ), moments.Resize( px ), fOUT.Resize( px ), taaOut.Resize( px ), target.Resize( px ), motion.Resize( px );
+	CUDA_CHECK( cudaMemsetAsync( target.ptr, 0, px * 16, s ) );
+	CUDA_CHECK( cudaMemsetAsync( taaOut.ptr, 0, px * 16, s ) );
+	FilterBuffers b = { acc.ptr, feat.ptr, wp.ptr, pwp.ptr, dd.ptr, shading.ptr, motion.ptr, moments.ptr, pmom.ptr, fIN.ptr, fOUT.ptr, prevPixels.ptr, taaOut.ptr, target.ptr };
+	FilterSettings fs;
+	fs.w = w, fs.h = h, fs.samplesTaken = io->samplesTaken, fs.camIsStationary = io->camIsStationary, fs.taa = io->taa;
+	fs.directClamp = io->directClamp, fs.indirectClamp = io->indirectClamp, fs.j0 = io->j0, fs.j1 = io->j1, fs.prevj0 = io->prevj0, fs.prevj1 = io->prevj1;
+	memcpy( fs.prevView, io->prevView, sizeof( fs.prevView ) );
+	// the chain overwrites 'shading' three times and filteredIN/OUT once each: run it stage by stage to hand back every output
+	FilterSettings one = fs;
+	LaunchFilterChainStaged( b, one, s, io->shadingAfterPrepare, io->phase1, io->phase2, io->phase3 );
+	CUDA_CHECK( cudaGetLastError() );
+	auto down = [&]( void* dst, const void* src, size_t bytes ) { if (dst) CUDA_CHECK( cudaMemcpyAsync( dst, src, bytes, cudaMemcpyDeviceToHost, s ) ); };
+	down( io->featuresOut, feat.ptr, px * 16 ), down( io->motion, motion.ptr, px * 8 ), down( io->moments, moments.ptr, px * 16 );
+	down( io->taaPixels, taaOut.ptr, px * 16 ), down( io->target, target.ptr, px * 16 );
+	CUDA_CHECK( cudaStreamSynchronize( s ) );
+	API_END
+}
+
 int lh2b_set_sample_shard( lh2b_core* core, int firstSample, int totalSpp )
 {
 	API_BEGIN

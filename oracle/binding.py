@@ -321,3 +321,53 @@ def ref_shade_gpu(oracle, view, path_length, O4, D4, T4, hits, R0, shift, pass_,
     ext = dict(O=ps[n:n + n_ext], D=ps[stride + n:stride + n + n_ext], T=ps[2 * stride + n:2 * stride + n + n_ext])
     sh = dict(O=conn[0:n_sh], D=conn[2 * stride:2 * stride + n_sh], E=conn[4 * stride:4 * stride + n_sh])
     return ext, sh, acc.reshape(oracle.h, oracle.w, 4), cnt
+
+
+# ---- the reference's own SVGF / TAA kernels (oracle/_ref/libref_filter_gpu.so) ---------------------------
+
+class FilterIO(ctypes.Structure):
+    """Shared by reffilter_run (reference kernels) and lh2b_filter_chain (product): identical field order."""
+    _fields_ = [("w", ctypes.c_int), ("h", ctypes.c_int), ("samplesTaken", ctypes.c_int), ("camIsStationary", ctypes.c_int), ("taa", ctypes.c_int),
+                ("directClamp", ctypes.c_float), ("indirectClamp", ctypes.c_float), ("j0", ctypes.c_float), ("j1", ctypes.c_float),
+                ("prevj0", ctypes.c_float), ("prevj1", ctypes.c_float), ("prevView", ctypes.c_float * 17),
+                ("accumulator", ctypes.c_void_p), ("features", ctypes.c_void_p), ("worldPos", ctypes.c_void_p), ("prevWorldPos", ctypes.c_void_p),
+                ("deltaDepth", ctypes.c_void_p), ("prevMoments", ctypes.c_void_p), ("filteredIN", ctypes.c_void_p), ("prevPixels", ctypes.c_void_p),
+                ("featuresOut", ctypes.c_void_p), ("shadingAfterPrepare", ctypes.c_void_p), ("motion", ctypes.c_void_p), ("moments", ctypes.c_void_p),
+                ("phase1", ctypes.c_void_p), ("phase2", ctypes.c_void_p), ("phase3", ctypes.c_void_p), ("taaPixels", ctypes.c_void_p), ("target", ctypes.c_void_p)]
+
+
+REF_FILTER_GPU = os.path.join(_HERE, "_ref", "libref_filter_gpu.so")
+FILTER_OUTPUTS = ("featuresOut", "shadingAfterPrepare", "motion", "moments", "phase1", "phase2", "phase3", "taaPixels", "target")
+
+
+def have_ref_filter_gpu():
+    return os.path.exists(REF_FILTER_GPU)
+
+
+def make_filter_io(inputs, settings):
+    """inputs: dict of numpy arrays (accumulator, features, worldPos, prevWorldPos, deltaDepth, prevMoments, filteredIN, prevPixels);
+    settings: dict(w, h, samplesTaken, camIsStationary, taa, directClamp, indirectClamp, j0, j1, prevj0, prevj1, prevView (ViewPyramid array)).
+    Returns (FilterIO, outputs dict, keepalive)."""
+    io = FilterIO()
+    w, h = settings["w"], settings["h"]
+    for k in ("w", "h", "samplesTaken", "camIsStationary", "taa", "directClamp", "indirectClamp", "j0", "j1", "prevj0", "prevj1"):
+        setattr(io, k, settings[k])
+    io.prevView[:] = [float(x) for x in np.frombuffer(np.ascontiguousarray(settings["prevView"]).tobytes(), np.float32)]
+    keep = {}
+    for k in ("accumulator", "features", "worldPos", "prevWorldPos", "deltaDepth", "prevMoments", "filteredIN", "prevPixels"):
+        keep[k] = np.ascontiguousarray(inputs[k])
+        setattr(io, k, keep[k].ctypes.data)
+    outs = {}
+    for k in FILTER_OUTPUTS:
+        shape = (h, w, 2) if k == "motion" else (h, w, 4)
+        outs[k] = np.zeros(shape, np.uint32 if k == "featuresOut" else np.float32)
+        setattr(io, k, outs[k].ctypes.data)
+    return io, outs, keep
+
+
+def ref_filter_gpu(inputs, settings):
+    io, outs, keep = make_filter_io(inputs, settings)
+    rc = ctypes.CDLL(REF_FILTER_GPU).reffilter_run(ctypes.byref(io))
+    if rc != 0:
+        raise RuntimeError("reffilter_run failed")
+    return outs
