@@ -128,6 +128,9 @@ typedef struct lh2b_filter_io
 	float* phase1; float* phase2; float* phase3; float* taaPixels; float* target;
 } lh2b_filter_io;
 LH2B_API int lh2b_filter_chain( lh2b_core* core, lh2b_filter_io* io );
+/* Filter mode only: copy the per-pixel filter inputs of the last frame to host (any pointer may be null):
+   features uint4[w*h], worldPos / deltaDepth float4[w*h], accumulator2 float4[2*w*h] (direct, then indirect). */
+LH2B_API int lh2b_read_filter_buffers( lh2b_core* core, uint32_t* features, float* worldPos, float* deltaDepth, float* accumulator2 );
 
 /* The C handle behind a CoreAPI_Base* obtained from CreateCore() (for headless read-back and statistics). */
 LH2B_API lh2b_core* lh2b_handle_of( void* coreApiBase );

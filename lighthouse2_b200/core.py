@@ -185,6 +185,13 @@ class RenderCore:
         sh = dict(O=out[3][:ns.value], D=out[4][:ns.value], E=out[5][:ns.value])
         return ext, sh, acc
 
+    def ReadFilterBuffers(self):
+        """Filter mode: (features uint32[h,w,4], worldPos, deltaDepth float32[h,w,4], accumulator float32[2,h,w,4]) of the last frame."""
+        h, w = self.height, self.width
+        f, wp, dd, acc = np.zeros((h, w, 4), np.uint32), np.zeros((h, w, 4), np.float32), np.zeros((h, w, 4), np.float32), np.zeros((2, h, w, 4), np.float32)
+        self._check(self._lib.lh2b_read_filter_buffers(self._h, _ptr(f), _ptr(wp), _ptr(dd), _ptr(acc)))
+        return f, wp, dd, acc
+
     def FilterChain(self, io):
         """Parity hook (lh2b_filter_chain): io is a ctypes structure laid out like lh2b_filter_io."""
         self._check(self._lib.lh2b_filter_chain(self._h, ctypes.byref(io)))

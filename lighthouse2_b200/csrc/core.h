@@ -100,6 +100,14 @@ struct lh2b_core
 	int skyW = 0, skyH = 0;
 	float worldToSky[12] = { 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0 };
 	lh2b::DevBuf<uint32_t> blueNoise;
+	// SVGF / TAA (Setting "filter", "TAA", "clampDirect", "clampIndirect"; lib/RenderCore_Optix7Filter/rendercore.cpp:656-678,897-948)
+	bool filterEnabled = false, taaEnabled = false, filterHistoryValid = false;
+	float clampDirect = 15.0f, clampIndirect = 15.0f;	// RenderSettings defaults (lib/RenderSystem/rendersystem.h:65-72)
+	lh2b::DevBuf<uint4> features;
+	lh2b::DevBuf<float4> worldPosBuf[2], deltaDepth, shading, momentsBuf[2], filteredBuf[2], taaBuf[2];
+	lh2b::DevBuf<float2> motion;
+	int filterFlip = 0;				// which of the double-buffered history sets is "current"
+	lh2abi::ViewPyramid prevView = {};
 	// timing
 	std::vector<cudaEvent_t> events;	// per frame: see render.cu
 	lh2b_frame_stats frameStats = {};

@@ -60,6 +60,48 @@ void ReleaseRenderState( lh2b_core* core )
 	if (core->hostCounters) cudaFreeHost( core->hostCounters ), core->hostCounters = nullptr;
 }
 
+static void EnsureFilterBuffers( lh2b_core* core )
+{
+	const size_t px = core->maxPixels;
+	if (core->features.count >= px) return;
+	cudaStream_t s = core->stream;
+	core->features.Resize( px ), core->deltaDepth.Resize( px ), core->shading.Resize( px ), core->motion.Resize( px );
+	CUDA_CHECK( cudaMemsetAsync( core->features.ptr, 0, px * 16, s ) );
+	for (int k = 0; k < 2; k++)
+	{
+		core->worldPosBuf[k].Resize( px ), core->momentsBuf[k].Resize( px ), core->filteredBuf[k].Resize( px ), core->taaBuf[k].Resize( px );
+		CUDA_CHECK( cudaMemsetAsync( core->worldPosBuf[k].ptr, 0, px * 16, s ) );
+		CUDA_CHECK( cudaMemsetAsync( core->momentsBuf[k].ptr, 0, px * 16, s ) );
+		CUDA_CHECK( cudaMemsetAsync( core->filteredBuf[k].ptr, 0, px * 16, s ) );
+		CUDA_CHECK( cudaMemsetAsync( core->taaBuf[k].ptr, 0, px * 16, s ) );
+	}
+	core->filterHistoryValid = false;
+}
+
+/* The SVGF / TAA tail of FinalizeRender (lib/RenderCore_Optix7Filter/rendercore.cpp:904-934), including its buffer rotation. */
+static void RunFilter( lh2b_core* core )
+{
+	const int cur = core->filterFlip, prev = cur ^ 1;
+	FilterBuffers b;
+	b.accumulator = core->accumulator.ptr, b.features = core->features.ptr, b.worldPos = core->worldPosBuf[cur].ptr, b.prevWorldPos = core->worldPosBuf[prev].ptr;
+	b.deltaDepth = core->deltaDepth.ptr, b.shading = core->shading.ptr, b.motion = core->motion.ptr;
+	b.moments = core->momentsBuf[cur].ptr, b.prevMoments = core->momentsBuf[prev].ptr;
+	b.filteredIN = core->filteredBuf[cur].ptr, b.filteredOUT = core->filteredBuf[prev].ptr;
+	b.prevPixels = core->taaBuf[prev].ptr, b.taaOut = core->taaBuf[cur].ptr, b.target = core->pixels.ptr;
+	FilterSettings fs;
+	fs.w = core->width, fs.h = core->height, fs.samplesTaken = core->samplesTaken;
+	fs.camIsStationary = core->samplesTaken == core->spp ? 0 : 1;
+	fs.taa = core->taaEnabled ? 1 : 0, fs.directClamp = core->clampDirect, fs.indirectClamp = core->clampIndirect;
+	fs.j0 = fs.j1 = fs.prevj0 = fs.prevj1 = 0;	// sub-pixel jitter comes from the blue-noise sampler of generate, not from the view
+	memcpy( fs.prevView, core->filterHistoryValid ? &core->prevView : &core->lastView, sizeof( fs.prevView ) );
+	LaunchFilterChain( b, fs, core->stream );
+	if (!core->taaEnabled)	// without TAA the history of the next frame's TAA pass is this frame's filtered image (swap( shading, prevPixels ))
+		CUDA_CHECK( cudaMemcpyAsync( core->taaBuf[cur].ptr, core->shading.ptr, (size_t)core->width * core->height * 16, cudaMemcpyDeviceToDevice, core->stream ) );
+	// rotation: this frame's phase-1 output (in filteredOUT = filteredBuf[prev]) is the next frame's temporal history (filteredIN)
+	core->filterFlip = prev;
+	core->prevView = core->lastView, core->filterHistoryValid = true;
+}
+
 static void FinishFrame( lh2b_core* core )
 {
 	if (!core->frameInFlight) return;
@@ -101,7 +143,8 @@ static void FinishFrame( lh2b_core* core )
 	const int localSamples = (int)((long long)core->samplesTaken * core->spp / total);
 	const int finEv = (int)core->events.size() - 2;
 	CUDA_CHECK( cudaEventRecord( core->events[finEv], core->stream ) );
-	LaunchFinalize( core->accumulator.ptr, core->pixels.ptr, core->width * core->height, localSamples, core->stream );
+	if (core->filterEnabled && core->features.count) RunFilter( core );
+	else LaunchFinalize( core->accumulator.ptr, core->pixels.ptr, core->width * core->height, localSamples, core->stream );
 	CUDA_CHECK( cudaEventRecord( core->events[finEv + 1], core->stream ) );
 	CUDA_CHECK( cudaStreamSynchronize( core->stream ) );
 	const double now = NowMs();
@@ -109,7 +152,8 @@ static void FinishFrame( lh2b_core* core )
 	st.frameOverhead = core->lastFrameEndMs > 0 ? fmaxf( 0.0f, (float)((core->renderStartMs - core->lastFrameEndMs) * 0.001) ) : 0;
 	core->lastFrameEndMs = now;
 	fs.generateExtendMs = st.traceTime0, fs.extendMs = st.traceTime1 + st.traceTimeX, fs.shadeMs = st.shadeTime, fs.connectMs = st.shadowTraceTime;
-	fs.finalizeMs = elapsed( finEv, finEv + 1 );
+	fs.finalizeMs = core->filterEnabled ? 0 : elapsed( finEv, finEv + 1 ), fs.filterMs = core->filterEnabled ? elapsed( finEv, finEv + 1 ) : 0;
+	st.filterTime = fs.filterMs * 0.001f;
 	fs.totalMs = elapsed( 0, finEv + 1 );
 	fs.primaryRays = st.primaryRayCount, fs.extensionRays = st.totalExtensionRays, fs.shadowRays = st.totalShadowRays;
 	fs.kernelLaunches = 3 * maxLen + 1;
@@ -142,6 +186,7 @@ static RenderParams BuildParams( lh2b_core* core, const lh2abi::ViewPyramid& vie
 	p.skyPixels = core->skyPixels.ptr, p.skyW = core->skyW, p.skyH = core->skyH;
 	memcpy( p.worldToSky, core->worldToSky, sizeof( p.worldToSky ) );
 	p.blueNoise = core->blueNoise.ptr, p.accumulator = core->accumulator.ptr, p.counters = core->counters.ptr;
+	if (core->filterEnabled && core->features.count) p.features = core->features.ptr, p.worldPos = core->worldPosBuf[core->filterFlip].ptr, p.deltaDepth = core->deltaDepth.ptr;
 	return p;
 }
 
@@ -151,7 +196,8 @@ static void RenderFrame( lh2b_core* core, const lh2abi::ViewPyramid& view )
 	const uint32_t stride = (uint32_t)core->width * core->height * core->spp;
 	core->lastView = view;
 	CUDA_CHECK( cudaEventRecord( core->events[0], s ) );
-	if (core->samplesTaken == 0) CUDA_CHECK( cudaMemsetAsync( core->accumulator.ptr, 0, (size_t)core->width * core->height * sizeof( float4 ), s ) );
+	if (core->samplesTaken == 0) CUDA_CHECK( cudaMemsetAsync( core->accumulator.ptr, 0, 2 * (size_t)core->width * core->height * sizeof( float4 ), s ) );
+	if (core->filterEnabled) EnsureFilterBuffers( core );
 	CUDA_CHECK( cudaMemsetAsync( core->counters.ptr, 0, sizeof( DevCounters ), s ) );
 	RandomUInt( core->shiftSeed );
 	RenderParams p = BuildParams( core, view );
@@ -219,12 +265,12 @@ int lh2b_set_target( lh2b_core* core, int width, int height, int spp )
 		for (int b = 0; b < 2; b++) for (int k = 0; k < 3; k++) core->pathBuf[b][k].Free(), core->pathBuf[b][k].Resize( rays );
 		for (int k = 0; k < 3; k++) core->connBuf[k].Free(), core->connBuf[k].Resize( rays );
 		core->hitBuf.Free(), core->hitBuf.Resize( rays );
-		core->accumulator.Free(), core->accumulator.Resize( core->maxPixels );
+		core->accumulator.Free(), core->accumulator.Resize( core->maxPixels * 2 );	// second half: indirect light in filter mode
 		core->pixels.Free(), core->pixels.Resize( core->maxPixels );
 	}
-	CUDA_CHECK( cudaMemsetAsync( core->accumulator.ptr, 0, pixels * sizeof( float4 ), core->stream ) );
+	CUDA_CHECK( cudaMemsetAsync( core->accumulator.ptr, 0, 2 * pixels * sizeof( float4 ), core->stream ) );
 	CUDA_CHECK( cudaMemsetAsync( core->pixels.ptr, 0, pixels * sizeof( float4 ), core->stream ) );
-	core->samplesTaken = 0;
+	core->samplesTaken = 0, core->filterHistoryValid = false;
 	API_END
 }
 
@@ -235,6 +281,11 @@ int lh2b_setting( lh2b_core* core, const char* name, float value )
 	if (!strcmp( name, "epsilon" )) core->geometryEpsilon = value;
 	else if (!strcmp( name, "clampValue" )) core->clampValue = value;
 	else if (!strcmp( name, "noiseShift" )) { /* accepted and unused, as in the reference (rendercore.cpp:756-759) */ }
+	// the filter core's settings (lib/RenderCore_Optix7Filter/rendercore.cpp:656-678); RenderSystem sends them to every core
+	else if (!strcmp( name, "filter" )) { const bool on = value > 0; if (on != core->filterEnabled) core->filterEnabled = on, core->filterHistoryValid = false, core->samplesTaken = 0; }
+	else if (!strcmp( name, "TAA" )) core->taaEnabled = value > 0;
+	else if (!strcmp( name, "clampDirect" )) core->clampDirect = value;
+	else if (!strcmp( name, "clampIndirect" )) core->clampIndirect = value;
 	// extensions of this core (the reference fixes these at compile time: core_settings.h:25, pathtracer.h:33)
 	else if (!strcmp( name, "maxPathLength" )) core->maxPathLength = value < 1 ? 1 : (value > LH2B_MAXPATHLENGTH ? LH2B_MAXPATHLENGTH : (int)value);
 	else if (!strcmp( name, "maxDiffuseBounces" )) core->enoughBounces = value <= 0 ? 0 : (value < 2 ? S_BOUNCED : S_BOUNCEDTWICE);
@@ -496,6 +547,22 @@ int lh2b_shade_paths( lh2b_core* core, int pathLength, int n, const float* O4, c
 	CUDA_CHECK( cudaMemcpyAsync( shD, conn.D, ns * sizeof( float4 ), cudaMemcpyDeviceToHost, s ) );
 	CUDA_CHECK( cudaMemcpyAsync( shE, conn.T, ns * sizeof( float4 ), cudaMemcpyDeviceToHost, s ) );
 	CUDA_CHECK( cudaMemcpyAsync( accumulator, core->accumulator.ptr, accBytes, cudaMemcpyDeviceToHost, s ) );
+	CUDA_CHECK( cudaStreamSynchronize( s ) );
+	API_END
+}
+
+int lh2b_read_filter_buffers( lh2b_core* core, uint32_t* features, float* worldPos, float* deltaDepth, float* accumulator2 )
+{
+	API_BEGIN
+	FinishFrame( core );
+	if (!core->filterEnabled || core->features.count == 0) throw CoreError( "read_filter_buffers: filter mode is off" );
+	const size_t px = (size_t)core->width * core->height;
+	const int cur = core->filterFlip ^ 1;	// FinishFrame already rotated: the frame just rendered sits in the other set
+	cudaStream_t s = core->stream;
+	if (features) CUDA_CHECK( cudaMemcpyAsync( features, core->features.ptr, px * 16, cudaMemcpyDeviceToHost, s ) );
+	if (worldPos) CUDA_CHECK( cudaMemcpyAsync( worldPos, core->worldPosBuf[cur].ptr, px * 16, cudaMemcpyDeviceToHost, s ) );
+	if (deltaDepth) CUDA_CHECK( cudaMemcpyAsync( deltaDepth, core->deltaDepth.ptr, px * 16, cudaMemcpyDeviceToHost, s ) );
+	if (accumulator2) CUDA_CHECK( cudaMemcpyAsync( accumulator2, core->accumulator.ptr, 2 * px * 16, cudaMemcpyDeviceToHost, s ) );
 	CUDA_CHECK( cudaStreamSynchronize( s ) );
 	API_END
 }

@@ -75,6 +75,11 @@ struct RenderParams
 	const uint32_t* blueNoise;
 	float4* accumulator;
 	DevCounters* counters;
+	// filter mode (Setting "filter" = 1): per-pixel features of the first diffuse vertex for the SVGF chain, and the
+	// accumulator split into direct [0, w*h) and indirect [w*h, 2*w*h) light (lib/RenderCore_Optix7Filter/kernels/pathtracer.h:44-58,95-125,195-234,286-300)
+	uint4* features;			// null: filter off
+	float4* worldPos;
+	float4* deltaDepth;
 };
 
 } // namespace lh2b

@@ -451,6 +451,38 @@ __device__ __forceinline__ float3 SampleBSDF( const Shading& s, float3 iN, const
 	return bsdf;
 }
 
+/* ---- filter features (Optix7Filter pathtracer.h:44-58; tools_shared.h:122-130,160-166) ---- */
+__device__ __forceinline__ uint32_t PackNormal2( const float3 N )
+{
+	const uint32_t x = min( max( (uint32_t)((N.x + 1) * 511), 0u ), 1023u ), y = min( max( (uint32_t)((N.y + 1) * 511), 0u ), 1023u );
+	const uint32_t z = min( max( (uint32_t)((N.z + 1) * 511), 0u ), 1023u );
+	return (x << 2u) + (y << 12u) + (z << 22u);
+}
+__device__ __forceinline__ uint32_t HDRtoRGB32( const float3 c )
+{
+	return ((uint32_t)(1023.0f * fminf( 1.0f, c.x )) << 22) + ((uint32_t)(2047.0f * fminf( 1.0f, c.y )) << 11) + (uint32_t)(2047.0f * fminf( 1.0f, c.z ));
+}
+__device__ __forceinline__ float3 RGB32toHDRs( const uint32_t c )
+{
+	return make_float3( (float)(c >> 22) * (1.0f / 1023.0f), (float)((c >> 11) & 2047) * (1.0f / 2047.0f), (float)(c & 2047) * (1.0f / 2047.0f) );
+}
+__device__ __forceinline__ void StoreFeatures( const RenderParams& p, const uint32_t pathIdx, const uint32_t albedo, const uint32_t packedNormal, const float t,
+	const uint32_t isSpecular, const uint32_t matid )
+{
+	const uint32_t history = p.features[pathIdx].w & 15;	// the history count survives (prepareFilter owns it)
+	p.features[pathIdx] = make_uint4( albedo, packedNormal, __float_as_uint( t ), (isSpecular << 4) + (matid << 6) + history );
+}
+__device__ __forceinline__ void StoreDepthDerivatives( const RenderParams& p, const uint32_t pathIdx, const float depth, const float4* __restrict__ tri )
+{
+	// depth of the triangle's plane along the rays through (x+1, y) and (x, y+1) minus the depth at (x, y)
+	const int x = pathIdx % p.w, y = pathIdx / p.w;
+	const float3 triN = make_float3( __ldg( tri + 2 ).w, __ldg( tri + 3 ).w, __ldg( tri + 4 ).w ), v0 = xyz( __ldg( tri + 8 ) ), pos = xyz( p.posLensSize );
+	const float3 dX = normalize3( p.p1 + (x + 0.5f + 1) * (1.0f / p.w) * p.right + (y + 0.5f) * (1.0f / p.h) * p.up - pos );
+	const float3 dY = normalize3( p.p1 + (x + 0.5f) * (1.0f / p.w) * p.right + (y + 0.5f + 1) * (1.0f / p.h) * p.up - pos );
+	const float num = dot( v0 - pos, triN );
+	p.deltaDepth[pathIdx] = make_float4( 0, 0, num / dot( triN, dX ) - depth, num / dot( triN, dY ) - depth );
+}
+
 __device__ __forceinline__ void ClampIntensity( float3& c, const float clampValue )
 {
 	const float v = fmaxf( c.x, fmaxf( c.y, c.z ) );
@@ -497,24 +529,39 @@ __global__ void __launch_bounds__( 128, 4 ) shadeKernel( const RenderParams p, c
 			float3 throughput = xyz( T4 );
 			const int prim = __float_as_int( hit.z ), instIdx = __float_as_int( hit.y );
 			const uint32_t pathIdx = data >> 6;
-			const uint32_t pixelIdx = pathIdx % (p.w * p.h);
+			const bool filter = p.features != nullptr;
+			// filter mode: light arriving after the first diffuse bounce goes to the second (indirect) accumulator half
+			const uint32_t pixelIdx = pathIdx % (p.w * p.h) + ((filter && (data & S_BOUNCED)) ? p.w * p.h : 0);
 			const uint32_t seedIdx = pathIdx + p.sampleBase * (p.w * p.h);	// path index within the whole (multi-GPU) frame
 			const uint32_t sampleIdx = seedIdx / (p.w * p.h) + p.pass;
+			const bool firstHitToBeStored = filter && (data & S_BOUNCED) == 0 && sampleIdx == 0;
+			if (pathLength == 1 && firstHitToBeStored)
+			{
+				StoreFeatures( p, pathIdx, 0, 0, 1e34f, 0, 0 );
+				p.worldPos[pathIdx] = make_float4( 0, 0, 0, __uint_as_float( 0u ) ), p.deltaDepth[pathIdx] = make_float4( 0, 0, 0, 0 );
+			}
 			if (prim == -1)
 			{
 				// sky (pathtracer.h:85-94)
 				const float* m = p.worldToSky;
 				const float3 tD = make_float3( -(m[0] * D.x + m[1] * D.y + m[2] * D.z), -(m[4] * D.x + m[5] * D.y + m[6] * D.z), -(m[8] * D.x + m[9] * D.y + m[10] * D.z) );
-				const float3 sky = SampleSky( p, tD, (data & S_BOUNCED) != 0 );
+				const float3 sky = SampleSky( p, tD, !filter && (data & S_BOUNCED) != 0 );	// the filter core always reads the full-size sky
 				float3 contribution = throughput * sky * (1.0f / bsdfPdf);
 				ClampIntensity( contribution, p.clampValue );
 				FixNan( contribution );
 				Accumulate( p.accumulator + pixelIdx, contribution );
+				if (firstHitToBeStored)
+				{
+					const uint32_t isSpecular = (data & S_VIASPECULAR) ? 1 : 0, packedNormal = PackNormal2( D * -1.0f ) + isSpecular;
+					StoreFeatures( p, pathIdx, HDRtoRGB32( contribution ), packedNormal, hit.w, isSpecular, 0 );
+					const float3 far = xyz( O4 ) + 50000 * D;
+					p.worldPos[pathIdx] = make_float4( far.x, far.y, far.z, __uint_as_float( packedNormal ) ), p.deltaDepth[pathIdx] = make_float4( 0, 0, 0, 0 );
+				}
 				break;
 			}
 			const float hitU = (__float_as_uint( hit.x ) & 65535) * (1.0f / 65535.0f), hitV = (__float_as_uint( hit.x ) >> 16) * (1.0f / 65535.0f);
 			const float hitT = hit.w;
-			if (pixelIdx == (uint32_t)p.probePixelIdx && pathLength == 1)
+			if (pixelIdx == (uint32_t)p.probePixelIdx && pathLength == 1 && (!filter || sampleIdx == 0))
 				p.counters->probedInstid = instIdx, p.counters->probedTriid = prim, p.counters->probedDist = hitT;
 			const InstDesc& inst = ((const InstDesc*)p.instDesc)[instIdx];
 			const float4* tri = inst.triangles + (size_t)prim * 13;
@@ -522,11 +569,22 @@ __global__ void __launch_bounds__( 128, 4 ) shadeKernel( const RenderParams p, c
 			float3 N, iN, fN, T;
 			const float3 I = xyz( O4 ) + hitT * D;
 			GetShadingData( p, D, hitU, hitV, p.spreadAngle * hitT, tri, inst, sh, N, iN, fN, T );
+			if (filter && !(sh.flags & 1))	// FILTERINGCORE: albedo never reaches zero so that it can be divided out (material_shared.h:200-205)
+				sh.color = make_float3( fmaxf( 0.05f, sh.color.x ), fmaxf( 0.05f, sh.color.y ), fmaxf( 0.05f, sh.color.z ) );
 			uint32_t seed = WangHash( seedIdx * 17 + R0 );
 			if (sh.flags & 1)
 			{
 				// alpha-rejected texel: continue the same ray behind the surface (pathtracer.h:113-124)
-				if (pathLength < p.maxPathLength)
+				if (pathLength == p.maxPathLength)
+				{
+					if (firstHitToBeStored)
+					{
+						const uint32_t isSpecular = (data & S_VIASPECULAR) ? 1 : 0, packedNormal = PackNormal2( N ) + isSpecular;
+						StoreFeatures( p, pathIdx, 0, packedNormal, hitT, isSpecular, 0 );
+						p.worldPos[pathIdx] = make_float4( I.x, I.y, I.z, __uint_as_float( packedNormal ) );
+					}
+				}
+				else
 				{
 					const float3 nO = I + D * p.geometryEpsilon;
 					if (!isfinite( T4.x + T4.y + T4.z )) T4 = make_float4( 0, 0, 0, T4.w );
@@ -555,12 +613,34 @@ __global__ void __launch_bounds__( 128, 4 ) shadeKernel( const RenderParams p, c
 					FixNan( contribution );
 					Accumulate( p.accumulator + pixelIdx, contribution );
 				}
+				if (firstHitToBeStored)
+				{
+					const uint32_t isSpecular = (data & S_VIASPECULAR) ? 1 : 0, packedNormal = PackNormal2( N ) + isSpecular;
+					StoreFeatures( p, pathIdx, HDRtoRGB32( sh.color ), packedNormal, hitT, isSpecular, 0 );
+					p.worldPos[pathIdx] = make_float4( I.x, I.y, I.z, __uint_as_float( packedNormal ) );
+					StoreDepthDerivatives( p, pathIdx, hitT, tri );
+				}
 				break;
 			}
-			if (data & S_BOUNCED) sh.parameters.x |= 255u << 24;	// path regularisation
+			if (!filter && (data & S_BOUNCED)) sh.parameters.x |= 255u << 24;	// path regularisation (not in the filter core)
 			const float roughness = SH_ROUGHNESS( sh );
-			if (roughness <= 0.001f || SH_TRANSMISSION( sh ) > 0.5f) data |= S_SPECULAR; else data &= ~S_SPECULAR;
+			if (roughness <= 0.001f || SH_TRANSMISSION( sh ) > (filter ? 0.999f : 0.5f)) data |= S_SPECULAR; else data &= ~S_SPECULAR;
 			const float faceDir = (dot( D, N ) > 0) ? -1 : 1;
+			if (firstHitToBeStored)
+			{
+				if (data & S_SPECULAR) p.features[pathIdx].x = HDRtoRGB32( sh.color );	// modulated by the first diffuse hit later
+				else
+				{
+					float3 albedo = sh.color;
+					if (data & S_VIASPECULAR) albedo *= RGB32toHDRs( p.features[pathIdx].x );
+					const uint32_t isSpecular = (data & S_VIASPECULAR) ? 1 : 0;
+					// the reference writes 'flip ? -fN : fN' with flip = +-1.0f, i.e. always -fN (Optix7Filter pathtracer.h:229): kept
+					const uint32_t packedNormal = PackNormal2( fN * -1.0f ) + isSpecular;
+					StoreFeatures( p, pathIdx, HDRtoRGB32( albedo ), packedNormal, hitT, isSpecular, 0 );
+					p.worldPos[pathIdx] = make_float4( I.x, I.y, I.z, __uint_as_float( packedNormal ) );
+					StoreDepthDerivatives( p, pathIdx, hitT, tri );
+				}
+			}
 			if (faceDir == 1) sh.transmittance = f3( 0 );
 			throughput *= 1.0f / bsdfPdf;
 			float4 r4;
@@ -596,7 +676,18 @@ __global__ void __launch_bounds__( 128, 4 ) shadeKernel( const RenderParams p, c
 					}
 				}
 			}
-			if ((data & p.enoughBounces) || pathLength == p.maxPathLength) break;
+			if (data & (filter ? (uint32_t)S_BOUNCED : p.enoughBounces)) break;	// filter core: one diffuse bounce, always
+			if (pathLength == p.maxPathLength)
+			{
+				if (firstHitToBeStored)
+				{
+					// nothing diffuse was found within the path length: leave something sensible for the filter
+					const uint32_t isSpecular = (data & S_VIASPECULAR) ? 1 : 0, packedNormal = PackNormal2( N ) + isSpecular;
+					StoreFeatures( p, pathIdx, 0, packedNormal, hitT, isSpecular, 0 );
+					p.worldPos[pathIdx] = make_float4( I.x, I.y, I.z, __uint_as_float( packedNormal ) );
+				}
+				break;
+			}
 			float3 R;
 			float newPdf;
 			bool specular = false;
@@ -605,7 +696,7 @@ __global__ void __launch_bounds__( 128, 4 ) shadeKernel( const RenderParams p, c
 			const float3 bsdf = SampleBSDF( sh, fN, N, D * -1.0f, hitT, r4.z, r4.w, R, newPdf, specular );
 			if (newPdf < 0.0001f || isnan( newPdf )) break;
 			if (specular) data |= S_SPECULAR;
-			const float rr = ((data & S_SPECULAR) || ((data & S_BOUNCED) == 0)) ? 1 : fminf( 1.0f, fmaxf( fmaxf( bsdf.x, bsdf.y ), bsdf.z ) );
+			const float rr = (filter || (data & S_SPECULAR) || ((data & S_BOUNCED) == 0)) ? 1 : fminf( 1.0f, fmaxf( fmaxf( bsdf.x, bsdf.y ), bsdf.z ) );
 			if (rr < RandomFloat( seed )) break;
 			throughput *= 1 / rr;
 			const uint32_t packedNormal = PackNormal( fN * faceDir );

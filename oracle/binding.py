@@ -111,7 +111,7 @@ class FrameOracle:
     (rendercore.h:122-123) so consecutive Render calls can be mirrored frame by frame."""
 
     def __init__(self, scene, width, height, spp=1, epsilon=1e-4, clamp=10.0, max_path_length=3, max_diffuse_bounces=1,
-                 threads=None, sample_base=0, total_spp=0):
+                 threads=None, sample_base=0, total_spp=0, filter=False):
         self.sd, self.w, self.h, self.spp = scene, width, height, spp
         self.eps, self.clamp, self.maxlen = epsilon, clamp, max_path_length
         self.enough = 0 if max_diffuse_bounces <= 0 else (2 if max_diffuse_bounces < 2 else 8)
@@ -120,7 +120,11 @@ class FrameOracle:
         self.samples_taken = 0
         self.shift_seed, self.cam_seed = 0x11331445, 0x12345678
         self.first_converging = True
-        self.accum = np.zeros((height, width, 4), np.float32)
+        self.filter = filter
+        self.accum = np.zeros((2, height, width, 4) if filter else (height, width, 4), np.float32)
+        self.features = np.zeros((height, width, 4), np.uint32) if filter else None
+        self.world_pos = np.zeros((height, width, 4), np.float32) if filter else None
+        self.delta_depth = np.zeros((height, width, 4), np.float32) if filter else None
         self.ray_counts = (0, 0)
 
     def render(self, view, converge=1, records=False):
@@ -135,8 +139,9 @@ class FrameOracle:
         counts = (ctypes.c_uint64 * 2)()
         seeds = (ctypes.c_uint * 2)()
         rec = np.zeros(self.w * self.h * self.spp, dtype=PathRecord) if records else None
+        fp = (lambda a: ctypes.c_void_p(a.ctypes.data)) if self.filter else (lambda a: None)
         lib().orc_render_frame(ctypes.byref(f), ctypes.c_void_p(self.accum.ctypes.data), counts, seeds,
-                               ctypes.c_void_p(rec.ctypes.data) if records else None)
+                               ctypes.c_void_p(rec.ctypes.data) if records else None, fp(self.features), fp(self.world_pos), fp(self.delta_depth))
         self.shift_seed, self.cam_seed = seeds[0], seeds[1]
         self.ray_counts = (int(counts[0]), int(counts[1]))
         total = self.total_spp if self.total_spp > 0 else self.spp

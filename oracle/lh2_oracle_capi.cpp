@@ -179,7 +179,9 @@ static void SetupScene( const OrcFrameIn& in, FrameCtx& ctx )
 	sc.blueNoise = bn.data();
 }
 
-ORC_API void orc_render_frame( const OrcFrameIn* inp, float* accum, uint64_t* rayCounts, uint32_t* seedsOut, orc::PathRecord* records )
+/* filter (optional): features uint4[w*h], worldPos / deltaDepth float4[w*h] (in/out: history bits persist); when given, accum is float4[2*w*h]. */
+ORC_API void orc_render_frame( const OrcFrameIn* inp, float* accum, uint64_t* rayCounts, uint32_t* seedsOut, orc::PathRecord* records,
+	uint32_t* features, float* worldPos, float* deltaDepth )
 {
 	const OrcFrameIn& in = *inp;
 	FrameCtx ctx;
@@ -197,7 +199,9 @@ ORC_API void orc_render_frame( const OrcFrameIn* inp, float* accum, uint64_t* ra
 	memcpy( st.view, in.view, sizeof( st.view ) );
 	if (seedsOut) seedsOut[0] = shiftSeed, seedsOut[1] = camSeed;
 	const int pixels = in.w * in.h;
-	std::vector<double> acc( (size_t)pixels * 4, 0.0 );
+	const orc::FilterArrays fa = { features, worldPos, deltaDepth };
+	const bool filter = features != nullptr;
+	std::vector<double> acc( (size_t)pixels * 4 * (filter ? 2 : 1), 0.0 );
 	const int threads = in.threads > 0 ? in.threads : 1;
 	std::vector<uint64_t> counts( (size_t)threads * 2, 0 );
 	std::vector<std::thread> pool;
@@ -209,12 +213,12 @@ ORC_API void orc_render_frame( const OrcFrameIn* inp, float* accum, uint64_t* ra
 			const uint32_t pathIdx = (uint32_t)(x + y * in.w) + (uint32_t)s * pixels;
 			orc::PathRecord* rec = records ? records + pathIdx : nullptr;
 			if (rec) memset( rec, 0, sizeof( *rec ) );
-			orc::TracePath( sc, st, pathIdx, acc.data(), rc, rec );
+			orc::TracePath( sc, st, pathIdx, acc.data(), rc, rec, filter ? &fa : nullptr );
 			counts[t * 2] += rc[0], counts[t * 2 + 1] += rc[1], rc[0] = rc[1] = 0;
 		}
 	} );
 	for (auto& th : pool) th.join();
-	for (size_t i = 0; i < (size_t)pixels * 4; i++) accum[i] += (float)acc[i];
+	for (size_t i = 0; i < acc.size(); i++) accum[i] += (float)acc[i];
 	if (rayCounts) { rayCounts[0] = rayCounts[1] = 0; for (int t = 0; t < threads; t++) rayCounts[0] += counts[t * 2], rayCounts[1] += counts[t * 2 + 1]; }
 	sc.geo.Release();
 }

@@ -547,6 +547,29 @@ struct PathRecord		// optional per-path trace for path-by-path comparison with t
 	float firstShadow[8];	// first NEE connection: origin.xyz, valid flag, L.xyz, tmax
 };
 
+/* Filter mode (Setting "filter"): per-pixel features of the first diffuse vertex and the direct / indirect split, following
+   lib/RenderCore_Optix7Filter/kernels/pathtracer.h:44-58,95-125,195-234,286-300 (feature rules) on top of the Optix7 core's
+   estimator and random numbers (that is what the CUDA core implements). */
+struct FilterArrays { uint32_t* features; float* worldPos; float* deltaDepth; };	// uint4 / float4 / float4 per pixel
+static inline uint32_t PackNormal2( V3 N )
+{
+	const uint32_t x = F2U( (N.x + 1) * 511 ) > 1023u ? 1023u : F2U( (N.x + 1) * 511 ), y = F2U( (N.y + 1) * 511 ) > 1023u ? 1023u : F2U( (N.y + 1) * 511 );
+	const uint32_t z = F2U( (N.z + 1) * 511 ) > 1023u ? 1023u : F2U( (N.z + 1) * 511 );
+	return (x << 2) + (y << 12) + (z << 22);
+}
+static inline uint32_t HDRtoRGB32( V3 c ) { return (F2U( 1023.0f * fminf( 1.0f, c.x ) ) << 22) + (F2U( 2047.0f * fminf( 1.0f, c.y ) ) << 11) + F2U( 2047.0f * fminf( 1.0f, c.z ) ); }
+static inline V3 RGB32toHDR( uint32_t c ) { return v3( (float)(c >> 22) * (1.0f / 1023.0f), (float)((c >> 11) & 2047) * (1.0f / 2047.0f), (float)(c & 2047) * (1.0f / 2047.0f) ); }
+static inline void StoreFeatures( const FilterArrays& fa, uint32_t pathIdx, uint32_t albedo, uint32_t packedNormal, float t, uint32_t isSpecular, uint32_t matid )
+{
+	uint32_t* f = fa.features + (size_t)pathIdx * 4;
+	f[0] = albedo, f[1] = packedNormal, f[2] = FBits( t ), f[3] = (isSpecular << 4) + (matid << 6) + (f[3] & 15);
+}
+static inline void StoreWorldPos( const FilterArrays& fa, uint32_t pathIdx, V3 P, uint32_t packedNormal )
+{
+	float* w = fa.worldPos + (size_t)pathIdx * 4;
+	w[0] = P.x, w[1] = P.y, w[2] = P.z, w[3] = BitsF( packedNormal );
+}
+
 /* One path vertex, exactly the content of the device buffers. */
 struct PathState { V3 O; uint32_t data; V3 D; uint32_t packedN; V3 T; float bsdfPdf; };
 struct ShadeOut
@@ -558,33 +581,59 @@ struct ShadeOut
 };
 
 /* shadeKernel for one path (pathtracer.h:54-238). hit = (u16|v16<<16, instance, primitive, t bits). */
-static inline void ShadeStep( const RenderScene& sc, const Settings& st, int pathLength, const PathState& in, const uint32_t* hit, int probePixelIdx, ShadeOut& out )
+static inline void ShadeStep( const RenderScene& sc, const Settings& st, int pathLength, const PathState& in, const uint32_t* hit, int probePixelIdx, ShadeOut& out,
+	const FilterArrays* fa = nullptr )
 {
 	memset( &out, 0, sizeof( out ) );
 	const uint32_t pixels = (uint32_t)st.w * st.h;
 	uint32_t data = in.data;
 	const uint32_t pathIdx = data >> 6;
-	const uint32_t pixelIdx = pathIdx % pixels, seedIdx = pathIdx + st.sampleBase * pixels;
+	const bool filter = fa != nullptr;
+	const uint32_t pixelIdx = pathIdx % pixels + ((filter && (data & S_BOUNCED)) ? pixels : 0), seedIdx = pathIdx + st.sampleBase * pixels;
 	const uint32_t sampleIdx = seedIdx / pixels + st.pass;
 	const bool useNEE = LightTotal( sc ) > 0;
 	const V3 O = in.O, D = in.D;
 	V3 throughput = pathLength == 1 ? v3( 1 ) : in.T;
 	const float bsdfPdf = pathLength == 1 ? 1.0f : in.bsdfPdf;
 	out.pixelIdx = pixelIdx;
+	const bool firstHitToBeStored = filter && (data & S_BOUNCED) == 0 && sampleIdx == 0;
+	if (pathLength == 1 && firstHitToBeStored)
+	{
+		StoreFeatures( *fa, pathIdx, 0, 0, 1e34f, 0, 0 ), StoreWorldPos( *fa, pathIdx, v3( 0 ), 0 );
+		memset( fa->deltaDepth + (size_t)pathIdx * 4, 0, 16 );
+	}
+	auto storeDepthDerivatives = [&]( float depth, const float* tri ) {
+		const float* vw = st.view;
+		const V3 pos = v3( vw[0], vw[1], vw[2] ), p1 = v3( vw[3], vw[4], vw[5] ), right = v3( vw[6], vw[7], vw[8] ) - p1, up = v3( vw[9], vw[10], vw[11] ) - p1;
+		const int x = pathIdx % st.w, y = pathIdx / st.w;
+		const V3 triN = v3( tri[11], tri[15], tri[19] ), v0 = v3( tri[32], tri[33], tri[34] );
+		const V3 dX = normalize( p1 + (x + 0.5f + 1) * (1.0f / st.w) * right + (y + 0.5f) * (1.0f / st.h) * up - pos );
+		const V3 dY = normalize( p1 + (x + 0.5f) * (1.0f / st.w) * right + (y + 0.5f + 1) * (1.0f / st.h) * up - pos );
+		const float num = dot( v0 - pos, triN );
+		float* d = fa->deltaDepth + (size_t)pathIdx * 4;
+		d[0] = d[1] = 0, d[2] = num / dot( triN, dX ) - depth, d[3] = num / dot( triN, dY ) - depth;
+	};
 	const int prim = (int)hit[2], instIdx = (int)hit[1];
 	if (prim == -1)
 	{
 		const float* m = sc.worldToSky;
 		const V3 tD = v3( -(m[0] * D.x + m[1] * D.y + m[2] * D.z), -(m[4] * D.x + m[5] * D.y + m[6] * D.z), -(m[8] * D.x + m[9] * D.y + m[10] * D.z) );
-		V3 contribution = throughput * SampleSky( sc, tD, (data & S_BOUNCED) != 0 ) * (1.0f / bsdfPdf);
+		V3 contribution = throughput * SampleSky( sc, tD, !filter && (data & S_BOUNCED) != 0 ) * (1.0f / bsdfPdf);
 		ClampIntensity( contribution, st.clampValue );
 		FixNan( contribution );
 		out.deposit = true, out.contribution = contribution;
+		if (firstHitToBeStored)
+		{
+			const uint32_t isSpecular = (data & S_VIASPECULAR) ? 1 : 0, packedNormal = PackNormal2( D * -1.0f ) + isSpecular;
+			StoreFeatures( *fa, pathIdx, HDRtoRGB32( contribution ), packedNormal, BitsF( hit[3] ), isSpecular, 0 );
+			StoreWorldPos( *fa, pathIdx, O + 50000 * D, packedNormal );
+			memset( fa->deltaDepth + (size_t)pathIdx * 4, 0, 16 );
+		}
 		return;
 	}
 	const float hu = (float)(hit[0] & 65535) * (1.0f / 65535.0f), hv = (float)(hit[0] >> 16) * (1.0f / 65535.0f);
 	const float ht = BitsF( hit[3] );
-	if ((int)pixelIdx == probePixelIdx && pathLength == 1) out.probe = true, out.probeInst = instIdx, out.probePrim = prim, out.probeDist = ht;
+	if ((int)pixelIdx == probePixelIdx && pathLength == 1 && (!filter || sampleIdx == 0)) out.probe = true, out.probeInst = instIdx, out.probePrim = prim, out.probeDist = ht;
 	const float* tri = sc.coreTris[sc.geo.instances[instIdx].mesh] + (size_t)prim * 52;
 	const float* invT = sc.geo.inverses + instIdx * 12;
 	Shading sh;
@@ -592,10 +641,19 @@ static inline void ShadeStep( const RenderScene& sc, const Settings& st, int pat
 	const V3 I = O + ht * D;
 	const float spreadAngle = st.view[13];
 	GetShadingData( sc, D, hu, hv, spreadAngle * ht, tri, invT, sh, N, iN, fN, T );
+	if (filter && !(sh.flags & 1)) sh.color = v3( fmaxf( 0.05f, sh.color.x ), fmaxf( 0.05f, sh.color.y ), fmaxf( 0.05f, sh.color.z ) );	// FILTERINGCORE
 	uint32_t seed = WangHash( seedIdx * 17 + st.R0[pathLength] );
 	if (sh.flags & 1)
 	{
-		if (pathLength < st.maxPathLength)
+		if (pathLength == st.maxPathLength)
+		{
+			if (firstHitToBeStored)
+			{
+				const uint32_t isSpecular = (data & S_VIASPECULAR) ? 1 : 0, packedNormal = PackNormal2( N ) + isSpecular;
+				StoreFeatures( *fa, pathIdx, 0, packedNormal, ht, isSpecular, 0 ), StoreWorldPos( *fa, pathIdx, I, packedNormal );
+			}
+		}
+		else
 		{
 			out.extend = true, out.next = in;
 			out.next.O = I + D * st.geometryEpsilon;
@@ -624,12 +682,30 @@ static inline void ShadeStep( const RenderScene& sc, const Settings& st, int pat
 			FixNan( contribution );
 			out.deposit = true, out.contribution = contribution;
 		}
+		if (firstHitToBeStored)
+		{
+			const uint32_t isSpecular = (data & S_VIASPECULAR) ? 1 : 0, packedNormal = PackNormal2( N ) + isSpecular;
+			StoreFeatures( *fa, pathIdx, HDRtoRGB32( sh.color ), packedNormal, ht, isSpecular, 0 ), StoreWorldPos( *fa, pathIdx, I, packedNormal );
+			storeDepthDerivatives( ht, tri );
+		}
 		return;
 	}
-	if (data & S_BOUNCED) sh.params[0] |= 255u << 24;
+	if (!filter && (data & S_BOUNCED)) sh.params[0] |= 255u << 24;
 	const float roughness = Roughness( sh );
-	if (roughness <= 0.001f || Transmission( sh ) > 0.5f) data |= S_SPECULAR; else data &= ~(uint32_t)S_SPECULAR;
+	if (roughness <= 0.001f || Transmission( sh ) > (filter ? 0.999f : 0.5f)) data |= S_SPECULAR; else data &= ~(uint32_t)S_SPECULAR;
 	const float faceDir = (dot( D, N ) > 0) ? -1.0f : 1.0f;
+	if (firstHitToBeStored)
+	{
+		if (data & S_SPECULAR) fa->features[(size_t)pathIdx * 4] = HDRtoRGB32( sh.color );
+		else
+		{
+			V3 albedo = sh.color;
+			if (data & S_VIASPECULAR) albedo = albedo * RGB32toHDR( fa->features[(size_t)pathIdx * 4] );
+			const uint32_t isSpecular = (data & S_VIASPECULAR) ? 1 : 0, packedNormal = PackNormal2( fN * -1.0f ) + isSpecular;	// sic: always -fN (Optix7Filter pathtracer.h:229)
+			StoreFeatures( *fa, pathIdx, HDRtoRGB32( albedo ), packedNormal, ht, isSpecular, 0 ), StoreWorldPos( *fa, pathIdx, I, packedNormal );
+			storeDepthDerivatives( ht, tri );
+		}
+	}
 	if (faceDir == 1) sh.transmittance = v3( 0 );
 	throughput = throughput * (1.0f / bsdfPdf);
 	float r4[4];
@@ -658,7 +734,16 @@ static inline void ShadeStep( const RenderScene& sc, const Settings& st, int pat
 			}
 		}
 	}
-	if ((data & st.enoughBounces) || pathLength == st.maxPathLength) return;
+	if (data & (filter ? (uint32_t)S_BOUNCED : st.enoughBounces)) return;
+	if (pathLength == st.maxPathLength)
+	{
+		if (firstHitToBeStored)
+		{
+			const uint32_t isSpecular = (data & S_VIASPECULAR) ? 1 : 0, packedNormal = PackNormal2( N ) + isSpecular;
+			StoreFeatures( *fa, pathIdx, 0, packedNormal, ht, isSpecular, 0 ), StoreWorldPos( *fa, pathIdx, I, packedNormal );
+		}
+		return;
+	}
 	V3 R;
 	float newPdf;
 	bool specular = false;
@@ -666,7 +751,7 @@ static inline void ShadeStep( const RenderScene& sc, const Settings& st, int pat
 	const V3 bsdf = SampleBSDF( sh, fN, N, D * -1.0f, ht, r4[2], r4[3], R, newPdf, specular );
 	if (newPdf < 0.0001f || newPdf != newPdf) return;
 	if (specular) data |= S_SPECULAR;
-	const float p = ((data & S_SPECULAR) || ((data & S_BOUNCED) == 0)) ? 1 : fminf( 1.0f, fmaxf( fmaxf( bsdf.x, bsdf.y ), bsdf.z ) );
+	const float p = (filter || (data & S_SPECULAR) || ((data & S_BOUNCED) == 0)) ? 1 : fminf( 1.0f, fmaxf( fmaxf( bsdf.x, bsdf.y ), bsdf.z ) );
 	if (p < RandomFloat( seed )) return;
 	throughput = throughput * (1 / p);
 	const uint32_t packedNormal = PackNormal( fN * faceDir );
@@ -680,7 +765,7 @@ static inline void ShadeStep( const RenderScene& sc, const Settings& st, int pat
 
 /* Trace one complete path: generate, then (closest hit, shade, connect) per path length. Deposits into accum
    (4 doubles per pixel). rayCounts[0] += extension rays, [1] += shadow rays. */
-static inline void TracePath( const RenderScene& sc, const Settings& st, uint32_t pathIdx, double* accum, uint32_t* rayCounts, PathRecord* rec )
+static inline void TracePath( const RenderScene& sc, const Settings& st, uint32_t pathIdx, double* accum, uint32_t* rayCounts, PathRecord* rec, const FilterArrays* fa = nullptr )
 {
 	PathState ps;
 	memset( &ps, 0, sizeof( ps ) );
@@ -696,7 +781,7 @@ static inline void TracePath( const RenderScene& sc, const Settings& st, uint32_
 		PackHit( hit, h, rec4 );
 		if (rec && pathLength == 1) memcpy( rec->hit, rec4, 16 );
 		ShadeOut so;
-		ShadeStep( sc, st, pathLength, ps, rec4, -1, so );
+		ShadeStep( sc, st, pathLength, ps, rec4, -1, so, fa );
 		double* px = accum + (size_t)so.pixelIdx * 4;
 		if (so.deposit) px[0] += so.contribution.x, px[1] += so.contribution.y, px[2] += so.contribution.z;
 		if (so.shadow)

@@ -1,0 +1,101 @@
+"""Filter mode end to end (Setting("filter", 1)): the shade stage writes the per-pixel features of the first diffuse
+vertex and splits direct / indirect light; FinalizeRender runs the SVGF / TAA chain.
+ (1) features, world positions, depth derivatives and both accumulator halves against the CPU oracle;
+ (2) the frame the core presents against the REFERENCE's filter kernels fed with the core's own buffers (pipeline wiring:
+     buffer roles, history rotation, settings);
+ (3) over a moving-camera sequence the output stays finite and is smoother than the unfiltered estimate."""
+import numpy as np
+import pytest
+
+from lighthouse2_b200 import RenderCore, scenes
+from oracle import binding as orc
+from util import rel_rmse
+
+pytestmark = pytest.mark.gpu
+W, H = 160, 96
+
+
+def _scene():
+    sd = scenes.config2_scene(48, 32, n_materials=6, light_quads=2, floaters=300)
+    sd.materials[1]["roughness"]["value"] = 0.0      # a mirror: exercises the via-specular feature path
+    return sd
+
+
+def _core(sd, taa):
+    core = RenderCore()
+    core.SetTarget(W, H, 1)
+    core.Setting("epsilon", 1e-3)
+    core.Setting("filter", 1)
+    core.Setting("TAA", taa)
+    core.Setting("clampDirect", 15.0)
+    core.Setting("clampIndirect", 15.0)
+    sd.upload(core)
+    return core
+
+
+def test_features_and_split_accumulator_match_oracle():
+    sd = _scene()
+    view = scenes.view_pyramid((0, 30, -80), (0, 0, 0), 40, W, H)
+    core = _core(sd, 0)
+    core.Render(view, 1)
+    feat, wp, dd, acc = core.ReadFilterBuffers()
+    o = orc.FrameOracle(sd, W, H, 1, 1e-3, 10.0, 3, 1, filter=True)
+    o.render(view, 1)
+    # packed words: albedo (10/11/11 bit), normal (3 x 10 bit + specular bit), depth bits, specular / material / history bits
+    same = (feat == o.features).all(axis=-1)
+    assert same.mean() > 0.99, f"{(~same).sum()} feature records differ"
+    close_depth = np.abs(feat[..., 2].view(np.float32) / np.maximum(o.features[..., 2].view(np.float32), 1e-6) - 1) < 1e-4
+    assert close_depth.mean() > 0.995
+    assert (np.abs(wp[..., :3] - o.world_pos[..., :3]) < 1e-2).all(axis=-1).mean() > 0.995
+    assert (wp[..., 3].view(np.uint32) == o.world_pos[..., 3].view(np.uint32)).mean() > 0.99
+    assert (np.abs(dd - o.delta_depth) < 1e-3 * (1 + np.abs(o.delta_depth))).all(axis=-1).mean() > 0.99
+    assert rel_rmse(acc[0], o.accum[0]) < 0.02 and rel_rmse(acc[1], o.accum[1]) < 0.05
+    assert acc[1, ..., :3].sum() > 0 and acc[0, ..., :3].sum() > 0
+    core.Shutdown()
+
+
+@pytest.mark.skipif(not orc.have_ref_filter_gpu(), reason="oracle/_ref/libref_filter_gpu.so is built only where /root/reference exists")
+@pytest.mark.parametrize("taa", [0, 1])
+def test_presented_frame_matches_reference_chain_on_same_buffers(taa):
+    sd = _scene()
+    views = [scenes.view_pyramid((0.0, 30, -80), (0, 0, 0), 40, W, H), scenes.view_pyramid((0.5, 30.1, -79.6), (0, 0, 0), 40, W, H)]
+    core = _core(sd, taa)
+    hist = dict(prevWorldPos=np.zeros((H, W, 4), np.float32), prevMoments=np.zeros((H, W, 4), np.float32),
+                filteredIN=np.zeros((H, W, 4), np.float32), prevPixels=np.zeros((H, W, 4), np.float32))
+    feat_hist = np.zeros((H, W, 4), np.uint32)
+    prev_view = views[0]
+    for k, view in enumerate(views):
+        core.Render(view, 1)                       # every frame restarts the accumulator (camera moved)
+        got = core.ReadPixels()
+        feat, wp, dd, acc = core.ReadFilterBuffers()
+        # history counter bits: the core's features buffer already holds the post-prepare counters; the reference starts
+        # from last frame's counters and the fresh feature words
+        feat_in = feat.copy()
+        feat_in[..., 3] = (feat[..., 3] & ~np.uint32(15)) | (feat_hist[..., 3] & 15)
+        st = dict(w=W, h=H, samplesTaken=1, camIsStationary=0, taa=taa, directClamp=15.0, indirectClamp=15.0, j0=0.0, j1=0.0, prevj0=0.0, prevj1=0.0,
+                  prevView=prev_view if k else view)
+        ref = orc.ref_filter_gpu(dict(accumulator=acc, features=feat_in, worldPos=wp, deltaDepth=dd, **hist), st)
+        inner = (slice(1, H - 1), slice(1, W - 1))
+        bad = (np.abs(got[inner][..., :3] - ref["target"][inner][..., :3]) > 3e-2).any(axis=-1).mean()
+        assert bad < 0.05, f"frame {k}: {bad:.3f} of the pixels differ from the reference chain"
+        hist = dict(prevWorldPos=wp, prevMoments=ref["moments"], filteredIN=ref["phase1"], prevPixels=ref["taaPixels"] if taa else ref["phase3"])
+        feat_hist, prev_view = ref["featuresOut"], view
+    core.Shutdown()
+
+
+def test_sequence_is_finite_and_smoother_than_unfiltered():
+    sd = _scene()
+    core = _core(sd, 1)
+    raw = RenderCore()
+    raw.SetTarget(W, H, 1); raw.Setting("epsilon", 1e-3); sd.upload(raw)
+    rough = lambda img: float(np.abs(np.diff(img[..., :3], axis=1)).mean())
+    for k in range(5):
+        view = scenes.view_pyramid((0.3 * k, 30, -80 + 0.2 * k), (0, 0, 0), 40, W, H)
+        core.Render(view, 1); raw.Render(view, 1)
+        f, u = core.ReadPixels(), raw.ReadPixels()
+        assert np.isfinite(f).all()
+        if k >= 2:
+            assert rough(np.sqrt(np.clip(f, 0, None))) < 0.8 * rough(np.sqrt(np.clip(u, 0, 10)))   # compare in the same (gamma) domain
+    st = core.GetCoreStats()
+    assert st["filterTime"] > 0
+    core.Shutdown(); raw.Shutdown()
