@@ -33,10 +33,19 @@ namespace lh2b
 #define WIDE_TRI_THRESHOLD 12	// lanes with pending triangles that trigger a triangle phase
 #define WIDE_REFILL_THRESHOLD 8	// idle lanes that trigger fetching new rays
 
-__device__ __forceinline__ float ByteFloat( const uint32_t word, const uint32_t selector )
+/* 0x47800000 = 65536.0f; dropping a byte into mantissa bits 8..15 gives exactly 65536 + 2 * byte. 'base' holds the
+   constant in a register (see OpaqueBase) so that the selector can be the instruction's immediate: one PRMT per plane. */
+template <int J> __device__ __forceinline__ float ByteFloat( const uint32_t word, const uint32_t base )
 {
-	// 0x47800000 = 65536.0f; dropping a byte into mantissa bits 8..15 gives exactly 65536 + 2 * byte
-	return __uint_as_float( __byte_perm( word, 0x47800000u, selector ) );
+	uint32_t r;
+	asm( "prmt.b32 %0, %1, %2, %3;" : "=r"( r ) : "r"( word ), "r"( base ), "n"( 0x7604 | (J << 4) ) );
+	return __uint_as_float( r );
+}
+__device__ __forceinline__ uint32_t OpaqueBase()
+{
+	uint32_t k;
+	asm volatile( "mov.b32 %0, 0x47800000;" : "=r"( k ) );	// volatile: the optimiser must not fold it back into an immediate
+	return k;
 }
 
 struct WideRay
@@ -67,6 +76,7 @@ __device__ __forceinline__ void TraverseWide( const DevScene& scene, RaySource& 
 	const uint4* __restrict__ nodes = scene.nodes;
 	const float4* __restrict__ tris = scene.tris;
 	const uint32_t NO_INST = 0xffffffffu;
+	const uint32_t fbase = OpaqueBase();
 	// lane state
 	bool active = false;
 	uint32_t workIdx = 0;
@@ -86,12 +96,7 @@ __device__ __forceinline__ void TraverseWide( const DevScene& scene, RaySource& 
 		// ---- lanes without a node group take the next one from their stack; finished rays retire -------------
 		if (active)
 		{
-			if (!TWO_LEVEL)
-			{
-				if (ng.y <= 0x00ffffffu && sp > 0) { ng = WIDE_TOP(); sp--; }
-				if (tg.y == 0 && tsp > 0) tg = triStack[--tsp];
-			}
-			else
+			if (TWO_LEVEL)
 			{
 				if (curInst != NO_INST && tg.y == 0 && tsp > 0) tg = triStack[--tsp];
 				if (ng.y <= 0x00ffffffu) while (sp > 0)
@@ -241,6 +246,7 @@ __device__ __forceinline__ void TraverseWide( const DevScene& scene, RaySource& 
 						}
 					}
 				}
+				if (!TWO_LEVEL && active && tg.y == 0 && tsp > 0) tg = triStack[--tsp];
 			}
 			continue;
 		}
@@ -283,20 +289,15 @@ __device__ __forceinline__ void TraverseWide( const DevScene& scene, RaySource& 
 				const uint32_t ny = D.y < 0 ? qhiy : qloy, fy = D.y < 0 ? qloy : qhiy;
 				const uint32_t nz = D.z < 0 ? qhiz : qloz, fz = D.z < 0 ? qloz : qhiz;
 #pragma unroll
-				for (int j = 0; j < 4; j++)
-				{
-					const uint32_t sel = 0x7604u | (uint32_t)(j << 4);
-					const float t0x = fmaf( ByteFloat( nx, sel ), hx, cnx ), t1x = fmaf( ByteFloat( fx, sel ), hx, cfx );
-					const float t0y = fmaf( ByteFloat( ny, sel ), hy, cny ), t1y = fmaf( ByteFloat( fy, sel ), hy, cfy );
-					const float t0z = fmaf( ByteFloat( nz, sel ), hz, cnz ), t1z = fmaf( ByteFloat( fz, sel ), hz, cfz );
-					const float cmin = fmaxf( fmaxf( t0x, t0y ), fmaxf( t0z, tmin ) );
-					const float cmax = fminf( fminf( t1x, t1y ), fminf( t1z, tmax ) ) * 1.0000005f;
-					if (cmin <= cmax)
-					{
-						const uint32_t cb = (childBits4 >> (8 * j)) & 255u, bi = (bitIndex4 >> (8 * j)) & 255u;
-						hitmask |= cb << bi;
-					}
-				}
+#define WIDE_CHILD( J ) { \
+					const float t0x = fmaf( ByteFloat<J>( nx, fbase ), hx, cnx ), t1x = fmaf( ByteFloat<J>( fx, fbase ), hx, cfx ); \
+					const float t0y = fmaf( ByteFloat<J>( ny, fbase ), hy, cny ), t1y = fmaf( ByteFloat<J>( fy, fbase ), hy, cfy ); \
+					const float t0z = fmaf( ByteFloat<J>( nz, fbase ), hz, cnz ), t1z = fmaf( ByteFloat<J>( fz, fbase ), hz, cfz ); \
+					const float cmin = fmaxf( fmaxf( t0x, t0y ), fmaxf( t0z, tmin ) ); \
+					const float cmax = fminf( fminf( t1x, t1y ), fminf( t1z, tmax ) ) * 1.0000005f; \
+					if (cmin <= cmax) hitmask |= ((childBits4 >> (8 * J)) & 255u) << ((bitIndex4 >> (8 * J)) & 255u); }
+				WIDE_CHILD( 0 ) WIDE_CHILD( 1 ) WIDE_CHILD( 2 ) WIDE_CHILD( 3 )
+#undef WIDE_CHILD
 			}
 			ng.y = (hitmask & 0xff000000u) | (n0.w >> 24);
 			ntg.y = hitmask & 0x00ffffffu;
@@ -305,6 +306,7 @@ __device__ __forceinline__ void TraverseWide( const DevScene& scene, RaySource& 
 				if (tg.y == 0) tg = ntg;
 				else triStack[tsp++] = ntg;
 			}
+			if (!TWO_LEVEL && ng.y <= 0x00ffffffu && sp > 0) { ng = WIDE_TOP(); sp--; }
 		}
 	}
 #undef WIDE_PUSH
