@@ -69,6 +69,11 @@ LH2B_API int lh2b_get_stats( lh2b_core* core, void* outCoreStats );
 
 /* Copy the finalized image (accumulator / samplesTaken, finalize_shared.h:29-45) to host: float4[w*h]. */
 LH2B_API int lh2b_read_pixels( lh2b_core* core, float* rgbaOut );
+/* Pipelined read-back: enqueues the device->host copy of the frame last passed to lh2b_render (it may still be in flight) on
+   the core's copy stream and returns at once; 'pinnedOut' must be page-locked and stay valid until lh2b_wait_read_pixels.
+   The next lh2b_render presents into a second pixel buffer, so the copy overlaps the next frame's kernels. */
+LH2B_API int lh2b_read_pixels_async( lh2b_core* core, float* pinnedOut );
+LH2B_API int lh2b_wait_read_pixels( lh2b_core* core );
 /* Copy the raw accumulator to host: float4[w*h]. */
 LH2B_API int lh2b_read_accumulator( lh2b_core* core, float* rgbaOut );
 /* Device pointer of the accumulator (float4[w*h]) for zero-copy collectives; samples taken so far. */

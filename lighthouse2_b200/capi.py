@@ -32,6 +32,8 @@ SIGNATURES = {
     "lh2b_wait_for_render": ([_vp], _ip),
     "lh2b_get_stats": ([_vp, _vp], _ip),
     "lh2b_read_pixels": ([_vp, _vp], _ip),
+    "lh2b_read_pixels_async": ([_vp, _vp], _ip),
+    "lh2b_wait_read_pixels": ([_vp], _ip),
     "lh2b_read_accumulator": ([_vp, _vp], _ip),
     "lh2b_accumulator_device_ptr": ([_vp, _c.POINTER(_vp), _c.POINTER(_ip)], _ip),
     "lh2b_finalize_external": ([_vp, _vp, _ip], _ip),

@@ -124,6 +124,13 @@ class RenderCore:
         self._check(self._lib.lh2b_read_pixels(self._h, _ptr(out)))
         return out
 
+    def ReadPixelsAsync(self, pinned_out):
+        """Enqueue the read-back of the last rendered frame into a page-locked array; overlaps the next Render."""
+        self._check(self._lib.lh2b_read_pixels_async(self._h, _ptr(pinned_out)))
+
+    def WaitReadPixels(self):
+        self._check(self._lib.lh2b_wait_read_pixels(self._h))
+
     def ReadAccumulator(self):
         out = np.empty((self.height, self.width, 4), np.float32)
         self._check(self._lib.lh2b_read_accumulator(self._h, _ptr(out)))

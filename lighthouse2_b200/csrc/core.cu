@@ -242,6 +242,9 @@ int lh2b_create( lh2b_core** out, int device )
 		std::unique_ptr<lh2b_core> core( new lh2b_core() );
 		core->device = device;
 		CUDA_CHECK( cudaStreamCreateWithFlags( &core->stream, cudaStreamNonBlocking ) );
+		CUDA_CHECK( cudaStreamCreateWithFlags( &core->copyStream, cudaStreamNonBlocking ) );
+		CUDA_CHECK( cudaEventCreateWithFlags( &core->frameDone, cudaEventDisableTiming ) );
+		for (int k = 0; k < 2; k++) CUDA_CHECK( cudaEventCreateWithFlags( &core->copyDone[k], cudaEventDisableTiming ) );
 		CUDA_CHECK( cudaEventCreate( &core->evA ) );
 		CUDA_CHECK( cudaEventCreate( &core->evB ) );
 		// device fields of CoreStats (rendercore.cpp:231-239)
@@ -267,6 +270,9 @@ int lh2b_destroy( lh2b_core* core )
 	ReleaseRenderState( core );
 	ReleaseGpuBuildScratch( core );
 	cudaEventDestroy( core->evA ), cudaEventDestroy( core->evB );
+	if (core->copyStream) cudaStreamSynchronize( core->copyStream ), cudaStreamDestroy( core->copyStream );
+	if (core->frameDone) cudaEventDestroy( core->frameDone );
+	for (int k = 0; k < 2; k++) if (core->copyDone[k]) cudaEventDestroy( core->copyDone[k] );
 	cudaStreamDestroy( core->stream );
 	delete[] core->stats.deviceName;
 	delete core;

@@ -82,6 +82,12 @@ struct lh2b_core
 	size_t maxPixels = 0; int allocatedSpp = 0;
 	lh2b::DevBuf<float4> pathBuf[2][3];		// ping-pong O/D/T
 	lh2b::DevBuf<float4> hitBuf, connBuf[3], accumulator, pixels;
+	// asynchronous read-back (lh2b_read_pixels_async): a second pixel buffer and a copy stream, so that the device->host copy
+	// of frame k overlaps the kernels of frame k+1. Index 0 of the pair arrays belongs to 'pixels', 1 to 'pixelsAlt'.
+	lh2b::DevBuf<float4> pixelsAlt;
+	cudaStream_t copyStream = nullptr;
+	cudaEvent_t frameDone = nullptr, copyDone[2] = { nullptr, nullptr };
+	bool copyPending[2] = { false, false };
 	lh2b::DevBuf<lh2b::DevCounters> counters;
 	lh2b::DevCounters* hostCounters = nullptr;	// pinned
 	int samplesTaken = 0;

@@ -13,6 +13,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstring>
+#include <utility>
 #include <cuda_fp16.h>
 
 extern "C" const unsigned char lh2b_bluenoise_bytes[];
@@ -137,16 +138,7 @@ static void FinishFrame( lh2b_core* core )
 		const float il = 1.0f / sqrtf( dx * dx + dy * dy + dz * dz );
 		st.probedWorldPos.x = v.pos.x + c.probedDist * dx * il, st.probedWorldPos.y = v.pos.y + c.probedDist * dy * il, st.probedWorldPos.z = v.pos.z + c.probedDist * dz * il;
 	}
-	// FinalizeRender (rendercore.cpp:963-979)
-	const int total = core->sampleShardTotal > 0 ? core->sampleShardTotal : core->spp;
-	core->samplesTaken += total;
-	const int localSamples = (int)((long long)core->samplesTaken * core->spp / total);
 	const int finEv = (int)core->events.size() - 2;
-	CUDA_CHECK( cudaEventRecord( core->events[finEv], core->stream ) );
-	if (core->filterEnabled && core->features.count) RunFilter( core );
-	else LaunchFinalize( core->accumulator.ptr, core->pixels.ptr, core->width * core->height, localSamples, core->stream );
-	CUDA_CHECK( cudaEventRecord( core->events[finEv + 1], core->stream ) );
-	CUDA_CHECK( cudaStreamSynchronize( core->stream ) );
 	const double now = NowMs();
 	st.renderTime = (float)((now - core->renderStartMs) * 0.001);	// the reference Timer reports seconds
 	st.frameOverhead = core->lastFrameEndMs > 0 ? fmaxf( 0.0f, (float)((core->renderStartMs - core->lastFrameEndMs) * 0.001) ) : 0;
@@ -190,12 +182,25 @@ static RenderParams BuildParams( lh2b_core* core, const lh2abi::ViewPyramid& vie
 	return p;
 }
 
+/* While an asynchronous read-back of 'pixels' is in flight the next frame presents into the other buffer; if that one is still
+   being copied too (two reads outstanding), the launch stream waits for that copy on the device - the host never blocks. */
+static void RotatePixelBuffers( lh2b_core* core )
+{
+	if (!core->copyPending[0]) return;
+	if (core->pixelsAlt.count < core->pixels.count) core->pixelsAlt.Resize( core->pixels.count );
+	core->pixels.Swap( core->pixelsAlt );
+	std::swap( core->copyDone[0], core->copyDone[1] );
+	std::swap( core->copyPending[0], core->copyPending[1] );
+	if (core->copyPending[0]) { CUDA_CHECK( cudaStreamWaitEvent( core->stream, core->copyDone[0], 0 ) ); core->copyPending[0] = false; }
+}
+
 static void RenderFrame( lh2b_core* core, const lh2abi::ViewPyramid& view )
 {
 	cudaStream_t s = core->stream;
 	const uint32_t stride = (uint32_t)core->width * core->height * core->spp;
 	core->lastView = view;
 	CUDA_CHECK( cudaEventRecord( core->events[0], s ) );
+	RotatePixelBuffers( core );
 	if (core->samplesTaken == 0) CUDA_CHECK( cudaMemsetAsync( core->accumulator.ptr, 0, 2 * (size_t)core->width * core->height * sizeof( float4 ), s ) );
 	if (core->filterEnabled) EnsureFilterBuffers( core );
 	CUDA_CHECK( cudaMemsetAsync( core->counters.ptr, 0, sizeof( DevCounters ), s ) );
@@ -220,6 +225,16 @@ static void RenderFrame( lh2b_core* core, const lh2abi::ViewPyramid& view )
 	}
 	CUDA_CHECK( cudaGetLastError() );
 	CUDA_CHECK( cudaMemcpyAsync( core->hostCounters, core->counters.ptr, sizeof( DevCounters ), cudaMemcpyDeviceToHost, s ) );
+	// FinalizeRender (rendercore.cpp:963-979), enqueued behind the last stage: nothing of it depends on host-visible results,
+	// so the whole frame is one uninterrupted sequence of launches and WaitForRender is a single stream synchronisation
+	const int total = core->sampleShardTotal > 0 ? core->sampleShardTotal : core->spp;
+	core->samplesTaken += total;
+	const int localSamples = (int)((long long)core->samplesTaken * core->spp / total);
+	const int finEv = (int)core->events.size() - 2;
+	CUDA_CHECK( cudaEventRecord( core->events[finEv], s ) );
+	if (core->filterEnabled && core->features.count) RunFilter( core );
+	else LaunchFinalize( core->accumulator.ptr, core->pixels.ptr, core->width * core->height, localSamples, s );
+	CUDA_CHECK( cudaEventRecord( core->events[finEv + 1], s ) );
 	core->frameInFlight = true;
 }
 
@@ -255,6 +270,8 @@ int lh2b_set_target( lh2b_core* core, int width, int height, int spp )
 	if (width <= 0 || height <= 0 || spp <= 0) throw CoreError( "SetTarget: width, height and spp must be positive" );
 	if ((unsigned long long)width * height * spp >= (1ull << 26)) throw CoreError( "SetTarget: w*h*spp must stay below 2^26 (path index is packed above 6 flag bits)" );
 	FinishFrame( core );
+	CUDA_CHECK( cudaStreamSynchronize( core->copyStream ) );
+	core->copyPending[0] = core->copyPending[1] = false;
 	core->width = width, core->height = height, core->spp = spp;
 	const size_t pixels = (size_t)width * height;
 	if (pixels > core->maxPixels || spp != core->allocatedSpp)
@@ -266,7 +283,7 @@ int lh2b_set_target( lh2b_core* core, int width, int height, int spp )
 		for (int k = 0; k < 3; k++) core->connBuf[k].Free(), core->connBuf[k].Resize( rays );
 		core->hitBuf.Free(), core->hitBuf.Resize( rays );
 		core->accumulator.Free(), core->accumulator.Resize( core->maxPixels * 2 );	// second half: indirect light in filter mode
-		core->pixels.Free(), core->pixels.Resize( core->maxPixels );
+		core->pixels.Free(), core->pixels.Resize( core->maxPixels ), core->pixelsAlt.Free();
 	}
 	CUDA_CHECK( cudaMemsetAsync( core->accumulator.ptr, 0, 2 * pixels * sizeof( float4 ), core->stream ) );
 	CUDA_CHECK( cudaMemsetAsync( core->pixels.ptr, 0, pixels * sizeof( float4 ), core->stream ) );
@@ -474,6 +491,26 @@ int lh2b_read_pixels( lh2b_core* core, float* rgbaOut )
 	FinishFrame( core );
 	CUDA_CHECK( cudaMemcpyAsync( rgbaOut, core->pixels.ptr, (size_t)core->width * core->height * sizeof( float4 ), cudaMemcpyDeviceToHost, core->stream ) );
 	CUDA_CHECK( cudaStreamSynchronize( core->stream ) );
+	API_END
+}
+
+int lh2b_read_pixels_async( lh2b_core* core, float* pinnedOut )
+{
+	API_BEGIN
+	// the frame (finalize included) is already enqueued on the launch stream: order the copy behind it on the copy stream
+	CUDA_CHECK( cudaEventRecord( core->frameDone, core->stream ) );
+	CUDA_CHECK( cudaStreamWaitEvent( core->copyStream, core->frameDone, 0 ) );
+	CUDA_CHECK( cudaMemcpyAsync( pinnedOut, core->pixels.ptr, (size_t)core->width * core->height * sizeof( float4 ), cudaMemcpyDeviceToHost, core->copyStream ) );
+	CUDA_CHECK( cudaEventRecord( core->copyDone[0], core->copyStream ) );
+	core->copyPending[0] = true;
+	API_END
+}
+
+int lh2b_wait_read_pixels( lh2b_core* core )
+{
+	API_BEGIN
+	CUDA_CHECK( cudaStreamSynchronize( core->copyStream ) );
+	core->copyPending[0] = core->copyPending[1] = false;
 	API_END
 }
 

@@ -288,7 +288,6 @@ __device__ __forceinline__ void TraverseWide( const DevScene& scene, RaySource& 
 				const uint32_t nx = D.x < 0 ? qhix : qlox, fx = D.x < 0 ? qlox : qhix;
 				const uint32_t ny = D.y < 0 ? qhiy : qloy, fy = D.y < 0 ? qloy : qhiy;
 				const uint32_t nz = D.z < 0 ? qhiz : qloz, fz = D.z < 0 ? qloz : qhiz;
-#pragma unroll
 #define WIDE_CHILD( J ) { \
 					const float t0x = fmaf( ByteFloat<J>( nx, fbase ), hx, cnx ), t1x = fmaf( ByteFloat<J>( fx, fbase ), hx, cfx ); \
 					const float t0y = fmaf( ByteFloat<J>( ny, fbase ), hy, cny ), t1y = fmaf( ByteFloat<J>( fy, fbase ), hy, cfy ); \

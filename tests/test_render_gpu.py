@@ -97,3 +97,27 @@ def test_probe_and_stats():
     assert abs(float(st["probedDist"]) / float(want[3:4].view(np.float32)[0]) - 1) < 1e-4
     assert st["primaryRayCount"] == W * H and st["totalRays"] == st["totalExtensionRays"] + st["totalShadowRays"]
     core.Shutdown()
+
+
+def test_pipelined_readback_matches_blocking():
+    """lh2b_read_pixels_async: the copy of frame k overlaps frame k+1 (which presents into the second pixel buffer); every
+    frame read that way must equal the blocking read of an identically seeded core. Six frames cover both buffers, the
+    device-side wait on a still-pending copy, and asynchronous Render (async=True) in front of the read."""
+    import torch
+    sd = _scene(3, 1)
+    views = [scenes.view_pyramid((10 + 3 * k, 25, -70), (0, 2, 0), 40, W, H) for k in range(6)]
+    a, b = _core(sd), _core(sd)
+    want = []
+    for v in views:
+        a.Render(v, 1)
+        want.append(a.ReadPixels().copy())
+    pinned = [torch.empty((H, W, 4), dtype=torch.float32, pin_memory=True) for _ in views]
+    for k, v in enumerate(views):
+        b.Render(v, 1, k % 2 == 1)               # odd frames: asynchronous render, read enqueued while the frame is in flight
+        b.ReadPixelsAsync(pinned[k].numpy())
+    b.WaitReadPixels()
+    for k in range(len(views)):
+        assert np.array_equal(pinned[k].numpy(), want[k]), k
+    # the blocking read still sees the last frame
+    assert np.array_equal(b.ReadPixels(), want[-1])
+    a.Shutdown(), b.Shutdown()
