@@ -5,10 +5,12 @@
    per-thread while-while loop: triangle tests ran with 3 of 32 lanes, node steps with 15 of 32, and the byte->float
    conversions (48 I2F.U8 per node step, quarter-rate XU pipe) dominated the stall samples. Hence:
 
-   1. The warp, not the thread, owns the loop. Every iteration all 32 lanes vote (ballot) on what they could do
-      next and the warp executes ONE phase: a node step for the lanes holding a node group, or a triangle test for
-      the lanes holding a triangle group. Triangle groups found while a lane still has node work are parked
-      (per-lane deferred stack) until enough lanes have triangles (TRI_THRESHOLD) or no lane has node work.
+   1. The warp, not the thread, owns the loop. Every iteration all 32 lanes vote (ballot) once on what they hold,
+      then the warp runs a triangle step for the lanes holding a triangle group, followed by a node step for the
+      lanes holding a node group (the "if-if" shape: both steps run convergent, each at most once per iteration).
+      Triangle groups found while a lane still has one pending are parked on a per-lane deferred stack.
+      TRI_THRESHOLD can postpone the triangle step until that many lanes have triangles; measured on the B200
+      (1 M-triangle terrain: primary / shadow / diffuse rays) the best value is 1, i.e. never postpone.
    2. Persistent threads: lanes whose ray is finished fetch the next ray index from a global counter with one
       warp-aggregated atomicAdd, so the warp stays full until the launch runs out of rays.
    3. Quantised plane bytes are turned into floats with one PRMT each (byte dropped into the mantissa of 65536.0f:
@@ -30,7 +32,7 @@ namespace lh2b
 #define WIDE_SMEM_STACK 12		// node-stack entries per thread kept in shared memory
 #define WIDE_LOCAL_STACK 40		// overflow entries in local memory
 #define WIDE_TRI_STACK 12		// deferred triangle groups per lane
-#define WIDE_TRI_THRESHOLD 12	// lanes with pending triangles that trigger a triangle phase
+#define WIDE_TRI_THRESHOLD 1	// lanes with pending triangles that trigger a triangle step
 #define WIDE_REFILL_THRESHOLD 8	// idle lanes that trigger fetching new rays
 
 /* 0x47800000 = 65536.0f; dropping a byte into mantissa bits 8..15 gives exactly 65536 + 2 * byte. 'base' holds the
@@ -248,10 +250,11 @@ __device__ __forceinline__ void TraverseWide( const DevScene& scene, RaySource& 
 				}
 				if (!TWO_LEVEL && active && tg.y == 0 && tsp > 0) tg = triStack[--tsp];
 			}
-			continue;
+			// lanes with a pending node take their node step in the same iteration: one vote for both phases
+			if (nodeMask == 0 || fullMask != 0) continue;	// (a full deferred-triangle stack drains before it may grow again)
 		}
 		// ---- node phase --------------------------------------------------------------------------------
-		if (hasNode)
+		if (hasNode && (!ANYHIT || active))
 		{
 			const uint32_t hits = ng.y;
 			const int bit = 31 - __clz( hits );
