@@ -227,14 +227,23 @@ def run_ours(args, rank, world, local_rank):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     ge_ms = stage["generateExtendMs"] / args.steps
     achieved = W * H * SPP * EXTEND_BYTES_PER_RAY / (ge_ms * 1e-3) / 1e9
-    traffic = None
+    traffic, issue = None, None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("wideGenerateExtendKernel_dram_bytes_per_launch")
+        tj = json.load(open(tpath))
+        traffic = tj.get("wideGenerateExtendKernel_dram_bytes_per_launch")
+        # traversal is bound by instruction issue, so also report rays/s against
+        # 148 SMs x 4 warp-instructions/clk x SM clock / (warp-instructions per ray, from the committed ncu capture)
+        wi = tj.get("wideGenerateExtendKernel_warp_inst_per_launch")
+        if wi and clocks and clocks.get("sm_mhz"):
+            per_ray = wi / tj["wideGenerateExtendKernel_rays_per_launch"]
+            peak_rays = 148 * 4 * clocks["sm_mhz"] * 1e6 / per_ray
+            issue = {"warp_inst_per_ray": per_ray, "peak_mrays_per_s": peak_rays / 1e6, "frac": (W * H * SPP / (ge_ms * 1e-3)) / peak_rays,
+                     "note": "issue-slot roofline of the dominant kernel; instruction count per ray from profiles/traffic.json"}
     roofline = {"kernel": "wideGenerateExtendKernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "ms_per_launch": ge_ms, "mrays_per_s": W * H * SPP / ge_ms / 1e3,
-                "note": "BVH traversal is latency/issue-bound, not HBM-bound (SURVEY.md 8d): the 67 MB CWBVH is L2-resident; "
-                        "see profiles/ for issue-slot and L1/L2 hit-rate evidence"}
+                "traffic": traffic, "peak_source": peak_src, "ms_per_launch": ge_ms, "mrays_per_s": W * H * SPP / ge_ms / 1e3, "issue": issue,
+                "note": "BVH traversal is latency/issue-bound, not HBM-bound (SURVEY.md 8d): the 67 MB CWBVH is L2-resident, DRAM traffic per launch "
+                        "matches the algorithmic 48 B/ray; 'issue' is the roofline that binds (see profiles/r1_v2_wide_kernels_full.txt)"}
     # ---- CPU baseline: oracle port on this box's host cores, bounded crop (rank 0, N = 1 only) ------------------
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
