@@ -177,14 +177,17 @@ struct ConnectSink
 };
 
 /* Primary rays: work items are 8x4 pixel tiles per warp (coherent rays per warp), per sample. */
-__device__ __forceinline__ void GeneratePrimary( const RenderParams& p, const uint32_t pathIdx, float3& O, float3& D )
+/* Exact n / d for any 32-bit n with m = ceil( 2^64 / d ), d >= 2 (n * (d * m - 2^64) < 2^64 always holds). */
+__device__ __forceinline__ uint32_t DivMagic( const uint32_t n, const uint64_t m ) { return (uint32_t)__umul64hi( (uint64_t)n, m ); }
+__host__ __device__ __forceinline__ uint64_t MagicOf( const uint32_t d ) { return d < 2 ? 0 : 0xffffffffffffffffull / d + 1; }
+
+/* (sx, sy) pixel, s = sample index within this frame's shard; pathIdx = sx + sy * w + s * w * h */
+__device__ __forceinline__ void GeneratePrimaryAt( const RenderParams& p, const int sx, const int sy, const uint32_t s, const uint32_t pathIdx, float3& O, float3& D )
 {
 	const uint32_t pixels = p.w * p.h;
-	const uint32_t pixelIdx = pathIdx % pixels;
 	const uint32_t seedIdx = pathIdx + p.sampleBase * pixels;
-	const uint32_t sampleIdx = seedIdx / pixels + p.pass;
+	const uint32_t sampleIdx = s + p.sampleBase + p.pass;
 	uint32_t seed = WangHashT( seedIdx * 16789 + p.pass * 1791 );
-	const int sx = pixelIdx % p.w, sy = pixelIdx / p.w;
 	float4 r4;
 	if (sampleIdx < 64)
 	{
@@ -198,17 +201,21 @@ __device__ __forceinline__ void GeneratePrimary( const RenderParams& p, const ui
 			(0.5f + (int)(v2 ^ scr.z)) * (1.0f / 256.0f), (0.5f + (int)(v3 ^ scr.w)) * (1.0f / 256.0f) );
 	}
 	else r4.x = RandomFloatT( seed ), r4.y = RandomFloatT( seed ), r4.z = RandomFloatT( seed ), r4.w = RandomFloatT( seed );
-	const float blade = (float)(int)(r4.x * 9);
-	float r1 = r4.z, r2 = (r4.x - blade * (1.0f / 9.0f)) * 9.0f;
-	float x1, y1, x2, y2;
-	const float PI_T = 3.14159265358979323846264f;
-	__sincosf( blade * PI_T / 4.5f, &x1, &y1 );
-	__sincosf( (blade + 1.0f) * PI_T / 4.5f, &x2, &y2 );
-	if ((r1 + r2) > 1) r1 = 1.0f - r1, r2 = 1.0f - r2;
-	const float xr = x1 * r1 + x2 * r2, yr = y1 * r1 + y2 * r2;
 	const float ap = p.posLensSize.w;
-	O = make_float3( p.posLensSize.x + ap * (p.right.x * xr + p.up.x * yr), p.posLensSize.y + ap * (p.right.y * xr + p.up.y * yr),
-		p.posLensSize.z + ap * (p.right.z * xr + p.up.z * yr) );
+	O = make_float3( p.posLensSize.x, p.posLensSize.y, p.posLensSize.z );
+	if (ap != 0)	// pinhole: the lens offset is 0 * finite, skip it (launch-uniform branch, same result)
+	{
+		const float blade = (float)(int)(r4.x * 9);
+		float r1 = r4.z, r2 = (r4.x - blade * (1.0f / 9.0f)) * 9.0f;
+		float x1, y1, x2, y2;
+		const float PI_T = 3.14159265358979323846264f;
+		__sincosf( blade * PI_T / 4.5f, &x1, &y1 );
+		__sincosf( (blade + 1.0f) * PI_T / 4.5f, &x2, &y2 );
+		if ((r1 + r2) > 1) r1 = 1.0f - r1, r2 = 1.0f - r2;
+		const float xr = x1 * r1 + x2 * r2, yr = y1 * r1 + y2 * r2;
+		O = make_float3( p.posLensSize.x + ap * (p.right.x * xr + p.up.x * yr), p.posLensSize.y + ap * (p.right.y * xr + p.up.y * yr),
+			p.posLensSize.z + ap * (p.right.z * xr + p.up.z * yr) );
+	}
 	float fu, fv;
 	if (p.distortion == 0) fu = ((float)sx + r4.y) * (1.0f / p.w), fv = ((float)sy + r4.w) * (1.0f / p.h);
 	else
@@ -225,24 +232,29 @@ __device__ __forceinline__ void GeneratePrimary( const RenderParams& p, const ui
 	D.x *= il, D.y *= il, D.z *= il;
 }
 
+__device__ __forceinline__ void GeneratePrimary( const RenderParams& p, const uint32_t pathIdx, float3& O, float3& D )
+{
+	const uint32_t pixels = p.w * p.h, s = pathIdx / pixels, pixelIdx = pathIdx - s * pixels;
+	const int sy = pixelIdx / p.w, sx = pixelIdx - sy * p.w;
+	GeneratePrimaryAt( p, sx, sy, s, pathIdx, O, D );
+}
+
 struct TiledPrimarySource
 {
 	const RenderParams* p; float4* __restrict__ outO; float4* __restrict__ outD; uint32_t* __restrict__ pathOf;	// pathOf: smem-free mapping kept in registers by the sink
 	uint32_t tilesX, itemsPerSample;
-	__device__ __forceinline__ uint32_t PathOf( const uint32_t work ) const
-	{
-		const uint32_t s = work / itemsPerSample, w = work - s * itemsPerSample;
-		const uint32_t tile = w >> 5, l = w & 31;
-		const uint32_t x = (tile % tilesX) * 8 + (l & 7), y = (tile / tilesX) * 4 + (l >> 3);
-		if (x >= (uint32_t)p->w || y >= (uint32_t)p->h) return 0xffffffffu;
-		return x + y * p->w + s * (p->w * p->h);
-	}
+	uint64_t tilesXMagic, itemsMagic;	// MagicOf( tilesX ), MagicOf( itemsPerSample ): the index arithmetic below runs per ray at ~1/3 SIMT width
 	__device__ __forceinline__ bool Load( const uint32_t work, WideRay& r, uint32_t& tag ) const
 	{
-		const uint32_t pathIdx = PathOf( work );
-		if (pathIdx == 0xffffffffu) return false;
+		// work item -> (sample, 8x4 pixel tile, lane in tile)
+		const uint32_t s = p->spp == 1 ? 0 : DivMagic( work, itemsMagic ), w = work - s * itemsPerSample;
+		const uint32_t tile = w >> 5, l = w & 31;
+		const uint32_t ty = tilesX == 1 ? tile : DivMagic( tile, tilesXMagic ), tx = tile - ty * tilesX;
+		const uint32_t x = tx * 8 + (l & 7), y = ty * 4 + (l >> 3);
+		if (x >= (uint32_t)p->w || y >= (uint32_t)p->h) return false;
+		const uint32_t pathIdx = x + y * p->w + s * (p->w * p->h);
 		tag = pathIdx;
-		GeneratePrimary( *p, pathIdx, r.O, r.D );
+		GeneratePrimaryAt( *p, (int)x, (int)y, s, pathIdx, r.O, r.D );
 		r.tmin = 0.0f, r.tmax = 1e34f;
 		outO[pathIdx] = make_float4( r.O.x, r.O.y, r.O.z, __uint_as_float( (pathIdx << 6) + 1 /* S_SPECULAR */ ) );
 		outD[pathIdx] = make_float4( r.D.x, r.D.y, r.D.z, 0 );
@@ -264,6 +276,7 @@ template <bool TWO_LEVEL> __global__ void __launch_bounds__( WIDE_BLOCK ) wideGe
 	src.p = &p, src.outO = out.O, src.outD = out.D, src.pathOf = nullptr;
 	src.tilesX = (p.w + 7) / 8;
 	src.itemsPerSample = src.tilesX * ((p.h + 3) / 4) * 32;
+	src.tilesXMagic = MagicOf( src.tilesX ), src.itemsMagic = MagicOf( src.itemsPerSample );
 	TiledHitSink sink = { &src, hits };
 	TraverseWide<false, TWO_LEVEL>( scene, src, sink, src.itemsPerSample * p.spp, workCounter, tune );
 }
