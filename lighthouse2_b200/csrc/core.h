@@ -76,6 +76,7 @@ struct lh2b_core
 	int bvhBuilder = 0;				// 0: GPU LBVH (default), 1: host binned SAH
 	float geometryEpsilon = 1e-4f, clampValue = 10.0f;	// reference defaults: stageClampValue(10) at rendercore.cpp:243; epsilon comes from RenderSystem (rendersystem.h:65-72)
 	int maxPathLength = 3;			// reference MAXPATHLENGTH (core_settings.h:25)
+	int bsdfModel = 0;					// Setting "bsdf": 0 lambert.h, 1 disney.h (what kernels/bsdf.h of the stock cores selects)
 	uint32_t enoughBounces = S_BOUNCED;	// reference ENOUGH_BOUNCES (pathtracer.h:33)
 	// render target + wavefront buffers (rendercore.cpp:284-326)
 	int width = 0, height = 0, spp = 1;

@@ -170,7 +170,7 @@ static RenderParams BuildParams( lh2b_core* core, const lh2abi::ViewPyramid& vie
 	p.stride = stride;
 	p.geometryEpsilon = core->geometryEpsilon, p.clampValue = core->clampValue;
 	p.probePixelIdx = core->probeX + core->width * core->probeY;
-	p.maxPathLength = core->maxPathLength, p.enoughBounces = core->enoughBounces;
+	p.maxPathLength = core->maxPathLength, p.enoughBounces = core->enoughBounces, p.bsdfModel = core->bsdfModel;
 	p.instDesc = core->instDesc.ptr, p.materials = core->materials.ptr;
 	p.triLights = core->triLights.ptr, p.pointLights = core->pointLights.ptr, p.spotLights = core->spotLights.ptr, p.dirLights = core->dirLights.ptr;
 	p.lightCounts = make_int4( core->lightCounts[0], core->lightCounts[1], core->lightCounts[2], core->lightCounts[3] );
@@ -305,6 +305,7 @@ int lh2b_setting( lh2b_core* core, const char* name, float value )
 	else if (!strcmp( name, "clampIndirect" )) core->clampIndirect = value;
 	// extensions of this core (the reference fixes these at compile time: core_settings.h:25, pathtracer.h:33)
 	else if (!strcmp( name, "maxPathLength" )) core->maxPathLength = value < 1 ? 1 : (value > LH2B_MAXPATHLENGTH ? LH2B_MAXPATHLENGTH : (int)value);
+	else if (!strcmp( name, "bsdf" )) { const int m = value >= 0.5f ? 1 : 0; if (m != core->bsdfModel) core->bsdfModel = m, core->samplesTaken = 0; }
 	else if (!strcmp( name, "maxDiffuseBounces" )) core->enoughBounces = value <= 0 ? 0 : (value < 2 ? S_BOUNCED : S_BOUNCEDTWICE);
 	else if (!strcmp( name, "bvhBuilder" )) core->bvhBuilder = (int)value;	// 0: GPU LBVH (default), 1: host binned SAH
 	else if (!strcmp( name, "bvhRefit" )) core->bvhRefit = (int)value;

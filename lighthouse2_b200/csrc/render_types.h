@@ -57,6 +57,7 @@ struct RenderParams
 	float geometryEpsilon, clampValue;
 	int probePixelIdx;
 	int maxPathLength;			// reference MAXPATHLENGTH (3)
+	int bsdfModel;				// 0: lambert.h (Lambert + pure specular + dielectric), 1: disney.h (principled); Setting "bsdf"
 	uint32_t enoughBounces;		// reference ENOUGH_BOUNCES flag mask (S_BOUNCED); 0 = never stop on bounce count
 	// scene (the __constant__ block of kernels/.cuda.cu:22-43)
 	const void* instDesc;		// CoreInstanceDesc[]

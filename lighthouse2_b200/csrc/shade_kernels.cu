@@ -137,6 +137,7 @@ struct Shading
 	float3 color; int flags;		// flags bit 0: alpha-rejected texel
 	float3 transmittance;
 	uint4 parameters;				// 0.8 fixed point Disney parameter block + eta (core_settings.h:146)
+	float4 tint;					// hue of the base colour at unit luminance + its luminance (material_shared.h:118-119); Disney model only
 };
 #define SH_ROUGHNESS( s ) (fmaxf( 0.001f, char2flt( (s).parameters.x, 24 ) ))
 #define SH_TRANSMISSION( s ) char2flt( (s).parameters.z, 16 )
@@ -161,6 +162,20 @@ __device__ __forceinline__ void GetShadingData( const RenderParams& p, const flo
 	s.color = make_float3( rg.x, rg.y, bm.x ), s.flags = 0;
 	s.transmittance = make_float3( bm.y, gb.x, gb.y );
 	s.parameters = mat.q[1];
+	{
+		// CIE XYZ round trip of the untextured base colour (material_shared.h:19-33,118-119)
+		const float3 c = s.color;
+		const float X = fmaxf( 0.0f, 0.412453f * c.x + 0.357580f * c.y + 0.180423f * c.z ), Y = fmaxf( 0.0f, 0.212671f * c.x + 0.715160f * c.y + 0.072169f * c.z );
+		const float Z = fmaxf( 0.0f, 0.019334f * c.x + 0.119193f * c.y + 0.950227f * c.z );
+		float3 t = f3( 1 );
+		if (Y > 0)
+		{
+			const float r = 1.0f / Y, x = X * r, y = Y * r, z = Z * r;
+			t = make_float3( fmaxf( 0.0f, 3.240479f * x - 1.537150f * y - 0.498535f * z ), fmaxf( 0.0f, -0.969256f * x + 1.875992f * y + 0.041556f * z ),
+				fmaxf( 0.0f, 0.055648f * x - 0.204043f * y + 1.057311f * z ) );
+		}
+		s.tint = make_float4( t.x, t.y, t.z, Y );
+	}
 	// SetupFrame (material_shared.h:42-85)
 	N = make_float3( t2.w, t3.w, t4.w ), iN = N;
 	T = xyz( t5 );
@@ -451,6 +466,11 @@ __device__ __forceinline__ float3 SampleBSDF( const Shading& s, float3 iN, const
 	return bsdf;
 }
 
+} // namespace lh2b
+#include "bsdf_disney.cuh"
+namespace lh2b
+{
+
 /* ---- filter features (Optix7Filter pathtracer.h:44-58; tools_shared.h:122-130,160-166) ---- */
 __device__ __forceinline__ uint32_t PackNormal2( const float3 N )
 {
@@ -507,7 +527,9 @@ __device__ __forceinline__ uint32_t WarpAlloc( uint32_t* counter, const bool wan
 	return base + __popc( mask & ((1u << lane) - 1) );
 }
 
-__global__ void __launch_bounds__( 128, 4 ) shadeKernel( const RenderParams p, const PathSet in, const PathSet out,
+/* BSDF: 0 = lambert.h model (a14), 1 = Disney principled model (bsdf_disney.cuh); the only line of pathtracer.h that depends on
+   the model is the ROUGHNESS factor on the NEE term (BSDF_HAS_PURE_SPECULARS, pathtracer.h:194-198) */
+template <int BSDF> __global__ void __launch_bounds__( 128, 4 ) shadeKernel( const RenderParams p, const PathSet in, const PathSet out,
 	const float4* __restrict__ hits, const PathSet conn, const int pathLength, const uint32_t R0, const int useNEE )
 {
 	const uint32_t pathCount = pathLength == 1 ? p.stride : p.counters->extensionRays[pathLength - 1];
@@ -662,7 +684,8 @@ __global__ void __launch_bounds__( 128, 4 ) shadeKernel( const RenderParams p, c
 				if (NdotL > 0 && lightPdf > 0)
 				{
 					float lobePdf;
-					const float3 f = EvaluateBSDF( sh, fN, L, lobePdf ) * roughness;
+					const float3 f = BSDF == 0 ? EvaluateBSDF( sh, fN, L, lobePdf ) * roughness :
+						EvaluateDisney( UnpackDisney( sh.color, sh.transmittance, sh.tint, sh.parameters ), fN, T, D * -1.0f, L, lobePdf );
 					if (lobePdf > 0)
 					{
 						float3 contribution = throughput * f * lightColor * (NdotL / (pickProb * lightPdf + lobePdf));
@@ -691,9 +714,9 @@ __global__ void __launch_bounds__( 128, 4 ) shadeKernel( const RenderParams p, c
 			float3 R;
 			float newPdf;
 			bool specular = false;
-			const float r5 = RandomFloat( seed );	// consumed by the BSDF slot of the reference call (unused by Lambert)
-			(void)r5;
-			const float3 bsdf = SampleBSDF( sh, fN, N, D * -1.0f, hitT, r4.z, r4.w, R, newPdf, specular );
+			const float r5 = RandomFloat( seed );	// third random number of the reference SampleBSDF call (unused by Lambert)
+			const float3 bsdf = BSDF == 0 ? SampleBSDF( sh, fN, N, D * -1.0f, hitT, r4.z, r4.w, R, newPdf, specular ) :
+				SampleDisney( UnpackDisney( sh.color, sh.transmittance, sh.tint, sh.parameters ), fN, N, T, D * -1.0f, hitT, r4.z, r4.w, r5, R, newPdf, specular );
 			if (newPdf < 0.0001f || isnan( newPdf )) break;
 			if (specular) data |= S_SPECULAR;
 			const float rr = (filter || (data & S_SPECULAR) || ((data & S_BOUNCED) == 0)) ? 1 : fminf( 1.0f, fmaxf( fmaxf( bsdf.x, bsdf.y ), bsdf.z ) );
@@ -733,7 +756,8 @@ void LaunchShade( const RenderParams& p, const PathSet& in, const PathSet& out, 
 	const uint32_t cap = (uint32_t)smCount * 4 * 16;
 	if (blocks > cap) blocks = cap;
 	if (blocks == 0) return;
-	shadeKernel<<<blocks, 128, 0, s>>>( p, in, out, hits, conn, pathLength, R0, useNEE ? 1 : 0 );
+	if (p.bsdfModel == 1) shadeKernel<1><<<blocks, 128, 0, s>>>( p, in, out, hits, conn, pathLength, R0, useNEE ? 1 : 0 );
+	else shadeKernel<0><<<blocks, 128, 0, s>>>( p, in, out, hits, conn, pathLength, R0, useNEE ? 1 : 0 );
 }
 
 void LaunchFinalize( const float4* accumulator, float4* out, int n, int samplesTaken, cudaStream_t s )

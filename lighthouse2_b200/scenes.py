@@ -225,7 +225,9 @@ def gradient_sky(w=512, h=256, zenith=(0.35, 0.5, 0.9), horizon=(0.9, 0.9, 0.85)
 
 
 def make_materials(specs):
-    """specs: list of dicts with optional keys color, roughness, transmission, eta, absorption, smooth."""
+    """specs: list of dicts with optional keys color, roughness, transmission, eta, absorption, smooth and the other
+    principled-model scalars (metallic, subsurface, specular, specularTint, anisotropic, sheen, sheenTint, clearcoat,
+    clearcoatGloss), all in [0, 1] as HostMaterial stores them."""
     m = abi.default_material(len(specs))
     for i, s in enumerate(specs):
         m[i]["color"]["value"] = s.get("color", (0.8, 0.8, 0.8))
@@ -233,20 +235,55 @@ def make_materials(specs):
         m[i]["transmission"]["value"] = s.get("transmission", 0.0)
         m[i]["eta"]["value"] = s.get("eta", 1.0)
         m[i]["absorption"]["value"] = s.get("absorption", (0.0, 0.0, 0.0))
+        for k in ("metallic", "subsurface", "specular", "specularTint", "anisotropic", "sheen", "sheenTint", "clearcoat", "clearcoatGloss"):
+            if k in s:
+                m[i][k]["value"] = s[k]
         m[i]["flags"] = 1 if s.get("smooth", False) else 0
     return m
 
 
-def config2_scene(nx=1000, nz=500, n_materials=1, light_quads=1, seed=0x12345678, floaters=0):
+def principled_specs(n, seed=7):
+    """n material specs that exercise every lobe of the principled model: rough / glossy dielectrics, metals, sheen cloth,
+    clearcoat, anisotropic brushed metal, subsurface, frosted glass."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for i in range(n):
+        col = tuple(0.25 + 0.7 * rng.random(3))
+        kind = i % 8
+        s = dict(color=col, roughness=float(0.15 + 0.8 * rng.random()), specular=float(rng.random()), specularTint=float(rng.random()))
+        if kind == 1:
+            s.update(metallic=1.0, roughness=float(0.1 + 0.5 * rng.random()))
+        elif kind == 2:
+            s.update(sheen=float(0.5 + 0.5 * rng.random()), sheenTint=float(rng.random()), roughness=1.0)
+        elif kind == 3:
+            s.update(clearcoat=float(0.5 + 0.5 * rng.random()), clearcoatGloss=float(rng.random()))
+        elif kind == 4:
+            s.update(metallic=float(0.5 + 0.5 * rng.random()), anisotropic=float(0.3 + 0.7 * rng.random()), roughness=float(0.2 + 0.4 * rng.random()))
+        elif kind == 5:
+            s.update(subsurface=float(0.3 + 0.7 * rng.random()))
+        elif kind == 6:
+            s.update(transmission=1.0, eta=float(1.0 / (1.3 + 0.3 * rng.random())), roughness=float(0.05 + 0.4 * rng.random()), absorption=(0.1, 0.3, 0.2))
+        elif kind == 7:
+            s.update(metallic=float(rng.random()), sheen=float(rng.random()), clearcoat=float(rng.random()), clearcoatGloss=float(rng.random()),
+                     anisotropic=float(rng.random()), subsurface=float(rng.random()), transmission=float(0.3 * rng.random()), eta=1.0 / 1.5)
+        out.append(s)
+    return out
+
+
+def config2_scene(nx=1000, nz=500, n_materials=1, light_quads=1, seed=0x12345678, floaters=0, material_specs=None):
     """BASELINE.json configs[1]/[2]: height-field terrain + emissive quads.
     n_materials > 1 assigns diffuse/specular materials with roughness in {0, 0.3, 1} to terrain patches."""
     sd = SceneDesc()
     rng = np.random.default_rng(seed ^ 0x9E3779B9)
     specs = []
+    if material_specs is not None:
+        n_materials = len(material_specs)
     for i in range(max(1, n_materials)):
         col = 0.35 + 0.6 * rng.random(3)
         rough = (1.0, 0.3, 0.0)[i % 3] if n_materials > 1 else 1.0
         specs.append(dict(color=tuple(col), roughness=rough))
+    if material_specs is not None:
+        specs = [dict(s) for s in material_specs]
     light_mat = len(specs)
     specs.append(dict(color=(100.0, 100.0, 80.0)))
     sd.materials = make_materials(specs)

@@ -96,7 +96,7 @@ class OrcFrameIn(ctypes.Structure):
                 ("sampleBase", ctypes.c_uint), ("shiftSeed", ctypes.c_uint), ("camRNGseed", ctypes.c_uint),
                 ("geometryEpsilon", ctypes.c_float), ("clampValue", ctypes.c_float),
                 ("maxPathLength", ctypes.c_int), ("enoughBounces", ctypes.c_uint),
-                ("view", ctypes.c_float * 17), ("threads", ctypes.c_int)]
+                ("view", ctypes.c_float * 17), ("threads", ctypes.c_int), ("bsdfModel", ctypes.c_int)]
 
 
 PathRecord = np.dtype([("hit", np.uint32, 4), ("firstShadow", np.float32, 8)])
@@ -111,7 +111,7 @@ class FrameOracle:
     (rendercore.h:122-123) so consecutive Render calls can be mirrored frame by frame."""
 
     def __init__(self, scene, width, height, spp=1, epsilon=1e-4, clamp=10.0, max_path_length=3, max_diffuse_bounces=1,
-                 threads=None, sample_base=0, total_spp=0, filter=False):
+                 threads=None, sample_base=0, total_spp=0, filter=False, bsdf=0):
         self.sd, self.w, self.h, self.spp = scene, width, height, spp
         self.eps, self.clamp, self.maxlen = epsilon, clamp, max_path_length
         self.enough = 0 if max_diffuse_bounces <= 0 else (2 if max_diffuse_bounces < 2 else 8)
@@ -121,6 +121,7 @@ class FrameOracle:
         self.shift_seed, self.cam_seed = 0x11331445, 0x12345678
         self.first_converging = True
         self.filter = filter
+        self.bsdf = int(bsdf)          # 0: lambert.h model, 1: principled (disney.h) model
         self.accum = np.zeros((2, height, width, 4) if filter else (height, width, 4), np.float32)
         self.features = np.zeros((height, width, 4), np.uint32) if filter else None
         self.world_pos = np.zeros((height, width, 4), np.float32) if filter else None
@@ -210,6 +211,7 @@ class FrameOracle:
         f.maxPathLength, f.enoughBounces = self.maxlen, self.enough
         f.view[:] = [float(x) for x in np.frombuffer(np.ascontiguousarray(view).tobytes(), np.float32)]
         f.threads = self.threads
+        f.bsdfModel = self.bsdf
         keep += [cm, ct, ci, mats, texs]
         return f, keep
 
@@ -266,18 +268,19 @@ class RefShadeIn(ctypes.Structure):
                 ("countersOut", ctypes.c_uint * 12)]
 
 
-REF_SHADE_GPU = os.path.join(_HERE, "_ref", "libref_shade_gpu.so")
+REF_SHADE_GPU = os.path.join(_HERE, "_ref", "libref_shade_gpu.so")                    # reference shadeKernel with lambert.h
+REF_SHADE_DISNEY_GPU = os.path.join(_HERE, "_ref", "libref_shade_disney_gpu.so")      # ... with ggxmdf.h + frosted.h + disney.h
 
 
-def have_ref_shade_gpu():
-    return os.path.exists(REF_SHADE_GPU)
+def have_ref_shade_gpu(bsdf=0):
+    return os.path.exists(REF_SHADE_DISNEY_GPU if bsdf else REF_SHADE_GPU)
 
 
-def ref_shade_gpu(oracle, view, path_length, O4, D4, T4, hits, R0, shift, pass_, accumulator):
+def ref_shade_gpu(oracle, view, path_length, O4, D4, T4, hits, R0, shift, pass_, accumulator, bsdf=0):
     """Run the REFERENCE shadeKernel (unmodified source, sm_100a build) on n paths. Returns compacted extension rays,
     shadow rays, the accumulator and the counters, like lh2b_shade_paths."""
     sd = oracle.sd
-    rl = ctypes.CDLL(REF_SHADE_GPU)
+    rl = ctypes.CDLL(REF_SHADE_DISNEY_GPU if bsdf else REF_SHADE_GPU)
     tb = oracle.reference_tables(view)
     n = O4.shape[0]
     stride = 2 * n

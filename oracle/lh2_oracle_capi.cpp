@@ -82,6 +82,7 @@ struct OrcFrameIn
 	int maxPathLength; uint32_t enoughBounces;
 	float view[17];
 	int threads;
+	int bsdfModel;								// 0 lambert.h, 1 disney.h
 };
 
 static uint32_t XorShift( uint32_t& s ) { s ^= s << 13, s ^= s >> 17, s ^= s << 5; return s; }
@@ -195,7 +196,7 @@ ORC_API void orc_render_frame( const OrcFrameIn* inp, float* accum, uint64_t* ra
 	st.shift = shiftSeed;
 	for (int L = 1; L <= in.maxPathLength; L++) st.R0[L] = XorShift( camSeed ) + L * 91771;
 	st.geometryEpsilon = in.geometryEpsilon, st.clampValue = in.clampValue;
-	st.maxPathLength = in.maxPathLength, st.enoughBounces = in.enoughBounces;
+	st.maxPathLength = in.maxPathLength, st.enoughBounces = in.enoughBounces, st.bsdfModel = in.bsdfModel;
 	memcpy( st.view, in.view, sizeof( st.view ) );
 	if (seedsOut) seedsOut[0] = shiftSeed, seedsOut[1] = camSeed;
 	const int pixels = in.w * in.h;
@@ -287,7 +288,7 @@ ORC_API void orc_shade_paths( const OrcFrameIn* inp, int pathLength, int n, cons
 	st.w = in.w, st.h = in.h, st.spp = in.spp, st.pass = pass, st.sampleBase = in.sampleBase, st.shift = shift;
 	st.R0[pathLength] = R0;
 	st.geometryEpsilon = in.geometryEpsilon, st.clampValue = in.clampValue;
-	st.maxPathLength = in.maxPathLength, st.enoughBounces = in.enoughBounces;
+	st.maxPathLength = in.maxPathLength, st.enoughBounces = in.enoughBounces, st.bsdfModel = in.bsdfModel;
 	memcpy( st.view, in.view, sizeof( st.view ) );
 	ParallelFor( n, in.threads, [&]( int a, int b ) {
 		for (int i = a; i < b; i++)

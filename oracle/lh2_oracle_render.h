@@ -123,6 +123,7 @@ struct Settings
 	int maxPathLength;
 	uint32_t enoughBounces;
 	float view[17];				// ViewPyramid
+	int bsdfModel;				// 0: lambert.h, 1: disney.h (lh2_oracle_disney.h)
 };
 
 enum { S_SPECULAR = 1, S_BOUNCED = 2, S_VIASPECULAR = 4, S_BOUNCEDTWICE = 8 };
@@ -214,12 +215,13 @@ static inline F4 FetchTexelTrilinear( const RenderScene& s, float lambda, float 
 }
 
 /* ---- shading data ---- */
-struct Shading { V3 color, transmittance; int flags; uint32_t params[4]; };
+struct Shading { V3 color, transmittance; int flags; uint32_t params[4]; V3 tint; float lum; };	// tint/lum: material_shared.h:118-119 (principled model)
 static inline float Char2Flt( uint32_t a, int s ) { return (float)((a >> s) & 255) * (1.0f / 255.0f); }
 static inline float Roughness( const Shading& s ) { return fmaxf( 0.001f, Char2Flt( s.params[0], 24 ) ); }
 static inline float Transmission( const Shading& s ) { return Char2Flt( s.params[2], 16 ); }
 static inline float Eta( const Shading& s ) { return BitsF( s.params[3] ); }
 
+static inline void TintOf( V3 c, V3& tint, float& lum );
 static inline void GetShadingData( const RenderScene& sc, V3 D, float u, float v, float coneWidth, const float* tri, const float* invT,
 	Shading& sh, V3& N, V3& iN, V3& fN, V3& T )
 {
@@ -228,6 +230,7 @@ static inline void GetShadingData( const RenderScene& sc, V3 D, float u, float v
 	sh.color = v3( mat.color[0], mat.color[1], mat.color[2] ), sh.flags = 0;
 	sh.transmittance = v3( mat.transmittance[0], mat.transmittance[1], mat.transmittance[2] );
 	memcpy( sh.params, mat.params, 16 );
+	TintOf( sh.color, sh.tint, sh.lum );
 	N = v3( tri[11], tri[15], tri[19] ), iN = N;
 	T = v3( tri[20], tri[21], tri[22] );
 	const float w = 1 - (u + v);
@@ -494,6 +497,11 @@ static inline V3 SampleBSDF( const Shading& s, V3 iN, V3 N, V3 wo, float distanc
 	return bsdf;
 }
 
+} // namespace orc
+#include "lh2_oracle_disney.h"
+namespace orc
+{
+
 static inline void ClampIntensity( V3& c, float clampValue )
 {
 	const float v = fmaxf( c.x, fmaxf( c.y, c.z ) );
@@ -723,7 +731,8 @@ static inline void ShadeStep( const RenderScene& sc, const Settings& st, int pat
 		if (NdotL > 0 && lightPdf > 0)
 		{
 			float lobePdf;
-			const V3 f = EvaluateBSDF( sh, fN, L, lobePdf ) * roughness;
+			// BSDF_HAS_PURE_SPECULARS (lambert.h:30) scales the NEE term by ROUGHNESS; the principled model does not (pathtracer.h:194-198)
+			const V3 f = st.bsdfModel == 0 ? EvaluateBSDF( sh, fN, L, lobePdf ) * roughness : EvaluatePrincipled( MakePrincipled( sh ), fN, T, D * -1.0f, L, lobePdf );
 			if (lobePdf > 0)
 			{
 				V3 contribution = throughput * f * lightColor * (NdotL / (pickProb * lightPdf + lobePdf));
@@ -747,8 +756,9 @@ static inline void ShadeStep( const RenderScene& sc, const Settings& st, int pat
 	V3 R;
 	float newPdf;
 	bool specular = false;
-	(void)RandomFloat( seed );	// r5 argument of the reference SampleBSDF call (unused by the Lambert model)
-	const V3 bsdf = SampleBSDF( sh, fN, N, D * -1.0f, ht, r4[2], r4[3], R, newPdf, specular );
+	const float r5 = RandomFloat( seed );	// third random number of the reference SampleBSDF call (unused by the Lambert model)
+	const V3 bsdf = st.bsdfModel == 0 ? SampleBSDF( sh, fN, N, D * -1.0f, ht, r4[2], r4[3], R, newPdf, specular ) :
+		SamplePrincipled( MakePrincipled( sh ), fN, N, T, D * -1.0f, ht, r4[2], r4[3], r5, R, newPdf, specular );
 	if (newPdf < 0.0001f || newPdf != newPdf) return;
 	if (specular) data |= S_SPECULAR;
 	const float p = (filter || (data & S_SPECULAR) || ((data & S_BOUNCED) == 0)) ? 1 : fminf( 1.0f, fmaxf( fmaxf( bsdf.x, bsdf.y ), bsdf.z ) );

@@ -1,7 +1,7 @@
 /* ref_shade_gpu.cu - TEST INFRASTRUCTURE ONLY. Harness that compiles the REFERENCE's own shading stack for
    sm_100a straight from the reference tree (nothing is copied): lib/rendercore_optix7/kernels/pathtracer.h
    (shadeKernel) with lib/CUDA/shared_kernel_code/{tools,sampling,material,lights}_shared.h and
-   lib/sharedBSDFs/{compatibility,lambert}.h. It re-declares the __constant__ globals that
+   lib/sharedBSDFs/{compatibility,lambert}.h - or, with -DREF_BSDF_DISNEY, {ggxmdf,frosted,disney}.h (second library). It re-declares the __constant__ globals that
    lib/rendercore_optix7/kernels/.cuda.cu:22-43,190 owns (that file cannot be compiled with CUDA 12: it pulls in the
    legacy surface reference of .cuda.h:54) and exposes one C entry point that runs shadeKernel on caller data.
    Built by oracle/Makefile into oracle/_ref/libref_shade_gpu.so when /root/reference is present.
@@ -54,7 +54,13 @@ static __device__ Counters* counters;
 #include "material_shared.h"
 #include "lights_shared.h"
 #include "compatibility.h"
+#ifdef REF_BSDF_DISNEY	// what kernels/bsdf.h:7-21 of the stock cores selects
+#include "ggxmdf.h"
+#include "frosted.h"
+#include "disney.h"
+#else
 #include "lambert.h"
+#endif
 #include "pathtracer.h"
 } // namespace lh2core
 

@@ -121,3 +121,16 @@ def test_pipelined_readback_matches_blocking():
     # the blocking read still sees the last frame
     assert np.array_equal(b.ReadPixels(), want[-1])
     a.Shutdown(), b.Shutdown()
+
+
+def test_frame_principled_materials():
+    """Setting("bsdf", 1): the principled model the stock reference cores compile (disney.h), 16 materials covering every lobe,
+    longer paths and two diffuse bounces so sampled lobes feed further vertices."""
+    sd = scenes.config2_scene(48, 32, light_quads=2, floaters=300, material_specs=scenes.principled_specs(16))
+    view = scenes.view_pyramid((0, 30, -80), (0, 0, 0), 40, W, H)
+    core = _core(sd, spp=2, maxlen=5, bounces=2)
+    core.Setting("bsdf", 1)
+    oracle = orc.FrameOracle(sd, W, H, 2, 1e-3, 10.0, 5, 2, bsdf=1)
+    for conv in (1, 0):
+        _compare(core, oracle, view, conv)
+    core.Shutdown()
