@@ -240,7 +240,6 @@ __global__ void __launch_bounds__( 256 ) prepareKernel( const PrepareArgs a )
 
 /* ---- a-trous (finalize_shared.h:320-484) ------------------------------------------------------------------------ */
 #define AT_BX 32
-#define AT_BY 8
 struct AtrousArgs
 {
 	const uint4* features; const float4* prevWorldPos; const float4* worldPos; const float4* deltaDepth; const float2* motion; const float4* moments;
@@ -248,64 +247,76 @@ struct AtrousArgs
 	int w, h, phase, lastPass;
 };
 
-template <int STEP> __global__ void __launch_bounds__( AT_BX * AT_BY ) atrousKernel( const AtrousArgs a )
+/* The block stages its tile plus the halo UNPACKED: every tile pixel is decoded once (5.11 fixed point -> float, luminances,
+   10-bit normal, 10/11/11-bit albedo) instead of once per tap of every pixel that reads it (20 taps). Four float4 planes:
+     dir = direct.rgb, luminance | ind = indirect.rgb, luminance | nrm = normal.xyz, depth | alb = albedo.rgb, feature word w */
+template <int STEP, int BY> __global__ void __launch_bounds__( AT_BX * BY ) atrousKernel( const AtrousArgs a )
 {
-	constexpr int HALO = 2 * STEP, TW = AT_BX + 2 * HALO, TH = AT_BY + 2 * HALO;
-	extern __shared__ float4 tile[];			// [TH][TW] shading, then [TH][TW] features (as float4 bit patterns)
-	float4* tShade = tile;
-	uint4* tFeat = (uint4*)(tile + TW * TH);
-	const int x0 = blockIdx.x * AT_BX, y0 = blockIdx.y * AT_BY;
-	for (int i = threadIdx.y * AT_BX + threadIdx.x; i < TW * TH; i += AT_BX * AT_BY)
+	constexpr int HALO = 2 * STEP, TW = AT_BX + 2 * HALO, TH = BY + 2 * HALO;
+	extern __shared__ float4 tile[];
+	float4* tDir = tile, * tInd = tile + TW * TH, * tNrm = tile + 2 * TW * TH, * tAlb = tile + 3 * TW * TH;
+	const int x0 = blockIdx.x * AT_BX, y0 = blockIdx.y * BY;
+	for (int i = threadIdx.y * AT_BX + threadIdx.x; i < TW * TH; i += AT_BX * BY)
 	{
 		const int ty = i / TW, tx = i - ty * TW;
 		const int gx = min( max( x0 - HALO + tx, 0 ), a.w - 1 ), gy = y0 - HALO + ty;
-		if (gy >= 0 && gy < a.h) tShade[i] = a.A[gx + gy * a.w], tFeat[i] = a.features[gx + gy * a.w];
+		if (gy >= 0 && gy < a.h)
+		{
+			const float4 c = a.A[gx + gy * a.w];
+			const uint4 f = a.features[gx + gy * a.w];
+			const float3 d = DirectOf( c ), in = IndirectOf( c ), n = UnpackNormal2( f.y ), al = RGB32toHDR( f.x );
+			tDir[i] = f4( d, Luminance( d ) ), tInd[i] = f4( in, Luminance( in ) );
+			tNrm[i] = f4( n, __uint_as_float( f.z ) ), tAlb[i] = f4( al, __uint_as_float( f.w ) );
+		}
 	}
 	__syncthreads();
 	const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
 	if (x >= a.w || y >= a.h) return;
 	const int pixelIdx = x + y * a.w, phase = a.phase;
 	const int cx = threadIdx.x + HALO, cy = threadIdx.y + HALO;
-	const uint4 lf = tFeat[cx + cy * TW];
-	const float3 localNormal = UnpackNormal2( lf.y ), localColor = RGB32toHDR( lf.x );
-	const int localMatID = lf.w >> 4;
-	const float4 combined = tShade[cx + cy * TW];
+	const float4 cDir = tDir[cx + cy * TW], cInd = tInd[cx + cy * TW], cNrm = tNrm[cx + cy * TW], cAlb = tAlb[cx + cy * TW];
+	const uint32_t lfw = __float_as_uint( cAlb.w );
+	const float3 localNormal = xyz( cNrm ), localColor = xyz( cAlb );
+	const int localMatID = lfw >> 4;
 	float dirW = 1, indW = 1;
-	float3 dirSum = DirectOf( combined ), indSum = IndirectOf( combined );
-	const float localDirect = Luminance( dirSum ), localIndirect = Luminance( indSum );
-	const float localDepth = __uint_as_float( lf.z );
+	float3 dirSum = xyz( cDir ), indSum = xyz( cInd );
+	const float localDirect = cDir.w, localIndirect = cInd.w;
+	const float localDepth = cNrm.w;
 	const float4 dd = a.deltaDepth[pixelIdx];
 	const float localDdx = dd.z, localDdy = dd.w;
 	const float sigma = 10.0f * OneOverPow2( phase - 1 );
-	const float factor = (lf.w & 15) == 0 ? 400.0f : 1.0f;
+	const float factor = (lfw & 15) == 0 ? 400.0f : 1.0f;
 	const float4 m = a.moments[pixelIdx];
 	const float var_dir = m.y - m.x * m.x, var_ind = m.w - m.z * m.z;
 	const float rdir = -1.0f / (sigma * factor * sqrtf( var_dir + 0.00001f ) + 0.00001f);
 	const float rind = -1.0f / (sigma * factor * sqrtf( var_ind + 0.00001f ) + 0.00001f);
+#pragma unroll
 	for (int vv = -2; vv <= 2; vv++)
 	{
 		const int v = vv * STEP + y;
 		const int r = abs( vv ) == 2 ? 1 : 2;
-		if (v >= 0 && v < a.h) for (int uu = -r; uu <= r; uu++) if (uu != 0 || vv != 0)
+		if (v >= 0 && v < a.h)
 		{
-			// columns are clamped to the image by the tile loader, like the reference clamps u
-			const int ti = (cx + uu * STEP) + (cy + vv * STEP) * TW;
-			const float4 nc = tShade[ti];
-			const uint4 nf = tFeat[ti];
-			const float w_dist = (uu * uu + vv * vv) * (-1.0f / 7.5f);
-			const float3 nDirect = DirectOf( nc ), nIndirect = IndirectOf( nc );
-			float w_normal = powf( fmaxf( 0.0f, dot( UnpackNormal2( nf.y ), localNormal ) ), 128 );
-			const float expected = localDepth + localDdx * (float)(uu * STEP) + localDdy * (float)(vv * STEP);
-			const float depthError = fabsf( expected - __uint_as_float( nf.z ) );
-			const float expectedDiff = fabsf( expected - localDepth );
-			const float w_depth = depthError / fmaxf( 0.00001f, (0.5f + phase * 0.5f) * expectedDiff );
-			w_normal *= ((int)(nf.w >> 4) != localMatID) ? 0.0001f : dot( localColor, RGB32toHDR( nf.x ) );
-			float wd = w_normal * __expf( fabsf( localDirect - Luminance( nDirect ) ) * rdir + w_dist - w_depth );
-			float wi = w_normal * __expf( fabsf( localIndirect - Luminance( nIndirect ) ) * rind + w_dist - w_depth );
-			if (!isfinite( wd )) wd = 0;
-			if (!isfinite( wi )) wi = 0;
-			dirSum += nDirect * wd, dirW += wd;
-			indSum += nIndirect * wi, indW += wi;
+#pragma unroll
+			for (int uu = -2; uu <= 2; uu++) if (abs( uu ) <= r && (uu != 0 || vv != 0))
+			{
+				// columns are clamped to the image by the tile loader, like the reference clamps u
+				const int ti = (cx + uu * STEP) + (cy + vv * STEP) * TW;
+				const float4 nDir = tDir[ti], nInd = tInd[ti], nNrm = tNrm[ti], nAlb = tAlb[ti];
+				const float w_dist = (uu * uu + vv * vv) * (-1.0f / 7.5f);
+				float w_normal = powf( fmaxf( 0.0f, dot( xyz( nNrm ), localNormal ) ), 128 );
+				const float expected = localDepth + localDdx * (float)(uu * STEP) + localDdy * (float)(vv * STEP);
+				const float depthError = fabsf( expected - nNrm.w );
+				const float expectedDiff = fabsf( expected - localDepth );
+				const float w_depth = depthError / fmaxf( 0.00001f, (0.5f + phase * 0.5f) * expectedDiff );
+				w_normal *= ((int)(__float_as_uint( nAlb.w ) >> 4) != localMatID) ? 0.0001f : dot( localColor, xyz( nAlb ) );
+				float wd = w_normal * __expf( fabsf( localDirect - nDir.w ) * rdir + w_dist - w_depth );
+				float wi = w_normal * __expf( fabsf( localIndirect - nInd.w ) * rind + w_dist - w_depth );
+				if (!isfinite( wd )) wd = 0;
+				if (!isfinite( wi )) wi = 0;
+				dirSum += xyz( nDir ) * wd, dirW += wd;
+				indSum += xyz( nInd ) * wi, indW += wi;
+			}
 		}
 	}
 	float3 dirF = dirSum * (1.0f / fmaxf( 0.0001f, dirW )), indF = indSum * (1.0f / fmaxf( 0.0001f, indW ));
@@ -324,8 +335,8 @@ template <int STEP> __global__ void __launch_bounds__( AT_BX * AT_BY ) atrousKer
 				prevDirect = RGBToYCoCg( prevDirect ), prevIndirect = RGBToYCoCg( prevIndirect );
 				float3 dirAvg = RGBToYCoCg( dirF ), dirVar = dirAvg * dirAvg, indAvg = RGBToYCoCg( indF ), indVar = indAvg * indAvg;
 				auto tap = [&]( const int ox, const int oy ) {
-					const float4 c4 = tShade[(cx + ox) + (cy + oy) * TW];
-					const float3 f = RGBToYCoCg( DirectOf( c4 ) ), g = RGBToYCoCg( IndirectOf( c4 ) );
+					const int ti = (cx + ox) + (cy + oy) * TW;
+					const float3 f = RGBToYCoCg( xyz( tDir[ti] ) ), g = RGBToYCoCg( xyz( tInd[ti] ) );
 					dirAvg += f, dirVar += f * f, indAvg += g, indVar += g * g;
 				};
 				if (x > 1)
@@ -354,7 +365,7 @@ template <int STEP> __global__ void __launch_bounds__( AT_BX * AT_BY ) atrousKer
 	}
 	if (a.lastPass)
 	{
-		const float3 c = (dirF + indF) * RGB32toHDR( lf.x );
+		const float3 c = (dirF + indF) * localColor;
 		a.C[pixelIdx] = make_float4( sqrtf( c.x ), sqrtf( c.y ), sqrtf( c.z ), 1 );
 	}
 	else a.C[pixelIdx] = CombineToFloat4( dirF, indF );
@@ -478,21 +489,24 @@ static void FilterChainImpl( const FilterBuffers& b, const FilterSettings& s, cu
 	AtrousArgs aa;
 	aa.features = b.features, aa.prevWorldPos = b.prevWorldPos, aa.worldPos = b.worldPos, aa.deltaDepth = b.deltaDepth, aa.motion = b.motion, aa.moments = b.moments;
 	aa.w = w, aa.h = h;
-	auto smem = []( int step ) { return (size_t)(AT_BX + 4 * step) * (AT_BY + 4 * step) * 32; };
+	// block heights: 8 rows for step 1, 16 for steps 2 and 4 (amortises the 2 * step halo); 64 bytes of tile per pixel
+	auto smem = []( int step, int by ) { return (size_t)(AT_BX + 4 * step) * (by + 4 * step) * 64; };
 	static bool attr = false;
 	if (!attr)
 	{
-		cudaFuncSetAttribute( atrousKernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem( 4 ) );
+		cudaFuncSetAttribute( atrousKernel<2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem( 2, 16 ) );
+		cudaFuncSetAttribute( atrousKernel<4, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem( 4, 16 ) );
 		attr = true;
 	}
+	const dim3 grid16( (w + 31) / 32, (h + 15) / 16 ), block16( 32, 16 );
 	aa.A = b.shading, aa.B = b.filteredIN, aa.C = b.filteredOUT, aa.phase = 1, aa.lastPass = 0;
-	atrousKernel<1><<<grid, block, smem( 1 ), st>>>( aa );
+	atrousKernel<1, 8><<<grid, block, smem( 1, 8 ), st>>>( aa );
 	snap( hP1, b.filteredOUT );
 	aa.A = b.filteredOUT, aa.B = nullptr, aa.C = b.filteredIN, aa.phase = 2;
-	atrousKernel<2><<<grid, block, smem( 2 ), st>>>( aa );
+	atrousKernel<2, 16><<<grid16, block16, smem( 2, 16 ), st>>>( aa );
 	snap( hP2, b.filteredIN );
 	aa.A = b.filteredIN, aa.C = b.shading, aa.phase = 3, aa.lastPass = 1;
-	atrousKernel<4><<<grid, block, smem( 4 ), st>>>( aa );
+	atrousKernel<4, 16><<<grid16, block16, smem( 4, 16 ), st>>>( aa );
 	snap( hP3, b.shading );
 	if (s.taa)
 	{
