@@ -52,6 +52,22 @@ LH2B_API int lh2b_set_sky( lh2b_core* core, const float* pixels, int width, int 
    vertexData: float4[vertexCount] (3 per triangle, not indexed); triangles: CoreTri[triangleCount]. */
 LH2B_API int lh2b_set_geometry( lh2b_core* core, int meshIdx, const float* vertexData, int vertexCount,
 	int triangleCount, const void* triangles );
+/* The same with DEVICE pointers (e.g. the output of the host's own simulation kernels): device-to-device copies, nothing
+   crosses PCIe. Pointers must be valid on the core's device. */
+LH2B_API int lh2b_set_geometry_device( lh2b_core* core, int meshIdx, const void* dVertexData, int vertexCount,
+	int triangleCount, const void* dTriangles );
+/* Device-side animation: replaces HostMesh::SetPose + the SetGeometry upload that follows it in
+   RenderSystem::UpdateSceneGraph (lib/RenderSystem/host_mesh.cpp:711-741 morph targets, :748-906 skinning). The current
+   geometry of the mesh becomes the bind pose; every later pose call rewrites positions, CoreTri::vertex0..2, vN0..2 (and
+   Nx/Ny/Nz for skinning) on the device and marks the mesh for a refit at the next FinalizeInstances.
+   joints4: uint4 per vertex; weights4: float4 per vertex; jointMatrices16: row-major 4x4 per joint (HostSkin::jointMat).
+   deltas4 / normals4: float4[targetCount][vertexCount] (poses 1..n of HostMesh::poses); weights: one per target. */
+LH2B_API int lh2b_set_skin( lh2b_core* core, int meshIdx, const uint32_t* joints4, const float* weights4, int vertexCount );
+LH2B_API int lh2b_set_pose( lh2b_core* core, int meshIdx, const float* jointMatrices16, int jointCount );
+LH2B_API int lh2b_set_morph_targets( lh2b_core* core, int meshIdx, const float* deltas4, const float* normals4, int targetCount, int vertexCount );
+LH2B_API int lh2b_set_morph_weights( lh2b_core* core, int meshIdx, const float* weights, int targetCount );
+/* Read back the current geometry of a mesh (tests, debugging): float4[3 * triangleCount] and / or CoreTri[triangleCount]. */
+LH2B_API int lh2b_read_geometry( lh2b_core* core, int meshIdx, float* vertexDataOut, void* trianglesOut );
 /* CoreAPI_Base::SetInstance (core_api_base.h:116, rendercore.cpp:346-376). transform: 16 floats row major;
    meshIdx == -1 truncates the instance list at instanceIdx. */
 LH2B_API int lh2b_set_instance( lh2b_core* core, int instanceIdx, int meshIdx, const float* transform );

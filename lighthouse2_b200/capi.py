@@ -26,6 +26,12 @@ SIGNATURES = {
     "lh2b_set_lights": ([_vp, _vp, _ip, _vp, _ip, _vp, _ip, _vp, _ip], _ip),
     "lh2b_set_sky": ([_vp, _vp, _ip, _ip, _vp], _ip),
     "lh2b_set_geometry": ([_vp, _ip, _vp, _ip, _ip, _vp], _ip),
+    "lh2b_set_geometry_device": ([_vp, _ip, _vp, _ip, _ip, _vp], _ip),
+    "lh2b_set_skin": ([_vp, _ip, _vp, _vp, _ip], _ip),
+    "lh2b_set_pose": ([_vp, _ip, _vp, _ip], _ip),
+    "lh2b_set_morph_targets": ([_vp, _ip, _vp, _vp, _ip, _ip], _ip),
+    "lh2b_set_morph_weights": ([_vp, _ip, _vp, _ip], _ip),
+    "lh2b_read_geometry": ([_vp, _ip, _vp, _vp], _ip),
     "lh2b_set_instance": ([_vp, _ip, _ip, _vp], _ip),
     "lh2b_finalize_instances": ([_vp], _ip),
     "lh2b_render": ([_vp, _vp, _ip, _ip], _ip),

@@ -99,6 +99,33 @@ class RenderCore:
         t = None if triangles is None else _arr(triangles, abi.CoreTri)
         self._check(self._lib.lh2b_set_geometry(self._h, mesh_idx, _ptr(v), v.shape[0], tri_count, _ptr(t)))
 
+    def SetGeometryDevice(self, mesh_idx, d_vertex_ptr, tri_count, d_triangles_ptr=None):
+        """SetGeometry from device pointers (ints): float4[3 * tri_count] and optionally CoreTri[tri_count]."""
+        self._check(self._lib.lh2b_set_geometry_device(self._h, mesh_idx, ctypes.c_void_p(d_vertex_ptr), 3 * tri_count, tri_count,
+                                                       ctypes.c_void_p(d_triangles_ptr) if d_triangles_ptr else None))
+
+    def SetSkin(self, mesh_idx, joints4, weights4):
+        j, w = _arr(joints4, np.uint32).reshape(-1, 4), _arr(weights4, np.float32).reshape(-1, 4)
+        self._check(self._lib.lh2b_set_skin(self._h, mesh_idx, _ptr(j), _ptr(w), j.shape[0]))
+
+    def SetPose(self, mesh_idx, joint_matrices):
+        m = _arr(joint_matrices, np.float32).reshape(-1, 16)
+        self._check(self._lib.lh2b_set_pose(self._h, mesh_idx, _ptr(m), m.shape[0]))
+
+    def SetMorphTargets(self, mesh_idx, deltas4, normals4):
+        d, n = _arr(deltas4, np.float32), _arr(normals4, np.float32)
+        targets, verts = d.shape[0], d.shape[1]
+        self._check(self._lib.lh2b_set_morph_targets(self._h, mesh_idx, _ptr(d), _ptr(n), targets, verts))
+
+    def SetMorphWeights(self, mesh_idx, weights):
+        w = _arr(weights, np.float32)
+        self._check(self._lib.lh2b_set_morph_weights(self._h, mesh_idx, _ptr(w), w.shape[0]))
+
+    def ReadGeometry(self, mesh_idx, tri_count):
+        v, t = np.empty((3 * tri_count, 4), np.float32), np.empty(tri_count, abi.CoreTri)
+        self._check(self._lib.lh2b_read_geometry(self._h, mesh_idx, _ptr(v), _ptr(t)))
+        return v, t
+
     def SetInstance(self, instance_idx, mesh_idx, transform=None):
         m = _arr(np.eye(4) if transform is None else transform, np.float32)
         self._check(self._lib.lh2b_set_instance(self._h, instance_idx, mesh_idx, _ptr(m)))

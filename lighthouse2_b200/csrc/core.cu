@@ -302,6 +302,123 @@ int lh2b_set_geometry( lh2b_core* core, int meshIdx, const float* vertexData, in
 	API_END
 }
 
+int lh2b_set_geometry_device( lh2b_core* core, int meshIdx, const void* dVertexData, int vertexCount, int triangleCount, const void* dTriangles )
+{
+	API_BEGIN
+	if (meshIdx < 0 || meshIdx > (int)core->meshes.size()) throw CoreError( "SetGeometry: meshes must be introduced in sequential order" );
+	if (vertexCount != triangleCount * 3) throw CoreError( "SetGeometry: vertexCount must be 3 * triangleCount" );
+	if (meshIdx == (int)core->meshes.size()) core->meshes.emplace_back( new Mesh() );
+	Mesh& mesh = *core->meshes[meshIdx];
+	mesh.triCount = triangleCount;
+	mesh.verts.Resize( (size_t)vertexCount );
+	CUDA_CHECK( cudaMemcpyAsync( mesh.verts.ptr, dVertexData, (size_t)vertexCount * 16, cudaMemcpyDeviceToDevice, core->stream ) );
+	if (dTriangles)
+	{
+		mesh.coreTris.Resize( (size_t)triangleCount * 13 );
+		CUDA_CHECK( cudaMemcpyAsync( mesh.coreTris.ptr, dTriangles, (size_t)triangleCount * 208, cudaMemcpyDeviceToDevice, core->stream ) );
+	}
+	if (core->bvhBuilder == 1)
+	{
+		mesh.hostVerts.resize( (size_t)vertexCount * 4 );
+		CUDA_CHECK( cudaMemcpyAsync( mesh.hostVerts.data(), mesh.verts.ptr, (size_t)vertexCount * 16, cudaMemcpyDeviceToHost, core->stream ) );
+		CUDA_CHECK( cudaStreamSynchronize( core->stream ) );
+	}
+	CUDA_CHECK( cudaStreamSynchronize( core->stream ) );	// the caller may reuse its device buffers on return
+	mesh.dirty = true;
+	API_END
+}
+
+static Mesh& AnimatedMesh( lh2b_core* core, int meshIdx, const char* what )
+{
+	if (meshIdx < 0 || meshIdx >= (int)core->meshes.size()) throw CoreError( std::string( what ) + ": unknown mesh" );
+	Mesh& mesh = *core->meshes[meshIdx];
+	if (mesh.coreTris.count != (size_t)mesh.triCount * 13 || mesh.triCount == 0) throw CoreError( std::string( what ) + ": the mesh needs SetGeometry with triangle records first" );
+	return mesh;
+}
+
+static void CaptureBindPose( lh2b_core* core, Mesh& mesh )
+{
+	const size_t n = (size_t)mesh.triCount * 3;
+	mesh.bindVerts.Resize( n ), mesh.bindNormals.Resize( n );
+	CUDA_CHECK( cudaMemcpyAsync( mesh.bindVerts.ptr, mesh.verts.ptr, n * 16, cudaMemcpyDeviceToDevice, core->stream ) );
+	LaunchCaptureBindPose( mesh.coreTris.ptr, mesh.bindNormals.ptr, mesh.triCount, core->stream );
+}
+
+static void AfterPose( lh2b_core* core, Mesh& mesh )
+{
+	if (core->bvhBuilder == 1)
+	{
+		mesh.hostVerts.resize( (size_t)mesh.triCount * 12 );
+		CUDA_CHECK( cudaMemcpyAsync( mesh.hostVerts.data(), mesh.verts.ptr, (size_t)mesh.triCount * 48, cudaMemcpyDeviceToHost, core->stream ) );
+		CUDA_CHECK( cudaStreamSynchronize( core->stream ) );
+	}
+	CUDA_CHECK( cudaGetLastError() );
+	mesh.dirty = true;	// same triangle count: FinalizeInstances refits
+}
+
+int lh2b_set_skin( lh2b_core* core, int meshIdx, const uint32_t* joints4, const float* weights4, int vertexCount )
+{
+	API_BEGIN
+	Mesh& mesh = AnimatedMesh( core, meshIdx, "SetSkin" );
+	if (vertexCount != mesh.triCount * 3) throw CoreError( "SetSkin: one joint quadruple and one weight quadruple per vertex (3 per triangle)" );
+	mesh.skinJoints.Upload( (const uint4*)joints4, (size_t)vertexCount, core->stream );
+	mesh.skinWeights.Upload( (const float4*)weights4, (size_t)vertexCount, core->stream );
+	CaptureBindPose( core, mesh );
+	CUDA_CHECK( cudaStreamSynchronize( core->stream ) );
+	API_END
+}
+
+int lh2b_set_pose( lh2b_core* core, int meshIdx, const float* jointMatrices16, int jointCount )
+{
+	API_BEGIN
+	Mesh& mesh = AnimatedMesh( core, meshIdx, "SetPose" );
+	if (mesh.skinJoints.count != (size_t)mesh.triCount * 3) throw CoreError( "SetPose: call SetSkin first" );
+	if (jointCount <= 0) throw CoreError( "SetPose: no joints" );
+	mesh.jointMats.Upload( (const float4*)jointMatrices16, (size_t)jointCount * 4, core->stream );
+	LaunchSkin( mesh.bindVerts.ptr, mesh.bindNormals.ptr, mesh.skinJoints.ptr, mesh.skinWeights.ptr, mesh.jointMats.ptr, jointCount,
+		mesh.verts.ptr, mesh.coreTris.ptr, mesh.triCount, core->stream );
+	CUDA_CHECK( cudaStreamSynchronize( core->stream ) );	// the matrix array was the copy source
+	AfterPose( core, mesh );
+	API_END
+}
+
+int lh2b_set_morph_targets( lh2b_core* core, int meshIdx, const float* deltas4, const float* normals4, int targetCount, int vertexCount )
+{
+	API_BEGIN
+	Mesh& mesh = AnimatedMesh( core, meshIdx, "SetMorphTargets" );
+	if (vertexCount != mesh.triCount * 3 || targetCount <= 0) throw CoreError( "SetMorphTargets: targetCount arrays of 3 * triangleCount float4 each" );
+	mesh.morphDeltas.Upload( (const float4*)deltas4, (size_t)targetCount * vertexCount, core->stream );
+	mesh.morphNormals.Upload( (const float4*)normals4, (size_t)targetCount * vertexCount, core->stream );
+	mesh.morphTargets = targetCount;
+	CaptureBindPose( core, mesh );
+	CUDA_CHECK( cudaStreamSynchronize( core->stream ) );
+	API_END
+}
+
+int lh2b_set_morph_weights( lh2b_core* core, int meshIdx, const float* weights, int targetCount )
+{
+	API_BEGIN
+	Mesh& mesh = AnimatedMesh( core, meshIdx, "SetMorphWeights" );
+	if (mesh.morphTargets == 0 || targetCount != mesh.morphTargets) throw CoreError( "SetMorphWeights: one weight per target of SetMorphTargets" );
+	mesh.morphWeights.Upload( weights, (size_t)targetCount, core->stream );
+	LaunchMorph( mesh.bindVerts.ptr, mesh.bindNormals.ptr, mesh.morphDeltas.ptr, mesh.morphNormals.ptr, mesh.morphWeights.ptr, targetCount,
+		mesh.verts.ptr, mesh.coreTris.ptr, mesh.triCount, core->stream );
+	CUDA_CHECK( cudaStreamSynchronize( core->stream ) );
+	AfterPose( core, mesh );
+	API_END
+}
+
+int lh2b_read_geometry( lh2b_core* core, int meshIdx, float* vertexDataOut, void* trianglesOut )
+{
+	API_BEGIN
+	if (meshIdx < 0 || meshIdx >= (int)core->meshes.size()) throw CoreError( "ReadGeometry: unknown mesh" );
+	Mesh& mesh = *core->meshes[meshIdx];
+	if (vertexDataOut) CUDA_CHECK( cudaMemcpyAsync( vertexDataOut, mesh.verts.ptr, (size_t)mesh.triCount * 48, cudaMemcpyDeviceToHost, core->stream ) );
+	if (trianglesOut && mesh.coreTris.count) CUDA_CHECK( cudaMemcpyAsync( trianglesOut, mesh.coreTris.ptr, (size_t)mesh.triCount * 208, cudaMemcpyDeviceToHost, core->stream ) );
+	CUDA_CHECK( cudaStreamSynchronize( core->stream ) );
+	API_END
+}
+
 int lh2b_set_instance( lh2b_core* core, int instanceIdx, int meshIdx, const float* transform )
 {
 	API_BEGIN

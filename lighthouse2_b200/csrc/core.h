@@ -38,6 +38,13 @@ struct Mesh
 	DevBuf<uint32_t> devCounts;		// node count, leaf count, overflow flag of the last build
 	bool hasTopology = false;
 	int builtTriCount = -1;
+	// device-side animation (skin_kernels.cu): bind pose captured by lh2b_set_skin / lh2b_set_morph_targets
+	DevBuf<float4> bindVerts, bindNormals;	// 3 per triangle
+	DevBuf<uint4> skinJoints;
+	DevBuf<float4> skinWeights, jointMats;
+	DevBuf<float4> morphDeltas, morphNormals;	// [target][vertex]
+	DevBuf<float> morphWeights;
+	int morphTargets = 0;
 };
 
 struct Instance { int mesh = 0; float xform[12] = { 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0 }; };

@@ -36,6 +36,12 @@ struct FilterSettings
 void LaunchFilterChain( const FilterBuffers& b, const FilterSettings& s, cudaStream_t st );
 void LaunchFilterChainStaged( const FilterBuffers& b, const FilterSettings& s, cudaStream_t st, float* hPrepare, float* hP1, float* hP2, float* hP3 );
 void LaunchTagTriangles( float4* tris, int triCount, uint32_t inst, cudaStream_t s );
+// skin_kernels.cu
+void LaunchCaptureBindPose( const float4* coreTris, float4* bindNormals, int triCount, cudaStream_t s );
+void LaunchSkin( const float4* bindVerts, const float4* bindNormals, const uint4* joints, const float4* weights, const float4* jointMats, int jointCount,
+	float4* verts, float4* coreTris, int triCount, cudaStream_t s );
+void LaunchMorph( const float4* bindVerts, const float4* bindNormals, const float4* deltas, const float4* normals, const float* weights, int targetCount,
+	float4* verts, float4* coreTris, int triCount, cudaStream_t s );
 void LaunchFinalize( const float4* accumulator, float4* out, int n, int samplesTaken, cudaStream_t s );
 
 } // namespace lh2b

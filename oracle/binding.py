@@ -379,3 +379,32 @@ def ref_filter_gpu(inputs, settings):
     if rc != 0:
         raise RuntimeError("reffilter_run failed")
     return outs
+
+
+def _bind_normals(tris):
+    """float4 per vertex: vN0..2 (+ the N component riding in w) of every CoreTri, as the skinning code sees them."""
+    t = np.ascontiguousarray(tris).view(np.float32).reshape(-1, 52)
+    return np.ascontiguousarray(t[:, 8:20].reshape(-1, 4))
+
+
+def skin_mesh(verts, tris, joints4, weights4, joint_matrices):
+    """HostMesh::SetPose( HostSkin ) on the CPU (oracle/lh2_oracle_anim.h). Returns (verts, CoreTri array) of the posed mesh."""
+    v0 = np.ascontiguousarray(verts, np.float32).reshape(-1, 4)
+    out_v, out_t = v0.copy(), np.ascontiguousarray(tris).copy()
+    bn = _bind_normals(tris)
+    j, w = np.ascontiguousarray(joints4, np.uint32), np.ascontiguousarray(weights4, np.float32)
+    m = np.ascontiguousarray(joint_matrices, np.float32).reshape(-1, 16)
+    P = lambda a: ctypes.c_void_p(a.ctypes.data)
+    lib().orc_skin_mesh(P(v0), P(bn), P(j), P(w), P(m), len(out_t), P(out_v), P(out_t))
+    return out_v, out_t
+
+
+def morph_mesh(verts, tris, deltas4, normals4, weights):
+    """HostMesh::SetPose( weights ) on the CPU."""
+    v0 = np.ascontiguousarray(verts, np.float32).reshape(-1, 4)
+    out_v, out_t = v0.copy(), np.ascontiguousarray(tris).copy()
+    bn = _bind_normals(tris)
+    d, n, w = (np.ascontiguousarray(a, np.float32) for a in (deltas4, normals4, weights))
+    P = lambda a: ctypes.c_void_p(a.ctypes.data)
+    lib().orc_morph_mesh(P(v0), P(bn), P(d), P(n), P(w), len(w), len(out_t), P(out_v), P(out_t))
+    return out_v, out_t

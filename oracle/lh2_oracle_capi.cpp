@@ -52,6 +52,7 @@ ORC_API void orc_occluded( const orc::Mesh* meshes, int meshCount, const orc::In
 
 /* ---- full frame ---------------------------------------------------------------------------- */
 #include "lh2_oracle_render.h"
+#include "lh2_oracle_anim.h"
 
 struct OrcMaterialIn
 {
@@ -311,4 +312,16 @@ ORC_API void orc_shade_paths( const OrcFrameIn* inp, int pathLength, int n, cons
 		}
 	} );
 	ctx.sc.geo.Release();
+}
+
+/* mesh animation (lh2_oracle_anim.h) */
+ORC_API void orc_skin_mesh( const float* bindVerts, const float* bindNormals, const uint32_t* joints, const float* weights, const float* jointMats,
+	int triCount, float* verts, float* tris )
+{
+	orc::SkinMesh( bindVerts, bindNormals, joints, weights, jointMats, triCount, verts, tris );
+}
+ORC_API void orc_morph_mesh( const float* bindVerts, const float* bindNormals, const float* deltas, const float* normals, const float* w, int targetCount,
+	int triCount, float* verts, float* tris )
+{
+	orc::MorphMesh( bindVerts, bindNormals, deltas, normals, w, targetCount, triCount, verts, tris );
 }

@@ -62,3 +62,28 @@ def test_white_furnace_floor_under_constant_sky():
     np.testing.assert_allclose(img[..., :3], np.broadcast_to(want, img[..., :3].shape), rtol=2e-4)
     assert o.ray_counts[0] == 2 * W * H * 2   # every path: primary + one bounce that escapes
     assert o.ray_counts[1] == 0                # no lights: no shadow rays
+
+
+def test_skinning_restatement_known_answers():
+    """host_mesh.cpp:884-904 on cases with closed-form answers: identity joints leave the mesh unchanged; one rigid joint
+    moves positions by M and normals by its rotation; two joints at half weight blend the matrices (not the results)."""
+    v = scenes.quad((0, 0, 0), (0, 1, 0), 2.0, 2.0)
+    t = scenes.core_tris_from_verts(v)
+    n = v.reshape(-1, 4).shape[0]
+    ident = np.eye(4, dtype=np.float32)[None]
+    j0, w0 = np.zeros((n, 4), np.uint32), np.tile(np.array([1, 0, 0, 0], np.float32), (n, 1))
+    gv, gt = orc.skin_mesh(v, t, j0, w0, ident)
+    assert np.allclose(gv[:, :3], v.reshape(-1, 4)[:, :3], atol=1e-7) and np.allclose(gt.view(np.float32), t.view(np.float32), atol=1e-6, equal_nan=True)
+    a = 0.5
+    R = np.eye(4, dtype=np.float32); R[0, 0], R[0, 1], R[1, 0], R[1, 1] = np.cos(a), -np.sin(a), np.sin(a), np.cos(a); R[:3, 3] = (1, 2, 3)
+    gv, gt = orc.skin_mesh(v, t, j0, w0, R[None])
+    pts = v.reshape(-1, 4).copy(); pts[:, 3] = 1
+    want = (R @ pts.T).T
+    assert np.allclose(gv[:, :3], want[:, :3], atol=1e-6)
+    f = gt.view(np.float32).reshape(-1, 52)
+    assert np.allclose(f[:, 8:11], np.tile(R[:3, :3] @ np.array([0, 1, 0], np.float32), (len(t), 1)), atol=1e-6)      # vN0
+    assert np.allclose(np.stack([f[:, 11], f[:, 15], f[:, 19]], 1), np.tile(R[:3, :3] @ np.array([0, 1, 0], np.float32), (len(t), 1)), atol=1e-6)  # N
+    T2 = np.eye(4, dtype=np.float32); T2[:3, 3] = (0, 4, 0)
+    j1 = np.tile(np.array([0, 1, 0, 0], np.uint32), (n, 1)); w1 = np.tile(np.array([0.5, 0.5, 0, 0], np.float32), (n, 1))
+    gv, _ = orc.skin_mesh(v, t, j1, w1, np.stack([np.eye(4, dtype=np.float32), T2]))
+    assert np.allclose(gv[:, 1], v.reshape(-1, 4)[:, 1] + 2.0, atol=1e-6)
