@@ -69,17 +69,23 @@ __global__ void triBoundsKernel( const float4* __restrict__ verts, const int n, 
 		b = make_float3( fmaxf( v0.x, fmaxf( v1.x, v2.x ) ), fmaxf( v0.y, fmaxf( v1.y, v2.y ) ), fmaxf( v0.z, fmaxf( v1.z, v2.z ) ) );
 		lo[i] = make_float4( a.x, a.y, a.z, 0 ), hi[i] = make_float4( b.x, b.y, b.z, 0 );
 	}
-	// warp reduce, one atomic set per warp
+	// warp reduce, then one atomic set per block (six atomics per warp serialised on one L2 line: 127 us for 1 M triangles)
 	for (int o = 16; o > 0; o >>= 1)
 	{
 		a.x = fminf( a.x, __shfl_xor_sync( 0xffffffffu, a.x, o ) ), a.y = fminf( a.y, __shfl_xor_sync( 0xffffffffu, a.y, o ) ), a.z = fminf( a.z, __shfl_xor_sync( 0xffffffffu, a.z, o ) );
 		b.x = fmaxf( b.x, __shfl_xor_sync( 0xffffffffu, b.x, o ) ), b.y = fmaxf( b.y, __shfl_xor_sync( 0xffffffffu, b.y, o ) ), b.z = fmaxf( b.z, __shfl_xor_sync( 0xffffffffu, b.z, o ) );
 	}
-	if ((threadIdx.x & 31) == 0)
+	__shared__ float red[8][6];
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	if (lane == 0) red[warp][0] = a.x, red[warp][1] = a.y, red[warp][2] = a.z, red[warp][3] = b.x, red[warp][4] = b.y, red[warp][5] = b.z;
+	__syncthreads();
+	if (threadIdx.x < 6)
 	{
+		float v = red[0][threadIdx.x];
+		const int warps = (blockDim.x + 31) >> 5;
+		for (int w = 1; w < warps; w++) v = threadIdx.x < 3 ? fminf( v, red[w][threadIdx.x] ) : fmaxf( v, red[w][threadIdx.x] );
 		int* box = (int*)(ctrl + 3);
-		atomicMin( box + 0, FloatOrdered( a.x ) ), atomicMin( box + 1, FloatOrdered( a.y ) ), atomicMin( box + 2, FloatOrdered( a.z ) );
-		atomicMax( box + 3, FloatOrdered( b.x ) ), atomicMax( box + 4, FloatOrdered( b.y ) ), atomicMax( box + 5, FloatOrdered( b.z ) );
+		if (threadIdx.x < 3) atomicMin( box + threadIdx.x, FloatOrdered( v ) ); else atomicMax( box + threadIdx.x, FloatOrdered( v ) );
 	}
 }
 
@@ -226,6 +232,7 @@ struct CollapseArgs
 	BuildTask* queue; uint32_t* ctrl;
 	float4* boundsOut;				// [0] = lo, [1] = hi of the root (kept on the device for the top-level build)
 	uint32_t* countsOut;			// [0] node count, [1] leaf count, [2] overflow flag
+	int* wideChild; int* wideSelf;	// BLAS: binary-tree node behind every slot of every wide node / behind the node itself (for refits)
 };
 
 __device__ __forceinline__ float HalfAreaD( const float4 lo, const float4 hi )
@@ -287,6 +294,11 @@ __device__ void CollapseTask( const CollapseArgs& a, const BuildTask task )
 			}
 			slotChild[bs] = child[bi], slotUsed |= 1u << bs, childDone |= 1u << bi;
 		}
+	}
+	if (a.wideChild)
+	{
+		a.wideSelf[task.cwNode] = root;
+		for (int s = 0; s < 8; s++) a.wideChild[(size_t)task.cwNode * 8 + s] = slotChild[s];
 	}
 	// counts and allocation
 	int internalCount = 0, leafPrims = 0;
@@ -411,6 +423,66 @@ __global__ void __launch_bounds__( 128 ) collapseKernel( const CollapseArgs a )
 	if (tid == 0 && a.countsOut) a.countsOut[0] = a.ctrl[0], a.countsOut[1] = a.ctrl[1], a.countsOut[2] = a.ctrl[9];
 }
 
+
+/* ---- refit of the wide tree in place -------------------------------------------------------------------------------
+   After the binary tree has been refitted (fitKernel over the kept topology) every wide node is independent: its frame
+   (origin, exponents) comes from the box of the binary node it was collapsed from, its eight quantised child boxes from the
+   binary nodes recorded per slot at collapse time. Child links, triangle ranges, meta bytes and the octant slot order stay.
+   Triangle records are rewritten from the new vertices; the primitive index and the instance tag they carry stay. */
+__global__ void __launch_bounds__( 128 ) requantKernel( const int nodeCount, const int* __restrict__ wideChild, const int* __restrict__ wideSelf,
+	const float4* __restrict__ nodeLo, const float4* __restrict__ nodeHi, uint4* __restrict__ outNodes, float4* __restrict__ boundsOut )
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= nodeCount) return;
+	const int self = wideSelf[i];
+	const float4 rlo = nodeLo[self], rhi = nodeHi[self];
+	if (i == 0 && boundsOut) boundsOut[0] = rlo, boundsOut[1] = rhi;
+	float quantum[3];
+	uint32_t e[3];
+	const float ext[3] = { rhi.x - rlo.x, rhi.y - rlo.y, rhi.z - rlo.z }, p[3] = { rlo.x, rlo.y, rlo.z };
+	for (int k = 0; k < 3; k++)
+	{
+		int ex = ext[k] > 0 ? (int)ceilf( log2f( ext[k] / 255.0f ) ) : -126;
+		ex = max( -126, min( 127, ex ) );
+		while (ex < 127 && ldexpf( 255.0f, ex ) < ext[k]) ex++;
+		e[k] = (uint32_t)(ex + 127), quantum[k] = ldexpf( 1.0f, ex );
+	}
+	uint32_t q[6][2] = { { 0, 0 }, { 0, 0 }, { 0, 0 }, { 0, 0 }, { 0, 0 }, { 0, 0 } };	// [lo x,y,z, hi x,y,z][slots 0-3, 4-7]
+	for (int s = 0; s < 8; s++)
+	{
+		const int c = wideChild[(size_t)i * 8 + s];
+		if (c < 0) continue;
+		const float4 clo = nodeLo[c], chi = nodeHi[c];
+		const float cl[3] = { clo.x, clo.y, clo.z }, ch[3] = { chi.x, chi.y, chi.z };
+		for (int k = 0; k < 3; k++)
+		{
+			int ql = (int)floorf( (cl[k] - p[k]) / quantum[k] ), qh = (int)ceilf( (ch[k] - p[k]) / quantum[k] );
+			ql = max( 0, min( 255, ql ) ), qh = max( 0, min( 255, qh ) );
+			while (ql > 0 && p[k] + ql * quantum[k] > cl[k]) ql--;
+			while (qh < 255 && p[k] + qh * quantum[k] < ch[k]) qh++;
+			q[k][s >> 2] |= (uint32_t)ql << (8 * (s & 3)), q[3 + k][s >> 2] |= (uint32_t)qh << (8 * (s & 3));
+		}
+	}
+	uint4* out = outNodes + (size_t)i * 5;
+	const uint32_t imask = out[0].w >> 24;
+	out[0] = make_uint4( __float_as_uint( p[0] ), __float_as_uint( p[1] ), __float_as_uint( p[2] ), e[0] | (e[1] << 8) | (e[2] << 16) | (imask << 24) );
+	out[2] = make_uint4( q[0][0], q[0][1], q[1][0], q[1][1] );
+	out[3] = make_uint4( q[2][0], q[2][1], q[3][0], q[3][1] );
+	out[4] = make_uint4( q[4][0], q[4][1], q[5][0], q[5][1] );
+}
+
+__global__ void triRewriteKernel( const int n, const float4* __restrict__ verts, float4* __restrict__ outTris )
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	float4* t = outTris + (size_t)i * 3;
+	const uint32_t prim = __float_as_uint( t[0].w );
+	const float tag = t[1].w;
+	const float4 v0 = verts[prim * 3], v1 = verts[prim * 3 + 1], v2 = verts[prim * 3 + 2];
+	t[0] = make_float4( v0.x, v0.y, v0.z, __uint_as_float( prim ) );
+	t[1] = make_float4( v1.x - v0.x, v1.y - v0.y, v1.z - v0.z, tag );
+	t[2] = make_float4( v2.x - v0.x, v2.y - v0.y, v2.z - v0.z, 0 );
+}
 
 /* ---- stage 4': PLOC (parallel locally-ordered clustering, Meister & Bittner 2018) instead of the radix tree ------------
    Clusters start as the Morton-sorted leaves. Each round every cluster looks PLOC_RADIUS positions left and right for the
@@ -574,7 +646,7 @@ static int CollapseGrid( lh2b_core* core )
 
 /* Shared tail of BLAS and TLAS builds: stages 2-6 over n primitive boxes already in scratch.primLo/primHi.
    sortTopology = false: keep the sorted order and the radix tree of the previous build (refit). */
-static void BuildFromBoxes( lh2b_core* core, GpuBuildScratch& s, const int n, const bool sortTopology, const bool usePloc, CollapseArgs args )
+static void BuildFromBoxes( lh2b_core* core, GpuBuildScratch& s, const int n, const bool sortTopology, const bool usePloc, CollapseArgs args, const bool keepWideTree = false, const int wideNodes = 0 )
 {
 	cudaStream_t st = core->stream;
 	const int blocks = (n + 255) / 256;
@@ -593,6 +665,13 @@ static void BuildFromBoxes( lh2b_core* core, GpuBuildScratch& s, const int n, co
 	else if (n > 1) resetVisitKernel<<<blocks, 256, 0, st>>>( s.visit.ptr, n - 1 );
 	s.nodeLo.Resize( 2 * n ), s.nodeHi.Resize( 2 * n );
 	fitKernel<<<blocks, 256, 0, st>>>( s.primLo.ptr, s.primHi.ptr, s.idxAlt.ptr, n, s.children.ptr, s.parent.ptr, s.visit.ptr, s.nodeLo.ptr, s.nodeHi.ptr );
+	if (keepWideTree)
+	{
+		requantKernel<<<(wideNodes + 127) / 128, 128, 0, st>>>( wideNodes, args.wideChild, args.wideSelf, s.nodeLo.ptr, s.nodeHi.ptr,
+			args.outNodes + (size_t)args.nodeOffset * 5, args.boundsOut );
+		triRewriteKernel<<<blocks, 256, 0, st>>>( n, args.verts, args.outTris + (size_t)args.triOffset * 3 );
+		return;
+	}
 	s.queue.Resize( (size_t)n + 8 );
 	args.n = n, args.children = s.children.ptr, args.subtree = s.subtree.ptr, args.nodeLo = s.nodeLo.ptr, args.nodeHi = s.nodeHi.ptr;
 	args.idx = s.idxAlt.ptr, args.queue = s.queue.ptr, args.ctrl = s.ctrl.ptr;
@@ -627,7 +706,7 @@ static void BuildPloc( lh2b_core* core, GpuBuildScratch& s, const int n )
 
 /* BLAS build (or refit) of one mesh from its device-resident vertices. Per-mesh topology (sorted order + radix tree) is
    kept in the mesh so that a later SetGeometry with the same triangle count can refit. */
-void GpuBuildMesh( lh2b_core* core, Mesh& mesh, const bool refit )
+void GpuBuildMesh( lh2b_core* core, Mesh& mesh, const int refit )
 {
 	GpuBuildScratch& s = Scratch( core );
 	cudaStream_t st = core->stream;
@@ -651,7 +730,10 @@ void GpuBuildMesh( lh2b_core* core, Mesh& mesh, const bool refit )
 	a.maxLeaf = core->bvhMaxLeaf, a.verts = mesh.verts.ptr, a.outNodes = core->arenaNodes.ptr, a.outTris = core->arenaTris.ptr;
 	a.nodeOffset = mesh.nodeOff, a.triOffset = mesh.triOff, a.nodeCapacity = mesh.nodeCap, a.triCapacity = mesh.triCap;
 	a.boundsOut = mesh.devBounds.ptr, a.countsOut = mesh.devCounts.ptr;
-	BuildFromBoxes( core, s, n, !refit, core->bvhBuilder != 2, a );
+	if (mesh.topoWideSelf.count < mesh.nodeCap) mesh.topoWideSelf.Resize( mesh.nodeCap ), mesh.topoWideChild.Resize( (size_t)mesh.nodeCap * 8 );
+	a.wideChild = mesh.topoWideChild.ptr, a.wideSelf = mesh.topoWideSelf.ptr;
+	// refit 0: full build | 1: binary-tree refit + requantisation of the wide tree in place | 2: binary-tree refit + new collapse
+	BuildFromBoxes( core, s, n, refit == 0, core->bvhBuilder != 2, a, refit == 1, (int)mesh.nodeCount );
 	s.idxAlt.Swap( mesh.topoIdx ), s.children.Swap( mesh.topoChildren ), s.subtree.Swap( mesh.topoSubtree );
 	s.parent.Swap( mesh.topoParent ), s.visit.Swap( mesh.topoVisit );
 }

@@ -48,7 +48,7 @@ static bool IsIdentity( const float* m )
 	return memcmp( m, id, sizeof( id ) ) == 0;
 }
 
-void GpuBuildMesh( lh2b_core* core, Mesh& mesh, const bool refit );
+void GpuBuildMesh( lh2b_core* core, Mesh& mesh, const int refit );
 void GpuBuildTlas( lh2b_core* core, const void* dInstIn, const int n, const uint32_t* dLinkedRoots );
 void ReleaseGpuBuildScratch( lh2b_core* core );
 
@@ -116,14 +116,25 @@ static void RebuildMeshHost( lh2b_core* core, Mesh& mesh )
    node slot overflowed (the caller grows it and retries). */
 static void RebuildMeshGpu( lh2b_core* core, Mesh& mesh )
 {
-	const bool refit = core->bvhRefit && mesh.hasTopology && mesh.builtTriCount == mesh.triCount;
+	const int refit = (core->bvhRefit && mesh.hasTopology && mesh.builtTriCount == mesh.triCount && mesh.triCount > 0) ? core->bvhRefit : 0;
+	if (!mesh.evStart) { CUDA_CHECK( cudaEventCreate( &mesh.evStart ) ); CUDA_CHECK( cudaEventCreate( &mesh.evEnd ) ); }
+	if (refit == 1)
+	{
+		// in-place refit: node and triangle counts cannot change, so nothing is read back and the host does not wait
+		CUDA_CHECK( cudaEventRecord( mesh.evStart, core->stream ) );
+		GpuBuildMesh( core, mesh, 1 );
+		CUDA_CHECK( cudaEventRecord( mesh.evEnd, core->stream ) );
+		CUDA_CHECK( cudaGetLastError() );
+		mesh.timingPending = true, mesh.dirty = false;
+		return;
+	}
 	uint32_t nodeGuess = std::max( mesh.nodeCap, (uint32_t)(mesh.triCount / 2 + 64) );
 	for (int attempt = 0; attempt < 4; attempt++)
 	{
 		EnsureMeshSlots( core, mesh, nodeGuess, (uint32_t)std::max( mesh.triCount, 1 ) );
-		CUDA_CHECK( cudaEventRecord( core->evA, core->stream ) );
+		CUDA_CHECK( cudaEventRecord( mesh.evStart, core->stream ) );
 		GpuBuildMesh( core, mesh, refit );
-		CUDA_CHECK( cudaEventRecord( core->evB, core->stream ) );
+		CUDA_CHECK( cudaEventRecord( mesh.evEnd, core->stream ) );
 		uint32_t counts[4] = { 0, 0, 0, 0 };
 		CUDA_CHECK( cudaMemcpyAsync( counts, mesh.devCounts.ptr, 16, cudaMemcpyDeviceToHost, core->stream ) );
 		CUDA_CHECK( cudaStreamSynchronize( core->stream ) );
@@ -131,7 +142,8 @@ static void RebuildMeshGpu( lh2b_core* core, Mesh& mesh )
 		if (counts[2] == 0)
 		{
 			mesh.nodeCount = mesh.triCount ? counts[0] : 1;
-			CUDA_CHECK( cudaEventElapsedTime( &mesh.buildMs, core->evA, core->evB ) );
+			CUDA_CHECK( cudaEventElapsedTime( &mesh.buildMs, mesh.evStart, mesh.evEnd ) );
+			mesh.timingPending = false;
 			mesh.hasTopology = mesh.triCount > 0, mesh.builtTriCount = mesh.triCount, mesh.taggedInst = 0, mesh.dirty = false;
 			return;
 		}
@@ -374,10 +386,12 @@ int lh2b_set_pose( lh2b_core* core, int meshIdx, const float* jointMatrices16, i
 	Mesh& mesh = AnimatedMesh( core, meshIdx, "SetPose" );
 	if (mesh.skinJoints.count != (size_t)mesh.triCount * 3) throw CoreError( "SetPose: call SetSkin first" );
 	if (jointCount <= 0) throw CoreError( "SetPose: no joints" );
-	mesh.jointMats.Upload( (const float4*)jointMatrices16, (size_t)jointCount * 4, core->stream );
+	// the matrices go through a pageable copy owned by the mesh: cudaMemcpyAsync stages pageable memory before it returns, so the
+	// caller's array is free on return and the host never waits for the device here
+	mesh.hostJointMats.assign( jointMatrices16, jointMatrices16 + (size_t)jointCount * 16 );
+	mesh.jointMats.Upload( (const float4*)mesh.hostJointMats.data(), (size_t)jointCount * 4, core->stream );
 	LaunchSkin( mesh.bindVerts.ptr, mesh.bindNormals.ptr, mesh.skinJoints.ptr, mesh.skinWeights.ptr, mesh.jointMats.ptr, jointCount,
 		mesh.verts.ptr, mesh.coreTris.ptr, mesh.triCount, core->stream );
-	CUDA_CHECK( cudaStreamSynchronize( core->stream ) );	// the matrix array was the copy source
 	AfterPose( core, mesh );
 	API_END
 }
@@ -400,10 +414,10 @@ int lh2b_set_morph_weights( lh2b_core* core, int meshIdx, const float* weights, 
 	API_BEGIN
 	Mesh& mesh = AnimatedMesh( core, meshIdx, "SetMorphWeights" );
 	if (mesh.morphTargets == 0 || targetCount != mesh.morphTargets) throw CoreError( "SetMorphWeights: one weight per target of SetMorphTargets" );
-	mesh.morphWeights.Upload( weights, (size_t)targetCount, core->stream );
+	mesh.hostJointMats.assign( weights, weights + targetCount );
+	mesh.morphWeights.Upload( mesh.hostJointMats.data(), (size_t)targetCount, core->stream );
 	LaunchMorph( mesh.bindVerts.ptr, mesh.bindNormals.ptr, mesh.morphDeltas.ptr, mesh.morphNormals.ptr, mesh.morphWeights.ptr, targetCount,
 		mesh.verts.ptr, mesh.coreTris.ptr, mesh.triCount, core->stream );
-	CUDA_CHECK( cudaStreamSynchronize( core->stream ) );
 	AfterPose( core, mesh );
 	API_END
 }
@@ -520,7 +534,13 @@ int lh2b_get_bvh_stats( lh2b_core* core, int meshIdx, lh2b_bvh_stats* out )
 	else
 	{
 		if (meshIdx < 0 || meshIdx >= (int)core->meshes.size()) throw CoreError( "unknown mesh" );
-		const Mesh& m = *core->meshes[meshIdx];
+		Mesh& m = *core->meshes[meshIdx];
+		if (m.timingPending)
+		{
+			CUDA_CHECK( cudaEventSynchronize( m.evEnd ) );
+			CUDA_CHECK( cudaEventElapsedTime( &m.buildMs, m.evStart, m.evEnd ) );
+			m.timingPending = false;
+		}
 		out->nodes = m.nodeCount, out->triangles = m.triCount;
 		out->bytes = (uint32_t)(m.nodeCount * 80 + (size_t)m.triCount * 48);
 		out->buildMs = m.buildMs, out->sahCost = m.sahCost;

@@ -36,8 +36,12 @@ struct Mesh
 	DevBuf<int> topoParent;
 	DevBuf<float4> devBounds;		// {lo, hi} of the mesh, device resident (feeds the top-level build)
 	DevBuf<uint32_t> devCounts;		// node count, leaf count, overflow flag of the last build
+	DevBuf<int> topoWideChild, topoWideSelf;	// binary node behind each slot of each wide node / behind the wide node (in-place refit)
 	bool hasTopology = false;
 	int builtTriCount = -1;
+	cudaEvent_t evStart = nullptr, evEnd = nullptr;	// device time of the last refit, read lazily (no sync on the refit path)
+	bool timingPending = false;
+	~Mesh() { if (evStart) cudaEventDestroy( evStart ), cudaEventDestroy( evEnd ); }
 	// device-side animation (skin_kernels.cu): bind pose captured by lh2b_set_skin / lh2b_set_morph_targets
 	DevBuf<float4> bindVerts, bindNormals;	// 3 per triangle
 	DevBuf<uint4> skinJoints;
@@ -45,6 +49,7 @@ struct Mesh
 	DevBuf<float4> morphDeltas, morphNormals;	// [target][vertex]
 	DevBuf<float> morphWeights;
 	int morphTargets = 0;
+	std::vector<float> hostJointMats;		// pageable staging copy of the per-frame pose parameters
 };
 
 struct Instance { int mesh = 0; float xform[12] = { 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0 }; };
@@ -78,7 +83,7 @@ struct lh2b_core
 	lh2b::DevBuf<uint8_t> instBuildIn;		// per-frame top-level build input
 	lh2b::DevBuf<uint32_t> linkedRoots;
 	int plocRadius = 8, bvhMaxLeaf = 2;	// swept on the 1M-triangle terrain (tools/quality_sweep.py)
-	int bvhRefit = 1;						// refit (keep topology) when a mesh is re-sent with the same triangle count	// work counter of the persistent query kernels
+	int bvhRefit = 1;						// same triangle count re-sent: 1 refit in place (binary + wide tree), 2 refit the binary tree and collapse again, 0 rebuild	// work counter of the persistent query kernels
 	// settings
 	int bvhBuilder = 0;				// 0: GPU LBVH (default), 1: host binned SAH
 	float geometryEpsilon = 1e-4f, clampValue = 10.0f;	// reference defaults: stageClampValue(10) at rendercore.cpp:243; epsilon comes from RenderSystem (rendersystem.h:65-72)

@@ -113,14 +113,20 @@ def test_empty_and_tiny():
     _check([tri], [(0, _rot((1, 0, 0), 0.5, (0, 1, 0)))], O, D, shadow_tmax=2.0)
 
 
-def test_refit_after_deformation():
-    """SetGeometry with the same triangle count: the GPU builder keeps the topology (refit) - results must still be exact."""
+@pytest.mark.parametrize("mode", [1, 2], ids=["in-place", "recollapse"])
+@pytest.mark.parametrize("xf", [False, True], ids=["flat", "two-level"])
+def test_refit_after_deformation(mode, xf):
+    """SetGeometry with the same triangle count: the GPU builder keeps the topology - bvhRefit 1 refits the binary tree and
+    requantises the wide tree in place, 2 collapses the refitted binary tree again. Results must still be exact, in a flat
+    scene (triangle records keep their instance tag) and behind an instance transform."""
     base = scenes.terrain(50, 40, extent=20, seed=21)
     O, D = scenes.random_rays(20000, extent=24, seed=22)
+    inst = [(0, _rot((0, 1, 0), 0.4, (1, 0.5, -2)) if xf else None)]
     core = RenderCore()
     core.Setting("bvhBuilder", _builder)
+    core.Setting("bvhRefit", mode)
     core.SetGeometry(0, base)
-    core.SetInstance(0, 0)
+    core.SetInstance(0, 0, inst[0][1])
     core.SetInstance(1, -1)
     core.FinalizeInstances()
     rng = np.random.default_rng(23)
@@ -130,7 +136,7 @@ def test_refit_after_deformation():
         core.SetGeometry(0, mesh)
         core.FinalizeInstances()
         got = core.TraceRays(O, D)
-        want = orc.closest_hits([mesh], [(0, None)], O, D)
+        want = orc.closest_hits([mesh], inst, O, D)
         assert np.array_equal(got, want), f"refit step {step}: {(got != want).any(axis=1).sum()} records differ"
     core.Shutdown()
 

@@ -118,6 +118,36 @@ if "c4" in which:
                  "set_instance_calls_ms": float(np.mean(inst_ms[1:])), "finalize_instances_wall_ms": float(np.mean(build_ms[1:])),
                  "refit_device_ms_10_meshes": refit_device, "tlas_device_ms": last["buildMs"], "render_ms": last["totalMs"],
                  "trace_mrays_per_s": last["rays"] / (last["generateExtendMs"] + last["extendMs"] + last["connectMs"]) / 1e3, "frame": last}
+    # the same animation done on the device (lh2b_set_skin / lh2b_set_pose): 4 joints per mesh, new joint
+    # matrices every frame -> skinning kernel + refit, no triangle data crosses PCIe (64 B per joint do)
+    nverts = base.reshape(-1, 4).shape[0]
+    jrng = np.random.default_rng(11)
+    joints = jrng.integers(0, 4, (nverts, 4)).astype(np.uint32)
+    wts = jrng.random((nverts, 4)).astype(np.float32); wts /= wts.sum(axis=1, keepdims=True)
+    for m in range(10):
+        core.SetGeometry(m, base, tris)
+    core.FinalizeInstances()
+    for m in range(10):
+        core.SetSkin(m, joints, wts)
+    pose_ms, fin_ms, rend = [], [], []
+    for f in range(1, 6):
+        mats4 = np.tile(np.eye(4, dtype=np.float32), (4, 1, 1))
+        for q in range(4):
+            mats4[q, 1, 3] = 0.2 * np.sin(f + q)
+        t0 = time.perf_counter()
+        for m in range(10):
+            core.SetPose(m, mats4)
+        t1 = time.perf_counter()
+        set_instances(f)
+        t2 = time.perf_counter()
+        core.FinalizeInstances()
+        t3 = time.perf_counter()
+        core.Render(view, 1)
+        fs = core.GetFrameStats()
+        pose_ms.append(1e3 * (t1 - t0)); fin_ms.append(1e3 * (t3 - t2)); rend.append(float(fs["totalMs"]))
+    res["c4"]["device_animation"] = {"set_pose_wall_ms_10_meshes": float(np.mean(pose_ms[1:])), "finalize_instances_wall_ms": float(np.mean(fin_ms[1:])),
+                                     "refit_device_ms_10_meshes": sum(float(core.GetBvhStats(m)["buildMs"]) for m in range(10)),
+                                     "render_ms": float(np.mean(rend[1:])), "pcie_bytes_per_frame": 10 * 4 * 64}
     core.Shutdown()
     print("c4", res["c4"], flush=True)
 
