@@ -82,7 +82,7 @@ struct lh2b_core
 	void* gpuBuild = nullptr;				// GpuBuildScratch (bvh_gpu.cu)
 	lh2b::DevBuf<uint8_t> instBuildIn;		// per-frame top-level build input
 	lh2b::DevBuf<uint32_t> linkedRoots;
-	int plocRadius = 8, bvhMaxLeaf = 2;	// swept on the 1M-triangle terrain (tools/quality_sweep.py)
+	int plocRadius = 8, bvhMaxLeaf = 1;	// swept on the 1M-triangle terrain (tools/quality_sweep.py)
 	int bvhRefit = 1;						// same triangle count re-sent: 1 refit in place (binary + wide tree), 2 refit the binary tree and collapse again, 0 rebuild	// work counter of the persistent query kernels
 	// settings
 	int bvhBuilder = 0;				// 0: GPU LBVH (default), 1: host binned SAH
