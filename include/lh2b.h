@@ -97,6 +97,30 @@ LH2B_API int lh2b_accumulator_device_ptr( lh2b_core* core, void** ptrOut, int* s
 /* Finalize an externally reduced accumulator (float4[w*h] on this device, e.g. the NCCL sum over the
    shards) into this core's pixel buffer: pixels = accum / samples. */
 LH2B_API int lh2b_finalize_external( lh2b_core* core, const void* dAccumulator, int samples );
+/* Pipelined multi-GPU frames (lighthouse2_b200/distributed.py): lh2b_snapshot_accumulator enqueues a device-to-device copy of
+   the accumulator on the core's stream - behind the frame last passed to lh2b_render, in front of the next one - so that the
+   reduce of frame k can run on another stream while frame k+1 renders; lh2b_finalize_external_on launches the finalize kernel
+   on the caller's stream (cudaStream_t), reading the reduced accumulator and writing float4[w*h] to dPixelsOut. */
+LH2B_API int lh2b_snapshot_accumulator( lh2b_core* core, void* dDst );
+LH2B_API int lh2b_finalize_external_on( lh2b_core* core, const void* dAccumulator, int samples, void* dPixelsOut, void* stream );
+
+/* ---- multi-GPU frame gather over NVLink peer memory (csrc/gather.cu) ----------------------------------------
+   One process per GPU renders its sample shard (lh2b_set_sample_shard); rank 0 ends every frame with the summed, finalized
+   image. Peer copies by the copy engines + stream memory operations for the hand-shake + one fused sum/finalize kernel; no
+   library collective on the data path, nothing blocks the host. Set-up: every rank creates its end, exports
+   lh2b_gather_handle_bytes() bytes of CUDA IPC handles, the caller all-gathers them (rank order) and every rank imports the
+   whole array. Per frame, on every rank: lh2b_render( ..., async = 1 ) then lh2b_gather_frame( g, samplesOfAllRanks, pinnedOut )
+   (pinnedOut: rank 0 only, page-locked float4[w*h] or null). lh2b_gather_wait blocks until this rank's part is complete. */
+typedef struct lh2b_gather lh2b_gather;
+LH2B_API int lh2b_gather_handle_bytes( void );
+LH2B_API int lh2b_gather_create( lh2b_core* core, int rank, int world, lh2b_gather** out );
+LH2B_API int lh2b_gather_export( lh2b_gather* g, void* handlesOut );
+LH2B_API int lh2b_gather_import( lh2b_gather* g, const void* handlesOfAllRanks );
+LH2B_API int lh2b_gather_frame( lh2b_gather* g, int samplesTotal, float* pinnedOut );
+LH2B_API int lh2b_gather_wait( lh2b_gather* g );
+LH2B_API int lh2b_gather_join( lh2b_gather* g, void* stream );	/* make a cudaStream_t wait for the work enqueued so far */
+LH2B_API int lh2b_gather_image_device_ptr( lh2b_gather* g, void** ptrOut );	/* rank 0: device image of the newest frame */
+LH2B_API int lh2b_gather_destroy( lh2b_gather* g );
 /* Multi-GPU sample sharding: this core renders sample indices [first, first+spp) of each pass and
    seeds as if it were part of a 'total'-spp frame. Default: first 0, total = spp. */
 LH2B_API int lh2b_set_sample_shard( lh2b_core* core, int firstSample, int totalSpp );

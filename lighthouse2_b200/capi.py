@@ -43,6 +43,17 @@ SIGNATURES = {
     "lh2b_read_accumulator": ([_vp, _vp], _ip),
     "lh2b_accumulator_device_ptr": ([_vp, _c.POINTER(_vp), _c.POINTER(_ip)], _ip),
     "lh2b_finalize_external": ([_vp, _vp, _ip], _ip),
+    "lh2b_snapshot_accumulator": ([_vp, _vp], _ip),
+    "lh2b_gather_handle_bytes": ([], _ip),
+    "lh2b_gather_create": ([_vp, _ip, _ip, _c.POINTER(_vp)], _ip),
+    "lh2b_gather_export": ([_vp, _vp], _ip),
+    "lh2b_gather_import": ([_vp, _vp], _ip),
+    "lh2b_gather_frame": ([_vp, _ip, _vp], _ip),
+    "lh2b_gather_wait": ([_vp], _ip),
+    "lh2b_gather_join": ([_vp, _vp], _ip),
+    "lh2b_gather_image_device_ptr": ([_vp, _c.POINTER(_vp)], _ip),
+    "lh2b_gather_destroy": ([_vp], _ip),
+    "lh2b_finalize_external_on": ([_vp, _vp, _ip, _vp, _vp], _ip),
     "lh2b_set_sample_shard": ([_vp, _ip, _ip], _ip),
     "lh2b_trace_rays": ([_vp, _vp, _vp, _ip, _vp], _ip),
     "lh2b_trace_shadow_rays": ([_vp, _vp, _vp, _ip, _vp], _ip),

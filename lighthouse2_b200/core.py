@@ -177,6 +177,44 @@ class RenderCore:
         ptr = accumulator.data_ptr() if hasattr(accumulator, "data_ptr") else int(accumulator)
         self._check(self._lib.lh2b_finalize_external(self._h, ctypes.c_void_p(ptr), int(samples)))
 
+    def SnapshotAccumulator(self, dst):
+        """Enqueue a device-to-device copy of the accumulator behind the frame rendered last (torch CUDA tensor or device pointer)."""
+        ptr = dst.data_ptr() if hasattr(dst, "data_ptr") else int(dst)
+        self._check(self._lib.lh2b_snapshot_accumulator(self._h, ctypes.c_void_p(ptr)))
+
+    def FinalizeExternalOn(self, accumulator, samples, pixels_out, stream):
+        """Finalize kernel on the caller's CUDA stream (int handle): pixels_out = accumulator / samples, both device buffers."""
+        a = accumulator.data_ptr() if hasattr(accumulator, "data_ptr") else int(accumulator)
+        o = pixels_out.data_ptr() if hasattr(pixels_out, "data_ptr") else int(pixels_out)
+        self._check(self._lib.lh2b_finalize_external_on(self._h, ctypes.c_void_p(a), int(samples), ctypes.c_void_p(o), ctypes.c_void_p(int(stream))))
+
+    # -- multi-GPU frame gather over peer memory (csrc/gather.cu) ---------------------------------
+    def GatherCreate(self, rank, world):
+        g = ctypes.c_void_p()
+        self._check(self._lib.lh2b_gather_create(self._h, rank, world, ctypes.byref(g)))
+        return g
+
+    def GatherExport(self, g):
+        buf = ctypes.create_string_buffer(self._lib.lh2b_gather_handle_bytes())
+        self._check(self._lib.lh2b_gather_export(g, buf))
+        return buf.raw
+
+    def GatherImport(self, g, handles_of_all_ranks):
+        self._check(self._lib.lh2b_gather_import(g, ctypes.c_char_p(handles_of_all_ranks)))
+
+    def GatherFrame(self, g, samples_total, pinned_out=None):
+        p = None if pinned_out is None else (ctypes.c_void_p(pinned_out.data_ptr()) if hasattr(pinned_out, "data_ptr") else _ptr(pinned_out))
+        self._check(self._lib.lh2b_gather_frame(g, int(samples_total), p))
+
+    def GatherWait(self, g):
+        self._check(self._lib.lh2b_gather_wait(g))
+
+    def GatherJoin(self, g, stream):
+        self._check(self._lib.lh2b_gather_join(g, ctypes.c_void_p(int(stream))))
+
+    def GatherDestroy(self, g):
+        self._check(self._lib.lh2b_gather_destroy(g))
+
     def SetSampleShard(self, first_sample, total_spp):
         self._check(self._lib.lh2b_set_sample_shard(self._h, first_sample, total_spp))
 

@@ -103,6 +103,13 @@ struct lh2b_core
 	bool copyPending[2] = { false, false };
 	lh2b::DevBuf<lh2b::DevCounters> counters;
 	lh2b::DevCounters* hostCounters = nullptr;	// pinned
+	// second frame slot for pipelined rendering (Setting "pipeline"): the frame that is still in flight while the next one is enqueued
+	lh2b::DevCounters* hostCountersB = nullptr;
+	std::vector<cudaEvent_t> eventsB;
+	bool frameInFlightB = false, pipeline = false;
+	double renderStartMsB = 0;
+	lh2abi::ViewPyramid lastViewB = {};
+	int maxPathLengthB = 0, filterB = 0;
 	int samplesTaken = 0;
 	int sampleShardFirst = 0, sampleShardTotal = 0;	// 0 total = not sharded
 	bool firstConvergingFrame = true, frameInFlight = false;

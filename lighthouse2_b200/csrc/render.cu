@@ -40,10 +40,13 @@ void InitRenderState( lh2b_core* core )
 	core->counters.Resize( 1 );
 	CUDA_CHECK( cudaMemsetAsync( core->counters.ptr, 0, sizeof( DevCounters ), core->stream ) );
 	CUDA_CHECK( cudaMallocHost( &core->hostCounters, sizeof( DevCounters ) ) );
-	memset( core->hostCounters, 0, sizeof( DevCounters ) );
+	CUDA_CHECK( cudaMallocHost( &core->hostCountersB, sizeof( DevCounters ) ) );
+	memset( core->hostCounters, 0, sizeof( DevCounters ) ), memset( core->hostCountersB, 0, sizeof( DevCounters ) );
 	// events: 0 frame start, then per path length L (1-based): 4 * L + {0: trace start, 1: trace end/shade start, 2: shade end/connect start, 3: connect end}
 	core->events.resize( 4 * (LH2B_MAXPATHLENGTH + 1) + 4 );
 	for (auto& e : core->events) CUDA_CHECK( cudaEventCreate( &e ) );
+	core->eventsB.resize( core->events.size() );
+	for (auto& e : core->eventsB) CUDA_CHECK( cudaEventCreate( &e ) );
 	// one-texel placeholders so table pointers are never null
 	const uchar4 z4 = make_uchar4( 0, 0, 0, 0 );
 	const float4 zf = make_float4( 0, 0, 0, 0 );
@@ -57,8 +60,10 @@ void InitRenderState( lh2b_core* core )
 void ReleaseRenderState( lh2b_core* core )
 {
 	for (auto& e : core->events) cudaEventDestroy( e );
-	core->events.clear();
+	for (auto& e : core->eventsB) cudaEventDestroy( e );
+	core->events.clear(), core->eventsB.clear();
 	if (core->hostCounters) cudaFreeHost( core->hostCounters ), core->hostCounters = nullptr;
+	if (core->hostCountersB) cudaFreeHost( core->hostCountersB ), core->hostCountersB = nullptr;
 }
 
 static void EnsureFilterBuffers( lh2b_core* core )
@@ -106,7 +111,8 @@ static void RunFilter( lh2b_core* core )
 static void FinishFrame( lh2b_core* core )
 {
 	if (!core->frameInFlight) return;
-	CUDA_CHECK( cudaStreamSynchronize( core->stream ) );
+	// wait for THIS frame (its last event), not for the stream: with pipelining the next frame is already queued behind it
+	CUDA_CHECK( cudaEventSynchronize( core->events.back() ) );
 	core->frameInFlight = false;
 	const DevCounters& c = *core->hostCounters;
 	const int maxLen = core->maxPathLength;
@@ -192,6 +198,14 @@ static void RotatePixelBuffers( lh2b_core* core )
 	std::swap( core->copyDone[0], core->copyDone[1] );
 	std::swap( core->copyPending[0], core->copyPending[1] );
 	if (core->copyPending[0]) { CUDA_CHECK( cudaStreamWaitEvent( core->stream, core->copyDone[0], 0 ) ); core->copyPending[0] = false; }
+}
+
+/* Frame slots: A (the members used everywhere) holds the frame being enqueued / harvested, B a frame that stays in flight. */
+static void SwapFrameSlots( lh2b_core* core )
+{
+	std::swap( core->hostCounters, core->hostCountersB ), core->events.swap( core->eventsB );
+	std::swap( core->frameInFlight, core->frameInFlightB ), std::swap( core->renderStartMs, core->renderStartMsB );
+	std::swap( core->lastView, core->lastViewB );
 }
 
 static void RenderFrame( lh2b_core* core, const lh2abi::ViewPyramid& view )
@@ -305,6 +319,7 @@ int lh2b_setting( lh2b_core* core, const char* name, float value )
 	else if (!strcmp( name, "clampIndirect" )) core->clampIndirect = value;
 	// extensions of this core (the reference fixes these at compile time: core_settings.h:25, pathtracer.h:33)
 	else if (!strcmp( name, "maxPathLength" )) core->maxPathLength = value < 1 ? 1 : (value > LH2B_MAXPATHLENGTH ? LH2B_MAXPATHLENGTH : (int)value);
+	else if (!strcmp( name, "pipeline" )) { FinishFrame( core ); core->pipeline = value > 0; }
 	else if (!strcmp( name, "bsdf" )) { const int m = value >= 0.5f ? 1 : 0; if (m != core->bsdfModel) core->bsdfModel = m, core->samplesTaken = 0; }
 	else if (!strcmp( name, "maxDiffuseBounces" )) core->enoughBounces = value <= 0 ? 0 : (value < 2 ? S_BOUNCED : S_BOUNCEDTWICE);
 	else if (!strcmp( name, "bvhBuilder" )) core->bvhBuilder = (int)value;	// 0: GPU LBVH (default), 1: host binned SAH
@@ -448,7 +463,11 @@ int lh2b_render( lh2b_core* core, const void* viewPtr, int converge, int async )
 	if (!core->sceneReady) return 0;	// silent no-op before the first FinalizeInstances (rendercore.cpp:821)
 	if (core->width == 0) throw CoreError( "Render: SetTarget has not been called" );
 	if (core->materials.count == 0) throw CoreError( "Render: SetMaterials has not been called" );
-	FinishFrame( core );
+	// pipelined mode (Setting "pipeline" 1, async calls): the frame in flight keeps running while this one is enqueued behind
+	// it; the older frame is harvested afterwards, so the device never idles between frames. GetCoreStats / frame stats then
+	// describe the previous frame; WaitForRender harvests the one still in flight.
+	const bool pipelined = core->pipeline && async && core->frameInFlight;
+	if (pipelined) SwapFrameSlots( core ); else FinishFrame( core );
 	if (converge == 1 || core->firstConvergingFrame)
 	{
 		core->samplesTaken = 0;
@@ -458,6 +477,12 @@ int lh2b_render( lh2b_core* core, const void* viewPtr, int converge, int async )
 	if (converge == 0) core->firstConvergingFrame = false;
 	core->renderStartMs = NowMs();
 	RenderFrame( core, *(const lh2abi::ViewPyramid*)viewPtr );
+	if (pipelined)
+	{
+		SwapFrameSlots( core );
+		FinishFrame( core );
+		SwapFrameSlots( core );
+	}
 	if (!async) FinishFrame( core );
 	API_END
 }
@@ -530,6 +555,24 @@ int lh2b_accumulator_device_ptr( lh2b_core* core, void** ptrOut, int* samplesTak
 	FinishFrame( core );
 	if (ptrOut) *ptrOut = core->accumulator.ptr;
 	if (samplesTakenOut) *samplesTakenOut = core->samplesTaken;
+	API_END
+}
+
+int lh2b_snapshot_accumulator( lh2b_core* core, void* dDst )
+{
+	API_BEGIN
+	if (!dDst) throw CoreError( "snapshot_accumulator: null destination" );
+	// stream-ordered behind the frame passed to lh2b_render last (which may still be in flight) and in front of the next one
+	CUDA_CHECK( cudaMemcpyAsync( dDst, core->accumulator.ptr, (size_t)core->width * core->height * sizeof( float4 ), cudaMemcpyDeviceToDevice, core->stream ) );
+	API_END
+}
+
+int lh2b_finalize_external_on( lh2b_core* core, const void* dAccumulator, int samples, void* dPixelsOut, void* stream )
+{
+	API_BEGIN
+	if (samples <= 0) throw CoreError( "finalize_external: samples must be positive" );
+	LaunchFinalize( (const float4*)dAccumulator, (float4*)dPixelsOut, core->width * core->height, samples, (cudaStream_t)stream );
+	CUDA_CHECK( cudaGetLastError() );
 	API_END
 }
 

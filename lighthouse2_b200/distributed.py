@@ -63,3 +63,94 @@ class ShardedRenderer:
         if self.rank == 0:
             self.core.FinalizeExternal(self._sum, total)
         return total
+
+
+class PipelinedShardedRenderer(ShardedRenderer):
+    """The same sharding with frames in flight (GPU only): the core renders frame k+1 (Setting "pipeline") while frame k's
+    accumulator snapshot is reduced over NCCL, finalized on rank 0 and copied to pinned host memory on a second stream.
+
+        frame(view, converge, host_out)   enqueue one frame everywhere; rank 0's image lands in host_out asynchronously
+        finish()                          wait for everything in flight
+    """
+
+    def __init__(self, core, spp, rank=None, world=None, device=None):
+        super().__init__(core, spp, rank, world, None)
+        core.Setting("pipeline", 1)
+        self.device = device
+        self._core_stream = torch.cuda.ExternalStream(core.Stream(), device=device)
+        self._comm = torch.cuda.Stream(device=device)
+        shape = (core.height, core.width, 4)
+        self._sums = [torch.empty(shape, dtype=torch.float32, device=device) for _ in range(2)]
+        self._img = [torch.empty(shape, dtype=torch.float32, device=device) for _ in range(2)] if self.rank == 0 else None
+        self._done = [None, None]
+        self._k = 0
+
+    def frame(self, view, converge=1, host_out=None):
+        slot = self._k & 1
+        if self._done[slot] is not None:
+            self._done[slot].synchronize()          # the buffers of frame k-2 are free again
+        self.core.Render(view, converge, True)       # frame k enqueued, frame k-1 harvested
+        total = self.core.SamplesTaken()
+        buf = self._sums[slot]
+        self.core.SnapshotAccumulator(buf)           # behind frame k on the core's stream, in front of frame k+1
+        ready = self._core_stream.record_event()
+        with torch.cuda.stream(self._comm):
+            self._comm.wait_event(ready)
+            if self.world > 1:
+                dist.reduce(buf, dst=0, op=dist.ReduceOp.SUM)
+            if self.rank == 0:
+                self.core.FinalizeExternalOn(buf, total, self._img[slot], self._comm.cuda_stream)
+                if host_out is not None:
+                    host_out.copy_(self._img[slot], non_blocking=True)
+            self._done[slot] = self._comm.record_event()
+        self._k += 1
+        return total
+
+    def finish(self):
+        self.core.WaitForRender()
+        self._comm.synchronize()
+
+    def last_event(self):
+        """Event after the newest frame's reduce / finalize / read-back (for device-side timing)."""
+        return self._done[(self._k - 1) & 1]
+
+
+class PeerGatherRenderer:
+    """Sample-sharded frames with the core's own collective (csrc/gather.cu): peers push their accumulator snapshot into
+    rank 0's memory with the copy engines over NVLink, rank 0 sums and finalizes in one kernel; hand-shakes are stream memory
+    operations, so neither SMs nor the host wait. torch.distributed only carries the CUDA IPC handles at set-up.
+
+        frame(view, converge, host_out)   enqueue one frame on this rank (rank 0: the image goes to pinned host_out, or None)
+        finish()                          wait for everything this rank has in flight
+    """
+
+    def __init__(self, core, spp, rank=None, world=None):
+        self.core = core
+        self.rank = dist.get_rank() if rank is None else rank
+        self.world = dist.get_world_size() if world is None else world
+        first, total = sample_shard(self.rank, self.world, spp)
+        core.SetSampleShard(first, total)
+        core.Setting("pipeline", 1)
+        self.g = core.GatherCreate(self.rank, self.world)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, core.GatherExport(self.g))
+        core.GatherImport(self.g, b"".join(handles))
+        dist.barrier()
+
+    def frame(self, view, converge=1, host_out=None):
+        self.core.Render(view, converge, True)
+        total = self.core.SamplesTaken()
+        self.core.GatherFrame(self.g, total, host_out if self.rank == 0 else None)
+        return total
+
+    def finish(self):
+        self.core.WaitForRender()
+        self.core.GatherWait(self.g)
+
+    def join(self, stream_handle):
+        self.core.GatherJoin(self.g, stream_handle)
+
+    def close(self):
+        self.finish()
+        dist.barrier()
+        self.core.GatherDestroy(self.g)

@@ -1,0 +1,68 @@
+"""Worker for tests/test_multigpu_gpu.py and for manual runs under torchrun (world_size >= 2, one GPU per rank):
+sample-sharded frames gathered on rank 0 by (a) the core's peer-memory collective and (b) the NCCL reduce must both equal
+one GPU rendering all samples (float sums in a different order: relative 1e-5)."""
+import os
+import sys
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from lighthouse2_b200 import RenderCore, scenes  # noqa: E402
+from lighthouse2_b200.distributed import PeerGatherRenderer, PipelinedShardedRenderer  # noqa: E402
+
+W, H, SPP = 160, 90, 2
+
+
+def make_core(dev, sd, spp):
+    core = RenderCore(dev)
+    core.SetTarget(W, H, spp)
+    core.Setting("epsilon", 1e-3)
+    core.Setting("maxPathLength", 3)
+    sd.upload(core)
+    return core
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    sd = scenes.config2_scene(48, 32, n_materials=4, light_quads=2, floaters=200)
+    views = [scenes.view_pyramid((5 * k, 30, -80), (0, 0, 0), 40, W, H) for k in range(6)]
+    conv = [1, 0, 0, 1, 0, 0]
+    want = []
+    if rank == 0:
+        single = make_core(local, sd, SPP * world)      # the same samples on one GPU
+        for v, c in zip(views, conv):
+            single.Render(v, c)
+            want.append(single.ReadPixels().copy())
+        single.Shutdown()
+    ok = True
+    for kind in ("peer", "nccl"):
+        core = make_core(local, sd, SPP)
+        r = PeerGatherRenderer(core, SPP, rank, world) if kind == "peer" else PipelinedShardedRenderer(core, SPP, rank, world, f"cuda:{local}")
+        outs = [torch.zeros((H, W, 4), dtype=torch.float32).pin_memory() for _ in views]
+        for k, (v, c) in enumerate(zip(views, conv)):
+            r.frame(v, c, outs[k])
+        r.finish()
+        if rank == 0:
+            for k in range(len(views)):
+                got = outs[k].numpy()
+                err = np.abs(got - want[k]).max() / max(1e-6, np.abs(want[k]).max())
+                print(f"{kind} frame {k}: max rel err {err:.2e}", flush=True)
+                ok &= bool(err < 1e-5)
+        if kind == "peer":
+            r.close()
+        core.Shutdown()
+        dist.barrier()
+    flag = torch.tensor([1 if ok else 0], device=f"cuda:{local}")
+    dist.broadcast(flag, 0)
+    dist.destroy_process_group()
+    if rank == 0:
+        print("MULTIGPU_OK" if ok else "MULTIGPU_FAIL", flush=True)
+    sys.exit(0 if int(flag.item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -134,3 +134,37 @@ def test_frame_principled_materials():
     for conv in (1, 0):
         _compare(core, oracle, view, conv)
     core.Shutdown()
+
+
+def test_pipelined_frames_match_blocking_frames():
+    """Setting("pipeline", 1) + asynchronous Render: frame k+1 is enqueued while frame k is in flight, frame k is harvested
+    afterwards. Pixels (read with the pipelined read-back) and ray counts must equal the blocking sequence, the statistics
+    lag one frame until WaitForRender."""
+    import torch
+    sd = _scene(3, 1)
+    views = [scenes.view_pyramid((10 + 3 * k, 25, -70), (0, 2, 0), 40, W, H) for k in range(5)]
+    conv = [1, 0, 0, 1, 0]
+    a, b = _core(sd), _core(sd)
+    want_px, want_rays = [], []
+    for v, c in zip(views, conv):
+        a.Render(v, c)
+        want_px.append(a.ReadPixels().copy())
+        st = a.GetCoreStats()
+        want_rays.append((int(st["totalExtensionRays"]), int(st["totalShadowRays"])))
+    b.Setting("pipeline", 1)
+    pinned = [torch.empty((H, W, 4), dtype=torch.float32, pin_memory=True) for _ in views]
+    got_rays = []
+    for k, (v, c) in enumerate(zip(views, conv)):
+        b.Render(v, c, True)
+        b.ReadPixelsAsync(pinned[k].numpy())
+        if k > 0:
+            st = b.GetCoreStats()              # describes frame k-1
+            got_rays.append((int(st["totalExtensionRays"]), int(st["totalShadowRays"])))
+    b.WaitForRender()
+    st = b.GetCoreStats()
+    got_rays.append((int(st["totalExtensionRays"]), int(st["totalShadowRays"])))
+    b.WaitReadPixels()
+    assert got_rays == want_rays
+    for k in range(len(views)):
+        assert np.array_equal(pinned[k].numpy(), want_px[k]), k
+    a.Shutdown(), b.Shutdown()
