@@ -154,6 +154,9 @@ def run_ours(args, rank, world, local_rank):
     core.Setting("epsilon", 1e-3)
     core.Setting("clampValue", 10.0)
     core.Setting("maxPathLength", 1)            # primary + shadow rays only
+    for k, v in os.environ.items():             # experiments: LH2B_SET_<setting>=<value> (recorded in config.overrides)
+        if k.startswith("LH2B_SET_"):
+            core.Setting(k[9:], float(v))
     sd.upload(core)
     bvh = core.GetBvhStats(0)
     from lighthouse2_b200.distributed import PeerGatherRenderer, PipelinedShardedRenderer
@@ -287,7 +290,7 @@ def run_ours(args, rank, world, local_rank):
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "triangles": int(bvh["triangles"]) + 2, "resolution": [W, H], "spp_per_gpu": SPP,
-                   "path_length": 1, "bvh": "CWBVH (8-wide, quantised)", "bvh_nodes": int(bvh["nodes"]),
+                   "path_length": 1, "overrides": {k[9:]: v for k, v in os.environ.items() if k.startswith("LH2B_SET_")}, "bvh": "CWBVH (8-wide, quantised)", "bvh_nodes": int(bvh["nodes"]),
                    "parallelism": "1 GPU" if world == 1 else f"sample-sharded x{world}, scene replicated, accumulators gathered on rank 0 ({args.collective})",
                    "frames": "pipelined: the next frame is enqueued while the previous one runs",
                    "l2": "no explicit flush: per-step working set (path state 0.2 GB + scene 0.3 GB) exceeds the 126 MB L2; the 67 MB BVH "

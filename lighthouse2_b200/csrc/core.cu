@@ -152,6 +152,32 @@ static void RebuildMeshGpu( lh2b_core* core, Mesh& mesh )
 	throw CoreError( "GPU BVH build: node slot overflow persists" );
 }
 
+/* Keep the BVH in L2 across the streaming traffic of a frame (path state, accumulator, peer pushes on rank 0): a persisting
+   access window over the node arena on the launch stream, backed by a set-aside of L2 (Setting "l2Persist", default on).
+   Everything else the stream touches is marked streaming by the window's miss property. */
+static void ApplyL2Policy( lh2b_core* core )
+{
+	const size_t nodeBytes = core->arenaNodes.count * sizeof( uint4 );
+	if (core->l2Persist == core->l2Applied && core->l2Base == (void*)core->arenaNodes.ptr && core->l2Bytes == nodeBytes) return;
+	cudaDeviceProp prop;
+	CUDA_CHECK( cudaGetDeviceProperties( &prop, core->device ) );
+	cudaStreamAttrValue attr = {};
+	if (core->l2Persist && prop.persistingL2CacheMaxSize > 0 && nodeBytes > 0)
+	{
+		const size_t window = std::min( nodeBytes, (size_t)prop.accessPolicyMaxWindowSize );
+		const size_t setAside = std::min( window, (size_t)prop.persistingL2CacheMaxSize );
+		CUDA_CHECK( cudaDeviceSetLimit( cudaLimitPersistingL2CacheSize, setAside ) );
+		attr.accessPolicyWindow.base_ptr = core->arenaNodes.ptr;
+		attr.accessPolicyWindow.num_bytes = window;
+		attr.accessPolicyWindow.hitRatio = window <= setAside ? 1.0f : (float)setAside / (float)window;
+		attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+		attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+	}
+	else attr.accessPolicyWindow.num_bytes = 0;
+	CUDA_CHECK( cudaStreamSetAttribute( core->stream, cudaStreamAttributeAccessPolicyWindow, &attr ) );
+	core->l2Applied = core->l2Persist, core->l2Base = core->arenaNodes.ptr, core->l2Bytes = nodeBytes;
+}
+
 struct InstBuildHost { float xform[12]; const float4* bounds; uint64_t pad; };
 
 void UpdateAccelerationStructures( lh2b_core* core )
@@ -219,6 +245,7 @@ void UpdateAccelerationStructures( lh2b_core* core )
 	core->scene.instances = core->instTrav.ptr;
 	core->scene.instanceCount = n;
 	core->scene.singleIdentity = flat ? 1 : 0;
+	ApplyL2Policy( core );
 }
 
 } // namespace lh2b
@@ -253,7 +280,12 @@ int lh2b_create( lh2b_core** out, int device )
 		CUDA_CHECK( cudaGetDeviceProperties( &prop, device ) );
 		std::unique_ptr<lh2b_core> core( new lh2b_core() );
 		core->device = device;
-		CUDA_CHECK( cudaStreamCreateWithFlags( &core->stream, cudaStreamNonBlocking ) );
+		{
+			// the launch stream gets the highest priority: copy / gather work on other streams only fills what the frame leaves idle
+			int least = 0, greatest = 0;
+			CUDA_CHECK( cudaDeviceGetStreamPriorityRange( &least, &greatest ) );
+			CUDA_CHECK( cudaStreamCreateWithPriority( &core->stream, cudaStreamNonBlocking, greatest ) );
+		}
 		CUDA_CHECK( cudaStreamCreateWithFlags( &core->copyStream, cudaStreamNonBlocking ) );
 		CUDA_CHECK( cudaEventCreateWithFlags( &core->frameDone, cudaEventDisableTiming ) );
 		for (int k = 0; k < 2; k++) CUDA_CHECK( cudaEventCreateWithFlags( &core->copyDone[k], cudaEventDisableTiming ) );

@@ -56,6 +56,11 @@ struct Instance { int mesh = 0; float xform[12] = { 1, 0, 0, 0, 0, 1, 0, 0, 0, 0
 
 } // namespace lh2b
 
+struct lh2b_gather;
+/* gather.cu: where the frame being enqueued must leave its accumulator snapshot (also orders the stream behind the consumer of
+   that buffer two frames ago) */
+float4* GatherSnapshotTarget( lh2b_gather* g, cudaStream_t coreStream );
+
 struct lh2b_core
 {
 	int device = 0;
@@ -83,6 +88,9 @@ struct lh2b_core
 	lh2b::DevBuf<uint8_t> instBuildIn;		// per-frame top-level build input
 	lh2b::DevBuf<uint32_t> linkedRoots;
 	int plocRadius = 8, bvhMaxLeaf = 1;	// swept on the 1M-triangle terrain (tools/quality_sweep.py)
+	struct lh2b_gather* gather = nullptr;		// attached multi-GPU gather (gather.cu): frames end with a snapshot for it instead of the local finalize
+	int l2Persist = 1, l2Applied = -1;			// persisting-L2 window over the node arena (ApplyL2Policy)
+	void* l2Base = nullptr; size_t l2Bytes = 0;
 	int bvhRefit = 1;						// same triangle count re-sent: 1 refit in place (binary + wide tree), 2 refit the binary tree and collapse again, 0 rebuild	// work counter of the persistent query kernels
 	// settings
 	int bvhBuilder = 0;				// 0: GPU LBVH (default), 1: host binned SAH

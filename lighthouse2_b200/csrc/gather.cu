@@ -56,6 +56,7 @@ struct lh2b_gather
 	int rank = 0, world = 1;
 	size_t pixels = 0;
 	uint32_t frame = 0;
+	bool snapshotInFrame = false;		// the frame enqueued last already wrote its snapshot (GatherSnapshotTarget)
 	cudaStream_t comm = nullptr;
 	cudaEvent_t snapReady = nullptr;		// core stream: the snapshot of this frame is complete
 	cudaEvent_t slotFree[2] = { nullptr, nullptr };	// comm stream: the local buffer of that parity has been consumed (kernel on rank 0, push elsewhere)
@@ -72,6 +73,15 @@ struct lh2b_gather
 	WaitValue32Fn waitValue = nullptr;
 	MemsetD32AsyncFn memsetD32 = nullptr;
 };
+
+float4* GatherSnapshotTarget( lh2b_gather* g, cudaStream_t coreStream )
+{
+	const uint32_t k = g->frame, slot = k & 1;
+	float4* local = g->rank == 0 ? g->slots + (size_t)slot * g->pixels : g->snap + (size_t)slot * g->pixels;
+	if (k >= 2) CUDA_CHECK( cudaStreamWaitEvent( coreStream, g->slotFree[slot], 0 ) );
+	g->snapshotInFrame = true;
+	return local;
+}
 
 #define API_BEGIN try {
 #define API_END } catch (const std::exception& e) { SetLastError( e.what() ); return 1; } return 0;
@@ -110,6 +120,7 @@ int lh2b_gather_create( lh2b_core* core, int rank, int world, lh2b_gather** out 
 	}
 	else CUDA_CHECK( cudaMalloc( &g->snap, 2 * g->pixels * sizeof( float4 ) ) );
 	CUDA_CHECK( cudaDeviceSynchronize() );
+	core->gather = g;
 	*out = g;
 	API_END
 }
@@ -157,9 +168,13 @@ int lh2b_gather_frame( lh2b_gather* g, int samplesTotal, float* pinnedOut )
 	const size_t bytes = g->pixels * sizeof( float4 );
 	float4* local = g->rank == 0 ? g->slots + (size_t)slot * g->pixels : g->snap + (size_t)slot * g->pixels;	// rank 0 owns slots[0][*]
 	// the local buffer of this parity was last used by frame k-2: its consumer (sum kernel on rank 0, peer copy elsewhere) runs on
-	// the comm stream, the snapshot on the core stream
-	if (k >= 2) CUDA_CHECK( cudaStreamWaitEvent( core->stream, g->slotFree[slot], 0 ) );
-	CUDA_CHECK( cudaMemcpyAsync( local, core->accumulator.ptr, bytes, cudaMemcpyDeviceToDevice, core->stream ) );
+	// the comm stream, the snapshot on the core stream. Normally the frame's own last kernel has written the snapshot already.
+	if (!g->snapshotInFrame)
+	{
+		if (k >= 2) CUDA_CHECK( cudaStreamWaitEvent( core->stream, g->slotFree[slot], 0 ) );
+		CUDA_CHECK( cudaMemcpyAsync( local, core->accumulator.ptr, bytes, cudaMemcpyDeviceToDevice, core->stream ) );
+	}
+	g->snapshotInFrame = false;
 	CUDA_CHECK( cudaEventRecord( g->snapReady, core->stream ) );
 	CUDA_CHECK( cudaStreamWaitEvent( g->comm, g->snapReady, 0 ) );
 	if (g->rank > 0)
@@ -220,6 +235,7 @@ int lh2b_gather_destroy( lh2b_gather* g )
 	if (!g) return 0;
 	cudaSetDevice( g->core->device );
 	cudaStreamSynchronize( g->comm );
+	if (g->core->gather == g) g->core->gather = nullptr;
 	if (g->rank == 0) { for (int r = 1; r < g->world; r++) if (g->peerAck[r]) cudaIpcCloseMemHandle( g->peerAck[r] ); }
 	else { if (g->rootSlots) cudaIpcCloseMemHandle( g->rootSlots ); if (g->rootArrived) cudaIpcCloseMemHandle( g->rootArrived ); }
 	cudaFree( g->slots ), cudaFree( g->arrived ), cudaFree( g->ack ), cudaFree( g->snap ), cudaFree( g->image );

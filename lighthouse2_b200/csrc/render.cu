@@ -246,7 +246,9 @@ static void RenderFrame( lh2b_core* core, const lh2abi::ViewPyramid& view )
 	const int localSamples = (int)((long long)core->samplesTaken * core->spp / total);
 	const int finEv = (int)core->events.size() - 2;
 	CUDA_CHECK( cudaEventRecord( core->events[finEv], s ) );
-	if (core->filterEnabled && core->features.count) RunFilter( core );
+	if (core->gather)	// sharded frame: rank 0 finalizes the sum of all shards (gather.cu); this rank's last kernel is the snapshot for it
+		LaunchFinalize( core->accumulator.ptr, GatherSnapshotTarget( core->gather, s ), core->width * core->height, 1, s );
+	else if (core->filterEnabled && core->features.count) RunFilter( core );
 	else LaunchFinalize( core->accumulator.ptr, core->pixels.ptr, core->width * core->height, localSamples, s );
 	CUDA_CHECK( cudaEventRecord( core->events[finEv + 1], s ) );
 	core->frameInFlight = true;
@@ -319,6 +321,7 @@ int lh2b_setting( lh2b_core* core, const char* name, float value )
 	else if (!strcmp( name, "clampIndirect" )) core->clampIndirect = value;
 	// extensions of this core (the reference fixes these at compile time: core_settings.h:25, pathtracer.h:33)
 	else if (!strcmp( name, "maxPathLength" )) core->maxPathLength = value < 1 ? 1 : (value > LH2B_MAXPATHLENGTH ? LH2B_MAXPATHLENGTH : (int)value);
+	else if (!strcmp( name, "l2Persist" )) core->l2Persist = value > 0 ? 1 : 0;	// takes effect at the next FinalizeInstances
 	else if (!strcmp( name, "pipeline" )) { FinishFrame( core ); core->pipeline = value > 0; }
 	else if (!strcmp( name, "bsdf" )) { const int m = value >= 0.5f ? 1 : 0; if (m != core->bsdfModel) core->bsdfModel = m, core->samplesTaken = 0; }
 	else if (!strcmp( name, "maxDiffuseBounces" )) core->enoughBounces = value <= 0 ? 0 : (value < 2 ? S_BOUNCED : S_BOUNCEDTWICE);

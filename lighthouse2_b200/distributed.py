@@ -115,6 +115,10 @@ class PipelinedShardedRenderer(ShardedRenderer):
         return self._done[(self._k - 1) & 1]
 
 
+import os as _os
+_SKIP_GATHER = _os.environ.get("LH2B_DEBUG_SKIP_GATHER") == "1"   # timing experiments only
+
+
 class PeerGatherRenderer:
     """Sample-sharded frames with the core's own collective (csrc/gather.cu): peers push their accumulator snapshot into
     rank 0's memory with the copy engines over NVLink, rank 0 sums and finalizes in one kernel; hand-shakes are stream memory
@@ -140,7 +144,8 @@ class PeerGatherRenderer:
     def frame(self, view, converge=1, host_out=None):
         self.core.Render(view, converge, True)
         total = self.core.SamplesTaken()
-        self.core.GatherFrame(self.g, total, host_out if self.rank == 0 else None)
+        if not _SKIP_GATHER:
+            self.core.GatherFrame(self.g, total, host_out if self.rank == 0 else None)
         return total
 
     def finish(self):
