@@ -30,6 +30,27 @@ def lib():
     return _lib
 
 
+def set_accel(mode):
+    """0: exhaustive search (the definition, default). 1: the same search pruned by a per-mesh BVH (lh2_oracle_bvh.h);
+    identical results, proven by tests/test_oracle_cpu.py::test_bvh_oracle_equals_exhaustive_search. Returns the old mode."""
+    old = lib().orc_get_accel()
+    lib().orc_set_accel(int(mode))
+    return old
+
+
+class accel:
+    """with orc.accel(1): ... - scoped set_accel."""
+
+    def __init__(self, mode=1):
+        self.mode = mode
+
+    def __enter__(self):
+        self.old = set_accel(self.mode)
+
+    def __exit__(self, *a):
+        set_accel(self.old)
+
+
 def _scene(meshes, instances):
     """meshes: list of float32[3T,4]; instances: list of (meshIdx, 4x4 or None)."""
     keep = [np.ascontiguousarray(m, np.float32).reshape(-1, 4) for m in meshes]

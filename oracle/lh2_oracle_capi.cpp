@@ -1,6 +1,7 @@
 /* lh2_oracle_capi.cpp - TEST INFRASTRUCTURE ONLY. C entry points (ctypes) of the CPU oracle.
    See lh2_oracle_geom.h / lh2_oracle_shade.h for what is restated and from where. */
 #include "lh2_oracle_geom.h"
+#include "lh2_oracle_bvh.h"
 #include <thread>
 #include <vector>
 #include <algorithm>
@@ -20,6 +21,10 @@ template <typename F> static void ParallelFor( int n, int threads, F f )
 	}
 	for (auto& th : pool) th.join();
 }
+
+/* 0: exhaustive search (the definition, default); 1: the same search pruned by a per-mesh BVH (lh2_oracle_bvh.h). */
+ORC_API void orc_set_accel( int mode ) { orc::AccelMode() = mode; }
+ORC_API int orc_get_accel() { return orc::AccelMode(); }
 
 /* hits4: uint32[4*n] = (u16|v16<<16, inst, prim, t bits); prim = 0xffffffff on a miss. */
 ORC_API void orc_closest_hits( const orc::Mesh* meshes, int meshCount, const orc::Instance* instances, int instanceCount,

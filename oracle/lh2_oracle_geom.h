@@ -92,21 +92,36 @@ static inline bool TriTest( const float* O, const float* D, const float* v0, con
 
 struct Hit { float t, u, v; int inst, prim; };
 
+/* Optional pruning structure (lh2_oracle_bvh.h). AccelMode() = 0 (default): exhaustive search, the definition.
+   1: the same search pruned by a per-mesh BVH; identical results (tests/test_oracle_cpu.py), used for full-size checks
+   and as the CPU baseline. */
+struct Accel;
+static inline int& AccelMode() { static int mode = 0; return mode; }
+struct Scene;
+static inline Accel* BuildSceneAccel( const Scene& s );
+static inline void FreeSceneAccel( Accel* a );
+
 struct Scene
 {
 	const Mesh* meshes; int meshCount;
 	const Instance* instances; int instanceCount;
 	float* inverses;	// 12 floats per instance, filled by Prepare
+	Accel* accel = nullptr;
 	void Prepare()
 	{
 		inverses = new float[(size_t)(instanceCount > 0 ? instanceCount : 1) * 12];
 		for (int i = 0; i < instanceCount; i++) InvertAffine( instances[i].xform, inverses + i * 12 );
+		accel = AccelMode() ? BuildSceneAccel( *this ) : nullptr;
 	}
-	void Release() { delete[] inverses; inverses = 0; }
+	void Release() { delete[] inverses; inverses = 0; if (accel) FreeSceneAccel( accel ); accel = nullptr; }
 };
+
+static inline bool AccelClosestHit( const Scene& s, const float* O, const float* D, const float tmin, float tmax, Hit& best );
+static inline bool AccelOccluded( const Scene& s, const float* O, const float* D, const float tmin, const float tmax );
 
 static inline bool ClosestHit( const Scene& s, const float* O, const float* D, const float tmin, float tmax, Hit& best )
 {
+	if (s.accel) return AccelClosestHit( s, O, D, tmin, tmax, best );
 	best.t = tmax, best.inst = -1, best.prim = -1, best.u = best.v = 0;
 	for (int i = 0; i < s.instanceCount; i++)
 	{
@@ -128,6 +143,7 @@ static inline bool ClosestHit( const Scene& s, const float* O, const float* D, c
 
 static inline bool Occluded( const Scene& s, const float* O, const float* D, const float tmin, const float tmax )
 {
+	if (s.accel) return AccelOccluded( s, O, D, tmin, tmax );
 	for (int i = 0; i < s.instanceCount; i++)
 	{
 		const Mesh& m = s.meshes[s.instances[i].mesh];

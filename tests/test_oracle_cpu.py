@@ -87,3 +87,72 @@ def test_skinning_restatement_known_answers():
     j1 = np.tile(np.array([0, 1, 0, 0], np.uint32), (n, 1)); w1 = np.tile(np.array([0.5, 0.5, 0, 0], np.float32), (n, 1))
     gv, _ = orc.skin_mesh(v, t, j1, w1, np.stack([np.eye(4, dtype=np.float32), T2]))
     assert np.allclose(gv[:, 1], v.reshape(-1, 4)[:, 1] + 2.0, atol=1e-6)
+
+
+def _random_rays(rng, n, lo, hi, toward_lo, toward_hi):
+    O = np.zeros((n, 4), np.float32); D = np.zeros((n, 4), np.float32)
+    O[:, :3] = rng.uniform(lo, hi, (n, 3))
+    d = rng.uniform(toward_lo, toward_hi, (n, 3)) - O[:, :3]
+    D[:, :3] = d / np.linalg.norm(d, axis=1, keepdims=True)
+    return O, D
+
+
+def test_bvh_oracle_equals_exhaustive_search():
+    """The BVH of lh2_oracle_bvh.h only prunes the exhaustive search: hit records and occlusion flags are identical, bit for bit,
+    on a terrain (coherent + random rays, rays along grid lines and through shared vertices / edges, axis-parallel rays with zero
+    direction components), on random triangle soup with duplicated triangles, and on a multi-instance scene with transforms."""
+    rng = np.random.default_rng(7)
+    sd = scenes.config2_scene(60, 40, n_materials=1, light_quads=1, seed=0x12345678)
+    verts = sd.meshes[0][0].reshape(-1, 4)
+    O, D = _random_rays(rng, 6000, (-60, 2, -60), (60, 40, 60), (-50, -1, -50), (50, 3, 50))
+    # rays aimed exactly at mesh vertices and edge midpoints (ties between neighbouring triangles)
+    k = rng.integers(0, verts.shape[0] // 3, 1500)
+    tgt = np.concatenate([verts[k * 3, :3], 0.5 * (verts[k * 3, :3] + verts[k * 3 + 1, :3])])
+    O2 = np.zeros((tgt.shape[0], 4), np.float32); D2 = np.zeros_like(O2)
+    O2[:, :3] = (0, 30, -80)
+    d = tgt - O2[:, :3]; D2[:, :3] = d / np.linalg.norm(d, axis=1, keepdims=True)
+    # axis-parallel rays (zero direction components -> inf / NaN in the slab test)
+    O3 = np.zeros((600, 4), np.float32); D3 = np.zeros_like(O3)
+    O3[:, :3] = rng.uniform((-50, 20, -50), (50, 30, 50), (600, 3)); D3[:, 1] = -1
+    O3[:200, :3] = np.round(O3[:200, :3])              # ... some of them exactly over grid lines
+    O, D = np.concatenate([O, O2, O3]), np.concatenate([D, D2, D3])
+    meshes, inst = [verts], [(0, None)]
+    ref = orc.closest_hits(meshes, inst, O, D)
+    Ds = D.copy(); Ds[:, 3] = rng.uniform(0.5, 150, O.shape[0])
+    ref_occ = orc.occluded(meshes, inst, O, Ds)
+    with orc.accel(1):
+        got, got_occ = orc.closest_hits(meshes, inst, O, D), orc.occluded(meshes, inst, O, Ds)
+    assert (ref[:, 2] != 0xFFFFFFFF).sum() > 4000
+    assert np.array_equal(ref, got) and np.array_equal(ref_occ, got_occ)
+    # triangle soup with exact duplicates (equal-t ties inside a mesh) + instances, one of them mirrored and scaled
+    soup = rng.uniform(-1, 1, (400, 3, 4)).astype(np.float32); soup[:, :, 3] = 0
+    soup[:, 1:, :3] = soup[:, :1, :3] + 0.3 * soup[:, 1:, :3]
+    soup = np.concatenate([soup, soup[:50]]).reshape(-1, 4)
+    xf = []
+    for i in range(12):
+        m = np.eye(4, dtype=np.float32); m[:3, 3] = rng.uniform(-4, 4, 3)
+        a = rng.uniform(0, 6.28); m[0, 0], m[0, 2], m[2, 0], m[2, 2] = np.cos(a), -np.sin(a), np.sin(a), np.cos(a)
+        if i == 3: m[:3, :3] *= np.float32([-1.5, 1.5, 1.5])[None]
+        xf.append((i % 2, m if i else None))
+    xf.append((0, xf[5][1]))                               # coincident instances: equal-t ties across instances
+    meshes = [soup, scenes.quad((0, -2, 0), (0, 1, 0), 30, 30).reshape(-1, 4)]
+    O, D = _random_rays(rng, 5000, (-8, -1, -8), (8, 6, 8), (-5, -2, -5), (5, 2, 5))
+    Ds = D.copy(); Ds[:, 3] = rng.uniform(0.5, 20, O.shape[0])
+    ref, ref_occ = orc.closest_hits(meshes, xf, O, D), orc.occluded(meshes, xf, O, Ds)
+    with orc.accel(1):
+        got, got_occ = orc.closest_hits(meshes, xf, O, D), orc.occluded(meshes, xf, O, Ds)
+    assert np.array_equal(ref, got) and np.array_equal(ref_occ, got_occ)
+    assert len(set(ref[:, 1].tolist())) > 5
+
+
+def test_bvh_oracle_full_frame_equals_exhaustive_frame():
+    """Same frame oracle with and without the BVH: identical accumulators and ray counts."""
+    sd = scenes.config2_scene(40, 30, n_materials=4, light_quads=2, seed=0x12345678)
+    W, H = 48, 27
+    view = scenes.view_pyramid((0, 30, -80), (0, 0, 0), 40, W, H)
+    o = orc.FrameOracle(sd, W, H, 2, 1e-3, 10.0, 3, 1, threads=4)
+    a = o.render(view, 1).copy(); ca = tuple(o.ray_counts)
+    with orc.accel(1):
+        o2 = orc.FrameOracle(sd, W, H, 2, 1e-3, 10.0, 3, 1, threads=4)
+        b = o2.render(view, 1).copy(); cb = tuple(o2.ray_counts)
+    assert ca == cb and np.array_equal(a, b)

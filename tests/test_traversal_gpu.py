@@ -152,3 +152,32 @@ def test_many_instances():
     O, D = scenes.random_rays(8000, extent=16, seed=34)
     hits = _check([m0, m1], inst, O, D, shadow_tmax=10.0)
     assert hits > 500
+
+
+def test_full_size_c2_frame_rays():
+    """BASELINE.json configs[1] at full size: the 1,000,002-triangle bench scene, all 2,073,600 primary rays of the 1920x1080
+    frame and as many shadow-type queries, bit-exact against the CPU oracle (exhaustive search pruned by the oracle's own BVH,
+    which tests/test_oracle_cpu.py proves identical to the unpruned search)."""
+    import bench
+    sd, view = bench.build_scene()
+    meshes = [m[0] for m in sd.meshes]
+    O, D = scenes.camera_rays(view, bench.W, bench.H)
+    assert O.shape[0] == bench.W * bench.H
+    with orc.accel(1):
+        hits = _check(meshes, list(sd.instances), O, D, shadow_tmax=45.0)
+    assert hits > bench.W * bench.H // 3
+
+
+def test_full_size_instanced_two_level():
+    """configs[3] shape: 1000 transformed instances of 10 meshes (100 k triangles each here), 400 k random rays, two-level
+    traversal bit-exact against the BVH-pruned oracle."""
+    rng = np.random.default_rng(41)
+    meshes = [scenes.terrain(250, 200, extent=3.0, seed=50 + i) for i in range(10)]
+    inst = []
+    for i in range(1000):
+        t = (rng.random(3) * 2 - 1) * [60, 10, 60]
+        inst.append((i % 10, _rot(rng.standard_normal(3), rng.random() * 6.28, t, 0.5 + rng.random())))
+    O, D = scenes.random_rays(400000, extent=70, seed=42)
+    with orc.accel(1):
+        hits = _check(meshes, inst, O, D, shadow_tmax=50.0)
+    assert hits > 20000
