@@ -168,3 +168,41 @@ def test_pipelined_frames_match_blocking_frames():
     for k in range(len(views)):
         assert np.array_equal(pinned[k].numpy(), want_px[k]), k
     a.Shutdown(), b.Shutdown()
+
+
+def _compare_full(sd, w, h, spp, maxlen, bounces, view):
+    core = RenderCore()
+    core.SetTarget(w, h, spp)
+    core.Setting("epsilon", 1e-3)
+    core.Setting("clampValue", 10.0)
+    core.Setting("maxPathLength", maxlen)
+    core.Setting("maxDiffuseBounces", bounces)
+    sd.upload(core)
+    with orc.accel(1):                       # BVH-pruned oracle: identical to its exhaustive search (tests/test_oracle_cpu.py)
+        oracle = orc.FrameOracle(sd, w, h, spp, 1e-3, 10.0, maxlen, bounces)
+        core.Render(view, 1)
+        got, want = core.ReadPixels(), oracle.render(view, 1)
+    st = core.GetCoreStats()
+    r, f = rel_rmse(got, want), pixel_mismatch_fraction(got, want)
+    ext, shd = oracle.ray_counts
+    core.Shutdown()
+    assert np.isfinite(got).all() and r < REL_RMSE_TOL and f < MISMATCH_TOL, (r, f)
+    assert abs(int(st["totalExtensionRays"]) - ext) <= max(8, ext // 2000), (st["totalExtensionRays"], ext)
+    assert abs(int(st["totalShadowRays"]) - shd) <= max(8, shd // 2000), (st["totalShadowRays"], shd)
+    return r, f
+
+
+def test_full_size_c2_frame():
+    """BASELINE.json configs[1] at full size - the bench workload itself (1,000,002 triangles, 1920x1080, path length 1):
+    every pixel of the frame against the CPU oracle frame, same seeds."""
+    import bench
+    sd, view = bench.build_scene()
+    _compare_full(sd, bench.W, bench.H, 1, 1, 1, view)
+
+
+def test_full_size_c3_frame():
+    """configs[2] shape at full resolution: 1 M triangles, 64 materials, 8 emissive quads, 1920x1080, path length 8 with two
+    diffuse bounces, NEE + MIS; 2 spp per Render here (16 in the config) so that the CPU oracle finishes in seconds."""
+    sd = scenes.config2_scene(1000, 500, n_materials=64, light_quads=8)
+    view = scenes.view_pyramid((0, 30, -80), (0, 0, 0), 40, 1920, 1080)
+    _compare_full(sd, 1920, 1080, 2, 8, 2, view)
