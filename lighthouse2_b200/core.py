@@ -67,7 +67,7 @@ class RenderCore:
         n = len(texels_list)
         descs = np.zeros(max(n, 1), dtype=abi.CoreTexDesc)
         self._tex_keepalive = []
-        for i, (tex, storage, w, h, mips) in enumerate(texels_list):
+        for i, (tex, storage, w, h, mips, *flags) in enumerate(texels_list):
             tex = np.ascontiguousarray(tex)
             self._tex_keepalive.append(tex)
             descs[i]["data"] = tex.ctypes.data
@@ -75,6 +75,7 @@ class RenderCore:
             descs[i]["pixelCount"] = tex.size // 4
             descs[i]["MIPlevels"] = mips
             descs[i]["storage"] = storage
+            descs[i]["flags"] = flags[0] if flags else 0
         self._check(self._lib.lh2b_set_textures(self._h, _ptr(descs), n))
         return descs[:n]
 

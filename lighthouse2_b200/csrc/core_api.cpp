@@ -12,11 +12,20 @@
    buffer. If the host process has OpenGL loaded and the target texture ID is non-zero, the finished
    frame is additionally uploaded with glTexSubImage2D (resolved at run time; no link dependency),
    which is enough for the reference's windowed apps to show the image.
+
+   Personas: the reference ships the plain path tracer and the filtering path tracer as two libraries
+   (RenderCore_Optix7, RenderCore_Optix7Filter) and RenderSystem sends "filter", "TAA", "clampDirect",
+   "clampIndirect" to whichever is loaded (rendersystem.cpp:220-226); the plain core ignores those names
+   (rendercore.cpp:746-760). One library serves both here: CreateCore() - loaded as RenderCore_B200 -
+   behaves as the plain core and drops those four names, CreateCoreFilter() - what libRenderCore_B200Filter.so's
+   CreateCore forwards to - passes them on to the SVGF / TAA chain. LH2B_PERSONA=filter|plain overrides.
 */
 #include "../../include/lh2_core_api.h"
 #include "../../include/lh2b.h"
 #include <dlfcn.h>
 #include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
 #include <vector>
 
 using namespace lh2abi;
@@ -30,6 +39,7 @@ typedef void (*glTexSubImage2DFn)(unsigned, int, int, int, int, int, unsigned, u
 class RenderCoreB200 : public CoreAPI_Base
 {
 public:
+	explicit RenderCoreB200( bool filterPersona ) : filterCore( filterPersona ) {}
 	CoreStats GetCoreStats() const override
 	{
 		CoreStats s = {};
@@ -45,7 +55,12 @@ public:
 		glTexture = target->ID, width = (int)target->width, height = (int)target->height;
 		Check( lh2b_set_target( core, width, height, (int)spp ), "SetTarget" );
 	}
-	void Setting( const char* name, float value ) override { if (core) Check( lh2b_setting( core, name, value ), "Setting" ); }
+	void Setting( const char* name, float value ) override
+	{
+		if (!core || !name) return;
+		if (!filterCore && (!strcmp( name, "filter" ) || !strcmp( name, "TAA" ) || !strcmp( name, "clampDirect" ) || !strcmp( name, "clampIndirect" ))) return;
+		Check( lh2b_setting( core, name, value ), "Setting" );
+	}
 	void Render( const ViewPyramid& view, const Convergence converge, bool async ) override
 	{
 		if (!core) return;
@@ -99,6 +114,7 @@ private:
 		sub( 0x0DE1, 0, 0, 0, width, height, 0x1908 /* GL_RGBA */, 0x1406 /* GL_FLOAT */, staging.data() );
 	}
 	lh2b_core* core = nullptr;
+	bool filterCore = false;
 	unsigned glTexture = 0;
 	int width = 0, height = 0;
 	std::vector<float> staging;
@@ -106,9 +122,22 @@ private:
 
 } // namespace
 
+static bool PersonaOverride( bool filter )
+{
+	const char* e = getenv( "LH2B_PERSONA" );
+	if (e && !strcmp( e, "filter" )) return true;
+	if (e && !strcmp( e, "plain" )) return false;
+	return filter;
+}
+
 extern "C" __attribute__( ( visibility( "default" ) ) ) lh2abi::CoreAPI_Base* CreateCore()
 {
-	return new RenderCoreB200();
+	return new RenderCoreB200( PersonaOverride( false ) );
+}
+
+extern "C" __attribute__( ( visibility( "default" ) ) ) lh2abi::CoreAPI_Base* CreateCoreFilter()
+{
+	return new RenderCoreB200( PersonaOverride( true ) );
 }
 
 /* Accessor for hosts that hold the C++ object but want the C handle (headless read-back, statistics). */

@@ -203,7 +203,7 @@ class SceneDesc:
     def upload(self, core):
         """Issue the calls in the order RenderSystem::SynchronizeSceneData does (rendersystem.cpp:203-211)."""
         if self.sky is not None:
-            core.SetSkyData(self.sky[0], self.sky[1], self.sky[2])
+            core.SetSkyData(*self.sky)      # (pixels, w, h[, worldToLight])
         if self.textures:
             core.SetTextures(self.textures)
         core.SetMaterials(self.materials)

@@ -201,11 +201,12 @@ class FrameOracle:
                 mats[i].uvscale[k][:] = [float(x) for x in m[n]["uvscale"]]
                 mats[i].uvoffset[k][:] = [float(x) for x in m[n]["uvoffset"]]
         texs = (OrcTexDesc * max(len(sd.textures), 1))()
-        for i, (tex, storage, w, h, mips) in enumerate(sd.textures):
+        for i, (tex, storage, w, h, mips, *flags) in enumerate(sd.textures):
             tex = np.ascontiguousarray(tex)
             keep.append(tex)
             texs[i].data, texs[i].width, texs[i].height = tex.ctypes.data, w, h
             texs[i].pixelCount, texs[i].mipLevels, texs[i].storage = tex.size // 4, mips, storage
+            texs[i].flags = flags[0] if flags else 0      # HostTexture flags (HDR = 8 matters: rendercore.cpp:539)
         f = OrcFrameIn()
         f.meshes, f.coreTris, f.meshCount = ctypes.addressof(cm), ctypes.addressof(ct), len(verts)
         f.instances, f.instanceCount = ctypes.addressof(ci), len(sd.instances)
@@ -221,7 +222,8 @@ class FrameOracle:
             sky = np.ascontiguousarray(sd.sky[0], np.float32)
             keep.append(sky)
             f.skyPixels, f.skyW, f.skyH = sky.ctypes.data, sd.sky[1], sd.sky[2]
-        f.worldToSky[:] = [float(x) for x in np.eye(4, dtype=np.float32).flat]
+        sky_xf = sd.sky[3] if sd.sky is not None and len(sd.sky) > 3 else np.eye(4, dtype=np.float32)
+        f.worldToSky[:] = [float(x) for x in np.asarray(sky_xf, np.float32).flat]
         bn = np.fromfile(_BLUENOISE, dtype=np.uint8)
         keep.append(bn)
         f.blueNoiseBytes = bn.ctypes.data
@@ -429,3 +431,61 @@ def morph_mesh(verts, tris, deltas4, normals4, weights):
     P = lambda a: ctypes.c_void_p(a.ctypes.data)
     lib().orc_morph_mesh(P(v0), P(bn), P(d), P(n), P(w), len(w), len(out_t), P(out_v), P(out_t))
     return out_v, out_t
+
+
+# ---- scenes recorded from the reference RenderSystem (oracle/ref_recorder_core.cpp) ------------------------------------------
+def load_recording(path):
+    """Parses the file oracle/_ref/libRenderCore_Recorder.so writes on Render: everything the reference RenderSystem sent through
+    the CoreAPI_Base calls. Returns (SceneDesc, info) with info = {view (ViewPyramid record), width, height, spp, settings{name:
+    value}, converge, probe}. Later calls supersede earlier ones the way a core would apply them."""
+    import struct
+    from lighthouse2_b200 import abi, scenes
+    raw = open(path, "rb").read()
+    pos, verts, tris, inst, texdescs, texels = 0, {}, {}, {}, None, {}
+    sd, info = scenes.SceneDesc(), {"settings": {}, "probe": None}
+    sky, skyxf = None, None
+    while pos < len(raw):
+        tag = raw[pos:pos + 16].split(b"\0")[0].decode()
+        a, b, n = struct.unpack_from("<QQQ", raw, pos + 16)
+        data = raw[pos + 40:pos + 40 + n]
+        pos += 40 + n
+        if tag == "verts":
+            verts[a] = np.frombuffer(data, np.float32).reshape(-1, 4).copy()
+        elif tag == "tris":
+            tris[a] = np.frombuffer(data, abi.CoreTri).copy()
+        elif tag == "instance":
+            model = struct.unpack("<q", struct.pack("<Q", b))[0]
+            if model == -1:
+                inst = {k: v for k, v in inst.items() if k < a}
+            else:
+                inst[a] = (int(model), np.frombuffer(data, np.float32).reshape(4, 4).copy())
+        elif tag == "materials":
+            sd.materials = np.frombuffer(data, abi.CoreMaterial).copy()
+        elif tag == "texdescs":
+            texdescs, texels = np.frombuffer(data, abi.CoreTexDesc).copy(), {}
+        elif tag == "texels":
+            texels[a] = np.frombuffer(data, np.float32 if b == 1 else np.uint8).copy()
+        elif tag in ("trilights", "pointlights", "spotlights", "dirlights"):
+            dt = {"trilights": abi.CoreLightTri, "pointlights": abi.CorePointLight, "spotlights": abi.CoreSpotLight, "dirlights": abi.CoreDirectionalLight}[tag]
+            setattr(sd, {"trilights": "tri_lights", "pointlights": "point_lights", "spotlights": "spot_lights", "dirlights": "dir_lights"}[tag],
+                    np.frombuffer(data, dt).copy())
+        elif tag == "sky":
+            sky = (np.frombuffer(data, np.float32).reshape(int(b), int(a), 3).copy(), int(a), int(b))
+        elif tag == "skyxform":
+            skyxf = np.frombuffer(data, np.float32).reshape(4, 4).copy()
+        elif tag == "target":
+            info["width"], info["height"], info["spp"] = (int(x) for x in np.frombuffer(data, np.uint32))
+        elif tag == "setting":
+            info["settings"][data[:60].split(b"\0")[0].decode()] = float(np.frombuffer(data[60:64], np.float32)[0])
+        elif tag == "view":
+            info["view"], info["converge"] = np.frombuffer(data, abi.ViewPyramid).copy(), int(b)
+        elif tag == "probe":
+            info["probe"] = tuple(int(x) for x in np.frombuffer(data, np.int32))
+    sd.meshes = [(verts[i], tris[i]) for i in sorted(verts)]
+    sd.instances = [inst[i] for i in sorted(inst)]
+    if sky is not None:
+        sd.sky = sky if skyxf is None else sky + (skyxf,)
+    if texdescs is not None:
+        for i, d in enumerate(texdescs):
+            sd.textures.append((texels[i], int(d["storage"]), int(d["width"]), int(d["height"]), int(d["MIPlevels"]), int(d["flags"])))
+    return sd, info
