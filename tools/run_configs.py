@@ -23,29 +23,50 @@ def frame_stats(core, view, frames, converge=1):
 
 
 if "c1" in which:
-    # C1: tinyapp-like scene (procedural stand-in: floor, a few hundred boxes' worth of triangles, the 6.9 x 6.9 light quad at
-    # y = 26 with colour (100,100,80)), 640x360, 1 spp, path length 3, camera.xml values; GPU vs CPU oracle, same seeds.
+    # C1: the literal tinyapp scene (pica glTF + light quad + legocar.obj, camera.xml) as the reference's own RenderSystem hands it
+    # to a core (recorded with oracle/_ref/libRenderCore_Recorder.so through oracle/_ref/tinyapp_ref_host), 640x360, 1 spp, path
+    # length 3: GPU core vs CPU oracle (BVH-pruned), same seeds. Falls back to a procedural stand-in when oracle/_ref is absent.
     from oracle import binding as orc
-    from tests_util_shim import rel_rmse
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+    import test_rendersystem_dropin as rs
     W, H = 640, 360
-    sd = scenes.config2_scene(40, 30, n_materials=5, light_quads=1, floaters=1500, seed=42)
-    view = scenes.view_pyramid((-19.17, 9.19, 33.1), (-13.5, 7.99, 24.95), 40, W, H, focal_distance=5.0, aperture=1e-4, distortion=0.05)
+    literal = os.path.exists(rs.HOST) and os.path.exists(rs.RECORDER)
+    if literal:
+        rs.run_host(rs.RECORDER, "/tmp/none.bin", frames=1, w=W, h=H, record="/tmp/c1.rec")
+        sd, info = orc.load_recording("/tmp/c1.rec")
+        view = info["view"]
+        t0 = time.perf_counter(); host = rs.run_host(rs.CORE, "/tmp/c1_frame.bin", frames=20, w=W, h=H); host_s = time.perf_counter() - t0
+    else:
+        sd = scenes.config2_scene(40, 30, n_materials=5, light_quads=1, floaters=1500, seed=42)
+        view = scenes.view_pyramid((-19.17, 9.19, 33.1), (-13.5, 7.99, 24.95), 40, W, H, focal_distance=5.0, aperture=1e-4, distortion=0.05)
     core = RenderCore(0); core.SetTarget(W, H, 1); core.Setting("epsilon", 1e-3); core.Setting("clampValue", 10); sd.upload(core)
     core.SetProbePos(W // 2, H // 2)
     a = frame_stats(core, view, 6)
     core.Render(view, 1); img = core.ReadPixels(); st = core.GetCoreStats()
+    orc.set_accel(1)
+    o = orc.FrameOracle(sd, W, H, 1, 1e-3, 10.0, 3, 1)
+    o.render(view, 1)                                    # builds and caches the oracle's BVHs
     o = orc.FrameOracle(sd, W, H, 1, 1e-3, 10.0, 3, 1)
     t0 = time.perf_counter(); _, rec = o.render(view, 1, records=True); cpu_s = time.perf_counter() - t0
     # the oracle frame above is frame 1 of its own sequence; rebuild one in lock-step with the core's 7th Restart frame
     o2 = orc.FrameOracle(sd, W, H, 1, 1e-3, 10.0, 3, 1)
     for _ in range(7):
         want = o2.render(view, 1)
+    orc.set_accel(0)
+    frac, rr, energy = rs.frames_agree(img, want)
     probe = rec[W // 2 + (H // 2) * W]["hit"]
-    res["c1"] = {"resolution": [W, H], "triangles": int(sum(len(t) for _, t in sd.meshes)), "gpu_ms_per_frame": a["totalMs"],
-                 "gpu_rays_per_frame": a["extensionRays"] + a["shadowRays"], "rel_rmse_vs_oracle": rel_rmse(img, want),
+    res["c1"] = {"scene": "tinyapp (pica/scene.gltf + light quad + legocar.obj) via the reference RenderSystem" if literal else "procedural stand-in",
+                 "resolution": [W, H], "meshes": len(sd.meshes), "instances": len(sd.instances), "triangles": int(sum(len(t) for _, t in sd.meshes)),
+                 "gpu_ms_per_frame": a["totalMs"], "gpu_rays_per_frame": a["extensionRays"] + a["shadowRays"],
+                 "gpu_mrays_per_s": (a["extensionRays"] + a["shadowRays"]) / a["totalMs"] / 1e3,
+                 "flipped_pixel_fraction": float(frac), "rel_rmse_other_pixels": float(rr), "energy_difference": float(energy),
                  "probe_gpu": [int(st["probedInstid"]), int(st["probedTriid"]), float(st["probedDist"])],
                  "probe_oracle_frame1": [int(probe[1]), int(probe[2]), float(probe[3:4].view(np.float32)[0])],
-                 "cpu_oracle_seconds": cpu_s, "cpu_oracle_mrays_per_s": sum(o.ray_counts) / cpu_s / 1e6, "cpu_threads": os.cpu_count()}
+                 "cpu_oracle_seconds": cpu_s, "cpu_oracle_mrays_per_s": sum(o.ray_counts) / cpu_s / 1e6, "cpu_threads": os.cpu_count(),
+                 "cpu_oracle_kind": "scalar C++ port, BVH-pruned ray queries"}
+    if literal:
+        res["c1"]["through_reference_rendersystem"] = {"frames": 20, "wall_s_incl_scene_load": host_s, "core_render_ms_last_frame": host["renderTime"] * 1e3,
+                                                       "rays_last_frame": host["totalRays"]}
     core.Shutdown()
     print("c1", res["c1"], flush=True)
 
