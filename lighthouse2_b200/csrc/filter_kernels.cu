@@ -134,20 +134,21 @@ __device__ __forceinline__ void ReadTexelConsistent2( const float4* __restrict__
 }
 
 /* ---- prepare (finalize_shared.h:169-314) ------------------------------------------------------------------------ */
-__device__ __forceinline__ float WorldDistance( const int x, const int y, const float4 cur, const float4* __restrict__ prevWorldPos, const int w, const int h )
+/* curN = UnpackNormal2( cur.w ), unpacked once per pixel by the caller instead of once per texel (16 texels per search step) */
+__device__ __forceinline__ float WorldDistance( const int x, const int y, const float4 cur, const float3 curN, const float4* __restrict__ prevWorldPos, const int w, const int h )
 {
 	const float4 p = ReadWorldPos( prevWorldPos, x, y, w, h );
 	if ((__float_as_uint( p.w ) & 3) != 1) return 1e21f;
-	if (dot( UnpackNormal2( __float_as_uint( cur.w ) ), UnpackNormal2( __float_as_uint( p.w ) ) ) < 0.85f) return 1e21f;
+	if (dot( curN, UnpackNormal2( __float_as_uint( p.w ) ) ) < 0.85f) return 1e21f;
 	return sqrtf( sqrLen( make_float3( cur.x - p.x, cur.y - p.y, cur.z - p.z ) ) );
 }
-__device__ __forceinline__ float FineWorldDistance( const float px, const float py, const float4 cur, const float4* __restrict__ prevWorldPos, const int w, const int h )
+__device__ __forceinline__ float FineWorldDistance( const float px, const float py, const float4 cur, const float3 curN, const float4* __restrict__ prevWorldPos, const int w, const int h )
 {
 	const int x0 = (int)px, y0 = (int)py;
 	const float fx = px - floorf( px ), fy = py - floorf( py );
 	const float w0 = (1 - fx) * (1 - fy), w1 = fx * (1 - fy), w2 = (1 - fx) * fy, w3 = fx * fy;
-	const float d0 = WorldDistance( x0, y0, cur, prevWorldPos, w, h ), d1 = WorldDistance( x0 + 1, y0, cur, prevWorldPos, w, h );
-	const float d2 = WorldDistance( x0, y0 + 1, cur, prevWorldPos, w, h ), d3 = WorldDistance( x0 + 1, y0 + 1, cur, prevWorldPos, w, h );
+	const float d0 = WorldDistance( x0, y0, cur, curN, prevWorldPos, w, h ), d1 = WorldDistance( x0 + 1, y0, cur, curN, prevWorldPos, w, h );
+	const float d2 = WorldDistance( x0, y0 + 1, cur, curN, prevWorldPos, w, h ), d3 = WorldDistance( x0 + 1, y0 + 1, cur, curN, prevWorldPos, w, h );
 	float totalWeight = 0, totalDist = 0;
 	if (d0 < 1e20f) totalDist += d0 * w0, totalWeight += w0;
 	if (d1 < 1e20f) totalDist += d1 * w1, totalWeight += w1;
@@ -165,60 +166,25 @@ struct PrepareArgs
 	int w, h; float pixelValueScale, directClamp, indirectClamp; int camIsStationary;
 };
 
-__global__ void __launch_bounds__( 256 ) prepareKernel( const PrepareArgs a )
+/* Per-pixel inputs of prepare: demodulated, clamped light (written to 'shading' by the first pass only) and its luminances. */
+struct PrepareLocal { float lumDirect, lumDirect2, lumIndirect, lumIndirect2; };
+__device__ __forceinline__ PrepareLocal PrepareLight( const PrepareArgs& a, const int pixelIdx, const uint4 feat, const bool store )
 {
-	const int x = threadIdx.x + blockIdx.x * blockDim.x, y = threadIdx.y + blockIdx.y * blockDim.y;
-	if (x >= a.w || y >= a.h) return;
-	const int pixelIdx = x + y * a.w;
 	const float3 direct = xyz( a.accumulator[pixelIdx] ) * a.pixelValueScale;
-	const uint4 feat = a.features[pixelIdx];
-	const float4 lwp = a.worldPos[pixelIdx];
 	const float3 albedo = RGB32toHDRmin1( feat.x );
 	const float3 indirect = xyz( a.accumulator[pixelIdx + a.w * a.h] ) * a.pixelValueScale;
 	const float3 reci = make_float3( 1.0f / albedo.x, 1.0f / albedo.y, 1.0f / albedo.z );
 	const float3 directLight = min3f( direct * reci, a.directClamp ), indirectLight = min3f( indirect * reci, a.indirectClamp );
-	a.shading[pixelIdx] = CombineToFloat4( directLight, indirectLight );
-	float lumDirect = Luminance( directLight ), lumDirect2 = lumDirect * lumDirect;
-	float lumIndirect = Luminance( indirectLight ), lumIndirect2 = lumIndirect * lumIndirect;
-	float2 prev;
-	if (((feat.w >> 4) & 3) == 0)
-	{
-		// diffuse: analytic reprojection into the previous view
-		const float3 D = xyz( lwp ) - xyz( a.prevPos );
-		const float il = rsqrtf( dot( D, D ) );
-		const float3 Dn = D * il;
-		const float t = a.prevPos.w / dot( xyz( a.prevE ), Dn );
-		const float3 S = xyz( a.prevPos ) + Dn * t;
-		prev = make_float2( dot( S, xyz( a.prevRight ) ) - a.prevRight.w - a.j0, dot( S, xyz( a.prevUp ) ) - a.prevUp.w - a.j1 );
-	}
-	else
-	{
-		prev = make_float2( (float)x, (float)y );
-		if (!a.camIsStationary)
-		{
-			// specular: diamond search for the world position of this pixel in the previous frame
-			const float4 pw = a.prevWorldPos[pixelIdx];
-			float bestDist = sqrtf( sqrLen( make_float3( lwp.x - pw.x, lwp.y - pw.y, lwp.z - pw.z ) ) ), stepSize = 5.0f;
-			const float ox = a.j0 - a.prevj0, oy = a.j1 - a.prevj1;
-			int iter = 0;
-			while (1)
-			{
-				int tap = 0;
-				const float cx = prev.x, cy = prev.y;
-				float d;
-				d = FineWorldDistance( cx - stepSize + ox, cy + oy, lwp, a.prevWorldPos, a.w, a.h );
-				if (d < bestDist) bestDist = d, prev = make_float2( cx - stepSize, cy ), tap = 1;
-				d = FineWorldDistance( cx + stepSize + ox, cy + oy, lwp, a.prevWorldPos, a.w, a.h );
-				if (d < bestDist) bestDist = d, prev = make_float2( cx + stepSize, cy ), tap = 2;
-				d = FineWorldDistance( cx + ox, cy - stepSize + oy, lwp, a.prevWorldPos, a.w, a.h );
-				if (d < bestDist) bestDist = d, prev = make_float2( cx, cy - stepSize ), tap = 3;
-				d = FineWorldDistance( cx + ox, cy + stepSize + oy, lwp, a.prevWorldPos, a.w, a.h );
-				if (d < bestDist) bestDist = d, prev = make_float2( cx, cy + stepSize ), tap = 4;
-				if (tap == 0) { stepSize *= 0.45f; if (stepSize < 0.05f) break; }
-				if (++iter == 25) break;
-			}
-		}
-	}
+	if (store) a.shading[pixelIdx] = CombineToFloat4( directLight, indirectLight );
+	PrepareLocal l;
+	l.lumDirect = Luminance( directLight ), l.lumDirect2 = l.lumDirect * l.lumDirect;
+	l.lumIndirect = Luminance( indirectLight ), l.lumIndirect2 = l.lumIndirect * l.lumIndirect;
+	return l;
+}
+
+/* History lookup at the reprojected position, moments, history counter, motion vector (finalize_shared.h:286-313). */
+__device__ __forceinline__ void PrepareFinish( const PrepareArgs& a, const int pixelIdx, const uint4 feat, const float4 lwp, float2 prev, PrepareLocal l )
+{
 	prev.x += 0.5f, prev.y += 0.5f;
 	uint32_t fw = feat.w;
 	if (prev.x >= 0 && prev.x < a.w && prev.y >= 0 && prev.y < a.h)
@@ -226,8 +192,8 @@ __global__ void __launch_bounds__( 256 ) prepareKernel( const PrepareArgs a )
 		const float4 history = ReadTexelConsistent( a.prevMoments, a.prevWorldPos, lwp, UnpackNormal2( feat.y ), prev.x, prev.y, a.w, a.h );
 		if (history.x > -1)
 		{
-			lumDirect = 0.2f * lumDirect + 0.8f * history.x, lumDirect2 = 0.2f * lumDirect2 + 0.8f * history.y;
-			lumIndirect = 0.2f * lumIndirect + 0.8f * history.z, lumIndirect2 = 0.2f * lumIndirect2 + 0.8f * history.w;
+			l.lumDirect = 0.2f * l.lumDirect + 0.8f * history.x, l.lumDirect2 = 0.2f * l.lumDirect2 + 0.8f * history.y;
+			l.lumIndirect = 0.2f * l.lumIndirect + 0.8f * history.z, l.lumIndirect2 = 0.2f * l.lumIndirect2 + 0.8f * history.w;
 			if ((fw & 15) < 15) fw++;
 		}
 		else fw &= 0xfffffff0u;
@@ -235,7 +201,160 @@ __global__ void __launch_bounds__( 256 ) prepareKernel( const PrepareArgs a )
 	else fw &= 0xfffffff0u;
 	if (fw != feat.w) a.features[pixelIdx].w = fw;
 	a.motion[pixelIdx] = prev;
-	a.moments[pixelIdx] = make_float4( lumDirect, lumDirect2, lumIndirect, lumIndirect2 );
+	a.moments[pixelIdx] = make_float4( l.lumDirect, l.lumDirect2, l.lumIndirect, l.lumIndirect2 );
+}
+
+/* specular pixels under a moving camera: diamond search for the world position of this pixel in the previous frame (:255-284) */
+__device__ __forceinline__ float2 DiamondSearch( const PrepareArgs& a, const int pixelIdx, const int x, const int y, const float4 lwp )
+{
+	float2 prev = make_float2( (float)x, (float)y );
+	const float4 pw = a.prevWorldPos[pixelIdx];
+	const float3 lwpN = UnpackNormal2( __float_as_uint( lwp.w ) );
+	float bestDist = sqrtf( sqrLen( make_float3( lwp.x - pw.x, lwp.y - pw.y, lwp.z - pw.z ) ) ), stepSize = 5.0f;
+	const float ox = a.j0 - a.prevj0, oy = a.j1 - a.prevj1;
+	int iter = 0;
+	while (1)
+	{
+		int tap = 0;
+		const float cx = prev.x, cy = prev.y;
+		float d;
+		d = FineWorldDistance( cx - stepSize + ox, cy + oy, lwp, lwpN, a.prevWorldPos, a.w, a.h );
+		if (d < bestDist) bestDist = d, prev = make_float2( cx - stepSize, cy ), tap = 1;
+		d = FineWorldDistance( cx + stepSize + ox, cy + oy, lwp, lwpN, a.prevWorldPos, a.w, a.h );
+		if (d < bestDist) bestDist = d, prev = make_float2( cx + stepSize, cy ), tap = 2;
+		d = FineWorldDistance( cx + ox, cy - stepSize + oy, lwp, lwpN, a.prevWorldPos, a.w, a.h );
+		if (d < bestDist) bestDist = d, prev = make_float2( cx, cy - stepSize ), tap = 3;
+		d = FineWorldDistance( cx + ox, cy + stepSize + oy, lwp, lwpN, a.prevWorldPos, a.w, a.h );
+		if (d < bestDist) bestDist = d, prev = make_float2( cx, cy + stepSize ), tap = 4;
+		if (tap == 0) { stepSize *= 0.45f; if (stepSize < 0.05f) break; }
+		if (++iter == 25) break;
+	}
+	return prev;
+}
+
+/* First pass over all pixels. The diamond search is up to 25 x 16 dependent gathers that only specular pixels under a moving
+   camera run; inside a 16 x 2-pixel warp that left 13 of 32 lanes working for 93 % of the kernel's instructions (ncu, C5).
+   With a queue (DEFER) those pixels are appended - one warp-aggregated atomicAdd - and finished by prepareSearchKernel
+   with full warps; everything a pixel writes is its own, so the split changes no value. */
+template <bool DEFER> __global__ void __launch_bounds__( 256 ) prepareKernel( const PrepareArgs a, uint32_t* __restrict__ queue, uint32_t* __restrict__ queueCount )
+{
+	const int x = threadIdx.x + blockIdx.x * blockDim.x, y = threadIdx.y + blockIdx.y * blockDim.y;
+	const bool inside = x < a.w && y < a.h;
+	const int pixelIdx = inside ? x + y * a.w : 0;
+	bool defer = false;
+	if (inside)
+	{
+		const uint4 feat = a.features[pixelIdx];
+		const float4 lwp = a.worldPos[pixelIdx];
+		const PrepareLocal l = PrepareLight( a, pixelIdx, feat, true );
+		float2 prev;
+		if (((feat.w >> 4) & 3) == 0)
+		{
+			// diffuse: analytic reprojection into the previous view
+			const float3 D = xyz( lwp ) - xyz( a.prevPos );
+			const float il = rsqrtf( dot( D, D ) );
+			const float3 Dn = D * il;
+			const float t = a.prevPos.w / dot( xyz( a.prevE ), Dn );
+			const float3 S = xyz( a.prevPos ) + Dn * t;
+			prev = make_float2( dot( S, xyz( a.prevRight ) ) - a.prevRight.w - a.j0, dot( S, xyz( a.prevUp ) ) - a.prevUp.w - a.j1 );
+		}
+		else if (a.camIsStationary) prev = make_float2( (float)x, (float)y );
+		else if (DEFER) defer = true;
+		else prev = DiamondSearch( a, pixelIdx, x, y, lwp );
+		if (!defer) PrepareFinish( a, pixelIdx, feat, lwp, prev, l );
+	}
+	if (DEFER)
+	{
+		// warp-aggregated append (all 32 lanes take part)
+		const uint32_t mask = __ballot_sync( 0xffffffffu, defer );
+		if (mask != 0)
+		{
+			const int lane = (threadIdx.x + threadIdx.y * blockDim.x) & 31, leader = __ffs( mask ) - 1;
+			uint32_t base = 0;
+			if (lane == leader) base = atomicAdd( queueCount, (uint32_t)__popc( mask ) );
+			base = __shfl_sync( 0xffffffffu, base, leader );
+			if (defer) queue[base + __popc( mask & ((1u << lane) - 1) )] = (uint32_t)pixelIdx;
+		}
+	}
+}
+
+/* Second pass: the diamond search for the queued pixels, persistent-thread style. The number of search iterations varies from
+   7 to 25 per pixel, so a lane that finishes early takes the next queued pixel (one warp-aggregated atomicAdd once 8 lanes are
+   idle) instead of idling until the slowest lane of its warp is done. The result (the reprojected position) is parked in the
+   motion buffer; prepareFinishKernel completes those pixels with full warps. counters: [0] = queue length, [1] = fetch cursor. */
+__global__ void __launch_bounds__( 256 ) prepareSearchKernel( const PrepareArgs a, const uint32_t* __restrict__ queue, uint32_t* __restrict__ counters )
+{
+	const uint32_t n = counters[0];
+	const int lane = threadIdx.x & 31;
+	bool active = false, exhausted = false;
+	int pixelIdx = 0, iter = 0;
+	float4 lwp = make_float4( 0, 0, 0, 0 );
+	float3 lwpN = make_float3( 0, 0, 0 );
+	float2 prev = make_float2( 0, 0 );
+	float bestDist = 0, stepSize = 0;
+	const float ox = a.j0 - a.prevj0, oy = a.j1 - a.prevj1;
+	while (true)
+	{
+		const uint32_t idle = __ballot_sync( 0xffffffffu, !active );
+		if (!exhausted && __popc( idle ) >= 8)
+		{
+			const int leader = __ffs( idle ) - 1;
+			uint32_t base = 0;
+			if (lane == leader) base = atomicAdd( counters + 1, (uint32_t)__popc( idle ) );
+			base = __shfl_sync( 0xffffffffu, base, leader );
+			if (base >= n) exhausted = true;
+			const uint32_t mine = base + __popc( idle & ((1u << lane) - 1) );
+			if (!active && mine < n)
+			{
+				pixelIdx = (int)queue[mine];
+				const int y = pixelIdx / a.w, x = pixelIdx - y * a.w;
+				lwp = a.worldPos[pixelIdx];
+				lwpN = UnpackNormal2( __float_as_uint( lwp.w ) );
+				const float4 pw = a.prevWorldPos[pixelIdx];
+				prev = make_float2( (float)x, (float)y );
+				bestDist = sqrtf( sqrLen( make_float3( lwp.x - pw.x, lwp.y - pw.y, lwp.z - pw.z ) ) ), stepSize = 5.0f, iter = 0;
+				active = true;
+			}
+		}
+		if (__ballot_sync( 0xffffffffu, active ) == 0)
+		{
+			if (exhausted) break;
+			continue;
+		}
+		if (active)
+		{
+			// one step of the search loop of DiamondSearch above
+			int tap = 0;
+			const float cx = prev.x, cy = prev.y;
+			float d;
+			d = FineWorldDistance( cx - stepSize + ox, cy + oy, lwp, lwpN, a.prevWorldPos, a.w, a.h );
+			if (d < bestDist) bestDist = d, prev = make_float2( cx - stepSize, cy ), tap = 1;
+			d = FineWorldDistance( cx + stepSize + ox, cy + oy, lwp, lwpN, a.prevWorldPos, a.w, a.h );
+			if (d < bestDist) bestDist = d, prev = make_float2( cx + stepSize, cy ), tap = 2;
+			d = FineWorldDistance( cx + ox, cy - stepSize + oy, lwp, lwpN, a.prevWorldPos, a.w, a.h );
+			if (d < bestDist) bestDist = d, prev = make_float2( cx, cy - stepSize ), tap = 3;
+			d = FineWorldDistance( cx + ox, cy + stepSize + oy, lwp, lwpN, a.prevWorldPos, a.w, a.h );
+			if (d < bestDist) bestDist = d, prev = make_float2( cx, cy + stepSize ), tap = 4;
+			bool done = false;
+			if (tap == 0) { stepSize *= 0.45f; if (stepSize < 0.05f) done = true; }
+			if (++iter == 25) done = true;
+			if (done) a.motion[pixelIdx] = prev, active = false;
+		}
+	}
+}
+
+/* Third pass: history lookup, moments, history counter and the final motion vector of the queued pixels. */
+__global__ void __launch_bounds__( 256 ) prepareFinishKernel( const PrepareArgs a, const uint32_t* __restrict__ queue, const uint32_t* __restrict__ counters )
+{
+	const uint32_t n = counters[0];
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+	{
+		const int pixelIdx = (int)queue[i];
+		const uint4 feat = a.features[pixelIdx];
+		const float4 lwp = a.worldPos[pixelIdx];
+		const PrepareLocal l = PrepareLight( a, pixelIdx, feat, false );
+		PrepareFinish( a, pixelIdx, feat, lwp, a.motion[pixelIdx], l );
+	}
 }
 
 /* ---- a-trous (finalize_shared.h:320-484) ------------------------------------------------------------------------ */
@@ -484,7 +603,18 @@ static void FilterChainImpl( const FilterBuffers& b, const FilterSettings& s, cu
 	pa.j0 = s.j0, pa.j1 = s.j1, pa.prevj0 = s.prevj0, pa.prevj1 = s.prevj1;
 	pa.w = w, pa.h = h, pa.pixelValueScale = 1.0f / (float)s.samplesTaken, pa.directClamp = s.directClamp, pa.indirectClamp = s.indirectClamp;
 	pa.camIsStationary = s.camIsStationary;
-	prepareKernel<<<grid, block, 0, st>>>( pa );
+	if (b.taaOut && !s.camIsStationary)
+	{
+		// queue of deferred (specular) pixels in the not yet used TAA output buffer: uint32[w*h], then the counter
+		uint32_t* queue = (uint32_t*)b.taaOut, * count = queue + (size_t)w * h;	// count[0]: queue length, count[1]: fetch cursor
+		cudaMemsetAsync( count, 0, 2 * sizeof( uint32_t ), st );
+		prepareKernel<true><<<grid, block, 0, st>>>( pa, queue, count );
+		int dev = 0, sms = 148;
+		cudaGetDevice( &dev ), cudaDeviceGetAttribute( &sms, cudaDevAttrMultiProcessorCount, dev );
+		prepareSearchKernel<<<sms * 5, 256, 0, st>>>( pa, queue, count );
+		prepareFinishKernel<<<sms * 8, 256, 0, st>>>( pa, queue, count );
+	}
+	else prepareKernel<false><<<grid, block, 0, st>>>( pa, nullptr, nullptr );
 	snap( hPrepare, b.shading );
 	AtrousArgs aa;
 	aa.features = b.features, aa.prevWorldPos = b.prevWorldPos, aa.worldPos = b.worldPos, aa.deltaDepth = b.deltaDepth, aa.motion = b.motion, aa.moments = b.moments;
