@@ -1,6 +1,6 @@
 """Worker for tests/test_multigpu_gpu.py and for manual runs under torchrun (world_size >= 2, one GPU per rank):
-sample-sharded frames gathered on rank 0 by (a) the core's peer-memory collective and (b) the NCCL reduce must both equal
-one GPU rendering all samples (float sums in a different order: relative 1e-5)."""
+sample-sharded frames gathered on rank 0 by (a) the core's peer-memory collective in both layouts (root gather, reduce-scatter) and
+(b) the NCCL reduce must all equal one GPU rendering all samples (float sums in a different order: relative 1e-5)."""
 import os
 import sys
 import numpy as np
@@ -39,9 +39,10 @@ def main():
             want.append(single.ReadPixels().copy())
         single.Shutdown()
     ok = True
-    for kind in ("peer", "nccl"):
+    for kind in ("peer", "peer-reduce-scatter", "nccl"):
         core = make_core(local, sd, SPP)
-        r = PeerGatherRenderer(core, SPP, rank, world) if kind == "peer" else PipelinedShardedRenderer(core, SPP, rank, world, f"cuda:{local}")
+        core.Setting("gatherMode", 1 if kind == "peer-reduce-scatter" else 0)
+        r = PeerGatherRenderer(core, SPP, rank, world) if kind.startswith("peer") else PipelinedShardedRenderer(core, SPP, rank, world, f"cuda:{local}")
         outs = [torch.zeros((H, W, 4), dtype=torch.float32).pin_memory() for _ in views]
         for k, (v, c) in enumerate(zip(views, conv)):
             r.frame(v, c, outs[k])
@@ -52,7 +53,7 @@ def main():
                 err = np.abs(got - want[k]).max() / max(1e-6, np.abs(want[k]).max())
                 print(f"{kind} frame {k}: max rel err {err:.2e}", flush=True)
                 ok &= bool(err < 1e-5)
-        if kind == "peer":
+        if kind.startswith("peer"):
             r.close()
         core.Shutdown()
         dist.barrier()
