@@ -25,3 +25,19 @@ namespace lighthouse2
 Shader::Shader( const char*, const char* ) { Unreachable( "Shader" ); }
 void Shader::Bind() { Unreachable( "Shader" ); }
 }
+
+/* The reference's skinning code (lib/RenderSystem/host_mesh.cpp:777-877) uses aligned AVX loads (_mm256_load_ps) on
+   std::vector<mat4> storage, which the MSVC runtime happens to satisfy and glibc's 16-byte malloc alignment does not: every
+   allocation of the headless host is 64-byte aligned. */
+#include <new>
+void* operator new( std::size_t n )
+{
+	void* p = nullptr;
+	if (posix_memalign( &p, 64, n ? n : 1 ) != 0) throw std::bad_alloc();
+	return p;
+}
+void* operator new[]( std::size_t n ) { return operator new( n ); }
+void operator delete( void* p ) noexcept { free( p ); }
+void operator delete[]( void* p ) noexcept { free( p ); }
+void operator delete( void* p, std::size_t ) noexcept { free( p ); }
+void operator delete[]( void* p, std::size_t ) noexcept { free( p ); }

@@ -11,7 +11,11 @@
    our core presents into "the GL texture" by resolving exactly these at run time (csrc/core_api.cpp: Present), so the frame
    arrives here and is written to <out> as raw float32 RGBA, rows top to bottom as the core produced them.
 
-   usage: tinyapp_ref_host <core name or path> <shareddata dir/> <camera.xml> <out.bin> [frames=1] [width=640] [height=360] [spp=1]
+   usage: tinyapp_ref_host <core name or path> <shareddata dir/> <camera.xml> <out.bin> [frames=1] [width=640] [height=360] [spp=1] [anim.glb]
+
+   anim.glb (optional, e.g. CesiumMan.glb): additionally loads that skinned / animated glTF scene the way apps/imguiapp/main.cpp:90
+   does and advances every animation by 0.05 s per frame (apps/imguiapp/main.cpp:257, viewerapp/main.cpp:189): RenderSystem then
+   re-skins the mesh on the host and re-sends it with SetGeometry (same triangle count) every frame - the core's refit path.
 */
 #include "platform.h"
 #include "rendersystem.h"
@@ -47,6 +51,7 @@ int main( int argc, char** argv )
 	const std::string data = argv[2];
 	const int frames = argc > 5 ? atoi( argv[5] ) : 1, w = argc > 6 ? atoi( argv[6] ) : 640, h = argc > 7 ? atoi( argv[7] ) : 360;
 	const int spp = argc > 8 ? atoi( argv[8] ) : 1;
+	const char* animFile = argc > 9 ? argv[9] : nullptr;
 	RenderAPI* renderer = RenderAPI::CreateRenderAPI( coreName );
 	renderer->DeserializeCamera( argv[3] );
 	// PrepareScene of the tinyapp
@@ -56,6 +61,7 @@ int main( int argc, char** argv )
 	const int lightQuad = renderer->AddQuad( make_float3( 0, -1, 0 ), make_float3( 0, 26.0f, 0 ), 6.9f, 6.9f, lightMat );
 	renderer->AddInstance( lightQuad );
 	const int car = renderer->AddInstance( renderer->AddMesh( "legocar.obj", data.c_str(), 10.0f ) );
+	if (animFile) renderer->AddScene( animFile, data.c_str(), mat4::Translate( -14, 6, 24 ) * mat4::Scale( 3.0f ) );	// in front of the camera
 	GLTexture* target = new GLTexture( w, h, GLTexture::FLOAT );
 	renderer->SetTarget( target, spp );
 	float r = 0;
@@ -67,6 +73,7 @@ int main( int argc, char** argv )
 		mat4 M = mat4::RotateY( r * 2.0f ) * mat4::RotateZ( 0.2f * sinf( r * 8.0f ) ) * mat4::Translate( make_float3( 0, 5, 0 ) );
 		renderer->SetNodeTransform( car, M );
 		if ((r += 0.025f * 0.3f) > 2 * PI) r -= 2 * PI;
+		if (animFile) for (int i = 0; i < renderer->AnimationCount(); i++) renderer->UpdateAnimation( i, 0.05f );
 	}
 	const CoreStats stats = renderer->GetCoreStats();
 	int lastW = 0, lastH = 0, presented = 0;
@@ -75,8 +82,8 @@ int main( int argc, char** argv )
 	if (out && lastFrame) fwrite( lastFrame, sizeof( float ), (size_t)lastW * lastH * 4, out );
 	if (out) fclose( out );
 	printf( "{\"frames\": %d, \"presented\": %d, \"width\": %d, \"height\": %d, \"primaryRays\": %u, \"totalRays\": %u, \"shadowRays\": %u, "
-		"\"probedInst\": %d, \"probedTri\": %d, \"renderTime\": %f}\n", frames, presented, lastW, lastH, stats.primaryRayCount, stats.totalRays,
-		stats.totalShadowRays, stats.probedInstid, stats.probedTriid, stats.renderTime );
+		"\"probedInst\": %d, \"probedTri\": %d, \"renderTime\": %f, \"animations\": %d}\n", frames, presented, lastW, lastH, stats.primaryRayCount, stats.totalRays,
+		stats.totalShadowRays, stats.probedInstid, stats.probedTriid, stats.renderTime, renderer->AnimationCount() );
 	renderer->Shutdown();
 	return 0;
 }

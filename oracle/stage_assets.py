@@ -29,7 +29,7 @@ def main():
     shared = os.path.join(ref, "apps", "_shareddata")
     os.makedirs(dst, exist_ok=True)
     shutil.copytree(os.path.join(shared, "pica"), os.path.join(dst, "pica"), dirs_exist_ok=True)
-    for name in ("legocar.obj", "legocar.mtl"):
+    for name in ("legocar.obj", "legocar.mtl", "CesiumMan.glb"):      # CesiumMan: the skinned, animated scene imguiapp / viewerapp use
         shutil.copy(os.path.join(shared, name), os.path.join(dst, name))
     shutil.copy(os.path.join(ref, "apps", "tinyapp", "camera.xml"), os.path.join(dst, "camera.xml"))
     # legocar.mtl names "textures/legoshld.tga" (resolved against the working directory, case-insensitively on the reference's

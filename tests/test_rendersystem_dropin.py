@@ -47,13 +47,13 @@ needs_ref = pytest.mark.skipif(not (os.path.exists(HOST) and os.path.exists(os.p
                                reason="oracle/_ref/tinyapp_ref_host not built (needs /root/reference at build time)")
 
 
-def run_host(core, out, frames=1, w=640, h=360, spp=1, record=None, env_extra=None):
+def run_host(core, out, frames=1, w=640, h=360, spp=1, record=None, env_extra=None, anim=None):
     env = dict(os.environ)
     if record:
         env["LH2_RECORD_PATH"] = record
     env.update(env_extra or {})
     # working directory = the staged asset directory: legocar.mtl names its texture relative to it
-    r = subprocess.run([HOST, core, "./", "camera.xml", out, str(frames), str(w), str(h), str(spp)], cwd=ASSETS, env=env,
+    r = subprocess.run([HOST, core, "./", "camera.xml", out, str(frames), str(w), str(h), str(spp)] + ([anim] if anim else []), cwd=ASSETS, env=env,
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     return json.loads(r.stdout.strip().splitlines()[-1])
@@ -129,3 +129,32 @@ def test_animated_frames_and_filter_persona(tmp_path):
     filt = np.fromfile(out2, np.float32).reshape(H, W, 4)
     assert st2["presented"] == 3 and np.isfinite(filt).all() and filt[..., :3].mean() > 0.01
     assert np.abs(filt[..., :3] - got[..., :3]).mean() > 1e-4
+
+
+@needs_ref
+@pytest.mark.gpu
+def test_skinned_animation_through_reference_rendersystem(tmp_path):
+    """imguiapp / viewerapp recipe: CesiumMan.glb (skinned, one animation) added to the tinyapp scene, every animation advanced
+    per frame. RenderSystem re-skins the mesh on the host and re-sends it through SetGeometry with an unchanged triangle count:
+    our core refits its BVH in place each frame (no rebuild). The fourth frame must match the oracle rendering the geometry of
+    that frame (recorded from the same RenderSystem) after the same four Restart frames."""
+    if not os.path.exists(os.path.join(ASSETS, "CesiumMan.glb")):
+        pytest.skip("CesiumMan.glb not staged")
+    W, H = 320, 180
+    out, rec = str(tmp_path / "frame.bin"), str(tmp_path / "scene.rec")
+    st = run_host(CORE, out, frames=4, w=W, h=H, anim="CesiumMan.glb")
+    assert st["presented"] == 4 and st["animations"] == 1
+    got = np.fromfile(out, np.float32).reshape(H, W, 4)
+    run_host(RECORDER, str(tmp_path / "none.bin"), frames=4, w=W, h=H, record=rec, anim="CesiumMan.glb")
+    sd, info = orc.load_recording(rec)
+    assert len(sd.meshes) == 173 and sd.meshes[-1][1].shape[0] == 4672
+    with orc.accel(1):
+        o = orc.FrameOracle(sd, W, H, 1, 1e-3, 10.0, 3, 1)
+        for _ in range(4):
+            want = o.render(info["view"], 1)
+    frames_agree(got, want)
+    # the pose really changed between frame 1 and frame 4 (otherwise this would not exercise the refit)
+    rec1 = str(tmp_path / "scene1.rec")
+    run_host(RECORDER, str(tmp_path / "none.bin"), frames=1, w=W, h=H, record=rec1, anim="CesiumMan.glb")
+    sd1, _ = orc.load_recording(rec1)
+    assert np.abs(sd1.meshes[-1][0] - sd.meshes[-1][0]).max() > 1e-3
