@@ -34,7 +34,18 @@ LH2B_API const char* lh2b_last_error( void );
 /* CoreAPI_Base::SetTarget (core_api_base.h:93, rendercore.cpp:284-326): only width/height of the
    GLTexture are used; the image is presented in a linear RGBA32F device buffer (lh2b_read_pixels). */
 LH2B_API int lh2b_set_target( lh2b_core* core, int width, int height, int spp );
-/* CoreAPI_Base::Setting (core_api_base.h:95, rendercore.cpp:746-760). Unknown names are ignored. */
+/* CoreAPI_Base::Setting (core_api_base.h:95, rendercore.cpp:746-760). Unknown names are ignored. Names:
+     reference (Optix7 core)        epsilon, clampValue, noiseShift (accepted, unused as there)
+     reference (Optix7Filter core)  filter, TAA, clampDirect, clampIndirect (lib/RenderCore_Optix7Filter/rendercore.cpp:656-678)
+     path tracer (compile-time in the reference)
+                                    maxPathLength (1..LH2B_MAXPATHLENGTH, default 3 = MAXPATHLENGTH), maxDiffuseBounces (1 = ENOUGH_BOUNCES
+                                    S_BOUNCED default, 2, 0 = unlimited), bsdf (0 lambert.h model, 1 principled model of disney.h)
+     acceleration structure         bvhBuilder (0 GPU PLOC default, 1 host binned SAH, 2 GPU LBVH), bvhRefit (1 in-place refit default, 2 refit +
+                                    re-collapse, 0 rebuild), plocRadius (1..64, default 8), bvhMaxLeaf (1..3 triangles, default 1),
+                                    l2Persist (1 default: persisting-L2 window over the node arena)
+     frame scheduling               pipeline (1: Render( async ) enqueues frame k+1 behind frame k; statistics lag one frame),
+                                    gatherMode (read by lh2b_gather_create: 0 root gather default, 1 reduce-scatter)
+     kernel tuning (measurement)    traversalVariant, wideBlocksPerSM, triThreshold, triThresholdShadow, refillThreshold, shadeBlocks (4 / 5 / 6) */
 LH2B_API int lh2b_setting( lh2b_core* core, const char* name, float value );
 /* CoreAPI_Base::SetProbePos (core_api_base.h:91, rendercore.cpp:85-88). */
 LH2B_API int lh2b_set_probe_pos( lh2b_core* core, int x, int y );

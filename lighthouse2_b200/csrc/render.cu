@@ -326,7 +326,7 @@ int lh2b_setting( lh2b_core* core, const char* name, float value )
 	else if (!strcmp( name, "pipeline" )) { FinishFrame( core ); core->pipeline = value > 0; }
 	else if (!strcmp( name, "bsdf" )) { const int m = value >= 0.5f ? 1 : 0; if (m != core->bsdfModel) core->bsdfModel = m, core->samplesTaken = 0; }
 	else if (!strcmp( name, "maxDiffuseBounces" )) core->enoughBounces = value <= 0 ? 0 : (value < 2 ? S_BOUNCED : S_BOUNCEDTWICE);
-	else if (!strcmp( name, "bvhBuilder" )) core->bvhBuilder = (int)value;	// 0: GPU LBVH (default), 1: host binned SAH
+	else if (!strcmp( name, "bvhBuilder" )) core->bvhBuilder = (int)value;	// 0: GPU PLOC (default), 1: host binned SAH, 2: GPU LBVH
 	else if (!strcmp( name, "bvhRefit" )) core->bvhRefit = (int)value;
 	else if (!strcmp( name, "plocRadius" )) core->plocRadius = value < 1 ? 1 : (value > 64 ? 64 : (int)value);
 	else if (!strcmp( name, "bvhMaxLeaf" )) core->bvhMaxLeaf = value < 1 ? 1 : (value > 3 ? 3 : (int)value);
