@@ -140,3 +140,37 @@ def test_shade_point_spot_directional_lights():
     hits = core.TraceRays(O4, D4)
     _check_level(core, oracle, view, 1, O4, D4, T4, hits, 0x1234567, 0x0BADF00D)
     core.Shutdown()
+
+
+def test_shade_recorded_tinyapp_scene(tmp_path):
+    """The literal tinyapp scene as the reference RenderSystem hands it to a core (recorded through
+    oracle/_ref/tinyapp_ref_host + libRenderCore_Recorder.so): 37 glTF / OBJ materials, 7 MIP-mapped textures (base colour,
+    metallic-roughness), 172 transformed instances. Our shade kernel, the reference's own shadeKernel and the CPU oracle on
+    identical path states at path lengths 1-3 - this pins texture fetches (FetchTexelTrilinear, sampling_shared.h:35-104), uv
+    transforms and instance normal transforms on real assets rather than on procedural scenes."""
+    import test_rendersystem_dropin as rs
+    import os
+    if not (os.path.exists(rs.HOST) and os.path.exists(rs.RECORDER) and os.path.exists(os.path.join(rs.ASSETS, ".staged"))):
+        pytest.skip("oracle/_ref/tinyapp_ref_host not built")
+    rec = str(tmp_path / "scene.rec")
+    rs.run_host(rs.RECORDER, str(tmp_path / "none.bin"), frames=1, w=W, h=H, record=rec)
+    sd, info = orc.load_recording(rec)
+    view = scenes.view_pyramid((-19.17, 9.19, 33.1), (-13.5, 7.99, 24.95), 40, W, H)
+    core = RenderCore()
+    core.SetTarget(W, H, 1)
+    core.Setting("epsilon", 1e-3)
+    sd.upload(core)
+    core.Render(view, 1)
+    with orc.accel(1):
+        oracle = orc.FrameOracle(sd, W, H, 1, 1e-3, 10.0, 3, 1)
+        O4, D4, T4 = _primary_state(view)
+        for L in (1, 2, 3):
+            hits = core.TraceRays(O4, D4)
+            R0 = (0x51ED270B * L + L * 91771) & 0xFFFFFFFF
+            ext, sh = _check_level(core, oracle, view, L, O4, D4, T4, hits, R0, 0x3C6EF372)
+            if L == 1:
+                assert (hits[:, 2] != 0xFFFFFFFF).mean() > 0.5 and len(sh["O"]) > W * H // 8
+            O4, D4, T4 = ext["O"], ext["D"], ext["T"]
+            if len(O4) == 0:
+                break
+    core.Shutdown()
