@@ -115,6 +115,23 @@ LH2B_API int lh2b_finalize_external( lh2b_core* core, const void* dAccumulator, 
 LH2B_API int lh2b_snapshot_accumulator( lh2b_core* core, void* dDst );
 LH2B_API int lh2b_finalize_external_on( lh2b_core* core, const void* dAccumulator, int samples, void* dPixelsOut, void* stream );
 
+/* ---- tile (row-band) sharding of one frame: strong scaling for real-time frames (csrc/tile_gather.cu) -----------
+   lh2b_set_row_band: this core renders rows [y0, y1) only (y0 = y1 = 0: the whole frame), with the path indices, seeds and buffers
+   of the whole frame. The tile gatherer (one per rank, created after lh2b_set_target and the filter setting) assigns the bands,
+   defers the frame's tail and, per frame - lh2b_render( ..., async = 1 ) then lh2b_tile_frame( g ) on every rank - moves the
+   peers' rows into rank 0's buffers over NVLink and runs the filter chain / finalize there. Handles are exchanged like the
+   gather's: lh2b_tile_handle_bytes() per rank, all-gathered in rank order. */
+typedef struct lh2b_tile_gather lh2b_tile_gather;
+LH2B_API int lh2b_set_row_band( lh2b_core* core, int y0, int y1 );
+LH2B_API int lh2b_tile_handle_bytes( void );
+LH2B_API int lh2b_tile_create( lh2b_core* core, int rank, int world, lh2b_tile_gather** out );
+LH2B_API int lh2b_tile_export( lh2b_tile_gather* g, void* handlesOut );
+LH2B_API int lh2b_tile_import( lh2b_tile_gather* g, const void* handlesOfAllRanks );
+LH2B_API int lh2b_tile_frame( lh2b_tile_gather* g );
+LH2B_API int lh2b_tile_wait( lh2b_tile_gather* g );
+LH2B_API int lh2b_tile_rows( lh2b_tile_gather* g, int* y0, int* y1 );
+LH2B_API int lh2b_tile_destroy( lh2b_tile_gather* g );
+
 /* ---- multi-GPU frame gather over NVLink peer memory (csrc/gather.cu) ----------------------------------------
    One process per GPU renders its sample shard (lh2b_set_sample_shard); rank 0 ends every frame with the summed, finalized
    image. Peer copies by the copy engines + stream memory operations for the hand-shake + one fused sum/finalize kernel; no

@@ -216,6 +216,37 @@ class RenderCore:
     def GatherDestroy(self, g):
         self._check(self._lib.lh2b_gather_destroy(g))
 
+    # ---- tile (row-band) sharding of one frame (csrc/tile_gather.cu) ----
+    def SetRowBand(self, y0, y1):
+        self._check(self._lib.lh2b_set_row_band(self._h, int(y0), int(y1)))
+
+    def TileCreate(self, rank, world):
+        g = ctypes.c_void_p()
+        self._check(self._lib.lh2b_tile_create(self._h, rank, world, ctypes.byref(g)))
+        return g
+
+    def TileExport(self, g):
+        buf = ctypes.create_string_buffer(self._lib.lh2b_tile_handle_bytes())
+        self._check(self._lib.lh2b_tile_export(g, buf))
+        return buf.raw
+
+    def TileImport(self, g, handles_of_all_ranks):
+        self._check(self._lib.lh2b_tile_import(g, ctypes.c_char_p(handles_of_all_ranks)))
+
+    def TileFrame(self, g):
+        self._check(self._lib.lh2b_tile_frame(g))
+
+    def TileWait(self, g):
+        self._check(self._lib.lh2b_tile_wait(g))
+
+    def TileRows(self, g):
+        y0, y1 = ctypes.c_int(), ctypes.c_int()
+        self._check(self._lib.lh2b_tile_rows(g, ctypes.byref(y0), ctypes.byref(y1)))
+        return y0.value, y1.value
+
+    def TileDestroy(self, g):
+        self._check(self._lib.lh2b_tile_destroy(g))
+
     def SetSampleShard(self, first_sample, total_spp):
         self._check(self._lib.lh2b_set_sample_shard(self._h, first_sample, total_spp))
 

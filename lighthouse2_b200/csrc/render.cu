@@ -118,7 +118,7 @@ static void FinishFrame( lh2b_core* core )
 	const int maxLen = core->maxPathLength;
 	lh2abi::CoreStats& st = core->stats;
 	lh2b_frame_stats& fs = core->frameStats;
-	const uint32_t stride = (uint32_t)core->width * core->height * core->spp;
+	const uint32_t stride = (uint32_t)core->width * (uint32_t)((core->bandY1 > core->bandY0 ? std::min( core->bandY1, core->height ) : core->height) - (core->bandY1 > core->bandY0 ? core->bandY0 : 0)) * core->spp;
 	st.primaryRayCount = stride;
 	st.bounce1RayCount = maxLen >= 2 ? c.extensionRays[1] : 0;
 	st.deepRayCount = 0;
@@ -161,9 +161,12 @@ static void FinishFrame( lh2b_core* core )
 	st.traceTime0 *= 0.001f, st.traceTime1 *= 0.001f, st.traceTimeX *= 0.001f, st.shadeTime *= 0.001f, st.shadowTraceTime *= 0.001f;
 }
 
+static int BandY0( const lh2b_core* core ) { return core->bandY1 > core->bandY0 ? core->bandY0 : 0; }
+static int BandY1( const lh2b_core* core ) { return core->bandY1 > core->bandY0 ? std::min( core->bandY1, core->height ) : core->height; }
+
 static RenderParams BuildParams( lh2b_core* core, const lh2abi::ViewPyramid& view )
 {
-	const uint32_t stride = (uint32_t)core->width * core->height * core->spp;
+	const uint32_t stride = (uint32_t)core->width * (uint32_t)(BandY1( core ) - BandY0( core )) * core->spp;
 	RenderParams p = {};
 	p.posLensSize = make_float4( view.pos.x, view.pos.y, view.pos.z, view.aperture );
 	p.right = make_float3( view.p2.x - view.p1.x, view.p2.y - view.p1.y, view.p2.z - view.p1.z );
@@ -173,7 +176,7 @@ static RenderParams BuildParams( lh2b_core* core, const lh2abi::ViewPyramid& vie
 	p.w = core->width, p.h = core->height, p.spp = core->spp;
 	p.pass = core->samplesTaken, p.shift = core->shiftSeed;
 	p.sampleBase = core->sampleShardTotal > 0 ? core->sampleShardFirst : 0;
-	p.stride = stride;
+	p.stride = stride, p.bandY0 = BandY0( core ), p.bandY1 = BandY1( core );
 	p.geometryEpsilon = core->geometryEpsilon, p.clampValue = core->clampValue;
 	p.probePixelIdx = core->probeX + core->width * core->probeY;
 	p.maxPathLength = core->maxPathLength, p.enoughBounces = core->enoughBounces, p.bsdfModel = core->bsdfModel;
@@ -211,11 +214,17 @@ static void SwapFrameSlots( lh2b_core* core )
 static void RenderFrame( lh2b_core* core, const lh2abi::ViewPyramid& view )
 {
 	cudaStream_t s = core->stream;
-	const uint32_t stride = (uint32_t)core->width * core->height * core->spp;
+	const uint32_t stride = (uint32_t)core->width * (uint32_t)(BandY1( core ) - BandY0( core )) * core->spp;
 	core->lastView = view;
 	CUDA_CHECK( cudaEventRecord( core->events[0], s ) );
 	RotatePixelBuffers( core );
-	if (core->samplesTaken == 0) CUDA_CHECK( cudaMemsetAsync( core->accumulator.ptr, 0, 2 * (size_t)core->width * core->height * sizeof( float4 ), s ) );
+	if (core->samplesTaken == 0)
+	{
+		// Restart: clear this core's rows of both accumulator halves (tile-sharded frames: the other rows belong to the peers' pushes)
+		const size_t px = (size_t)core->width * core->height, first = (size_t)BandY0( core ) * core->width, n = (size_t)stride / core->spp;
+		CUDA_CHECK( cudaMemsetAsync( core->accumulator.ptr + first, 0, n * sizeof( float4 ), s ) );
+		CUDA_CHECK( cudaMemsetAsync( core->accumulator.ptr + px + first, 0, n * sizeof( float4 ), s ) );
+	}
 	if (core->filterEnabled) EnsureFilterBuffers( core );
 	CUDA_CHECK( cudaMemsetAsync( core->counters.ptr, 0, sizeof( DevCounters ), s ) );
 	RandomUInt( core->shiftSeed );
@@ -246,12 +255,23 @@ static void RenderFrame( lh2b_core* core, const lh2abi::ViewPyramid& view )
 	const int localSamples = (int)((long long)core->samplesTaken * core->spp / total);
 	const int finEv = (int)core->events.size() - 2;
 	CUDA_CHECK( cudaEventRecord( core->events[finEv], s ) );
-	if (core->gather)	// sharded frame: rank 0 finalizes the sum of all shards (gather.cu); this rank's last kernel is the snapshot for it
+	if (core->deferTail) { /* tile-sharded frame: lh2b_tile_frame enqueues the tail once the peers' rows are in place */ }
+	else if (core->gather)	// sharded frame: rank 0 finalizes the sum of all shards (gather.cu); this rank's last kernel is the snapshot for it
 		LaunchFinalize( core->accumulator.ptr, GatherSnapshotTarget( core->gather, s ), core->width * core->height, 1, s );
 	else if (core->filterEnabled && core->features.count) RunFilter( core );
 	else LaunchFinalize( core->accumulator.ptr, core->pixels.ptr, core->width * core->height, localSamples, s );
 	CUDA_CHECK( cudaEventRecord( core->events[finEv + 1], s ) );
 	core->frameInFlight = true;
+}
+
+void EnsureFilterBuffersForSharing( lh2b_core* core ) { EnsureFilterBuffers( core ); }
+
+/* The tail of a frame whose finalize / filter was deferred (core->deferTail): called by the tile gatherer on rank 0, on the
+   core's stream, after every peer's rows have landed in this core's buffers. */
+void RunDeferredTail( lh2b_core* core )
+{
+	if (core->filterEnabled && core->features.count) RunFilter( core );
+	else LaunchFinalize( core->accumulator.ptr, core->pixels.ptr, core->width * core->height, core->samplesTaken, core->stream );
 }
 
 } // namespace lh2b
@@ -682,6 +702,17 @@ int lh2b_filter_chain( lh2b_core* core, lh2b_filter_io* io )
 	down( io->featuresOut, feat.ptr, px * 16 ), down( io->motion, motion.ptr, px * 8 ), down( io->moments, moments.ptr, px * 16 );
 	down( io->taaPixels, taaOut.ptr, px * 16 ), down( io->target, target.ptr, px * 16 );
 	CUDA_CHECK( cudaStreamSynchronize( s ) );
+	API_END
+}
+
+/* Tile-sharded frames (partitioning 2): this core renders rows [y0, y1) of the frame only - same path indices,
+   seeds and buffers as the whole frame, so the rows are bit-identical to what one GPU would produce. y0 = y1 = 0: whole frame. */
+int lh2b_set_row_band( lh2b_core* core, int y0, int y1 )
+{
+	API_BEGIN
+	if (y0 < 0 || y1 < y0 || (core->height > 0 && y1 > core->height)) throw CoreError( "set_row_band: rows out of range" );
+	FinishFrame( core );
+	core->bandY0 = y0, core->bandY1 = y1, core->samplesTaken = 0;
 	API_END
 }
 

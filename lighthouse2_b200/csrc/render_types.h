@@ -53,7 +53,8 @@ struct RenderParams
 	int pass;					// samplesTaken before this frame
 	uint32_t shift;				// blue-noise tile shift (rendercore.cpp:855,860)
 	uint32_t sampleBase;		// first sample index of this core's shard (multi-GPU), 0 otherwise
-	uint32_t stride;			// w * h * spp
+	uint32_t stride;			// paths of this frame on this core: w * (bandY1 - bandY0) * spp
+	int bandY0, bandY1;			// rows rendered by this core (tile-sharded frames, lh2b_set_row_band); the whole frame: 0, h
 	float geometryEpsilon, clampValue;
 	int probePixelIdx;
 	int maxPathLength;			// reference MAXPATHLENGTH (3)

@@ -536,11 +536,18 @@ template <int BSDF, int MINB> __global__ void __launch_bounds__( 128, MINB ) sha
 	const uint32_t rounds = (pathCount + blockDim.x * gridDim.x - 1) / (blockDim.x * gridDim.x);
 	for (uint32_t round = 0; round < rounds; round++)
 	{
-		const uint32_t job = (round * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
+		uint32_t job = (round * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
+		const bool inRange = job < pathCount;
+		if (pathLength == 1 && p.stride != (uint32_t)(p.w * p.h * p.spp) && inRange)
+		{
+			// tile-sharded frame: primary paths live at their global path index; job -> (sample, pixel of the band)
+			const uint32_t bandPixels = (uint32_t)(p.bandY1 - p.bandY0) * p.w, smp = job / bandPixels;
+			job = smp * (p.w * p.h) + (uint32_t)p.bandY0 * p.w + (job - smp * bandPixels);
+		}
 		// every lane takes part in the two warp-wide allocations below; inactive lanes carry 'false'
 		bool emitShadow = false, emitExt = false;
 		float4 cO, cD, cE, eO, eD, eT;
-		if (job < pathCount) do
+		if (inRange) do
 		{
 			const float4 O4 = in.O[job], D4 = in.D[job];
 			float4 T4 = pathLength == 1 ? make_float4( 1, 1, 1, 1 ) : in.T[job];

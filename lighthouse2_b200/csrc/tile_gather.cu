@@ -1,0 +1,261 @@
+/* tile_gather.cu - tile (row-band) sharding of ONE frame over the GPUs of a box: the strong-scaling mode of SURVEY.md 8e
+   (partitioning 2) for BASELINE.json configs[4], "4K 1 spp + SVGF filter, real-time frame-time mode at 1/2/4/8 B200".
+
+   Sample sharding (gather.cu) cannot shorten a 1-spp frame. Here rank r path-traces rows [y_r, y_(r+1)) of the frame
+   (lh2b_set_row_band: same path indices, seeds and buffers as the whole frame, so every row is bit-identical to what a single
+   GPU produces) and the rows are gathered on rank 0, which runs the tail of the frame - the SVGF / TAA chain with its temporal
+   history, or the plain finalize - on the complete buffers. A row band is one contiguous range of every per-pixel buffer, so
+   the exchange is a handful of peer copies per rank, straight into rank 0's own frame buffers:
+
+     rank r > 0, frame k:  [core stream]  render rows y_r .. y_(r+1) into the local buffers (tail deferred)
+                           [comm stream]  wait( ack >= k )                          rank 0 has finished the tail of frame k-1
+                                          copy rows of: accumulator (direct), and in filter mode accumulator (indirect),
+                                          worldPos, deltaDepth -> the same rows of rank 0's buffers; features -> rank 0's staging
+                                          set rank0.arrived[r] = k+1
+     rank 0, frame k:      [core stream]  render its own rows
+                                          wait( arrived[r] >= k+1 ) for every r     cuStreamWaitValue32 on the core's own stream
+                                          mergeFeaturesKernel (filter mode): staged feature rows -> features, keeping the history
+                                          counter bits that rank 0's prepare pass owns
+                                          tail: filter chain / finalize -> pixels;  set rank r .ack = k+1 for every r
+   80 B per pixel cross NVLink in filter mode (16 B without the filter): 4K -> 663 MB x (N-1)/N per frame into rank 0. The result
+   equals the single-GPU frame bit for bit at 1 spp (one path per pixel: no accumulation-order freedom), which is what
+   tests/multigpu_worker.py checks. Buffers are shared through CUDA IPC handles like gather.cu's; create the gatherer after
+   SetTarget and after Setting( "filter" ) (the handles name the buffers those calls allocate).
+*/
+#include "core.h"
+#include "kernels.h"
+#include <cuda.h>
+#include <cstring>
+#include <algorithm>
+
+namespace lh2b
+{
+
+void EnsureFilterBuffersForSharing( lh2b_core* core );	// render.cu
+void RunDeferredTail( lh2b_core* core );				// render.cu
+
+typedef CUresult( *TgWaitValue32Fn )( CUstream, CUdeviceptr, cuuint32_t, unsigned int );
+typedef CUresult( *TgMemsetD32AsyncFn )( CUdeviceptr, unsigned int, size_t, CUstream );
+
+#define TILE_MAX_RANKS 16
+struct TileHandles
+{
+	cudaIpcMemHandle_t accumulator, featStage, worldPos[2], deltaDepth, arrived, ack;	// all but 'ack' are meaningful for rank 0 only
+	int filter, flip0, pad[2];																// rank 0: filter mode and the worldPos buffer index of its next frame
+};
+
+__global__ void __launch_bounds__( 256 ) mergeFeaturesKernel( uint4* __restrict__ features, const uint4* __restrict__ staged, const int first, const int n )
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const uint4 s = staged[first + i];
+	const uint32_t history = features[first + i].w & 15u;
+	features[first + i] = make_uint4( s.x, s.y, s.z, (s.w & ~15u) | history );
+}
+
+} // namespace lh2b
+
+using namespace lh2b;
+
+struct lh2b_tile_gather
+{
+	lh2b_core* core = nullptr;
+	int rank = 0, world = 1, filter = 0, flip0 = 0;
+	size_t pixels = 0;
+	int rowOf[TILE_MAX_RANKS + 1] = {};		// band boundaries (multiples of 4 rows: the generate kernel works on 8x4-pixel tiles)
+	uint32_t frame = 0;
+	cudaStream_t comm = nullptr;
+	cudaEvent_t rendered = nullptr;
+	uint32_t* arrived = nullptr;				// rank 0: [world]
+	uint32_t* ack = nullptr;					// every rank
+	uint4* featStage = nullptr;					// rank 0: staged feature rows of the peers
+	// peer mappings (rank > 0: rank 0's buffers; rank 0: every peer's ack)
+	float4* rootAccumulator = nullptr; uint4* rootFeatStage = nullptr; float4* rootWorldPos[2] = { nullptr, nullptr }; float4* rootDeltaDepth = nullptr;
+	uint32_t* rootArrived = nullptr;
+	uint32_t* peerAck[TILE_MAX_RANKS] = {};
+	TgWaitValue32Fn waitValue = nullptr;
+	TgMemsetD32AsyncFn memsetD32 = nullptr;
+};
+
+#define API_BEGIN try {
+#define API_END } catch (const std::exception& e) { SetLastError( e.what() ); return 1; } return 0;
+#define CU_CHECK( call ) do { CUresult r_ = (call); if (r_ != CUDA_SUCCESS) { char b_[256]; snprintf( b_, sizeof( b_ ), "%s failed at %s:%d: CUresult %d", #call, __FILE__, __LINE__, (int)r_ ); throw lh2b::CoreError( b_ ); } } while (0)
+
+extern "C" {
+
+int lh2b_tile_handle_bytes() { return (int)sizeof( TileHandles ); }
+
+int lh2b_tile_create( lh2b_core* core, int rank, int world, lh2b_tile_gather** out )
+{
+	API_BEGIN
+	if (!core || !out) throw CoreError( "tile_create: null argument" );
+	if (world < 1 || world > TILE_MAX_RANKS || rank < 0 || rank >= world) throw CoreError( "tile_create: rank / world out of range (at most 16 ranks)" );
+	if (core->width == 0) throw CoreError( "tile_create: SetTarget first" );
+	if (core->height < 4 * world) throw CoreError( "tile_create: fewer than 4 rows per rank" );
+	CUDA_CHECK( cudaSetDevice( core->device ) );
+	lh2b_tile_gather* g = new lh2b_tile_gather();
+	g->core = core, g->rank = rank, g->world = world, g->pixels = (size_t)core->width * core->height;
+	g->filter = core->filterEnabled ? 1 : 0;
+	for (int r = 0; r <= world; r++) g->rowOf[r] = r == world ? core->height : (int)((long long)core->height * r / world) & ~3;
+	if (g->filter) EnsureFilterBuffersForSharing( core );
+	g->flip0 = core->filterFlip;
+	CUDA_CHECK( cudaStreamCreateWithFlags( &g->comm, cudaStreamNonBlocking ) );
+	CUDA_CHECK( cudaEventCreateWithFlags( &g->rendered, cudaEventDisableTiming ) );
+	cudaDriverEntryPointQueryResult q;
+	void* fn = nullptr;
+	CUDA_CHECK( cudaGetDriverEntryPoint( "cuStreamWaitValue32", &fn, cudaEnableDefault, &q ) );
+	if (!fn || q != cudaDriverEntryPointSuccess) throw CoreError( "tile_create: cuStreamWaitValue32 is not available" );
+	g->waitValue = (TgWaitValue32Fn)fn;
+	CUDA_CHECK( cudaGetDriverEntryPoint( "cuMemsetD32Async", &fn, cudaEnableDefault, &q ) );
+	if (!fn || q != cudaDriverEntryPointSuccess) throw CoreError( "tile_create: cuMemsetD32Async is not available" );
+	g->memsetD32 = (TgMemsetD32AsyncFn)fn;
+	CUDA_CHECK( cudaMalloc( &g->ack, 256 ) );
+	CUDA_CHECK( cudaMemset( g->ack, 0, 256 ) );
+	if (rank == 0)
+	{
+		CUDA_CHECK( cudaMalloc( &g->arrived, 256 ) );
+		CUDA_CHECK( cudaMemset( g->arrived, 0, 256 ) );
+		if (g->filter) CUDA_CHECK( cudaMalloc( &g->featStage, g->pixels * sizeof( uint4 ) ) );
+	}
+	// this core renders its band only; the tail of the frame runs in lh2b_tile_frame on rank 0
+	const int rc = lh2b_set_row_band( core, g->rowOf[rank], g->rowOf[rank + 1] );
+	if (rc != 0) throw CoreError( lh2b_last_error() );
+	core->deferTail = true;
+	CUDA_CHECK( cudaDeviceSynchronize() );
+	*out = g;
+	API_END
+}
+
+int lh2b_tile_export( lh2b_tile_gather* g, void* handlesOut )
+{
+	API_BEGIN
+	TileHandles h;
+	memset( &h, 0, sizeof( h ) );
+	CUDA_CHECK( cudaIpcGetMemHandle( &h.ack, g->ack ) );
+	if (g->rank == 0)
+	{
+		lh2b_core* c = g->core;
+		CUDA_CHECK( cudaIpcGetMemHandle( &h.accumulator, c->accumulator.ptr ) );
+		CUDA_CHECK( cudaIpcGetMemHandle( &h.arrived, g->arrived ) );
+		if (g->filter)
+		{
+			CUDA_CHECK( cudaIpcGetMemHandle( &h.featStage, g->featStage ) );
+			CUDA_CHECK( cudaIpcGetMemHandle( &h.worldPos[0], c->worldPosBuf[0].ptr ) );
+			CUDA_CHECK( cudaIpcGetMemHandle( &h.worldPos[1], c->worldPosBuf[1].ptr ) );
+			CUDA_CHECK( cudaIpcGetMemHandle( &h.deltaDepth, c->deltaDepth.ptr ) );
+		}
+	}
+	h.filter = g->filter, h.flip0 = g->flip0;
+	memcpy( handlesOut, &h, sizeof( h ) );
+	API_END
+}
+
+int lh2b_tile_import( lh2b_tile_gather* g, const void* handlesOfAllRanks )
+{
+	API_BEGIN
+	const TileHandles* h = (const TileHandles*)handlesOfAllRanks;
+	CUDA_CHECK( cudaSetDevice( g->core->device ) );
+	for (int r = 0; r < g->world; r++) if (h[r].filter != g->filter) throw CoreError( "tile_import: ranks disagree on the filter setting" );
+	if (g->rank == 0)
+	{
+		for (int r = 1; r < g->world; r++) CUDA_CHECK( cudaIpcOpenMemHandle( (void**)&g->peerAck[r], h[r].ack, cudaIpcMemLazyEnablePeerAccess ) );
+	}
+	else
+	{
+		const unsigned f = cudaIpcMemLazyEnablePeerAccess;
+		CUDA_CHECK( cudaIpcOpenMemHandle( (void**)&g->rootAccumulator, h[0].accumulator, f ) );
+		CUDA_CHECK( cudaIpcOpenMemHandle( (void**)&g->rootArrived, h[0].arrived, f ) );
+		if (g->filter)
+		{
+			CUDA_CHECK( cudaIpcOpenMemHandle( (void**)&g->rootFeatStage, h[0].featStage, f ) );
+			CUDA_CHECK( cudaIpcOpenMemHandle( (void**)&g->rootWorldPos[0], h[0].worldPos[0], f ) );
+			CUDA_CHECK( cudaIpcOpenMemHandle( (void**)&g->rootWorldPos[1], h[0].worldPos[1], f ) );
+			CUDA_CHECK( cudaIpcOpenMemHandle( (void**)&g->rootDeltaDepth, h[0].deltaDepth, f ) );
+		}
+		g->flip0 = h[0].flip0;
+	}
+	API_END
+}
+
+/* One frame: call after lh2b_render( ..., async = 1 ) of that frame on every rank. Rank 0 ends with the complete frame in its pixel
+   buffer (lh2b_read_pixels / lh2b_read_pixels_async as usual). */
+int lh2b_tile_frame( lh2b_tile_gather* g )
+{
+	API_BEGIN
+	lh2b_core* core = g->core;
+	CUDA_CHECK( cudaSetDevice( core->device ) );
+	const uint32_t k = g->frame++;
+	const size_t w = (size_t)core->width, first = (size_t)g->rowOf[g->rank] * w, n = (size_t)(g->rowOf[g->rank + 1] - g->rowOf[g->rank]) * w;
+	if (g->rank > 0)
+	{
+		CUstream cs = (CUstream)g->comm;
+		CUDA_CHECK( cudaEventRecord( g->rendered, core->stream ) );
+		CUDA_CHECK( cudaStreamWaitEvent( g->comm, g->rendered, 0 ) );
+		if (k >= 1) CU_CHECK( g->waitValue( cs, (CUdeviceptr)g->ack, k, CU_STREAM_WAIT_VALUE_GEQ ) );	// rank 0 is done with frame k-1's buffers
+		auto push = [&]( void* dst, const void* src, size_t elem ) {
+			CUDA_CHECK( cudaMemcpyAsync( (char*)dst + first * elem, (const char*)src + first * elem, n * elem, cudaMemcpyDeviceToDevice, g->comm ) ); };
+		push( g->rootAccumulator, core->accumulator.ptr, 16 );
+		if (g->filter)
+		{
+			push( g->rootAccumulator + g->pixels, core->accumulator.ptr + g->pixels, 16 );	// indirect half
+			push( g->rootFeatStage, core->features.ptr, 16 );
+			push( g->rootWorldPos[(g->flip0 + k) & 1], core->worldPosBuf[core->filterFlip].ptr, 16 );	// rank 0 flips its world-position buffers every frame
+			push( g->rootDeltaDepth, core->deltaDepth.ptr, 16 );
+		}
+		CU_CHECK( g->memsetD32( (CUdeviceptr)(g->rootArrived + g->rank), k + 1, 1, cs ) );
+		// the next frame of this rank overwrites the rows just pushed: it has to wait for the copies
+		CUDA_CHECK( cudaEventRecord( g->rendered, g->comm ) );
+		CUDA_CHECK( cudaStreamWaitEvent( core->stream, g->rendered, 0 ) );
+	}
+	else
+	{
+		CUstream cs = (CUstream)core->stream;
+		for (int r = 1; r < g->world; r++) CU_CHECK( g->waitValue( cs, (CUdeviceptr)(g->arrived + r), k + 1, CU_STREAM_WAIT_VALUE_GEQ ) );
+		if (g->filter && g->world > 1)
+		{
+			const int peerFirst = (int)((size_t)g->rowOf[1] * w), peerCount = (int)(g->pixels - (size_t)peerFirst);
+			mergeFeaturesKernel<<<(peerCount + 255) / 256, 256, 0, core->stream>>>( core->features.ptr, g->featStage, peerFirst, peerCount );
+			CUDA_CHECK( cudaGetLastError() );
+		}
+		RunDeferredTail( core );
+		for (int r = 1; r < g->world; r++) CU_CHECK( g->memsetD32( (CUdeviceptr)g->peerAck[r], k + 1, 1, cs ) );
+	}
+	API_END
+}
+
+int lh2b_tile_wait( lh2b_tile_gather* g )
+{
+	API_BEGIN
+	CUDA_CHECK( cudaStreamSynchronize( g->comm ) );
+	CUDA_CHECK( cudaStreamSynchronize( g->core->stream ) );
+	API_END
+}
+
+int lh2b_tile_rows( lh2b_tile_gather* g, int* y0, int* y1 )
+{
+	API_BEGIN
+	*y0 = g->rowOf[g->rank], *y1 = g->rowOf[g->rank + 1];
+	API_END
+}
+
+int lh2b_tile_destroy( lh2b_tile_gather* g )
+{
+	API_BEGIN
+	if (!g) return 0;
+	cudaSetDevice( g->core->device );
+	cudaStreamSynchronize( g->comm ), cudaStreamSynchronize( g->core->stream );
+	g->core->deferTail = false;
+	lh2b_set_row_band( g->core, 0, 0 );
+	if (g->rank == 0) { for (int r = 1; r < g->world; r++) if (g->peerAck[r]) cudaIpcCloseMemHandle( g->peerAck[r] ); }
+	else
+	{
+		void* maps[] = { g->rootAccumulator, g->rootFeatStage, g->rootWorldPos[0], g->rootWorldPos[1], g->rootDeltaDepth, g->rootArrived };
+		for (void* m : maps) if (m) cudaIpcCloseMemHandle( m );
+	}
+	cudaFree( g->arrived ), cudaFree( g->ack ), cudaFree( g->featStage );
+	cudaEventDestroy( g->rendered ), cudaStreamDestroy( g->comm );
+	delete g;
+	API_END
+}
+
+} // extern "C"

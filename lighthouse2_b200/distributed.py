@@ -159,3 +159,43 @@ class PeerGatherRenderer:
         self.finish()
         dist.barrier()
         self.core.GatherDestroy(self.g)
+
+
+class TileShardedRenderer:
+    """Strong scaling of ONE frame (real-time mode, BASELINE.json configs[4]): rank r path-traces a band of rows, the bands are
+    gathered on rank 0 over NVLink peer memory and rank 0 runs the frame's tail (SVGF / TAA chain or finalize) on the complete
+    buffers (csrc/tile_gather.cu). Create after SetTarget and Setting("filter"). At 1 spp the frame equals the single-GPU frame
+    bit for bit.
+
+        frame(view, converge, host_out)   enqueue one frame on this rank (rank 0: the image goes to pinned host_out, or None)
+        finish()                          wait for everything this rank has in flight
+    """
+
+    def __init__(self, core, rank=None, world=None):
+        self.core = core
+        self.rank = dist.get_rank() if rank is None else rank
+        self.world = dist.get_world_size() if world is None else world
+        core.Setting("pipeline", 1)
+        self.g = core.TileCreate(self.rank, self.world)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, core.TileExport(self.g))
+        core.TileImport(self.g, b"".join(handles))
+        self.rows = core.TileRows(self.g)
+        dist.barrier()
+
+    def frame(self, view, converge=1, host_out=None):
+        self.core.Render(view, converge, True)
+        self.core.TileFrame(self.g)
+        if self.rank == 0 and host_out is not None:
+            self.core.ReadPixelsAsync(host_out.numpy() if hasattr(host_out, "numpy") else host_out)
+
+    def finish(self):
+        self.core.WaitForRender()
+        self.core.TileWait(self.g)
+        if self.rank == 0:
+            self.core.WaitReadPixels()
+
+    def close(self):
+        self.finish()
+        dist.barrier()
+        self.core.TileDestroy(self.g)

@@ -10,7 +10,7 @@ import torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from lighthouse2_b200 import RenderCore, scenes  # noqa: E402
-from lighthouse2_b200.distributed import PeerGatherRenderer, PipelinedShardedRenderer  # noqa: E402
+from lighthouse2_b200.distributed import PeerGatherRenderer, PipelinedShardedRenderer, TileShardedRenderer  # noqa: E402
 
 W, H, SPP = 160, 90, 2
 
@@ -22,6 +22,47 @@ def make_core(dev, sd, spp):
     core.Setting("maxPathLength", 3)
     sd.upload(core)
     return core
+
+
+def tile_sharding(rank, world, local, sd):
+    """Tile (row-band) sharded frames, plain and with the SVGF / TAA chain, moving camera: rank 0's image must equal the
+    single-GPU frame bit for bit (1 spp)."""
+    TW, TH = 192, 128
+    views = [scenes.view_pyramid((3 * k, 30, -80 + k), (0, 0, 0), 40, TW, TH) for k in range(5)]
+    ok = True
+    for filt in (0, 1):
+        def make(spp=1):
+            c = RenderCore(local)
+            c.SetTarget(TW, TH, spp)
+            c.Setting("epsilon", 1e-3)
+            c.Setting("maxPathLength", 3)
+            c.Setting("filter", filt)
+            c.Setting("TAA", filt)
+            sd.upload(c)
+            return c
+        want = []
+        if rank == 0:
+            single = make()
+            for v in views:
+                single.Render(v, 1)
+                want.append(single.ReadPixels().copy())
+            single.Shutdown()
+        core = make()
+        r = TileShardedRenderer(core, rank, world)
+        outs = [torch.zeros((TH, TW, 4), dtype=torch.float32).pin_memory() for _ in views]
+        for k, v in enumerate(views):
+            r.frame(v, 1, outs[k])
+        r.finish()
+        if rank == 0:
+            for k in range(len(views)):
+                same = np.array_equal(outs[k].numpy(), want[k])
+                err = np.abs(outs[k].numpy() - want[k]).max()
+                print(f"tile {'filter' if filt else 'plain'} frame {k}: rows {r.rows} identical={same} max abs err {err:.2e}", flush=True)
+                ok &= bool(same)
+        r.close()
+        core.Shutdown()
+        dist.barrier()
+    return ok
 
 
 def main():
@@ -57,6 +98,7 @@ def main():
             r.close()
         core.Shutdown()
         dist.barrier()
+    ok &= tile_sharding(rank, world, local, sd)
     flag = torch.tensor([1 if ok else 0], device=f"cuda:{local}")
     dist.broadcast(flag, 0)
     dist.destroy_process_group()
