@@ -44,7 +44,8 @@ LH2B_API int lh2b_set_target( lh2b_core* core, int width, int height, int spp );
                                     re-collapse, 0 rebuild), plocRadius (1..64, default 8), bvhMaxLeaf (1..3 triangles, default 1),
                                     l2Persist (1 default: persisting-L2 window over the node arena)
      frame scheduling               pipeline (1: Render( async ) enqueues frame k+1 behind frame k; statistics lag one frame),
-                                    gatherMode (read by lh2b_gather_create: 0 root gather default, 1 reduce-scatter)
+                                    gatherMode (read by lh2b_gather_create: 0 root gather default, 1 reduce-scatter),
+                                    tileRootShare (read by lh2b_tile_create: rank 0's band relative to an equal share, 0..1)
      kernel tuning (measurement)    traversalVariant, wideBlocksPerSM, triThreshold, triThresholdShadow, refillThreshold, shadeBlocks (4 / 5 / 6) */
 LH2B_API int lh2b_setting( lh2b_core* core, const char* name, float value );
 /* CoreAPI_Base::SetProbePos (core_api_base.h:91, rendercore.cpp:85-88). */

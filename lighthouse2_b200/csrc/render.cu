@@ -341,6 +341,7 @@ int lh2b_setting( lh2b_core* core, const char* name, float value )
 	else if (!strcmp( name, "clampIndirect" )) core->clampIndirect = value;
 	// extensions of this core (the reference fixes these at compile time: core_settings.h:25, pathtracer.h:33)
 	else if (!strcmp( name, "maxPathLength" )) core->maxPathLength = value < 1 ? 1 : (value > LH2B_MAXPATHLENGTH ? LH2B_MAXPATHLENGTH : (int)value);
+	else if (!strcmp( name, "tileRootShare" )) core->tileRootShare = value < 0 ? 0 : (value > 1 ? 1 : value);	// read by lh2b_tile_create
 	else if (!strcmp( name, "gatherMode" )) core->gatherMode = value > 0 ? 1 : 0;	// read by lh2b_gather_create
 	else if (!strcmp( name, "l2Persist" )) core->l2Persist = value > 0 ? 1 : 0;	// takes effect at the next FinalizeInstances
 	else if (!strcmp( name, "pipeline" )) { FinishFrame( core ); core->pipeline = value > 0; }

@@ -96,7 +96,11 @@ int lh2b_tile_create( lh2b_core* core, int rank, int world, lh2b_tile_gather** o
 	lh2b_tile_gather* g = new lh2b_tile_gather();
 	g->core = core, g->rank = rank, g->world = world, g->pixels = (size_t)core->width * core->height;
 	g->filter = core->filterEnabled ? 1 : 0;
-	for (int r = 0; r <= world; r++) g->rowOf[r] = r == world ? core->height : (int)((long long)core->height * r / world) & ~3;
+	// rank 0 also runs the tail of every frame while the peers already render the next one: Setting "tileRootShare" (0..1, default 1)
+	// scales its band relative to an equal share; the other ranks split the remaining rows evenly. Boundaries: multiples of 4 rows.
+	const int rootRows = world == 1 ? core->height : std::max( 4, (int)((double)core->height / world * core->tileRootShare) & ~3 );
+	g->rowOf[0] = 0;
+	for (int r = 1; r <= world; r++) g->rowOf[r] = r == world ? core->height : (rootRows + (int)((long long)(core->height - rootRows) * (r - 1) / (world - 1))) & ~3;
 	if (g->filter) EnsureFilterBuffersForSharing( core );
 	g->flip0 = core->filterFlip;
 	CUDA_CHECK( cudaStreamCreateWithFlags( &g->comm, cudaStreamNonBlocking ) );
