@@ -124,13 +124,14 @@ LH2B_API int lh2b_finalize_external_on( lh2b_core* core, const void* dAccumulato
    gather's: lh2b_tile_handle_bytes() per rank, all-gathered in rank order. */
 typedef struct lh2b_tile_gather lh2b_tile_gather;
 LH2B_API int lh2b_set_row_band( lh2b_core* core, int y0, int y1 );
+LH2B_API int lh2b_set_row_band_strided( lh2b_core* core, int y0, int y1, int stepTileRows );	/* tile rows y0/4 + j * step below row y1 */
 LH2B_API int lh2b_tile_handle_bytes( void );
 LH2B_API int lh2b_tile_create( lh2b_core* core, int rank, int world, lh2b_tile_gather** out );
 LH2B_API int lh2b_tile_export( lh2b_tile_gather* g, void* handlesOut );
 LH2B_API int lh2b_tile_import( lh2b_tile_gather* g, const void* handlesOfAllRanks );
 LH2B_API int lh2b_tile_frame( lh2b_tile_gather* g );
 LH2B_API int lh2b_tile_wait( lh2b_tile_gather* g );
-LH2B_API int lh2b_tile_rows( lh2b_tile_gather* g, int* y0, int* y1 );
+LH2B_API int lh2b_tile_rows( lh2b_tile_gather* g, int* y0, int* y1, int* stepTileRows );
 LH2B_API int lh2b_tile_destroy( lh2b_tile_gather* g );
 
 /* ---- multi-GPU frame gather over NVLink peer memory (csrc/gather.cu) ----------------------------------------

@@ -45,13 +45,14 @@ SIGNATURES = {
     "lh2b_finalize_external": ([_vp, _vp, _ip], _ip),
     "lh2b_snapshot_accumulator": ([_vp, _vp], _ip),
     "lh2b_set_row_band": ([_vp, _ip, _ip], _ip),
+    "lh2b_set_row_band_strided": ([_vp, _ip, _ip, _ip], _ip),
     "lh2b_tile_handle_bytes": ([], _ip),
     "lh2b_tile_create": ([_vp, _ip, _ip, _c.POINTER(_vp)], _ip),
     "lh2b_tile_export": ([_vp, _vp], _ip),
     "lh2b_tile_import": ([_vp, _vp], _ip),
     "lh2b_tile_frame": ([_vp], _ip),
     "lh2b_tile_wait": ([_vp], _ip),
-    "lh2b_tile_rows": ([_vp, _c.POINTER(_ip), _c.POINTER(_ip)], _ip),
+    "lh2b_tile_rows": ([_vp, _c.POINTER(_ip), _c.POINTER(_ip), _c.POINTER(_ip)], _ip),
     "lh2b_tile_destroy": ([_vp], _ip),
     "lh2b_gather_handle_bytes": ([], _ip),
     "lh2b_gather_create": ([_vp, _ip, _ip, _c.POINTER(_vp)], _ip),

@@ -217,8 +217,9 @@ class RenderCore:
         self._check(self._lib.lh2b_gather_destroy(g))
 
     # ---- tile (row-band) sharding of one frame (csrc/tile_gather.cu) ----
-    def SetRowBand(self, y0, y1):
-        self._check(self._lib.lh2b_set_row_band(self._h, int(y0), int(y1)))
+    def SetRowBand(self, y0, y1, step_tile_rows=1):
+        """Rows [y0, y1) only; step_tile_rows > 1: every step-th 4-row tile row of that range (interleaved bands)."""
+        self._check(self._lib.lh2b_set_row_band_strided(self._h, int(y0), int(y1), int(step_tile_rows)))
 
     def TileCreate(self, rank, world):
         g = ctypes.c_void_p()
@@ -240,9 +241,9 @@ class RenderCore:
         self._check(self._lib.lh2b_tile_wait(g))
 
     def TileRows(self, g):
-        y0, y1 = ctypes.c_int(), ctypes.c_int()
-        self._check(self._lib.lh2b_tile_rows(g, ctypes.byref(y0), ctypes.byref(y1)))
-        return y0.value, y1.value
+        y0, y1, st = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        self._check(self._lib.lh2b_tile_rows(g, ctypes.byref(y0), ctypes.byref(y1), ctypes.byref(st)))
+        return y0.value, y1.value, st.value
 
     def TileDestroy(self, g):
         self._check(self._lib.lh2b_tile_destroy(g))

@@ -89,7 +89,7 @@ struct lh2b_core
 	lh2b::DevBuf<uint32_t> linkedRoots;
 	int plocRadius = 8, bvhMaxLeaf = 1;	// swept on the 1M-triangle terrain (tools/quality_sweep.py)
 	struct lh2b_gather* gather = nullptr;		// attached multi-GPU gather (gather.cu): frames end with a snapshot for it instead of the local finalize
-	int bandY0 = 0, bandY1 = 0;				// rows this core renders (lh2b_set_row_band; 0, 0 = the whole frame)
+	int bandY0 = 0, bandY1 = 0, bandStep = 1;	// rows this core renders (lh2b_set_row_band[_strided]; 0, 0 = the whole frame)
 	float tileRootShare = 1.0f;				// lh2b_tile_create: rank 0's band relative to an equal share (it also runs the frame's tail)
 	bool deferTail = false;					// tile-sharded frames: finalize / filter is enqueued by the gatherer once every band has arrived
 	int gatherMode = 0;						// lh2b_gather_create: 0 root gather, 1 reduce-scatter (csrc/gather.cu)

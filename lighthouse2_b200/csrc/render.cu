@@ -108,6 +108,8 @@ static void RunFilter( lh2b_core* core )
 	core->prevView = core->lastView, core->filterHistoryValid = true;
 }
 
+static uint32_t BandRowsOfCore( const lh2b_core* core );
+
 static void FinishFrame( lh2b_core* core )
 {
 	if (!core->frameInFlight) return;
@@ -118,7 +120,7 @@ static void FinishFrame( lh2b_core* core )
 	const int maxLen = core->maxPathLength;
 	lh2abi::CoreStats& st = core->stats;
 	lh2b_frame_stats& fs = core->frameStats;
-	const uint32_t stride = (uint32_t)core->width * (uint32_t)((core->bandY1 > core->bandY0 ? std::min( core->bandY1, core->height ) : core->height) - (core->bandY1 > core->bandY0 ? core->bandY0 : 0)) * core->spp;
+	const uint32_t stride = (uint32_t)core->width * (core->bandY1 > core->bandY0 ? BandRowsOfCore( core ) : (uint32_t)core->height) * core->spp;
 	st.primaryRayCount = stride;
 	st.bounce1RayCount = maxLen >= 2 ? c.extensionRays[1] : 0;
 	st.deepRayCount = 0;
@@ -163,10 +165,31 @@ static void FinishFrame( lh2b_core* core )
 
 static int BandY0( const lh2b_core* core ) { return core->bandY1 > core->bandY0 ? core->bandY0 : 0; }
 static int BandY1( const lh2b_core* core ) { return core->bandY1 > core->bandY0 ? std::min( core->bandY1, core->height ) : core->height; }
+static int BandStep( const lh2b_core* core ) { return core->bandY1 > core->bandY0 ? std::max( 1, core->bandStep ) : 1; }
+static uint32_t BandTileRowsOf( const lh2b_core* core )
+{
+	const uint32_t first = (uint32_t)BandY0( core ) / 4, end = ((uint32_t)BandY1( core ) + 3) / 4, step = (uint32_t)BandStep( core );
+	return end > first ? (end - first + step - 1) / step : 0;
+}
+static bool WholeFrame( const lh2b_core* core ) { return BandY0( core ) == 0 && BandY1( core ) == core->height && BandStep( core ) == 1; }
+/* job slots of path length 1 (tile rows x 4 rows x width; rows outside the band are skipped by the kernels) */
+static uint32_t BandSlots( const lh2b_core* core ) { return WholeFrame( core ) ? (uint32_t)core->width * core->height : BandTileRowsOf( core ) * 4u * core->width; }
+/* rows this core really renders */
+static uint32_t BandRows( const lh2b_core* core )
+{
+	uint32_t rows = 0;
+	for (uint32_t j = 0, n = BandTileRowsOf( core ); j < n; j++)
+	{
+		const int t0 = ((BandY0( core ) / 4) + (int)j * BandStep( core )) * 4;
+		rows += (uint32_t)std::max( 0, std::min( t0 + 4, BandY1( core ) ) - std::max( t0, BandY0( core ) ) );
+	}
+	return rows;
+}
+static uint32_t BandRowsOfCore( const lh2b_core* core ) { return BandRows( core ); }
 
 static RenderParams BuildParams( lh2b_core* core, const lh2abi::ViewPyramid& view )
 {
-	const uint32_t stride = (uint32_t)core->width * (uint32_t)(BandY1( core ) - BandY0( core )) * core->spp;
+	const uint32_t stride = BandSlots( core ) * core->spp;
 	RenderParams p = {};
 	p.posLensSize = make_float4( view.pos.x, view.pos.y, view.pos.z, view.aperture );
 	p.right = make_float3( view.p2.x - view.p1.x, view.p2.y - view.p1.y, view.p2.z - view.p1.z );
@@ -176,7 +199,7 @@ static RenderParams BuildParams( lh2b_core* core, const lh2abi::ViewPyramid& vie
 	p.w = core->width, p.h = core->height, p.spp = core->spp;
 	p.pass = core->samplesTaken, p.shift = core->shiftSeed;
 	p.sampleBase = core->sampleShardTotal > 0 ? core->sampleShardFirst : 0;
-	p.stride = stride, p.bandY0 = BandY0( core ), p.bandY1 = BandY1( core );
+	p.stride = stride, p.bandY0 = BandY0( core ), p.bandY1 = BandY1( core ), p.bandStep = BandStep( core );
 	p.geometryEpsilon = core->geometryEpsilon, p.clampValue = core->clampValue;
 	p.probePixelIdx = core->probeX + core->width * core->probeY;
 	p.maxPathLength = core->maxPathLength, p.enoughBounces = core->enoughBounces, p.bsdfModel = core->bsdfModel;
@@ -214,16 +237,23 @@ static void SwapFrameSlots( lh2b_core* core )
 static void RenderFrame( lh2b_core* core, const lh2abi::ViewPyramid& view )
 {
 	cudaStream_t s = core->stream;
-	const uint32_t stride = (uint32_t)core->width * (uint32_t)(BandY1( core ) - BandY0( core )) * core->spp;
+	const uint32_t stride = BandSlots( core ) * core->spp;
 	core->lastView = view;
 	CUDA_CHECK( cudaEventRecord( core->events[0], s ) );
 	RotatePixelBuffers( core );
 	if (core->samplesTaken == 0)
 	{
 		// Restart: clear this core's rows of both accumulator halves (tile-sharded frames: the other rows belong to the peers' pushes)
-		const size_t px = (size_t)core->width * core->height, first = (size_t)BandY0( core ) * core->width, n = (size_t)stride / core->spp;
-		CUDA_CHECK( cudaMemsetAsync( core->accumulator.ptr + first, 0, n * sizeof( float4 ), s ) );
-		CUDA_CHECK( cudaMemsetAsync( core->accumulator.ptr + px + first, 0, n * sizeof( float4 ), s ) );
+		const size_t px = (size_t)core->width * core->height, rowBytes = (size_t)core->width * sizeof( float4 );
+		if (BandStep( core ) == 1)
+		{
+			const size_t first = (size_t)BandY0( core ) * core->width, n = (size_t)(BandY1( core ) - BandY0( core )) * core->width;
+			CUDA_CHECK( cudaMemsetAsync( core->accumulator.ptr + first, 0, n * sizeof( float4 ), s ) );
+			CUDA_CHECK( cudaMemsetAsync( core->accumulator.ptr + px + first, 0, n * sizeof( float4 ), s ) );
+		}
+		else for (int half = 0; half < 2; half++)	// strided tile rows (lh2b_set_row_band_strided guarantees whole tile rows)
+			CUDA_CHECK( cudaMemset2DAsync( core->accumulator.ptr + half * px + (size_t)BandY0( core ) * core->width, (size_t)BandStep( core ) * 4 * rowBytes, 0,
+				4 * rowBytes, BandTileRowsOf( core ), s ) );
 	}
 	if (core->filterEnabled) EnsureFilterBuffers( core );
 	CUDA_CHECK( cudaMemsetAsync( core->counters.ptr, 0, sizeof( DevCounters ), s ) );
@@ -708,12 +738,18 @@ int lh2b_filter_chain( lh2b_core* core, lh2b_filter_io* io )
 
 /* Tile-sharded frames (partitioning 2): this core renders rows [y0, y1) of the frame only - same path indices,
    seeds and buffers as the whole frame, so the rows are bit-identical to what one GPU would produce. y0 = y1 = 0: whole frame. */
-int lh2b_set_row_band( lh2b_core* core, int y0, int y1 )
+int lh2b_set_row_band( lh2b_core* core, int y0, int y1 ) { return lh2b_set_row_band_strided( core, y0, y1, 1 ); }
+
+/* The same with a stride: this core renders the 4-row tile rows y0/4 + j * stepTileRows below row y1 (interleaved bands balance the
+   load between ranks when the cost of a row varies over the image). stepTileRows > 1 needs y0, y1 and the frame height to be
+   multiples of 4. */
+int lh2b_set_row_band_strided( lh2b_core* core, int y0, int y1, int stepTileRows )
 {
 	API_BEGIN
-	if (y0 < 0 || y1 < y0 || (core->height > 0 && y1 > core->height)) throw CoreError( "set_row_band: rows out of range" );
+	if (y0 < 0 || y1 < y0 || (core->height > 0 && y1 > core->height) || stepTileRows < 1) throw CoreError( "set_row_band: rows out of range" );
+	if (stepTileRows > 1 && ((y0 | y1 | core->height) & 3)) throw CoreError( "set_row_band_strided: strided bands need rows in multiples of 4" );
 	FinishFrame( core );
-	core->bandY0 = y0, core->bandY1 = y1, core->samplesTaken = 0;
+	core->bandY0 = y0, core->bandY1 = y1, core->bandStep = stepTileRows, core->samplesTaken = 0;
 	API_END
 }
 

@@ -54,7 +54,8 @@ struct RenderParams
 	uint32_t shift;				// blue-noise tile shift (rendercore.cpp:855,860)
 	uint32_t sampleBase;		// first sample index of this core's shard (multi-GPU), 0 otherwise
 	uint32_t stride;			// paths of this frame on this core: w * (bandY1 - bandY0) * spp
-	int bandY0, bandY1;			// rows rendered by this core (tile-sharded frames, lh2b_set_row_band); the whole frame: 0, h
+	int bandY0, bandY1, bandStep;	// rows rendered by this core (tile-sharded frames, lh2b_set_row_band): the 4-row tile rows bandY0/4 + j * bandStep
+								// below row bandY1; the whole frame: 0, h, 1
 	float geometryEpsilon, clampValue;
 	int probePixelIdx;
 	int maxPathLength;			// reference MAXPATHLENGTH (3)
@@ -83,5 +84,13 @@ struct RenderParams
 	float4* worldPos;
 	float4* deltaDepth;
 };
+
+/* number of 4-row tile rows this core renders (tile-sharded frames) */
+static __host__ __device__ inline uint32_t BandTileRows( const RenderParams& p )
+{
+	const uint32_t first = (uint32_t)p.bandY0 / 4, end = ((uint32_t)p.bandY1 + 3) / 4;
+	return end > first ? (end - first + (uint32_t)p.bandStep - 1) / (uint32_t)p.bandStep : 0;
+}
+
 
 } // namespace lh2b

@@ -537,12 +537,14 @@ template <int BSDF, int MINB> __global__ void __launch_bounds__( 128, MINB ) sha
 	for (uint32_t round = 0; round < rounds; round++)
 	{
 		uint32_t job = (round * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
-		const bool inRange = job < pathCount;
+		bool inRange = job < pathCount;
 		if (pathLength == 1 && p.stride != (uint32_t)(p.w * p.h * p.spp) && inRange)
 		{
-			// tile-sharded frame: primary paths live at their global path index; job -> (sample, pixel of the band)
-			const uint32_t bandPixels = (uint32_t)(p.bandY1 - p.bandY0) * p.w, smp = job / bandPixels;
-			job = smp * (p.w * p.h) + (uint32_t)p.bandY0 * p.w + (job - smp * bandPixels);
+			// tile-sharded frame: primary paths live at their global path index; job -> (sample, tile row of the band, pixel in it)
+			const uint32_t tileRowPixels = 4u * p.w, bandPixels = BandTileRows( p ) * tileRowPixels, smp = job / bandPixels, i = job - smp * bandPixels;
+			const uint32_t j = i / tileRowPixels, rem = i - j * tileRowPixels, row = ((uint32_t)p.bandY0 / 4 + j * p.bandStep) * 4 + rem / p.w;
+			inRange = row < (uint32_t)p.bandY1 && row >= (uint32_t)p.bandY0;
+			job = smp * (p.w * p.h) + row * p.w + rem % p.w;
 		}
 		// every lane takes part in the two warp-wide allocations below; inactive lanes carry 'false'
 		bool emitShadow = false, emitExt = false;

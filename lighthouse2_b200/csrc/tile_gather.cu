@@ -7,7 +7,12 @@
    history, or the plain finalize - on the complete buffers. A row band is one contiguous range of every per-pixel buffer, so
    the exchange is a handful of peer copies per rank, straight into rank 0's own frame buffers:
 
-     rank r > 0, frame k:  [core stream]  render rows y_r .. y_(r+1) into the local buffers (tail deferred)
+   Layout of the bands: rank 0 takes rows [0, rootRows) (Setting "tileRootShare" x an equal share: it also runs the tail), the other
+   ranks interleave the remaining 4-row tile rows (rank r: tile rows rootRows/4 + (r-1) + j * (world-1)), because the cost of a
+   row varies over the image (sky vs. near geometry) and contiguous bands left the slowest peer to set the frame time. An
+   interleaved band is a 2D range (tile row x pitch) of every buffer: still one (2D) copy per buffer.
+
+     rank r > 0, frame k:  [core stream]  render its tile rows into the local buffers (tail deferred)
                            [comm stream]  wait( ack >= k )                          rank 0 has finished the tail of frame k-1
                                           copy rows of: accumulator (direct), and in filter mode accumulator (indirect),
                                           worldPos, deltaDepth -> the same rows of rank 0's buffers; features -> rank 0's staging
@@ -62,7 +67,8 @@ struct lh2b_tile_gather
 	lh2b_core* core = nullptr;
 	int rank = 0, world = 1, filter = 0, flip0 = 0;
 	size_t pixels = 0;
-	int rowOf[TILE_MAX_RANKS + 1] = {};		// band boundaries (multiples of 4 rows: the generate kernel works on 8x4-pixel tiles)
+	int rootRows = 0;							// rank 0 renders rows [0, rootRows); multiples of 4 rows: the generate kernel works on 8x4-pixel tiles
+	int bandY0 = 0, bandY1 = 0, bandStep = 1, tileRows = 0;	// this rank: tile rows bandY0/4 + j * bandStep below bandY1 (tileRows of them)
 	uint32_t frame = 0;
 	cudaStream_t comm = nullptr;
 	cudaEvent_t rendered = nullptr;
@@ -98,9 +104,11 @@ int lh2b_tile_create( lh2b_core* core, int rank, int world, lh2b_tile_gather** o
 	g->filter = core->filterEnabled ? 1 : 0;
 	// rank 0 also runs the tail of every frame while the peers already render the next one: Setting "tileRootShare" (0..1, default 1)
 	// scales its band relative to an equal share; the other ranks split the remaining rows evenly. Boundaries: multiples of 4 rows.
-	const int rootRows = world == 1 ? core->height : std::max( 4, (int)((double)core->height / world * core->tileRootShare) & ~3 );
-	g->rowOf[0] = 0;
-	for (int r = 1; r <= world; r++) g->rowOf[r] = r == world ? core->height : (rootRows + (int)((long long)(core->height - rootRows) * (r - 1) / (world - 1))) & ~3;
+	if ((core->height & 3) && world > 2) throw CoreError( "tile_create: interleaved bands need a frame height that is a multiple of 4" );
+	g->rootRows = world == 1 ? core->height : std::max( 4, (int)((double)core->height / world * core->tileRootShare) & ~3 );
+	if (rank == 0) g->bandY0 = 0, g->bandY1 = g->rootRows, g->bandStep = 1;
+	else g->bandY0 = g->rootRows + 4 * (rank - 1), g->bandY1 = core->height, g->bandStep = world - 1;
+	g->tileRows = g->bandY1 > g->bandY0 ? (((g->bandY1 + 3) / 4 - g->bandY0 / 4) + g->bandStep - 1) / g->bandStep : 0;
 	if (g->filter) EnsureFilterBuffersForSharing( core );
 	g->flip0 = core->filterFlip;
 	CUDA_CHECK( cudaStreamCreateWithFlags( &g->comm, cudaStreamNonBlocking ) );
@@ -122,7 +130,7 @@ int lh2b_tile_create( lh2b_core* core, int rank, int world, lh2b_tile_gather** o
 		if (g->filter) CUDA_CHECK( cudaMalloc( &g->featStage, g->pixels * sizeof( uint4 ) ) );
 	}
 	// this core renders its band only; the tail of the frame runs in lh2b_tile_frame on rank 0
-	const int rc = lh2b_set_row_band( core, g->rowOf[rank], g->rowOf[rank + 1] );
+	const int rc = lh2b_set_row_band_strided( core, g->bandY0, g->bandY1, g->bandStep );
 	if (rc != 0) throw CoreError( lh2b_last_error() );
 	core->deferTail = true;
 	CUDA_CHECK( cudaDeviceSynchronize() );
@@ -189,15 +197,18 @@ int lh2b_tile_frame( lh2b_tile_gather* g )
 	lh2b_core* core = g->core;
 	CUDA_CHECK( cudaSetDevice( core->device ) );
 	const uint32_t k = g->frame++;
-	const size_t w = (size_t)core->width, first = (size_t)g->rowOf[g->rank] * w, n = (size_t)(g->rowOf[g->rank + 1] - g->rowOf[g->rank]) * w;
+	const size_t w = (size_t)core->width, first = (size_t)g->bandY0 * w;
 	if (g->rank > 0)
 	{
 		CUstream cs = (CUstream)g->comm;
 		CUDA_CHECK( cudaEventRecord( g->rendered, core->stream ) );
 		CUDA_CHECK( cudaStreamWaitEvent( g->comm, g->rendered, 0 ) );
 		if (k >= 1) CU_CHECK( g->waitValue( cs, (CUdeviceptr)g->ack, k, CU_STREAM_WAIT_VALUE_GEQ ) );	// rank 0 is done with frame k-1's buffers
+		// this rank's rows of one per-pixel buffer: tileRows chunks of 4 rows, bandStep tile rows apart (one contiguous range if bandStep = 1)
 		auto push = [&]( void* dst, const void* src, size_t elem ) {
-			CUDA_CHECK( cudaMemcpyAsync( (char*)dst + first * elem, (const char*)src + first * elem, n * elem, cudaMemcpyDeviceToDevice, g->comm ) ); };
+			const size_t chunk = 4 * w * elem, pitch = chunk * (size_t)g->bandStep;
+			if (g->bandStep == 1) CUDA_CHECK( cudaMemcpyAsync( (char*)dst + first * elem, (const char*)src + first * elem, (size_t)(g->bandY1 - g->bandY0) * w * elem, cudaMemcpyDeviceToDevice, g->comm ) );
+			else CUDA_CHECK( cudaMemcpy2DAsync( (char*)dst + first * elem, pitch, (const char*)src + first * elem, pitch, chunk, (size_t)g->tileRows, cudaMemcpyDeviceToDevice, g->comm ) ); };
 		push( g->rootAccumulator, core->accumulator.ptr, 16 );
 		if (g->filter)
 		{
@@ -217,7 +228,7 @@ int lh2b_tile_frame( lh2b_tile_gather* g )
 		for (int r = 1; r < g->world; r++) CU_CHECK( g->waitValue( cs, (CUdeviceptr)(g->arrived + r), k + 1, CU_STREAM_WAIT_VALUE_GEQ ) );
 		if (g->filter && g->world > 1)
 		{
-			const int peerFirst = (int)((size_t)g->rowOf[1] * w), peerCount = (int)(g->pixels - (size_t)peerFirst);
+			const int peerFirst = (int)((size_t)g->rootRows * w), peerCount = (int)(g->pixels - (size_t)peerFirst);
 			mergeFeaturesKernel<<<(peerCount + 255) / 256, 256, 0, core->stream>>>( core->features.ptr, g->featStage, peerFirst, peerCount );
 			CUDA_CHECK( cudaGetLastError() );
 		}
@@ -235,10 +246,11 @@ int lh2b_tile_wait( lh2b_tile_gather* g )
 	API_END
 }
 
-int lh2b_tile_rows( lh2b_tile_gather* g, int* y0, int* y1 )
+/* this rank's band: tile rows y0/4 + j * step below row y1 */
+int lh2b_tile_rows( lh2b_tile_gather* g, int* y0, int* y1, int* stepTileRows )
 {
 	API_BEGIN
-	*y0 = g->rowOf[g->rank], *y1 = g->rowOf[g->rank + 1];
+	*y0 = g->bandY0, *y1 = g->bandY1, *stepTileRows = g->bandStep;
 	API_END
 }
 

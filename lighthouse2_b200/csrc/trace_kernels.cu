@@ -54,7 +54,10 @@ __global__ void __launch_bounds__( 128 ) generateExtendKernel( const DevScene sc
 	for (uint32_t pathIdx = blockIdx.x * blockDim.x + threadIdx.x; pathIdx < pixels * p.spp; pathIdx += gridDim.x * blockDim.x)
 	{
 		const uint32_t pixelIdx = pathIdx % pixels;
-		if ((int)(pixelIdx / p.w) < p.bandY0 || (int)(pixelIdx / p.w) >= p.bandY1) continue;	// tile-sharded frame: not this core's rows
+		{
+			const int row = (int)(pixelIdx / p.w), rel = row / 4 - p.bandY0 / 4;	// tile-sharded frame: skip rows that are not this core's
+			if (row < p.bandY0 || row >= p.bandY1 || rel % p.bandStep != 0) continue;
+		}
 		const uint32_t seedIdx = pathIdx + p.sampleBase * pixels;
 		const uint32_t sampleIdx = seedIdx / pixels + p.pass;
 		uint32_t seed = WangHashT( seedIdx * 16789 + p.pass * 1791 );
@@ -243,7 +246,7 @@ __device__ __forceinline__ void GeneratePrimary( const RenderParams& p, const ui
 struct TiledPrimarySource
 {
 	const RenderParams* p; float4* __restrict__ outO; float4* __restrict__ outD; uint32_t* __restrict__ pathOf;	// pathOf: smem-free mapping kept in registers by the sink
-	uint32_t tilesX, itemsPerSample, tileY0;	// tileY0: first 4-row tile row of this core's band
+	uint32_t tilesX, itemsPerSample, tileY0, tileStep;	// this core's tile rows: tileY0 + j * tileStep
 	uint64_t tilesXMagic, itemsMagic;	// MagicOf( tilesX ), MagicOf( itemsPerSample ): the index arithmetic below runs per ray at ~1/3 SIMT width
 	__device__ __forceinline__ bool Load( const uint32_t work, WideRay& r, uint32_t& tag ) const
 	{
@@ -251,7 +254,7 @@ struct TiledPrimarySource
 		const uint32_t s = p->spp == 1 ? 0 : DivMagic( work, itemsMagic ), w = work - s * itemsPerSample;
 		const uint32_t tile = w >> 5, l = w & 31;
 		const uint32_t ty = tilesX == 1 ? tile : DivMagic( tile, tilesXMagic ), tx = tile - ty * tilesX;
-		const uint32_t x = tx * 8 + (l & 7), y = (tileY0 + ty) * 4 + (l >> 3);
+		const uint32_t x = tx * 8 + (l & 7), y = (tileY0 + ty * tileStep) * 4 + (l >> 3);
 		if (x >= (uint32_t)p->w || (int)y < p->bandY0 || (int)y >= p->bandY1) return false;
 		const uint32_t pathIdx = x + y * p->w + s * (p->w * p->h);
 		tag = pathIdx;
@@ -275,8 +278,8 @@ template <bool TWO_LEVEL> __global__ void __launch_bounds__( WIDE_BLOCK ) wideGe
 {
 	TiledPrimarySource src;
 	src.p = &p, src.outO = out.O, src.outD = out.D, src.pathOf = nullptr;
-	src.tilesX = (p.w + 7) / 8, src.tileY0 = (uint32_t)p.bandY0 / 4;
-	src.itemsPerSample = src.tilesX * ((uint32_t)(p.bandY1 + 3) / 4 - src.tileY0) * 32;
+	src.tilesX = (p.w + 7) / 8, src.tileY0 = (uint32_t)p.bandY0 / 4, src.tileStep = (uint32_t)p.bandStep;
+	src.itemsPerSample = src.tilesX * BandTileRows( p ) * 32;
 	src.tilesXMagic = MagicOf( src.tilesX ), src.itemsMagic = MagicOf( src.itemsPerSample );
 	TiledHitSink sink = { &src, hits };
 	TraverseWide<false, TWO_LEVEL>( scene, src, sink, src.itemsPerSample * p.spp, workCounter, tune );
@@ -341,7 +344,7 @@ void LaunchGenerateExtend( const DevScene& scene, const RenderParams& p, const P
 {
 	if (g_traversalVariant == 1)
 	{
-		const uint32_t items = ((p.w + 7) / 8) * ((p.bandY1 + 3) / 4 - p.bandY0 / 4) * 32 * p.spp, grid = PersistentGrid( items, smCount, g_wideBlocksPerSM );
+		const uint32_t items = ((p.w + 7) / 8) * BandTileRows( p ) * 32 * p.spp, grid = PersistentGrid( items, smCount, g_wideBlocksPerSM );
 		if (scene.singleIdentity) wideGenerateExtendKernel<false><<<grid, WIDE_BLOCK, 0, s>>>( scene, p, out, hits, workCounter, TUNE );
 		else wideGenerateExtendKernel<true><<<grid, WIDE_BLOCK, 0, s>>>( scene, p, out, hits, workCounter, TUNE );
 	}

@@ -27,7 +27,7 @@ def make_core(dev, sd, spp):
 def tile_sharding(rank, world, local, sd):
     """Tile (row-band) sharded frames, plain and with the SVGF / TAA chain, moving camera: rank 0's image must equal the
     single-GPU frame bit for bit (1 spp)."""
-    TW, TH = 192, 128
+    TW, TH = 192, 160
     views = [scenes.view_pyramid((3 * k, 30, -80 + k), (0, 0, 0), 40, TW, TH) for k in range(5)]
     ok = True
     for filt in (0, 1):

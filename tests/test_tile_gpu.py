@@ -21,14 +21,21 @@ def _core(sd, spp, filt):
     return core
 
 
+def _rows(band):
+    y0, y1, step = band
+    return np.array([y for y in range(y0, y1) if ((y // 4) - (y0 // 4)) % step == 0])
+
+
 @pytest.mark.parametrize("filt", [False, True], ids=["plain", "filter-mode"])
-@pytest.mark.parametrize("band", [(0, 32), (20, 52), (64, 96)], ids=["top", "middle-unaligned", "bottom"])
+@pytest.mark.parametrize("band", [(0, 32, 1), (20, 52, 1), (64, 96, 1), (16, 96, 3), (8, 96, 7)],
+                         ids=["top", "middle-unaligned", "bottom", "every-3rd-tile-row", "every-7th-tile-row"])
 def test_row_band_equals_rows_of_the_whole_frame(band, filt):
     sd = scenes.config2_scene(48, 32, n_materials=6, light_quads=2, floaters=300)
     views = [scenes.view_pyramid((2 * k, 30, -80), (0, 0, 0), 40, W, H) for k in range(3)]
-    y0, y1 = band
+    y0, y1, step = band
+    rows = _rows(band)
     full, part = _core(sd, 1, filt), _core(sd, 1, filt)
-    part.SetRowBand(y0, y1)
+    part.SetRowBand(y0, y1, step)
     for v in views:                      # Restart frames: seeds evolve, history bits of the features persist
         full.Render(v, 1), part.Render(v, 1)
         if filt:
@@ -39,12 +46,14 @@ def test_row_band_equals_rows_of_the_whole_frame(band, filt):
             ff[..., 3] &= 0xFFFFFFF0
             pf[..., 3] &= 0xFFFFFFF0
             for a, b in ((ff, pf), (fw, pw), (fd, pd)):          # bit patterns: packed words and NaN-able floats live in these buffers
-                assert np.array_equal(a[y0:y1].view(np.uint32), b[y0:y1].view(np.uint32))
-            assert np.array_equal(fa[:, y0:y1].view(np.uint32), pa[:, y0:y1].view(np.uint32))
+                assert np.array_equal(a[rows].view(np.uint32), b[rows].view(np.uint32))
+            assert np.array_equal(fa[:, rows].view(np.uint32), pa[:, rows].view(np.uint32))
         else:
-            assert np.array_equal(full.ReadAccumulator()[y0:y1], part.ReadAccumulator()[y0:y1])
+            assert np.array_equal(full.ReadAccumulator()[rows], part.ReadAccumulator()[rows])
+            others = np.setdiff1d(np.arange(H), rows)
+            assert not part.ReadAccumulator()[others].any()
     st_full, st_part = full.GetCoreStats(), part.GetCoreStats()
-    assert int(st_part["primaryRayCount"]) == W * (y1 - y0) and int(st_full["primaryRayCount"]) == W * H
+    assert int(st_part["primaryRayCount"]) == W * len(rows) and int(st_full["primaryRayCount"]) == W * H
     assert 0 < int(st_part["totalRays"]) < int(st_full["totalRays"])
     # back to the whole frame
     part.SetRowBand(0, 0)

@@ -13,6 +13,7 @@ from lighthouse2_b200.distributed import TileShardedRenderer
 
 out_path = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/c5_scaling.json"
 frames = int(sys.argv[2]) if len(sys.argv) > 2 else 40
+readback = (sys.argv[3] if len(sys.argv) > 3 else "readback") == "readback"   # "device": the finished frame stays in rank 0's pixel buffer
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
 if world > 1:
@@ -37,10 +38,11 @@ if r is None:
 def run(n, f0):
     for f in range(n):
         if r is not None:
-            r.frame(view_of(f0 + f), 1, host[f & 1] if rank == 0 else None)
+            r.frame(view_of(f0 + f), 1, host[f & 1] if (rank == 0 and readback) else None)
         else:
             core.Render(view_of(f0 + f), 1, True)
-            core.ReadPixelsAsync(host[f & 1].numpy())
+            if readback:
+                core.ReadPixelsAsync(host[f & 1].numpy())
     if r is not None:
         r.finish()
     else:
@@ -60,8 +62,9 @@ dt = time.perf_counter() - t0
 if rank == 0:
     res = {"config": "C5: 3840x2160, 1 spp, path length 3, filter + TAA, moving camera, 1,000,016 triangles, 64 materials", "n_gpus": world,
            "frames": frames, "ms_per_frame": dt / frames * 1e3, "fps": frames / dt,
+           "frame_ends": "in pinned host memory (133 MB RGBA32F over PCIe per frame)" if readback else "in rank 0's device pixel buffer (what a GL / display path consumes)",
            "sharding": "tile (row bands), bands gathered on rank 0 over NVLink peer memory, filter chain on rank 0" if world > 1 else "none",
-           "rows_rank0": list(r.rows) if r is not None else [0, H], "image_mean": float(host[(frames - 1) & 1].numpy()[..., :3].mean())}
+           "rows_rank0": list(r.rows) if r is not None else [0, H], "image_mean": float(host[(frames - 1) & 1].numpy()[..., :3].mean()) if readback else float(core.ReadPixels()[..., :3].mean())}
     print(json.dumps(res), flush=True)
     os.makedirs(os.path.dirname(out_path) or ".", exist_ok=True)
     json.dump(res, open(out_path, "w"), indent=1)
