@@ -39,5 +39,7 @@ def test_own_header_host_renders():
 def test_reference_header_host_matches():
     a, b = _run(REF_HOST), _run(_own_host())
     assert a["flavour"] == "reference-headers" and b["flavour"] == "own-header"
-    for k in ("mean", "primary", "extension", "shadow", "total", "probe", "device", "sm"):
+    for k in ("primary", "extension", "shadow", "total", "probe", "device", "sm"):
         assert a[k] == b[k], k
+    # 2 spp: two paths add to one pixel with float atomics, so the sums may differ in the last bits from run to run
+    assert all(abs(x - y) <= 1e-4 * abs(y) for x, y in zip(a["mean"], b["mean"])), (a["mean"], b["mean"])
