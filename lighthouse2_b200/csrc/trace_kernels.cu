@@ -243,7 +243,7 @@ __device__ __forceinline__ void GeneratePrimary( const RenderParams& p, const ui
 	GeneratePrimaryAt( p, sx, sy, s, pathIdx, O, D );
 }
 
-struct TiledPrimarySource
+template <bool BAND> struct TiledPrimarySource	// BAND: tile-sharded frame (this core renders some tile rows only); false keeps the whole-frame index math
 {
 	const RenderParams* p; float4* __restrict__ outO; float4* __restrict__ outD; uint32_t* __restrict__ pathOf;	// pathOf: smem-free mapping kept in registers by the sink
 	uint32_t tilesX, itemsPerSample, tileY0, tileStep;	// this core's tile rows: tileY0 + j * tileStep
@@ -254,8 +254,8 @@ struct TiledPrimarySource
 		const uint32_t s = p->spp == 1 ? 0 : DivMagic( work, itemsMagic ), w = work - s * itemsPerSample;
 		const uint32_t tile = w >> 5, l = w & 31;
 		const uint32_t ty = tilesX == 1 ? tile : DivMagic( tile, tilesXMagic ), tx = tile - ty * tilesX;
-		const uint32_t x = tx * 8 + (l & 7), y = (tileY0 + ty * tileStep) * 4 + (l >> 3);
-		if (x >= (uint32_t)p->w || (int)y < p->bandY0 || (int)y >= p->bandY1) return false;
+		const uint32_t x = tx * 8 + (l & 7), y = (BAND ? tileY0 + ty * tileStep : ty) * 4 + (l >> 3);
+		if (x >= (uint32_t)p->w || (BAND ? ((int)y < p->bandY0 || (int)y >= p->bandY1) : y >= (uint32_t)p->h)) return false;
 		const uint32_t pathIdx = x + y * p->w + s * (p->w * p->h);
 		tag = pathIdx;
 		GeneratePrimaryAt( *p, (int)x, (int)y, s, pathIdx, r.O, r.D );
@@ -268,20 +268,20 @@ struct TiledPrimarySource
 
 struct TiledHitSink
 {
-	const TiledPrimarySource* src; float4* __restrict__ hits;
+	float4* __restrict__ hits;
 	__device__ __forceinline__ void Closest( const uint32_t pathIdx, const bool hit, const TraceResult& r ) const { hits[pathIdx] = PackHit( hit, r ); }
 	__device__ __forceinline__ void AnyHit( const uint32_t, const bool ) const {}
 };
 
-template <bool TWO_LEVEL> __global__ void __launch_bounds__( WIDE_BLOCK ) wideGenerateExtendKernel( const DevScene scene, const RenderParams p, const PathSet out, float4* __restrict__ hits,
+template <bool TWO_LEVEL, bool BAND> __global__ void __launch_bounds__( WIDE_BLOCK ) wideGenerateExtendKernel( const DevScene scene, const RenderParams p, const PathSet out, float4* __restrict__ hits,
 	uint32_t* workCounter, const WideTuning tune )
 {
-	TiledPrimarySource src;
+	TiledPrimarySource<BAND> src;
 	src.p = &p, src.outO = out.O, src.outD = out.D, src.pathOf = nullptr;
 	src.tilesX = (p.w + 7) / 8, src.tileY0 = (uint32_t)p.bandY0 / 4, src.tileStep = (uint32_t)p.bandStep;
-	src.itemsPerSample = src.tilesX * BandTileRows( p ) * 32;
+	src.itemsPerSample = src.tilesX * (BAND ? BandTileRows( p ) : ((uint32_t)p.h + 3) / 4) * 32;
 	src.tilesXMagic = MagicOf( src.tilesX ), src.itemsMagic = MagicOf( src.itemsPerSample );
-	TiledHitSink sink = { &src, hits };
+	TiledHitSink sink = { hits };
 	TraverseWide<false, TWO_LEVEL>( scene, src, sink, src.itemsPerSample * p.spp, workCounter, tune );
 }
 
@@ -345,8 +345,14 @@ void LaunchGenerateExtend( const DevScene& scene, const RenderParams& p, const P
 	if (g_traversalVariant == 1)
 	{
 		const uint32_t items = ((p.w + 7) / 8) * BandTileRows( p ) * 32 * p.spp, grid = PersistentGrid( items, smCount, g_wideBlocksPerSM );
-		if (scene.singleIdentity) wideGenerateExtendKernel<false><<<grid, WIDE_BLOCK, 0, s>>>( scene, p, out, hits, workCounter, TUNE );
-		else wideGenerateExtendKernel<true><<<grid, WIDE_BLOCK, 0, s>>>( scene, p, out, hits, workCounter, TUNE );
+		const bool band = !(p.bandY0 == 0 && p.bandY1 == p.h && p.bandStep == 1);
+		if (scene.singleIdentity)
+		{
+			if (band) wideGenerateExtendKernel<false, true><<<grid, WIDE_BLOCK, 0, s>>>( scene, p, out, hits, workCounter, TUNE );
+			else wideGenerateExtendKernel<false, false><<<grid, WIDE_BLOCK, 0, s>>>( scene, p, out, hits, workCounter, TUNE );
+		}
+		else if (band) wideGenerateExtendKernel<true, true><<<grid, WIDE_BLOCK, 0, s>>>( scene, p, out, hits, workCounter, TUNE );
+		else wideGenerateExtendKernel<true, false><<<grid, WIDE_BLOCK, 0, s>>>( scene, p, out, hits, workCounter, TUNE );
 	}
 	else generateExtendKernel<<<GridFor( (uint32_t)p.w * p.h * p.spp, smCount ), 128, 0, s>>>( scene, p, out, hits );
 }
