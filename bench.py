@@ -44,7 +44,8 @@ def build_scene():
 
 
 class ClockSampler:
-    """nvidia-smi sampled every 200 ms while the timed region runs (recipe: /opt/skills/guides/B200_PROFILING.md)."""
+    """nvidia-smi sampled every 20 ms (recipe: /opt/skills/guides/B200_PROFILING.md). Started well before the timed region (the tool
+    takes a few hundred ms to produce its first line); stop() keeps the samples that fall inside the window it is given."""
 
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
@@ -53,9 +54,11 @@ class ClockSampler:
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
+            import atexit
+            atexit.register(lambda: self.proc is not None and self.proc.poll() is None and self.proc.terminate())
         except OSError:
             self.proc = None
 
@@ -68,7 +71,9 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
-        rows = [r for t, r in self.rows if t0 - 0.05 <= t <= t1 + 0.15] or [r for _, r in self.rows]
+        rows = [r for t, r in self.rows if t0 - 0.02 <= t <= t1 + 0.05]
+        if not rows:      # (nvidia-smi slower than the window: the samples closest to it)
+            rows = [r for _, r in sorted(self.rows, key=lambda tr: min(abs(tr[0] - t0), abs(tr[0] - t1)))[:3]]
         sm, mx, reasons = [], [], set()
         for r in rows:
             try:
@@ -151,6 +156,7 @@ def run_ours(args, rank, world, local_rank):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - the core has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     sd, view = build_scene()
     core = RenderCore(local_rank)
     core.SetTarget(W, H, SPP)
@@ -224,7 +230,6 @@ def run_ours(args, rank, world, local_rank):
     for k in stage:
         stage[k] = 0.0
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     barrier()
     t0 = time.time()
     ev0.record(stream)
@@ -233,7 +238,6 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     t1 = time.time()
     ms = ev0.elapsed_time(ev1)
-    clocks = sampler.stop(t0, t1) if sampler else None
     timed_stage = dict(stage)
     # ---- end-to-end run through the public API: view from host memory, every frame read back to pinned host memory ----
     barrier()
@@ -241,6 +245,8 @@ def run_ours(args, rank, world, local_rank):
     e_rays = run(args.steps, True)
     barrier()
     e_secs = time.perf_counter() - e0
+    # clocks under load: the device-timed region and the end-to-end region that follows it run the same workload back to back
+    clocks = sampler.stop(t0, time.time()) if sampler else None
     stage = timed_stage
     if world > 1:
         t = torch.tensor([ms, e_secs, float(rays), float(e_rays)], dtype=torch.float64, device=f"cuda:{local_rank}")
