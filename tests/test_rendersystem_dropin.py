@@ -89,6 +89,28 @@ def test_reference_rendersystem_feeds_the_tinyapp_scene(tmp_path):
 
 
 @needs_ref
+def test_reference_rendersystem_resends_skinned_geometry_every_frame(tmp_path):
+    """CPU: the animated glTF scene the imguiapp / viewerapp load (CesiumMan.glb). RenderSystem re-skins the mesh on the host and
+    hands it to the core again through SetGeometry - same mesh index, same triangle count, new vertices and normals."""
+    if not os.path.exists(os.path.join(ASSETS, "CesiumMan.glb")):
+        pytest.skip("CesiumMan.glb not staged")
+    recs = []
+    for frames in (1, 3):
+        rec = str(tmp_path / f"scene{frames}.rec")
+        st = run_host(RECORDER, str(tmp_path / "none.bin"), frames=frames, w=64, h=36, record=rec, anim="CesiumMan.glb")
+        assert st["animations"] == 1
+        recs.append(orc.load_recording(rec)[0])
+    a, b = recs
+    assert len(a.meshes) == len(b.meshes) == 173 and a.meshes[-1][1].shape[0] == b.meshes[-1][1].shape[0] == 4672
+    assert np.abs(a.meshes[-1][0] - b.meshes[-1][0]).max() > 1e-3                       # the pose moved
+    assert np.abs(a.meshes[-1][1]["vN0"] - b.meshes[-1][1]["vN0"]).max() > 1e-4         # and the normals with it
+    assert np.array_equal(a.meshes[0][0], b.meshes[0][0])                               # static meshes are not touched
+    for sd in recs:                                                                      # CoreTri vertices agree with the float4 vertex stream
+        v, t = sd.meshes[-1]
+        assert np.allclose(t["vertex0"], v[0::3, :3]) and np.allclose(t["vertex2"], v[2::3, :3])
+
+
+@needs_ref
 @pytest.mark.gpu
 def test_tinyapp_through_reference_rendersystem_on_our_core(tmp_path):
     W, H = 640, 360
