@@ -404,6 +404,15 @@ def ref_filter_gpu(inputs, settings):
     return outs
 
 
+def filter_chain_cpu(inputs, settings):
+    """The oracle's CPU restatement of the SVGF / TAA chain (lh2_oracle_filter.h) on the same inputs / settings dictionaries as
+    ref_filter_gpu; returns the same dictionary of outputs."""
+    io, outs, keep = make_filter_io(inputs, settings)
+    if lib().orc_filter_chain(ctypes.byref(io)) != 0:
+        raise RuntimeError("orc_filter_chain failed")
+    return outs
+
+
 def _bind_normals(tris):
     """float4 per vertex: vN0..2 (+ the N component riding in w) of every CoreTri, as the skinning code sees them."""
     t = np.ascontiguousarray(tris).view(np.float32).reshape(-1, 52)

@@ -330,3 +330,56 @@ ORC_API void orc_morph_mesh( const float* bindVerts, const float* bindNormals, c
 {
 	orc::MorphMesh( bindVerts, bindNormals, deltas, normals, w, targetCount, triCount, verts, tris );
 }
+
+/* ---- SVGF / TAA chain (lh2_oracle_filter.h) -------------------------------------------------------------------------- */
+#include "lh2_oracle_filter.h"
+
+/* same layout as RefFilterIO of oracle/ref_filter_gpu.cu (ctypes: binding.FilterIO), so one set of buffers drives the reference
+   kernels, the product's parity hook and this restatement */
+struct OrcFilterIO
+{
+	int w, h, samplesTaken, camIsStationary, taa;
+	float directClamp, indirectClamp, j0, j1, prevj0, prevj1;
+	float prevView[17];
+	const float* accumulator; const uint32_t* features; const float* worldPos; const float* prevWorldPos; const float* deltaDepth;
+	const float* prevMoments; const float* filteredIN; const float* prevPixels;
+	uint32_t* featuresOut; float* shadingAfterPrepare; float* motion; float* moments;
+	float* phase1; float* phase2; float* phase3; float* taaPixels; float* target;
+};
+
+ORC_API int orc_filter_chain( const OrcFilterIO* io )
+{
+	using namespace orcf;
+	const int w = io->w, h = io->h;
+	const size_t px = (size_t)w * h;
+	std::vector<U4> feat( px );
+	memcpy( feat.data(), io->features, px * 16 );
+	std::vector<V4> shading( px ), moments( px ), fOUT( px ), fIN( px ), taa( px ), target( px, V4{ 0, 0, 0, 0 } );
+	std::vector<V2> motion( px );
+	memcpy( fIN.data(), io->filteredIN, px * 16 );
+	Chain c;
+	c.w = w, c.h = h, c.samplesTaken = io->samplesTaken, c.camIsStationary = io->camIsStationary, c.taa = io->taa;
+	c.directClamp = io->directClamp, c.indirectClamp = io->indirectClamp, c.j0 = io->j0, c.j1 = io->j1, c.prevj0 = io->prevj0, c.prevj1 = io->prevj1;
+	memcpy( c.prevView, io->prevView, sizeof( c.prevView ) );
+	c.accumulator = (const V4*)io->accumulator, c.features = feat.data(), c.worldPos = (const V4*)io->worldPos, c.prevWorldPos = (const V4*)io->prevWorldPos;
+	c.deltaDepth = (const V4*)io->deltaDepth, c.prevMoments = (const V4*)io->prevMoments;
+	c.shading = shading.data(), c.motion = motion.data(), c.moments = moments.data();
+	Prepare( c );
+	memcpy( io->shadingAfterPrepare, shading.data(), px * 16 ), memcpy( io->motion, motion.data(), px * 8 );
+	memcpy( io->moments, moments.data(), px * 16 ), memcpy( io->featuresOut, feat.data(), px * 16 );
+	ApplyFilter( c, shading.data(), fIN.data(), fOUT.data(), 1, 0 );
+	memcpy( io->phase1, fOUT.data(), px * 16 );
+	ApplyFilter( c, fOUT.data(), nullptr, fIN.data(), 2, 0 );
+	memcpy( io->phase2, fIN.data(), px * 16 );
+	ApplyFilter( c, fIN.data(), nullptr, shading.data(), 3, 1 );
+	memcpy( io->phase3, shading.data(), px * 16 );
+	if (io->taa)
+	{
+		TaaPass( shading.data(), taa.data(), (const V4*)io->prevPixels, motion.data(), w, h );
+		memcpy( io->taaPixels, taa.data(), px * 16 );
+		UnsharpenTaa( taa.data(), target.data(), w, h );
+	}
+	else FinalizeNoTaa( shading.data(), target.data(), w, h );
+	memcpy( io->target, target.data(), px * 16 );
+	return 0;
+}

@@ -88,3 +88,59 @@ def test_golden_covers_the_branches(setup):
     assert len(g["L1_extO"]) > 1000 and len(g["L1_shO"]) > 1000 and len(g["L2_extO"]) > 20 and len(g["L3_shO"]) > 3
     flags = g["L1_extO"][:, 3].view(np.uint32) & 63
     assert (flags & 1).any() and (flags & 2).any() and (flags & 4).any()      # specular, bounced and via-specular paths all occur
+
+
+def _frac_bad(a, b, tol):
+    return float((np.abs(np.asarray(a, np.float64) - np.asarray(b, np.float64)) > tol).any(axis=-1).mean())
+
+
+def _uncombine(x):
+    """5.11 fixed-point pairs (tools_shared.h:237-262) -> (direct, indirect) float triples"""
+    u = np.ascontiguousarray(x).view(np.uint32)
+    d = np.stack([(u[..., 0] >> 16), (u[..., 0] & 65535), u[..., 1]], -1) / 2048.0
+    i = np.stack([(u[..., 2] >> 16), (u[..., 2] & 65535), u[..., 3]], -1) / 2048.0
+    return d, i
+
+
+def test_filter_chain_against_reference_kernel_vectors():
+    """The oracle's CPU restatement of the SVGF / TAA chain (oracle/lh2_oracle_filter.h) against outputs of the REFERENCE's own
+    filter kernels (finalize_shared.h, compiled unmodified for sm_100a and run on the B200 by tools/make_golden_filter.py).
+    The reference kernels are fast-math builds, the oracle uses libm, and two stages are sensitive to that: the diamond search of
+    specular pixels accepts a step on `d < bestDist`, which is a tie on planar regions (one search step of 5 * 0.45^k pixels
+    more or less - 34 % of the specular pixels here, none of the diffuse ones), and the reference's TAA pass is racy (stored as a
+    per-pixel [min, max] over 12 executions). Tolerances below are the measured disagreement with head-room."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "filter_reference_vectors.npz"))
+    inputs = {k[3:]: g[k] for k in g.files if k.startswith("in_")}
+    H, W = inputs["features"].shape[:2]
+
+    def settings(taa, stationary):
+        return dict(w=W, h=H, samplesTaken=1, camIsStationary=stationary, taa=taa, directClamp=15.0, indirectClamp=15.0, j0=0.0, j1=0.0,
+                    prevj0=0.0, prevj1=0.0, prevView=g["prevView"])
+
+    # B: stationary camera, no TAA - no search, no race: everything agrees closely
+    b = orc.filter_chain_cpu(inputs, settings(0, 1))
+    gd, gi = _uncombine(b["shadingAfterPrepare"]); wd, wi = _uncombine(g["B_shadingAfterPrepare"])
+    assert _frac_bad(gd, wd, 1.5 / 2048) == 0 and _frac_bad(gi, wi, 1.5 / 2048) == 0
+    assert _frac_bad(b["motion"], g["B_motion"], 1e-3) == 0 and _frac_bad(b["moments"], g["B_moments"], 2e-3) < 0.002
+    assert (b["featuresOut"] != g["B_featuresOut"]).any(axis=-1).mean() < 0.002
+    assert _frac_bad(b["phase3"][..., :3], g["B_phase3"][..., :3], 5e-3) < 0.005
+    assert _frac_bad(b["target"][..., :3], g["B_target"][..., :3], 5e-3) < 0.005
+    assert not b["target"][0].any() and not b["target"][:, 0].any()          # border pixels are never written (finalize_shared.h:594)
+    # A: moving camera, TAA
+    a = orc.filter_chain_cpu(inputs, settings(1, 0))
+    gd, gi = _uncombine(a["shadingAfterPrepare"]); wd, wi = _uncombine(g["A_shadingAfterPrepare"])
+    assert _frac_bad(gd, wd, 1.5 / 2048) == 0 and _frac_bad(gi, wi, 1.5 / 2048) == 0
+    spec = ((inputs["features"][..., 3] >> 4) & 3) != 0
+    d = np.abs(a["motion"] - g["A_motion"]).max(axis=-1)
+    assert (d[~spec] > 1e-3).mean() == 0                                      # analytic reprojection of diffuse pixels
+    assert 0.05 < spec.mean() < 0.5 and (d[spec] > 2e-2).mean() < 0.5 and (d[spec] > 1.1).mean() < 0.01   # searched pixels: within one early step
+    assert _frac_bad(a["moments"], g["A_moments"], 2e-3) < 0.03
+    assert (a["featuresOut"] != g["A_featuresOut"]).any(axis=-1).mean() < 0.01
+    for k in ("phase1", "phase2"):
+        gd, gi = _uncombine(a[k]); wd, wi = _uncombine(g["A_" + k])
+        assert _frac_bad(gd, wd, 4.0 / 2048) < 0.02 and _frac_bad(gi, wi, 4.0 / 2048) < 0.03, k
+    assert _frac_bad(a["phase3"][..., :3], g["A_phase3"][..., :3], 5e-3) < 0.015
+    for k, tol, bound in (("taaPixels", 1e-2, 0.06), ("target", 3e-2, 0.05)):
+        lo, hi, x = g["A_" + k + "_min"][..., :3], g["A_" + k + "_max"][..., :3], a[k][..., :3]
+        assert float(((x < lo - tol) | (x > hi + tol)).any(axis=-1).mean()) < bound, k
+    assert np.isfinite(a["target"]).all() and a["target"][1:-1, 1:-1, :3].mean() > 0.05
