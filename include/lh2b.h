@@ -126,6 +126,7 @@ typedef struct lh2b_tile_gather lh2b_tile_gather;
 LH2B_API int lh2b_set_row_band( lh2b_core* core, int y0, int y1 );
 LH2B_API int lh2b_set_row_band_strided( lh2b_core* core, int y0, int y1, int stepTileRows );	/* tile rows y0/4 + j * step below row y1 */
 LH2B_API int lh2b_tile_handle_bytes( void );
+LH2B_API int lh2b_tile_layout( int height, int world, float rootShare, int rank, int* y0, int* y1, int* stepTileRows );	/* the band of a rank; needs no device */
 LH2B_API int lh2b_tile_create( lh2b_core* core, int rank, int world, lh2b_tile_gather** out );
 LH2B_API int lh2b_tile_export( lh2b_tile_gather* g, void* handlesOut );
 LH2B_API int lh2b_tile_import( lh2b_tile_gather* g, const void* handlesOfAllRanks );

@@ -47,6 +47,7 @@ SIGNATURES = {
     "lh2b_set_row_band": ([_vp, _ip, _ip], _ip),
     "lh2b_set_row_band_strided": ([_vp, _ip, _ip, _ip], _ip),
     "lh2b_tile_handle_bytes": ([], _ip),
+    "lh2b_tile_layout": ([_ip, _ip, _c.c_float, _ip, _c.POINTER(_ip), _c.POINTER(_ip), _c.POINTER(_ip)], _ip),
     "lh2b_tile_create": ([_vp, _ip, _ip, _c.POINTER(_vp)], _ip),
     "lh2b_tile_export": ([_vp, _vp], _ip),
     "lh2b_tile_import": ([_vp, _vp], _ip),

@@ -91,6 +91,21 @@ extern "C" {
 
 int lh2b_tile_handle_bytes() { return (int)sizeof( TileHandles ); }
 
+/* Band layout (pure host arithmetic, no device needed): rank 0 renders rows [0, rootRows), rootRows = an equal share x rootShare,
+   at least one tile row; rank r > 0 renders the 4-row tile rows rootRows/4 + (r-1) + j * (world-1) below the last row. Every row
+   belongs to exactly one rank. Returns the band as (y0, y1, step) for lh2b_set_row_band_strided. */
+int lh2b_tile_layout( int height, int world, float rootShare, int rank, int* y0, int* y1, int* stepTileRows )
+{
+	API_BEGIN
+	if (world < 1 || world > TILE_MAX_RANKS || rank < 0 || rank >= world || height < 4 * world) throw CoreError( "tile_layout: arguments out of range" );
+	if ((height & 3) && world > 2) throw CoreError( "tile_layout: interleaved bands need a frame height that is a multiple of 4" );
+	const float share = rootShare < 0 ? 0 : (rootShare > 1 ? 1 : rootShare);
+	const int rootRows = world == 1 ? height : std::max( 4, (int)((double)height / world * share) & ~3 );
+	if (rank == 0) *y0 = 0, *y1 = rootRows, *stepTileRows = 1;
+	else *y0 = rootRows + 4 * (rank - 1), *y1 = height, *stepTileRows = world - 1;
+	API_END
+}
+
 int lh2b_tile_create( lh2b_core* core, int rank, int world, lh2b_tile_gather** out )
 {
 	API_BEGIN
@@ -104,10 +119,10 @@ int lh2b_tile_create( lh2b_core* core, int rank, int world, lh2b_tile_gather** o
 	g->filter = core->filterEnabled ? 1 : 0;
 	// rank 0 also runs the tail of every frame while the peers already render the next one: Setting "tileRootShare" (0..1, default 1)
 	// scales its band relative to an equal share; the other ranks split the remaining rows evenly. Boundaries: multiples of 4 rows.
-	if ((core->height & 3) && world > 2) throw CoreError( "tile_create: interleaved bands need a frame height that is a multiple of 4" );
-	g->rootRows = world == 1 ? core->height : std::max( 4, (int)((double)core->height / world * core->tileRootShare) & ~3 );
-	if (rank == 0) g->bandY0 = 0, g->bandY1 = g->rootRows, g->bandStep = 1;
-	else g->bandY0 = g->rootRows + 4 * (rank - 1), g->bandY1 = core->height, g->bandStep = world - 1;
+	int r0y0, r0y1, r0step;
+	if (lh2b_tile_layout( core->height, world, core->tileRootShare, 0, &r0y0, &r0y1, &r0step ) != 0) throw CoreError( lh2b_last_error() );
+	if (lh2b_tile_layout( core->height, world, core->tileRootShare, rank, &g->bandY0, &g->bandY1, &g->bandStep ) != 0) throw CoreError( lh2b_last_error() );
+	g->rootRows = r0y1;
 	g->tileRows = g->bandY1 > g->bandY0 ? (((g->bandY1 + 3) / 4 - g->bandY0 / 4) + g->bandStep - 1) / g->bandStep : 0;
 	if (g->filter) EnsureFilterBuffersForSharing( core );
 	g->flip0 = core->filterFlip;
