@@ -413,6 +413,40 @@ def filter_chain_cpu(inputs, settings):
     return outs
 
 
+class FilteredFrameOracle:
+    """CPU counterpart of the filtering core for whole frame sequences (BASELINE.json configs[4] at oracle sizes): FrameOracle in
+    filter mode (feature writes, direct / indirect split: lib/RenderCore_Optix7Filter/kernels/pathtracer.h) followed by the CPU
+    restatement of the SVGF / TAA chain (lh2_oracle_filter.h) with the buffer rotation of RenderCore::FinalizeRender
+    (lib/RenderCore_Optix7Filter/rendercore.cpp:904-934: swap filteredIN / filteredOUT, shading / prevPixels, worldPos /
+    prevWorldPos, moments / prevMoments). render() returns the presented frame (float32 [h, w, 4])."""
+
+    def __init__(self, scene, width, height, epsilon=1e-3, clamp=10.0, max_path_length=3, taa=True, clamp_direct=15.0, clamp_indirect=15.0, threads=None):
+        self.frame = FrameOracle(scene, width, height, 1, epsilon, clamp, max_path_length, 1, threads=threads, filter=True)
+        self.w, self.h, self.taa = width, height, 1 if taa else 0
+        self.clamp_direct, self.clamp_indirect = clamp_direct, clamp_indirect
+        z = lambda: np.zeros((height, width, 4), np.float32)
+        self.prev_world_pos, self.prev_moments, self.filtered_in, self.prev_pixels = z(), z(), z(), z()
+        self.prev_view = None
+        self.stages = None
+
+    def render(self, view, converge=1):
+        f = self.frame
+        f.render(view, converge)
+        view_bytes = np.frombuffer(np.ascontiguousarray(view).tobytes(), np.float32).copy()
+        st = dict(w=self.w, h=self.h, samplesTaken=f.samples_taken, camIsStationary=0 if f.samples_taken == f.spp else 1, taa=self.taa,
+                  directClamp=self.clamp_direct, indirectClamp=self.clamp_indirect, j0=0.0, j1=0.0, prevj0=0.0, prevj1=0.0,
+                  prevView=self.prev_view if self.prev_view is not None else view_bytes)
+        inputs = dict(accumulator=f.accum, features=f.features, worldPos=f.world_pos, prevWorldPos=self.prev_world_pos, deltaDepth=f.delta_depth,
+                      prevMoments=self.prev_moments, filteredIN=self.filtered_in, prevPixels=self.prev_pixels)
+        out = filter_chain_cpu(inputs, st)
+        f.features[...] = out["featuresOut"]                       # the history counters prepare updated (shade keeps them next frame)
+        self.prev_world_pos, self.prev_moments = f.world_pos.copy(), out["moments"]
+        self.filtered_in = out["phase1"]                             # this frame's phase-1 output is the next frame's temporal history
+        self.prev_pixels = out["taaPixels"] if self.taa else out["phase3"]
+        self.prev_view, self.stages = view_bytes, out
+        return out["target"]
+
+
 def _bind_normals(tris):
     """float4 per vertex: vN0..2 (+ the N component riding in w) of every CoreTri, as the skinning code sees them."""
     t = np.ascontiguousarray(tris).view(np.float32).reshape(-1, 52)

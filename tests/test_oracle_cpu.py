@@ -156,3 +156,35 @@ def test_bvh_oracle_full_frame_equals_exhaustive_frame():
         o2 = orc.FrameOracle(sd, W, H, 2, 1e-3, 10.0, 3, 1, threads=4)
         b = o2.render(view, 1).copy(); cb = tuple(o2.ray_counts)
     assert ca == cb and np.array_equal(a, b)
+
+
+def test_filtered_frame_oracle_denoises_and_accumulates_history():
+    """Properties of the CPU counterpart of the filtering core (FrameOracle in filter mode + the restated SVGF / TAA chain with
+    the buffer rotation of FinalizeRender): over a stationary 1-spp sequence (new seeds every frame) the history counters climb
+    towards 15, and the presented frames change far less from frame to frame than the raw 1-spp frames they are made from -
+    the point of the stage - while keeping the image's energy."""
+    sd = scenes.config2_scene(24, 16, n_materials=1, light_quads=2, floaters=40)      # diffuse only: the a-trous passes act on every pixel
+    W, H = 112, 72
+    view = scenes.view_pyramid((0, 30, -80), (0, 0, 0), 40, W, H)
+    # The reference's neighbourhood clamps skip the taps of columns / rows 0 and 1 but still divide by 9 (`if (x > 1)`,
+    # finalize_shared.h:411-424,516-527: kept), which darkens the two border pixels; the three a-trous passes spread that up to
+    # 2 * (1 + 2 + 4) = 14 pixels inwards. Negligible at 4K, not on a test image: the properties are checked 16 pixels in.
+    inner = (slice(16, H - 16), slice(16, W - 16))
+    with orc.accel(1):
+        fo = orc.FilteredFrameOracle(sd, W, H, taa=True, threads=4)
+        raws, outs, hist = [], [], []
+        for k in range(7):
+            out = fo.render(view, 1)[..., :3]                      # Restart frames: 1 spp each, the history lives in the filter
+            assert np.isfinite(out).all()
+            raws.append(np.clip((fo.frame.accum[0] + fo.frame.accum[1])[..., :3][inner], 0, 2).copy())
+            outs.append(np.clip(out[inner], 0, 2).copy())
+            hist.append(float((fo.frame.features[..., 3] & 15).mean()))
+    assert hist[0] <= 1.0 and hist[-1] > 4.5 and all(b >= a for a, b in zip(hist, hist[1:])), hist
+    flicker = lambda seq: float(np.mean([np.sqrt(((a - b) ** 2).mean()) for a, b in zip(seq[3:], seq[4:])]))
+    assert flicker(outs) < 0.45 * flicker(raws), (flicker(outs), flicker(raws))       # measured 0.31 (0.68 with mirror-like materials in the scene)
+    assert abs(np.mean(outs[-1]) / np.mean(raws[-1]) - 1) < 0.05                      # energy is kept (clamps and the unsharp mask move it a little)
+    # the chain's stages are exposed for inspection; a stationary camera reprojects every pixel onto itself
+    assert set(fo.stages) >= {"shadingAfterPrepare", "motion", "moments", "phase1", "phase2", "phase3", "taaPixels", "target"}
+    # (motion = the sub-pixel position the primary ray went through, plus the reference's half-pixel offset: finalize_shared.h:286)
+    off = (fo.stages["motion"] - (np.stack(np.meshgrid(np.arange(W), np.arange(H)), -1) + 0.5))[inner]
+    assert off.min() > -0.01 and off.max() < 1.01
