@@ -121,7 +121,9 @@ LH2B_API int lh2b_finalize_external_on( lh2b_core* core, const void* dAccumulato
    of the whole frame. The tile gatherer (one per rank, created after lh2b_set_target and the filter setting) assigns the bands,
    defers the frame's tail and, per frame - lh2b_render( ..., async = 1 ) then lh2b_tile_frame( g ) on every rank - moves the
    peers' rows into rank 0's buffers over NVLink and runs the filter chain / finalize there. Handles are exchanged like the
-   gather's: lh2b_tile_handle_bytes() per rank, all-gathered in rank order. */
+   gather's: lh2b_tile_handle_bytes() per rank, all-gathered in rank order. While a tile gatherer is attached only rank 0 presents:
+   the peers' pixel buffers are not updated (their frames end after the last connect), and a probe pixel outside a rank's band is
+   not probed by that rank. */
 typedef struct lh2b_tile_gather lh2b_tile_gather;
 LH2B_API int lh2b_set_row_band( lh2b_core* core, int y0, int y1 );
 LH2B_API int lh2b_set_row_band_strided( lh2b_core* core, int y0, int y1, int stepTileRows );	/* tile rows y0/4 + j * step below row y1 */
