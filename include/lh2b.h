@@ -116,6 +116,12 @@ LH2B_API int lh2b_finalize_external( lh2b_core* core, const void* dAccumulator, 
 LH2B_API int lh2b_snapshot_accumulator( lh2b_core* core, void* dDst );
 LH2B_API int lh2b_finalize_external_on( lh2b_core* core, const void* dAccumulator, int samples, void* dPixelsOut, void* stream );
 
+/* ---- host builder introspection (needs no device) -------------------------------------------------------------------------
+   The CWBVH the host builder (Setting "bvhBuilder" 1) produces for one mesh: 80-byte nodes and 48-byte triangle records in the
+   layout documented in csrc/bvh.h, root = node 0, indices relative to the returned arrays. counts[0] / counts[1] receive the
+   node / triangle-record counts; returns 1 when maxNodes / maxTris are too small. */
+LH2B_API int lh2b_host_bvh_build( const float* verts4, int triCount, void* nodesOut, int maxNodes, void* trisOut, int maxTris, int* counts );
+
 /* ---- tile (row-band) sharding of one frame: strong scaling for real-time frames (csrc/tile_gather.cu) -----------
    lh2b_set_row_band: this core renders rows [y0, y1) only (y0 = y1 = 0: the whole frame), with the path indices, seeds and buffers
    of the whole frame. The tile gatherer (one per rank, created after lh2b_set_target and the filter setting) assigns the bands,

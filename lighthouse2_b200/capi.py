@@ -44,6 +44,7 @@ SIGNATURES = {
     "lh2b_accumulator_device_ptr": ([_vp, _c.POINTER(_vp), _c.POINTER(_ip)], _ip),
     "lh2b_finalize_external": ([_vp, _vp, _ip], _ip),
     "lh2b_snapshot_accumulator": ([_vp, _vp], _ip),
+    "lh2b_host_bvh_build": ([_vp, _ip, _vp, _ip, _vp, _ip, _c.POINTER(_ip)], _ip),
     "lh2b_set_row_band": ([_vp, _ip, _ip], _ip),
     "lh2b_set_row_band_strided": ([_vp, _ip, _ip, _ip], _ip),
     "lh2b_tile_handle_bytes": ([], _ip),

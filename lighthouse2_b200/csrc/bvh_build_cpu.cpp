@@ -320,3 +320,25 @@ void CollapseToCwBvh( const std::vector<Bvh2Node>& bvh2v, const std::vector<uint
 }
 
 } // namespace lh2b
+
+/* Device-free entry: the host builder's output for one mesh (binned-SAH binary tree -> 8-wide collapse -> CWBVH encoding), copied
+   out for inspection. tests/test_host_bvh_cpu.py decodes it from the layout documented in bvh.h and checks it on the CPU.
+   counts: [0] nodes, [1] triangle records. Returns 1 if the caller's arrays are too small (counts are still filled in). */
+#include "../../include/lh2b.h"
+extern "C" int lh2b_host_bvh_build( const float* verts4, int triCount, void* nodesOut, int maxNodes, void* trisOut, int maxTris, int* counts )
+{
+	try
+	{
+		std::vector<lh2b::Bvh2Node> bvh2;
+		std::vector<uint32_t> prim;
+		lh2b::BuildBvh2SAH( verts4, triCount, bvh2, prim );
+		lh2b::CwBvh cw;
+		lh2b::CollapseToCwBvh( bvh2, prim, verts4, cw );
+		counts[0] = (int)cw.nodes.size(), counts[1] = (int)cw.tris.size();
+		if (counts[0] > maxNodes || counts[1] > maxTris) return 1;
+		memcpy( nodesOut, cw.nodes.data(), cw.nodes.size() * sizeof( lh2b::CwNode ) );
+		memcpy( trisOut, cw.tris.data(), cw.tris.size() * sizeof( lh2b::CwTri ) );
+		return 0;
+	}
+	catch (...) { return 2; }
+}

@@ -404,6 +404,32 @@ def ref_filter_gpu(inputs, settings):
     return outs
 
 
+CWBVH_REPORT = ("nodesVisited", "trisVisited", "maxDepth", "emptySlots", "leafSlots", "innerSlots", "errors", "firstError")
+
+
+def cwbvh_check(nodes, tris, verts4):
+    """Structural check of a CWBVH in the product's documented format (lh2_oracle_cwbvh.h); returns the report as a dict."""
+    nodes = np.ascontiguousarray(nodes, np.uint8).reshape(-1, 80)
+    tris = np.ascontiguousarray(tris, np.float32).reshape(-1, 12)
+    v = np.ascontiguousarray(verts4, np.float32).reshape(-1, 4)
+    rep = (ctypes.c_int * 8)()
+    lib().orc_cwbvh_check(ctypes.c_void_p(nodes.ctypes.data), nodes.shape[0], ctypes.c_void_p(tris.ctypes.data), tris.shape[0],
+                          ctypes.c_void_p(v.ctypes.data), v.shape[0] // 3, rep)
+    return dict(zip(CWBVH_REPORT, [int(x) for x in rep]))
+
+
+def cwbvh_closest_hits(nodes, tris, O4, D4, threads=None):
+    """Closest hits through a CWBVH in the product's format, decoded and traversed by the oracle's own reader."""
+    nodes = np.ascontiguousarray(nodes, np.uint8).reshape(-1, 80)
+    tris = np.ascontiguousarray(tris, np.float32).reshape(-1, 12)
+    O4 = np.ascontiguousarray(O4, np.float32).reshape(-1, 4)
+    D4 = np.ascontiguousarray(D4, np.float32).reshape(-1, 4)
+    hits = np.empty((O4.shape[0], 4), np.uint32)
+    lib().orc_cwbvh_closest_hits(ctypes.c_void_p(nodes.ctypes.data), ctypes.c_void_p(tris.ctypes.data), ctypes.c_void_p(O4.ctypes.data),
+                                 ctypes.c_void_p(D4.ctypes.data), O4.shape[0], ctypes.c_void_p(hits.ctypes.data), threads or os.cpu_count())
+    return hits
+
+
 def filter_chain_cpu(inputs, settings):
     """The oracle's CPU restatement of the SVGF / TAA chain (lh2_oracle_filter.h) on the same inputs / settings dictionaries as
     ref_filter_gpu; returns the same dictionary of outputs."""

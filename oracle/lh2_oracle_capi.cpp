@@ -383,3 +383,24 @@ ORC_API int orc_filter_chain( const OrcFilterIO* io )
 	memcpy( io->target, target.data(), px * 16 );
 	return 0;
 }
+
+/* ---- independent reader of the product's CWBVH format (lh2_oracle_cwbvh.h) ------------------------------------------------ */
+#include "lh2_oracle_cwbvh.h"
+
+ORC_API void orc_cwbvh_check( const uint8_t* nodes, int nNodes, const float* tris, int nTris, const float* verts4, int triCount, int* report8 )
+{
+	const orcw::Report r = orcw::Check( nodes, nNodes, tris, nTris, verts4, triCount );
+	memcpy( report8, &r, sizeof( r ) );
+}
+
+ORC_API void orc_cwbvh_closest_hits( const uint8_t* nodes, const float* tris, const float* O4, const float* D4, int n, uint32_t* hits4, int threads )
+{
+	ParallelFor( n, threads, [&]( int a, int b ) {
+		for (int i = a; i < b; i++)
+		{
+			orc::Hit h;
+			const bool hit = orcw::ClosestHit( nodes, tris, O4 + i * 4, D4 + i * 4, h );
+			orc::PackHit( hit, h, hits4 + i * 4 );
+		}
+	} );
+}
