@@ -38,7 +38,13 @@ void InitRenderState( lh2b_core* core )
 	for (int i = 0; i < 128 * 128 * 8; i++) bn[i + 3 * 65536] = b[65536 + 131072 + i];
 	core->blueNoise.Upload( bn.data(), bn.size(), core->stream );
 	core->counters.Resize( 1 );
-	CUDA_CHECK( cudaMemsetAsync( core->counters.ptr, 0, sizeof( DevCounters ), core->stream ) );
+	{
+		DevCounters init;
+		memset( &init, 0, sizeof( init ) );
+		init.probedTriid = -1;	// nothing probed yet
+		CUDA_CHECK( cudaMemcpyAsync( core->counters.ptr, &init, sizeof( init ), cudaMemcpyHostToDevice, core->stream ) );
+		CUDA_CHECK( cudaStreamSynchronize( core->stream ) );
+	}
 	CUDA_CHECK( cudaMallocHost( &core->hostCounters, sizeof( DevCounters ) ) );
 	CUDA_CHECK( cudaMallocHost( &core->hostCountersB, sizeof( DevCounters ) ) );
 	memset( core->hostCounters, 0, sizeof( DevCounters ) ), memset( core->hostCountersB, 0, sizeof( DevCounters ) );
@@ -256,7 +262,7 @@ static void RenderFrame( lh2b_core* core, const lh2abi::ViewPyramid& view )
 				4 * rowBytes, BandTileRowsOf( core ), s ) );
 	}
 	if (core->filterEnabled) EnsureFilterBuffers( core );
-	CUDA_CHECK( cudaMemsetAsync( core->counters.ptr, 0, sizeof( DevCounters ), s ) );
+	CUDA_CHECK( cudaMemsetAsync( core->counters.ptr, 0, offsetof( DevCounters, probedInstid ), s ) );	// the probe words keep the last pick
 	RandomUInt( core->shiftSeed );
 	RenderParams p = BuildParams( core, view );
 	const bool useNEE = (core->lightCounts[0] + core->lightCounts[1] + core->lightCounts[2] + core->lightCounts[3]) > 0;
@@ -662,7 +668,7 @@ int lh2b_shade_paths( lh2b_core* core, int pathLength, int n, const float* O4, c
 	DevCounters hc;
 	memset( &hc, 0, sizeof( hc ) );
 	hc.extensionRays[pathLength - 1] = (uint32_t)n;
-	CUDA_CHECK( cudaMemcpyAsync( core->counters.ptr, &hc, sizeof( hc ), cudaMemcpyHostToDevice, s ) );
+	CUDA_CHECK( cudaMemcpyAsync( core->counters.ptr, &hc, offsetof( DevCounters, probedInstid ), cudaMemcpyHostToDevice, s ) );
 	lh2abi::ViewPyramid view = core->lastView;
 	RenderParams p = BuildParams( core, view );
 	p.stride = pathLength == 1 ? (uint32_t)n : stride;

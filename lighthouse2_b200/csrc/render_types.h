@@ -16,6 +16,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stddef.h>
 
 namespace lh2b
 {
@@ -33,10 +34,13 @@ struct DevCounters
 	uint32_t extensionRays[LH2B_MAXPATHLENGTH + 2];	// [L] = rays produced by shade at path length L
 	uint32_t shadowRays[LH2B_MAXPATHLENGTH + 2];		// [L] = shadow rays produced by shade at path length L
 	uint32_t workFetch[2 * LH2B_MAXPATHLENGTH + 8];	// dynamic work counters of the persistent kernels
+	// probe: written by one path per frame with a single 16-byte store (keep the four words together and 16-byte aligned); NOT cleared
+	// per frame - like the reference's counters (kernels/.cuda.cu:191-202 never touches them) a frame without a probe hit keeps the last one
 	int32_t probedInstid, probedTriid;
 	float probedDist;
 	uint32_t pad;
 };
+static_assert( offsetof( DevCounters, probedInstid ) % 16 == 0, "probe words must be 16-byte aligned" );
 
 struct PathSet { float4* O; float4* D; float4* T; };
 

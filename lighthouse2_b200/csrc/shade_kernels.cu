@@ -592,8 +592,11 @@ template <int BSDF, int MINB> __global__ void __launch_bounds__( 128, MINB ) sha
 			}
 			const float hitU = (__float_as_uint( hit.x ) & 65535) * (1.0f / 65535.0f), hitV = (__float_as_uint( hit.x ) >> 16) * (1.0f / 65535.0f);
 			const float hitT = hit.w;
-			if (pixelIdx == (uint32_t)p.probePixelIdx && pathLength == 1 && (!filter || sampleIdx == 0))
-				p.counters->probedInstid = instIdx, p.counters->probedTriid = prim, p.counters->probedDist = hitT;
+			// object picking (pathtracer.h:97-102; filter core pathtracer.h:130-133). The reference lets every sample of the probed pixel
+			// store the three words (a race at spp > 1): here exactly one path - the frame's first sample of that pixel -
+			// writes them, with one 16-byte store, so the triple is deterministic and cannot tear.
+			if (pathIdx == (uint32_t)p.probePixelIdx && pathLength == 1 && (!filter || sampleIdx == 0))
+				*(int4*)&p.counters->probedInstid = make_int4( instIdx, prim, __float_as_int( hitT ), 0 );
 			const InstDesc& inst = ((const InstDesc*)p.instDesc)[instIdx];
 			const float4* tri = inst.triangles + (size_t)prim * 13;
 			Shading sh;

@@ -641,7 +641,9 @@ static inline void ShadeStep( const RenderScene& sc, const Settings& st, int pat
 	}
 	const float hu = (float)(hit[0] & 65535) * (1.0f / 65535.0f), hv = (float)(hit[0] >> 16) * (1.0f / 65535.0f);
 	const float ht = BitsF( hit[3] );
-	if ((int)pixelIdx == probePixelIdx && pathLength == 1 && (!filter || sampleIdx == 0)) out.probe = true, out.probeInst = instIdx, out.probePrim = prim, out.probeDist = ht;
+	// picking: the reference lets every sample of the probed pixel write (pathtracer.h:97-102, a race at spp > 1); the defined outcome we
+	// restate is "the frame's first sample of that pixel" (pathIdx < w*h), which is what the CUDA core writes
+	if ((int)pathIdx == probePixelIdx && pathLength == 1 && (!filter || sampleIdx == 0)) out.probe = true, out.probeInst = instIdx, out.probePrim = prim, out.probeDist = ht;
 	const float* tri = sc.coreTris[sc.geo.instances[instIdx].mesh] + (size_t)prim * 52;
 	const float* invT = sc.geo.inverses + instIdx * 12;
 	Shading sh;
