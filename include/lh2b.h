@@ -41,12 +41,12 @@ LH2B_API int lh2b_set_target( lh2b_core* core, int width, int height, int spp );
                                     maxPathLength (1..LH2B_MAXPATHLENGTH, default 3 = MAXPATHLENGTH), maxDiffuseBounces (1 = ENOUGH_BOUNCES
                                     S_BOUNCED default, 2, 0 = unlimited), bsdf (0 lambert.h model, 1 principled model of disney.h)
      acceleration structure         bvhBuilder (0 GPU PLOC default, 1 host binned SAH, 2 GPU LBVH), bvhRefit (1 in-place refit default, 2 refit +
-                                    re-collapse, 0 rebuild), plocRadius (1..64, default 8), bvhMaxLeaf (1..3 triangles, default 1),
+                                    re-collapse, 0 rebuild), plocRadius (1..64, default 8),
                                     l2Persist (1 default: persisting-L2 window over the node arena)
      frame scheduling               pipeline (1: Render( async ) enqueues frame k+1 behind frame k; statistics lag one frame),
                                     gatherMode (read by lh2b_gather_create: 0 root gather default, 1 reduce-scatter),
                                     tileRootShare (read by lh2b_tile_create: rank 0's band relative to an equal share, 0..1)
-     kernel tuning (measurement)    traversalVariant, wideBlocksPerSM, triThreshold, triThresholdShadow, refillThreshold, shadeBlocks (4 / 5 / 6) */
+     kernel tuning (measurement)    wideBlocksPerSM, triThreshold, triThresholdShadow, refillThreshold, shadeBlocks (4 / 5 / 6) */
 LH2B_API int lh2b_setting( lh2b_core* core, const char* name, float value );
 /* CoreAPI_Base::SetProbePos (core_api_base.h:91, rendercore.cpp:85-88). */
 LH2B_API int lh2b_set_probe_pos( lh2b_core* core, int x, int y );
@@ -117,7 +117,7 @@ LH2B_API int lh2b_snapshot_accumulator( lh2b_core* core, void* dDst );
 LH2B_API int lh2b_finalize_external_on( lh2b_core* core, const void* dAccumulator, int samples, void* dPixelsOut, void* stream );
 
 /* ---- host builder introspection (needs no device) -------------------------------------------------------------------------
-   The CWBVH the host builder (Setting "bvhBuilder" 1) produces for one mesh: 80-byte nodes and 48-byte triangle records in the
+   The wide BVH the host builder (Setting "bvhBuilder" 1) produces for one mesh: 128-byte nodes and 48-byte triangle records in the
    layout documented in csrc/bvh.h, root = node 0, indices relative to the returned arrays. counts[0] / counts[1] receive the
    node / triangle-record counts; returns 1 when maxNodes / maxTris are too small. */
 LH2B_API int lh2b_host_bvh_build( const float* verts4, int triCount, void* nodesOut, int maxNodes, void* trisOut, int maxTris, int* counts );
@@ -175,6 +175,14 @@ LH2B_API int lh2b_trace_shadow_rays( lh2b_core* core, const float* origins, cons
    kernel time of 'repeat' back-to-back launches measured with CUDA events on that stream. */
 LH2B_API int lh2b_trace_rays_device( lh2b_core* core, const void* dOrigins, const void* dDirections, int n, void* dHitsOut, int repeat, float* msOut );
 LH2B_API int lh2b_trace_shadow_rays_device( lh2b_core* core, const void* dOrigins, const void* dDirections, int n, void* dOccludedOut, int repeat, float* msOut );
+/* Traversal work counters (measurement; the issue roofline of bench.py is computed from them): while enabled, every traversal
+   launch of this core - frame stages and ray queries - runs its counting instantiation (a few per cent slower) and adds to
+   nine 64-bit device counters. lh2b_trace_stats_read copies them out (and clears them when 'reset' is set):
+     [0] rays  [1] node steps  [2] triangle tests  [3] instance entries            (per ray)
+     [4] loop iterations  [5] node phases  [6] triangle phases                      (per warp)
+     [7] lanes active over all node phases  [8] lanes active over all triangle phases */
+LH2B_API int lh2b_trace_stats_enable( lh2b_core* core, int on );
+LH2B_API int lh2b_trace_stats_read( lh2b_core* core, unsigned long long* out9, int reset );
 /* The CUDA stream the core launches on (cudaStream_t as void*). */
 LH2B_API int lh2b_stream( lh2b_core* core, void** streamOut );
 /* Per-stage device times of the last Render in ms and ray counts; see lh2b_frame_stats below. */

@@ -71,6 +71,8 @@ SIGNATURES = {
     "lh2b_trace_shadow_rays": ([_vp, _vp, _vp, _ip, _vp], _ip),
     "lh2b_trace_rays_device": ([_vp, _vp, _vp, _ip, _vp, _ip, _fp], _ip),
     "lh2b_trace_shadow_rays_device": ([_vp, _vp, _vp, _ip, _vp, _ip, _fp], _ip),
+    "lh2b_trace_stats_enable": ([_vp, _ip], _ip),
+    "lh2b_trace_stats_read": ([_vp, _vp, _ip], _ip),
     "lh2b_stream": ([_vp, _c.POINTER(_vp)], _ip),
     "lh2b_get_frame_stats": ([_vp, _vp], _ip),
     "lh2b_get_bvh_stats": ([_vp, _ip, _vp], _ip),

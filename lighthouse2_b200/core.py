@@ -311,6 +311,17 @@ class RenderCore:
         self._check(self._lib.lh2b_get_frame_stats(self._h, _ptr(s)))
         return s[0]
 
+    TRACE_STATS = ("rays", "nodeSteps", "triTests", "instanceEntries", "iterations", "nodePhases", "triPhases", "nodeLanes", "triLanes")
+
+    def TraceStatsEnable(self, on=True):
+        """Work counters of the traversal kernels (measurement): counting instantiations run while enabled."""
+        self._check(self._lib.lh2b_trace_stats_enable(self._h, 1 if on else 0))
+
+    def TraceStatsRead(self, reset=True):
+        out = np.zeros(9, np.uint64)
+        self._check(self._lib.lh2b_trace_stats_read(self._h, _ptr(out), 1 if reset else 0))
+        return dict(zip(self.TRACE_STATS, (int(x) for x in out)))
+
     def GetBvhStats(self, mesh_idx=-1):
         s = np.zeros(1, dtype=abi.BvhStats)
         self._check(self._lib.lh2b_get_bvh_stats(self._h, mesh_idx, _ptr(s)))

@@ -1,5 +1,5 @@
-/* bvh_build_cpu.cpp - host-side BVH construction: binned-SAH binary build, greedy collapse
-   to 8-wide, CWBVH node encoding.
+/* bvh_build_cpu.cpp - host-side BVH construction: binned-SAH binary build (one primitive per leaf), greedy collapse
+   to 8-wide, node encoding (bvh.h).
 
    Replaces optixAccelBuild (reference call sites: lib/rendercore_optix7/core_mesh.cpp:105,123 for
    triangle meshes, lib/rendercore_optix7/rendercore.cpp:795 for the instance level). The GPU LBVH
@@ -36,7 +36,6 @@ struct BuildCtx
 	uint32_t* idx;
 	Bvh2Node* nodes;
 	std::atomic<int> nodePtr;
-	int maxLeaf;
 };
 
 static const int BINS = 16;
@@ -94,13 +93,6 @@ static void Subdivide( BuildCtx& c, const int nodeIdx, const int first, const in
 			if (cost < bestCost) bestCost = cost, bestAxis = a, bestSplit = b + 1;
 		}
 	}
-	const float nodeArea = HalfArea( lo, hi );
-	if (count <= c.maxLeaf)
-	{
-		// a leaf is legal: keep it unless the split is clearly cheaper (node visit ~ 0.5 tri tests in an 8-wide tree)
-		const float leafCost = nodeArea * count;
-		if (bestAxis < 0 || bestCost + 0.5f * nodeArea >= leafCost) { makeLeaf(); return; }
-	}
 	int mid;
 	if (bestAxis >= 0)
 	{
@@ -132,7 +124,7 @@ static void Subdivide( BuildCtx& c, const int nodeIdx, const int first, const in
 	}
 }
 
-void BuildBvh2FromBoxes( const Aabb* boxes, int count, int maxLeaf, std::vector<Bvh2Node>& nodes, std::vector<uint32_t>& primIdx )
+void BuildBvh2FromBoxes( const Aabb* boxes, int count, std::vector<Bvh2Node>& nodes, std::vector<uint32_t>& primIdx )
 {
 	nodes.assign( count > 0 ? 2 * count : 1, Bvh2Node{} );
 	primIdx.resize( count );
@@ -145,7 +137,7 @@ void BuildBvh2FromBoxes( const Aabb* boxes, int count, int maxLeaf, std::vector<
 		return;
 	}
 	BuildCtx c;
-	c.boxes = boxes, c.idx = primIdx.data(), c.nodes = nodes.data(), c.maxLeaf = maxLeaf;
+	c.boxes = boxes, c.idx = primIdx.data(), c.nodes = nodes.data();
 	c.cent.resize( (size_t)count * 3 );
 	for (int i = 0; i < count; i++)
 	{
@@ -167,7 +159,7 @@ void BuildBvh2SAH( const float* verts4, int triCount, std::vector<Bvh2Node>& nod
 			boxes[i].lo[a] = std::min( v[a], std::min( v[4 + a], v[8 + a] ) ),
 			boxes[i].hi[a] = std::max( v[a], std::max( v[4 + a], v[8 + a] ) );
 	}
-	BuildBvh2FromBoxes( boxes.data(), triCount, 3, nodes, primIdx );
+	BuildBvh2FromBoxes( boxes.data(), triCount, nodes, primIdx );
 }
 
 /* ---- collapse + encode ------------------------------------------------------------------ */
@@ -227,7 +219,7 @@ void CollapseToCwBvh( const std::vector<Bvh2Node>& bvh2v, const std::vector<uint
 		const Bvh2Node& root = bvh2[task.bvh2Node];
 		// gather up to 8 children by repeatedly opening the internal child with the largest area
 		int child[8], n = 0;
-		if (IsLeaf( root )) child[n++] = task.bvh2Node;
+		if (IsLeaf( root )) { if (root.right > 0) child[n++] = task.bvh2Node; }	// (an empty mesh is one node without children)
 		else
 		{
 			child[n++] = root.left, child[n++] = root.right;
@@ -250,71 +242,42 @@ void CollapseToCwBvh( const std::vector<Bvh2Node>& bvh2v, const std::vector<uint
 		int childInSlot[8];
 		for (int s = 0; s < 8; s++) childInSlot[s] = -1;
 		for (int i = 0; i < n; i++) childInSlot[slotOf[i]] = child[i];
-		// node header
-		uint8_t bytes[80] = {};
-		float p[3] = { root.lo[0], root.lo[1], root.lo[2] };
-		uint8_t e[3];
-		float quantum[3];
-		for (int a = 0; a < 3; a++)
+		// header + planes (bvh.h): one primitive per leaf slot, children of a kind are stored in slot order
+		CwNode node = {};
+		uint32_t imask = 0, lmask = 0;
+		for (int s = 0; s < 8; s++) if (childInSlot[s] >= 0)
 		{
-			const float ext = root.hi[a] - root.lo[a];
-			int ex = ext > 0 ? (int)ceilf( log2f( ext / 255.0f ) ) : -126;
-			ex = std::max( -126, std::min( 127, ex ) );
-			// make sure 255 quanta really cover the extent (log2f rounding)
-			while (ex < 127 && ldexpf( 255.0f, ex ) < ext) ex++;
-			e[a] = (uint8_t)(ex + 127), quantum[a] = ldexpf( 1.0f, ex );
+			if (linkedRoots || !IsLeaf( bvh2[childInSlot[s]] )) imask |= 1u << s; else lmask |= 1u << s;
 		}
-		memcpy( bytes, p, 12 );
-		bytes[12] = e[0], bytes[13] = e[1], bytes[14] = e[2];
-		uint8_t imask = 0;
-		int internalCount = 0, triCount = 0;
-		for (int s = 0; s < 8; s++) if (childInSlot[s] >= 0 && (linkedRoots || !IsLeaf( bvh2[childInSlot[s]] ))) imask |= 1 << s, internalCount++;
-		bytes[15] = imask;
+		int internalCount = 0;
+		for (int s = 0; s < 8; s++) internalCount += (imask >> s) & 1;
 		const uint32_t childBase = (uint32_t)out.nodes.size();
 		const uint32_t triBase = (uint32_t)(verts4 ? out.tris.size() : out.leafIds.size());
-		const uint32_t childBaseAbs = childBase + nodeOffset, triBaseAbs = triBase + triOffset;
-		memcpy( bytes + 16, &childBaseAbs, 4 ), memcpy( bytes + 20, &triBaseAbs, 4 );
+		node.w[3] = imask | (lmask << 8), node.w[4] = childBase + nodeOffset, node.w[5] = triBase + triOffset;
+		float clo[8][3] = {}, chi[8][3] = {};
 		int nextInternal = 0;
 		for (int s = 0; s < 8; s++)
 		{
 			const int ci = childInSlot[s];
-			if (ci < 0) continue; // meta 0, boxes 0
+			if (ci < 0) continue;
 			const Bvh2Node& c = bvh2[ci];
+			memcpy( clo[s], c.lo, 12 ), memcpy( chi[s], c.hi, 12 );
 			if (IsLeaf( c ) && linkedRoots)
 			{
 				// flat scene: the instance's BLAS root is copied in as an internal child
-				bytes[24 + s] = (uint8_t)((1 << 5) | (24 + s));
 				links.push_back( { (int)childBase + nextInternal, primIdx[~c.left] } );
 				nextInternal++;
 			}
-			else if (IsLeaf( c ))
-			{
-				const int first = ~c.left, count = c.right;
-				// count is 1..3 by construction; unary encode
-				bytes[24 + s] = (uint8_t)((((1 << count) - 1) << 5) | triCount);
-				for (int k = 0; k < count; k++) emitLeafPrim( primIdx[first + k] );
-				triCount += count;
-			}
+			else if (IsLeaf( c )) emitLeafPrim( primIdx[~c.left] );	// exactly one primitive (BuildBvh2FromBoxes)
 			else
 			{
-				bytes[24 + s] = (uint8_t)((1 << 5) | (24 + s));
 				queue.push_back( { ci, (int)childBase + nextInternal } );
 				nextInternal++;
 			}
-			for (int a = 0; a < 3; a++)
-			{
-				// conservative quantisation: floor for lo, ceil for hi, checked against float rounding of p + q * 2^e
-				int qlo = (int)floorf( (c.lo[a] - p[a]) / quantum[a] );
-				int qhi = (int)ceilf( (c.hi[a] - p[a]) / quantum[a] );
-				qlo = std::max( 0, std::min( 255, qlo ) ), qhi = std::max( 0, std::min( 255, qhi ) );
-				while (qlo > 0 && p[a] + qlo * quantum[a] > c.lo[a]) qlo--;
-				while (qhi < 255 && p[a] + qhi * quantum[a] < c.hi[a]) qhi++;
-				bytes[32 + a * 8 + s] = (uint8_t)qlo;
-				bytes[56 + a * 8 + s] = (uint8_t)qhi;
-			}
 		}
+		CwEncodePlanes( node.w, root.lo, root.hi, clo, chi, imask | lmask );
 		for (int k = 0; k < internalCount; k++) out.nodes.push_back( CwNode{} );
-		memcpy( &out.nodes[task.cwNode], bytes, 80 );
+		out.nodes[task.cwNode] = node;
 	}
 	for (const Link& l : links) out.nodes[l.cwNode] = linkedRoots[l.prim];
 }

@@ -1,5 +1,5 @@
 /* bvh_gpu.cu - GPU construction of the acceleration structures: Morton-code LBVH (Karras 2012) -> bottom-up bounds ->
-   greedy collapse to 8-wide -> CWBVH encoding, all on the core's stream without host round trips. Also the "refit"
+   greedy collapse to 8-wide -> node encoding (bvh.h), all on the core's stream without host round trips. Also the "refit"
    path (same topology, new bounds, re-collapse) and the per-frame top level over instance boxes.
 
    Replaces the closed OptiX builders: optixAccelBuild on triangles (lib/rendercore_optix7/core_mesh.cpp:67-129, always
@@ -12,7 +12,7 @@
      4. radixTreeKernel ...... Karras' binary radix tree over the sorted codes (ties broken by index)
      5. fitKernel ............ leaf boxes, then parents bottom-up (second arrival continues)            = refit
      6. collapseKernel ....... persistent cooperative kernel, one BFS level per grid.sync(): each task turns one binary
-                               subtree root into one 80-byte CWBVH node (<= 8 children, octant slots, quantised boxes),
+                               subtree root into one 128-byte wide node (<= 8 children, octant slots, bfloat16 child planes),
                                emits leaf triangles in Moeller-Trumbore form and queues the internal children.
    Encoding rules are identical to the host builder (bvh_build_cpu.cpp); both are checked against the brute-force oracle.
 */
@@ -221,7 +221,7 @@ __global__ void resetVisitKernel( uint32_t* visit, const int n )
 /* stage 6 */
 struct CollapseArgs
 {
-	int n, maxLeaf;
+	int n;
 	const int2* children; const uint32_t* subtree; const float4* nodeLo; const float4* nodeHi; const uint32_t* idx;
 	const float4* verts;			// BLAS: triangle vertices; null for the TLAS
 	uint4* outNodes;				// arena base
@@ -244,11 +244,7 @@ __device__ __forceinline__ float HalfAreaD( const float4 lo, const float4 hi )
 __device__ void CollapseTask( const CollapseArgs& a, const BuildTask task )
 {
 	const int n = a.n;
-	auto leafLike = [&]( const int node ) -> bool {
-		if (node >= n - 1) return true;
-		if (a.linkedRootOf) return false;
-		return a.subtree[node] <= (uint32_t)a.maxLeaf;
-	};
+	auto leafLike = [&]( const int node ) -> bool { return node >= n - 1; };	// binary leaves hold one primitive: one leaf slot each
 	int child[8], cnt = 0;
 	const int root = task.bvh2Node;
 	if (leafLike( root )) child[cnt++] = root;
@@ -300,15 +296,13 @@ __device__ void CollapseTask( const CollapseArgs& a, const BuildTask task )
 		a.wideSelf[task.cwNode] = root;
 		for (int s = 0; s < 8; s++) a.wideChild[(size_t)task.cwNode * 8 + s] = slotChild[s];
 	}
-	// counts and allocation
+	// counts and allocation: internal children and leaf primitives are stored in slot order
 	int internalCount = 0, leafPrims = 0;
-	uint32_t imask = 0;
+	uint32_t imask = 0, lmask = 0;
 	for (int s = 0; s < 8; s++) if (slotChild[s] >= 0)
 	{
-		const int c = slotChild[s];
-		const bool isLeaf = leafLike( c ) && !a.linkedRootOf;
-		if (!isLeaf) imask |= 1u << s, internalCount++;
-		else leafPrims += c >= n - 1 ? 1 : (int)a.subtree[c];
+		const bool isLeaf = leafLike( slotChild[s] ) && !a.linkedRootOf;
+		if (!isLeaf) imask |= 1u << s, internalCount++; else lmask |= 1u << s, leafPrims++;
 	}
 	const uint32_t childBase = internalCount ? atomicAdd( a.ctrl + 0, (uint32_t)internalCount ) : 0;
 	const uint32_t leafBase = leafPrims ? atomicAdd( a.ctrl + 1, (uint32_t)leafPrims ) : 0;
@@ -316,89 +310,52 @@ __device__ void CollapseTask( const CollapseArgs& a, const BuildTask task )
 	uint32_t queueBase = 0;
 	{
 		int realInternal = 0;
-		for (int s = 0; s < 8; s++) if (slotChild[s] >= 0 && (imask >> s & 1) && !(a.linkedRootOf && slotChild[s] >= n - 1)) realInternal++;
+		for (int s = 0; s < 8; s++) if ((imask >> s & 1) && !(a.linkedRootOf && slotChild[s] >= n - 1)) realInternal++;
 		if (realInternal) queueBase = atomicAdd( a.ctrl + 2, (uint32_t)realInternal );
 	}
-	// header
-	float quantum[3];
-	uint32_t e[3];
-	const float ext[3] = { rhi.x - rlo.x, rhi.y - rlo.y, rhi.z - rlo.z };
-	for (int k = 0; k < 3; k++)
-	{
-		int ex = ext[k] > 0 ? (int)ceilf( log2f( ext[k] / 255.0f ) ) : -126;
-		ex = max( -126, min( 127, ex ) );
-		while (ex < 127 && ldexpf( 255.0f, ex ) < ext[k]) ex++;
-		e[k] = (uint32_t)(ex + 127), quantum[k] = ldexpf( 1.0f, ex );
-	}
-	uint32_t meta[8], qlo[3][8], qhi[3][8];
-	for (int s = 0; s < 8; s++) { meta[s] = 0; for (int k = 0; k < 3; k++) qlo[k][s] = qhi[k][s] = 0; }
+	float clo[8][3], chi[8][3];
 	int nextInternal = 0, nextQueued = 0, triCursor = 0;
-	const float p[3] = { rlo.x, rlo.y, rlo.z };
 	for (int s = 0; s < 8; s++)
 	{
 		const int c = slotChild[s];
 		if (c < 0) continue;
-		const float4 clo = a.nodeLo[c], chi = a.nodeHi[c];
+		const float4 l4 = a.nodeLo[c], h4 = a.nodeHi[c];
+		clo[s][0] = l4.x, clo[s][1] = l4.y, clo[s][2] = l4.z, chi[s][0] = h4.x, chi[s][1] = h4.y, chi[s][2] = h4.z;
 		if (imask >> s & 1)
 		{
-			meta[s] = (1u << 5) | (24u + s);
 			const uint32_t dst = childBase + nextInternal;
 			if (a.linkedRootOf && c >= n - 1)
 			{
 				// flat scene: copy the BLAS root of this instance in as the child node
 				const uint32_t inst = a.idx[c - (n - 1)];
-				const uint4* src = a.outNodes + (size_t)a.linkedRootOf[inst] * 5;
-				uint4* d = a.outNodes + (size_t)(a.nodeOffset + dst) * 5;
-				for (int k = 0; k < 5; k++) d[k] = src[k];
+				const uint4* src = a.outNodes + (size_t)a.linkedRootOf[inst] * CW_NODE_QUADS;
+				uint4* d = a.outNodes + (size_t)(a.nodeOffset + dst) * CW_NODE_QUADS;
+				for (int k = 0; k < CW_NODE_QUADS; k++) d[k] = src[k];
 			}
 			else a.queue[queueBase + nextQueued++] = BuildTask{ c, dst };
 			nextInternal++;
 		}
 		else
 		{
-			// the (at most maxLeaf) primitives below this child: tiny depth-first walk
-			int leafPos[4], count = 0, walk[4], wsp = 0;
-			walk[wsp++] = c;
-			while (wsp > 0)
+			const uint32_t prim = a.idx[c - (n - 1)];
+			const uint32_t at = leafBase + triCursor++;
+			if (a.verts)
 			{
-				const int nd = walk[--wsp];
-				if (nd >= n - 1) leafPos[count++] = nd - (n - 1);
-				else { const int2 cc = a.children[nd]; walk[wsp++] = cc.y, walk[wsp++] = cc.x; }
+				const float4 v0 = a.verts[prim * 3], v1 = a.verts[prim * 3 + 1], v2 = a.verts[prim * 3 + 2];
+				float4* t = a.outTris + (size_t)(a.triOffset + at) * 3;
+				t[0] = make_float4( v0.x, v0.y, v0.z, __uint_as_float( prim ) );
+				t[1] = make_float4( v1.x - v0.x, v1.y - v0.y, v1.z - v0.z, __uint_as_float( 0u ) );
+				t[2] = make_float4( v2.x - v0.x, v2.y - v0.y, v2.z - v0.z, 0 );
 			}
-			meta[s] = (((1u << count) - 1) << 5) | (uint32_t)triCursor;
-			for (int k = 0; k < count; k++)
-			{
-				const uint32_t prim = a.idx[leafPos[k]];
-				const uint32_t at = leafBase + triCursor + k;
-				if (a.verts)
-				{
-					const float4 v0 = a.verts[prim * 3], v1 = a.verts[prim * 3 + 1], v2 = a.verts[prim * 3 + 2];
-					float4* t = a.outTris + (size_t)(a.triOffset + at) * 3;
-					t[0] = make_float4( v0.x, v0.y, v0.z, __uint_as_float( prim ) );
-					t[1] = make_float4( v1.x - v0.x, v1.y - v0.y, v1.z - v0.z, __uint_as_float( 0u ) );
-					t[2] = make_float4( v2.x - v0.x, v2.y - v0.y, v2.z - v0.z, 0 );
-				}
-				else a.outLeafIds[at] = prim;
-			}
-			triCursor += count;
-		}
-		const float cl[3] = { clo.x, clo.y, clo.z }, ch[3] = { chi.x, chi.y, chi.z };
-		for (int k = 0; k < 3; k++)
-		{
-			int ql = (int)floorf( (cl[k] - p[k]) / quantum[k] ), qh = (int)ceilf( (ch[k] - p[k]) / quantum[k] );
-			ql = max( 0, min( 255, ql ) ), qh = max( 0, min( 255, qh ) );
-			while (ql > 0 && p[k] + ql * quantum[k] > cl[k]) ql--;
-			while (qh < 255 && p[k] + qh * quantum[k] < ch[k]) qh++;
-			qlo[k][s] = (uint32_t)ql, qhi[k][s] = (uint32_t)qh;
+			else a.outLeafIds[at] = prim;
 		}
 	}
-	auto pack4 = []( const uint32_t* b ) { return b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24); };
-	uint4* out = a.outNodes + (size_t)(a.nodeOffset + task.cwNode) * 5;
-	out[0] = make_uint4( __float_as_uint( p[0] ), __float_as_uint( p[1] ), __float_as_uint( p[2] ), e[0] | (e[1] << 8) | (e[2] << 16) | (imask << 24) );
-	out[1] = make_uint4( a.nodeOffset + childBase, a.triOffset + leafBase, pack4( meta ), pack4( meta + 4 ) );
-	out[2] = make_uint4( pack4( qlo[0] ), pack4( qlo[0] + 4 ), pack4( qlo[1] ), pack4( qlo[1] + 4 ) );
-	out[3] = make_uint4( pack4( qlo[2] ), pack4( qlo[2] + 4 ), pack4( qhi[0] ), pack4( qhi[0] + 4 ) );
-	out[4] = make_uint4( pack4( qhi[1] ), pack4( qhi[1] + 4 ), pack4( qhi[2] ), pack4( qhi[2] + 4 ) );
+	uint32_t w[CW_NODE_WORDS];
+	const float nlo[3] = { rlo.x, rlo.y, rlo.z }, nhi[3] = { rhi.x, rhi.y, rhi.z };
+	CwEncodePlanes( w, nlo, nhi, clo, chi, imask | lmask );
+	w[3] = imask | (lmask << 8), w[4] = a.nodeOffset + childBase, w[5] = a.triOffset + leafBase, w[6] = w[7] = 0;
+	uint4* out = a.outNodes + (size_t)(a.nodeOffset + task.cwNode) * CW_NODE_QUADS;
+	for (int k = 0; k < CW_NODE_QUADS; k++) out[k] = make_uint4( w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3] );
 }
 
 __global__ void __launch_bounds__( 128 ) collapseKernel( const CollapseArgs a )
@@ -437,38 +394,23 @@ __global__ void __launch_bounds__( 128 ) requantKernel( const int nodeCount, con
 	const int self = wideSelf[i];
 	const float4 rlo = nodeLo[self], rhi = nodeHi[self];
 	if (i == 0 && boundsOut) boundsOut[0] = rlo, boundsOut[1] = rhi;
-	float quantum[3];
-	uint32_t e[3];
-	const float ext[3] = { rhi.x - rlo.x, rhi.y - rlo.y, rhi.z - rlo.z }, p[3] = { rlo.x, rlo.y, rlo.z };
-	for (int k = 0; k < 3; k++)
-	{
-		int ex = ext[k] > 0 ? (int)ceilf( log2f( ext[k] / 255.0f ) ) : -126;
-		ex = max( -126, min( 127, ex ) );
-		while (ex < 127 && ldexpf( 255.0f, ex ) < ext[k]) ex++;
-		e[k] = (uint32_t)(ex + 127), quantum[k] = ldexpf( 1.0f, ex );
-	}
-	uint32_t q[6][2] = { { 0, 0 }, { 0, 0 }, { 0, 0 }, { 0, 0 }, { 0, 0 }, { 0, 0 } };	// [lo x,y,z, hi x,y,z][slots 0-3, 4-7]
+	float clo[8][3], chi[8][3];
+	uint32_t valid = 0;
 	for (int s = 0; s < 8; s++)
 	{
 		const int c = wideChild[(size_t)i * 8 + s];
 		if (c < 0) continue;
-		const float4 clo = nodeLo[c], chi = nodeHi[c];
-		const float cl[3] = { clo.x, clo.y, clo.z }, ch[3] = { chi.x, chi.y, chi.z };
-		for (int k = 0; k < 3; k++)
-		{
-			int ql = (int)floorf( (cl[k] - p[k]) / quantum[k] ), qh = (int)ceilf( (ch[k] - p[k]) / quantum[k] );
-			ql = max( 0, min( 255, ql ) ), qh = max( 0, min( 255, qh ) );
-			while (ql > 0 && p[k] + ql * quantum[k] > cl[k]) ql--;
-			while (qh < 255 && p[k] + qh * quantum[k] < ch[k]) qh++;
-			q[k][s >> 2] |= (uint32_t)ql << (8 * (s & 3)), q[3 + k][s >> 2] |= (uint32_t)qh << (8 * (s & 3));
-		}
+		const float4 l4 = nodeLo[c], h4 = nodeHi[c];
+		clo[s][0] = l4.x, clo[s][1] = l4.y, clo[s][2] = l4.z, chi[s][0] = h4.x, chi[s][1] = h4.y, chi[s][2] = h4.z;
+		valid |= 1u << s;
 	}
-	uint4* out = outNodes + (size_t)i * 5;
-	const uint32_t imask = out[0].w >> 24;
-	out[0] = make_uint4( __float_as_uint( p[0] ), __float_as_uint( p[1] ), __float_as_uint( p[2] ), e[0] | (e[1] << 8) | (e[2] << 16) | (imask << 24) );
-	out[2] = make_uint4( q[0][0], q[0][1], q[1][0], q[1][1] );
-	out[3] = make_uint4( q[2][0], q[2][1], q[3][0], q[3][1] );
-	out[4] = make_uint4( q[4][0], q[4][1], q[5][0], q[5][1] );
+	uint4* out = outNodes + (size_t)i * CW_NODE_QUADS;
+	uint32_t w[CW_NODE_WORDS];
+	const float nlo[3] = { rlo.x, rlo.y, rlo.z }, nhi[3] = { rhi.x, rhi.y, rhi.z };
+	CwEncodePlanes( w, nlo, nhi, clo, chi, valid );
+	const uint4 keep = out[0];	// slot masks stay; childBase / triBase (out[1]) are not touched
+	out[0] = make_uint4( w[0], w[1], w[2], keep.w );
+	for (int k = 2; k < CW_NODE_QUADS; k++) out[k] = make_uint4( w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3] );
 }
 
 __global__ void triRewriteKernel( const int n, const float4* __restrict__ verts, float4* __restrict__ outTris )
@@ -668,7 +610,7 @@ static void BuildFromBoxes( lh2b_core* core, GpuBuildScratch& s, const int n, co
 	if (keepWideTree)
 	{
 		requantKernel<<<(wideNodes + 127) / 128, 128, 0, st>>>( wideNodes, args.wideChild, args.wideSelf, s.nodeLo.ptr, s.nodeHi.ptr,
-			args.outNodes + (size_t)args.nodeOffset * 5, args.boundsOut );
+			args.outNodes + (size_t)args.nodeOffset * CW_NODE_QUADS, args.boundsOut );
 		triRewriteKernel<<<blocks, 256, 0, st>>>( n, args.verts, args.outTris + (size_t)args.triOffset * 3 );
 		return;
 	}
@@ -716,7 +658,7 @@ void GpuBuildMesh( lh2b_core* core, Mesh& mesh, const int refit )
 	if (n == 0)
 	{
 		// empty mesh: one node without children, zero box
-		CUDA_CHECK( cudaMemsetAsync( core->arenaNodes.ptr + (size_t)mesh.nodeOff * 5, 0, 80, st ) );
+		CUDA_CHECK( cudaMemsetAsync( core->arenaNodes.ptr + (size_t)mesh.nodeOff * CW_NODE_QUADS, 0, sizeof( CwNode ), st ) );
 		CUDA_CHECK( cudaMemsetAsync( mesh.devBounds.ptr, 0, 32, st ) );
 		CUDA_CHECK( cudaMemsetAsync( mesh.devCounts.ptr, 0, 16, st ) );
 		return;
@@ -727,7 +669,7 @@ void GpuBuildMesh( lh2b_core* core, Mesh& mesh, const int refit )
 	s.idxAlt.Swap( mesh.topoIdx ), s.children.Swap( mesh.topoChildren ), s.subtree.Swap( mesh.topoSubtree );
 	s.parent.Swap( mesh.topoParent ), s.visit.Swap( mesh.topoVisit );
 	CollapseArgs a = {};
-	a.maxLeaf = core->bvhMaxLeaf, a.verts = mesh.verts.ptr, a.outNodes = core->arenaNodes.ptr, a.outTris = core->arenaTris.ptr;
+	a.verts = mesh.verts.ptr, a.outNodes = core->arenaNodes.ptr, a.outTris = core->arenaTris.ptr;
 	a.nodeOffset = mesh.nodeOff, a.triOffset = mesh.triOff, a.nodeCapacity = mesh.nodeCap, a.triCapacity = mesh.triCap;
 	a.boundsOut = mesh.devBounds.ptr, a.countsOut = mesh.devCounts.ptr;
 	if (mesh.topoWideSelf.count < mesh.nodeCap) mesh.topoWideSelf.Resize( mesh.nodeCap ), mesh.topoWideChild.Resize( (size_t)mesh.nodeCap * 8 );
@@ -749,7 +691,7 @@ void GpuBuildTlas( lh2b_core* core, const void* dInstIn, const int n, const uint
 	s.primLo.Resize( n ), s.primHi.Resize( n );
 	instBoundsKernel<<<(n + 127) / 128, 128, 0, st>>>( (const InstBuildIn*)dInstIn, n, s.primLo.ptr, s.primHi.ptr, s.ctrl.ptr );
 	CollapseArgs a = {};
-	a.maxLeaf = 1, a.verts = nullptr, a.outNodes = core->arenaNodes.ptr, a.outLeafIds = core->tlasLeafIds.ptr, a.linkedRootOf = dLinkedRoots;
+	a.verts = nullptr, a.outNodes = core->arenaNodes.ptr, a.outLeafIds = core->tlasLeafIds.ptr, a.linkedRootOf = dLinkedRoots;
 	a.nodeOffset = core->tlasOff, a.triOffset = 0, a.nodeCapacity = core->tlasCap, a.triCapacity = (uint32_t)core->tlasLeafIds.capacity;
 	BuildFromBoxes( core, s, n, true, false, a );
 }

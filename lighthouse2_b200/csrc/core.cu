@@ -71,7 +71,7 @@ static uint32_t ArenaAllocNodes( lh2b_core* core, uint32_t cap )
 {
 	const uint32_t off = core->arenaNodeTop;
 	core->arenaNodeTop += cap;
-	GrowArena( core, core->arenaNodes, (size_t)core->arenaNodeTop * 5 );
+	GrowArena( core, core->arenaNodes, (size_t)core->arenaNodeTop * CW_NODE_QUADS );
 	return off;
 }
 
@@ -94,6 +94,13 @@ static void EnsureMeshSlots( lh2b_core* core, Mesh& mesh, uint32_t nodesNeeded, 
 static void RebuildMeshHost( lh2b_core* core, Mesh& mesh )
 {
 	const double t0 = NowMs();
+	if (mesh.hostVerts.size() != (size_t)mesh.triCount * 12)
+	{
+		// the mesh was uploaded while another builder was selected: fetch the positions back
+		mesh.hostVerts.resize( (size_t)mesh.triCount * 12 );
+		if (mesh.triCount > 0) CUDA_CHECK( cudaMemcpyAsync( mesh.hostVerts.data(), mesh.verts.ptr, (size_t)mesh.triCount * 48, cudaMemcpyDeviceToHost, core->stream ) );
+		CUDA_CHECK( cudaStreamSynchronize( core->stream ) );
+	}
 	std::vector<Bvh2Node> bvh2;
 	std::vector<uint32_t> primIdx;
 	BuildBvh2SAH( mesh.hostVerts.data(), mesh.triCount, bvh2, primIdx );
@@ -104,7 +111,7 @@ static void RebuildMeshHost( lh2b_core* core, Mesh& mesh )
 	if (probe.tris.empty()) probe.tris.push_back( CwTri{} );
 	mesh.nodeCount = (uint32_t)probe.nodes.size(), mesh.taggedInst = 0, mesh.hasTopology = false;
 	const float4 b[2] = { make_float4( probe.bounds.lo[0], probe.bounds.lo[1], probe.bounds.lo[2], 0 ), make_float4( probe.bounds.hi[0], probe.bounds.hi[1], probe.bounds.hi[2], 0 ) };
-	CUDA_CHECK( cudaMemcpyAsync( core->arenaNodes.ptr + (size_t)mesh.nodeOff * 5, probe.nodes.data(), probe.nodes.size() * sizeof( CwNode ), cudaMemcpyHostToDevice, core->stream ) );
+	CUDA_CHECK( cudaMemcpyAsync( core->arenaNodes.ptr + (size_t)mesh.nodeOff * CW_NODE_QUADS, probe.nodes.data(), probe.nodes.size() * sizeof( CwNode ), cudaMemcpyHostToDevice, core->stream ) );
 	CUDA_CHECK( cudaMemcpyAsync( core->arenaTris.ptr + (size_t)mesh.triOff * 3, probe.tris.data(), probe.tris.size() * sizeof( CwTri ), cudaMemcpyHostToDevice, core->stream ) );
 	CUDA_CHECK( cudaMemcpyAsync( mesh.devBounds.ptr, b, sizeof( b ), cudaMemcpyHostToDevice, core->stream ) );
 	CUDA_CHECK( cudaStreamSynchronize( core->stream ) );
@@ -230,7 +237,7 @@ void UpdateAccelerationStructures( lh2b_core* core )
 	core->instDesc.Upload( desc.data(), desc.size(), core->stream );
 	core->instBuildIn.Upload( (const uint8_t*)buildIn.data(), buildIn.size() * sizeof( InstBuildHost ), core->stream );
 	core->linkedRoots.Upload( linked.data(), linked.size(), core->stream );
-	if (n == 0) CUDA_CHECK( cudaMemsetAsync( core->arenaNodes.ptr + (size_t)core->tlasOff * 5, 0, 80, core->stream ) );
+	if (n == 0) CUDA_CHECK( cudaMemsetAsync( core->arenaNodes.ptr + (size_t)core->tlasOff * CW_NODE_QUADS, 0, sizeof( CwNode ), core->stream ) );
 	else GpuBuildTlas( core, core->instBuildIn.ptr, n, flat ? core->linkedRoots.ptr : nullptr );
 	CUDA_CHECK( cudaEventRecord( core->evB, core->stream ) );
 	CUDA_CHECK( cudaStreamSynchronize( core->stream ) );	// the host vectors above were the copy sources
@@ -245,6 +252,7 @@ void UpdateAccelerationStructures( lh2b_core* core )
 	core->scene.instances = core->instTrav.ptr;
 	core->scene.instanceCount = n;
 	core->scene.singleIdentity = flat ? 1 : 0;
+	core->scene.stats = core->traceStatsOn ? (TraceStats*)core->traceStats.ptr : nullptr;
 	ApplyL2Policy( core );
 }
 
@@ -553,6 +561,30 @@ int lh2b_trace_shadow_rays( lh2b_core* core, const float* origins, const float* 
 	API_END
 }
 
+int lh2b_trace_stats_enable( lh2b_core* core, int on )
+{
+	API_BEGIN
+	CUDA_CHECK( cudaStreamSynchronize( core->stream ) );
+	if (on && core->traceStats.count == 0)
+	{
+		core->traceStats.Resize( 16 );
+		CUDA_CHECK( cudaMemsetAsync( core->traceStats.ptr, 0, 16 * sizeof( unsigned long long ), core->stream ) );
+	}
+	core->traceStatsOn = on != 0;
+	core->scene.stats = core->traceStatsOn ? (TraceStats*)core->traceStats.ptr : nullptr;
+	API_END
+}
+
+int lh2b_trace_stats_read( lh2b_core* core, unsigned long long* out9, int reset )
+{
+	API_BEGIN
+	if (core->traceStats.count == 0) throw CoreError( "trace_stats_read: counters were never enabled" );
+	CUDA_CHECK( cudaMemcpyAsync( out9, core->traceStats.ptr, 9 * sizeof( unsigned long long ), cudaMemcpyDeviceToHost, core->stream ) );
+	if (reset) CUDA_CHECK( cudaMemsetAsync( core->traceStats.ptr, 0, 16 * sizeof( unsigned long long ), core->stream ) );
+	CUDA_CHECK( cudaStreamSynchronize( core->stream ) );
+	API_END
+}
+
 int lh2b_get_bvh_stats( lh2b_core* core, int meshIdx, lh2b_bvh_stats* out )
 {
 	API_BEGIN
@@ -560,7 +592,7 @@ int lh2b_get_bvh_stats( lh2b_core* core, int meshIdx, lh2b_bvh_stats* out )
 	if (meshIdx == -1)
 	{
 		out->nodes = (uint32_t)core->instances.size() + 1, out->triangles = (uint32_t)core->instances.size();
-		out->bytes = (uint32_t)(core->tlasCap * 80 + core->tlasLeafIds.Bytes() + core->instTrav.Bytes());
+		out->bytes = (uint32_t)(core->tlasCap * sizeof( CwNode ) + core->tlasLeafIds.Bytes() + core->instTrav.Bytes());
 		out->buildMs = core->tlasBuildMs;
 	}
 	else
@@ -574,7 +606,7 @@ int lh2b_get_bvh_stats( lh2b_core* core, int meshIdx, lh2b_bvh_stats* out )
 			m.timingPending = false;
 		}
 		out->nodes = m.nodeCount, out->triangles = m.triCount;
-		out->bytes = (uint32_t)(m.nodeCount * 80 + (size_t)m.triCount * 48);
+		out->bytes = (uint32_t)(m.nodeCount * sizeof( CwNode ) + (size_t)m.triCount * 48);
 		out->buildMs = m.buildMs, out->sahCost = m.sahCost;
 	}
 	API_END

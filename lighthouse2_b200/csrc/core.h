@@ -84,10 +84,12 @@ struct lh2b_core
 	lh2b::DevBuf<float4> qO, qD, qHits;
 	lh2b::DevBuf<uint8_t> qOcc;
 	lh2b::DevBuf<uint32_t> queryCounter;
+	lh2b::DevBuf<unsigned long long> traceStats;	// 9 counters (TraceStats, traverse_wide.cuh); scene.stats points here while enabled
+	bool traceStatsOn = false;
 	void* gpuBuild = nullptr;				// GpuBuildScratch (bvh_gpu.cu)
 	lh2b::DevBuf<uint8_t> instBuildIn;		// per-frame top-level build input
 	lh2b::DevBuf<uint32_t> linkedRoots;
-	int plocRadius = 8, bvhMaxLeaf = 1;	// swept on the 1M-triangle terrain (tools/quality_sweep.py)
+	int plocRadius = 8;	// swept on the 1M-triangle terrain (tools/quality_sweep.py)
 	struct lh2b_gather* gather = nullptr;		// attached multi-GPU gather (gather.cu): frames end with a snapshot for it instead of the local finalize
 	int bandY0 = 0, bandY1 = 0, bandStep = 1;	// rows this core renders (lh2b_set_row_band[_strided]; 0, 0 = the whole frame)
 	float tileRootShare = 1.0f;				// lh2b_tile_create: rank 0's band relative to an equal share (it also runs the frame's tail)
@@ -97,7 +99,7 @@ struct lh2b_core
 	void* l2Base = nullptr; size_t l2Bytes = 0;
 	int bvhRefit = 1;						// same triangle count re-sent: 1 refit in place (binary + wide tree), 2 refit the binary tree and collapse again, 0 rebuild	// work counter of the persistent query kernels
 	// settings
-	int bvhBuilder = 0;				// 0: GPU LBVH (default), 1: host binned SAH
+	int bvhBuilder = 0;				// 0: GPU PLOC (default), 1: host binned SAH, 2: GPU LBVH
 	float geometryEpsilon = 1e-4f, clampValue = 10.0f;	// reference defaults: stageClampValue(10) at rendercore.cpp:243; epsilon comes from RenderSystem (rendersystem.h:65-72)
 	int maxPathLength = 3;			// reference MAXPATHLENGTH (core_settings.h:25)
 	int bsdfModel = 0;					// Setting "bsdf": 0 lambert.h, 1 disney.h (what kernels/bsdf.h of the stock cores selects)

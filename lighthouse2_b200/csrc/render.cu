@@ -386,8 +386,6 @@ int lh2b_setting( lh2b_core* core, const char* name, float value )
 	else if (!strcmp( name, "bvhBuilder" )) core->bvhBuilder = (int)value;	// 0: GPU PLOC (default), 1: host binned SAH, 2: GPU LBVH
 	else if (!strcmp( name, "bvhRefit" )) core->bvhRefit = (int)value;
 	else if (!strcmp( name, "plocRadius" )) core->plocRadius = value < 1 ? 1 : (value > 64 ? 64 : (int)value);
-	else if (!strcmp( name, "bvhMaxLeaf" )) core->bvhMaxLeaf = value < 1 ? 1 : (value > 3 ? 3 : (int)value);
-	else if (!strcmp( name, "traversalVariant" )) g_traversalVariant = (int)value;
 	else if (!strcmp( name, "wideBlocksPerSM" )) g_wideBlocksPerSM = value < 1 ? 1 : (int)value;
 	else if (!strcmp( name, "triThreshold" )) g_triThreshold = (int)value;
 	else if (!strcmp( name, "triThresholdShadow" )) g_triThresholdShadow = (int)value;

@@ -1,12 +1,11 @@
-/* trace_kernels.cu - standalone extend / connect kernels over ray buffers in HBM.
-
-   extendKernel  = setupSecondaryRay   (lib/rendercore_optix7/optix/.optix.cu:131-140)
-   occludeKernel = the traversal half of generateShadowRay (.optix.cu:142-149), reporting a flag per ray.
-   Both read O4/D4 as float4 (32 B per ray) and write 16 B (hit) or 1 B (flag).
+/* trace_kernels.cu - the ray-tracing stages: generate + extend, extend, connect, and the stand-alone ray queries, all instances of
+   the persistent warp-cooperative traversal (traverse_wide.cuh) over ray buffers in HBM: 32 B per ray in (O4, D4), 16 B out (hit
+   record) or a 16-byte accumulator update per unoccluded shadow ray.
 */
 #include "kernels.h"
 #include "render_types.h"
 #include "traverse.cuh"
+#define WIDE_MIN_BLOCKS 8		// resident blocks per SM the traversal kernels are compiled for (64 registers per thread)
 #include "traverse_wide.cuh"
 
 namespace lh2b
@@ -19,127 +18,12 @@ __device__ __forceinline__ float4 PackHit( const bool hit, const TraceResult& r 
 	return make_float4( __uint_as_float( uv ), __uint_as_float( r.inst ), __uint_as_float( r.prim ), r.t );
 }
 
-__global__ void __launch_bounds__( 128 ) extendKernel( const DevScene scene, const float4* __restrict__ O4, const float4* __restrict__ D4,
-	float4* __restrict__ hits, const int n )
-{
-	const int i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n) return;
-	const float4 o = O4[i], d = D4[i];
-	TraceResult r;
-	const bool hit = Traverse<false>( scene, make_float3( o.x, o.y, o.z ), make_float3( d.x, d.y, d.z ), 0.0f, 1e34f, r );
-	hits[i] = PackHit( hit, r );
-}
-
-__global__ void __launch_bounds__( 128 ) occludeKernel( const DevScene scene, const float4* __restrict__ O4, const float4* __restrict__ D4,
-	uint8_t* __restrict__ occluded, const int n )
-{
-	const int i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n) return;
-	const float4 o = O4[i], d = D4[i];
-	TraceResult r;
-	occluded[i] = Traverse<true>( scene, make_float3( o.x, o.y, o.z ), make_float3( d.x, d.y, d.z ), 0.0f, d.w, r ) ? 1 : 0;
-}
-
 /* ---- wavefront stages ------------------------------------------------------------------- */
 
 __device__ __forceinline__ uint32_t WangHashT( uint32_t s ) { s = (s ^ 61) ^ (s >> 16), s *= 9, s = s ^ (s >> 4), s *= 0x27d4eb2d, s = s ^ (s >> 15); return s; }
 __device__ __forceinline__ float RandomFloatT( uint32_t& s ) { s ^= s << 13, s ^= s >> 17, s ^= s << 5; return s * 2.3283064365387e-10f; }
 
-/* generate + extend for path length 1: setupPrimaryRay (.optix.cu:112-129) with generateEyeRay (:85-104),
-   RandomPointOnLens (:71-83), blueNoiseSampler4 (:56-69) and RayTarget (lib/RenderSystem/common_functions.h:29-50).
-   One thread per path, grid-stride over the w*h*spp paths of this core. */
-__global__ void __launch_bounds__( 128 ) generateExtendKernel( const DevScene scene, const RenderParams p, const PathSet out, float4* __restrict__ hits )
-{
-	const uint32_t pixels = p.w * p.h;
-	for (uint32_t pathIdx = blockIdx.x * blockDim.x + threadIdx.x; pathIdx < pixels * p.spp; pathIdx += gridDim.x * blockDim.x)
-	{
-		const uint32_t pixelIdx = pathIdx % pixels;
-		{
-			const int row = (int)(pixelIdx / p.w), rel = row / 4 - p.bandY0 / 4;	// tile-sharded frame: skip rows that are not this core's
-			if (row < p.bandY0 || row >= p.bandY1 || rel % p.bandStep != 0) continue;
-		}
-		const uint32_t seedIdx = pathIdx + p.sampleBase * pixels;
-		const uint32_t sampleIdx = seedIdx / pixels + p.pass;
-		uint32_t seed = WangHashT( seedIdx * 16789 + p.pass * 1791 );
-		const int sx = pixelIdx % p.w, sy = pixelIdx / p.w;
-		float4 r4;
-		if (sampleIdx < 64)
-		{
-			const int x = (sx + (p.shift & 127)) & 127, y = (sy + (p.shift >> 24)) & 127;
-			const uint32_t* bn = p.blueNoise;
-			const uint4 rank = *(const uint4*)(bn + (x + y * 128) * 8 + 65536 * 3);
-			const uint32_t v0 = bn[0 + ((sampleIdx ^ rank.x) & 255) * 256], v1 = bn[1 + ((sampleIdx ^ rank.y) & 255) * 256];
-			const uint32_t v2 = bn[2 + ((sampleIdx ^ rank.z) & 255) * 256], v3 = bn[3 + ((sampleIdx ^ rank.w) & 255) * 256];
-			const uint4 scr = *(const uint4*)(bn + (x + y * 128) * 8 + 65536);
-			r4 = make_float4( (0.5f + (int)(v0 ^ scr.x)) * (1.0f / 256.0f), (0.5f + (int)(v1 ^ scr.y)) * (1.0f / 256.0f),
-				(0.5f + (int)(v2 ^ scr.z)) * (1.0f / 256.0f), (0.5f + (int)(v3 ^ scr.w)) * (1.0f / 256.0f) );
-		}
-		else r4.x = RandomFloatT( seed ), r4.y = RandomFloatT( seed ), r4.z = RandomFloatT( seed ), r4.w = RandomFloatT( seed );
-		// lens: 9-blade aperture
-		const float blade = (float)(int)(r4.x * 9);
-		float r1 = r4.z, r2 = (r4.x - blade * (1.0f / 9.0f)) * 9.0f;
-		float x1, y1, x2, y2;
-		const float PI_T = 3.14159265358979323846264f;
-		__sincosf( blade * PI_T / 4.5f, &x1, &y1 );
-		__sincosf( (blade + 1.0f) * PI_T / 4.5f, &x2, &y2 );
-		if ((r1 + r2) > 1) r1 = 1.0f - r1, r2 = 1.0f - r2;
-		const float xr = x1 * r1 + x2 * r2, yr = y1 * r1 + y2 * r2;
-		const float ap = p.posLensSize.w;
-		const float3 O = make_float3( p.posLensSize.x + ap * (p.right.x * xr + p.up.x * yr), p.posLensSize.y + ap * (p.right.y * xr + p.up.y * yr),
-			p.posLensSize.z + ap * (p.right.z * xr + p.up.z * yr) );
-		// point on the pixel
-		float fu, fv;
-		if (p.distortion == 0) fu = ((float)sx + r4.y) * (1.0f / p.w), fv = ((float)sy + r4.w) * (1.0f / p.h);
-		else
-		{
-			const float tx = sx / (float)p.w - 0.5f, ty = sy / (float)p.h - 0.5f;
-			const float rr = tx * tx + ty * ty;
-			const float rq = sqrtf( rr ) * (1.0f + p.distortion * rr + p.distortion * rr * rr);
-			const float theta = atan2f( tx, ty );
-			const float bx = (sinf( theta ) * rq + 0.5f) * p.w, by = (cosf( theta ) * rq + 0.5f) * p.h;
-			fu = (bx + r4.y) / (float)p.w, fv = (by + r4.w) / (float)p.h;
-		}
-		float3 D = make_float3( p.p1.x + fu * p.right.x + fv * p.up.x - O.x, p.p1.y + fu * p.right.y + fv * p.up.y - O.y, p.p1.z + fu * p.right.z + fv * p.up.z - O.z );
-		const float il = rsqrtf( D.x * D.x + D.y * D.y + D.z * D.z );
-		D.x *= il, D.y *= il, D.z *= il;
-		out.O[pathIdx] = make_float4( O.x, O.y, O.z, __uint_as_float( (pathIdx << 6) + 1 /* S_SPECULAR */ ) );
-		out.D[pathIdx] = make_float4( D.x, D.y, D.z, 0 );
-		TraceResult r;
-		const bool hit = Traverse<false>( scene, O, D, 0.0f, 1e34f, r );
-		hits[pathIdx] = PackHit( hit, r );
-	}
-}
-
-/* extend for path length > 1 (setupSecondaryRay, .optix.cu:131-140): ray count comes from the device counter. */
-__global__ void __launch_bounds__( 128 ) extendCountedKernel( const DevScene scene, const PathSet in, float4* __restrict__ hits,
-	const uint32_t* __restrict__ countPtr )
-{
-	const uint32_t n = *countPtr;
-	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-	{
-		const float4 o = in.O[i], d = in.D[i];
-		TraceResult r;
-		const bool hit = Traverse<false>( scene, make_float3( o.x, o.y, o.z ), make_float3( d.x, d.y, d.z ), 0.0f, 1e34f, r );
-		hits[i] = PackHit( hit, r );
-	}
-}
-
-/* connect (generateShadowRay, .optix.cu:142-154): unoccluded shadow rays deposit their potential contribution. */
-__global__ void __launch_bounds__( 128 ) connectKernel( const DevScene scene, const PathSet conn, float4* __restrict__ accumulator,
-	const uint32_t* __restrict__ countPtr )
-{
-	const uint32_t n = *countPtr;
-	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-	{
-		const float4 o = conn.O[i], d = conn.D[i];
-		TraceResult r;
-		if (Traverse<true>( scene, make_float3( o.x, o.y, o.z ), make_float3( d.x, d.y, d.z ), 0.0f, d.w, r )) continue;
-		const float4 e = conn.T[i];
-		atomicAdd( accumulator + __float_as_int( e.w ), make_float4( e.x, e.y, e.z, 1 ) );
-	}
-}
-
-/* ---- persistent warp-cooperative variants (single identity instance: no top level) ------------------------- */
+/* ---- persistent warp-cooperative kernels (traverse_wide.cuh) ---------------------------------------------------- */
 
 struct BufferRaySource
 {
@@ -273,7 +157,9 @@ struct TiledHitSink
 	__device__ __forceinline__ void AnyHit( const uint32_t, const bool ) const {}
 };
 
-template <bool TWO_LEVEL, bool BAND> __global__ void __launch_bounds__( WIDE_BLOCK ) wideGenerateExtendKernel( const DevScene scene, const RenderParams p, const PathSet out, float4* __restrict__ hits,
+/* generate + extend for path length 1: setupPrimaryRay (.optix.cu:112-129) with generateEyeRay (:85-104), RandomPointOnLens (:71-83),
+   blueNoiseSampler4 (:56-69) and RayTarget (lib/RenderSystem/common_functions.h:29-50), fused into the work fetch of the traversal. */
+template <bool TWO_LEVEL, bool BAND, bool STATS> __global__ void __launch_bounds__( WIDE_BLOCK, WIDE_MIN_BLOCKS ) wideGenerateExtendKernel( const DevScene scene, const RenderParams p, const PathSet out, float4* __restrict__ hits,
 	uint32_t* workCounter, const WideTuning tune )
 {
 	TiledPrimarySource<BAND> src;
@@ -282,31 +168,34 @@ template <bool TWO_LEVEL, bool BAND> __global__ void __launch_bounds__( WIDE_BLO
 	src.itemsPerSample = src.tilesX * (BAND ? BandTileRows( p ) : ((uint32_t)p.h + 3) / 4) * 32;
 	src.tilesXMagic = MagicOf( src.tilesX ), src.itemsMagic = MagicOf( src.itemsPerSample );
 	TiledHitSink sink = { hits };
-	TraverseWide<false, TWO_LEVEL>( scene, src, sink, src.itemsPerSample * p.spp, workCounter, tune );
+	TraverseWide<false, TWO_LEVEL, STATS>( scene, src, sink, src.itemsPerSample * p.spp, workCounter, tune, scene.stats );
 }
 
-template <bool TWO_LEVEL> __global__ void __launch_bounds__( WIDE_BLOCK ) wideExtendKernel( const DevScene scene, const float4* __restrict__ O4, const float4* __restrict__ D4,
+/* extend for path length > 1 (setupSecondaryRay, .optix.cu:131-140): the ray count comes from a device counter (frames) or is fixed (queries) */
+template <bool TWO_LEVEL, bool STATS> __global__ void __launch_bounds__( WIDE_BLOCK, WIDE_MIN_BLOCKS ) wideExtendKernel( const DevScene scene, const float4* __restrict__ O4, const float4* __restrict__ D4,
 	float4* __restrict__ hits, const uint32_t* __restrict__ countPtr, const uint32_t fixedCount, uint32_t* workCounter, const WideTuning tune )
 {
 	BufferRaySource src = { O4, D4, false };
 	HitBufferSink sink = { hits };
-	TraverseWide<false, TWO_LEVEL>( scene, src, sink, countPtr ? *countPtr : fixedCount, workCounter, tune );
+	TraverseWide<false, TWO_LEVEL, STATS>( scene, src, sink, countPtr ? *countPtr : fixedCount, workCounter, tune, scene.stats );
 }
 
-template <bool TWO_LEVEL> __global__ void __launch_bounds__( WIDE_BLOCK ) wideOccludeKernel( const DevScene scene, const float4* __restrict__ O4, const float4* __restrict__ D4,
+/* the traversal half of generateShadowRay (.optix.cu:142-149), reporting a flag per ray (ray queries) */
+template <bool TWO_LEVEL, bool STATS> __global__ void __launch_bounds__( WIDE_BLOCK, WIDE_MIN_BLOCKS ) wideOccludeKernel( const DevScene scene, const float4* __restrict__ O4, const float4* __restrict__ D4,
 	uint8_t* __restrict__ flags, const uint32_t fixedCount, uint32_t* workCounter, const WideTuning tune )
 {
 	BufferRaySource src = { O4, D4, true };
 	OccludedFlagSink sink = { flags };
-	TraverseWide<true, TWO_LEVEL>( scene, src, sink, fixedCount, workCounter, tune );
+	TraverseWide<true, TWO_LEVEL, STATS>( scene, src, sink, fixedCount, workCounter, tune, scene.stats );
 }
 
-template <bool TWO_LEVEL> __global__ void __launch_bounds__( WIDE_BLOCK ) wideConnectKernel( const DevScene scene, const PathSet conn, float4* __restrict__ accumulator,
+/* connect (generateShadowRay, .optix.cu:142-154): unoccluded shadow rays deposit their potential contribution */
+template <bool TWO_LEVEL, bool STATS> __global__ void __launch_bounds__( WIDE_BLOCK, WIDE_MIN_BLOCKS ) wideConnectKernel( const DevScene scene, const PathSet conn, float4* __restrict__ accumulator,
 	const uint32_t* __restrict__ countPtr, uint32_t* workCounter, const WideTuning tune )
 {
 	BufferRaySource src = { conn.O, conn.D, true };
 	ConnectSink sink = { conn.T, accumulator };
-	TraverseWide<true, TWO_LEVEL>( scene, src, sink, *countPtr, workCounter, tune );
+	TraverseWide<true, TWO_LEVEL, STATS>( scene, src, sink, *countPtr, workCounter, tune, scene.stats );
 }
 
 /* flat scenes: write the owning instance index into the spare word of every traversal triangle */
@@ -327,82 +216,57 @@ static uint32_t PersistentGrid( uint32_t maxItems, int smCount, int blocksPerSM 
 	return need < cap ? (need ? need : 1) : cap;
 }
 
-static uint32_t GridFor( uint32_t maxItems, int smCount )
-{
-	uint32_t blocks = (maxItems + 127) / 128;
-	const uint32_t cap = (uint32_t)smCount * 8 * 8;
-	return blocks > cap ? cap : (blocks ? blocks : 1);
-}
-
-int g_traversalVariant = 1;	// 1: persistent warp-cooperative kernels for single-instance scenes, 0: per-thread while-while everywhere
-int g_wideBlocksPerSM = 8;
+int g_wideBlocksPerSM = WIDE_MIN_BLOCKS;
 int g_triThreshold = WIDE_TRI_THRESHOLD, g_refillThreshold = WIDE_REFILL_THRESHOLD, g_triThresholdShadow = WIDE_TRI_THRESHOLD;
 #define TUNE WideTuning{ g_triThreshold, g_refillThreshold }
 #define TUNE_SHADOW WideTuning{ g_triThresholdShadow, g_refillThreshold }
+/* picks the instantiation: two-level or flat scene, work counters on (scene.stats set by lh2b_trace_stats) or off */
+#define WIDE_LAUNCH( kernel, grid, s, ... ) do { \
+	if (scene.singleIdentity) { if (scene.stats) kernel<false, true><<<grid, WIDE_BLOCK, 0, s>>>( __VA_ARGS__ ); else kernel<false, false><<<grid, WIDE_BLOCK, 0, s>>>( __VA_ARGS__ ); } \
+	else { if (scene.stats) kernel<true, true><<<grid, WIDE_BLOCK, 0, s>>>( __VA_ARGS__ ); else kernel<true, false><<<grid, WIDE_BLOCK, 0, s>>>( __VA_ARGS__ ); } } while (0)
 
 void LaunchGenerateExtend( const DevScene& scene, const RenderParams& p, const PathSet& out, float4* hits, uint32_t* workCounter, int smCount, cudaStream_t s )
 {
-	if (g_traversalVariant == 1)
+	const uint32_t items = ((p.w + 7) / 8) * BandTileRows( p ) * 32 * p.spp, grid = PersistentGrid( items, smCount, g_wideBlocksPerSM );
+	const bool band = !(p.bandY0 == 0 && p.bandY1 == p.h && p.bandStep == 1);
+	const bool stats = scene.stats != nullptr;
+#define GEN_LAUNCH( TL, BAND, ST ) wideGenerateExtendKernel<TL, BAND, ST><<<grid, WIDE_BLOCK, 0, s>>>( scene, p, out, hits, workCounter, TUNE )
+	if (scene.singleIdentity)
 	{
-		const uint32_t items = ((p.w + 7) / 8) * BandTileRows( p ) * 32 * p.spp, grid = PersistentGrid( items, smCount, g_wideBlocksPerSM );
-		const bool band = !(p.bandY0 == 0 && p.bandY1 == p.h && p.bandStep == 1);
-		if (scene.singleIdentity)
-		{
-			if (band) wideGenerateExtendKernel<false, true><<<grid, WIDE_BLOCK, 0, s>>>( scene, p, out, hits, workCounter, TUNE );
-			else wideGenerateExtendKernel<false, false><<<grid, WIDE_BLOCK, 0, s>>>( scene, p, out, hits, workCounter, TUNE );
-		}
-		else if (band) wideGenerateExtendKernel<true, true><<<grid, WIDE_BLOCK, 0, s>>>( scene, p, out, hits, workCounter, TUNE );
-		else wideGenerateExtendKernel<true, false><<<grid, WIDE_BLOCK, 0, s>>>( scene, p, out, hits, workCounter, TUNE );
+		if (band) { if (stats) GEN_LAUNCH( false, true, true ); else GEN_LAUNCH( false, true, false ); }
+		else { if (stats) GEN_LAUNCH( false, false, true ); else GEN_LAUNCH( false, false, false ); }
 	}
-	else generateExtendKernel<<<GridFor( (uint32_t)p.w * p.h * p.spp, smCount ), 128, 0, s>>>( scene, p, out, hits );
+	else if (band) { if (stats) GEN_LAUNCH( true, true, true ); else GEN_LAUNCH( true, true, false ); }
+	else { if (stats) GEN_LAUNCH( true, false, true ); else GEN_LAUNCH( true, false, false ); }
+#undef GEN_LAUNCH
 }
 
 void LaunchExtendCounted( const DevScene& scene, const PathSet& in, float4* hits, const uint32_t* countPtr, uint32_t* workCounter, uint32_t maxRays, int smCount, cudaStream_t s )
 {
-	if (g_traversalVariant == 1)
-	{
-		const uint32_t grid = PersistentGrid( maxRays, smCount, g_wideBlocksPerSM );
-		if (scene.singleIdentity) wideExtendKernel<false><<<grid, WIDE_BLOCK, 0, s>>>( scene, in.O, in.D, hits, countPtr, 0, workCounter, TUNE );
-		else wideExtendKernel<true><<<grid, WIDE_BLOCK, 0, s>>>( scene, in.O, in.D, hits, countPtr, 0, workCounter, TUNE );
-	}
-	else extendCountedKernel<<<GridFor( maxRays, smCount ), 128, 0, s>>>( scene, in, hits, countPtr );
+	const uint32_t grid = PersistentGrid( maxRays, smCount, g_wideBlocksPerSM );
+	WIDE_LAUNCH( wideExtendKernel, grid, s, scene, in.O, in.D, hits, countPtr, 0, workCounter, TUNE );
 }
 
 void LaunchConnect( const DevScene& scene, const PathSet& conn, float4* accumulator, const uint32_t* countPtr, uint32_t* workCounter, uint32_t maxRays, int smCount, cudaStream_t s )
 {
-	if (g_traversalVariant == 1)
-	{
-		const uint32_t grid = PersistentGrid( maxRays, smCount, g_wideBlocksPerSM );
-		if (scene.singleIdentity) wideConnectKernel<false><<<grid, WIDE_BLOCK, 0, s>>>( scene, conn, accumulator, countPtr, workCounter, TUNE_SHADOW );
-		else wideConnectKernel<true><<<grid, WIDE_BLOCK, 0, s>>>( scene, conn, accumulator, countPtr, workCounter, TUNE_SHADOW );
-	}
-	else connectKernel<<<GridFor( maxRays, smCount ), 128, 0, s>>>( scene, conn, accumulator, countPtr );
+	const uint32_t grid = PersistentGrid( maxRays, smCount, g_wideBlocksPerSM );
+	WIDE_LAUNCH( wideConnectKernel, grid, s, scene, conn, accumulator, countPtr, workCounter, TUNE_SHADOW );
 }
 
 void LaunchExtend( const DevScene& scene, const float4* O4, const float4* D4, float4* hits, int n, uint32_t* workCounter, int smCount, cudaStream_t s )
 {
 	if (n <= 0) return;
-	if (g_traversalVariant == 1)
-	{
-		cudaMemsetAsync( workCounter, 0, sizeof( uint32_t ), s );
-		const uint32_t grid = PersistentGrid( (uint32_t)n, smCount, g_wideBlocksPerSM );
-		if (scene.singleIdentity) wideExtendKernel<false><<<grid, WIDE_BLOCK, 0, s>>>( scene, O4, D4, hits, nullptr, (uint32_t)n, workCounter, TUNE );
-		else wideExtendKernel<true><<<grid, WIDE_BLOCK, 0, s>>>( scene, O4, D4, hits, nullptr, (uint32_t)n, workCounter, TUNE );
-	}
-	else extendKernel<<<(n + 127) / 128, 128, 0, s>>>( scene, O4, D4, hits, n );
+	cudaMemsetAsync( workCounter, 0, sizeof( uint32_t ), s );
+	const uint32_t grid = PersistentGrid( (uint32_t)n, smCount, g_wideBlocksPerSM );
+	WIDE_LAUNCH( wideExtendKernel, grid, s, scene, O4, D4, hits, nullptr, (uint32_t)n, workCounter, TUNE );
 }
 
 void LaunchOcclude( const DevScene& scene, const float4* O4, const float4* D4, uint8_t* occluded, int n, uint32_t* workCounter, int smCount, cudaStream_t s )
 {
 	if (n <= 0) return;
-	if (g_traversalVariant == 1)
-	{
-		cudaMemsetAsync( workCounter, 0, sizeof( uint32_t ), s );
-		const uint32_t grid = PersistentGrid( (uint32_t)n, smCount, g_wideBlocksPerSM );
-		if (scene.singleIdentity) wideOccludeKernel<false><<<grid, WIDE_BLOCK, 0, s>>>( scene, O4, D4, occluded, (uint32_t)n, workCounter, TUNE_SHADOW );
-		else wideOccludeKernel<true><<<grid, WIDE_BLOCK, 0, s>>>( scene, O4, D4, occluded, (uint32_t)n, workCounter, TUNE_SHADOW );
-	}
-	else occludeKernel<<<(n + 127) / 128, 128, 0, s>>>( scene, O4, D4, occluded, n );
+	cudaMemsetAsync( workCounter, 0, sizeof( uint32_t ), s );
+	const uint32_t grid = PersistentGrid( (uint32_t)n, smCount, g_wideBlocksPerSM );
+	WIDE_LAUNCH( wideOccludeKernel, grid, s, scene, O4, D4, occluded, (uint32_t)n, workCounter, TUNE_SHADOW );
 }
 
 } // namespace lh2b

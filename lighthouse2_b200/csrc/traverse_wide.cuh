@@ -1,26 +1,34 @@
-/* traverse_wide.cuh - persistent, warp-cooperative CWBVH traversal (sm_100a).
+/* traverse_wide.cuh - persistent, warp-cooperative traversal of the 8-wide BVH of bvh.h (sm_100a).
 
-   Same contract and bit-identical results as traverse.cuh (see there for the reference call sites it replaces);
-   this is the throughput path. What the first ncu profile (profiles/r1_v0_generateExtend_full.txt) showed for the
-   per-thread while-while loop: triangle tests ran with 3 of 32 lanes, node steps with 15 of 32, and the byte->float
-   conversions (48 I2F.U8 per node step, quarter-rate XU pipe) dominated the stall samples. Hence:
+   Contract: traverse.cuh (the reference call sites it replaces are listed there). What shaped it, with the ncu evidence:
 
-   1. The warp, not the thread, owns the loop. Every iteration all 32 lanes vote (ballot) once on what they hold,
-      then the warp runs a triangle step for the lanes holding a triangle group, followed by a node step for the
-      lanes holding a node group (the "if-if" shape: both steps run convergent, each at most once per iteration).
-      Triangle groups found while a lane still has one pending are parked on a per-lane deferred stack.
-      TRI_THRESHOLD can postpone the triangle step until that many lanes have triangles; measured on the B200
-      (1 M-triangle terrain: primary / shadow / diffuse rays) the best value is 1, i.e. never postpone.
-   2. Persistent threads: lanes whose ray is finished fetch the next ray index from a global counter with one
-      warp-aggregated atomicAdd, so the warp stays full until the launch runs out of rays.
-   3. Quantised plane bytes are turned into floats with one PRMT each (byte dropped into the mantissa of 65536.0f:
-      value 65536 + 2q), folded into the slab FMA; the 2^-9-quantum rounding this adds is covered by separate,
-      outward-rounded near/far offsets.
-   4. The node stack head lives in shared memory ([entry][thread] layout: conflict-free for any per-lane depth),
-      overflow and the deferred-triangle stack in local memory.
+   Round 1 (profiles/r1_v*): the per-thread while-while loop ran triangle tests with 3 of 32 lanes and node steps with 15 of
+   32, hence the warp-cooperative shape kept here:
+   1. The warp, not the thread, owns the loop. Every iteration all 32 lanes vote (ballot) once on what they hold, then the warp
+      runs a triangle step for the lanes holding a triangle group, followed by a node step for the lanes holding a node group
+      (the "if-if" shape: both steps run convergent, each at most once per iteration). Triangle groups found while a lane still
+      has one pending are parked on a per-lane deferred stack.
+   2. Persistent threads: lanes whose ray is finished fetch the next ray index from a global counter with one warp-aggregated
+      atomicAdd, so the warp stays full until the launch runs out of rays.
+   3. The node stack head lives in shared memory ([entry][thread] layout: conflict-free for any per-lane depth), overflow and
+      the deferred-triangle stack in local memory.
 
-   Closest-hit order independence (tie-break on (instance, primitive)) is what makes deferring legal: the result
-   does not depend on the order in which triangles are tested.
+   Round 2 (profiles/r1_v4_kernels_full.txt read again): the node step was 282 warp instructions, 2/3 of them on the ALU pipe,
+   which issues at half rate - ALU pipe 68 % busy, FMA pipe 28 %, math-pipe-throttle stalls; the kernel was ALU-pipe bound, not
+   "issue bound". 48 of those instructions were byte->float PRMTs and ~50 assembled the hit mask with per-child variable shifts.
+   The node format was therefore redesigned around the instruction stream (bvh.h):
+   4. child planes are bfloat16 offsets: decoding is free (odd slots) or one shift (even slots); no exponents, no bias
+      correction; near / far planes are picked with one SEL per word (two children);
+   5. the three per-child rejections (slab empty, behind tmax, behind the origin) are three values whose SIGN bits are OR-ed and
+      shifted into an 8-bit miss mask with one funnel shift per child - differences and the far-side padding run on the FMA pipe
+      (FFMA / FADD), only the two 3-input min / max per child stay on the ALU pipe;
+   6. one triangle per leaf slot: the hit mask is 8 bits in slot order, AND-ed with the node's internal / leaf masks; the
+      front-to-back choice among hit children is one shared-memory table look-up per pop (octant x mask -> slot);
+   7. a node is one aligned 128-byte line fetched with four 256-bit loads (LDG.E.256): 4 sector requests per node instead of 5
+      requests over 3-4 sectors.
+
+   Closest-hit order independence (tie-break on (instance, primitive)) is what makes deferring legal: the result does not depend
+   on the order in which triangles are tested.
 */
 #pragma once
 #include "traverse.cuh"
@@ -35,50 +43,67 @@ namespace lh2b
 #define WIDE_TRI_THRESHOLD 1	// lanes with pending triangles that trigger a triangle step
 #define WIDE_REFILL_THRESHOLD 8	// idle lanes that trigger fetching new rays
 
-/* 0x47800000 = 65536.0f; dropping a byte into mantissa bits 8..15 gives exactly 65536 + 2 * byte. 'base' holds the
-   constant in a register (see OpaqueBase) so that the selector can be the instruction's immediate: one PRMT per plane. */
-template <int J> __device__ __forceinline__ float ByteFloat( const uint32_t word, const uint32_t base )
+/* one 32-byte sector with a single 256-bit load (sm_100+); the data is read-only for the whole launch */
+__device__ __forceinline__ void LoadSector( const void* p, uint32_t (&r)[8] )
 {
-	uint32_t r;
-	asm( "prmt.b32 %0, %1, %2, %3;" : "=r"( r ) : "r"( word ), "r"( base ), "n"( 0x7604 | (J << 4) ) );
-	return __uint_as_float( r );
-}
-__device__ __forceinline__ uint32_t OpaqueBase()
-{
-	uint32_t k;
-	asm volatile( "mov.b32 %0, 0x47800000;" : "=r"( k ) );	// volatile: the optimiser must not fold it back into an immediate
-	return k;
+	asm( "ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+		: "=r"( r[0] ), "=r"( r[1] ), "=r"( r[2] ), "=r"( r[3] ), "=r"( r[4] ), "=r"( r[5] ), "=r"( r[6] ), "=r"( r[7] ) : "l"( p ) );
 }
 
 struct WideRay
 {
 	float3 O, D;
-	float tmin, tmax;
+	float tmin, tmax;	// the box test assumes tmin >= 0 (every ray source passes 0)
 };
+
+/* Work counters of a launch (STATS instantiations only; lh2b_trace_stats): what the issue roofline is computed from. */
+struct TraceStats
+{
+	unsigned long long rays, nodeSteps, triTests, instanceEntries;	// per ray (lane) events
+	unsigned long long iterations, nodePhases, triPhases;				// per warp events
+	unsigned long long nodeLanes, triLanes;							// lanes active in those phases (SIMT utilisation of each step)
+};
+
+/* octant x child-hit mask -> slot to visit next: the hit slot s with the largest s ^ octinv (front to back) */
+__device__ __forceinline__ void FillPopTable( uint8_t* table )
+{
+	for (int i = threadIdx.x; i < 2048; i += blockDim.x)
+	{
+		const int o = i >> 8, m = i & 255;
+		int best = 0, bestPriority = -1;
+		for (int s = 0; s < 8; s++) if (((m >> s) & 1) && (s ^ o) > bestPriority) bestPriority = s ^ o, best = s;
+		table[i] = (uint8_t)best;
+	}
+}
 
 /* RaySource: bool Load( uint32_t workIdx, WideRay&, uint32_t& tag ) (false: nothing to trace for this index; tag is
               an opaque per-ray word handed back to the sink, e.g. the path index)
    HitSink:   void Closest( uint32_t tag, bool hit, const TraceResult& ) / void AnyHit( uint32_t tag, bool occluded )
 
+   Stack / group encoding (uint2): node group  = ( childBase, hitInner << 24 | imask )   - y > 0x00ffffff
+                                   leaf group  = ( triBase,   hitLeaf | lmask << 8 )      - 0 < y <= 0x00ffffff
+                                   sentinel    = ( restoreRay, 0 )                        - two-level only
    TWO_LEVEL: the lane is either in the top level (curInst == ~0: node groups index TLAS nodes, leaf groups are
    instances) or inside one instance. Entering an instance transforms the ray, pushes the remaining top-level work and
    a sentinel; the sentinel is only popped once every triangle of that instance (pending group + deferred stack) has
    been tested, because deferred triangle groups are meaningless outside their instance. */
 struct WideTuning { int triThreshold, refillThreshold; };
 
-template <bool ANYHIT, bool TWO_LEVEL, class RaySource, class HitSink>
+template <bool ANYHIT, bool TWO_LEVEL, bool STATS, class RaySource, class HitSink>
 __device__ __forceinline__ void TraverseWide( const DevScene& scene, RaySource& src, HitSink& sink, const uint32_t rayCount, uint32_t* workCounter,
-	const WideTuning tune )
+	const WideTuning tune, TraceStats* statsOut = nullptr )
 {
 	__shared__ uint2 smemStack[WIDE_SMEM_STACK][WIDE_BLOCK];
 	__shared__ float worldRay[TWO_LEVEL ? 6 : 1][WIDE_BLOCK];	// world-space O, D while the lane is inside a transformed instance
+	__shared__ uint8_t popTable[2048];
 	uint2 localStack[WIDE_LOCAL_STACK];
 	uint2 triStack[WIDE_TRI_STACK];
+	FillPopTable( popTable );
+	__syncthreads();
 	const uint32_t lane = threadIdx.x & 31;
-	const uint4* __restrict__ nodes = scene.nodes;
+	const char* __restrict__ nodes = (const char*)scene.nodes;
 	const float4* __restrict__ tris = scene.tris;
 	const uint32_t NO_INST = 0xffffffffu;
-	const uint32_t fbase = OpaqueBase();
 	// lane state
 	bool active = false;
 	uint32_t workIdx = 0;
@@ -91,8 +116,13 @@ __device__ __forceinline__ void TraverseWide( const DevScene& scene, RaySource& 
 	uint32_t bestPrim = 0xffffffffu, bestInst = 0xffffffffu;
 	float bestU = 0, bestV = 0;
 	bool exhausted = false;	// no more rays in the launch
+	unsigned long long stRays = 0, stNodes = 0, stTris = 0, stInst = 0, stIter = 0, stNodePh = 0, stTriPh = 0, stNodeLanes = 0, stTriLanes = 0;
 #define WIDE_PUSH( e ) do { if (sp < WIDE_SMEM_STACK) smemStack[sp][threadIdx.x] = (e); else localStack[sp - WIDE_SMEM_STACK] = (e); sp++; } while (0)
 #define WIDE_TOP() (sp <= WIDE_SMEM_STACK ? smemStack[sp - 1][threadIdx.x] : localStack[sp - 1 - WIDE_SMEM_STACK])
+	/* takes the highest hit leaf slot out of a leaf group and returns the index of its triangle / instance */
+#define WIDE_TAKE_LEAF( g, index ) do { const int s_ = 31 - __clz( (g).y & 0xffu ); \
+		index = (g).x + __popc( ((g).y >> 8) & ((1u << s_) - 1u) ); \
+		(g).y &= ~(1u << s_); if (((g).y & 0xffu) == 0) (g).y = 0; } while (0)
 	while (true)
 	{
 		// ---- lanes without a node group take the next one from their stack; finished rays retire -------------
@@ -126,9 +156,9 @@ __device__ __forceinline__ void TraverseWide( const DevScene& scene, RaySource& 
 				if (curInst == NO_INST && tg.y != 0)
 				{
 					// enter one instance of the pending top-level leaf group
-					const int bit = 31 - __clz( tg.y );
-					tg.y &= ~(1u << bit);
-					const uint32_t inst = __ldg( scene.tlasLeafIds + tg.x + bit );
+					uint32_t leaf;
+					WIDE_TAKE_LEAF( tg, leaf );
+					const uint32_t inst = __ldg( scene.tlasLeafIds + leaf );
 					if (tg.y != 0) WIDE_PUSH( tg );
 					if (ng.y > 0x00ffffffu) WIDE_PUSH( ng );
 					const InstTrav& it = scene.instances[inst];
@@ -150,7 +180,8 @@ __device__ __forceinline__ void TraverseWide( const DevScene& scene, RaySource& 
 						octinv = (D.x < 0 ? 0 : 4) | (D.y < 0 ? 0 : 2) | (D.z < 0 ? 0 : 1);
 					}
 					curInst = inst;
-					ng = make_uint2( it.rootNode, 0x80000000u ), tg = make_uint2( 0, 0 );
+					ng = make_uint2( it.rootNode, 0x01000001u ), tg = make_uint2( 0, 0 );
+					if (STATS) stInst++;
 				}
 			}
 			if (ng.y <= 0x00ffffffu && tg.y == 0)
@@ -185,9 +216,11 @@ __device__ __forceinline__ void TraverseWide( const DevScene& scene, RaySource& 
 					O = ray.O, D = ray.D, tmin = ray.tmin, tmax = ray.tmax;
 					idx = SafeRcpDir( D.x ), idy = SafeRcpDir( D.y ), idz = SafeRcpDir( D.z );
 					octinv = (D.x < 0 ? 0 : 4) | (D.y < 0 ? 0 : 2) | (D.z < 0 ? 0 : 1);
-					ng = make_uint2( TWO_LEVEL ? scene.tlasRoot : scene.singleRoot, 0x80000000u ), tg = make_uint2( 0, 0 );
+					// the root is entered as "slot 0 of a group whose only child is the root" (imask = 1, hit = 1)
+					ng = make_uint2( TWO_LEVEL ? scene.tlasRoot : scene.singleRoot, 0x01000001u ), tg = make_uint2( 0, 0 );
 					sp = 0, tsp = 0, bestPrim = 0xffffffffu, bestInst = 0xffffffffu, bestU = bestV = 0;
 					curInst = TWO_LEVEL ? NO_INST : 0u;
+					if (STATS) stRays++;
 				}
 			}
 		}
@@ -196,6 +229,7 @@ __device__ __forceinline__ void TraverseWide( const DevScene& scene, RaySource& 
 		const bool hasTri = active && tg.y != 0 && (!TWO_LEVEL || curInst != NO_INST);
 		const uint32_t nodeMask = __ballot_sync( 0xffffffffu, hasNode ), triMask = __ballot_sync( 0xffffffffu, hasTri );
 		const uint32_t fullMask = __ballot_sync( 0xffffffffu, tsp >= WIDE_TRI_STACK - 1 );
+		if (STATS && lane == 0) stIter++;
 		if ((nodeMask | triMask) == 0)
 		{
 			// no lane can do a node or a triangle step: either nothing is active, or (two-level) lanes are about to
@@ -206,11 +240,13 @@ __device__ __forceinline__ void TraverseWide( const DevScene& scene, RaySource& 
 		const bool triPhase = triMask != 0 && (nodeMask == 0 || __popc( triMask ) >= tune.triThreshold || fullMask != 0);
 		if (triPhase)
 		{
+			if (STATS && lane == 0) stTriPh++, stTriLanes += __popc( triMask );
 			if (hasTri)
 			{
-				const int bit = 31 - __clz( tg.y );
-				tg.y &= ~(1u << bit);
-				const float4* tp = tris + (size_t)(tg.x + bit) * 3;
+				uint32_t triIdx;
+				WIDE_TAKE_LEAF( tg, triIdx );
+				if (STATS) stTris++;
+				const float4* tp = tris + (size_t)triIdx * 3;
 				const float4 v0 = __ldg( tp ), e1 = __ldg( tp + 1 ), e2 = __ldg( tp + 2 );
 				const float pvx = CROSS_X( D.x, D.y, D.z, e2.x, e2.y, e2.z );
 				const float pvy = CROSS_Y( D.x, D.y, D.z, e2.x, e2.y, e2.z );
@@ -254,65 +290,72 @@ __device__ __forceinline__ void TraverseWide( const DevScene& scene, RaySource& 
 			if (nodeMask == 0 || fullMask != 0) continue;	// (a full deferred-triangle stack drains before it may grow again)
 		}
 		// ---- node phase --------------------------------------------------------------------------------
+		if (STATS && lane == 0) stNodePh++, stNodeLanes += __popc( nodeMask );
 		if (hasNode && (!ANYHIT || active))
 		{
+			if (STATS) stNodes++;
 			const uint32_t hits = ng.y;
-			const int bit = 31 - __clz( hits );
-			ng.y &= ~(1u << bit);
+			const uint32_t slot = popTable[(octinv << 8) | (hits >> 24)];
+			ng.y = hits & ~(0x01000000u << slot);
 			if (ng.y > 0x00ffffffu) WIDE_PUSH( ng );
-			const uint32_t slot = (uint32_t)(bit - 24) ^ octinv;
-			const uint32_t rel = __popc( hits & ~(0xffffffffu << slot) & 0xffu );
-			const uint4* np = nodes + (size_t)(ng.x + rel) * 5;
-			const uint4 n0 = __ldg( np ), n1 = __ldg( np + 1 ), n2 = __ldg( np + 2 ), n3 = __ldg( np + 3 ), n4 = __ldg( np + 4 );
-			// t(q) = (p + q * 2^e - o) * idir = (65536 + 2q) * (2^e * idir / 2) + ((p - o) * idir - 32768 * 2^e * idir)
-			const float sx = __uint_as_float( (n0.w & 255u) << 23 ) * idx, sy = __uint_as_float( ((n0.w >> 8) & 255u) << 23 ) * idy;
-			const float sz = __uint_as_float( ((n0.w >> 16) & 255u) << 23 ) * idz;
-			const float hx = 0.5f * sx, hy = 0.5f * sy, hz = 0.5f * sz;
-			const float cx = fmaf( -32768.0f, sx, (__uint_as_float( n0.x ) - O.x) * idx );
-			const float cy = fmaf( -32768.0f, sy, (__uint_as_float( n0.y ) - O.y) * idy );
-			const float cz = fmaf( -32768.0f, sz, (__uint_as_float( n0.z ) - O.z) * idz );
-			// outward slack of 2^-8 quantum on both sides covers the rounding of the shifted offset
-			const float ex = 0.00390625f * fabsf( sx ), ey = 0.00390625f * fabsf( sy ), ez = 0.00390625f * fabsf( sz );
-			const float cnx = cx - ex, cfx = cx + ex, cny = cy - ey, cfy = cy + ey, cnz = cz - ez, cfz = cz + ez;
-			const uint32_t octinv4 = octinv * 0x01010101u;
-			ng.x = n1.x;
-			uint2 ntg = make_uint2( n1.y, 0 );
-			uint32_t hitmask = 0;
+			const uint32_t rel = __popc( hits & 0xffu & ((1u << slot) - 1u) );
+			const char* np = nodes + (size_t)(ng.x + rel) * 128;
+			uint32_t h[8], px[8], py[8], pz[8];
+			LoadSector( np, h ), LoadSector( np + 32, px ), LoadSector( np + 64, py ), LoadSector( np + 96, pz );
+			const bool negx = !(octinv & 4), negy = !(octinv & 2), negz = !(octinv & 1);
+			// t( plane ) = ( pmin + offset - o ) * idir = offset * idir + c
+			const float cx = (__uint_as_float( h[0] ) - O.x) * idx, cy = (__uint_as_float( h[1] ) - O.y) * idy, cz = (__uint_as_float( h[2] ) - O.z) * idz;
+			uint32_t miss = 0;
 #pragma unroll
-			for (int half = 0; half < 2; half++)
+			for (int k = 3; k >= 0; k--)
 			{
-				const uint32_t meta4 = half ? n1.w : n1.z;
-				const uint32_t isInner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
-				const uint32_t innerMask4 = SignExtendS8x4( isInner4 << 3 );
-				const uint32_t bitIndex4 = (meta4 ^ (octinv4 & innerMask4)) & 0x1f1f1f1fu;
-				const uint32_t childBits4 = (meta4 >> 5) & 0x07070707u;
-				const uint32_t qlox = half ? n2.y : n2.x, qloy = half ? n2.w : n2.z, qloz = half ? n3.y : n3.x;
-				const uint32_t qhix = half ? n3.w : n3.z, qhiy = half ? n4.y : n4.x, qhiz = half ? n4.w : n4.z;
-				const uint32_t nx = D.x < 0 ? qhix : qlox, fx = D.x < 0 ? qlox : qhix;
-				const uint32_t ny = D.y < 0 ? qhiy : qloy, fy = D.y < 0 ? qloy : qhiy;
-				const uint32_t nz = D.z < 0 ? qhiz : qloz, fz = D.z < 0 ? qloz : qhiz;
-#define WIDE_CHILD( J ) { \
-					const float t0x = fmaf( ByteFloat<J>( nx, fbase ), hx, cnx ), t1x = fmaf( ByteFloat<J>( fx, fbase ), hx, cfx ); \
-					const float t0y = fmaf( ByteFloat<J>( ny, fbase ), hy, cny ), t1y = fmaf( ByteFloat<J>( fy, fbase ), hy, cfy ); \
-					const float t0z = fmaf( ByteFloat<J>( nz, fbase ), hz, cnz ), t1z = fmaf( ByteFloat<J>( fz, fbase ), hz, cfz ); \
-					const float cmin = fmaxf( fmaxf( t0x, t0y ), fmaxf( t0z, tmin ) ); \
-					const float cmax = fminf( fminf( t1x, t1y ), fminf( t1z, tmax ) ) * 1.0000005f; \
-					if (cmin <= cmax) hitmask |= ((childBits4 >> (8 * J)) & 255u) << ((bitIndex4 >> (8 * J)) & 255u); }
-				WIDE_CHILD( 0 ) WIDE_CHILD( 1 ) WIDE_CHILD( 2 ) WIDE_CHILD( 3 )
-#undef WIDE_CHILD
+				// words k hold slots 2k (low half) and 2k + 1; near = the plane the ray meets first on that axis
+				const uint32_t nx = negx ? px[4 + k] : px[k], fx = negx ? px[k] : px[4 + k];
+				const uint32_t ny = negy ? py[4 + k] : py[k], fy = negy ? py[k] : py[4 + k];
+				const uint32_t nz = negz ? pz[4 + k] : pz[k], fz = negz ? pz[k] : pz[4 + k];
+#pragma unroll
+				for (int odd = 1; odd >= 0; odd--)
+				{
+#define WIDE_OFFSET( w ) __uint_as_float( odd ? (w) : (w) << 16 )
+					const float t0x = fmaf( WIDE_OFFSET( nx ), idx, cx ), t1x = fmaf( WIDE_OFFSET( fx ), idx, cx );
+					const float t0y = fmaf( WIDE_OFFSET( ny ), idy, cy ), t1y = fmaf( WIDE_OFFSET( fy ), idy, cy );
+					const float t0z = fmaf( WIDE_OFFSET( nz ), idz, cz ), t1z = fmaf( WIDE_OFFSET( fz ), idz, cz );
+#undef WIDE_OFFSET
+					const float cmin = fmaxf( fmaxf( t0x, t0y ), t0z ), cmax = fminf( fminf( t1x, t1y ), t1z );
+					// miss <=> the slab interval is empty (far side padded by a few ulp: this arithmetic differs from the exact
+					// triangle test), or starts behind tmax, or ends behind the origin: the OR of three sign bits
+					const float d1 = fmaf( cmax, 1.0000005f, -cmin ), d2 = tmax - cmin;
+					const uint32_t sign = __float_as_uint( d1 ) | __float_as_uint( d2 ) | __float_as_uint( cmax );
+					miss = __funnelshift_l( sign, miss, 1 );	// slots arrive 7, 6, .. 0: slot s ends up in bit s
+				}
 			}
-			ng.y = (hitmask & 0xff000000u) | (n0.w >> 24);
-			ntg.y = hitmask & 0x00ffffffu;
-			if (ntg.y != 0)
+			const uint32_t hitInner = ~miss & h[3] & 0xffu, hitLeaf = ~miss & (h[3] >> 8) & 0xffu;
+			ng = make_uint2( h[4], (hitInner << 24) | (h[3] & 0xffu) );
+			if (hitLeaf != 0)
 			{
+				const uint2 ntg = make_uint2( h[5], hitLeaf | (h[3] & 0xff00u) );
 				if (tg.y == 0) tg = ntg;
 				else triStack[tsp++] = ntg;
 			}
 			if (!TWO_LEVEL && ng.y <= 0x00ffffffu && sp > 0) { ng = WIDE_TOP(); sp--; }
 		}
 	}
+	if (STATS && statsOut)
+	{
+		for (int o = 16; o > 0; o >>= 1)
+			stRays += __shfl_xor_sync( 0xffffffffu, stRays, o ), stNodes += __shfl_xor_sync( 0xffffffffu, stNodes, o ),
+			stTris += __shfl_xor_sync( 0xffffffffu, stTris, o ), stInst += __shfl_xor_sync( 0xffffffffu, stInst, o );
+		if (lane == 0)
+		{
+			atomicAdd( &statsOut->rays, stRays ), atomicAdd( &statsOut->nodeSteps, stNodes ), atomicAdd( &statsOut->triTests, stTris );
+			atomicAdd( &statsOut->instanceEntries, stInst ), atomicAdd( &statsOut->iterations, stIter );
+			atomicAdd( &statsOut->nodePhases, stNodePh ), atomicAdd( &statsOut->triPhases, stTriPh );
+			atomicAdd( &statsOut->nodeLanes, stNodeLanes ), atomicAdd( &statsOut->triLanes, stTriLanes );
+		}
+	}
 #undef WIDE_PUSH
 #undef WIDE_TOP
+#undef WIDE_TAKE_LEAF
 }
 
 } // namespace lh2b

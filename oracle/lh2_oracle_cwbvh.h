@@ -1,9 +1,10 @@
 /* lh2_oracle_cwbvh.h - TEST INFRASTRUCTURE ONLY. An independent CPU reader of the product's acceleration-structure format: it decodes
-   the 8-wide compressed BVH exactly as lighthouse2_b200/csrc/bvh.h documents it (80-byte nodes: origin, three exponents, imask,
-   child / triangle base, 8 meta bytes, 6 x 8 quantised plane bytes; 48-byte triangle records v0 / e1 / e2 + primitive index) and
+   the 8-wide BVH exactly as lighthouse2_b200/csrc/bvh.h documents it (128-byte nodes: padded minimum corner, slot masks imask / lmask,
+   child / triangle base, 6 x 8 bfloat16 plane offsets where an odd slot is decoded together with its even neighbour's bits; one
+   triangle per leaf slot; 48-byte triangle records v0 / e1 / e2 + primitive index) and
      Check:        walks the tree and verifies that it is a correct acceleration structure for the mesh - every node and every
                    triangle record reachable exactly once, records equal to the mesh triangles, every decoded child box contains
-                   everything below it (the quantisation is conservative), meta bytes well-formed;
+                   everything below it (the encoding is conservative), slot masks well-formed, empty slots self-rejecting;
      ClosestHits:  traverses it with plain float slab tests (boxes padded like lh2_oracle_bvh.h) and the oracle's triangle test and
                    tie rule, so the hits must equal the exhaustive search of lh2_oracle_geom.h bit for bit.
    Used by tests/test_host_bvh_cpu.py on the output of the product's host builder (lh2b_host_bvh_build) - no GPU involved.
@@ -16,27 +17,38 @@
 namespace orcw
 {
 
+static const int NODE_BYTES = 128;
+
 struct Node
 {
-	float p[3]; float quantum[3]; uint32_t imask, childBase, triBase; uint8_t meta[8], qlo[3][8], qhi[3][8];
+	float p[3]; uint32_t imask, lmask, childBase, triBase; float lo[3][8], hi[3][8];	// plane OFFSETS from p, per axis and slot
 };
+
+static inline float BitsToFloat( uint32_t u ) { float f; memcpy( &f, &u, 4 ); return f; }
 
 static inline Node Decode( const uint8_t* b )
 {
 	Node n;
-	memcpy( n.p, b, 12 );
-	for (int a = 0; a < 3; a++) { const uint32_t bits = (uint32_t)b[12 + a] << 23; memcpy( &n.quantum[a], &bits, 4 ); }
-	n.imask = b[15];
-	memcpy( &n.childBase, b + 16, 4 ), memcpy( &n.triBase, b + 20, 4 );
-	memcpy( n.meta, b + 24, 8 );
-	for (int a = 0; a < 3; a++) memcpy( n.qlo[a], b + 32 + a * 8, 8 ), memcpy( n.qhi[a], b + 56 + a * 8, 8 );
+	uint32_t w[32];
+	memcpy( w, b, 128 );
+	memcpy( n.p, w, 12 );
+	n.imask = w[3] & 255u, n.lmask = (w[3] >> 8) & 255u, n.childBase = w[4], n.triBase = w[5];
+	for (int a = 0; a < 3; a++) for (int s = 0; s < 8; s++)
+	{
+		// words 8 + 8a .. : lo offsets of slots (2k, 2k+1) in word k; words 12 + 8a .. : hi offsets. Even slot: the low half moved up;
+		// odd slot: the whole word read as a float (the even neighbour's half rides along in the low mantissa bits)
+		const uint32_t wl = w[8 + a * 8 + s / 2], wh = w[12 + a * 8 + s / 2];
+		n.lo[a][s] = BitsToFloat( (s & 1) ? wl : wl << 16 ), n.hi[a][s] = BitsToFloat( (s & 1) ? wh : wh << 16 );
+	}
 	return n;
 }
 
 static inline void ChildBox( const Node& n, int s, float* lo, float* hi )
 {
-	for (int a = 0; a < 3; a++) lo[a] = n.p[a] + n.qlo[a][s] * n.quantum[a], hi[a] = n.p[a] + n.qhi[a][s] * n.quantum[a];
+	for (int a = 0; a < 3; a++) lo[a] = n.p[a] + n.lo[a][s], hi[a] = n.p[a] + n.hi[a][s];
 }
+
+static inline int Rank( uint32_t mask, int s ) { return __builtin_popcount( mask & ((1u << s) - 1u) ); }
 
 struct Report { int nodesVisited, trisVisited, maxDepth, emptySlots, leafSlots, innerSlots, errors, firstError; };
 
@@ -49,49 +61,47 @@ static inline void CheckNode( const uint8_t* nodes, int nNodes, const float* tri
 	if (idx < 0 || idx >= nNodes) { fail( 1 ); return; }
 	if (nodeSeen[idx]++) { fail( 2 ); return; }
 	r.nodesVisited++, r.maxDepth = std::max( r.maxDepth, depth );
-	const Node n = Decode( nodes + (size_t)idx * 80 );
-	int inner = 0;
+	const Node n = Decode( nodes + (size_t)idx * NODE_BYTES );
+	if (n.imask & n.lmask) fail( 3 );
 	for (int s = 0; s < 8; s++)
 	{
-		const uint8_t m = n.meta[s];
-		const bool isInner = (n.imask >> s) & 1;
-		if (m == 0) { if (isInner) fail( 3 ); r.emptySlots++; continue; }
+		const bool isInner = (n.imask >> s) & 1, isLeaf = (n.lmask >> s) & 1;
 		float clo[3], chi[3], blo[3], bhi[3];
 		ChildBox( n, s, blo, bhi );
+		if (!isInner && !isLeaf)
+		{
+			// empty slot: must reject every ray by itself (lo far above hi on every axis)
+			for (int a = 0; a < 3; a++) if (!(n.lo[a][s] > 1e37f && n.hi[a][s] < -1e37f)) fail( 4 );
+			r.emptySlots++;
+			continue;
+		}
 		if (isInner)
 		{
-			if (m != (uint8_t)((1 << 5) | (24 + s))) fail( 4 );	// internal: 0b001_11000 | slot
 			r.innerSlots++;
-			CheckNode( nodes, nNodes, tris, nTris, verts4, triCount, nodeSeen, primSeen, recSeen, (int)n.childBase + inner, depth + 1, clo, chi, r );
-			inner++;
+			CheckNode( nodes, nNodes, tris, nTris, verts4, triCount, nodeSeen, primSeen, recSeen, (int)n.childBase + Rank( n.imask, s ), depth + 1, clo, chi, r );
 		}
 		else
 		{
-			const int unary = m >> 5, first = m & 31, count = unary == 1 ? 1 : (unary == 3 ? 2 : (unary == 7 ? 3 : -1));
-			if (count < 0 || first + count > 24) { fail( 5 ); continue; }
 			r.leafSlots++;
 			for (int a = 0; a < 3; a++) clo[a] = 3e38f, chi[a] = -3e38f;
-			for (int k = 0; k < count; k++)
+			const int rec = (int)n.triBase + Rank( n.lmask, s );	// exactly one triangle per leaf slot
+			if (rec < 0 || rec >= nTris) { fail( 6 ); continue; }
+			if (recSeen[rec]++) fail( 7 );
+			r.trisVisited++;
+			const float* t = tris + (size_t)rec * 12;
+			int prim; memcpy( &prim, t + 3, 4 );
+			if (prim < 0 || prim >= triCount) { fail( 8 ); continue; }
+			primSeen[prim]++;
+			const float* v = verts4 + (size_t)prim * 12;
+			for (int a = 0; a < 3; a++)
 			{
-				const int rec = (int)n.triBase + first + k;
-				if (rec < 0 || rec >= nTris) { fail( 6 ); continue; }
-				if (recSeen[rec]++) fail( 7 );
-				r.trisVisited++;
-				const float* t = tris + (size_t)rec * 12;
-				int prim; memcpy( &prim, t + 3, 4 );
-				if (prim < 0 || prim >= triCount) { fail( 8 ); continue; }
-				primSeen[prim]++;
-				const float* v = verts4 + (size_t)prim * 12;
-				for (int a = 0; a < 3; a++)
-				{
-					// the record is the Moeller-Trumbore form of exactly this triangle
-					if (t[a] != v[a] || t[4 + a] != v[4 + a] - v[a] || t[8 + a] != v[8 + a] - v[a]) fail( 9 );
-					clo[a] = std::min( clo[a], std::min( v[a], std::min( v[4 + a], v[8 + a] ) ) );
-					chi[a] = std::max( chi[a], std::max( v[a], std::max( v[4 + a], v[8 + a] ) ) );
-				}
+				// the record is the Moeller-Trumbore form of exactly this triangle
+				if (t[a] != v[a] || t[4 + a] != v[4 + a] - v[a] || t[8 + a] != v[8 + a] - v[a]) fail( 9 );
+				clo[a] = std::min( clo[a], std::min( v[a], std::min( v[4 + a], v[8 + a] ) ) );
+				chi[a] = std::max( chi[a], std::max( v[a], std::max( v[4 + a], v[8 + a] ) ) );
 			}
 		}
-		// conservative quantisation: the decoded box of the slot contains everything below it
+		// conservative encoding: the decoded box of the slot contains everything below it
 		for (int a = 0; a < 3; a++) if (clo[a] <= chi[a] && (blo[a] > clo[a] || bhi[a] < chi[a])) fail( 10 );
 		for (int a = 0; a < 3; a++) lo[a] = std::min( lo[a], clo[a] ), hi[a] = std::max( hi[a], chi[a] );
 	}
@@ -151,27 +161,20 @@ static inline bool ClosestHit( const uint8_t* nodes, const float* tris, const fl
 	stack[sp++] = 0;
 	while (sp > 0)
 	{
-		const Node n = Decode( nodes + (size_t)stack[--sp] * 80 );
-		int inner = 0;
+		const Node n = Decode( nodes + (size_t)stack[--sp] * NODE_BYTES );
 		for (int s = 0; s < 8; s++)
 		{
-			const uint8_t m = n.meta[s];
-			if (m == 0) continue;
-			const bool isInner = (n.imask >> s) & 1;
+			const bool isInner = (n.imask >> s) & 1, isLeaf = (n.lmask >> s) & 1;
+			if (!isInner && !isLeaf) continue;
 			float lo[3], hi[3];
 			ChildBox( n, s, lo, hi );
-			const bool hit = SlabHit( lo, hi, O, invD, 0.0f, best.t );
-			if (isInner) { if (hit && sp < 255) stack[sp++] = (int)n.childBase + inner; inner++; continue; }
-			if (!hit) continue;
-			const int unary = m >> 5, first = m & 31, count = unary == 1 ? 1 : (unary == 3 ? 2 : 3);
-			for (int k = 0; k < count; k++)
-			{
-				const float* t = tris + (size_t)(n.triBase + first + k) * 12;
-				float tt, u, v;
-				if (!RecordTest( O, D, t, tt, u, v ) || !(tt > 0.0f)) continue;
-				int prim; memcpy( &prim, t + 3, 4 );
-				if (tt < best.t || (tt == best.t && best.prim >= 0 && prim < best.prim)) best.t = tt, best.u = u, best.v = v, best.inst = 0, best.prim = prim;
-			}
+			if (!SlabHit( lo, hi, O, invD, 0.0f, best.t )) continue;
+			if (isInner) { if (sp < 255) stack[sp++] = (int)n.childBase + Rank( n.imask, s ); continue; }
+			const float* t = tris + (size_t)(n.triBase + Rank( n.lmask, s )) * 12;
+			float tt, u, v;
+			if (!RecordTest( O, D, t, tt, u, v ) || !(tt > 0.0f)) continue;
+			int prim; memcpy( &prim, t + 3, 4 );
+			if (tt < best.t || (tt == best.t && best.prim >= 0 && prim < best.prim)) best.t = tt, best.u = u, best.v = v, best.inst = 0, best.prim = prim;
 		}
 	}
 	return best.prim >= 0;
