@@ -41,7 +41,7 @@ LH2B_API int lh2b_set_target( lh2b_core* core, int width, int height, int spp );
                                     maxPathLength (1..LH2B_MAXPATHLENGTH, default 3 = MAXPATHLENGTH), maxDiffuseBounces (1 = ENOUGH_BOUNCES
                                     S_BOUNCED default, 2, 0 = unlimited), bsdf (0 lambert.h model, 1 principled model of disney.h)
      acceleration structure         bvhBuilder (0 GPU PLOC default, 1 host binned SAH, 2 GPU LBVH), bvhRefit (1 in-place refit default, 2 refit +
-                                    re-collapse, 0 rebuild), plocRadius (1..64, default 8),
+                                    re-collapse, 0 rebuild), plocRadius (1..64, default 8), bvhCollapse (1 SAH-optimal collapse to 8-wide, default; 0 greedy),
                                     l2Persist (1 default: persisting-L2 window over the node arena)
      frame scheduling               pipeline (1: Render( async ) enqueues frame k+1 behind frame k; statistics lag one frame),
                                     gatherMode (read by lh2b_gather_create: 0 root gather default, 1 reduce-scatter),

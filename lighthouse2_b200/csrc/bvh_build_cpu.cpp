@@ -1,4 +1,4 @@
-/* bvh_build_cpu.cpp - host-side BVH construction: binned-SAH binary build (one primitive per leaf), greedy collapse
+/* bvh_build_cpu.cpp - host-side BVH construction: binned-SAH binary build (one primitive per leaf), SAH-optimal collapse
    to 8-wide, node encoding (bvh.h).
 
    Replaces optixAccelBuild (reference call sites: lib/rendercore_optix7/core_mesh.cpp:105,123 for
@@ -213,28 +213,60 @@ void CollapseToCwBvh( const std::vector<Bvh2Node>& bvh2v, const std::vector<uint
 		}
 		else out.leafIds.push_back( prim );
 	};
+	// SAH-optimal collapse (same dynamic program as bvh_gpu.cu fitKernel; children are allocated after their parent, so a
+	// descending sweep sees children first): T[n][i] = cheapest way to present subtree n as at most i slots, split[n][i-1] = the
+	// number of slots the left child gets (0: T[n][i-1] kept), split[n][7] = the same for the node's own eight slots
+	const float SAH_NODE = 1.0f, SAH_LEAF = 0.3f;
+	std::vector<float> T( bvh2v.size() * 7 );
+	std::vector<uint8_t> split( bvh2v.size() * 8, 0 );
+	for (int i = (int)bvh2v.size() - 1; i >= 0; i--)
+	{
+		const Bvh2Node& nd = bvh2[i];
+		if (IsLeaf( nd )) { for (int k = 0; k < 7; k++) T[(size_t)i * 7 + k] = HalfArea( nd.lo, nd.hi ) * SAH_LEAF; continue; }
+		const float* tl = &T[(size_t)nd.left * 7], * tr = &T[(size_t)nd.right * 7];
+		float d[9];
+		uint8_t dk[9];
+		for (int j = 2; j <= 8; j++)
+		{
+			float best = 3e38f;
+			int bk = 1;
+			for (int k = std::max( 1, j - 7 ); k <= std::min( 7, j - 1 ); k++)
+			{
+				const float v = tl[k - 1] + tr[j - k - 1];
+				if (v < best) best = v, bk = k;
+			}
+			d[j] = best, dk[j] = (uint8_t)bk;
+		}
+		float* t = &T[(size_t)i * 7];
+		uint8_t* sp = &split[(size_t)i * 8];
+		t[0] = HalfArea( nd.lo, nd.hi ) * SAH_NODE + d[8], sp[0] = 0, sp[7] = dk[8];
+		for (int k = 2; k <= 7; k++)
+		{
+			if (d[k] < t[k - 2]) t[k - 1] = d[k], sp[k - 1] = dk[k];
+			else t[k - 1] = t[k - 2], sp[k - 1] = 0;
+		}
+	}
 	while (head < queue.size())
 	{
 		const Task task = queue[head++];
 		const Bvh2Node& root = bvh2[task.bvh2Node];
-		// gather up to 8 children by repeatedly opening the internal child with the largest area
+		// the node's children: unfold the choices of the dynamic program - (binary node, slots granted) pairs until each is one slot
 		int child[8], n = 0;
 		if (IsLeaf( root )) { if (root.right > 0) child[n++] = task.bvh2Node; }	// (an empty mesh is one node without children)
 		else
 		{
-			child[n++] = root.left, child[n++] = root.right;
-			while (n < 8)
+			int stackNode[8], stackSlots[8], sp = 0;
+			const int k8 = split[(size_t)task.bvh2Node * 8 + 7];
+			stackNode[sp] = root.right, stackSlots[sp++] = 8 - k8, stackNode[sp] = root.left, stackSlots[sp++] = k8;
+			while (sp > 0)
 			{
-				float bestA = -1;
-				int bi = -1;
-				for (int i = 0; i < n; i++) if (!IsLeaf( bvh2[child[i]] ))
-				{
-					const float a = HalfArea( bvh2[child[i]].lo, bvh2[child[i]].hi );
-					if (a > bestA) bestA = a, bi = i;
-				}
-				if (bi < 0) break;
-				const Bvh2Node& open = bvh2[child[bi]];
-				child[bi] = open.left, child[n++] = open.right;
+				const int nd = stackNode[--sp];
+				int slots = stackSlots[sp];
+				if (IsLeaf( bvh2[nd] )) { child[n++] = nd; continue; }
+				while (slots > 1 && split[(size_t)nd * 8 + slots - 1] == 0) slots--;
+				if (slots == 1) { child[n++] = nd; continue; }
+				const int k = split[(size_t)nd * 8 + slots - 1];
+				stackNode[sp] = bvh2[nd].right, stackSlots[sp++] = slots - k, stackNode[sp] = bvh2[nd].left, stackSlots[sp++] = k;
 			}
 		}
 		int slotOf[8];

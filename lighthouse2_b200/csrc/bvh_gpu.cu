@@ -43,6 +43,8 @@ struct GpuBuildScratch
 	DevBuf<int> parent;						// per binary node
 	DevBuf<uint32_t> visit;					// per internal node arrival counter
 	DevBuf<BuildTask> queue;
+	DevBuf<float> dpCost;					// per internal node: T[1..7] of the optimal collapse (see fitKernel)
+	DevBuf<uint8_t> dpSplit;				// per internal node: the choice behind T[1..7] and behind the node's own 8 slots
 	DevBuf<uint32_t> ctrl;					// [0] node counter, [1] leaf counter, [2] queue tail, [3..8] scene box as ordered ints, [9] error flag
 };
 
@@ -186,9 +188,22 @@ __global__ void radixTreeKernel( const uint64_t* __restrict__ keys, const int n,
 	if (i == 0) parent[0] = -1;
 }
 
-/* stage 5: leaf boxes from the (possibly updated) primitive boxes, parents bottom-up */
+/* stage 5: leaf boxes from the (possibly updated) primitive boxes, parents bottom-up.
+
+   With dpCost / dpSplit the same bottom-up sweep also fills the tables of the SAH-optimal collapse to 8-wide nodes (the dynamic
+   program of Ylitie, Karras, Laine 2017, section 3.2, restated for nodes whose leaf slots hold one primitive): for a binary node n
+     T[n][i]  = cheapest way to present the subtree of n to a parent as at most i slots          (i = 1..7)
+     D[n][j]  = min over k of T[left][k] + T[right][j - k]                                        (both sides get a slot)
+     T[n][1]  = area( n ) * LH2B_SAH_NODE + D[n][8]      - n becomes a wide node and fills its own eight slots
+     T[n][i]  = min( T[n][i - 1], D[n][i] )
+     T[leaf][i] = area( leaf ) * LH2B_SAH_LEAF
+   dpSplit[n][i - 1] (i = 2..7) = the k behind T[n][i], 0 if T[n][i - 1] was kept; dpSplit[n][7] = the k of the node's own slots.
+   collapseKernel then unfolds the choices top-down instead of opening the largest child greedily. */
+#define LH2B_SAH_NODE 1.0f
+#define LH2B_SAH_LEAF 0.3f
 __global__ void fitKernel( const float4* __restrict__ primLo, const float4* __restrict__ primHi, const uint32_t* __restrict__ idx, const int n,
-	const int2* __restrict__ children, const int* __restrict__ parent, uint32_t* __restrict__ visit, float4* __restrict__ nodeLo, float4* __restrict__ nodeHi )
+	const int2* __restrict__ children, const int* __restrict__ parent, uint32_t* __restrict__ visit, float4* __restrict__ nodeLo, float4* __restrict__ nodeHi,
+	float* __restrict__ dpCost, uint8_t* __restrict__ dpSplit )
 {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
@@ -197,6 +212,11 @@ __global__ void fitKernel( const float4* __restrict__ primLo, const float4* __re
 	float4 lo = primLo[p], hi = primHi[p];
 	nodeLo[node] = lo, nodeHi[node] = hi;
 	if (n == 1) return;
+	float tCur[7];	// T[node][1..7] of the node this thread carries upwards
+	{
+		const float ex = hi.x - lo.x, ey = hi.y - lo.y, ez = hi.z - lo.z, leaf = (ex * ey + ey * ez + ez * ex) * LH2B_SAH_LEAF;
+		for (int k = 0; k < 7; k++) tCur[k] = leaf;
+	}
 	int cur = parent[node];
 	while (cur >= 0)
 	{
@@ -205,6 +225,45 @@ __global__ void fitKernel( const float4* __restrict__ primLo, const float4* __re
 		const int2 c = children[cur];
 		const int other = c.x == node ? c.y : c.x;
 		const float4 olo = __ldcg( nodeLo + other ), ohi = __ldcg( nodeHi + other );	// written by another SM: bypass L1
+		if (dpCost)
+		{
+			float tOther[7];
+			if (other >= n - 1)
+			{
+				const float ex = ohi.x - olo.x, ey = ohi.y - olo.y, ez = ohi.z - olo.z, leaf = (ex * ey + ey * ez + ez * ex) * LH2B_SAH_LEAF;
+				for (int k = 0; k < 7; k++) tOther[k] = leaf;
+			}
+			else for (int k = 0; k < 7; k++) tOther[k] = __ldcg( dpCost + (size_t)other * 7 + k );
+			const bool nodeIsLeft = c.x == node;
+			const float* tl = nodeIsLeft ? tCur : tOther;
+			const float* tr = nodeIsLeft ? tOther : tCur;
+			float d[9];
+			uint8_t dk[9];
+			for (int j = 2; j <= 8; j++)
+			{
+				float best = 3e38f;
+				int bk = 1;
+				for (int k = (j - 7 > 1 ? j - 7 : 1); k <= (j - 1 < 7 ? j - 1 : 7); k++)
+				{
+					const float v = tl[k - 1] + tr[j - k - 1];
+					if (v < best) best = v, bk = k;
+				}
+				d[j] = best, dk[j] = (uint8_t)bk;
+			}
+			const float ulx = fminf( lo.x, olo.x ), uly = fminf( lo.y, olo.y ), ulz = fminf( lo.z, olo.z );
+			const float uhx = fmaxf( hi.x, ohi.x ), uhy = fmaxf( hi.y, ohi.y ), uhz = fmaxf( hi.z, ohi.z );
+			const float ex = uhx - ulx, ey = uhy - uly, ez = uhz - ulz;
+			float tNew[7];
+			uint8_t split[8];
+			tNew[0] = (ex * ey + ey * ez + ez * ex) * LH2B_SAH_NODE + d[8], split[0] = 0, split[7] = dk[8];
+			for (int k = 2; k <= 7; k++)
+			{
+				if (d[k] < tNew[k - 2]) tNew[k - 1] = d[k], split[k - 1] = dk[k];
+				else tNew[k - 1] = tNew[k - 2], split[k - 1] = 0;
+			}
+			for (int k = 0; k < 7; k++) dpCost[(size_t)cur * 7 + k] = tNew[k], tCur[k] = tNew[k];
+			*(uint2*)(dpSplit + (size_t)cur * 8) = make_uint2( split[0] | (split[1] << 8) | (split[2] << 16) | (split[3] << 24), split[4] | (split[5] << 8) | (split[6] << 16) | (split[7] << 24) );
+		}
 		lo = make_float4( fminf( lo.x, olo.x ), fminf( lo.y, olo.y ), fminf( lo.z, olo.z ), 0 );
 		hi = make_float4( fmaxf( hi.x, ohi.x ), fmaxf( hi.y, ohi.y ), fmaxf( hi.z, ohi.z ), 0 );
 		nodeLo[cur] = lo, nodeHi[cur] = hi;
@@ -233,6 +292,7 @@ struct CollapseArgs
 	float4* boundsOut;				// [0] = lo, [1] = hi of the root (kept on the device for the top-level build)
 	uint32_t* countsOut;			// [0] node count, [1] leaf count, [2] overflow flag
 	int* wideChild; int* wideSelf;	// BLAS: binary-tree node behind every slot of every wide node / behind the node itself (for refits)
+	const uint8_t* dpSplit;			// choices of the SAH-optimal collapse (fitKernel); null: greedy largest-area opening
 };
 
 __device__ __forceinline__ float HalfAreaD( const float4 lo, const float4 hi )
@@ -248,6 +308,27 @@ __device__ void CollapseTask( const CollapseArgs& a, const BuildTask task )
 	int child[8], cnt = 0;
 	const int root = task.bvh2Node;
 	if (leafLike( root )) child[cnt++] = root;
+	else if (a.dpSplit)
+	{
+		// unfold the dynamic program: (binary node, slots granted) pairs until every pair is one slot
+		int stackNode[8], stackSlots[8], sp = 0;
+		{
+			const int2 c = a.children[root];
+			const int k = a.dpSplit[(size_t)root * 8 + 7];
+			stackNode[sp] = c.y, stackSlots[sp++] = 8 - k, stackNode[sp] = c.x, stackSlots[sp++] = k;
+		}
+		while (sp > 0)
+		{
+			const int nd = stackNode[--sp];
+			int slots = stackSlots[sp];
+			if (leafLike( nd )) { child[cnt++] = nd; continue; }
+			while (slots > 1 && a.dpSplit[(size_t)nd * 8 + slots - 1] == 0) slots--;
+			if (slots == 1) { child[cnt++] = nd; continue; }	// stays a wide node of its own
+			const int k = a.dpSplit[(size_t)nd * 8 + slots - 1];
+			const int2 c = a.children[nd];
+			stackNode[sp] = c.y, stackSlots[sp++] = slots - k, stackNode[sp] = c.x, stackSlots[sp++] = k;
+		}
+	}
 	else
 	{
 		const int2 c = a.children[root];
@@ -606,7 +687,10 @@ static void BuildFromBoxes( lh2b_core* core, GpuBuildScratch& s, const int n, co
 	}
 	else if (n > 1) resetVisitKernel<<<blocks, 256, 0, st>>>( s.visit.ptr, n - 1 );
 	s.nodeLo.Resize( 2 * n ), s.nodeHi.Resize( 2 * n );
-	fitKernel<<<blocks, 256, 0, st>>>( s.primLo.ptr, s.primHi.ptr, s.idxAlt.ptr, n, s.children.ptr, s.parent.ptr, s.visit.ptr, s.nodeLo.ptr, s.nodeHi.ptr );
+	const bool optimal = core->bvhCollapse == 1 && !keepWideTree && n > 1;
+	if (optimal) s.dpCost.Resize( (size_t)n * 7 ), s.dpSplit.Resize( (size_t)n * 8 );
+	fitKernel<<<blocks, 256, 0, st>>>( s.primLo.ptr, s.primHi.ptr, s.idxAlt.ptr, n, s.children.ptr, s.parent.ptr, s.visit.ptr, s.nodeLo.ptr, s.nodeHi.ptr,
+		optimal ? s.dpCost.ptr : nullptr, optimal ? s.dpSplit.ptr : nullptr );
 	if (keepWideTree)
 	{
 		requantKernel<<<(wideNodes + 127) / 128, 128, 0, st>>>( wideNodes, args.wideChild, args.wideSelf, s.nodeLo.ptr, s.nodeHi.ptr,
@@ -616,7 +700,7 @@ static void BuildFromBoxes( lh2b_core* core, GpuBuildScratch& s, const int n, co
 	}
 	s.queue.Resize( (size_t)n + 8 );
 	args.n = n, args.children = s.children.ptr, args.subtree = s.subtree.ptr, args.nodeLo = s.nodeLo.ptr, args.nodeHi = s.nodeHi.ptr;
-	args.idx = s.idxAlt.ptr, args.queue = s.queue.ptr, args.ctrl = s.ctrl.ptr;
+	args.idx = s.idxAlt.ptr, args.queue = s.queue.ptr, args.ctrl = s.ctrl.ptr, args.dpSplit = optimal ? s.dpSplit.ptr : nullptr;
 	void* params[] = { &args };
 	CUDA_CHECK( cudaLaunchCooperativeKernel( (void*)collapseKernel, dim3( CollapseGrid( core ) ), dim3( 128 ), params, 0, st ) );
 }

@@ -89,6 +89,7 @@ struct lh2b_core
 	void* gpuBuild = nullptr;				// GpuBuildScratch (bvh_gpu.cu)
 	lh2b::DevBuf<uint8_t> instBuildIn;		// per-frame top-level build input
 	lh2b::DevBuf<uint32_t> linkedRoots;
+	int bvhCollapse = 1;	// 1: SAH-optimal collapse to 8-wide (dynamic program), 0: greedy largest-area opening
 	int plocRadius = 8;	// swept on the 1M-triangle terrain (tools/quality_sweep.py)
 	struct lh2b_gather* gather = nullptr;		// attached multi-GPU gather (gather.cu): frames end with a snapshot for it instead of the local finalize
 	int bandY0 = 0, bandY1 = 0, bandStep = 1;	// rows this core renders (lh2b_set_row_band[_strided]; 0, 0 = the whole frame)

@@ -385,6 +385,7 @@ int lh2b_setting( lh2b_core* core, const char* name, float value )
 	else if (!strcmp( name, "maxDiffuseBounces" )) core->enoughBounces = value <= 0 ? 0 : (value < 2 ? S_BOUNCED : S_BOUNCEDTWICE);
 	else if (!strcmp( name, "bvhBuilder" )) core->bvhBuilder = (int)value;	// 0: GPU PLOC (default), 1: host binned SAH, 2: GPU LBVH
 	else if (!strcmp( name, "bvhRefit" )) core->bvhRefit = (int)value;
+	else if (!strcmp( name, "bvhCollapse" )) core->bvhCollapse = value > 0 ? 1 : 0;
 	else if (!strcmp( name, "plocRadius" )) core->plocRadius = value < 1 ? 1 : (value > 64 ? 64 : (int)value);
 	else if (!strcmp( name, "wideBlocksPerSM" )) g_wideBlocksPerSM = value < 1 ? 1 : (int)value;
 	else if (!strcmp( name, "triThreshold" )) g_triThreshold = (int)value;
