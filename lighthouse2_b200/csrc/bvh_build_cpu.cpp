@@ -285,7 +285,7 @@ void CollapseToCwBvh( const std::vector<Bvh2Node>& bvh2v, const std::vector<uint
 		for (int s = 0; s < 8; s++) internalCount += (imask >> s) & 1;
 		const uint32_t childBase = (uint32_t)out.nodes.size();
 		const uint32_t triBase = (uint32_t)(verts4 ? out.tris.size() : out.leafIds.size());
-		node.w[3] = imask | (lmask << 8), node.w[4] = childBase + nodeOffset, node.w[5] = triBase + triOffset;
+		node.w[4] = childBase + nodeOffset, node.w[5] = triBase + triOffset, node.w[6] = imask | (lmask << 8);
 		float clo[8][3] = {}, chi[8][3] = {};
 		int nextInternal = 0;
 		for (int s = 0; s < 8; s++)

@@ -12,7 +12,7 @@
      4. radixTreeKernel ...... Karras' binary radix tree over the sorted codes (ties broken by index)
      5. fitKernel ............ leaf boxes, then parents bottom-up (second arrival continues)            = refit
      6. collapseKernel ....... persistent cooperative kernel, one BFS level per grid.sync(): each task turns one binary
-                               subtree root into one 128-byte wide node (<= 8 children, octant slots, bfloat16 child planes),
+                               subtree root into one 80-byte wide node (<= 8 children, octant slots, 8-bit child planes),
                                emits leaf triangles in Moeller-Trumbore form and queues the internal children.
    Encoding rules are identical to the host builder (bvh_build_cpu.cpp); both are checked against the brute-force oracle.
 */
@@ -433,8 +433,8 @@ __device__ void CollapseTask( const CollapseArgs& a, const BuildTask task )
 	}
 	uint32_t w[CW_NODE_WORDS];
 	const float nlo[3] = { rlo.x, rlo.y, rlo.z }, nhi[3] = { rhi.x, rhi.y, rhi.z };
+	w[4] = a.nodeOffset + childBase, w[5] = a.triOffset + leafBase, w[6] = imask | (lmask << 8), w[7] = 0;
 	CwEncodePlanes( w, nlo, nhi, clo, chi, imask | lmask );
-	w[3] = imask | (lmask << 8), w[4] = a.nodeOffset + childBase, w[5] = a.triOffset + leafBase, w[6] = w[7] = 0;
 	uint4* out = a.outNodes + (size_t)(a.nodeOffset + task.cwNode) * CW_NODE_QUADS;
 	for (int k = 0; k < CW_NODE_QUADS; k++) out[k] = make_uint4( w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3] );
 }
@@ -488,9 +488,11 @@ __global__ void __launch_bounds__( 128 ) requantKernel( const int nodeCount, con
 	uint4* out = outNodes + (size_t)i * CW_NODE_QUADS;
 	uint32_t w[CW_NODE_WORDS];
 	const float nlo[3] = { rlo.x, rlo.y, rlo.z }, nhi[3] = { rhi.x, rhi.y, rhi.z };
+	const uint4 keep = out[1];	// childBase, triBase and the slot masks stay
+	w[6] = keep.z;
 	CwEncodePlanes( w, nlo, nhi, clo, chi, valid );
-	const uint4 keep = out[0];	// slot masks stay; childBase / triBase (out[1]) are not touched
-	out[0] = make_uint4( w[0], w[1], w[2], keep.w );
+	out[0] = make_uint4( w[0], w[1], w[2], w[3] );
+	out[1] = make_uint4( keep.x, keep.y, w[6], keep.w );
 	for (int k = 2; k < CW_NODE_QUADS; k++) out[k] = make_uint4( w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3] );
 }
 

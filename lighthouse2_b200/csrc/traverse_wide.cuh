@@ -14,18 +14,19 @@
       the deferred-triangle stack in local memory.
 
    Round 2 (profiles/r1_v4_kernels_full.txt read again): the node step was 282 warp instructions, 2/3 of them on the ALU pipe,
-   which issues at half rate - ALU pipe 68 % busy, FMA pipe 28 %, math-pipe-throttle stalls; the kernel was ALU-pipe bound, not
-   "issue bound". 48 of those instructions were byte->float PRMTs and ~50 assembled the hit mask with per-child variable shifts.
-   The node format was therefore redesigned around the instruction stream (bvh.h):
-   4. child planes are bfloat16 offsets: decoding is free (odd slots) or one shift (even slots); no exponents, no bias
-      correction; near / far planes are picked with one SEL per word (two children);
+   which issues at half rate - ALU pipe 68 % busy, FMA pipe 28 %, math-pipe-throttle stalls: ALU-pipe bound, not "issue bound".
+   ~50 of those instructions assembled the hit mask with per-child variable shifts, ~30 decoded exponents and folded the bias.
+   A first redesign (128-byte nodes, bfloat16 planes, decoding for free: profiles/r2_v5_*) cut the instructions by 20 % and moved
+   the limit to the L1 data pipe (83 % busy: divergent lanes get 16 bytes per unique address per cycle, so bytes per node step
+   are cycles) at unchanged speed. The format kept (bvh.h) stays at 80 bytes and spends its instructions where they are cheap:
+   4. origin pre-biased and spacings stored as floats by the builder: the per-node set-up is 3 masks / shifts, 6 FMUL, 3 FADD;
+      each plane byte becomes a float with one PRMT (byte dropped into the mantissa of 65536.0f), folded into the slab FFMA;
    5. the three per-child rejections (slab empty, behind tmax, behind the origin) are three values whose SIGN bits are OR-ed and
       shifted into an 8-bit miss mask with one funnel shift per child - differences and the far-side padding run on the FMA pipe
       (FFMA / FADD), only the two 3-input min / max per child stay on the ALU pipe;
    6. one triangle per leaf slot: the hit mask is 8 bits in slot order, AND-ed with the node's internal / leaf masks; the
       front-to-back choice among hit children is one shared-memory table look-up per pop (octant x mask -> slot);
-   7. a node is one aligned 128-byte line fetched with four 256-bit loads (LDG.E.256): 4 sector requests per node instead of 5
-      requests over 3-4 sectors.
+   7. box padding against the triangle test's rounding is applied once by the builder, not per node step.
 
    Closest-hit order independence (tie-break on (instance, primitive)) is what makes deferring legal: the result does not depend
    on the order in which triangles are tested.
@@ -43,11 +44,19 @@ namespace lh2b
 #define WIDE_TRI_THRESHOLD 1	// lanes with pending triangles that trigger a triangle step
 #define WIDE_REFILL_THRESHOLD 8	// idle lanes that trigger fetching new rays
 
-/* one 32-byte sector with a single 256-bit load (sm_100+); the data is read-only for the whole launch */
-__device__ __forceinline__ void LoadSector( const void* p, uint32_t (&r)[8] )
+/* 0x47800000 = 65536.0f; dropping a byte into mantissa bits 8..15 gives exactly 65536 + 2 * byte. 'base' holds the
+   constant in a register (see OpaqueBase) so that the selector can be the instruction's immediate: one PRMT per plane. */
+template <int J> __device__ __forceinline__ float ByteFloat( const uint32_t word, const uint32_t base )
 {
-	asm( "ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-		: "=r"( r[0] ), "=r"( r[1] ), "=r"( r[2] ), "=r"( r[3] ), "=r"( r[4] ), "=r"( r[5] ), "=r"( r[6] ), "=r"( r[7] ) : "l"( p ) );
+	uint32_t r;
+	asm( "prmt.b32 %0, %1, %2, %3;" : "=r"( r ) : "r"( word ), "r"( base ), "n"( 0x7604 | (J << 4) ) );
+	return __uint_as_float( r );
+}
+__device__ __forceinline__ uint32_t OpaqueBase()
+{
+	uint32_t k;
+	asm volatile( "mov.b32 %0, 0x47800000;" : "=r"( k ) );	// volatile: the optimiser must not fold it back into an immediate
+	return k;
 }
 
 struct WideRay
@@ -101,7 +110,8 @@ __device__ __forceinline__ void TraverseWide( const DevScene& scene, RaySource& 
 	FillPopTable( popTable );
 	__syncthreads();
 	const uint32_t lane = threadIdx.x & 31;
-	const char* __restrict__ nodes = (const char*)scene.nodes;
+	const uint4* __restrict__ nodes = scene.nodes;
+	const uint32_t fbase = OpaqueBase();
 	const float4* __restrict__ tris = scene.tris;
 	const uint32_t NO_INST = 0xffffffffu;
 	// lane state
@@ -299,36 +309,37 @@ __device__ __forceinline__ void TraverseWide( const DevScene& scene, RaySource& 
 			ng.y = hits & ~(0x01000000u << slot);
 			if (ng.y > 0x00ffffffu) WIDE_PUSH( ng );
 			const uint32_t rel = __popc( hits & 0xffu & ((1u << slot) - 1u) );
-			const char* np = nodes + (size_t)(ng.x + rel) * 128;
-			uint32_t h[8], px[8], py[8], pz[8];
-			LoadSector( np, h ), LoadSector( np + 32, px ), LoadSector( np + 64, py ), LoadSector( np + 96, pz );
+			const uint4* np = nodes + (size_t)(ng.x + rel) * 5;
+			const uint4 n0 = __ldg( np ), n1 = __ldg( np + 1 ), n2 = __ldg( np + 2 ), n3 = __ldg( np + 3 ), n4 = __ldg( np + 4 );
+			// t( q ) = ( pb + (32768 + q) * 2^e - o ) * idir = f * h + c,  f = 65536 + 2q (ByteFloat), h = 2^(e-1) * idir, c = (pb - o) * idir
+			const float hx = __uint_as_float( n0.w & 0xffff0000u ) * idx, hy = __uint_as_float( n0.w << 16 ) * idy, hz = __uint_as_float( n1.z & 0xffff0000u ) * idz;
+			const float cx = (__uint_as_float( n0.x ) - O.x) * idx, cy = (__uint_as_float( n0.y ) - O.y) * idy, cz = (__uint_as_float( n0.z ) - O.z) * idz;
 			const bool negx = !(octinv & 4), negy = !(octinv & 2), negz = !(octinv & 1);
-			// t( plane ) = ( pmin + offset - o ) * idir = offset * idir + c
-			const float cx = (__uint_as_float( h[0] ) - O.x) * idx, cy = (__uint_as_float( h[1] ) - O.y) * idy, cz = (__uint_as_float( h[2] ) - O.z) * idz;
 			uint32_t miss = 0;
 #pragma unroll
-			for (int k = 3; k >= 0; k--)
+			for (int half = 1; half >= 0; half--)
 			{
-				// words k hold slots 2k (low half) and 2k + 1; near = the plane the ray meets first on that axis
-				const uint32_t nx = negx ? px[4 + k] : px[k], fx = negx ? px[k] : px[4 + k];
-				const uint32_t ny = negy ? py[4 + k] : py[k], fy = negy ? py[k] : py[4 + k];
-				const uint32_t nz = negz ? pz[4 + k] : pz[k], fz = negz ? pz[k] : pz[4 + k];
-#pragma unroll
-				for (int odd = 1; odd >= 0; odd--)
-				{
-#define WIDE_OFFSET( w ) __uint_as_float( odd ? (w) : (w) << 16 )
-					const float t0x = fmaf( WIDE_OFFSET( nx ), idx, cx ), t1x = fmaf( WIDE_OFFSET( fx ), idx, cx );
-					const float t0y = fmaf( WIDE_OFFSET( ny ), idy, cy ), t1y = fmaf( WIDE_OFFSET( fy ), idy, cy );
-					const float t0z = fmaf( WIDE_OFFSET( nz ), idz, cz ), t1z = fmaf( WIDE_OFFSET( fz ), idz, cz );
-#undef WIDE_OFFSET
-					const float cmin = fmaxf( fmaxf( t0x, t0y ), t0z ), cmax = fminf( fminf( t1x, t1y ), t1z );
-					// miss <=> the slab interval is empty (far side padded by a few ulp: this arithmetic differs from the exact
-					// triangle test), or starts behind tmax, or ends behind the origin: the OR of three sign bits
-					const float d1 = fmaf( cmax, 1.0000005f, -cmin ), d2 = tmax - cmin;
-					const uint32_t sign = __float_as_uint( d1 ) | __float_as_uint( d2 ) | __float_as_uint( cmax );
-					miss = __funnelshift_l( sign, miss, 1 );	// slots arrive 7, 6, .. 0: slot s ends up in bit s
-				}
+				// plane words: qlo x n2.xy, y n2.zw, z n3.xy; qhi x n3.zw, y n4.xy, z n4.zw (slots 0-3, 4-7); near = the plane the ray meets first
+				const uint32_t qlox = half ? n2.y : n2.x, qloy = half ? n2.w : n2.z, qloz = half ? n3.y : n3.x;
+				const uint32_t qhix = half ? n3.w : n3.z, qhiy = half ? n4.y : n4.x, qhiz = half ? n4.w : n4.z;
+				const uint32_t nx = negx ? qhix : qlox, fx = negx ? qlox : qhix;
+				const uint32_t ny = negy ? qhiy : qloy, fy = negy ? qloy : qhiy;
+				const uint32_t nz = negz ? qhiz : qloz, fz = negz ? qloz : qhiz;
+#define WIDE_CHILD( J ) { \
+				const float t0x = fmaf( ByteFloat<J>( nx, fbase ), hx, cx ), t1x = fmaf( ByteFloat<J>( fx, fbase ), hx, cx ); \
+				const float t0y = fmaf( ByteFloat<J>( ny, fbase ), hy, cy ), t1y = fmaf( ByteFloat<J>( fy, fbase ), hy, cy ); \
+				const float t0z = fmaf( ByteFloat<J>( nz, fbase ), hz, cz ), t1z = fmaf( ByteFloat<J>( fz, fbase ), hz, cz ); \
+				const float cmin = fmaxf( fmaxf( t0x, t0y ), t0z ), cmax = fminf( fminf( t1x, t1y ), t1z ); \
+				/* miss <=> the slab interval is empty (far side padded by a few ulp: this arithmetic differs from the exact triangle \
+				   test), or starts behind tmax, or ends behind the origin: the OR of three sign bits */ \
+				const float d1 = fmaf( cmax, 1.0000005f, -cmin ), d2 = tmax - cmin; \
+				const uint32_t sign = __float_as_uint( d1 ) | __float_as_uint( d2 ) | __float_as_uint( cmax ); \
+				miss = __funnelshift_l( sign, miss, 1 ); }	/* slots arrive 7, 6, .. 0: slot s ends up in bit s */
+				WIDE_CHILD( 3 ) WIDE_CHILD( 2 ) WIDE_CHILD( 1 ) WIDE_CHILD( 0 )
+#undef WIDE_CHILD
 			}
+			uint32_t h[8];
+			h[3] = n1.z, h[4] = n1.x, h[5] = n1.y;	// slot masks (imask | lmask << 8 in the low half), childBase, triBase
 			const uint32_t hitInner = ~miss & h[3] & 0xffu, hitLeaf = ~miss & (h[3] >> 8) & 0xffu;
 			ng = make_uint2( h[4], (hitInner << 24) | (h[3] & 0xffu) );
 			if (hitLeaf != 0)

@@ -409,7 +409,7 @@ CWBVH_REPORT = ("nodesVisited", "trisVisited", "maxDepth", "emptySlots", "leafSl
 
 def cwbvh_check(nodes, tris, verts4):
     """Structural check of a CWBVH in the product's documented format (lh2_oracle_cwbvh.h); returns the report as a dict."""
-    nodes = np.ascontiguousarray(nodes, np.uint8).reshape(-1, 128)
+    nodes = np.ascontiguousarray(nodes, np.uint8).reshape(-1, 80)
     tris = np.ascontiguousarray(tris, np.float32).reshape(-1, 12)
     v = np.ascontiguousarray(verts4, np.float32).reshape(-1, 4)
     rep = (ctypes.c_int * 8)()
@@ -420,7 +420,7 @@ def cwbvh_check(nodes, tris, verts4):
 
 def cwbvh_closest_hits(nodes, tris, O4, D4, threads=None):
     """Closest hits through a CWBVH in the product's format, decoded and traversed by the oracle's own reader."""
-    nodes = np.ascontiguousarray(nodes, np.uint8).reshape(-1, 128)
+    nodes = np.ascontiguousarray(nodes, np.uint8).reshape(-1, 80)
     tris = np.ascontiguousarray(tris, np.float32).reshape(-1, 12)
     O4 = np.ascontiguousarray(O4, np.float32).reshape(-1, 4)
     D4 = np.ascontiguousarray(D4, np.float32).reshape(-1, 4)

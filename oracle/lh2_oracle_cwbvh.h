@@ -1,10 +1,10 @@
 /* lh2_oracle_cwbvh.h - TEST INFRASTRUCTURE ONLY. An independent CPU reader of the product's acceleration-structure format: it decodes
-   the 8-wide BVH exactly as lighthouse2_b200/csrc/bvh.h documents it (128-byte nodes: padded minimum corner, slot masks imask / lmask,
-   child / triangle base, 6 x 8 bfloat16 plane offsets where an odd slot is decoded together with its even neighbour's bits; one
-   triangle per leaf slot; 48-byte triangle records v0 / e1 / e2 + primitive index) and
+   the 8-wide compressed BVH exactly as lighthouse2_b200/csrc/bvh.h documents it (80-byte nodes: biased grid origin, three half
+   spacings stored as the upper halves of floats, slot masks imask / lmask, child / triangle base, 6 x 8 plane bytes; one triangle
+   per leaf slot; 48-byte triangle records v0 / e1 / e2 + primitive index) and
      Check:        walks the tree and verifies that it is a correct acceleration structure for the mesh - every node and every
                    triangle record reachable exactly once, records equal to the mesh triangles, every decoded child box contains
-                   everything below it (the encoding is conservative), slot masks well-formed, empty slots self-rejecting;
+                   everything below it (the quantisation is conservative), slot masks well-formed;
      ClosestHits:  traverses it with plain float slab tests (boxes padded like lh2_oracle_bvh.h) and the oracle's triangle test and
                    tie rule, so the hits must equal the exhaustive search of lh2_oracle_geom.h bit for bit.
    Used by tests/test_host_bvh_cpu.py on the output of the product's host builder (lh2b_host_bvh_build) - no GPU involved.
@@ -17,11 +17,11 @@
 namespace orcw
 {
 
-static const int NODE_BYTES = 128;
+static const int NODE_BYTES = 80;
 
 struct Node
 {
-	float p[3]; uint32_t imask, lmask, childBase, triBase; float lo[3][8], hi[3][8];	// plane OFFSETS from p, per axis and slot
+	double pb[3], spacing[3]; uint32_t imask, lmask, childBase, triBase; uint8_t qlo[3][8], qhi[3][8];
 };
 
 static inline float BitsToFloat( uint32_t u ) { float f; memcpy( &f, &u, 4 ); return f; }
@@ -29,23 +29,26 @@ static inline float BitsToFloat( uint32_t u ) { float f; memcpy( &f, &u, 4 ); re
 static inline Node Decode( const uint8_t* b )
 {
 	Node n;
-	uint32_t w[32];
-	memcpy( w, b, 128 );
-	memcpy( n.p, w, 12 );
-	n.imask = w[3] & 255u, n.lmask = (w[3] >> 8) & 255u, n.childBase = w[4], n.triBase = w[5];
-	for (int a = 0; a < 3; a++) for (int s = 0; s < 8; s++)
-	{
-		// words 8 + 8a .. : lo offsets of slots (2k, 2k+1) in word k; words 12 + 8a .. : hi offsets. Even slot: the low half moved up;
-		// odd slot: the whole word read as a float (the even neighbour's half rides along in the low mantissa bits)
-		const uint32_t wl = w[8 + a * 8 + s / 2], wh = w[12 + a * 8 + s / 2];
-		n.lo[a][s] = BitsToFloat( (s & 1) ? wl : wl << 16 ), n.hi[a][s] = BitsToFloat( (s & 1) ? wh : wh << 16 );
-	}
+	uint32_t w[20];
+	memcpy( w, b, 80 );
+	for (int a = 0; a < 3; a++) n.pb[a] = BitsToFloat( w[a] );
+	// half spacings: upper 16 bits of a float each - x in the high half of w[3], y in its low half, z in the high half of w[6]
+	n.spacing[0] = 2.0 * BitsToFloat( w[3] & 0xffff0000u ), n.spacing[1] = 2.0 * BitsToFloat( w[3] << 16 ), n.spacing[2] = 2.0 * BitsToFloat( w[6] & 0xffff0000u );
+	n.imask = w[6] & 255u, n.lmask = (w[6] >> 8) & 255u, n.childBase = w[4], n.triBase = w[5];
+	memcpy( n.qlo, b + 32, 24 ), memcpy( n.qhi, b + 56, 24 );
 	return n;
 }
 
+/* plane( q ) = pb + (32768 + q) * spacing, in double: exact for the float inputs */
 static inline void ChildBox( const Node& n, int s, float* lo, float* hi )
 {
-	for (int a = 0; a < 3; a++) lo[a] = n.p[a] + n.lo[a][s], hi[a] = n.p[a] + n.hi[a][s];
+	for (int a = 0; a < 3; a++)
+	{
+		const double l = n.pb[a] + (32768.0 + n.qlo[a][s]) * n.spacing[a], h = n.pb[a] + (32768.0 + n.qhi[a][s]) * n.spacing[a];
+		lo[a] = (float)l, hi[a] = (float)h;
+		if ((double)lo[a] > l) lo[a] = nextafterf( lo[a], -3e38f );	// round outwards: the check below must not pass by rounding
+		if ((double)hi[a] < h) hi[a] = nextafterf( hi[a], 3e38f );
+	}
 }
 
 static inline int Rank( uint32_t mask, int s ) { return __builtin_popcount( mask & ((1u << s) - 1u) ); }
@@ -70,8 +73,6 @@ static inline void CheckNode( const uint8_t* nodes, int nNodes, const float* tri
 		ChildBox( n, s, blo, bhi );
 		if (!isInner && !isLeaf)
 		{
-			// empty slot: must reject every ray by itself (lo far above hi on every axis)
-			for (int a = 0; a < 3; a++) if (!(n.lo[a][s] > 1e37f && n.hi[a][s] < -1e37f)) fail( 4 );
 			r.emptySlots++;
 			continue;
 		}

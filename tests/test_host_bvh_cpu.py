@@ -16,7 +16,7 @@ def host_bvh(verts):
     lib = capi.load_library()
     v = np.ascontiguousarray(verts, np.float32).reshape(-1, 4)
     n = v.shape[0] // 3
-    nodes, tris = np.zeros((2 * n + 8, 128), np.uint8), np.zeros((n + 8, 12), np.float32)
+    nodes, tris = np.zeros((2 * n + 8, 80), np.uint8), np.zeros((n + 8, 12), np.float32)
     counts = (ctypes.c_int * 2)()
     rc = lib.lh2b_host_bvh_build(ctypes.c_void_p(v.ctypes.data), n, ctypes.c_void_p(nodes.ctypes.data), nodes.shape[0],
                                  ctypes.c_void_p(tris.ctypes.data), tris.shape[0], counts)
@@ -59,17 +59,14 @@ def test_reader_detects_a_broken_structure():
     verts = scenes.terrain(20, 16, extent=20, seed=5).reshape(-1, 4)
     nodes, tris = host_bvh(verts)
     assert orc.cwbvh_check(nodes, tris, verts)["errors"] == 0
-    words = nodes.view(np.uint32).reshape(-1, 32)
-    slot = int(np.nonzero([(int(words[0, 3]) >> s) & 1 or (int(words[0, 3]) >> (8 + s)) & 1 for s in range(8)])[0][0])
-    bad = words.copy()
-    lane = bad[0, 12 + slot // 2]                          # hi.x word of the slot pair := lo.x word: the child's box collapses in x
-    lo_lane = bad[0, 8 + slot // 2]
-    mask = np.uint32(0xFFFF0000 if slot & 1 else 0x0000FFFF)
-    bad[0, 12 + slot // 2] = (lane & ~mask) | (lo_lane & mask)
-    assert orc.cwbvh_check(bad.view(np.uint8).reshape(-1, 128), tris, verts)["errors"] > 0
-    bad = words.copy()
-    bad[0, 3] &= ~np.uint32((1 << slot) | (1 << (8 + slot)))   # the slot is declared empty although its planes / children say otherwise
-    assert orc.cwbvh_check(bad.view(np.uint8).reshape(-1, 128), tris, verts)["errors"] > 0
+    masks = int(nodes.view(np.uint32).reshape(-1, 20)[0, 6])
+    slot = int(np.nonzero([(masks >> s) & 1 or (masks >> (8 + s)) & 1 for s in range(8)])[0][0])
+    bad = nodes.copy()
+    bad[0, 56 + slot] = bad[0, 32 + slot]                 # qhi.x := qlo.x: the child's box collapses in x
+    assert orc.cwbvh_check(bad, tris, verts)["errors"] > 0
+    bad = nodes.copy()
+    bad.view(np.uint32).reshape(-1, 20)[0, 6] &= ~np.uint32((1 << slot) | (1 << (8 + slot)))   # the slot is declared empty: what hangs below it is lost
+    assert orc.cwbvh_check(bad, tris, verts)["errors"] > 0
     t2 = tris.copy()
     t2[5, 0] += 0.25                                       # a record that is no longer the mesh's triangle
     assert orc.cwbvh_check(nodes, t2, verts)["errors"] > 0
