@@ -66,18 +66,18 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def stop(self, t0, t1):
+    def window(self, t0, t1):
+        """clock median / throttle reasons of the samples inside [t0, t1]"""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
-        self.proc.terminate()
         rows = [r for t, r in self.rows if t0 - 0.02 <= t <= t1 + 0.05]
         if not rows:      # (nvidia-smi slower than the window: the samples closest to it)
             rows = [r for _, r in sorted(self.rows, key=lambda tr: min(abs(tr[0] - t0), abs(tr[0] - t1)))[:3]]
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         for r in rows:
             try:
-                sm.append(float(r[0])), mx.append(float(r[1]))
+                sm.append(float(r[0])), mx.append(float(r[1])), pw.append(float(r[2]))
             except (ValueError, IndexError):
                 continue
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
@@ -85,7 +85,11 @@ class ClockSampler:
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "power_w_max": max(pw) if pw else None}
+
+    def close(self):
+        if self.proc is not None and self.proc.poll() is None:
+            self.proc.terminate()
 
 
 def oracle_crop_run(sd, view, crop_w, crop_h, threads):
@@ -148,28 +152,76 @@ def run_reference(args, rank, world):
         "gpu_launches": 0}))
 
 
+# Algorithmic instruction model of the traversal kernels (DESIGN.md section 3 derives it from the SASS of traverse_wide.cuh): thread
+# instructions a perfectly packed warp would need - what the work counters of a launch are multiplied with for the issue roofline.
+I_NODE = 183      # one node step: 5 LDG.128, 15 set-up, 8 x (6 PRMT + 6 FFMA + 2 FMNMX3 + FFMA + FADD + LOP3 + SHF), 12 SEL, 15 pop / push / masks
+I_TRI = 45        # one Moeller-Trumbore test: 3 LDG.128, 3 cross products, 4 dot products, reciprocal, 6 compares / selects
+I_PRIMARY = 70    # generating one primary ray (blue-noise fetches, pixel target, normalisation) and storing O4 / D4 / the hit record
+
+
+def work_counters(core, view, lights_off_sd=None):
+    """Traversal work of one frame from the counting instantiations (lh2b_trace_stats). lights_off_sd: render that frame without
+    lights (no connect launch), so that the counters describe the generate+extend kernel alone; the lights are restored."""
+    if lights_off_sd is not None:
+        core.SetLights()
+    core.Render(view, 1)
+    core.TraceStatsEnable(True)
+    core.Render(view, 1)
+    st = core.TraceStatsRead()
+    core.TraceStatsEnable(False)
+    if lights_off_sd is not None:
+        core.SetLights(lights_off_sd.tri_lights, lights_off_sd.point_lights, lights_off_sd.spot_lights, lights_off_sd.dir_lights)
+        core.Render(view, 1)
+    r = max(1, st["rays"])
+    return {"rays": st["rays"], "node_steps_per_ray": st["nodeSteps"] / r, "tri_tests_per_ray": st["triTests"] / r,
+            "warp_iterations_x32_per_ray": st["iterations"] * 32 / r, "lanes_per_node_phase": st["nodeLanes"] / max(1, st["nodePhases"]),
+            "lanes_per_tri_phase": st["triLanes"] / max(1, st["triPhases"])}
+
+
+def overrides(core):
+    for k, v in os.environ.items():             # experiments: LH2B_SET_<setting>=<value> (recorded in config.overrides)
+        if k.startswith("LH2B_SET_"):
+            core.Setting(k[9:], float(v))
+
+
 def run_ours(args, rank, world, local_rank):
     import numpy as np
     import torch
     import torch.distributed as dist
-    from lighthouse2_b200 import RenderCore
+    from lighthouse2_b200 import RenderCore, scenes
+    from lighthouse2_b200.distributed import PeerGatherRenderer, PipelinedShardedRenderer, TileShardedRenderer
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - the core has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
+    device = f"cuda:{local_rank}"
     sampler = ClockSampler(local_rank) if rank == 0 else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def reduce_max_sum(mx_vals, sum_vals):
+        if world == 1:
+            return mx_vals, sum_vals
+        t = torch.tensor(list(mx_vals) + list(sum_vals), dtype=torch.float64, device=device)
+        mx, sm = t.clone(), t.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        n = len(mx_vals)
+        return [mx[i].item() for i in range(n)], [sm[n + i].item() for i in range(len(sum_vals))]
+
+    # ================================ headline: C2 (configs[1]) =================================================================
     sd, view = build_scene()
     core = RenderCore(local_rank)
     core.SetTarget(W, H, SPP)
     core.Setting("epsilon", 1e-3)
     core.Setting("clampValue", 10.0)
     core.Setting("maxPathLength", 1)            # primary + shadow rays only
-    for k, v in os.environ.items():             # experiments: LH2B_SET_<setting>=<value> (recorded in config.overrides)
-        if k.startswith("LH2B_SET_"):
-            core.Setting(k[9:], float(v))
+    overrides(core)
     sd.upload(core)
     bvh = core.GetBvhStats(0)
-    from lighthouse2_b200.distributed import PeerGatherRenderer, PipelinedShardedRenderer
-    device = f"cuda:{local_rank}"
+    work = work_counters(core, view, lights_off_sd=sd)      # generate+extend alone (outside every timed region)
     host_imgs = [torch.empty((H, W, 4), dtype=torch.float32, pin_memory=True) for _ in range(2)]
     host_nps = [t.numpy() for t in host_imgs]
     stream = torch.cuda.ExternalStream(core.Stream(), device=device)
@@ -182,11 +234,6 @@ def run_ours(args, rank, world, local_rank):
         psr = PeerGatherRenderer(core, SPP, rank, world) if args.collective == "peer" else PipelinedShardedRenderer(core, SPP, rank, world, device)
     if psr is None:
         core.Setting("pipeline", 1)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
 
     def enqueue(k, to_host):
         """One Restart frame; with to_host the finished frame of rank 0 goes to pinned host memory (asynchronously)."""
@@ -225,6 +272,27 @@ def run_ours(args, rank, world, local_rank):
         drain()
         return rays + frame_rays()
 
+    # ---- N > 1: in-run parity of the sharded frame (outside the timed region): frame 3 of this run, gathered on rank 0, against
+    # frame 3 of ONE core rendering all world x SPP samples with the same seeds (float sums in another order: 1e-5 relative)
+    parity_ok = None
+    run(3, True)
+    if world > 1:
+        if rank == 0:
+            got = host_nps[0].copy()                 # frame index 2 (k & 1 == 0)
+            single = RenderCore(local_rank)
+            single.SetTarget(W, H, SPP * world)
+            single.Setting("epsilon", 1e-3), single.Setting("clampValue", 10.0), single.Setting("maxPathLength", 1)
+            overrides(single)
+            sd.upload(single)
+            single.Render(view, 1), single.Render(view, 1)       # the two frames the work counters took on the sharded core
+            single.Render(view, 1)                               # and the one that restored the lights
+            for _ in range(3):
+                single.Render(view, 1)
+            want = single.ReadPixels()
+            single.Shutdown()
+            err = float(np.abs(got - want).max() / max(1e-6, np.abs(want).max()))
+            parity_ok = {"ok": bool(err < 1e-5), "max_rel_err": err, "what": "gathered %d-sample frame vs one GPU rendering all samples, same seeds" % (SPP * world)}
+        barrier()
     run(max(args.warmup, 3), True)
     # ---- device-timed run: inputs resident, CUDA events on the launch stream ---------------------------------
     for k in stage:
@@ -245,46 +313,69 @@ def run_ours(args, rank, world, local_rank):
     e_rays = run(args.steps, True)
     barrier()
     e_secs = time.perf_counter() - e0
+    t2 = time.time()
     # clocks under load: the device-timed region and the end-to-end region that follows it run the same workload back to back
-    clocks = sampler.stop(t0, time.time()) if sampler else None
+    clocks = sampler.window(t0, t2) if sampler else None
+    # ---- sustained: the same step back to back for at least --sustain seconds (the headline region is a burst of tens of ms) ----
+    sustained = None
+    if args.sustain > 0:
+        barrier()
+        s0, sus_ms, sus_rays, sus_steps = time.time(), 0.0, 0, 0
+        while time.time() - s0 < args.sustain and sus_steps < 200000:
+            ev0.record(stream)
+            sus_rays += run(200, False)
+            ev1.record(stream)
+            torch.cuda.synchronize()
+            sus_ms += ev0.elapsed_time(ev1)
+            sus_steps += 200
+        s1 = time.time()
+        (sus_ms,), (sus_rays,) = reduce_max_sum([sus_ms], [float(sus_rays)])
+        sustained = {"value": sus_rays / (sus_ms * 1e-3) / 1e6, "unit": UNIT, "steps": sus_steps, "seconds": s1 - s0, "ms_per_step": sus_ms / sus_steps,
+                     "clocks": sampler.window(s0, s1) if sampler else None}
     stage = timed_stage
-    if world > 1:
-        t = torch.tensor([ms, e_secs, float(rays), float(e_rays)], dtype=torch.float64, device=f"cuda:{local_rank}")
-        mx = t.clone()
-        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        sm = t.clone()
-        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        ms, e_secs, rays, e_rays = mx[0].item(), mx[1].item(), sm[2].item(), sm[3].item()
+    (ms, e_secs), (rays, e_rays) = reduce_max_sum([ms, e_secs], [float(rays), float(e_rays)])
+    if psr is not None and args.collective == "peer":
+        psr.close()
+    core.Shutdown()
+    del core
+    extra = {}
+    if not args.no_extra_configs:
+        extra["c3"] = bench_c3(args, rank, world, local_rank, barrier, reduce_max_sum)
+        extra["c5"] = bench_c5(args, rank, world, local_rank, barrier, reduce_max_sum)
+    if sampler:
+        sampler.close()
     if rank != 0:
-        core.Shutdown()
         return
     value = rays / (ms * 1e-3) / 1e6
     e2e = e_rays / e_secs / 1e6
-    # ---- roofline of the dominant kernel (generate+extend), live per-launch time from CUDA events on the launch stream
+    # ---- roofline of the dominant kernel (generate+extend): live per-launch time from CUDA events on the launch stream. The kernel
+    # is bound by instruction issue (the BVH is L2-resident: SURVEY.md 8d), so the roofline is thread instructions per second:
+    # achieved = ALGORITHMIC instructions of one launch (work counters x the per-step instruction model above) / launch time,
+    # peak = 148 SMs x 4 schedulers x 32 lanes x SM clock. Wasted instructions and idle lanes both lower the fraction. ------------
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    hbm_peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     if os.path.exists(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        hbm_peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     ge_ms = stage["generateExtendMs"] / args.steps
-    achieved = W * H * SPP * EXTEND_BYTES_PER_RAY / (ge_ms * 1e-3) / 1e9
-    traffic, issue = None, None
+    n_primary = W * H * SPP
+    inst_per_ray = work["node_steps_per_ray"] * I_NODE + work["tri_tests_per_ray"] * I_TRI + I_PRIMARY
+    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    issue_peak = 148 * 4 * 32 * sm_mhz * 1e6 / 1e9                  # G thread-instructions / s
+    issue_achieved = n_primary * inst_per_ray / (ge_ms * 1e-3) / 1e9
+    hbm_achieved = n_primary * EXTEND_BYTES_PER_RAY / (ge_ms * 1e-3) / 1e9
+    traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
-        tj = json.load(open(tpath))
-        traffic = tj.get("wideGenerateExtendKernel_dram_bytes_per_launch")
-        # traversal is bound by instruction issue, so also report rays/s against
-        # 148 SMs x 4 warp-instructions/clk x SM clock / (warp-instructions per ray, from the committed ncu capture)
-        wi = tj.get("wideGenerateExtendKernel_warp_inst_per_launch")
-        if wi and clocks and clocks.get("sm_mhz"):
-            per_ray = wi / tj["wideGenerateExtendKernel_rays_per_launch"]
-            peak_rays = 148 * 4 * clocks["sm_mhz"] * 1e6 / per_ray
-            issue = {"warp_inst_per_ray": per_ray, "peak_mrays_per_s": peak_rays / 1e6, "frac": (W * H * SPP / (ge_ms * 1e-3)) / peak_rays,
-                     "note": "issue-slot roofline of the dominant kernel; instruction count per ray from profiles/traffic.json"}
-    roofline = {"kernel": "wideGenerateExtendKernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "ms_per_launch": ge_ms, "mrays_per_s": W * H * SPP / ge_ms / 1e3, "issue": issue,
-                "note": "BVH traversal is latency/issue-bound, not HBM-bound (SURVEY.md 8d): the 67 MB CWBVH is L2-resident, DRAM traffic per launch "
-                        "matches the algorithmic 48 B/ray; 'issue' is the roofline that binds (see profiles/r1_v2_wide_kernels_full.txt)"}
-    # ---- CPU baseline: oracle port on this box's host cores, bounded crop (rank 0, N = 1 only) ------------------
+        traffic = json.load(open(tpath)).get("wideGenerateExtendKernel_dram_bytes_per_launch")
+    roofline = {"kernel": "wideGenerateExtendKernel", "bound": "issue", "achieved": issue_achieved, "peak": issue_peak, "unit": "G thread-instructions/s",
+                "frac": issue_achieved / issue_peak, "traffic": traffic, "ms_per_launch": ge_ms, "mrays_per_s": n_primary / ge_ms / 1e3,
+                "algorithmic_thread_instructions_per_ray": inst_per_ray, "model": {"node_step": I_NODE, "triangle_test": I_TRI, "primary_ray": I_PRIMARY},
+                "work": work, "peak_source": "148 SMs x 4 schedulers x 32 lanes x %.0f MHz (SM clock sampled under load)" % sm_mhz,
+                "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak, "peak_source": peak_src,
+                        "note": "48 B/ray algorithmic (SURVEY.md 8d); not the bound: the 64 MB BVH is L2-resident, DRAM traffic per launch ~ the algorithmic bytes"},
+                "note": "traversal is bound by instruction issue and the L1 data path, not by HBM or tensor cores (SURVEY.md 8d; ncu: profiles/r2_*): "
+                        "the fraction is algorithmic instructions (work counters of this run x the per-step model) over the issue peak"}
+    # ---- CPU baseline: oracle port on this box's host cores (rank 0, N = 1 only) ------------------
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         from oracle import binding as orc
@@ -292,23 +383,144 @@ def run_ours(args, rank, world, local_rank):
         threads = os.cpu_count() or 1
         r, dt = cpu_frames(sd, view, threads, 8)
         cpu = {"value": r / dt / 1e6, "unit": UNIT, "cores": threads, "kind": "port", "sample": CPU_SAMPLE.format(frames=8, rays=r // 8, secs=dt)}
+    ref_kernels = None
+    rk = os.path.join(ROOT, "profiles", "r2_reference_kernels.json")
+    if os.path.exists(rk):
+        ref_kernels = dict(json.load(open(rk)), source="profiles/r2_reference_kernels.json (tools/ref_kernel_timing.py on a B200; not re-measured by this run)")
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "triangles": int(bvh["triangles"]) + 2, "resolution": [W, H], "spp_per_gpu": SPP,
-                   "path_length": 1, "overrides": {k[9:]: v for k, v in os.environ.items() if k.startswith("LH2B_SET_")}, "bvh": "CWBVH (8-wide, quantised)", "bvh_nodes": int(bvh["nodes"]),
+                   "path_length": 1, "overrides": {k[9:]: v for k, v in os.environ.items() if k.startswith("LH2B_SET_")}, "bvh": "8-wide compressed BVH, 80-byte nodes", "bvh_nodes": int(bvh["nodes"]),
                    "parallelism": "1 GPU" if world == 1 else f"sample-sharded x{world}, scene replicated, accumulators gathered on rank 0 ({args.collective})",
                    "frames": "pipelined: the next frame is enqueued while the previous one runs",
-                   "l2": "no explicit flush: per-step working set (path state 0.2 GB + scene 0.3 GB) exceeds the 126 MB L2; the 67 MB BVH "
+                   "l2": "no explicit flush: per-step working set (path state 0.2 GB + scene 0.3 GB) exceeds the 126 MB L2; the 64 MB BVH "
                          "staying L2-resident across frames is the steady state of the renderer"},
         "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()},
         "rays_per_step": rays / args.steps,
         "roofline": roofline, "cpu_baseline": cpu,
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 68, "d2h_bytes_per_step": W * H * 16, "ms_per_step": e_secs / args.steps * 1e3},
-        "gpu_launches": (4 if world == 1 else 5) * args.steps, "clocks": clocks}
+        "gpu_launches": (4 if world == 1 else 5) * args.steps, "clocks": clocks, "sustained": sustained, "parity_ok": parity_ok,
+        "extra_configs": extra, "reference_kernels": ref_kernels}
     print(json.dumps(out))
+
+
+def _timed_frames(core, stream, frame_fn, finish_fn, frames, warm, barrier):
+    """`frames` pipelined frames after `warm` untimed ones, device-timed with CUDA events on the core's launch stream."""
+    import torch
+    for f in range(warm):
+        frame_fn(f)
+    finish_fn()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for f in range(frames):
+        frame_fn(warm + f)
+    finish_fn()
+    ev1.record(stream)
+    barrier()
+    return ev0.elapsed_time(ev1)
+
+
+def bench_c3(args, rank, world, local_rank, barrier, reduce_max_sum):
+    """BASELINE.json configs[2]: 1M triangles, 64 materials, 8 emissive quads, 1080p, 16 spp per frame, path length 8, NEE,
+    two diffuse bounces (the stock Optix7 build stops after one: stated variant). N GPUs: the 16 samples are sharded (16 / N per
+    rank, same seeds as one GPU), accumulators gathered on rank 0 - strong scaling of one frame, reported as samples / s."""
+    import torch
+    from lighthouse2_b200 import RenderCore, scenes
+    from lighthouse2_b200.distributed import PeerGatherRenderer
+    TOTAL = 16
+    if TOTAL % world:
+        return {"skipped": "16 spp do not divide over %d ranks" % world}
+    spp = TOTAL // world
+    sd = scenes.config2_scene(NX, NZ, n_materials=64, light_quads=8)
+    view = scenes.view_pyramid(CAM_POS, CAM_TARGET, FOV, W, H)
+    core = RenderCore(local_rank)
+    core.SetTarget(W, H, spp)
+    core.Setting("epsilon", 1e-3), core.Setting("maxPathLength", 8), core.Setting("maxDiffuseBounces", 2)
+    overrides(core)
+    sd.upload(core)
+    stream = torch.cuda.ExternalStream(core.Stream(), device=f"cuda:{local_rank}")
+    psr = PeerGatherRenderer(core, spp, rank, world) if world > 1 else None
+    if psr is None:
+        core.Setting("pipeline", 1)
+    rays = [0]
+
+    def frame(f):
+        if psr is not None:
+            psr.frame(view, 1, None)
+        else:
+            core.Render(view, 1, True)
+
+    def finish():
+        if psr is not None:
+            psr.finish()
+            psr.join(core.Stream())
+        else:
+            core.WaitForRender()
+
+    frames = 6
+    ms = _timed_frames(core, stream, frame, finish, frames, 2, barrier)
+    fs = core.GetFrameStats()
+    rays_per_frame = float(fs["extensionRays"]) + float(fs["shadowRays"])
+    stages = {k: float(fs[k]) for k in ("generateExtendMs", "extendMs", "shadeMs", "connectMs")}
+    (ms,), (rays_per_frame,) = reduce_max_sum([ms], [rays_per_frame])
+    if psr is not None:
+        psr.close()
     core.Shutdown()
+    return {"workload": "synthetic 1M-triangle scene, 1080p 16 spp, path length 8 with NEE, sharedBSDF (configs[2])", "n_gpus": world, "spp_per_gpu": spp,
+            "frames": frames, "ms_per_frame": ms / frames, "samples_per_s": W * H * TOTAL / (ms / frames * 1e-3), "mrays_per_s": rays_per_frame / (ms / frames) / 1e3,
+            "rays_per_frame": rays_per_frame, "stage_ms_rank0_last_frame": stages, "max_diffuse_bounces": 2,
+            "parallelism": "1 GPU" if world == 1 else f"sample-sharded x{world} (strong scaling of one 16-spp frame), accumulators gathered on rank 0 over NVLink peer memory"}
+
+
+def bench_c5(args, rank, world, local_rank, barrier, reduce_max_sum):
+    """BASELINE.json configs[4]: 4K, 1 spp, SVGF filter + TAA, moving camera, real-time frame-time mode. N GPUs: the frame is
+    tile-sharded (row bands rendered per rank, gathered on rank 0 over NVLink peer memory, filter chain on rank 0). The frame ends
+    in rank 0's device pixel buffer (what a display path consumes); reported as ms per frame."""
+    import torch
+    from lighthouse2_b200 import RenderCore, scenes
+    from lighthouse2_b200.distributed import TileShardedRenderer
+    W5, H5 = 3840, 2160
+    sd = scenes.config2_scene(NX, NZ, n_materials=64, light_quads=8)
+    core = RenderCore(local_rank)
+    core.SetTarget(W5, H5, 1)
+    core.Setting("epsilon", 1e-3), core.Setting("filter", 1), core.Setting("TAA", 1)
+    overrides(core)
+    sd.upload(core)
+    stream = torch.cuda.ExternalStream(core.Stream(), device=f"cuda:{local_rank}")
+    view_of = lambda f: scenes.view_pyramid((0.2 * f, 30, -80 + 0.1 * f), (0, 0, 0), 40, W5, H5)
+    r = TileShardedRenderer(core, rank, world) if world > 1 else None
+    if r is None:
+        core.Setting("pipeline", 1)
+
+    def frame(f):
+        if r is not None:
+            r.frame(view_of(f), 1, None)
+        else:
+            core.Render(view_of(f), 1, True)
+
+    def finish():
+        if r is not None:
+            r.finish()
+        else:
+            core.WaitForRender()
+
+    frames = 12
+    t0 = time.perf_counter()
+    ms = _timed_frames(core, stream, frame, finish, frames, 4, barrier)
+    fs = core.GetFrameStats()
+    stages = {k: float(fs[k]) for k in ("generateExtendMs", "extendMs", "shadeMs", "connectMs", "filterMs")}
+    (ms,), _ = reduce_max_sum([ms], [])
+    if r is not None:
+        r.close()
+    core.Shutdown()
+    px = W5 * H5
+    return {"workload": "4K 1 spp + SVGF temporal / a-trous filter + TAA, moving camera, real-time frame-time mode (configs[4])", "n_gpus": world,
+            "frames": frames, "ms_per_frame": ms / frames, "fps": frames / (ms * 1e-3), "stage_ms_rank0_last_frame": stages,
+            "filter_gb_per_s_at_584_B_per_px": (px * 584 / (stages["filterMs"] * 1e-3) / 1e9) if stages["filterMs"] > 0 else None,
+            "parallelism": "1 GPU" if world == 1 else f"tile-sharded x{world} (row bands), bands gathered on rank 0 over NVLink peer memory, filter chain on rank 0"}
 
 
 def main():
@@ -318,6 +530,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra-configs", action="store_true", help="skip the short C3 / C5 runs (extra_configs)")
+    ap.add_argument("--sustain", type=float, default=2.0, help="seconds of the sustained C2 loop (0: skip)")
     ap.add_argument("--collective", default="peer", choices=["peer", "nccl"], help="N > 1: own NVLink peer-memory gather (default) or NCCL reduce")
     args = ap.parse_args()
     rank, world, local_rank = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))

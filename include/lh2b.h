@@ -44,6 +44,7 @@ LH2B_API int lh2b_set_target( lh2b_core* core, int width, int height, int spp );
                                     re-collapse, 0 rebuild), plocRadius (1..64, default 8), bvhCollapse (1 SAH-optimal collapse to 8-wide, default; 0 greedy),
                                     l2Persist (1 default: persisting-L2 window over the node arena)
      frame scheduling               pipeline (1: Render( async ) enqueues frame k+1 behind frame k; statistics lag one frame),
+                                    overlapConnect (1 default: connect( L ) runs next to extend( L + 1 ) on a second stream),
                                     gatherMode (read by lh2b_gather_create: 0 root gather default, 1 reduce-scatter),
                                     tileRootShare (read by lh2b_tile_create: rank 0's band relative to an equal share, 0..1)
      kernel tuning (measurement)    wideBlocksPerSM, triThreshold, triThresholdShadow, refillThreshold, shadeBlocks (4 / 5 / 6) */
@@ -218,8 +219,15 @@ typedef struct lh2b_filter_io
 	const float* prevMoments; const float* filteredIN; const float* prevPixels;
 	uint32_t* featuresOut; float* shadingAfterPrepare; float* motion; float* moments;
 	float* phase1; float* phase2; float* phase3; float* taaPixels; float* target;
+	int timingRuns;		/* > 0: after the checked run, time that many more runs of the whole chain on the same inputs */
+	float stageMs[8];	/* mean ms: prepare, a-trous 1, 2, 3, TAA, present, whole chain, 0 (CUDA events on the core's stream) */
 } lh2b_filter_io;
 LH2B_API int lh2b_filter_chain( lh2b_core* core, lh2b_filter_io* io );
+/* Measurement twin of lh2b_shade_paths: uploads the same inputs once and times 'runs' launches of the shade kernel on them with
+   CUDA events on the core's stream (the kernel reads one path-state set and writes the other, so nothing needs restoring but the
+   counters). msOut[0] = fastest, msOut[1] = mean launch. */
+LH2B_API int lh2b_shade_paths_time( lh2b_core* core, int pathLength, int n, const float* O4, const float* D4, const float* T4, const float* hits,
+	uint32_t R0, uint32_t shift, int pass, int runs, float* msOut );
 /* Filter mode only: copy the per-pixel filter inputs of the last frame to host (any pointer may be null):
    features uint4[w*h], worldPos / deltaDepth float4[w*h], accumulator2 float4[2*w*h] (direct, then indirect). */
 LH2B_API int lh2b_read_filter_buffers( lh2b_core* core, uint32_t* features, float* worldPos, float* deltaDepth, float* accumulator2 );

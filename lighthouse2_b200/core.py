@@ -290,6 +290,14 @@ class RenderCore:
         sh = dict(O=out[3][:ns.value], D=out[4][:ns.value], E=out[5][:ns.value])
         return ext, sh, acc
 
+    def ShadePathsTime(self, path_length, O4, D4, T4, hits, R0, shift, pass_, runs=10):
+        """(fastest, mean) ms of `runs` launches of the shade kernel on these path states (lh2b_shade_paths_time)."""
+        o, d, t = (_arr(a, np.float32).reshape(-1, 4) for a in (O4, D4, T4))
+        hb = np.ascontiguousarray(hits).view(np.float32).reshape(-1, 4)
+        ms = np.zeros(2, np.float32)
+        self._check(self._lib.lh2b_shade_paths_time(self._h, path_length, o.shape[0], _ptr(o), _ptr(d), _ptr(t), _ptr(hb), R0, shift, pass_, runs, _ptr(ms)))
+        return float(ms[0]), float(ms[1])
+
     def ReadFilterBuffers(self):
         """Filter mode: (features uint32[h,w,4], worldPos, deltaDepth float32[h,w,4], accumulator float32[2,h,w,4]) of the last frame."""
         h, w = self.height, self.width

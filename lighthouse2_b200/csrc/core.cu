@@ -182,6 +182,7 @@ static void ApplyL2Policy( lh2b_core* core )
 	}
 	else attr.accessPolicyWindow.num_bytes = 0;
 	CUDA_CHECK( cudaStreamSetAttribute( core->stream, cudaStreamAttributeAccessPolicyWindow, &attr ) );
+	CUDA_CHECK( cudaStreamSetAttribute( core->connectStream, cudaStreamAttributeAccessPolicyWindow, &attr ) );
 	core->l2Applied = core->l2Persist, core->l2Base = core->arenaNodes.ptr, core->l2Bytes = nodeBytes;
 }
 
@@ -293,6 +294,7 @@ int lh2b_create( lh2b_core** out, int device )
 			int least = 0, greatest = 0;
 			CUDA_CHECK( cudaDeviceGetStreamPriorityRange( &least, &greatest ) );
 			CUDA_CHECK( cudaStreamCreateWithPriority( &core->stream, cudaStreamNonBlocking, greatest ) );
+			CUDA_CHECK( cudaStreamCreateWithPriority( &core->connectStream, cudaStreamNonBlocking, greatest ) );
 		}
 		CUDA_CHECK( cudaStreamCreateWithFlags( &core->copyStream, cudaStreamNonBlocking ) );
 		CUDA_CHECK( cudaEventCreateWithFlags( &core->frameDone, cudaEventDisableTiming ) );
@@ -323,6 +325,7 @@ int lh2b_destroy( lh2b_core* core )
 	ReleaseGpuBuildScratch( core );
 	cudaEventDestroy( core->evA ), cudaEventDestroy( core->evB );
 	if (core->copyStream) cudaStreamSynchronize( core->copyStream ), cudaStreamDestroy( core->copyStream );
+	if (core->connectStream) cudaStreamSynchronize( core->connectStream ), cudaStreamDestroy( core->connectStream );
 	if (core->frameDone) cudaEventDestroy( core->frameDone );
 	for (int k = 0; k < 2; k++) if (core->copyDone[k]) cudaEventDestroy( core->copyDone[k] );
 	cudaStreamDestroy( core->stream );

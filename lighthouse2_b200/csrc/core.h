@@ -114,6 +114,8 @@ struct lh2b_core
 	// of frame k overlaps the kernels of frame k+1. Index 0 of the pair arrays belongs to 'pixels', 1 to 'pixelsAlt'.
 	lh2b::DevBuf<float4> pixelsAlt;
 	cudaStream_t copyStream = nullptr;
+	cudaStream_t connectStream = nullptr;	// connect( L ) runs here, next to extend( L + 1 ) on the launch stream (Setting "overlapConnect")
+	int overlapConnect = 1;
 	cudaEvent_t frameDone = nullptr, copyDone[2] = { nullptr, nullptr };
 	bool copyPending[2] = { false, false };
 	lh2b::DevBuf<lh2b::DevCounters> counters;

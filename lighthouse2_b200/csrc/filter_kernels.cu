@@ -583,8 +583,10 @@ __global__ void __launch_bounds__( 256 ) presentKernel( const float4* __restrict
 }
 
 /* ---- host side --------------------------------------------------------------------------------------------------- */
-static void FilterChainImpl( const FilterBuffers& b, const FilterSettings& s, cudaStream_t st, float* hPrepare, float* hP1, float* hP2, float* hP3 )
+static void FilterChainImpl( const FilterBuffers& b, const FilterSettings& s, cudaStream_t st, float* hPrepare, float* hP1, float* hP2, float* hP3, cudaEvent_t* ev = nullptr )
 {
+	auto mark = [&]( int k ) { if (ev) cudaEventRecord( ev[k], st ); };
+	mark( 0 );
 	auto snap = [&]( float* dst, const float4* src ) { if (dst) cudaMemcpyAsync( dst, src, (size_t)s.w * s.h * 16, cudaMemcpyDeviceToHost, st ); };
 	const int w = s.w, h = s.h;
 	const dim3 grid( (w + 31) / 32, (h + 7) / 8 ), block( 32, 8 );
@@ -615,6 +617,7 @@ static void FilterChainImpl( const FilterBuffers& b, const FilterSettings& s, cu
 		prepareFinishKernel<<<sms * 8, 256, 0, st>>>( pa, queue, count );
 	}
 	else prepareKernel<false><<<grid, block, 0, st>>>( pa, nullptr, nullptr );
+	mark( 1 );
 	snap( hPrepare, b.shading );
 	AtrousArgs aa;
 	aa.features = b.features, aa.prevWorldPos = b.prevWorldPos, aa.worldPos = b.worldPos, aa.deltaDepth = b.deltaDepth, aa.motion = b.motion, aa.moments = b.moments;
@@ -631,22 +634,31 @@ static void FilterChainImpl( const FilterBuffers& b, const FilterSettings& s, cu
 	const dim3 grid16( (w + 31) / 32, (h + 15) / 16 ), block16( 32, 16 );
 	aa.A = b.shading, aa.B = b.filteredIN, aa.C = b.filteredOUT, aa.phase = 1, aa.lastPass = 0;
 	atrousKernel<1, 8><<<grid, block, smem( 1, 8 ), st>>>( aa );
+	mark( 2 );
 	snap( hP1, b.filteredOUT );
 	aa.A = b.filteredOUT, aa.B = nullptr, aa.C = b.filteredIN, aa.phase = 2;
 	atrousKernel<2, 16><<<grid16, block16, smem( 2, 16 ), st>>>( aa );
+	mark( 3 );
 	snap( hP2, b.filteredIN );
 	aa.A = b.filteredIN, aa.C = b.shading, aa.phase = 3, aa.lastPass = 1;
 	atrousKernel<4, 16><<<grid16, block16, smem( 4, 16 ), st>>>( aa );
+	mark( 4 );
 	snap( hP3, b.shading );
 	if (s.taa)
 	{
 		taaKernel<<<grid, block, 0, st>>>( b.shading, b.taaOut, b.prevPixels, b.motion, w, h );
+		mark( 5 );
 		presentKernel<<<grid, block, 0, st>>>( b.taaOut, b.target, w, h, 1 );
 	}
-	else presentKernel<<<grid, block, 0, st>>>( b.shading, b.target, w, h, 0 );
+	else
+	{
+		mark( 5 );
+		presentKernel<<<grid, block, 0, st>>>( b.shading, b.target, w, h, 0 );
+	}
+	mark( 6 );
 }
 
-void LaunchFilterChain( const FilterBuffers& b, const FilterSettings& s, cudaStream_t st ) { FilterChainImpl( b, s, st, nullptr, nullptr, nullptr, nullptr ); }
+void LaunchFilterChain( const FilterBuffers& b, const FilterSettings& s, cudaStream_t st, cudaEvent_t* stageEvents ) { FilterChainImpl( b, s, st, nullptr, nullptr, nullptr, nullptr, stageEvents ); }
 void LaunchFilterChainStaged( const FilterBuffers& b, const FilterSettings& s, cudaStream_t st, float* hPrepare, float* hP1, float* hP2, float* hP3 )
 {
 	FilterChainImpl( b, s, st, hPrepare, hP1, hP2, hP3 );

@@ -33,7 +33,7 @@ struct FilterSettings
 	float directClamp, indirectClamp, j0, j1, prevj0, prevj1;
 	float prevView[17];
 };
-void LaunchFilterChain( const FilterBuffers& b, const FilterSettings& s, cudaStream_t st );
+void LaunchFilterChain( const FilterBuffers& b, const FilterSettings& s, cudaStream_t st, cudaEvent_t* stageEvents = nullptr );	// stageEvents: 7 events recorded at the stage boundaries
 void LaunchFilterChainStaged( const FilterBuffers& b, const FilterSettings& s, cudaStream_t st, float* hPrepare, float* hP1, float* hP2, float* hP3 );
 void LaunchTagTriangles( float4* tris, int triCount, uint32_t inst, cudaStream_t s );
 // skin_kernels.cu

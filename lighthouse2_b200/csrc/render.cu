@@ -48,8 +48,9 @@ void InitRenderState( lh2b_core* core )
 	CUDA_CHECK( cudaMallocHost( &core->hostCounters, sizeof( DevCounters ) ) );
 	CUDA_CHECK( cudaMallocHost( &core->hostCountersB, sizeof( DevCounters ) ) );
 	memset( core->hostCounters, 0, sizeof( DevCounters ) ), memset( core->hostCountersB, 0, sizeof( DevCounters ) );
-	// events: 0 frame start, then per path length L (1-based): 4 * L + {0: trace start, 1: trace end/shade start, 2: shade end/connect start, 3: connect end}
-	core->events.resize( 4 * (LH2B_MAXPATHLENGTH + 1) + 4 );
+	// events: 0 frame start, then per path length L (1-based): 5 * L + {0: trace start, 1: trace end, 2: shade start (connect( L - 1 ) has finished),
+	// 3: shade end / connect start, 4: connect end - on the connect stream when the overlap is on}
+	core->events.resize( 5 * (LH2B_MAXPATHLENGTH + 1) + 4 );
 	for (auto& e : core->events) CUDA_CHECK( cudaEventCreate( &e ) );
 	core->eventsB.resize( core->events.size() );
 	for (auto& e : core->eventsB) CUDA_CHECK( cudaEventCreate( &e ) );
@@ -136,11 +137,12 @@ static void FinishFrame( lh2b_core* core )
 	for (int L = 1; L <= maxLen; L++) st.totalShadowRays += c.shadowRays[L];
 	st.totalRays = st.totalExtensionRays + st.totalShadowRays;
 	auto elapsed = [&]( int a, int b ) { float ms = 0; cudaEventElapsedTime( &ms, core->events[a], core->events[b] ); return ms; };
-	st.traceTime0 = elapsed( 4, 5 );
-	st.traceTime1 = maxLen >= 2 ? elapsed( 8, 9 ) : 0;
+	st.traceTime0 = elapsed( 5, 6 );
+	st.traceTime1 = maxLen >= 2 ? elapsed( 10, 11 ) : 0;
 	st.traceTimeX = 0, st.shadeTime = 0, st.shadowTraceTime = 0;
-	for (int L = 3; L <= maxLen; L++) st.traceTimeX += elapsed( 4 * L, 4 * L + 1 );
-	for (int L = 1; L <= maxLen; L++) st.shadeTime += elapsed( 4 * L + 1, 4 * L + 2 ), st.shadowTraceTime += elapsed( 4 * L + 2, 4 * L + 3 );
+	for (int L = 3; L <= maxLen; L++) st.traceTimeX += elapsed( 5 * L, 5 * L + 1 );
+	// (with the connect overlap the stage times overlap too: connect( L ) runs next to extend( L + 1 ), their sum exceeds the frame time)
+	for (int L = 1; L <= maxLen; L++) st.shadeTime += elapsed( 5 * L + 2, 5 * L + 3 ), st.shadowTraceTime += elapsed( 5 * L + 3, 5 * L + 4 );
 	st.probedInstid = c.probedInstid, st.probedTriid = c.probedTriid, st.probedDist = c.probedDist;
 	// probe world position (rendercore.cpp:935-937)
 	{
@@ -268,20 +270,30 @@ static void RenderFrame( lh2b_core* core, const lh2abi::ViewPyramid& view )
 	const bool useNEE = (core->lightCounts[0] + core->lightCounts[1] + core->lightCounts[2] + core->lightCounts[3]) > 0;
 	const PathSet conn = { core->connBuf[0].ptr, core->connBuf[1].ptr, core->connBuf[2].ptr };
 	const int sm = (int)core->stats.SMcount;
+	// connect( L ) only feeds the accumulator; extend( L + 1 ) only needs shade( L ): the two traversal launches run side by side
+	// on two streams (the tail of one persistent grid is filled by the other - what counts for small frames and deep, thin path
+	// lengths). shade( L + 1 ) waits for both, so deposits still reach the accumulator in the serial order: generate-time
+	// determinism (bit-identical frames at 1 spp) is kept.
+	const bool overlap = core->overlapConnect && useNEE && core->connectStream;
+	cudaStream_t cs = overlap ? core->connectStream : s;
 	for (int L = 1; L <= core->maxPathLength; L++)
 	{
 		const PathSet in = { core->pathBuf[(L - 1) & 1][0].ptr, core->pathBuf[(L - 1) & 1][1].ptr, core->pathBuf[(L - 1) & 1][2].ptr };
 		const PathSet out = { core->pathBuf[L & 1][0].ptr, core->pathBuf[L & 1][1].ptr, core->pathBuf[L & 1][2].ptr };
-		CUDA_CHECK( cudaEventRecord( core->events[4 * L], s ) );
+		CUDA_CHECK( cudaEventRecord( core->events[5 * L], s ) );
 		if (L == 1) LaunchGenerateExtend( core->scene, p, in, core->hitBuf.ptr, &core->counters.ptr->workFetch[2 * L], sm, s );
 		else LaunchExtendCounted( core->scene, in, core->hitBuf.ptr, &core->counters.ptr->extensionRays[L - 1], &core->counters.ptr->workFetch[2 * L], stride, sm, s );
-		CUDA_CHECK( cudaEventRecord( core->events[4 * L + 1], s ) );
+		CUDA_CHECK( cudaEventRecord( core->events[5 * L + 1], s ) );
+		if (overlap && L > 1) CUDA_CHECK( cudaStreamWaitEvent( s, core->events[5 * (L - 1) + 4], 0 ) );	// connect( L - 1 ) is done
+		CUDA_CHECK( cudaEventRecord( core->events[5 * L + 2], s ) );
 		const uint32_t R0 = RandomUInt( core->camRNGseed ) + L * 91771;
 		LaunchShade( p, in, out, core->hitBuf.ptr, conn, L, R0, useNEE, stride, sm, s );
-		CUDA_CHECK( cudaEventRecord( core->events[4 * L + 2], s ) );
-		if (useNEE) LaunchConnect( core->scene, conn, core->accumulator.ptr, &core->counters.ptr->shadowRays[L], &core->counters.ptr->workFetch[2 * L + 1], stride, sm, s );
-		CUDA_CHECK( cudaEventRecord( core->events[4 * L + 3], s ) );
+		CUDA_CHECK( cudaEventRecord( core->events[5 * L + 3], s ) );
+		if (overlap) CUDA_CHECK( cudaStreamWaitEvent( cs, core->events[5 * L + 3], 0 ) );
+		if (useNEE) LaunchConnect( core->scene, conn, core->accumulator.ptr, &core->counters.ptr->shadowRays[L], &core->counters.ptr->workFetch[2 * L + 1], stride, sm, cs );
+		CUDA_CHECK( cudaEventRecord( core->events[5 * L + 4], cs ) );
 	}
+	if (overlap) CUDA_CHECK( cudaStreamWaitEvent( s, core->events[5 * core->maxPathLength + 4], 0 ) );
 	CUDA_CHECK( cudaGetLastError() );
 	CUDA_CHECK( cudaMemcpyAsync( core->hostCounters, core->counters.ptr, sizeof( DevCounters ), cudaMemcpyDeviceToHost, s ) );
 	// FinalizeRender (rendercore.cpp:963-979), enqueued behind the last stage: nothing of it depends on host-visible results,
@@ -380,6 +392,7 @@ int lh2b_setting( lh2b_core* core, const char* name, float value )
 	else if (!strcmp( name, "tileRootShare" )) core->tileRootShare = value < 0 ? 0 : (value > 1 ? 1 : value);	// read by lh2b_tile_create
 	else if (!strcmp( name, "gatherMode" )) core->gatherMode = value > 0 ? 1 : 0;	// read by lh2b_gather_create
 	else if (!strcmp( name, "l2Persist" )) core->l2Persist = value > 0 ? 1 : 0;	// takes effect at the next FinalizeInstances
+	else if (!strcmp( name, "overlapConnect" )) { FinishFrame( core ); core->overlapConnect = value > 0 ? 1 : 0; }
 	else if (!strcmp( name, "pipeline" )) { FinishFrame( core ); core->pipeline = value > 0; }
 	else if (!strcmp( name, "bsdf" )) { const int m = value >= 0.5f ? 1 : 0; if (m != core->bsdfModel) core->bsdfModel = m, core->samplesTaken = 0; }
 	else if (!strcmp( name, "maxDiffuseBounces" )) core->enoughBounces = value <= 0 ? 0 : (value < 2 ? S_BOUNCED : S_BOUNCEDTWICE);
@@ -738,6 +751,70 @@ int lh2b_filter_chain( lh2b_core* core, lh2b_filter_io* io )
 	down( io->featuresOut, feat.ptr, px * 16 ), down( io->motion, motion.ptr, px * 8 ), down( io->moments, moments.ptr, px * 16 );
 	down( io->taaPixels, taaOut.ptr, px * 16 ), down( io->target, target.ptr, px * 16 );
 	CUDA_CHECK( cudaStreamSynchronize( s ) );
+	for (int k = 0; k < 8; k++) io->stageMs[k] = 0;
+	if (io->timingRuns > 0)
+	{
+		DevBuf<uint4> feat0;
+		feat0.Upload( (const uint4*)io->features, px, s );
+		cudaEvent_t ev[7];
+		for (auto& e : ev) CUDA_CHECK( cudaEventCreate( &e ) );
+		for (int r = 0; r < io->timingRuns + 1; r++)	// the first one warms up
+		{
+			CUDA_CHECK( cudaMemcpyAsync( feat.ptr, feat0.ptr, px * 16, cudaMemcpyDeviceToDevice, s ) );	// the history counter is updated in place
+			CUDA_CHECK( cudaStreamSynchronize( s ) );
+			LaunchFilterChain( b, fs, s, ev );
+			CUDA_CHECK( cudaEventSynchronize( ev[6] ) );
+			if (r == 0) continue;
+			for (int k = 0; k < 6; k++) { float ms = 0; CUDA_CHECK( cudaEventElapsedTime( &ms, ev[k], ev[k + 1] ) ); io->stageMs[k] += ms / io->timingRuns; }
+			float ms = 0;
+			CUDA_CHECK( cudaEventElapsedTime( &ms, ev[0], ev[6] ) );
+			io->stageMs[6] += ms / io->timingRuns;
+		}
+		for (auto& e : ev) cudaEventDestroy( e );
+	}
+	API_END
+}
+
+int lh2b_shade_paths_time( lh2b_core* core, int pathLength, int n, const float* O4, const float* D4, const float* T4, const float* hits,
+	uint32_t R0, uint32_t shift, int pass, int runs, float* msOut )
+{
+	API_BEGIN
+	FinishFrame( core );
+	if (!core->sceneReady || core->width == 0) throw CoreError( "shade_paths_time: scene and target must be set" );
+	const uint32_t stride = (uint32_t)core->width * core->height * core->spp;
+	if (n < 0 || (uint32_t)n > stride) throw CoreError( "shade_paths_time: n exceeds w*h*spp" );
+	if (pathLength < 1 || pathLength > core->maxPathLength || runs < 1) throw CoreError( "shade_paths_time: pathLength / runs out of range" );
+	cudaStream_t s = core->stream;
+	const size_t bytes = (size_t)n * sizeof( float4 );
+	CUDA_CHECK( cudaMemcpyAsync( core->pathBuf[0][0].ptr, O4, bytes, cudaMemcpyHostToDevice, s ) );
+	CUDA_CHECK( cudaMemcpyAsync( core->pathBuf[0][1].ptr, D4, bytes, cudaMemcpyHostToDevice, s ) );
+	CUDA_CHECK( cudaMemcpyAsync( core->pathBuf[0][2].ptr, T4, bytes, cudaMemcpyHostToDevice, s ) );
+	CUDA_CHECK( cudaMemcpyAsync( core->hitBuf.ptr, hits, bytes, cudaMemcpyHostToDevice, s ) );
+	DevCounters hc;
+	memset( &hc, 0, sizeof( hc ) );
+	hc.extensionRays[pathLength - 1] = (uint32_t)n;
+	RenderParams p = BuildParams( core, core->lastView );
+	p.stride = pathLength == 1 ? (uint32_t)n : stride;
+	p.shift = shift, p.pass = pass;
+	const bool useNEE = (core->lightCounts[0] + core->lightCounts[1] + core->lightCounts[2] + core->lightCounts[3]) > 0;
+	const PathSet in = { core->pathBuf[0][0].ptr, core->pathBuf[0][1].ptr, core->pathBuf[0][2].ptr };
+	const PathSet out = { core->pathBuf[1][0].ptr, core->pathBuf[1][1].ptr, core->pathBuf[1][2].ptr };
+	const PathSet conn = { core->connBuf[0].ptr, core->connBuf[1].ptr, core->connBuf[2].ptr };
+	float best = 1e30f, sum = 0;
+	for (int r = 0; r < runs + 1; r++)	// the first one warms up
+	{
+		CUDA_CHECK( cudaMemcpyAsync( core->counters.ptr, &hc, offsetof( DevCounters, probedInstid ), cudaMemcpyHostToDevice, s ) );
+		CUDA_CHECK( cudaStreamSynchronize( s ) );
+		CUDA_CHECK( cudaEventRecord( core->evA, s ) );
+		LaunchShade( p, in, out, core->hitBuf.ptr, conn, pathLength, R0, useNEE, (uint32_t)n, (int)core->stats.SMcount, s );
+		CUDA_CHECK( cudaEventRecord( core->evB, s ) );
+		CUDA_CHECK( cudaEventSynchronize( core->evB ) );
+		CUDA_CHECK( cudaGetLastError() );
+		float ms = 0;
+		CUDA_CHECK( cudaEventElapsedTime( &ms, core->evA, core->evB ) );
+		if (r > 0) best = ms < best ? ms : best, sum += ms;
+	}
+	msOut[0] = best, msOut[1] = sum / runs;
 	API_END
 }
 

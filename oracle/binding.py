@@ -288,7 +288,7 @@ class RefShadeIn(ctypes.Structure):
                 ("pathStates", ctypes.c_void_p), ("hits", ctypes.c_void_p), ("connections", ctypes.c_void_p), ("accumulator", ctypes.c_void_p),
                 ("R0", ctypes.c_uint), ("shift", ctypes.c_uint), ("pass_", ctypes.c_int), ("probePixelIdx", ctypes.c_int),
                 ("pathLength", ctypes.c_int), ("w", ctypes.c_int), ("h", ctypes.c_int), ("spreadAngle", ctypes.c_float), ("useNEE", ctypes.c_int),
-                ("countersOut", ctypes.c_uint * 12)]
+                ("countersOut", ctypes.c_uint * 12), ("timingRuns", ctypes.c_int), ("timingMsMin", ctypes.c_float), ("timingMsMean", ctypes.c_float)]
 
 
 REF_SHADE_GPU = os.path.join(_HERE, "_ref", "libref_shade_gpu.so")                    # reference shadeKernel with lambert.h
@@ -299,7 +299,7 @@ def have_ref_shade_gpu(bsdf=0):
     return os.path.exists(REF_SHADE_DISNEY_GPU if bsdf else REF_SHADE_GPU)
 
 
-def ref_shade_gpu(oracle, view, path_length, O4, D4, T4, hits, R0, shift, pass_, accumulator, bsdf=0):
+def ref_shade_gpu(oracle, view, path_length, O4, D4, T4, hits, R0, shift, pass_, accumulator, bsdf=0, timing_runs=0):
     """Run the REFERENCE shadeKernel (unmodified source, sm_100a build) on n paths. Returns compacted extension rays,
     shadow rays, the accumulator and the counters, like lh2b_shade_paths."""
     sd = oracle.sd
@@ -344,6 +344,7 @@ def ref_shade_gpu(oracle, view, path_length, O4, D4, T4, hits, R0, shift, pass_,
     r.w, r.h = oracle.w, oracle.h
     r.spreadAngle = float(np.ascontiguousarray(view)[0]["spreadAngle"])
     r.useNEE = int(sum(len(l) for l in lights) > 0)
+    r.timingRuns = timing_runs
     rc = rl.refshade_run(ctypes.byref(r))
     if rc != 0:
         raise RuntimeError("refshade_run failed")
@@ -351,6 +352,8 @@ def ref_shade_gpu(oracle, view, path_length, O4, D4, T4, hits, R0, shift, pass_,
     n_ext, n_sh = cnt[5] - n, cnt[6]          # Counters.extensionRays started at n (see ref_shade_gpu.cu), shadowRays at 0
     ext = dict(O=ps[n:n + n_ext], D=ps[stride + n:stride + n + n_ext], T=ps[2 * stride + n:2 * stride + n + n_ext])
     sh = dict(O=conn[0:n_sh], D=conn[2 * stride:2 * stride + n_sh], E=conn[4 * stride:4 * stride + n_sh])
+    if timing_runs:
+        return ext, sh, acc.reshape(oracle.h, oracle.w, 4), cnt, {"ms_min": float(r.timingMsMin), "ms_mean": float(r.timingMsMean)}
     return ext, sh, acc.reshape(oracle.h, oracle.w, 4), cnt
 
 
@@ -364,7 +367,8 @@ class FilterIO(ctypes.Structure):
                 ("accumulator", ctypes.c_void_p), ("features", ctypes.c_void_p), ("worldPos", ctypes.c_void_p), ("prevWorldPos", ctypes.c_void_p),
                 ("deltaDepth", ctypes.c_void_p), ("prevMoments", ctypes.c_void_p), ("filteredIN", ctypes.c_void_p), ("prevPixels", ctypes.c_void_p),
                 ("featuresOut", ctypes.c_void_p), ("shadingAfterPrepare", ctypes.c_void_p), ("motion", ctypes.c_void_p), ("moments", ctypes.c_void_p),
-                ("phase1", ctypes.c_void_p), ("phase2", ctypes.c_void_p), ("phase3", ctypes.c_void_p), ("taaPixels", ctypes.c_void_p), ("target", ctypes.c_void_p)]
+                ("phase1", ctypes.c_void_p), ("phase2", ctypes.c_void_p), ("phase3", ctypes.c_void_p), ("taaPixels", ctypes.c_void_p), ("target", ctypes.c_void_p),
+                ("timingRuns", ctypes.c_int), ("stageMs", ctypes.c_float * 8)]
 
 
 REF_FILTER_GPU = os.path.join(_HERE, "_ref", "libref_filter_gpu.so")
@@ -396,11 +400,18 @@ def make_filter_io(inputs, settings):
     return io, outs, keep
 
 
-def ref_filter_gpu(inputs, settings):
+FILTER_STAGES = ("prepare", "atrous1", "atrous2", "atrous3", "taa", "present", "chain")
+
+
+def ref_filter_gpu(inputs, settings, timing_runs=0):
+    """The reference's own filter kernels on the inputs; with timing_runs also {stage: mean ms} of that many timed runs of the chain."""
     io, outs, keep = make_filter_io(inputs, settings)
+    io.timingRuns = timing_runs
     rc = ctypes.CDLL(REF_FILTER_GPU).reffilter_run(ctypes.byref(io))
     if rc != 0:
         raise RuntimeError("reffilter_run failed")
+    if timing_runs:
+        return outs, dict(zip(FILTER_STAGES, (float(x) for x in io.stageMs)))
     return outs
 
 

@@ -51,6 +51,8 @@ struct RefFilterIO
 	// outputs (host)
 	uint* featuresOut; float* shadingAfterPrepare; float* motion; float* moments;
 	float* phase1; float* phase2; float* phase3; float* taaPixels; float* target;
+	int timingRuns;				// > 0: after the checked run, time that many more runs of the whole chain on the same inputs
+	float stageMs[8];			// mean ms: prepare, a-trous 1, 2, 3, TAA, unsharp / finalizeNoTAA, whole chain, 0 (CUDA events between the reference's own launches)
 };
 
 #define CK( x ) do { cudaError_t e = (x); if (e != cudaSuccess) { fprintf( stderr, "ref_filter_gpu: %s: %s\n", #x, cudaGetErrorString( e ) ); return 1; } } while (0)
@@ -114,6 +116,41 @@ extern "C" __attribute__( ( visibility( "default" ) ) ) int reffilter_run( RefFi
 	else finalizeNoTAA( shading, w, h );
 	CK( cudaDeviceSynchronize() );
 	CK( cudaMemcpy2DFromArray( io->target, w * 16, arr, 0, 0, w * 16, h, cudaMemcpyDeviceToHost ) );
+	for (int k = 0; k < 8; k++) io->stageMs[k] = 0;
+	if (io->timingRuns > 0)
+	{
+		// launch shapes are the reference's own (the host wrappers of finalize_shared.h, as lib/RenderCore_Optix7Filter/rendercore.cpp:897-948 calls them)
+		uint4* feat0 = Up<uint4>( io->features, b16 );
+		cudaEvent_t ev[7];
+		for (auto& evt : ev) CK( cudaEventCreate( &evt ) );
+		for (int r = 0; r < io->timingRuns + 1; r++)	// the first one warms up
+		{
+			CK( cudaMemcpy( feat, feat0, b16, cudaMemcpyDeviceToDevice ) );	// the history counter in the features is updated in place
+			CK( cudaDeviceSynchronize() );
+			CK( cudaEventRecord( ev[0] ) );
+			prepareFilter( acc, feat, wp, pwp, shading, motion, moments, pmom, dd, pv, io->j0, io->j1, io->prevj0, io->prevj1,
+				w, h, io->samplesTaken, io->directClamp, io->indirectClamp, io->camIsStationary );
+			CK( cudaEventRecord( ev[1] ) );
+			applyFilter( feat, pwp, wp, dd, motion, moments, shading, fIN, fOUT, w, h, 1, 0 );
+			CK( cudaEventRecord( ev[2] ) );
+			applyFilter( feat, pwp, wp, dd, motion, moments, fOUT, 0, fIN, w, h, 2, 0 );
+			CK( cudaEventRecord( ev[3] ) );
+			applyFilter( feat, pwp, wp, dd, motion, moments, fIN, 0, shading, w, h, 3, 1 );
+			CK( cudaEventRecord( ev[4] ) );
+			if (io->taa) TAApass( shading, prevPixels, 0, 0, wp, pwp, motion, w, h );
+			CK( cudaEventRecord( ev[5] ) );
+			if (io->taa) unsharpenTAA( shading, w, h ); else finalizeNoTAA( shading, w, h );
+			CK( cudaEventRecord( ev[6] ) );
+			CK( cudaEventSynchronize( ev[6] ) );
+			if (r == 0) continue;
+			for (int k = 0; k < 6; k++) { float ms = 0; CK( cudaEventElapsedTime( &ms, ev[k], ev[k + 1] ) ); io->stageMs[k] += ms / io->timingRuns; }
+			float ms = 0;
+			CK( cudaEventElapsedTime( &ms, ev[0], ev[6] ) );
+			io->stageMs[6] += ms / io->timingRuns;
+		}
+		for (auto& evt : ev) cudaEventDestroy( evt );
+		cudaFree( feat0 );
+	}
 	cudaDestroySurfaceObject( surf ), cudaFreeArray( arr );
 	for (void* p : { (void*)acc, (void*)feat, (void*)wp, (void*)pwp, (void*)dd, (void*)shading, (void*)moments, (void*)pmom, (void*)motion, (void*)fIN, (void*)fOUT, (void*)prevPixels, (void*)dbg }) cudaFree( p );
 	return 0;

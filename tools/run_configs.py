@@ -22,6 +22,25 @@ def frame_stats(core, view, frames, converge=1):
     return acc
 
 
+def overrides(core):
+    """experiments: LH2B_SET_<setting>=<value>"""
+    for k, v in os.environ.items():
+        if k.startswith("LH2B_SET_"):
+            core.Setting(k[9:], float(v))
+
+
+def counted_frame(core, view, converge=1):
+    """one more frame with the traversal work counters on (lh2b_trace_stats): work per ray and SIMT utilisation of the two phases"""
+    core.TraceStatsEnable(True)
+    core.Render(view, converge)
+    st = core.TraceStatsRead()
+    core.TraceStatsEnable(False)
+    r = max(1, st["rays"])
+    return {"rays": st["rays"], "node_steps_per_ray": st["nodeSteps"] / r, "tri_tests_per_ray": st["triTests"] / r, "instance_entries_per_ray": st["instanceEntries"] / r,
+            "iterations_x32_per_ray": st["iterations"] * 32 / r, "node_phase_lanes": st["nodeLanes"] / max(1, st["nodePhases"]),
+            "tri_phase_lanes": st["triLanes"] / max(1, st["triPhases"])}
+
+
 if "c1" in which:
     # C1: the literal tinyapp scene (pica glTF + light quad + legocar.obj, camera.xml) as the reference's own RenderSystem hands it
     # to a core (recorded with oracle/_ref/libRenderCore_Recorder.so through oracle/_ref/tinyapp_ref_host), 640x360, 1 spp, path
@@ -39,24 +58,26 @@ if "c1" in which:
     else:
         sd = scenes.config2_scene(40, 30, n_materials=5, light_quads=1, floaters=1500, seed=42)
         view = scenes.view_pyramid((-19.17, 9.19, 33.1), (-13.5, 7.99, 24.95), 40, W, H, focal_distance=5.0, aperture=1e-4, distortion=0.05)
-    core = RenderCore(0); core.SetTarget(W, H, 1); core.Setting("epsilon", 1e-3); core.Setting("clampValue", 10); sd.upload(core)
+    core = RenderCore(0); core.SetTarget(W, H, 1); core.Setting("epsilon", 1e-3); core.Setting("clampValue", 10); overrides(core); sd.upload(core)
     core.SetProbePos(W // 2, H // 2)
     a = frame_stats(core, view, 6)
+    work = counted_frame(core, view)
     core.Render(view, 1); img = core.ReadPixels(); st = core.GetCoreStats()
     orc.set_accel(1)
     o = orc.FrameOracle(sd, W, H, 1, 1e-3, 10.0, 3, 1)
     o.render(view, 1)                                    # builds and caches the oracle's BVHs
     o = orc.FrameOracle(sd, W, H, 1, 1e-3, 10.0, 3, 1)
     t0 = time.perf_counter(); _, rec = o.render(view, 1, records=True); cpu_s = time.perf_counter() - t0
-    # the oracle frame above is frame 1 of its own sequence; rebuild one in lock-step with the core's 7th Restart frame
+    # the oracle frame above is frame 1 of its own sequence; rebuild one in lock-step with the core's 8th Restart frame
     o2 = orc.FrameOracle(sd, W, H, 1, 1e-3, 10.0, 3, 1)
-    for _ in range(7):
+    for _ in range(8):
         want = o2.render(view, 1)
     orc.set_accel(0)
     frac, rr, energy = rs.frames_agree(img, want)
     probe = rec[W // 2 + (H // 2) * W]["hit"]
     res["c1"] = {"scene": "tinyapp (pica/scene.gltf + light quad + legocar.obj) via the reference RenderSystem" if literal else "procedural stand-in",
                  "resolution": [W, H], "meshes": len(sd.meshes), "instances": len(sd.instances), "triangles": int(sum(len(t) for _, t in sd.meshes)),
+                 "stage_ms": {k: a[k] for k in ("generateExtendMs", "extendMs", "shadeMs", "connectMs", "finalizeMs")}, "traversal_work": work,
                  "gpu_ms_per_frame": a["totalMs"], "gpu_rays_per_frame": a["extensionRays"] + a["shadowRays"],
                  "gpu_mrays_per_s": (a["extensionRays"] + a["shadowRays"]) / a["totalMs"] / 1e3,
                  "flipped_pixel_fraction": float(frac), "rel_rmse_other_pixels": float(rr), "energy_difference": float(energy),
@@ -75,11 +96,12 @@ if "c3" in which:
     # two diffuse bounces allowed (the stock Optix7 build stops after one; stated as the variant)
     W, H, SPP = 1920, 1080, 16
     sd = scenes.config2_scene(1000, 500, n_materials=64, light_quads=8)
-    core = RenderCore(0); core.SetTarget(W, H, SPP); core.Setting("epsilon", 1e-3); core.Setting("maxPathLength", 8); core.Setting("maxDiffuseBounces", 2)
+    core = RenderCore(0); core.SetTarget(W, H, SPP); core.Setting("epsilon", 1e-3); core.Setting("maxPathLength", 8); core.Setting("maxDiffuseBounces", 2); overrides(core)
     sd.upload(core)
     view = scenes.view_pyramid((0, 30, -80), (0, 0, 0), 40, W, H)
     a = frame_stats(core, view, 5)
-    res["c3"] = {"resolution": [W, H], "spp": SPP, "max_path_length": 8, "max_diffuse_bounces": 2, "ms_per_frame": a["totalMs"],
+    work = counted_frame(core, view)
+    res["c3"] = {"traversal_work": work, "resolution": [W, H], "spp": SPP, "max_path_length": 8, "max_diffuse_bounces": 2, "ms_per_frame": a["totalMs"],
                  "samples_per_s": W * H * SPP / (a["totalMs"] * 1e-3), "mrays_per_s": (a["extensionRays"] + a["shadowRays"]) / a["totalMs"] / 1e3,
                  "stage_ms": {k: a[k] for k in ("generateExtendMs", "extendMs", "shadeMs", "connectMs", "finalizeMs")},
                  "extension_rays": a["extensionRays"], "shadow_rays": a["shadowRays"], "path_length_reached": a["pathLengthReached"]}
@@ -90,7 +112,7 @@ if "c4" in which:
     # C4: 10 meshes x 1M triangles, 1000 instances, per-frame vertex displacement on every mesh (same triangle count -> refit)
     # and new rigid transforms on every instance (top level rebuilt), 1080p, 1 spp
     W, H = 1920, 1080
-    core = RenderCore(0); core.SetTarget(W, H, 1); core.Setting("epsilon", 1e-3)
+    core = RenderCore(0); core.SetTarget(W, H, 1); core.Setting("epsilon", 1e-3); overrides(core)
     base = scenes.terrain(1000, 500, extent=6.0, seed=5)
     base[:, 1] *= 0.3
     mats = scenes.make_materials([dict(color=(0.7, 0.7, 0.7)), dict(color=(80, 80, 64))])
@@ -135,7 +157,8 @@ if "c4" in which:
                       {"rays": int(fs["extensionRays"]) + int(fs["shadowRays"])})
     refit_device = sum(float(core.GetBvhStats(m)["buildMs"]) for m in range(10))
     last = frames[-1]
-    res["c4"] = {"meshes": 10, "triangles_per_mesh": len(base) // 3, "instances": 1001, "vertex_upload_ms_per_frame": float(np.mean(upload_ms[1:])),
+    work = counted_frame(core, view)
+    res["c4"] = {"traversal_work": work, "meshes": 10, "triangles_per_mesh": len(base) // 3, "instances": 1001, "vertex_upload_ms_per_frame": float(np.mean(upload_ms[1:])),
                  "set_instance_calls_ms": float(np.mean(inst_ms[1:])), "finalize_instances_wall_ms": float(np.mean(build_ms[1:])),
                  "refit_device_ms_10_meshes": refit_device, "tlas_device_ms": last["buildMs"], "render_ms": last["totalMs"],
                  "trace_mrays_per_s": last["rays"] / (last["generateExtendMs"] + last["extendMs"] + last["connectMs"]) / 1e3, "frame": last}
@@ -176,7 +199,7 @@ if "c5" in which:
     # C5: the C3 scene at 3840x2160, 1 spp, SVGF filter + TAA, moving camera: ms per stage
     W, H = 3840, 2160
     sd = scenes.config2_scene(1000, 500, n_materials=64, light_quads=8)
-    core = RenderCore(0); core.SetTarget(W, H, 1); core.Setting("epsilon", 1e-3); core.Setting("filter", 1); core.Setting("TAA", 1)
+    core = RenderCore(0); core.SetTarget(W, H, 1); core.Setting("epsilon", 1e-3); core.Setting("filter", 1); core.Setting("TAA", 1); overrides(core)
     sd.upload(core)
     acc = {}
     n = 8
