@@ -368,13 +368,47 @@ struct AtrousArgs
 
 /* The block stages its tile plus the halo UNPACKED: every tile pixel is decoded once (5.11 fixed point -> float, luminances,
    10-bit normal, 10/11/11-bit albedo) instead of once per tap of every pixel that reads it (20 taps). Four float4 planes:
-     dir = direct.rgb, luminance | ind = indirect.rgb, luminance | nrm = normal.xyz, depth | alb = albedo.rgb, feature word w */
-template <int STEP, int BY> __global__ void __launch_bounds__( AT_BX * BY ) atrousKernel( const AtrousArgs a )
+     dir = direct.rgb, luminance | ind = indirect.rgb, luminance | nrm = normal.xyz, depth | alb = albedo.rgb, feature word w
+   ncu (profiles/r1_v4_filter_kernels_full.txt) had these kernels at 86-91 % of the L1 / shared-memory throughput (80 LDS.128 per
+   pixel) with the XU pipe next (five MUFU per tap: lg2 + ex2 of powf( x, 128 ), two exp, one reciprocal). Hence:
+     - a thread can filter PIX = 2 pixels STEP rows apart: four of the five tap rows of one are tap rows of the other, so a tap is
+       loaded once and weighed for both centres - 48 instead of 80 LDS.128 per pixel, at twice the registers. */
+struct AtrousCentre
 {
-	constexpr int HALO = 2 * STEP, TW = AT_BX + 2 * HALO, TH = BY + 2 * HALO;
+	float3 normal, color, dirSum, indSum;
+	float depth, ddx, ddy, lumDir, lumInd, rdir, rind, dirW, indW;
+	int matID;
+};
+
+template <int STEP> __device__ __forceinline__ void AtrousTap( AtrousCentre& c, const float4 nDir, const float4 nInd, const float4 nNrm, const float4 nAlb,
+	const int uu, const int vv, const int phase )
+{
+	const float w_dist = (uu * uu + vv * vv) * (-1.0f / 7.5f);
+	// x^128 stays powf (lg2 + ex2 on the XU pipe under --use_fast_math): the kernel is bound by the FMA pipe (ncu r2: FMUL / FFMA / FADD are
+	// 60 % of its instructions), seven squarings there measured slower than two MUFU here
+	const float p = powf( fmaxf( 0.0f, dot( xyz( nNrm ), c.normal ) ), 128 );
+	const float expected = c.depth + c.ddx * (float)(uu * STEP) + c.ddy * (float)(vv * STEP);
+	const float depthError = fabsf( expected - nNrm.w );
+	const float expectedDiff = fabsf( expected - c.depth );
+	const float w_depth = depthError / fmaxf( 0.00001f, (0.5f + phase * 0.5f) * expectedDiff );
+	const float w_normal = p * (((int)(__float_as_uint( nAlb.w ) >> 4) != c.matID) ? 0.0001f : dot( c.color, xyz( nAlb ) ));
+	float wd = w_normal * __expf( fabsf( c.lumDir - nDir.w ) * c.rdir + w_dist - w_depth );
+	float wi = w_normal * __expf( fabsf( c.lumInd - nInd.w ) * c.rind + w_dist - w_depth );
+	if (!isfinite( wd )) wd = 0;
+	if (!isfinite( wi )) wi = 0;
+	c.dirSum += xyz( nDir ) * wd, c.dirW += wd;
+	c.indSum += xyz( nInd ) * wi, c.indW += wi;
+}
+
+/* block: AT_BX x BY threads filter AT_BX x PIX*BY pixels; with PIX = 2 thread row ty owns the pixel rows base and base + STEP,
+   base = (ty / STEP) * 2 * STEP + ty % STEP */
+template <int STEP, int BY, int PIX> __global__ void __launch_bounds__( AT_BX * BY ) atrousKernel( const AtrousArgs a )
+{
+	constexpr int HALO = 2 * STEP, ROWS = PIX * BY, TW = AT_BX + 2 * HALO, TH = ROWS + 2 * HALO;
+	static_assert( PIX == 1 || BY % STEP == 0, "rows of a block must pair up" );
 	extern __shared__ float4 tile[];
 	float4* tDir = tile, * tInd = tile + TW * TH, * tNrm = tile + 2 * TW * TH, * tAlb = tile + 3 * TW * TH;
-	const int x0 = blockIdx.x * AT_BX, y0 = blockIdx.y * BY;
+	const int x0 = blockIdx.x * AT_BX, y0 = blockIdx.y * ROWS;
 	for (int i = threadIdx.y * AT_BX + threadIdx.x; i < TW * TH; i += AT_BX * BY)
 	{
 		const int ty = i / TW, tx = i - ty * TW;
@@ -389,120 +423,166 @@ template <int STEP, int BY> __global__ void __launch_bounds__( AT_BX * BY ) atro
 		}
 	}
 	__syncthreads();
-	const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
-	if (x >= a.w || y >= a.h) return;
-	const int pixelIdx = x + y * a.w, phase = a.phase;
-	const int cx = threadIdx.x + HALO, cy = threadIdx.y + HALO;
-	const float4 cDir = tDir[cx + cy * TW], cInd = tInd[cx + cy * TW], cNrm = tNrm[cx + cy * TW], cAlb = tAlb[cx + cy * TW];
-	const uint32_t lfw = __float_as_uint( cAlb.w );
-	const float3 localNormal = xyz( cNrm ), localColor = xyz( cAlb );
-	const int localMatID = lfw >> 4;
-	float dirW = 1, indW = 1;
-	float3 dirSum = xyz( cDir ), indSum = xyz( cInd );
-	const float localDirect = cDir.w, localIndirect = cInd.w;
-	const float localDepth = cNrm.w;
-	const float4 dd = a.deltaDepth[pixelIdx];
-	const float localDdx = dd.z, localDdy = dd.w;
+	const int x = x0 + threadIdx.x;
+	const int rowBase = PIX == 1 ? (int)threadIdx.y : ((int)threadIdx.y / STEP) * 2 * STEP + (int)threadIdx.y % STEP;	// row of the first pixel inside the block
+	if (x >= a.w || y0 + rowBase >= a.h) return;
+	const int phase = a.phase, cx = threadIdx.x + HALO;
 	const float sigma = 10.0f * OneOverPow2( phase - 1 );
-	const float factor = (lfw & 15) == 0 ? 400.0f : 1.0f;
-	const float4 m = a.moments[pixelIdx];
-	const float var_dir = m.y - m.x * m.x, var_ind = m.w - m.z * m.z;
-	const float rdir = -1.0f / (sigma * factor * sqrtf( var_dir + 0.00001f ) + 0.00001f);
-	const float rind = -1.0f / (sigma * factor * sqrtf( var_ind + 0.00001f ) + 0.00001f);
+	AtrousCentre c[PIX];
+	int cy[PIX], py[PIX];
+	bool live[PIX];
+	uint32_t lfw[PIX];
 #pragma unroll
-	for (int vv = -2; vv <= 2; vv++)
+	for (int k = 0; k < PIX; k++)
 	{
-		const int v = vv * STEP + y;
-		const int r = abs( vv ) == 2 ? 1 : 2;
+		py[k] = y0 + rowBase + k * STEP, cy[k] = rowBase + k * STEP + HALO, live[k] = py[k] < a.h;
+		const int pix = x + min( py[k], a.h - 1 ) * a.w;
+		const float4 cDir = tDir[cx + cy[k] * TW], cInd = tInd[cx + cy[k] * TW], cNrm = tNrm[cx + cy[k] * TW], cAlb = tAlb[cx + cy[k] * TW];
+		lfw[k] = __float_as_uint( cAlb.w );
+		c[k].normal = xyz( cNrm ), c[k].color = xyz( cAlb ), c[k].matID = lfw[k] >> 4;
+		c[k].dirW = 1, c[k].indW = 1, c[k].dirSum = xyz( cDir ), c[k].indSum = xyz( cInd );
+		c[k].lumDir = cDir.w, c[k].lumInd = cInd.w, c[k].depth = cNrm.w;
+		const float4 dd = a.deltaDepth[pix];
+		c[k].ddx = dd.z, c[k].ddy = dd.w;
+		const float factor = (lfw[k] & 15) == 0 ? 400.0f : 1.0f;
+		const float4 m = a.moments[pix];
+		const float var_dir = m.y - m.x * m.x, var_ind = m.w - m.z * m.z;
+		c[k].rdir = -1.0f / (sigma * factor * sqrtf( var_dir + 0.00001f ) + 0.00001f);
+		c[k].rind = -1.0f / (sigma * factor * sqrtf( var_ind + 0.00001f ) + 0.00001f);
+	}
+	// tap rows -2 .. 3 relative to the first pixel (in units of STEP): row r is row r of pixel 0 and row r - 1 of pixel 1
+#pragma unroll
+	for (int r = -2; r <= 1 + PIX; r++)
+	{
+		const int v = py[0] + r * STEP;
 		if (v >= 0 && v < a.h)
 		{
 #pragma unroll
-			for (int uu = -2; uu <= 2; uu++) if (abs( uu ) <= r && (uu != 0 || vv != 0))
+			for (int uu = -2; uu <= 2; uu++)
 			{
+				const int vv0 = r, vv1 = r - 1;
+				const bool use0 = vv0 <= 2 && abs( uu ) <= (abs( vv0 ) == 2 ? 1 : 2) && (uu != 0 || vv0 != 0);
+				const bool use1 = PIX == 2 && vv1 >= -2 && abs( uu ) <= (abs( vv1 ) == 2 ? 1 : 2) && (uu != 0 || vv1 != 0);
+				if (!use0 && !use1) continue;
 				// columns are clamped to the image by the tile loader, like the reference clamps u
-				const int ti = (cx + uu * STEP) + (cy + vv * STEP) * TW;
+				const int ti = (cx + uu * STEP) + (cy[0] + r * STEP) * TW;
 				const float4 nDir = tDir[ti], nInd = tInd[ti], nNrm = tNrm[ti], nAlb = tAlb[ti];
-				const float w_dist = (uu * uu + vv * vv) * (-1.0f / 7.5f);
-				float w_normal = powf( fmaxf( 0.0f, dot( xyz( nNrm ), localNormal ) ), 128 );
-				const float expected = localDepth + localDdx * (float)(uu * STEP) + localDdy * (float)(vv * STEP);
-				const float depthError = fabsf( expected - nNrm.w );
-				const float expectedDiff = fabsf( expected - localDepth );
-				const float w_depth = depthError / fmaxf( 0.00001f, (0.5f + phase * 0.5f) * expectedDiff );
-				w_normal *= ((int)(__float_as_uint( nAlb.w ) >> 4) != localMatID) ? 0.0001f : dot( localColor, xyz( nAlb ) );
-				float wd = w_normal * __expf( fabsf( localDirect - nDir.w ) * rdir + w_dist - w_depth );
-				float wi = w_normal * __expf( fabsf( localIndirect - nInd.w ) * rind + w_dist - w_depth );
-				if (!isfinite( wd )) wd = 0;
-				if (!isfinite( wi )) wi = 0;
-				dirSum += xyz( nDir ) * wd, dirW += wd;
-				indSum += xyz( nInd ) * wi, indW += wi;
+				if (use0) AtrousTap<STEP>( c[0], nDir, nInd, nNrm, nAlb, uu, vv0, phase );
+				if (use1) AtrousTap<STEP>( c[PIX - 1], nDir, nInd, nNrm, nAlb, uu, vv1, phase );
 			}
 		}
 	}
-	float3 dirF = dirSum * (1.0f / fmaxf( 0.0001f, dirW )), indF = indSum * (1.0f / fmaxf( 0.0001f, indW ));
-	if (STEP == 1 && phase == 1)
+#pragma unroll
+	for (int k = 0; k < PIX; k++)
 	{
-		// temporal blend with the previous frame's phase-1 output, clamped to the 3x3 YCoCg neighbourhood
-		const float2 pp = a.motion[pixelIdx];
-		const int px = (int)pp.x, py = (int)pp.y;
-		if (px >= 0 && px < a.w && py >= 0 && py < a.h)
+		if (!live[k]) continue;
+		const int y = py[k], pixelIdx = x + y * a.w;
+		const float3 localNormal = c[k].normal, localColor = c[k].color;
+		float3 dirF = c[k].dirSum * (1.0f / fmaxf( 0.0001f, c[k].dirW )), indF = c[k].indSum * (1.0f / fmaxf( 0.0001f, c[k].indW ));
+		if (STEP == 1 && phase == 1)
 		{
-			float3 prevDirect, prevIndirect;
-			const float4 localPos = a.worldPos[pixelIdx];
-			ReadTexelConsistent2( a.B, a.prevWorldPos, localPos, localNormal, pp.x, pp.y, a.w, a.h, prevDirect, prevIndirect );
-			if (prevDirect.x != -1)
+			// temporal blend with the previous frame's phase-1 output, clamped to the 3x3 YCoCg neighbourhood
+			const float2 pp = a.motion[pixelIdx];
+			const int px = (int)pp.x, pyy = (int)pp.y;
+			if (px >= 0 && px < a.w && pyy >= 0 && pyy < a.h)
 			{
-				prevDirect = RGBToYCoCg( prevDirect ), prevIndirect = RGBToYCoCg( prevIndirect );
-				float3 dirAvg = RGBToYCoCg( dirF ), dirVar = dirAvg * dirAvg, indAvg = RGBToYCoCg( indF ), indVar = indAvg * indAvg;
-				auto tap = [&]( const int ox, const int oy ) {
-					const int ti = (cx + ox) + (cy + oy) * TW;
-					const float3 f = RGBToYCoCg( xyz( tDir[ti] ) ), g = RGBToYCoCg( xyz( tInd[ti] ) );
-					dirAvg += f, dirVar += f * f, indAvg += g, indVar += g * g;
-				};
-				if (x > 1)
+				float3 prevDirect, prevIndirect;
+				const float4 localPos = a.worldPos[pixelIdx];
+				ReadTexelConsistent2( a.B, a.prevWorldPos, localPos, localNormal, pp.x, pp.y, a.w, a.h, prevDirect, prevIndirect );
+				if (prevDirect.x != -1)
 				{
-					if (y > 1) tap( -1, -1 );
-					tap( -1, 0 );
-					if (y < a.h - 1) tap( -1, 1 );
+					prevDirect = RGBToYCoCg( prevDirect ), prevIndirect = RGBToYCoCg( prevIndirect );
+					float3 dirAvg = RGBToYCoCg( dirF ), dirVar = dirAvg * dirAvg, indAvg = RGBToYCoCg( indF ), indVar = indAvg * indAvg;
+					auto tap = [&]( const int ox, const int oy ) {
+						const int ti = (cx + ox) + (cy[k] + oy) * TW;
+						const float3 f = RGBToYCoCg( xyz( tDir[ti] ) ), g = RGBToYCoCg( xyz( tInd[ti] ) );
+						dirAvg += f, dirVar += f * f, indAvg += g, indVar += g * g;
+					};
+					if (x > 1)
+					{
+						if (y > 1) tap( -1, -1 );
+						tap( -1, 0 );
+						if (y < a.h - 1) tap( -1, 1 );
+					}
+					if (y > 1) tap( 0, -1 );
+					if (y < a.h - 1) tap( 0, 1 );
+					if (x < a.w - 1)
+					{
+						if (y > 1) tap( 1, -1 );
+						tap( 1, 0 );
+						if (y < a.h - 1) tap( 1, 1 );
+					}
+					dirAvg *= 1.0f / 9.0f, dirVar *= 1.0f / 9.0f, indAvg *= 1.0f / 9.0f, indVar *= 1.0f / 9.0f;
+					float3 sDir = max3v( f3( 0 ), dirVar - dirAvg * dirAvg ), sInd = max3v( f3( 0 ), indVar - indAvg * indAvg );
+					sDir = make_float3( sqrtf( sDir.x ), sqrtf( sDir.y ), sqrtf( sDir.z ) ), sInd = make_float3( sqrtf( sInd.x ), sqrtf( sInd.y ), sqrtf( sInd.z ) );
+					prevDirect = clamp3( prevDirect, dirAvg - 0.75f * sDir, dirAvg + 0.75f * sDir );
+					prevIndirect = clamp3( prevIndirect, indAvg - 0.75f * sInd, indAvg + 0.75f * sInd );
+					dirF = dirF * 0.1f + YCoCgToRGB( prevDirect ) * 0.9f;
+					indF = indF * 0.1f + YCoCgToRGB( prevIndirect ) * 0.9f;
 				}
-				if (y > 1) tap( 0, -1 );
-				if (y < a.h - 1) tap( 0, 1 );
-				if (x < a.w - 1)
-				{
-					if (y > 1) tap( 1, -1 );
-					tap( 1, 0 );
-					if (y < a.h - 1) tap( 1, 1 );
-				}
-				dirAvg *= 1.0f / 9.0f, dirVar *= 1.0f / 9.0f, indAvg *= 1.0f / 9.0f, indVar *= 1.0f / 9.0f;
-				float3 sDir = max3v( f3( 0 ), dirVar - dirAvg * dirAvg ), sInd = max3v( f3( 0 ), indVar - indAvg * indAvg );
-				sDir = make_float3( sqrtf( sDir.x ), sqrtf( sDir.y ), sqrtf( sDir.z ) ), sInd = make_float3( sqrtf( sInd.x ), sqrtf( sInd.y ), sqrtf( sInd.z ) );
-				prevDirect = clamp3( prevDirect, dirAvg - 0.75f * sDir, dirAvg + 0.75f * sDir );
-				prevIndirect = clamp3( prevIndirect, indAvg - 0.75f * sInd, indAvg + 0.75f * sInd );
-				dirF = dirF * 0.1f + YCoCgToRGB( prevDirect ) * 0.9f;
-				indF = indF * 0.1f + YCoCgToRGB( prevIndirect ) * 0.9f;
 			}
 		}
+		if (a.lastPass)
+		{
+			const float3 o = (dirF + indF) * localColor;
+			a.C[pixelIdx] = make_float4( sqrtf( o.x ), sqrtf( o.y ), sqrtf( o.z ), 1 );
+		}
+		else a.C[pixelIdx] = CombineToFloat4( dirF, indF );
 	}
-	if (a.lastPass)
+}
+
+/* ---- tile staging with the TMA engine ---------------------------------------------------------------------------------------
+   The 3x3-neighbourhood kernels (TAA, present) read a 34 x 10 float4 tile of one buffer. A tile row is 544 contiguous bytes in
+   global memory, so the rows are fetched with bulk asynchronous copies (cp.async.bulk, SASS UBLKCP - the TMA engine without a
+   tensor map) that signal an mbarrier: ten threads issue one copy each, nobody moves data through registers. Rows are clamped to
+   the image by choosing the source row; blocks that touch the left / right image edge need clamped columns and take the plain
+   path. (An out-of-image halo texel is never used by these kernels - their taps are guarded - so any value will do there.) */
+__device__ __forceinline__ uint32_t SmemAddr( const void* p ) { return (uint32_t)__cvta_generic_to_shared( p ); }
+
+__device__ __forceinline__ void LoadTile34x10( float4 (*tile)[34], uint64_t* bar, const float4* __restrict__ src, const int x0, const int y0, const int w, const int h )
+{
+	const int t = threadIdx.y * 32 + threadIdx.x;
+	if (x0 >= 1 && x0 + 33 <= w)	// block-uniform
 	{
-		const float3 c = (dirF + indF) * localColor;
-		a.C[pixelIdx] = make_float4( sqrtf( c.x ), sqrtf( c.y ), sqrtf( c.z ), 1 );
+		constexpr uint32_t ROW_BYTES = 34 * sizeof( float4 );
+		if (t == 0)
+		{
+			asm volatile( "mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"( SmemAddr( bar ) ) );
+			asm volatile( "fence.mbarrier_init.release.cluster;" ::: "memory" );
+			asm volatile( "mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"( SmemAddr( bar ) ), "r"( 10 * ROW_BYTES ) : "memory" );
+		}
+		__syncthreads();
+		if (t < 10)
+		{
+			const int gy = min( max( y0 - 1 + t, 0 ), h - 1 );
+			const float4* row = src + (x0 - 1) + (size_t)gy * w;
+			asm volatile( "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+				:: "r"( SmemAddr( &tile[t][0] ) ), "l"( row ), "r"( ROW_BYTES ), "r"( SmemAddr( bar ) ) : "memory" );
+		}
+		uint32_t done = 0;
+		while (!done)
+			asm volatile( "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"( done ) : "r"( SmemAddr( bar ) ) : "memory" );
 	}
-	else a.C[pixelIdx] = CombineToFloat4( dirF, indF );
+	else
+	{
+		for (int i = t; i < 340; i += 256)
+		{
+			const int ty = i / 34, tx = i - ty * 34;
+			const int gx = min( max( x0 - 1 + tx, 0 ), w - 1 ), gy = min( max( y0 - 1 + ty, 0 ), h - 1 );
+			tile[ty][tx] = src[gx + gy * w];
+		}
+		__syncthreads();
+	}
 }
 
 /* ---- TAA (finalize_shared.h:498-548) ------------------------------------------------------------------------------ */
 __global__ void __launch_bounds__( 256 ) taaKernel( const float4* __restrict__ pixelsIn, float4* __restrict__ pixelsOut, const float4* __restrict__ prevPixels,
 	const float2* __restrict__ motion, const int w, const int h )
 {
-	__shared__ float4 tile[10][34];
+	__shared__ __align__( 16 ) float4 tile[10][34];
+	__shared__ __align__( 8 ) uint64_t tileBar;
 	const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 8;
-	for (int i = threadIdx.y * 32 + threadIdx.x; i < 340; i += 256)
-	{
-		const int ty = i / 34, tx = i - ty * 34;
-		const int gx = min( max( x0 - 1 + tx, 0 ), w - 1 ), gy = min( max( y0 - 1 + ty, 0 ), h - 1 );
-		tile[ty][tx] = pixelsIn[gx + gy * w];
-	}
-	__syncthreads();
+	LoadTile34x10( tile, &tileBar, pixelsIn, x0, y0, w, h );
 	const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
 	if (x >= w || y >= h) return;
 	const int pixelIdx = x + y * w, cx = threadIdx.x + 1, cy = threadIdx.y + 1;
@@ -556,15 +636,10 @@ __global__ void __launch_bounds__( 256 ) taaKernel( const float4* __restrict__ p
 /* ---- present: unsharpenTAAKernel (:554-583) or finalizeNoTAAKernel (:589-600); border pixels are left untouched ---- */
 __global__ void __launch_bounds__( 256 ) presentKernel( const float4* __restrict__ pixels, float4* __restrict__ target, const int w, const int h, const int taa )
 {
-	__shared__ float4 tile[10][34];
+	__shared__ __align__( 16 ) float4 tile[10][34];
+	__shared__ __align__( 8 ) uint64_t tileBar;
 	const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 8;
-	for (int i = threadIdx.y * 32 + threadIdx.x; i < 340; i += 256)
-	{
-		const int ty = i / 34, tx = i - ty * 34;
-		const int gx = min( max( x0 - 1 + tx, 0 ), w - 1 ), gy = min( max( y0 - 1 + ty, 0 ), h - 1 );
-		tile[ty][tx] = pixels[gx + gy * w];
-	}
-	__syncthreads();
+	LoadTile34x10( tile, &tileBar, pixels, x0, y0, w, h );
 	const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
 	if (x == 0 || y == 0 || x >= w - 1 || y >= h - 1) return;
 	const int cx = threadIdx.x + 1, cy = threadIdx.y + 1;
@@ -622,26 +697,28 @@ static void FilterChainImpl( const FilterBuffers& b, const FilterSettings& s, cu
 	AtrousArgs aa;
 	aa.features = b.features, aa.prevWorldPos = b.prevWorldPos, aa.worldPos = b.worldPos, aa.deltaDepth = b.deltaDepth, aa.motion = b.motion, aa.moments = b.moments;
 	aa.w = w, aa.h = h;
-	// block heights: 8 rows for step 1, 16 for steps 2 and 4 (amortises the 2 * step halo); 64 bytes of tile per pixel
-	auto smem = []( int step, int by ) { return (size_t)(AT_BX + 4 * step) * (by + 4 * step) * 64; };
+	// step 1: 32 x 8 threads, one pixel each (62 registers, 8 blocks / SM); steps 2 and 4: 32 x 8 threads, two pixels STEP rows apart each
+	// (the halo of 2 * STEP pixels is amortised over 16 rows and every tap is weighed for both) - measured per pass at 4K in
+	// profiles/r2_reference_kernels.json; 64 bytes of tile per pixel
+	auto smem = []( int step, int rows ) { return (size_t)(AT_BX + 4 * step) * (rows + 4 * step) * 64; };
 	static bool attr = false;
 	if (!attr)
 	{
-		cudaFuncSetAttribute( atrousKernel<2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem( 2, 16 ) );
-		cudaFuncSetAttribute( atrousKernel<4, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem( 4, 16 ) );
+		cudaFuncSetAttribute( atrousKernel<2, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem( 2, 16 ) );
+		cudaFuncSetAttribute( atrousKernel<4, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem( 4, 16 ) );
 		attr = true;
 	}
-	const dim3 grid16( (w + 31) / 32, (h + 15) / 16 ), block16( 32, 16 );
+	const dim3 grid16( (w + 31) / 32, (h + 15) / 16 );
 	aa.A = b.shading, aa.B = b.filteredIN, aa.C = b.filteredOUT, aa.phase = 1, aa.lastPass = 0;
-	atrousKernel<1, 8><<<grid, block, smem( 1, 8 ), st>>>( aa );
+	atrousKernel<1, 8, 1><<<grid, block, smem( 1, 8 ), st>>>( aa );
 	mark( 2 );
 	snap( hP1, b.filteredOUT );
 	aa.A = b.filteredOUT, aa.B = nullptr, aa.C = b.filteredIN, aa.phase = 2;
-	atrousKernel<2, 16><<<grid16, block16, smem( 2, 16 ), st>>>( aa );
+	atrousKernel<2, 8, 2><<<grid16, block, smem( 2, 16 ), st>>>( aa );
 	mark( 3 );
 	snap( hP2, b.filteredIN );
 	aa.A = b.filteredIN, aa.C = b.shading, aa.phase = 3, aa.lastPass = 1;
-	atrousKernel<4, 16><<<grid16, block16, smem( 4, 16 ), st>>>( aa );
+	atrousKernel<4, 8, 2><<<grid16, block, smem( 4, 16 ), st>>>( aa );
 	mark( 4 );
 	snap( hP3, b.shading );
 	if (s.taa)
