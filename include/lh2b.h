@@ -232,6 +232,14 @@ LH2B_API int lh2b_shade_paths_time( lh2b_core* core, int pathLength, int n, cons
    features uint4[w*h], worldPos / deltaDepth float4[w*h], accumulator2 float4[2*w*h] (direct, then indirect). */
 LH2B_API int lh2b_read_filter_buffers( lh2b_core* core, uint32_t* features, float* worldPos, float* deltaDepth, float* accumulator2 );
 
+/* Presenting through CUDA-OpenGL interop, as the reference's InteropTexture does (lib/CUDA/shared_host_code/interoptexture.cpp:53-61:
+   cudaGraphicsGLRegisterImage on GLTexture::ID, map, write, unmap): copies the finished frame from the core's linear RGBA32F
+   pixel buffer into the GL_RGBA32F texture 'glTextureId' on the device - no host round trip. Must be called from the thread that owns
+   the GL context, after the frame is finished (lh2b_wait_for_render or a synchronous lh2b_render). The texture is registered on
+   first use and re-registered when the id or the target size changes. Returns non-zero (see lh2b_last_error) when the process has no
+   usable GL context or the texture cannot be registered - the C++ class then falls back to glTexSubImage2D from host memory. */
+LH2B_API int lh2b_present_gl( lh2b_core* core, unsigned int glTextureId );
+
 /* The C handle behind a CoreAPI_Base* obtained from CreateCore() (for headless read-back and statistics). */
 LH2B_API lh2b_core* lh2b_handle_of( void* coreApiBase );
 

@@ -77,6 +77,7 @@ SIGNATURES = {
     "lh2b_get_frame_stats": ([_vp, _vp], _ip),
     "lh2b_get_bvh_stats": ([_vp, _ip, _vp], _ip),
     "lh2b_handle_of": ([_vp], _vp),
+    "lh2b_present_gl": ([_vp, _c.c_uint], _ip),
     "lh2b_filter_chain": ([_vp, _vp], _ip),
     "lh2b_shade_paths_time": ([_vp, _ip, _ip, _vp, _vp, _vp, _vp, _c.c_uint, _c.c_uint, _ip, _ip, _vp], _ip),
     "lh2b_read_filter_buffers": ([_vp, _vp, _vp, _vp, _vp], _ip),

@@ -116,6 +116,9 @@ struct lh2b_core
 	cudaStream_t copyStream = nullptr;
 	cudaStream_t connectStream = nullptr;	// connect( L ) runs here, next to extend( L + 1 ) on the launch stream (Setting "overlapConnect")
 	int overlapConnect = 1;
+	// CUDA-GL interop present path (lh2b_present_gl): the registered target texture
+	struct cudaGraphicsResource* glResource = nullptr;
+	unsigned glRegisteredTexture = 0; int glRegisteredW = 0, glRegisteredH = 0;
 	cudaEvent_t frameDone = nullptr, copyDone[2] = { nullptr, nullptr };
 	bool copyPending[2] = { false, false };
 	lh2b::DevBuf<lh2b::DevCounters> counters;

@@ -10,8 +10,10 @@
    Presenting: the reference writes into an OpenGL texture through CUDA-GL interop
    (lib/CUDA/shared_host_code/interoptexture.cpp:53). This core renders to a linear RGBA32F device
    buffer. If the host process has OpenGL loaded and the target texture ID is non-zero, the finished
-   frame is additionally uploaded with glTexSubImage2D (resolved at run time; no link dependency),
-   which is enough for the reference's windowed apps to show the image.
+   frame is copied into that texture on the device through the same interop (lh2b_present_gl:
+   cudaGraphicsGLRegisterImage + map + cudaMemcpy2DToArray); if the texture cannot be registered
+   the frame is uploaded with glTexSubImage2D from host memory instead (resolved at run time; no
+   link dependency on OpenGL either way).
 
    Personas: the reference ships the plain path tracer and the filtering path tracer as two libraries
    (RenderCore_Optix7, RenderCore_Optix7Filter) and RenderSystem sends "filter", "TAA", "clampDirect",
@@ -105,6 +107,13 @@ private:
 	void Present()
 	{
 		if (glTexture == 0 || width <= 0) return;
+		// first choice: CUDA-GL interop, device to device, like the reference's InteropTexture (interoptexture.cpp:53-61); it needs a current GL
+		// context - when there is none (or registration fails once) fall back to an upload from host memory
+		if (interop && dlsym( RTLD_DEFAULT, "glBindTexture" ))
+		{
+			if (lh2b_present_gl( core, glTexture ) == 0) return;
+			interop = false;
+		}
 		static glBindTextureFn bind = (glBindTextureFn)dlsym( RTLD_DEFAULT, "glBindTexture" );
 		static glTexSubImage2DFn sub = (glTexSubImage2DFn)dlsym( RTLD_DEFAULT, "glTexSubImage2D" );
 		if (!bind || !sub) return;	// headless process: the image stays in the linear buffer
@@ -114,7 +123,7 @@ private:
 		sub( 0x0DE1, 0, 0, 0, width, height, 0x1908 /* GL_RGBA */, 0x1406 /* GL_FLOAT */, staging.data() );
 	}
 	lh2b_core* core = nullptr;
-	bool filterCore = false;
+	bool filterCore = false, interop = true;
 	unsigned glTexture = 0;
 	int width = 0, height = 0;
 	std::vector<float> staging;

@@ -66,6 +66,7 @@ void InitRenderState( lh2b_core* core )
 
 void ReleaseRenderState( lh2b_core* core )
 {
+	if (core->glResource) cudaGraphicsUnregisterResource( core->glResource ), core->glResource = nullptr;
 	for (auto& e : core->events) cudaEventDestroy( e );
 	for (auto& e : core->eventsB) cudaEventDestroy( e );
 	core->events.clear(), core->eventsB.clear();
@@ -333,6 +334,12 @@ static uint32_t ToChar( float a ) { return (uint32_t)(a * 255.0f); }	// truncati
 static uint32_t Pack4( float a, float b, float c, float d ) { return ToChar( a ) + (ToChar( b ) << 8) + (ToChar( c ) << 16) + (ToChar( d ) << 24); }
 static uint32_t HalfBits( float f ) { const __half h = __float2half_rn( f ); unsigned short u; memcpy( &u, &h, 2 ); return u; }
 
+static void ReleaseGlTarget( lh2b_core* core )
+{
+	if (core->glResource) cudaGraphicsUnregisterResource( core->glResource );
+	core->glResource = nullptr, core->glRegisteredTexture = 0;
+}
+
 template <typename V> static uint4 MakeMap( const lh2b_core* core, const V& v )
 {
 	// CUDAMaterial::Map { short width, height; half uscale, vscale, uoffs, voffs; uint addr } (core_settings.h:141, rendercore.h:78-85)
@@ -353,9 +360,12 @@ int lh2b_set_target( lh2b_core* core, int width, int height, int spp )
 	API_BEGIN
 	if (width <= 0 || height <= 0 || spp <= 0) throw CoreError( "SetTarget: width, height and spp must be positive" );
 	if ((unsigned long long)width * height * spp >= (1ull << 26)) throw CoreError( "SetTarget: w*h*spp must stay below 2^26 (path index is packed above 6 flag bits)" );
+	if ((core->gather || core->deferTail) && (width != core->width || height != core->height || spp != core->spp))
+		throw CoreError( "SetTarget: a multi-GPU gatherer is attached to this core (its peer buffers are sized for the current target); destroy it first" );
 	FinishFrame( core );
 	CUDA_CHECK( cudaStreamSynchronize( core->copyStream ) );
 	core->copyPending[0] = core->copyPending[1] = false;
+	if (core->glResource && (width != core->glRegisteredW || height != core->glRegisteredH)) ReleaseGlTarget( core );
 	core->width = width, core->height = height, core->spp = spp;
 	const size_t pixels = (size_t)width * height;
 	if (pixels > core->maxPixels || spp != core->allocatedSpp)
@@ -383,7 +393,12 @@ int lh2b_setting( lh2b_core* core, const char* name, float value )
 	else if (!strcmp( name, "clampValue" )) core->clampValue = value;
 	else if (!strcmp( name, "noiseShift" )) { /* accepted and unused, as in the reference (rendercore.cpp:756-759) */ }
 	// the filter core's settings (lib/RenderCore_Optix7Filter/rendercore.cpp:656-678); RenderSystem sends them to every core
-	else if (!strcmp( name, "filter" )) { const bool on = value > 0; if (on != core->filterEnabled) core->filterEnabled = on, core->filterHistoryValid = false, core->samplesTaken = 0; }
+	else if (!strcmp( name, "filter" ))
+	{
+		const bool on = value > 0;
+		if (on != core->filterEnabled && (core->gather || core->deferTail)) throw CoreError( "Setting filter: a multi-GPU gatherer is attached to this core; destroy it first" );
+		if (on != core->filterEnabled) core->filterEnabled = on, core->filterHistoryValid = false, core->samplesTaken = 0;
+	}
 	else if (!strcmp( name, "TAA" )) core->taaEnabled = value > 0;
 	else if (!strcmp( name, "clampDirect" )) core->clampDirect = value;
 	else if (!strcmp( name, "clampIndirect" )) core->clampIndirect = value;
@@ -495,7 +510,7 @@ int lh2b_set_lights( lh2b_core* core, const void* tri, int nTri, const void* poi
 {
 	API_BEGIN
 	FinishFrame( core );
-	if (nTri + nPoint + nSpot + nDir > 64) throw CoreError( "SetLights: at most 64 lights are importance sampled (MAXISLIGHTS, lights_shared.h:26)" );
+	// (more than MAXISLIGHTS = 64 lights in total: the shade kernel picks uniformly instead of by potential - shade_kernels.cu LightPickProb)
 	UploadLights( core, core->triLights, tri, nTri, 6 ), UploadLights( core, core->pointLights, point, nPoint, 2 );
 	UploadLights( core, core->spotLights, spot, nSpot, 3 ), UploadLights( core, core->dirLights, dir, nDir, 2 );
 	core->lightCounts[0] = nTri, core->lightCounts[1] = nPoint, core->lightCounts[2] = nSpot, core->lightCounts[3] = nDir;
@@ -611,6 +626,39 @@ int lh2b_wait_read_pixels( lh2b_core* core )
 	API_BEGIN
 	CUDA_CHECK( cudaStreamSynchronize( core->copyStream ) );
 	core->copyPending[0] = core->copyPending[1] = false;
+	API_END
+}
+
+/* declared here instead of including cuda_gl_interop.h, which needs the OpenGL headers; the symbol lives in the CUDA runtime */
+extern "C" cudaError_t cudaGraphicsGLRegisterImage( struct cudaGraphicsResource** resource, unsigned int image, unsigned int target, unsigned int flags );
+
+int lh2b_present_gl( lh2b_core* core, unsigned int glTextureId )
+{
+	API_BEGIN
+	if (glTextureId == 0 || core->width <= 0) throw CoreError( "present_gl: no target" );
+	FinishFrame( core );
+	if (core->glResource && (core->glRegisteredTexture != glTextureId || core->glRegisteredW != core->width || core->glRegisteredH != core->height)) ReleaseGlTarget( core );
+	if (!core->glResource)
+	{
+		// interoptexture.cpp:53: cudaGraphicsGLRegisterImage( &res, ID, GL_TEXTURE_2D, cudaGraphicsMapFlagsWriteDiscard )
+		const cudaError_t e = cudaGraphicsGLRegisterImage( &core->glResource, glTextureId, 0x0DE1 /* GL_TEXTURE_2D */, cudaGraphicsRegisterFlagsWriteDiscard );
+		if (e != cudaSuccess)
+		{
+			core->glResource = nullptr;
+			cudaGetLastError();	// not sticky: clear it
+			throw CoreError( std::string( "present_gl: cudaGraphicsGLRegisterImage: " ) + cudaGetErrorString( e ) );
+		}
+		core->glRegisteredTexture = glTextureId, core->glRegisteredW = core->width, core->glRegisteredH = core->height;
+	}
+	cudaStream_t s = core->stream;
+	CUDA_CHECK( cudaGraphicsMapResources( 1, &core->glResource, s ) );
+	cudaArray_t array = nullptr;
+	cudaError_t e = cudaGraphicsSubResourceGetMappedArray( &array, core->glResource, 0, 0 );
+	if (e == cudaSuccess) e = cudaMemcpy2DToArrayAsync( array, 0, 0, core->pixels.ptr, (size_t)core->width * sizeof( float4 ), (size_t)core->width * sizeof( float4 ),
+		(size_t)core->height, cudaMemcpyDeviceToDevice, s );
+	cudaGraphicsUnmapResources( 1, &core->glResource, s );
+	if (e != cudaSuccess) throw CoreError( std::string( "present_gl: copy into the mapped texture: " ) + cudaGetErrorString( e ) );
+	CUDA_CHECK( cudaStreamSynchronize( s ) );
 	API_END
 }
 
@@ -830,6 +878,7 @@ int lh2b_set_row_band_strided( lh2b_core* core, int y0, int y1, int stepTileRows
 	API_BEGIN
 	if (y0 < 0 || y1 < y0 || (core->height > 0 && y1 > core->height) || stepTileRows < 1) throw CoreError( "set_row_band: rows out of range" );
 	if (stepTileRows > 1 && ((y0 | y1 | core->height) & 3)) throw CoreError( "set_row_band_strided: strided bands need rows in multiples of 4" );
+	if (y1 > y0 && (y0 & 3)) throw CoreError( "set_row_band: the first row of a band must be a multiple of 4 (bands are made of 4-row tile rows)" );
 	FinishFrame( core );
 	core->bandY0 = y0, core->bandY1 = y1, core->bandStep = stepTileRows, core->samplesTaken = 0;
 	API_END

@@ -326,8 +326,12 @@ __device__ __forceinline__ float LightPotentials( const RenderParams& p, float* 
 	return sum;
 }
 
+/* More than MAXISLIGHTS lights: the reference's importance sampling overruns potential[MAXISLIGHTS] (undefined behaviour); this core
+   then takes the reference's other branch - the #else of ISLIGHTS, lights_shared.h:256-260: uniform pick, pickProb = 1 / lightCount. */
+__device__ __forceinline__ int LightTotal( const RenderParams& p ) { return NTRI( p ) + p.lightCounts.y + p.lightCounts.z + p.lightCounts.w; }
 __device__ __forceinline__ float LightPickProb( const RenderParams& p, const int idx, const float3 O, const float3 N, const float3 I )
 {
+	if (LightTotal( p ) > MAXISLIGHTS) return 1.0f / (float)LightTotal( p );
 	float potential[MAXISLIGHTS];
 	const float sum = LightPotentials( p, potential, O, N, I, f3( -1 ) );
 	if (sum <= 0) return 0;
@@ -340,15 +344,19 @@ __device__ __forceinline__ float3 RandomPointOnLight( const RenderParams& p, con
 	const int nTri = NTRI( p ), nPoint = p.lightCounts.y, nSpot = p.lightCounts.z, nDir = p.lightCounts.w;
 	const float lightCount = nTri + nPoint + nSpot + nDir;
 	const float3 bary = RandomBarycentrics( r0 );
-	float potential[MAXISLIGHTS];
-	const float sum = LightPotentials( p, potential, I, N, I, bary );
-	if (sum <= 0) { lightPdf = 0; return f3( 1 ); }
-	const int lights = (int)lightCount;
-	r1 *= sum;
-	float total = 0;
 	int lightIdx = 0;
-	for (int i = 0; i < lights; i++) { total += potential[i]; if (total >= r1) { lightIdx = i; break; } }
-	pickProb = potential[lightIdx] / sum;
+	if (lightCount > MAXISLIGHTS) pickProb = 1.0f / lightCount, lightIdx = (int)(r1 * lightCount);
+	else
+	{
+		float potential[MAXISLIGHTS];
+		const float sum = LightPotentials( p, potential, I, N, I, bary );
+		if (sum <= 0) { lightPdf = 0; return f3( 1 ); }
+		const int lights = (int)lightCount;
+		r1 *= sum;
+		float total = 0;
+		for (int i = 0; i < lights; i++) { total += potential[i]; if (total >= r1) { lightIdx = i; break; } }
+		pickProb = potential[lightIdx] / sum;
+	}
 	lightIdx = max( 0, min( lightIdx, (int)lightCount - 1 ) );
 	if (lightIdx < nTri)
 	{

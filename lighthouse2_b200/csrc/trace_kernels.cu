@@ -5,7 +5,9 @@
 #include "kernels.h"
 #include "render_types.h"
 #include "traverse.cuh"
-#define WIDE_MIN_BLOCKS 8		// resident blocks per SM the traversal kernels are compiled for (64 registers per thread)
+#ifndef WIDE_MIN_BLOCKS
+#define WIDE_MIN_BLOCKS 9		// resident blocks per SM the traversal kernels are compiled for (56 registers per thread, no spills)
+#endif
 #include "traverse_wide.cuh"
 
 namespace lh2b
@@ -30,7 +32,7 @@ struct BufferRaySource
 	const float4* __restrict__ O4; const float4* __restrict__ D4; bool shadow;
 	__device__ __forceinline__ bool Load( const uint32_t i, WideRay& r, uint32_t& tag ) const
 	{
-		const float4 o = O4[i], d = D4[i];
+		const float4 o = __ldcs( O4 + i ), d = __ldcs( D4 + i );	// streamed once: evict-first, the BVH keeps the L2
 		r.O = make_float3( o.x, o.y, o.z ), r.D = make_float3( d.x, d.y, d.z );
 		r.tmin = 0.0f, r.tmax = shadow ? d.w : 1e34f;
 		tag = i;
@@ -41,7 +43,7 @@ struct BufferRaySource
 struct HitBufferSink
 {
 	float4* __restrict__ hits;
-	__device__ __forceinline__ void Closest( const uint32_t i, const bool hit, const TraceResult& r ) const { hits[i] = PackHit( hit, r ); }
+	__device__ __forceinline__ void Closest( const uint32_t i, const bool hit, const TraceResult& r ) const { __stcs( hits + i, PackHit( hit, r ) ); }
 	__device__ __forceinline__ void AnyHit( const uint32_t, const bool ) const {}
 };
 
@@ -59,7 +61,7 @@ struct ConnectSink
 	__device__ __forceinline__ void AnyHit( const uint32_t i, const bool occluded ) const
 	{
 		if (occluded) return;
-		const float4 e = E4[i];
+		const float4 e = __ldcs( E4 + i );
 		atomicAdd( accumulator + __float_as_int( e.w ), make_float4( e.x, e.y, e.z, 1 ) );
 	}
 };
@@ -144,8 +146,8 @@ template <bool BAND> struct TiledPrimarySource	// BAND: tile-sharded frame (this
 		tag = pathIdx;
 		GeneratePrimaryAt( *p, (int)x, (int)y, s, pathIdx, r.O, r.D );
 		r.tmin = 0.0f, r.tmax = 1e34f;
-		outO[pathIdx] = make_float4( r.O.x, r.O.y, r.O.z, __uint_as_float( (pathIdx << 6) + 1 /* S_SPECULAR */ ) );
-		outD[pathIdx] = make_float4( r.D.x, r.D.y, r.D.z, 0 );
+		__stcs( outO + pathIdx, make_float4( r.O.x, r.O.y, r.O.z, __uint_as_float( (pathIdx << 6) + 1 /* S_SPECULAR */ ) ) );
+		__stcs( outD + pathIdx, make_float4( r.D.x, r.D.y, r.D.z, 0 ) );
 		return true;
 	}
 };
@@ -153,7 +155,7 @@ template <bool BAND> struct TiledPrimarySource	// BAND: tile-sharded frame (this
 struct TiledHitSink
 {
 	float4* __restrict__ hits;
-	__device__ __forceinline__ void Closest( const uint32_t pathIdx, const bool hit, const TraceResult& r ) const { hits[pathIdx] = PackHit( hit, r ); }
+	__device__ __forceinline__ void Closest( const uint32_t pathIdx, const bool hit, const TraceResult& r ) const { __stcs( hits + pathIdx, PackHit( hit, r ) ); }
 	__device__ __forceinline__ void AnyHit( const uint32_t, const bool ) const {}
 };
 

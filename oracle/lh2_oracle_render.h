@@ -365,8 +365,12 @@ static inline float LightPotentials( const RenderScene& s, float* potential, V3 
 	}
 	return sum;
 }
+/* More than MAXISLIGHTS (64) lights: the reference's importance sampling would overrun its potential[64] array (lights_shared.h:225-240,
+   undefined behaviour). Both the CUDA core and this oracle then take the reference's own other branch (its #else of ISLIGHTS,
+   lights_shared.h:256-260): a uniform pick, pickProb = 1 / lightCount. */
 static inline float LightPickProb( const RenderScene& s, int idx, V3 O, V3 N, V3 I )
 {
+	if (LightTotal( s ) > 64) return 1.0f / (float)LightTotal( s );
 	float potential[64];
 	const float sum = LightPotentials( s, potential, O, N, I, v3( -1 ) );
 	if (sum <= 0) return 0;
@@ -377,14 +381,18 @@ static inline V3 RandomPointOnLight( const RenderScene& s, float r0, float r1, V
 	const int nTri = s.triLightCount & 0xffff, nPoint = s.pointLightCount, nSpot = s.spotLightCount;
 	const int lightCount = LightTotal( s );
 	const V3 bary = RandomBarycentrics( r0 );
-	float potential[64];
-	const float sum = LightPotentials( s, potential, I, N, I, bary );
-	if (sum <= 0) { lightPdf = 0; return v3( 1 ); }
-	r1 *= sum;
-	float total = 0;
 	int lightIdx = 0;
-	for (int i = 0; i < lightCount; i++) { total += potential[i]; if (total >= r1) { lightIdx = i; break; } }
-	pickProb = potential[lightIdx] / sum;
+	if (lightCount > 64) pickProb = 1.0f / (float)lightCount, lightIdx = (int)(r1 * (float)lightCount);
+	else
+	{
+		float potential[64];
+		const float sum = LightPotentials( s, potential, I, N, I, bary );
+		if (sum <= 0) { lightPdf = 0; return v3( 1 ); }
+		r1 *= sum;
+		float total = 0;
+		for (int i = 0; i < lightCount; i++) { total += potential[i]; if (total >= r1) { lightIdx = i; break; } }
+		pickProb = potential[lightIdx] / sum;
+	}
 	if (lightIdx > lightCount - 1) lightIdx = lightCount - 1;
 	if (lightIdx < 0) lightIdx = 0;
 	if (lightIdx < nTri)

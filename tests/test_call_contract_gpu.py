@@ -92,3 +92,21 @@ def test_no_lights_no_sky_is_black():
     st = core.GetCoreStats()
     assert not core.ReadPixels()[..., :3].any() and int(st["totalShadowRays"]) == 0 and int(st["primaryRayCount"]) == W * H
     core.Shutdown()
+
+
+def test_present_gl_without_a_gl_context_fails_cleanly():
+    """lh2b_present_gl (CUDA-GL interop, the reference's InteropTexture path) in a process without an OpenGL context: an error code and a
+    message, no crash, and the core keeps rendering - the C++ class then falls back to the host upload."""
+    from lighthouse2_b200 import capi
+    lib = capi.load_library()
+    sd = scenes.config2_scene(12, 8, n_materials=1, light_quads=1)
+    core = RenderCore()
+    core.SetTarget(64, 48, 1)
+    sd.upload(core)
+    view = scenes.view_pyramid((0, 30, -80), (0, 0, 0), 40, 64, 48)
+    core.Render(view, 1)
+    rc = lib.lh2b_present_gl(core._h, 7)
+    assert rc != 0 and b"present_gl" in lib.lh2b_last_error()
+    core.Render(view, 1)
+    assert np.isfinite(core.ReadPixels()).all()
+    core.Shutdown()

@@ -206,3 +206,23 @@ def test_full_size_c3_frame():
     sd = scenes.config2_scene(1000, 500, n_materials=64, light_quads=8)
     view = scenes.view_pyramid((0, 30, -80), (0, 0, 0), 40, 1920, 1080)
     _compare_full(sd, 1920, 1080, 2, 8, 2, view)
+
+
+def test_more_than_64_lights_are_picked_uniformly():
+    """80 emissive triangles: beyond MAXISLIGHTS the reference's importance sampling overruns its table; the core (and the oracle) take the
+    reference's uniform-pick branch instead of rejecting the scene. Frame parity against the oracle as usual."""
+    sd = scenes.config2_scene(24, 16, n_materials=3, light_quads=40, floaters=60)
+    assert len(sd.tri_lights) == 80
+    Wl, Hl = 96, 54
+    view = scenes.view_pyramid((0, 30, -80), (0, 0, 0), 40, Wl, Hl)
+    core = RenderCore()
+    core.SetTarget(Wl, Hl, 1)
+    core.Setting("epsilon", 1e-3)
+    sd.upload(core)
+    core.Render(view, 1)
+    img = core.ReadPixels()
+    st = core.GetCoreStats()
+    want = orc.FrameOracle(sd, Wl, Hl, 1, 1e-3, 10.0, 3, 1).render(view, 1)
+    assert int(st["totalShadowRays"]) > 0
+    assert np.isfinite(img).all() and rel_rmse(img, want) < 0.02 and pixel_mismatch_fraction(img, want) < 0.005
+    core.Shutdown()

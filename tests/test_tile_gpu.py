@@ -72,3 +72,13 @@ def test_row_band_multi_spp_and_untouched_rows():
     np.testing.assert_allclose(b[24:72], a[24:72], rtol=1e-5, atol=1e-6)
     assert not b[:24].any() and not b[72:].any()
     full.Shutdown(), part.Shutdown()
+
+
+def test_row_band_must_start_on_a_tile_row():
+    """Bands are made of 4-row tile rows: a band starting inside one would shade rows it never generated."""
+    sd = scenes.config2_scene(12, 8, n_materials=1, light_quads=1)
+    core = _core(sd, 1, False)
+    with pytest.raises(Exception, match="multiple of 4"):
+        core.SetRowBand(2, 40)
+    core.SetRowBand(4, 40)
+    core.Shutdown()
