@@ -9,7 +9,7 @@ struct DevScene;
 struct RenderParams;
 struct PathSet;
 
-extern int g_wideBlocksPerSM, g_triThreshold, g_refillThreshold, g_triThresholdShadow, g_shadeBlocks;
+extern int g_wideBlocksPerSM, g_triThreshold, g_refillThreshold, g_triThresholdShadow, g_raysPerLane;
 void LaunchExtend( const DevScene& scene, const float4* O4, const float4* D4, float4* hits, int n, uint32_t* workCounter, int smCount, cudaStream_t s );
 void LaunchOcclude( const DevScene& scene, const float4* O4, const float4* D4, uint8_t* occluded, int n, uint32_t* workCounter, int smCount, cudaStream_t s );
 

@@ -419,7 +419,7 @@ int lh2b_setting( lh2b_core* core, const char* name, float value )
 	else if (!strcmp( name, "triThreshold" )) g_triThreshold = (int)value;
 	else if (!strcmp( name, "triThresholdShadow" )) g_triThresholdShadow = (int)value;
 	else if (!strcmp( name, "refillThreshold" )) g_refillThreshold = (int)value;
-	else if (!strcmp( name, "shadeBlocks" )) g_shadeBlocks = (int)value;
+	else if (!strcmp( name, "raysPerLane" )) g_raysPerLane = value < 1 ? 1 : (int)value;
 	// unknown names are ignored
 	API_END
 }

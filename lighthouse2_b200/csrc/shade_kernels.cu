@@ -768,21 +768,18 @@ __global__ void finalizeKernel( const float4* __restrict__ accumulator, float4* 
 	out[i] = make_float4( a.x * scale, a.y * scale, a.z * scale, a.w * scale );
 }
 
-int g_shadeBlocks = 5;	// resident blocks per SM the Lambert shade kernel is compiled for: 5 (102 registers, 54 B of spills) measured 9 % faster
-						// than 4 (123 registers, none) and 4 % faster than 6 on the B200; Setting "shadeBlocks" selects 4 / 5 / 6
-
+/* resident blocks per SM the shade kernels are compiled for: Lambert 5 (102 registers, 54 B of spills: measured 9 % faster than 4 - 123
+   registers, none - and 4 % faster than 6 on the B200, round 1), principled model 4 */
 void LaunchShade( const RenderParams& p, const PathSet& in, const PathSet& out, const float4* hits, const PathSet& conn,
 	int pathLength, uint32_t R0, bool useNEE, uint32_t maxPaths, int smCount, cudaStream_t s )
 {
-	// persistent-style grid: enough blocks to cover maxPaths, capped at 16 resident waves of 4 blocks/SM
+	// persistent-style grid: enough blocks to cover maxPaths, capped at 16 resident waves
 	uint32_t blocks = (maxPaths + 127) / 128;
-	const uint32_t cap = (uint32_t)smCount * (uint32_t)(p.bsdfModel == 1 ? 4 : g_shadeBlocks) * 16;
+	const uint32_t cap = (uint32_t)smCount * (uint32_t)(p.bsdfModel == 1 ? 4 : 5) * 16;
 	if (blocks > cap) blocks = cap;
 	if (blocks == 0) return;
 	if (p.bsdfModel == 1) shadeKernel<1, 4><<<blocks, 128, 0, s>>>( p, in, out, hits, conn, pathLength, R0, useNEE ? 1 : 0 );
-	else if (g_shadeBlocks == 5) shadeKernel<0, 5><<<blocks, 128, 0, s>>>( p, in, out, hits, conn, pathLength, R0, useNEE ? 1 : 0 );
-	else if (g_shadeBlocks == 6) shadeKernel<0, 6><<<blocks, 128, 0, s>>>( p, in, out, hits, conn, pathLength, R0, useNEE ? 1 : 0 );
-	else shadeKernel<0, 4><<<blocks, 128, 0, s>>>( p, in, out, hits, conn, pathLength, R0, useNEE ? 1 : 0 );
+	else shadeKernel<0, 5><<<blocks, 128, 0, s>>>( p, in, out, hits, conn, pathLength, R0, useNEE ? 1 : 0 );
 }
 
 void LaunchFinalize( const float4* accumulator, float4* out, int n, int samplesTaken, cudaStream_t s )

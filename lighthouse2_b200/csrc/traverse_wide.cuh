@@ -96,7 +96,7 @@ __device__ __forceinline__ void FillPopTable( uint8_t* table )
    instances) or inside one instance. Entering an instance transforms the ray, pushes the remaining top-level work and
    a sentinel; the sentinel is only popped once every triangle of that instance (pending group + deferred stack) has
    been tested, because deferred triangle groups are meaningless outside their instance. */
-struct WideTuning { int triThreshold, refillThreshold; };
+struct WideTuning { int triThreshold, refillThreshold, raysPerLane; };	// raysPerLane: a launch with few rays uses fewer, fuller warps (blocks beyond rays / (128 * raysPerLane) retire at once)
 
 template <bool ANYHIT, bool TWO_LEVEL, bool STATS, class RaySource, class HitSink>
 __device__ __forceinline__ void TraverseWide( const DevScene& scene, RaySource& src, HitSink& sink, const uint32_t rayCount, uint32_t* workCounter,
@@ -107,6 +107,9 @@ __device__ __forceinline__ void TraverseWide( const DevScene& scene, RaySource& 
 	__shared__ uint8_t popTable[2048];
 	uint2 localStack[WIDE_LOCAL_STACK];
 	uint2 triStack[WIDE_TRI_STACK];
+	// few rays (small frames, deep path lengths): keep the persistent-thread refill working by giving every lane several rays instead of
+	// spreading one ray per lane over the whole grid
+	if (blockIdx.x > 0 && (unsigned long long)blockIdx.x * (WIDE_BLOCK * tune.raysPerLane) >= rayCount) return;
 	FillPopTable( popTable );
 	__syncthreads();
 	const uint32_t lane = threadIdx.x & 31;
