@@ -220,8 +220,8 @@ static uint32_t PersistentGrid( uint32_t maxItems, int smCount, int blocksPerSM 
 
 int g_wideBlocksPerSM = WIDE_MIN_BLOCKS;
 int g_triThreshold = WIDE_TRI_THRESHOLD, g_refillThreshold = WIDE_REFILL_THRESHOLD, g_triThresholdShadow = WIDE_TRI_THRESHOLD, g_raysPerLane = 1;
-#define TUNE WideTuning{ g_triThreshold, g_refillThreshold, g_raysPerLane }
-#define TUNE_SHADOW WideTuning{ g_triThresholdShadow, g_refillThreshold, g_raysPerLane }
+#define TUNE WideTuning{ g_triThreshold, g_refillThreshold, g_raysPerLane, 0x47800000u }
+#define TUNE_SHADOW WideTuning{ g_triThresholdShadow, g_refillThreshold, g_raysPerLane, 0x47800000u }
 /* picks the instantiation: two-level or flat scene, work counters on (scene.stats set by lh2b_trace_stats) or off */
 #define WIDE_LAUNCH( kernel, grid, s, ... ) do { \
 	if (scene.singleIdentity) { if (scene.stats) kernel<false, true><<<grid, WIDE_BLOCK, 0, s>>>( __VA_ARGS__ ); else kernel<false, false><<<grid, WIDE_BLOCK, 0, s>>>( __VA_ARGS__ ); } \

@@ -44,19 +44,15 @@ namespace lh2b
 #define WIDE_TRI_THRESHOLD 1	// lanes with pending triangles that trigger a triangle step
 #define WIDE_REFILL_THRESHOLD 8	// idle lanes that trigger fetching new rays
 
-/* 0x47800000 = 65536.0f; dropping a byte into mantissa bits 8..15 gives exactly 65536 + 2 * byte. 'base' holds the
-   constant in a register (see OpaqueBase) so that the selector can be the instruction's immediate: one PRMT per plane. */
+/* 0x47800000 = 65536.0f; dropping a byte into mantissa bits 8..15 gives exactly 65536 + 2 * byte: one PRMT per plane, with the byte
+   selector as the instruction's immediate. For that the constant must NOT be an immediate too (ptxas then puts the selector into a
+   register and re-materialises it before every PRMT: 45 extra moves per node step in the SASS of the first round-2 build): it
+   travels as a kernel parameter (WideTuning::byteBase), i.e. a constant-bank operand of the PRMT. */
 template <int J> __device__ __forceinline__ float ByteFloat( const uint32_t word, const uint32_t base )
 {
 	uint32_t r;
 	asm( "prmt.b32 %0, %1, %2, %3;" : "=r"( r ) : "r"( word ), "r"( base ), "n"( 0x7604 | (J << 4) ) );
 	return __uint_as_float( r );
-}
-__device__ __forceinline__ uint32_t OpaqueBase()
-{
-	uint32_t k;
-	asm volatile( "mov.b32 %0, 0x47800000;" : "=r"( k ) );	// volatile: the optimiser must not fold it back into an immediate
-	return k;
 }
 
 struct WideRay
@@ -96,7 +92,7 @@ __device__ __forceinline__ void FillPopTable( uint8_t* table )
    instances) or inside one instance. Entering an instance transforms the ray, pushes the remaining top-level work and
    a sentinel; the sentinel is only popped once every triangle of that instance (pending group + deferred stack) has
    been tested, because deferred triangle groups are meaningless outside their instance. */
-struct WideTuning { int triThreshold, refillThreshold, raysPerLane; };	// raysPerLane: a launch with few rays uses fewer, fuller warps (blocks beyond rays / (128 * raysPerLane) retire at once)
+struct WideTuning { int triThreshold, refillThreshold, raysPerLane; uint32_t byteBase; };	// byteBase: 0x47800000, see ByteFloat;	// raysPerLane: a launch with few rays uses fewer, fuller warps (blocks beyond rays / (128 * raysPerLane) retire at once)
 
 template <bool ANYHIT, bool TWO_LEVEL, bool STATS, class RaySource, class HitSink>
 __device__ __forceinline__ void TraverseWide( const DevScene& scene, RaySource& src, HitSink& sink, const uint32_t rayCount, uint32_t* workCounter,
@@ -114,7 +110,7 @@ __device__ __forceinline__ void TraverseWide( const DevScene& scene, RaySource& 
 	__syncthreads();
 	const uint32_t lane = threadIdx.x & 31;
 	const uint4* __restrict__ nodes = scene.nodes;
-	const uint32_t fbase = OpaqueBase();
+	const uint32_t fbase = tune.byteBase;
 	const float4* __restrict__ tris = scene.tris;
 	const uint32_t NO_INST = 0xffffffffu;
 	// lane state
@@ -250,7 +246,8 @@ __device__ __forceinline__ void TraverseWide( const DevScene& scene, RaySource& 
 			if (exhausted && __ballot_sync( 0xffffffffu, active ) == 0) break;
 			continue;
 		}
-		const bool triPhase = triMask != 0 && (nodeMask == 0 || __popc( triMask ) >= tune.triThreshold || fullMask != 0);
+		// a triangle step runs when enough lanes hold triangles, or when a lane holds nothing else (it would idle through the node step)
+		const bool triPhase = triMask != 0 && (__popc( triMask ) >= tune.triThreshold || (triMask & ~nodeMask) != 0 || fullMask != 0);
 		if (triPhase)
 		{
 			if (STATS && lane == 0) stTriPh++, stTriLanes += __popc( triMask );
