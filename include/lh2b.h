@@ -47,6 +47,8 @@ LH2B_API int lh2b_set_target( lh2b_core* core, int width, int height, int spp );
                                     overlapConnect (1 default: connect( L ) runs next to extend( L + 1 ) on a second stream),
                                     gatherMode (read by lh2b_gather_create: 0 root gather default, 1 reduce-scatter),
                                     tileRootShare (read by lh2b_tile_create: rank 0's band relative to an equal share, 0..1)
+     numerics                       preciseMath (1: the shade and filter stages run their IEEE / libm-accurate builds - no fast math, no FMA
+                                    contraction; default 0 = the reference's -use_fast_math behaviour)
      kernel tuning (measurement)    wideBlocksPerSM, triThreshold, triThresholdShadow, refillThreshold */
 LH2B_API int lh2b_setting( lh2b_core* core, const char* name, float value );
 /* CoreAPI_Base::SetProbePos (core_api_base.h:91, rendercore.cpp:85-88). */

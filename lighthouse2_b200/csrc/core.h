@@ -116,6 +116,7 @@ struct lh2b_core
 	cudaStream_t copyStream = nullptr;
 	cudaStream_t connectStream = nullptr;	// connect( L ) runs here, next to extend( L + 1 ) on the launch stream (Setting "overlapConnect")
 	int overlapConnect = 1;
+	int preciseMath = 0;	// 1: shade and filter stages run their IEEE / libm-accurate builds (parity tests)
 	// CUDA-GL interop present path (lh2b_present_gl): the registered target texture
 	struct cudaGraphicsResource* glResource = nullptr;
 	unsigned glRegisteredTexture = 0; int glRegisteredW = 0, glRegisteredH = 0;

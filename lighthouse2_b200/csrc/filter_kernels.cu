@@ -18,6 +18,20 @@
 #include "kernels.h"
 #include "common.cuh"
 
+/* Second build (build/filter_kernels_precise.o, -DLH2B_PRECISE, no --use_fast_math, -fmad=false), selected by Setting "preciseMath" 1:
+   see shade_kernels.cu. */
+#ifdef LH2B_PRECISE
+#define LaunchFilterChain LaunchFilterChainPrecise
+#define LaunchFilterChainStaged LaunchFilterChainStagedPrecise
+#define prepareKernel prepareKernelPrecise
+#define prepareSearchKernel prepareSearchKernelPrecise
+#define prepareFinishKernel prepareFinishKernelPrecise
+#define atrousKernel atrousKernelPrecise
+#define taaKernel taaKernelPrecise
+#define presentKernel presentKernelPrecise
+#define __expf expf
+#endif
+
 namespace lh2b
 {
 

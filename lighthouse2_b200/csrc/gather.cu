@@ -55,13 +55,13 @@ __global__ void __launch_bounds__( 256 ) sumFinalizeKernel( const PeerSlots slot
 {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
-	float4 a = slots.p[0][i];
+	float4 a = __ldcs( slots.p[0] + i );	// streamed once: evict-first, the BVH of the frame rendering next to this kernel keeps the L2
 	for (int r = 1; r < world; r++)
 	{
-		const float4 b = slots.p[r][i];
+		const float4 b = __ldcs( slots.p[r] + i );
 		a.x += b.x, a.y += b.y, a.z += b.z, a.w += b.w;
 	}
-	out[i] = make_float4( a.x * scale, a.y * scale, a.z * scale, a.w * scale );
+	__stcs( out + i, make_float4( a.x * scale, a.y * scale, a.z * scale, a.w * scale ) );
 }
 
 /* mode 1: this rank's slice. in[j] = the slice as rendered by rank j (own snapshot for j == rank, staged copies otherwise); out points

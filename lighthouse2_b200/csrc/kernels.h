@@ -43,5 +43,10 @@ void LaunchSkin( const float4* bindVerts, const float4* bindNormals, const uint4
 void LaunchMorph( const float4* bindVerts, const float4* bindNormals, const float4* deltas, const float4* normals, const float* weights, int targetCount,
 	float4* verts, float4* coreTris, int triCount, cudaStream_t s );
 void LaunchFinalize( const float4* accumulator, float4* out, int n, int samplesTaken, cudaStream_t s );
+// the IEEE / libm-accurate builds of the shade and filter stages (Setting "preciseMath", see shade_kernels.cu)
+void LaunchShadePrecise( const RenderParams& p, const PathSet& in, const PathSet& out, const float4* hits, const PathSet& conn,
+	int pathLength, uint32_t R0, bool useNEE, uint32_t maxPaths, int smCount, cudaStream_t s );
+void LaunchFilterChainPrecise( const FilterBuffers& b, const FilterSettings& s, cudaStream_t st, cudaEvent_t* stageEvents = nullptr );
+void LaunchFilterChainStagedPrecise( const FilterBuffers& b, const FilterSettings& s, cudaStream_t st, float* hPrepare, float* hP1, float* hP2, float* hP3 );
 
 } // namespace lh2b

@@ -108,7 +108,7 @@ static void RunFilter( lh2b_core* core )
 	fs.taa = core->taaEnabled ? 1 : 0, fs.directClamp = core->clampDirect, fs.indirectClamp = core->clampIndirect;
 	fs.j0 = fs.j1 = fs.prevj0 = fs.prevj1 = 0;	// sub-pixel jitter comes from the blue-noise sampler of generate, not from the view
 	memcpy( fs.prevView, core->filterHistoryValid ? &core->prevView : &core->lastView, sizeof( fs.prevView ) );
-	LaunchFilterChain( b, fs, core->stream );
+	if (core->preciseMath) LaunchFilterChainPrecise( b, fs, core->stream ); else LaunchFilterChain( b, fs, core->stream );
 	if (!core->taaEnabled)	// without TAA the history of the next frame's TAA pass is this frame's filtered image (swap( shading, prevPixels ))
 		CUDA_CHECK( cudaMemcpyAsync( core->taaBuf[cur].ptr, core->shading.ptr, (size_t)core->width * core->height * 16, cudaMemcpyDeviceToDevice, core->stream ) );
 	// rotation: this frame's phase-1 output (in filteredOUT = filteredBuf[prev]) is the next frame's temporal history (filteredIN)
@@ -288,7 +288,8 @@ static void RenderFrame( lh2b_core* core, const lh2abi::ViewPyramid& view )
 		if (overlap && L > 1) CUDA_CHECK( cudaStreamWaitEvent( s, core->events[5 * (L - 1) + 4], 0 ) );	// connect( L - 1 ) is done
 		CUDA_CHECK( cudaEventRecord( core->events[5 * L + 2], s ) );
 		const uint32_t R0 = RandomUInt( core->camRNGseed ) + L * 91771;
-		LaunchShade( p, in, out, core->hitBuf.ptr, conn, L, R0, useNEE, stride, sm, s );
+		if (core->preciseMath) LaunchShadePrecise( p, in, out, core->hitBuf.ptr, conn, L, R0, useNEE, stride, sm, s );
+		else LaunchShade( p, in, out, core->hitBuf.ptr, conn, L, R0, useNEE, stride, sm, s );
 		CUDA_CHECK( cudaEventRecord( core->events[5 * L + 3], s ) );
 		if (overlap) CUDA_CHECK( cudaStreamWaitEvent( cs, core->events[5 * L + 3], 0 ) );
 		if (useNEE) LaunchConnect( core->scene, conn, core->accumulator.ptr, &core->counters.ptr->shadowRays[L], &core->counters.ptr->workFetch[2 * L + 1], stride, sm, cs );
@@ -407,6 +408,7 @@ int lh2b_setting( lh2b_core* core, const char* name, float value )
 	else if (!strcmp( name, "tileRootShare" )) core->tileRootShare = value < 0 ? 0 : (value > 1 ? 1 : value);	// read by lh2b_tile_create
 	else if (!strcmp( name, "gatherMode" )) core->gatherMode = value > 0 ? 1 : 0;	// read by lh2b_gather_create
 	else if (!strcmp( name, "l2Persist" )) core->l2Persist = value > 0 ? 1 : 0;	// takes effect at the next FinalizeInstances
+	else if (!strcmp( name, "preciseMath" )) { const int m = value > 0 ? 1 : 0; if (m != core->preciseMath) core->preciseMath = m, core->samplesTaken = 0; }
 	else if (!strcmp( name, "overlapConnect" )) { FinishFrame( core ); core->overlapConnect = value > 0 ? 1 : 0; }
 	else if (!strcmp( name, "pipeline" )) { FinishFrame( core ); core->pipeline = value > 0; }
 	else if (!strcmp( name, "bsdf" )) { const int m = value >= 0.5f ? 1 : 0; if (m != core->bsdfModel) core->bsdfModel = m, core->samplesTaken = 0; }
@@ -737,7 +739,8 @@ int lh2b_shade_paths( lh2b_core* core, int pathLength, int n, const float* O4, c
 	const PathSet in = { core->pathBuf[0][0].ptr, core->pathBuf[0][1].ptr, core->pathBuf[0][2].ptr };
 	const PathSet out = { core->pathBuf[1][0].ptr, core->pathBuf[1][1].ptr, core->pathBuf[1][2].ptr };
 	const PathSet conn = { core->connBuf[0].ptr, core->connBuf[1].ptr, core->connBuf[2].ptr };
-	LaunchShade( p, in, out, core->hitBuf.ptr, conn, pathLength, R0, useNEE, (uint32_t)n, (int)core->stats.SMcount, s );
+	if (core->preciseMath) LaunchShadePrecise( p, in, out, core->hitBuf.ptr, conn, pathLength, R0, useNEE, (uint32_t)n, (int)core->stats.SMcount, s );
+	else LaunchShade( p, in, out, core->hitBuf.ptr, conn, pathLength, R0, useNEE, (uint32_t)n, (int)core->stats.SMcount, s );
 	CUDA_CHECK( cudaGetLastError() );
 	CUDA_CHECK( cudaMemcpyAsync( &hc, core->counters.ptr, sizeof( hc ), cudaMemcpyDeviceToHost, s ) );
 	CUDA_CHECK( cudaStreamSynchronize( s ) );
@@ -793,7 +796,8 @@ int lh2b_filter_chain( lh2b_core* core, lh2b_filter_io* io )
 	memcpy( fs.prevView, io->prevView, sizeof( fs.prevView ) );
 	// the chain overwrites 'shading' three times and filteredIN/OUT once each: run it stage by stage to hand back every output
 	FilterSettings one = fs;
-	LaunchFilterChainStaged( b, one, s, io->shadingAfterPrepare, io->phase1, io->phase2, io->phase3 );
+	if (core->preciseMath) LaunchFilterChainStagedPrecise( b, one, s, io->shadingAfterPrepare, io->phase1, io->phase2, io->phase3 );
+	else LaunchFilterChainStaged( b, one, s, io->shadingAfterPrepare, io->phase1, io->phase2, io->phase3 );
 	CUDA_CHECK( cudaGetLastError() );
 	auto down = [&]( void* dst, const void* src, size_t bytes ) { if (dst) CUDA_CHECK( cudaMemcpyAsync( dst, src, bytes, cudaMemcpyDeviceToHost, s ) ); };
 	down( io->featuresOut, feat.ptr, px * 16 ), down( io->motion, motion.ptr, px * 8 ), down( io->moments, moments.ptr, px * 16 );

@@ -19,6 +19,18 @@
 #include "common.cuh"
 #include <cuda_fp16.h>
 
+/* Second build of this file (csrc/Makefile: build/shade_kernels_precise.o, -DLH2B_PRECISE, no --use_fast_math, -fmad=false): the same
+   kernels with IEEE division / sqrt, libm-accurate transcendentals and no FMA contraction, under other names. Setting "preciseMath" 1
+   selects it - not for speed: it is what lets the end-to-end parity tests against the CPU oracle (libm, no contraction) use tight bounds. */
+#ifdef LH2B_PRECISE
+#define LaunchShade LaunchShadePrecise
+#define LaunchFinalize LaunchFinalizePrecise
+#define shadeKernel shadeKernelPrecise
+#define finalizeKernel finalizeKernelPrecise
+#define __expf expf
+#define __sincosf sincosf
+#endif
+
 namespace lh2b
 {
 
@@ -764,8 +776,8 @@ __global__ void finalizeKernel( const float4* __restrict__ accumulator, float4* 
 {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
-	const float4 a = accumulator[i];
-	out[i] = make_float4( a.x * scale, a.y * scale, a.z * scale, a.w * scale );
+	const float4 a = __ldcs( accumulator + i );
+	__stcs( out + i, make_float4( a.x * scale, a.y * scale, a.z * scale, a.w * scale ) );
 }
 
 /* resident blocks per SM the shade kernels are compiled for: Lambert 5 (102 registers, 54 B of spills: measured 9 % faster than 4 - 123

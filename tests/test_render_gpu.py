@@ -226,3 +226,21 @@ def test_more_than_64_lights_are_picked_uniformly():
     assert int(st["totalShadowRays"]) > 0
     assert np.isfinite(img).all() and rel_rmse(img, want) < 0.02 and pixel_mismatch_fraction(img, want) < 0.005
     core.Shutdown()
+
+
+def test_precise_math_frames_agree_tightly():
+    """Setting "preciseMath" 1 (IEEE division / sqrt, accurate transcendentals, no FMA contraction in the shade stage): what separates the
+    shipping fast-math frame from the libm oracle is then gone except for isolated discrete flips - at most 0.1 % of the pixels differ by
+    more than 1e-3 relative (fast-math bound: 0.5 %) and the relative RMSE stays below 1 % over a Restart / Converge sequence with long
+    paths and several samples."""
+    sd = _scene(6, 3)
+    view = scenes.view_pyramid((0, 12, -60), (0, 0, 0), 50, W, H)
+    core, oracle = _core(sd, spp=2, maxlen=8, bounces=2), orc.FrameOracle(sd, W, H, 2, 1e-3, 10.0, 8, 2)
+    core.Setting("preciseMath", 1)
+    worst = (0.0, 0.0)
+    for conv in (1, 0, 1):
+        core.Render(view, conv)
+        got, want = core.ReadPixels(), oracle.render(view, conv)
+        worst = max(worst, (pixel_mismatch_fraction(got, want), rel_rmse(got, want)))
+    assert worst[0] < 0.001 and worst[1] < 0.01, worst
+    core.Shutdown()
