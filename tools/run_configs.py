@@ -161,7 +161,8 @@ if "c4" in which:
     res["c4"] = {"traversal_work": work, "meshes": 10, "triangles_per_mesh": len(base) // 3, "instances": 1001, "vertex_upload_ms_per_frame": float(np.mean(upload_ms[1:])),
                  "set_instance_calls_ms": float(np.mean(inst_ms[1:])), "finalize_instances_wall_ms": float(np.mean(build_ms[1:])),
                  "refit_device_ms_10_meshes": refit_device, "tlas_device_ms": last["buildMs"], "render_ms": last["totalMs"],
-                 "trace_mrays_per_s": last["rays"] / (last["generateExtendMs"] + last["extendMs"] + last["connectMs"]) / 1e3, "frame": last}
+                 "trace_mrays_per_s": last["rays"] / (last["totalMs"] - last["shadeMs"]) / 1e3,      # connect( L ) overlaps extend( L + 1 ): wall time spent tracing
+                 "frame": last}
     # the same animation done on the device (lh2b_set_skin / lh2b_set_pose): 4 joints per mesh, new joint
     # matrices every frame -> skinning kernel + refit, no triangle data crosses PCIe (64 B per joint do)
     nverts = base.reshape(-1, 4).shape[0]
