@@ -197,6 +197,8 @@ __global__ void radixTreeKernel( const uint64_t* __restrict__ keys, const int n,
      T[n][1]  = area( n ) * LH2B_SAH_NODE + D[n][8]      - n becomes a wide node and fills its own eight slots
      T[n][i]  = min( T[n][i - 1], D[n][i] )
      T[leaf][i] = area( leaf ) * LH2B_SAH_LEAF
+   (every triangle ends up in exactly one leaf slot whatever is chosen, so the leaf term is the same for all collapses: the program minimises
+   the summed area of the wide nodes; measured: LH2B_SAH_LEAF 0.1 .. 2.0 gives the same tree)
    dpSplit[n][i - 1] (i = 2..7) = the k behind T[n][i], 0 if T[n][i - 1] was kept; dpSplit[n][7] = the k of the node's own slots.
    collapseKernel then unfolds the choices top-down instead of opening the largest child greedily. */
 #define LH2B_SAH_NODE 1.0f
