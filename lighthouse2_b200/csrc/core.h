@@ -94,6 +94,9 @@ struct lh2b_core
 	struct lh2b_gather* gather = nullptr;		// attached multi-GPU gather (gather.cu): frames end with a snapshot for it instead of the local finalize
 	int bandY0 = 0, bandY1 = 0, bandStep = 1;	// rows this core renders (lh2b_set_row_band[_strided]; 0, 0 = the whole frame)
 	float tileRootShare = 1.0f;				// lh2b_tile_create: rank 0's band relative to an equal share (it also runs the frame's tail)
+	bool tileDouble = false;					// tile-sharded frames on rank 0 with peers: the buffers the peers push into are double-buffered (tile_gather.cu)
+	uint32_t tileFrames = 0;					// frames rendered since the tile gatherer was attached (parity = which set is current)
+	lh2b::DevBuf<float4> accumulatorAlt, deltaDepthAlt;	// the other set (swapped with accumulator / deltaDepth every frame while tileDouble)
 	bool deferTail = false;					// tile-sharded frames: finalize / filter is enqueued by the gatherer once every band has arrived
 	int gatherMode = 0;						// lh2b_gather_create: 0 root gather, 1 reduce-scatter (csrc/gather.cu)
 	int l2Persist = 1, l2Applied = -1;			// persisting-L2 window over the node arena (ApplyL2Policy)

@@ -250,6 +250,20 @@ static void RenderFrame( lh2b_core* core, const lh2abi::ViewPyramid& view )
 	core->lastView = view;
 	CUDA_CHECK( cudaEventRecord( core->events[0], s ) );
 	RotatePixelBuffers( core );
+	if (core->tileDouble && core->tileFrames++ > 0)
+	{
+		// rank 0 of a tile-sharded frame: the peers push the rows of frame k into set k & 1 while the tail of frame k - 1 still reads the
+		// other set. A converging frame continues the sums of this rank's own rows, which live in the set used last.
+		core->accumulator.Swap( core->accumulatorAlt ), core->deltaDepth.Swap( core->deltaDepthAlt );
+		if (core->samplesTaken != 0)
+		{
+			// (only this rank's own rows - a contiguous band: the peers' rows of this frame may have arrived in the new set already)
+			const size_t px = (size_t)core->width * core->height, first = (size_t)BandY0( core ) * core->width, n = (size_t)(BandY1( core ) - BandY0( core )) * core->width * sizeof( float4 );
+			CUDA_CHECK( cudaMemcpyAsync( core->accumulator.ptr + first, core->accumulatorAlt.ptr + first, n, cudaMemcpyDeviceToDevice, s ) );
+			CUDA_CHECK( cudaMemcpyAsync( core->accumulator.ptr + px + first, core->accumulatorAlt.ptr + px + first, n, cudaMemcpyDeviceToDevice, s ) );
+			if (core->deltaDepth.count) CUDA_CHECK( cudaMemcpyAsync( core->deltaDepth.ptr + first, core->deltaDepthAlt.ptr + first, n, cudaMemcpyDeviceToDevice, s ) );
+		}
+	}
 	if (core->samplesTaken == 0)
 	{
 		// Restart: clear this core's rows of both accumulator halves (tile-sharded frames: the other rows belong to the peers' pushes)

@@ -13,14 +13,16 @@
    interleaved band is a 2D range (tile row x pitch) of every buffer: still one (2D) copy per buffer.
 
      rank r > 0, frame k:  [core stream]  render its tile rows into the local buffers (tail deferred)
-                           [comm stream]  wait( ack >= k )                          rank 0 has finished the tail of frame k-1
+                           [comm stream]  wait( ack >= k-1 )                        rank 0 has finished the tail of frame k-2
                                           copy rows of: accumulator (direct), and in filter mode accumulator (indirect),
-                                          worldPos, deltaDepth -> the same rows of rank 0's buffers; features -> rank 0's staging
+                                          deltaDepth -> the same rows of rank 0's buffer SET k & 1 (r2: rank 0 swaps two sets of these
+                                          buffers every frame, so frame k arrives while the tail of frame k-1 runs);
+                                          features, worldPos -> rank 0's staging set k & 1
                                           set rank0.arrived[r] = k+1
      rank 0, frame k:      [core stream]  render its own rows
                                           wait( arrived[r] >= k+1 ) for every r     cuStreamWaitValue32 on the core's own stream
                                           mergeFeaturesKernel (filter mode): staged feature rows -> features, keeping the history
-                                          counter bits that rank 0's prepare pass owns
+                                          counter bits that rank 0's prepare pass owns; staged world positions -> current buffer
                                           tail: filter chain / finalize -> pixels;  set rank r .ack = k+1 for every r
    80 B per pixel cross NVLink in filter mode (16 B without the filter): 4K -> 663 MB x (N-1)/N per frame into rank 0. The result
    equals the single-GPU frame bit for bit at 1 spp (one path per pixel: no accumulation-order freedom), which is what
@@ -45,7 +47,7 @@ typedef CUresult( *TgMemsetD32AsyncFn )( CUdeviceptr, unsigned int, size_t, CUst
 #define TILE_MAX_RANKS 16
 struct TileHandles
 {
-	cudaIpcMemHandle_t accumulator, featStage, worldPos[2], deltaDepth, arrived, ack;	// all but 'ack' are meaningful for rank 0 only
+	cudaIpcMemHandle_t accumulator[2], featStage[2], worldPosStage[2], deltaDepth[2], arrived, ack;	// all but 'ack' are meaningful for rank 0 only; [k & 1]: the set of frame k
 	int filter, flip0, pad[2];																// rank 0: filter mode and the worldPos buffer index of its next frame
 };
 
@@ -74,9 +76,10 @@ struct lh2b_tile_gather
 	cudaEvent_t rendered = nullptr;
 	uint32_t* arrived = nullptr;				// rank 0: [world]
 	uint32_t* ack = nullptr;					// every rank
-	uint4* featStage = nullptr;					// rank 0: staged feature rows of the peers
+	uint4* featStage[2] = { nullptr, nullptr };	// rank 0: staged feature rows of the peers, per frame parity
+	float4* wpStage[2] = { nullptr, nullptr };	// rank 0: staged world positions of the peers (copied into the core's current buffer before the tail)
 	// peer mappings (rank > 0: rank 0's buffers; rank 0: every peer's ack)
-	float4* rootAccumulator = nullptr; uint4* rootFeatStage = nullptr; float4* rootWorldPos[2] = { nullptr, nullptr }; float4* rootDeltaDepth = nullptr;
+	float4* rootAccumulator[2] = { nullptr, nullptr }; uint4* rootFeatStage[2] = { nullptr, nullptr }; float4* rootWorldPos[2] = { nullptr, nullptr }; float4* rootDeltaDepth[2] = { nullptr, nullptr };
 	uint32_t* rootArrived = nullptr;
 	uint32_t* peerAck[TILE_MAX_RANKS] = {};
 	TgWaitValue32Fn waitValue = nullptr;
@@ -142,7 +145,22 @@ int lh2b_tile_create( lh2b_core* core, int rank, int world, lh2b_tile_gather** o
 	{
 		CUDA_CHECK( cudaMalloc( &g->arrived, 256 ) );
 		CUDA_CHECK( cudaMemset( g->arrived, 0, 256 ) );
-		if (g->filter) CUDA_CHECK( cudaMalloc( &g->featStage, g->pixels * sizeof( uint4 ) ) );
+		if (world > 1)
+		{
+			// double-buffered destinations of the peers' rows: the bands of frame k + 1 arrive while the tail of frame k runs
+			core->accumulatorAlt.Resize( core->accumulator.count );
+			CUDA_CHECK( cudaMemsetAsync( core->accumulatorAlt.ptr, 0, core->accumulatorAlt.count * sizeof( float4 ), core->stream ) );
+			if (g->filter)
+			{
+				core->deltaDepthAlt.Resize( core->deltaDepth.count );
+				for (int i = 0; i < 2; i++)
+				{
+					CUDA_CHECK( cudaMalloc( &g->featStage[i], g->pixels * sizeof( uint4 ) ) );
+					CUDA_CHECK( cudaMalloc( &g->wpStage[i], g->pixels * sizeof( float4 ) ) );
+				}
+			}
+			core->tileDouble = true, core->tileFrames = 0;
+		}
 	}
 	// this core renders its band only; the tail of the frame runs in lh2b_tile_frame on rank 0
 	const int rc = lh2b_set_row_band_strided( core, g->bandY0, g->bandY1, g->bandStep );
@@ -162,14 +180,22 @@ int lh2b_tile_export( lh2b_tile_gather* g, void* handlesOut )
 	if (g->rank == 0)
 	{
 		lh2b_core* c = g->core;
-		CUDA_CHECK( cudaIpcGetMemHandle( &h.accumulator, c->accumulator.ptr ) );
 		CUDA_CHECK( cudaIpcGetMemHandle( &h.arrived, g->arrived ) );
-		if (g->filter)
+		if (g->world > 1)
 		{
-			CUDA_CHECK( cudaIpcGetMemHandle( &h.featStage, g->featStage ) );
-			CUDA_CHECK( cudaIpcGetMemHandle( &h.worldPos[0], c->worldPosBuf[0].ptr ) );
-			CUDA_CHECK( cudaIpcGetMemHandle( &h.worldPos[1], c->worldPosBuf[1].ptr ) );
-			CUDA_CHECK( cudaIpcGetMemHandle( &h.deltaDepth, c->deltaDepth.ptr ) );
+			if (c->tileFrames != 0) throw CoreError( "tile_export: export the handles before the first frame" );
+			CUDA_CHECK( cudaIpcGetMemHandle( &h.accumulator[0], c->accumulator.ptr ) );	// set of the even frames (the first frame does not swap)
+			CUDA_CHECK( cudaIpcGetMemHandle( &h.accumulator[1], c->accumulatorAlt.ptr ) );
+			if (g->filter)
+			{
+				CUDA_CHECK( cudaIpcGetMemHandle( &h.deltaDepth[0], c->deltaDepth.ptr ) );
+				CUDA_CHECK( cudaIpcGetMemHandle( &h.deltaDepth[1], c->deltaDepthAlt.ptr ) );
+				for (int i = 0; i < 2; i++)
+				{
+					CUDA_CHECK( cudaIpcGetMemHandle( &h.featStage[i], g->featStage[i] ) );
+					CUDA_CHECK( cudaIpcGetMemHandle( &h.worldPosStage[i], g->wpStage[i] ) );
+				}
+			}
 		}
 	}
 	h.filter = g->filter, h.flip0 = g->flip0;
@@ -190,14 +216,14 @@ int lh2b_tile_import( lh2b_tile_gather* g, const void* handlesOfAllRanks )
 	else
 	{
 		const unsigned f = cudaIpcMemLazyEnablePeerAccess;
-		CUDA_CHECK( cudaIpcOpenMemHandle( (void**)&g->rootAccumulator, h[0].accumulator, f ) );
 		CUDA_CHECK( cudaIpcOpenMemHandle( (void**)&g->rootArrived, h[0].arrived, f ) );
-		if (g->filter)
+		for (int i = 0; i < 2; i++)
 		{
-			CUDA_CHECK( cudaIpcOpenMemHandle( (void**)&g->rootFeatStage, h[0].featStage, f ) );
-			CUDA_CHECK( cudaIpcOpenMemHandle( (void**)&g->rootWorldPos[0], h[0].worldPos[0], f ) );
-			CUDA_CHECK( cudaIpcOpenMemHandle( (void**)&g->rootWorldPos[1], h[0].worldPos[1], f ) );
-			CUDA_CHECK( cudaIpcOpenMemHandle( (void**)&g->rootDeltaDepth, h[0].deltaDepth, f ) );
+			CUDA_CHECK( cudaIpcOpenMemHandle( (void**)&g->rootAccumulator[i], h[0].accumulator[i], f ) );
+			if (!g->filter) continue;
+			CUDA_CHECK( cudaIpcOpenMemHandle( (void**)&g->rootFeatStage[i], h[0].featStage[i], f ) );
+			CUDA_CHECK( cudaIpcOpenMemHandle( (void**)&g->rootWorldPos[i], h[0].worldPosStage[i], f ) );
+			CUDA_CHECK( cudaIpcOpenMemHandle( (void**)&g->rootDeltaDepth[i], h[0].deltaDepth[i], f ) );
 		}
 		g->flip0 = h[0].flip0;
 	}
@@ -218,19 +244,20 @@ int lh2b_tile_frame( lh2b_tile_gather* g )
 		CUstream cs = (CUstream)g->comm;
 		CUDA_CHECK( cudaEventRecord( g->rendered, core->stream ) );
 		CUDA_CHECK( cudaStreamWaitEvent( g->comm, g->rendered, 0 ) );
-		if (k >= 1) CU_CHECK( g->waitValue( cs, (CUdeviceptr)g->ack, k, CU_STREAM_WAIT_VALUE_GEQ ) );	// rank 0 is done with frame k-1's buffers
+		const uint32_t set = k & 1;	// destinations are double-buffered on rank 0: frame k may arrive while the tail of frame k - 1 runs
+		if (k >= 2) CU_CHECK( g->waitValue( cs, (CUdeviceptr)g->ack, k - 1, CU_STREAM_WAIT_VALUE_GEQ ) );	// rank 0 is done with frame k - 2 (the same set)
 		// this rank's rows of one per-pixel buffer: tileRows chunks of 4 rows, bandStep tile rows apart (one contiguous range if bandStep = 1)
 		auto push = [&]( void* dst, const void* src, size_t elem ) {
 			const size_t chunk = 4 * w * elem, pitch = chunk * (size_t)g->bandStep;
 			if (g->bandStep == 1) CUDA_CHECK( cudaMemcpyAsync( (char*)dst + first * elem, (const char*)src + first * elem, (size_t)(g->bandY1 - g->bandY0) * w * elem, cudaMemcpyDeviceToDevice, g->comm ) );
 			else CUDA_CHECK( cudaMemcpy2DAsync( (char*)dst + first * elem, pitch, (const char*)src + first * elem, pitch, chunk, (size_t)g->tileRows, cudaMemcpyDeviceToDevice, g->comm ) ); };
-		push( g->rootAccumulator, core->accumulator.ptr, 16 );
+		push( g->rootAccumulator[set], core->accumulator.ptr, 16 );
 		if (g->filter)
 		{
-			push( g->rootAccumulator + g->pixels, core->accumulator.ptr + g->pixels, 16 );	// indirect half
-			push( g->rootFeatStage, core->features.ptr, 16 );
-			push( g->rootWorldPos[(g->flip0 + k) & 1], core->worldPosBuf[core->filterFlip].ptr, 16 );	// rank 0 flips its world-position buffers every frame
-			push( g->rootDeltaDepth, core->deltaDepth.ptr, 16 );
+			push( g->rootAccumulator[set] + g->pixels, core->accumulator.ptr + g->pixels, 16 );	// indirect half
+			push( g->rootFeatStage[set], core->features.ptr, 16 );
+			push( g->rootWorldPos[set], core->worldPosBuf[core->filterFlip].ptr, 16 );	// staged: rank 0's two world-position buffers are both in use by the tail of the frame before
+			push( g->rootDeltaDepth[set], core->deltaDepth.ptr, 16 );
 		}
 		CU_CHECK( g->memsetD32( (CUdeviceptr)(g->rootArrived + g->rank), k + 1, 1, cs ) );
 		// the next frame of this rank overwrites the rows just pushed: it has to wait for the copies
@@ -244,8 +271,11 @@ int lh2b_tile_frame( lh2b_tile_gather* g )
 		if (g->filter && g->world > 1)
 		{
 			const int peerFirst = (int)((size_t)g->rootRows * w), peerCount = (int)(g->pixels - (size_t)peerFirst);
-			mergeFeaturesKernel<<<(peerCount + 255) / 256, 256, 0, core->stream>>>( core->features.ptr, g->featStage, peerFirst, peerCount );
+			mergeFeaturesKernel<<<(peerCount + 255) / 256, 256, 0, core->stream>>>( core->features.ptr, g->featStage[k & 1], peerFirst, peerCount );
 			CUDA_CHECK( cudaGetLastError() );
+			// the peers' world positions of this frame: from the staging set into the buffer the frame's tail reads as 'current'
+			CUDA_CHECK( cudaMemcpyAsync( core->worldPosBuf[core->filterFlip].ptr + peerFirst, g->wpStage[k & 1] + peerFirst, (size_t)peerCount * sizeof( float4 ),
+				cudaMemcpyDeviceToDevice, core->stream ) );
 		}
 		RunDeferredTail( core );
 		for (int r = 1; r < g->world; r++) CU_CHECK( g->memsetD32( (CUdeviceptr)g->peerAck[r], k + 1, 1, cs ) );
@@ -280,10 +310,17 @@ int lh2b_tile_destroy( lh2b_tile_gather* g )
 	if (g->rank == 0) { for (int r = 1; r < g->world; r++) if (g->peerAck[r]) cudaIpcCloseMemHandle( g->peerAck[r] ); }
 	else
 	{
-		void* maps[] = { g->rootAccumulator, g->rootFeatStage, g->rootWorldPos[0], g->rootWorldPos[1], g->rootDeltaDepth, g->rootArrived };
+		void* maps[] = { g->rootAccumulator[0], g->rootAccumulator[1], g->rootFeatStage[0], g->rootFeatStage[1], g->rootWorldPos[0], g->rootWorldPos[1],
+			g->rootDeltaDepth[0], g->rootDeltaDepth[1], g->rootArrived };
 		for (void* m : maps) if (m) cudaIpcCloseMemHandle( m );
 	}
-	cudaFree( g->arrived ), cudaFree( g->ack ), cudaFree( g->featStage );
+	if (g->core->tileDouble)
+	{
+		g->core->tileDouble = false, g->core->tileFrames = 0;
+		g->core->accumulatorAlt.Free(), g->core->deltaDepthAlt.Free();	// whichever set is not current
+	}
+	cudaFree( g->arrived ), cudaFree( g->ack );
+	for (int i = 0; i < 2; i++) cudaFree( g->featStage[i] ), cudaFree( g->wpStage[i] );
 	cudaEventDestroy( g->rendered ), cudaStreamDestroy( g->comm );
 	delete g;
 	API_END

@@ -134,15 +134,21 @@ def test_filter_chain_matches_reference_kernels(case, taa, stationary):
     if taa:
         # The reference's TAApass reads and writes one buffer in place (a race): its own output changes from run to run (measured
         # with tools/filter_determinism_probe.py: every run differs, up to 2 % of the target pixels by more than 1e-2), ours is
-        # deterministic (test_filter_chain_is_deterministic). The reference is therefore sampled up to four times.
-        for attempt in range(4):
-            ok = _frac_bad(got["taaPixels"][..., :3], want["taaPixels"][..., :3], 1e-2) < 0.03 and \
-                _frac_bad(got["target"][..., :3], want["target"][..., :3], 3e-2) < 0.05
-            if ok:
-                break
-            want = orc.ref_filter_gpu(inputs, dict(w=W, h=H, samplesTaken=1, camIsStationary=stationary, taa=taa, directClamp=15.0, indirectClamp=15.0,
-                                                   j0=0.0, j1=0.0, prevj0=0.0, prevj1=0.0, prevView=prev_view))
-        assert ok, "TAA / unsharp + un-gamma"
+        # deterministic (test_filter_chain_is_deterministic). Two checks that do not depend on how one run of the race falls:
+        #  (1) against the per-pixel [min, max] envelope of eight runs of the reference kernels (as tests/test_oracle_golden.py does with
+        #      the committed envelope of twelve runs);
+        st = dict(w=W, h=H, samplesTaken=1, camIsStationary=stationary, taa=taa, directClamp=15.0, indirectClamp=15.0, j0=0.0, j1=0.0, prevj0=0.0, prevj1=0.0,
+                  prevView=prev_view)
+        runs = [want] + [orc.ref_filter_gpu(inputs, st) for _ in range(7)]
+        for k, tol, bound in (("taaPixels", 1e-2, 0.06), ("target", 3e-2, 0.05)):
+            stack = np.stack([np.asarray(r[k])[..., :3] for r in runs])
+            lo, hi, x = stack.min(axis=0), stack.max(axis=0), got[k][..., :3]
+            assert float(((x < lo - tol) | (x > hi + tol)).any(axis=-1).mean()) < bound, k
+        #  (2) against the CPU restatement of the chain (race-free by construction like ours, pinned to the reference by the golden envelope):
+        #      deterministic on both sides
+        cpu = orc.filter_chain_cpu(inputs, st)
+        assert _frac_bad(got["taaPixels"][..., :3], cpu["taaPixels"][..., :3], 1e-2) < 0.02, "TAA vs the CPU restatement"
+        assert _frac_bad(got["target"][1:-1, 1:-1, :3], cpu["target"][1:-1, 1:-1, :3], 3e-2) < 0.02, "unsharp + un-gamma vs the CPU restatement"
     else:
         assert _frac_bad(got["target"][..., :3], want["target"][..., :3], 5e-3) < 0.01, "finalizeNoTAA"
     assert np.isfinite(got["target"]).all() and got["target"][1:-1, 1:-1, :3].mean() > 0.05
