@@ -233,6 +233,9 @@ LH2B_API int lh2b_shade_paths_time( lh2b_core* core, int pathLength, int n, cons
 /* Filter mode only: copy the per-pixel filter inputs of the last frame to host (any pointer may be null):
    features uint4[w*h], worldPos / deltaDepth float4[w*h], accumulator2 float4[2*w*h] (direct, then indirect). */
 LH2B_API int lh2b_read_filter_buffers( lh2b_core* core, uint32_t* features, float* worldPos, float* deltaDepth, float* accumulator2 );
+/* ... and what the chain of the last frame left for the next one (any pointer may be null; float4[w*h], motion float2[w*h]):
+   luminance moments, phase-1 a-trous output, TAA image, phase-3 output, motion vectors. */
+LH2B_API int lh2b_read_filter_history( lh2b_core* core, float* moments, float* phase1, float* taa, float* phase3, float* motion );
 
 /* Presenting through CUDA-OpenGL interop, as the reference's InteropTexture does (lib/CUDA/shared_host_code/interoptexture.cpp:53-61:
    cudaGraphicsGLRegisterImage on GLTexture::ID, map, write, unmap): copies the finished frame from the core's linear RGBA32F

@@ -81,6 +81,7 @@ SIGNATURES = {
     "lh2b_filter_chain": ([_vp, _vp], _ip),
     "lh2b_shade_paths_time": ([_vp, _ip, _ip, _vp, _vp, _vp, _vp, _c.c_uint, _c.c_uint, _ip, _ip, _vp], _ip),
     "lh2b_read_filter_buffers": ([_vp, _vp, _vp, _vp, _vp], _ip),
+    "lh2b_read_filter_history": ([_vp, _vp, _vp, _vp, _vp, _vp], _ip),
     "lh2b_shade_paths": ([_vp, _ip, _ip, _vp, _vp, _vp, _vp, _c.c_uint, _c.c_uint, _ip, _vp, _vp, _vp, _c.POINTER(_ip),
                           _vp, _vp, _vp, _c.POINTER(_ip), _vp], _ip),
     "CreateCore": ([], _vp),

@@ -305,6 +305,15 @@ class RenderCore:
         self._check(self._lib.lh2b_read_filter_buffers(self._h, _ptr(f), _ptr(wp), _ptr(dd), _ptr(acc)))
         return f, wp, dd, acc
 
+    def ReadFilterHistory(self):
+        """Filter mode: dict of what the last frame's chain left behind (float32[h,w,4]; motion float32[h,w,2]) - moments, phase-1 output,
+        TAA image, phase-3 output, motion vectors (for tests)."""
+        h, w = self.height, self.width
+        out = {k: np.zeros((h, w, 4), np.float32) for k in ("moments", "phase1", "taa", "phase3")}
+        out["motion"] = np.zeros((h, w, 2), np.float32)
+        self._check(self._lib.lh2b_read_filter_history(self._h, *[_ptr(out[k]) for k in ("moments", "phase1", "taa", "phase3", "motion")]))
+        return out
+
     def FilterChain(self, io):
         """Parity hook (lh2b_filter_chain): io is a ctypes structure laid out like lh2b_filter_io."""
         self._check(self._lib.lh2b_filter_chain(self._h, ctypes.byref(io)))

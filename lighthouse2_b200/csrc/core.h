@@ -11,6 +11,7 @@
 #include "common.cuh"
 #include "traverse.cuh"
 #include "render_types.h"
+#include "kernels.h"
 #include <memory>
 #include <vector>
 
@@ -97,6 +98,16 @@ struct lh2b_core
 	bool tileDouble = false;					// tile-sharded frames on rank 0 with peers: the buffers the peers push into are double-buffered (tile_gather.cu)
 	uint32_t tileFrames = 0;					// frames rendered since the tile gatherer was attached (parity = which set is current)
 	lh2b::DevBuf<float4> accumulatorAlt, deltaDepthAlt;	// the other set (swapped with accumulator / deltaDepth every frame while tileDouble)
+	// filter chain sharded over the ranks of a tile gatherer (tile_gather.cu; Settings "tileFilterShard", "tileInterleave", read by lh2b_tile_create)
+	int tileFilterShard = 0, tileInterleave = 1;
+	const lh2b::FilterShard* filterShard = nullptr;		// set while attached: band, halo rows, phase2Out; RunFilter fills the history tables from shardHist
+	const float4* shardHist[4][2][LH2B_MAX_SHARDS] = {};	// [worldPos, moments, filtered, taa][flip][rank]: every rank's history buffers (peer mappings, own = local)
+	float4* worldPosOverride = nullptr;				// the frame being rendered writes its world positions here (staging set of that frame) instead of worldPosBuf[filterFlip]
+	uint4* featuresOverride = nullptr;				// ... and its features here (its history-counter bits are then meaningless: the gatherer merges them into 'features')
+	cudaStream_t tailStream = nullptr;				// when set, the filter chain runs on this stream (next to the following frame's path tracing on 'stream')
+	float4* shardTarget = nullptr;					// where the present pass of the next tail writes (a peer mapping of rank 0's staging image on ranks > 0)
+	cudaEvent_t* filterStageEvents = nullptr;			// when set, the next RunFilter records its 7 stage boundaries here (tile timing)
+	cudaEvent_t tailEvent = nullptr;					// rank 0: recorded when the peers' rows of the last frame are in 'pixels' too; readers of 'pixels' wait for it
 	bool deferTail = false;					// tile-sharded frames: finalize / filter is enqueued by the gatherer once every band has arrived
 	int gatherMode = 0;						// lh2b_gather_create: 0 root gather, 1 reduce-scatter (csrc/gather.cu)
 	int l2Persist = 1, l2Applied = -1;			// persisting-L2 window over the node arena (ApplyL2Policy)

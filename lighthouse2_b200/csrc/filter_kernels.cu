@@ -17,6 +17,7 @@
 */
 #include "kernels.h"
 #include "common.cuh"
+#include <algorithm>
 
 /* Second build (build/filter_kernels_precise.o, -DLH2B_PRECISE, no --use_fast_math, -fmad=false), selected by Setting "preciseMath" 1:
    see shade_kernels.cu. */
@@ -99,21 +100,37 @@ __device__ __forceinline__ float MitchellNetravali( const float v )
 	return 0.0f;
 }
 
-/* sampling_shared.h:111-215 */
-__device__ __forceinline__ float4 ReadWorldPos( const float4* __restrict__ buffer, const int x, const int y, const int w, const int h )
+/* History buffers (the previous frame's world positions, moments, phase-1 output and TAA image) are read at reprojected positions,
+   i.e. anywhere in the frame. When the filter chain of one frame is sharded over the GPUs of a box (FilterShard, kernels.h; tile_gather.cu)
+   every rank keeps the history rows of its own band and the kernels read a row from the rank that owns it - plain loads through the
+   peer mappings over NVLink. On one GPU the same code runs with lo = 0, hi = h (every row is local): ONE instantiation of every kernel
+   serves both cases, because the sharded frame has to equal the single-GPU frame bit for bit and two instantiations of the same source
+   need not round alike (measured: a second instantiation of the TAA kernel differed by 1-10 ulp where the 4x4 history footprint touches
+   the left image edge - the compiler had versioned that loop differently). The price on one GPU is a compare and a select per history read. */
+struct HistBuf { const float4* p[LH2B_MAX_SHARDS]; const float4* local; int lo, hi; };	// rows [lo, hi) of this rank's own copy are valid (its band plus the halo rows it computes itself)
+struct ShardMap { uint32_t magic; int last; };	// owner of row y: min( y / rowsPerBand, last ), the division as a multiplication by magic = 2^32 / rowsPerBand + 1
+__device__ __forceinline__ float4 HistAt( const HistBuf& b, const ShardMap& m, const int x, const int y, const int w )
 {
-	if (x >= 0 && y >= 0 && x < w && y < h) return buffer[x + y * w];
+	// halo rows are computed on both sides of a band boundary with identical results: whatever this rank computed itself it reads locally
+	const float4* base = (uint32_t)(y - b.lo) < (uint32_t)(b.hi - b.lo) ? b.local : b.p[min( (int)__umulhi( (uint32_t)y, m.magic ), m.last )];
+	return __ldg( base + x + y * w );
+}
+
+/* sampling_shared.h:111-215 */
+__device__ __forceinline__ float4 ReadWorldPos( const HistBuf& buffer, const ShardMap& m, const int x, const int y, const int w, const int h )
+{
+	if (x >= 0 && y >= 0 && x < w && y < h) return HistAt( buffer, m, x, y, w );
 	return make_float4( 1e20f, 1e20f, 1e20f, __uint_as_float( 0 ) );
 }
-__device__ __forceinline__ float4 ReadTexelConsistent( const float4* __restrict__ buffer, const float4* __restrict__ prevWorldPos, const float4 localPos,
+__device__ __forceinline__ float4 ReadTexelConsistent( const HistBuf& buffer, const HistBuf& prevWorldPos, const ShardMap& m, const float4 localPos,
 	const float3 localNormal, const float u, const float v, const int w, const int h )
 {
 	const int iu1 = (int)floorf( u ), iv1 = (int)floorf( v ), iu0 = max( 0, iu1 - 1 ), iv0 = max( 0, iv1 - 1 );
 	if (iu1 >= w || iv1 >= h || iu1 < 0 || iv1 < 0) return make_float4( -1, -1, -1, -1 );
 	const float fx = u - floorf( u ), fy = v - floorf( v );
-	const float4 p0 = buffer[iu0 + iv0 * w], p1 = buffer[iu1 + iv0 * w], p2 = buffer[iu0 + iv1 * w], p3 = buffer[iu1 + iv1 * w];
-	const uint32_t n0 = __float_as_uint( prevWorldPos[iu0 + iv0 * w].w ), n1 = __float_as_uint( prevWorldPos[iu1 + iv0 * w].w );
-	const uint32_t n2 = __float_as_uint( prevWorldPos[iu0 + iv1 * w].w ), n3 = __float_as_uint( prevWorldPos[iu1 + iv1 * w].w );
+	const float4 p0 = HistAt( buffer, m, iu0, iv0, w ), p1 = HistAt( buffer, m, iu1, iv0, w ), p2 = HistAt( buffer, m, iu0, iv1, w ), p3 = HistAt( buffer, m, iu1, iv1, w );
+	const uint32_t n0 = __float_as_uint( HistAt( prevWorldPos, m, iu0, iv0, w ).w ), n1 = __float_as_uint( HistAt( prevWorldPos, m, iu1, iv0, w ).w );
+	const uint32_t n2 = __float_as_uint( HistAt( prevWorldPos, m, iu0, iv1, w ).w ), n3 = __float_as_uint( HistAt( prevWorldPos, m, iu1, iv1, w ).w );
 	const uint32_t spec = __float_as_uint( localPos.w ) & 3;
 	float w0 = (1 - fx) * (1 - fy), w1 = fx * (1 - fy), w2 = (1 - fx) * fy, w3 = 1 - (w0 + w1 + w2);
 	if (dot( UnpackNormal2( n0 ), localNormal ) < 0.95f || (n0 & 3) != spec) w0 = 0;
@@ -124,16 +141,16 @@ __device__ __forceinline__ float4 ReadTexelConsistent( const float4* __restrict_
 	if (sum == 0) return make_float4( -1, -1, -1, -1 );
 	return (w0 * p0 + w1 * p1 + w2 * p2 + w3 * p3) * (1.0f / sum);
 }
-__device__ __forceinline__ void ReadTexelConsistent2( const float4* __restrict__ buffer, const float4* __restrict__ prevWorldPos, const float4 localPos,
+__device__ __forceinline__ void ReadTexelConsistent2( const HistBuf& buffer, const HistBuf& prevWorldPos, const ShardMap& m, const float4 localPos,
 	const float3 localNormal, const float u, const float v, const int w, const int h, float3& direct, float3& indirect )
 {
 	direct.x = -1;
 	const int iu1 = (int)floorf( u ), iv1 = (int)floorf( v ), iu0 = max( 0, iu1 - 1 ), iv0 = max( 0, iv1 - 1 );
 	if (iu1 >= w || iv1 >= h || iu1 < 0 || iv1 < 0) return;
 	const float fx = u - floorf( u ), fy = v - floorf( v );
-	const float4 p0 = buffer[iu0 + iv0 * w], p1 = buffer[iu1 + iv0 * w], p2 = buffer[iu0 + iv1 * w], p3 = buffer[iu1 + iv1 * w];
-	const uint32_t n0 = __float_as_uint( prevWorldPos[iu0 + iv0 * w].w ), n1 = __float_as_uint( prevWorldPos[iu1 + iv0 * w].w );
-	const uint32_t n2 = __float_as_uint( prevWorldPos[iu0 + iv1 * w].w ), n3 = __float_as_uint( prevWorldPos[iu1 + iv1 * w].w );
+	const float4 p0 = HistAt( buffer, m, iu0, iv0, w ), p1 = HistAt( buffer, m, iu1, iv0, w ), p2 = HistAt( buffer, m, iu0, iv1, w ), p3 = HistAt( buffer, m, iu1, iv1, w );
+	const uint32_t n0 = __float_as_uint( HistAt( prevWorldPos, m, iu0, iv0, w ).w ), n1 = __float_as_uint( HistAt( prevWorldPos, m, iu1, iv0, w ).w );
+	const uint32_t n2 = __float_as_uint( HistAt( prevWorldPos, m, iu0, iv1, w ).w ), n3 = __float_as_uint( HistAt( prevWorldPos, m, iu1, iv1, w ).w );
 	const uint32_t spec = __float_as_uint( localPos.w ) & 3;
 	float w0 = (1 - fx) * (1 - fy), w1 = fx * (1 - fy), w2 = (1 - fx) * fy, w3 = 1 - (w0 + w1 + w2);
 	if (dot( UnpackNormal2( n0 ), localNormal ) < 0.975f || (n0 & 3) != spec) w0 = 0;
@@ -149,20 +166,20 @@ __device__ __forceinline__ void ReadTexelConsistent2( const float4* __restrict__
 
 /* ---- prepare (finalize_shared.h:169-314) ------------------------------------------------------------------------ */
 /* curN = UnpackNormal2( cur.w ), unpacked once per pixel by the caller instead of once per texel (16 texels per search step) */
-__device__ __forceinline__ float WorldDistance( const int x, const int y, const float4 cur, const float3 curN, const float4* __restrict__ prevWorldPos, const int w, const int h )
+__device__ __forceinline__ float WorldDistance( const int x, const int y, const float4 cur, const float3 curN, const HistBuf& prevWorldPos, const ShardMap& m, const int w, const int h )
 {
-	const float4 p = ReadWorldPos( prevWorldPos, x, y, w, h );
+	const float4 p = ReadWorldPos( prevWorldPos, m, x, y, w, h );
 	if ((__float_as_uint( p.w ) & 3) != 1) return 1e21f;
 	if (dot( curN, UnpackNormal2( __float_as_uint( p.w ) ) ) < 0.85f) return 1e21f;
 	return sqrtf( sqrLen( make_float3( cur.x - p.x, cur.y - p.y, cur.z - p.z ) ) );
 }
-__device__ __forceinline__ float FineWorldDistance( const float px, const float py, const float4 cur, const float3 curN, const float4* __restrict__ prevWorldPos, const int w, const int h )
+__device__ __forceinline__ float FineWorldDistance( const float px, const float py, const float4 cur, const float3 curN, const HistBuf& prevWorldPos, const ShardMap& m, const int w, const int h )
 {
 	const int x0 = (int)px, y0 = (int)py;
 	const float fx = px - floorf( px ), fy = py - floorf( py );
 	const float w0 = (1 - fx) * (1 - fy), w1 = fx * (1 - fy), w2 = (1 - fx) * fy, w3 = fx * fy;
-	const float d0 = WorldDistance( x0, y0, cur, curN, prevWorldPos, w, h ), d1 = WorldDistance( x0 + 1, y0, cur, curN, prevWorldPos, w, h );
-	const float d2 = WorldDistance( x0, y0 + 1, cur, curN, prevWorldPos, w, h ), d3 = WorldDistance( x0 + 1, y0 + 1, cur, curN, prevWorldPos, w, h );
+	const float d0 = WorldDistance( x0, y0, cur, curN, prevWorldPos, m, w, h ), d1 = WorldDistance( x0 + 1, y0, cur, curN, prevWorldPos, m, w, h );
+	const float d2 = WorldDistance( x0, y0 + 1, cur, curN, prevWorldPos, m, w, h ), d3 = WorldDistance( x0 + 1, y0 + 1, cur, curN, prevWorldPos, m, w, h );
 	float totalWeight = 0, totalDist = 0;
 	if (d0 < 1e20f) totalDist += d0 * w0, totalWeight += w0;
 	if (d1 < 1e20f) totalDist += d1 * w1, totalWeight += w1;
@@ -173,8 +190,9 @@ __device__ __forceinline__ float FineWorldDistance( const float px, const float 
 
 struct PrepareArgs
 {
-	const float4* accumulator; uint4* features; const float4* worldPos; const float4* prevWorldPos;
-	float4* shading; float2* motion; float4* moments; const float4* prevMoments; const float4* deltaDepth;
+	const float4* accumulator; uint4* features; const float4* worldPos; HistBuf prevWorldPos;
+	float4* shading; float2* motion; float4* moments; HistBuf prevMoments; const float4* deltaDepth;
+	ShardMap map; int yBlock0;	// first block row of the launch (a band of the frame when the chain is sharded)
 	float4 prevPos, prevE, prevRight, prevUp;
 	float j0, j1, prevj0, prevj1;
 	int w, h; float pixelValueScale, directClamp, indirectClamp; int camIsStationary;
@@ -203,7 +221,7 @@ __device__ __forceinline__ void PrepareFinish( const PrepareArgs& a, const int p
 	uint32_t fw = feat.w;
 	if (prev.x >= 0 && prev.x < a.w && prev.y >= 0 && prev.y < a.h)
 	{
-		const float4 history = ReadTexelConsistent( a.prevMoments, a.prevWorldPos, lwp, UnpackNormal2( feat.y ), prev.x, prev.y, a.w, a.h );
+		const float4 history = ReadTexelConsistent( a.prevMoments, a.prevWorldPos, a.map, lwp, UnpackNormal2( feat.y ), prev.x, prev.y, a.w, a.h );
 		if (history.x > -1)
 		{
 			l.lumDirect = 0.2f * l.lumDirect + 0.8f * history.x, l.lumDirect2 = 0.2f * l.lumDirect2 + 0.8f * history.y;
@@ -222,7 +240,7 @@ __device__ __forceinline__ void PrepareFinish( const PrepareArgs& a, const int p
 __device__ __forceinline__ float2 DiamondSearch( const PrepareArgs& a, const int pixelIdx, const int x, const int y, const float4 lwp )
 {
 	float2 prev = make_float2( (float)x, (float)y );
-	const float4 pw = a.prevWorldPos[pixelIdx];
+	const float4 pw = HistAt( a.prevWorldPos, a.map, x, y, a.w );
 	const float3 lwpN = UnpackNormal2( __float_as_uint( lwp.w ) );
 	float bestDist = sqrtf( sqrLen( make_float3( lwp.x - pw.x, lwp.y - pw.y, lwp.z - pw.z ) ) ), stepSize = 5.0f;
 	const float ox = a.j0 - a.prevj0, oy = a.j1 - a.prevj1;
@@ -232,13 +250,13 @@ __device__ __forceinline__ float2 DiamondSearch( const PrepareArgs& a, const int
 		int tap = 0;
 		const float cx = prev.x, cy = prev.y;
 		float d;
-		d = FineWorldDistance( cx - stepSize + ox, cy + oy, lwp, lwpN, a.prevWorldPos, a.w, a.h );
+		d = FineWorldDistance( cx - stepSize + ox, cy + oy, lwp, lwpN, a.prevWorldPos, a.map, a.w, a.h );
 		if (d < bestDist) bestDist = d, prev = make_float2( cx - stepSize, cy ), tap = 1;
-		d = FineWorldDistance( cx + stepSize + ox, cy + oy, lwp, lwpN, a.prevWorldPos, a.w, a.h );
+		d = FineWorldDistance( cx + stepSize + ox, cy + oy, lwp, lwpN, a.prevWorldPos, a.map, a.w, a.h );
 		if (d < bestDist) bestDist = d, prev = make_float2( cx + stepSize, cy ), tap = 2;
-		d = FineWorldDistance( cx + ox, cy - stepSize + oy, lwp, lwpN, a.prevWorldPos, a.w, a.h );
+		d = FineWorldDistance( cx + ox, cy - stepSize + oy, lwp, lwpN, a.prevWorldPos, a.map, a.w, a.h );
 		if (d < bestDist) bestDist = d, prev = make_float2( cx, cy - stepSize ), tap = 3;
-		d = FineWorldDistance( cx + ox, cy + stepSize + oy, lwp, lwpN, a.prevWorldPos, a.w, a.h );
+		d = FineWorldDistance( cx + ox, cy + stepSize + oy, lwp, lwpN, a.prevWorldPos, a.map, a.w, a.h );
 		if (d < bestDist) bestDist = d, prev = make_float2( cx, cy + stepSize ), tap = 4;
 		if (tap == 0) { stepSize *= 0.45f; if (stepSize < 0.05f) break; }
 		if (++iter == 25) break;
@@ -252,7 +270,7 @@ __device__ __forceinline__ float2 DiamondSearch( const PrepareArgs& a, const int
    with full warps; everything a pixel writes is its own, so the split changes no value. */
 template <bool DEFER> __global__ void __launch_bounds__( 256 ) prepareKernel( const PrepareArgs a, uint32_t* __restrict__ queue, uint32_t* __restrict__ queueCount )
 {
-	const int x = threadIdx.x + blockIdx.x * blockDim.x, y = threadIdx.y + blockIdx.y * blockDim.y;
+	const int x = threadIdx.x + blockIdx.x * blockDim.x, y = threadIdx.y + (blockIdx.y + a.yBlock0) * blockDim.y;
 	const bool inside = x < a.w && y < a.h;
 	const int pixelIdx = inside ? x + y * a.w : 0;
 	bool defer = false;
@@ -324,7 +342,7 @@ __global__ void __launch_bounds__( 256 ) prepareSearchKernel( const PrepareArgs 
 				const int y = pixelIdx / a.w, x = pixelIdx - y * a.w;
 				lwp = a.worldPos[pixelIdx];
 				lwpN = UnpackNormal2( __float_as_uint( lwp.w ) );
-				const float4 pw = a.prevWorldPos[pixelIdx];
+				const float4 pw = HistAt( a.prevWorldPos, a.map, x, y, a.w );
 				prev = make_float2( (float)x, (float)y );
 				bestDist = sqrtf( sqrLen( make_float3( lwp.x - pw.x, lwp.y - pw.y, lwp.z - pw.z ) ) ), stepSize = 5.0f, iter = 0;
 				active = true;
@@ -341,13 +359,13 @@ __global__ void __launch_bounds__( 256 ) prepareSearchKernel( const PrepareArgs 
 			int tap = 0;
 			const float cx = prev.x, cy = prev.y;
 			float d;
-			d = FineWorldDistance( cx - stepSize + ox, cy + oy, lwp, lwpN, a.prevWorldPos, a.w, a.h );
+			d = FineWorldDistance( cx - stepSize + ox, cy + oy, lwp, lwpN, a.prevWorldPos, a.map, a.w, a.h );
 			if (d < bestDist) bestDist = d, prev = make_float2( cx - stepSize, cy ), tap = 1;
-			d = FineWorldDistance( cx + stepSize + ox, cy + oy, lwp, lwpN, a.prevWorldPos, a.w, a.h );
+			d = FineWorldDistance( cx + stepSize + ox, cy + oy, lwp, lwpN, a.prevWorldPos, a.map, a.w, a.h );
 			if (d < bestDist) bestDist = d, prev = make_float2( cx + stepSize, cy ), tap = 2;
-			d = FineWorldDistance( cx + ox, cy - stepSize + oy, lwp, lwpN, a.prevWorldPos, a.w, a.h );
+			d = FineWorldDistance( cx + ox, cy - stepSize + oy, lwp, lwpN, a.prevWorldPos, a.map, a.w, a.h );
 			if (d < bestDist) bestDist = d, prev = make_float2( cx, cy - stepSize ), tap = 3;
-			d = FineWorldDistance( cx + ox, cy + stepSize + oy, lwp, lwpN, a.prevWorldPos, a.w, a.h );
+			d = FineWorldDistance( cx + ox, cy + stepSize + oy, lwp, lwpN, a.prevWorldPos, a.map, a.w, a.h );
 			if (d < bestDist) bestDist = d, prev = make_float2( cx, cy + stepSize ), tap = 4;
 			bool done = false;
 			if (tap == 0) { stepSize *= 0.45f; if (stepSize < 0.05f) done = true; }
@@ -375,9 +393,10 @@ __global__ void __launch_bounds__( 256 ) prepareFinishKernel( const PrepareArgs 
 #define AT_BX 32
 struct AtrousArgs
 {
-	const uint4* features; const float4* prevWorldPos; const float4* worldPos; const float4* deltaDepth; const float2* motion; const float4* moments;
-	const float4* A; const float4* B; float4* C;
+	const uint4* features; HistBuf prevWorldPos; const float4* worldPos; const float4* deltaDepth; const float2* motion; const float4* moments;
+	const float4* A; HistBuf B; float4* C;
 	int w, h, phase, lastPass;
+	ShardMap map; int yBlock0;
 };
 
 /* The block stages its tile plus the halo UNPACKED: every tile pixel is decoded once (5.11 fixed point -> float, luminances,
@@ -422,7 +441,7 @@ template <int STEP, int BY, int PIX> __global__ void __launch_bounds__( AT_BX * 
 	static_assert( PIX == 1 || BY % STEP == 0, "rows of a block must pair up" );
 	extern __shared__ float4 tile[];
 	float4* tDir = tile, * tInd = tile + TW * TH, * tNrm = tile + 2 * TW * TH, * tAlb = tile + 3 * TW * TH;
-	const int x0 = blockIdx.x * AT_BX, y0 = blockIdx.y * ROWS;
+	const int x0 = blockIdx.x * AT_BX, y0 = (blockIdx.y + a.yBlock0) * ROWS;
 	for (int i = threadIdx.y * AT_BX + threadIdx.x; i < TW * TH; i += AT_BX * BY)
 	{
 		const int ty = i / TW, tx = i - ty * TW;
@@ -502,7 +521,7 @@ template <int STEP, int BY, int PIX> __global__ void __launch_bounds__( AT_BX * 
 			{
 				float3 prevDirect, prevIndirect;
 				const float4 localPos = a.worldPos[pixelIdx];
-				ReadTexelConsistent2( a.B, a.prevWorldPos, localPos, localNormal, pp.x, pp.y, a.w, a.h, prevDirect, prevIndirect );
+				ReadTexelConsistent2( a.B, a.prevWorldPos, a.map, localPos, localNormal, pp.x, pp.y, a.w, a.h, prevDirect, prevIndirect );
 				if (prevDirect.x != -1)
 				{
 					prevDirect = RGBToYCoCg( prevDirect ), prevIndirect = RGBToYCoCg( prevIndirect );
@@ -590,12 +609,12 @@ __device__ __forceinline__ void LoadTile34x10( float4 (*tile)[34], uint64_t* bar
 }
 
 /* ---- TAA (finalize_shared.h:498-548) ------------------------------------------------------------------------------ */
-__global__ void __launch_bounds__( 256 ) taaKernel( const float4* __restrict__ pixelsIn, float4* __restrict__ pixelsOut, const float4* __restrict__ prevPixels,
-	const float2* __restrict__ motion, const int w, const int h )
+__global__ void __launch_bounds__( 256 ) taaKernel( const float4* __restrict__ pixelsIn, float4* __restrict__ pixelsOut, const __grid_constant__ HistBuf prevPixels, const __grid_constant__ ShardMap map,
+	const float2* __restrict__ motion, const int w, const int h, const int yBlock0 )
 {
 	__shared__ __align__( 16 ) float4 tile[10][34];
 	__shared__ __align__( 8 ) uint64_t tileBar;
-	const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 8;
+	const int x0 = blockIdx.x * 32, y0 = (blockIdx.y + yBlock0) * 8;
 	LoadTile34x10( tile, &tileBar, pixelsIn, x0, y0, w, h );
 	const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
 	if (x >= w || y >= h) return;
@@ -615,7 +634,7 @@ __global__ void __launch_bounds__( 256 ) taaKernel( const float4* __restrict__ p
 			for (int yy = y1; yy < y1 + 4; yy++) for (int xx = x1; xx < x1 + 4; xx++) if (xx >= 0 && yy > 0 && xx < w && yy < h)
 			{
 				const float weight = MitchellNetravali( (float)xx - pu ) * MitchellNetravali( (float)yy - pv );
-				total = total + prevPixels[xx + yy * w] * weight, totalWeight += weight;
+				total = total + HistAt( prevPixels, map, xx, yy, w ) * weight, totalWeight += weight;
 			}
 			hist = xyz( total * (1.0f / totalWeight) );
 		}
@@ -648,14 +667,16 @@ __global__ void __launch_bounds__( 256 ) taaKernel( const float4* __restrict__ p
 }
 
 /* ---- present: unsharpenTAAKernel (:554-583) or finalizeNoTAAKernel (:589-600); border pixels are left untouched ---- */
-__global__ void __launch_bounds__( 256 ) presentKernel( const float4* __restrict__ pixels, float4* __restrict__ target, const int w, const int h, const int taa )
+/* rows [rowFirst, rowEnd) only (the whole frame, or the band of this rank when the chain is sharded) */
+__global__ void __launch_bounds__( 256 ) presentKernel( const float4* __restrict__ pixels, float4* __restrict__ target, const int w, const int h, const int taa,
+	const int yBlock0, const int rowFirst, const int rowEnd )
 {
 	__shared__ __align__( 16 ) float4 tile[10][34];
 	__shared__ __align__( 8 ) uint64_t tileBar;
-	const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 8;
+	const int x0 = blockIdx.x * 32, y0 = (blockIdx.y + yBlock0) * 8;
 	LoadTile34x10( tile, &tileBar, pixels, x0, y0, w, h );
 	const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
-	if (x == 0 || y == 0 || x >= w - 1 || y >= h - 1) return;
+	if (x == 0 || y == 0 || x >= w - 1 || y >= h - 1 || y < rowFirst || y >= rowEnd) return;
 	const int cx = threadIdx.x + 1, cy = threadIdx.y + 1;
 	const float4 c = tile[cy][cx];
 	if (!taa)
@@ -678,7 +699,22 @@ static void FilterChainImpl( const FilterBuffers& b, const FilterSettings& s, cu
 	mark( 0 );
 	auto snap = [&]( float* dst, const float4* src ) { if (dst) cudaMemcpyAsync( dst, src, (size_t)s.w * s.h * 16, cudaMemcpyDeviceToHost, st ); };
 	const int w = s.w, h = s.h;
-	const dim3 grid( (w + 31) / 32, (h + 7) / 8 ), block( 32, 8 );
+	// rows this launch works on: the frame, or (sharded chain) this rank's band plus the halo - rowFirst is a multiple of 16
+	const FilterShard* sh = b.shard;
+	const int rowFirst = sh ? sh->rowFirst : 0, rowEnd = sh ? sh->rowEnd : h, rows = rowEnd - rowFirst;
+	const int presentFirst = sh ? sh->presentFirst : 0, presentEnd = sh ? sh->presentEnd : h;
+	const dim3 grid( (w + 31) / 32, (rows + 7) / 8 ), block( 32, 8 );
+	ShardMap map = { 0, 0 };
+	if (sh) map.magic = (uint32_t)((1ull << 32) / (uint32_t)sh->rowsPerBand + 1), map.last = sh->world - 1;
+	// margin: how many rows beyond the band this rank's own copy of last frame's buffer is valid (16: every halo row, 14: phase-1 output, 1: TAA image)
+	auto hist = [&]( const float4* local, const float4* const* perRank, const int margin ) {
+		HistBuf hb = {};
+		hb.local = local;
+		if (!sh) { hb.p[0] = local, hb.lo = 0, hb.hi = h; return hb; }	// one GPU: every row is local
+		for (int r = 0; r < sh->world; r++) hb.p[r] = perRank[r];
+		hb.lo = std::max( margin > 16 ? 0 : rowFirst, sh->presentFirst - margin ), hb.hi = std::min( margin > 16 ? h : rowEnd, sh->presentEnd + margin );
+		if (getenv( "LH2B_SHARD_NO_LOCAL" )) hb.lo = sh->presentFirst, hb.hi = sh->presentEnd;	// experiment: halo rows from their owner as well
+		return hb; };
 	// reprojection constants of the previous view (finalize_shared.h:301-313)
 	const float* pv = s.prevView;
 	const float3 pos = make_float3( pv[0], pv[1], pv[2] ), p1 = make_float3( pv[3], pv[4], pv[5] ), p2 = make_float3( pv[6], pv[7], pv[8] ), p3 = make_float3( pv[9], pv[10], pv[11] );
@@ -687,8 +723,9 @@ static void FilterChainImpl( const FilterBuffers& b, const FilterSettings& s, cu
 	const float3 centre = 0.5f * (p2 + p3), direction = norm( centre - pos ), right = norm( p2 - p1 ), up = norm( p3 - p1 );
 	const float lenReci = h / len( p3 - p1 );
 	PrepareArgs pa;
-	pa.accumulator = b.accumulator, pa.features = b.features, pa.worldPos = b.worldPos, pa.prevWorldPos = b.prevWorldPos;
-	pa.shading = b.shading, pa.motion = b.motion, pa.moments = b.moments, pa.prevMoments = b.prevMoments, pa.deltaDepth = b.deltaDepth;
+	pa.accumulator = b.accumulator, pa.features = b.features, pa.worldPos = b.worldPos, pa.prevWorldPos = hist( b.prevWorldPos, sh ? sh->prevWorldPos : nullptr, sh ? sh->worldPosMargin : 16 );
+	pa.shading = b.shading, pa.motion = b.motion, pa.moments = b.moments, pa.prevMoments = hist( b.prevMoments, sh ? sh->prevMoments : nullptr, 16 ), pa.deltaDepth = b.deltaDepth;
+	pa.map = map, pa.yBlock0 = rowFirst / 8;
 	pa.prevPos = f4( pos, -(dot( pos, direction ) - dot( centre, direction )) ), pa.prevE = f4( direction, 0 );
 	pa.prevRight = f4( right * lenReci, dot( p1, right ) * lenReci ), pa.prevUp = f4( up * lenReci, dot( p1, up ) * lenReci );
 	pa.j0 = s.j0, pa.j1 = s.j1, pa.prevj0 = s.prevj0, pa.prevj1 = s.prevj1;
@@ -709,8 +746,8 @@ static void FilterChainImpl( const FilterBuffers& b, const FilterSettings& s, cu
 	mark( 1 );
 	snap( hPrepare, b.shading );
 	AtrousArgs aa;
-	aa.features = b.features, aa.prevWorldPos = b.prevWorldPos, aa.worldPos = b.worldPos, aa.deltaDepth = b.deltaDepth, aa.motion = b.motion, aa.moments = b.moments;
-	aa.w = w, aa.h = h;
+	aa.features = b.features, aa.prevWorldPos = pa.prevWorldPos, aa.worldPos = b.worldPos, aa.deltaDepth = b.deltaDepth, aa.motion = b.motion, aa.moments = b.moments;
+	aa.w = w, aa.h = h, aa.map = map;
 	// step 1: 32 x 8 threads, one pixel each (62 registers, 8 blocks / SM); steps 2 and 4: 32 x 8 threads, two pixels STEP rows apart each
 	// (the halo of 2 * STEP pixels is amortised over 16 rows and every tap is weighed for both) - measured per pass at 4K in
 	// profiles/r2_reference_kernels.json; 64 bytes of tile per pixel
@@ -722,34 +759,43 @@ static void FilterChainImpl( const FilterBuffers& b, const FilterSettings& s, cu
 		cudaFuncSetAttribute( atrousKernel<4, 8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem( 4, 16 ) );
 		attr = true;
 	}
-	const dim3 grid16( (w + 31) / 32, (h + 15) / 16 );
-	aa.A = b.shading, aa.B = b.filteredIN, aa.C = b.filteredOUT, aa.phase = 1, aa.lastPass = 0;
+	const dim3 grid16( (w + 31) / 32, (rows + 15) / 16 );
+	// sharded: phase 2 must not overwrite filteredIN - the other ranks read it (last frame's phase-1 output) until they are through phase 1
+	float4* phase2Out = sh ? sh->phase2Out : b.filteredIN;
+	aa.A = b.shading, aa.B = hist( b.filteredIN, sh ? sh->filteredIN : nullptr, 14 ), aa.C = b.filteredOUT, aa.phase = 1, aa.lastPass = 0, aa.yBlock0 = rowFirst / 8;
 	atrousKernel<1, 8, 1><<<grid, block, smem( 1, 8 ), st>>>( aa );
 	mark( 2 );
 	snap( hP1, b.filteredOUT );
-	aa.A = b.filteredOUT, aa.B = nullptr, aa.C = b.filteredIN, aa.phase = 2;
+	aa.A = b.filteredOUT, aa.B = HistBuf{}, aa.C = phase2Out, aa.phase = 2, aa.yBlock0 = rowFirst / 16;
 	atrousKernel<2, 8, 2><<<grid16, block, smem( 2, 16 ), st>>>( aa );
 	mark( 3 );
-	snap( hP2, b.filteredIN );
-	aa.A = b.filteredIN, aa.C = b.shading, aa.phase = 3, aa.lastPass = 1;
+	snap( hP2, phase2Out );
+	aa.A = phase2Out, aa.C = b.shading, aa.phase = 3, aa.lastPass = 1;
 	atrousKernel<4, 8, 2><<<grid16, block, smem( 4, 16 ), st>>>( aa );
 	mark( 4 );
 	snap( hP3, b.shading );
+	const dim3 gridPresent( (w + 31) / 32, (presentEnd - presentFirst + 7) / 8 );
 	if (s.taa)
 	{
-		taaKernel<<<grid, block, 0, st>>>( b.shading, b.taaOut, b.prevPixels, b.motion, w, h );
+		// (sharded: the present pass needs one TAA row beyond the band - one 8-row block either side; their history taps are remote reads)
+		const int taaFirst = sh ? std::max( rowFirst, presentFirst - 8 ) : 0, taaEnd = sh ? std::min( rowEnd, presentEnd + 8 ) : h;
+		const dim3 gridTaa( (w + 31) / 32, (taaEnd - taaFirst + 7) / 8 );
+		taaKernel<<<gridTaa, block, 0, st>>>( b.shading, b.taaOut, hist( b.prevPixels, sh ? sh->prevPixels : nullptr, 1 ), map, b.motion, w, h, taaFirst / 8 );
 		mark( 5 );
-		presentKernel<<<grid, block, 0, st>>>( b.taaOut, b.target, w, h, 1 );
+		presentKernel<<<gridPresent, block, 0, st>>>( b.taaOut, b.target, w, h, 1, presentFirst / 8, presentFirst, presentEnd );
 	}
 	else
 	{
 		mark( 5 );
-		presentKernel<<<grid, block, 0, st>>>( b.shading, b.target, w, h, 0 );
+		presentKernel<<<gridPresent, block, 0, st>>>( b.shading, b.target, w, h, 0, presentFirst / 8, presentFirst, presentEnd );
 	}
 	mark( 6 );
 }
 
-void LaunchFilterChain( const FilterBuffers& b, const FilterSettings& s, cudaStream_t st, cudaEvent_t* stageEvents ) { FilterChainImpl( b, s, st, nullptr, nullptr, nullptr, nullptr, stageEvents ); }
+void LaunchFilterChain( const FilterBuffers& b, const FilterSettings& s, cudaStream_t st, cudaEvent_t* stageEvents )
+{
+	FilterChainImpl( b, s, st, nullptr, nullptr, nullptr, nullptr, stageEvents );
+}
 void LaunchFilterChainStaged( const FilterBuffers& b, const FilterSettings& s, cudaStream_t st, float* hPrepare, float* hP1, float* hP2, float* hP3 )
 {
 	FilterChainImpl( b, s, st, hPrepare, hP1, hP2, hP3 );

@@ -18,6 +18,21 @@ void LaunchExtendCounted( const DevScene& scene, const PathSet& in, float4* hits
 void LaunchConnect( const DevScene& scene, const PathSet& conn, float4* accumulator, const uint32_t* countPtr, uint32_t* workCounter, uint32_t maxRays, int smCount, cudaStream_t s );
 void LaunchShade( const RenderParams& p, const PathSet& in, const PathSet& out, const float4* hits, const PathSet& conn,
 	int pathLength, uint32_t R0, bool useNEE, uint32_t maxPaths, int smCount, cudaStream_t s );
+/* The filter chain of ONE frame sharded over the GPUs of a box (tile_gather.cu): this rank runs every stage on the rows of its band plus
+   16 halo rows on either side (prepare +-16 -> a-trous 1 +-14 -> a-trous 2 +-10 -> a-trous 3 +-2 -> TAA +-1 -> present: the band), and the
+   history buffers, which are read at reprojected positions anywhere in the frame, are read row by row from the rank that owns the row -
+   loads over NVLink through the peer mappings below, issued by the filter kernels themselves. */
+#define LH2B_MAX_SHARDS 8
+struct FilterShard
+{
+	int world, rowsPerBand;			// row y of a history buffer lives on rank min( y / rowsPerBand, world - 1 ); rowsPerBand is a multiple of 16
+	int rowFirst, rowEnd;				// rows every stage computes here (band + halo, clipped to the frame)
+	int presentFirst, presentEnd;		// rows the present pass writes: the band
+	int worldPosMargin;				// rows beyond the band for which this rank holds last frame's world positions itself (the renderers send a wider strip of this
+									// input than the 16 halo rows: the diamond search of prepare wanders, and its dependent gathers should not cross NVLink)
+	const float4* prevWorldPos[LH2B_MAX_SHARDS], * prevMoments[LH2B_MAX_SHARDS], * filteredIN[LH2B_MAX_SHARDS], * prevPixels[LH2B_MAX_SHARDS];	// per rank; [own rank] = the local buffer
+	float4* phase2Out;				// output of the second a-trous pass (the single-GPU chain reuses filteredIN for it)
+};
 /* SVGF / TAA chain (filter_kernels.cu). Buffers are float4[w*h] unless noted. */
 struct FilterBuffers
 {
@@ -26,6 +41,7 @@ struct FilterBuffers
 	float4* shading; float2* motion; float4* moments; const float4* prevMoments;
 	float4* filteredIN; float4* filteredOUT;	// IN holds last frame's phase-1 output on entry and this frame's phase-2 output on exit
 	const float4* prevPixels; float4* taaOut; float4* target;
+	const FilterShard* shard = nullptr;	// set: prevWorldPos / prevMoments / filteredIN (as history) / prevPixels above are ignored in favour of the per-rank tables
 };
 struct FilterSettings
 {

@@ -102,15 +102,34 @@ static void RunFilter( lh2b_core* core )
 	b.moments = core->momentsBuf[cur].ptr, b.prevMoments = core->momentsBuf[prev].ptr;
 	b.filteredIN = core->filteredBuf[cur].ptr, b.filteredOUT = core->filteredBuf[prev].ptr;
 	b.prevPixels = core->taaBuf[prev].ptr, b.taaOut = core->taaBuf[cur].ptr, b.target = core->pixels.ptr;
+	FilterShard shard;
+	if (core->filterShard)
+	{
+		// this rank filters its band of the frame; history rows come from the rank that owns them (all ranks flip in step)
+		shard = *core->filterShard;
+		for (int r = 0; r < shard.world; r++)
+			shard.prevWorldPos[r] = core->shardHist[0][prev][r], shard.prevMoments[r] = core->shardHist[1][prev][r],
+			shard.filteredIN[r] = core->shardHist[2][cur][r], shard.prevPixels[r] = core->shardHist[3][prev][r];
+		if (getenv( "LH2B_SHARD_LOCAL_HIST" ))	// timing experiment only (wrong image): every history read stays on this GPU
+			for (int r = 0; r < shard.world; r++)
+				shard.prevWorldPos[r] = core->worldPosBuf[prev].ptr, shard.prevMoments[r] = core->momentsBuf[prev].ptr,
+				shard.filteredIN[r] = core->filteredBuf[cur].ptr, shard.prevPixels[r] = core->taaBuf[prev].ptr;
+		b.shard = &shard;
+		if (core->shardTarget) b.target = core->shardTarget;
+	}
 	FilterSettings fs;
 	fs.w = core->width, fs.h = core->height, fs.samplesTaken = core->samplesTaken;
 	fs.camIsStationary = core->samplesTaken == core->spp ? 0 : 1;
 	fs.taa = core->taaEnabled ? 1 : 0, fs.directClamp = core->clampDirect, fs.indirectClamp = core->clampIndirect;
 	fs.j0 = fs.j1 = fs.prevj0 = fs.prevj1 = 0;	// sub-pixel jitter comes from the blue-noise sampler of generate, not from the view
 	memcpy( fs.prevView, core->filterHistoryValid ? &core->prevView : &core->lastView, sizeof( fs.prevView ) );
-	if (core->preciseMath) LaunchFilterChainPrecise( b, fs, core->stream ); else LaunchFilterChain( b, fs, core->stream );
+	cudaStream_t st = core->tailStream ? core->tailStream : core->stream;
+	if (core->preciseMath) LaunchFilterChainPrecise( b, fs, st, core->filterStageEvents ); else LaunchFilterChain( b, fs, st, core->filterStageEvents );
 	if (!core->taaEnabled)	// without TAA the history of the next frame's TAA pass is this frame's filtered image (swap( shading, prevPixels ))
-		CUDA_CHECK( cudaMemcpyAsync( core->taaBuf[cur].ptr, core->shading.ptr, (size_t)core->width * core->height * 16, cudaMemcpyDeviceToDevice, core->stream ) );
+	{
+		const size_t first = core->filterShard ? (size_t)shard.rowFirst * core->width : 0, rows = core->filterShard ? shard.rowEnd - shard.rowFirst : core->height;
+		CUDA_CHECK( cudaMemcpyAsync( core->taaBuf[cur].ptr + first, core->shading.ptr + first, rows * core->width * 16, cudaMemcpyDeviceToDevice, st ) );
+	}
 	// rotation: this frame's phase-1 output (in filteredOUT = filteredBuf[prev]) is the next frame's temporal history (filteredIN)
 	core->filterFlip = prev;
 	core->prevView = core->lastView, core->filterHistoryValid = true;
@@ -219,7 +238,7 @@ static RenderParams BuildParams( lh2b_core* core, const lh2abi::ViewPyramid& vie
 	p.skyPixels = core->skyPixels.ptr, p.skyW = core->skyW, p.skyH = core->skyH;
 	memcpy( p.worldToSky, core->worldToSky, sizeof( p.worldToSky ) );
 	p.blueNoise = core->blueNoise.ptr, p.accumulator = core->accumulator.ptr, p.counters = core->counters.ptr;
-	if (core->filterEnabled && core->features.count) p.features = core->features.ptr, p.worldPos = core->worldPosBuf[core->filterFlip].ptr, p.deltaDepth = core->deltaDepth.ptr;
+	if (core->filterEnabled && core->features.count) p.features = core->featuresOverride ? core->featuresOverride : core->features.ptr, p.worldPos = core->worldPosOverride ? core->worldPosOverride : core->worldPosBuf[core->filterFlip].ptr, p.deltaDepth = core->deltaDepth.ptr;
 	return p;
 }
 
@@ -228,7 +247,11 @@ static RenderParams BuildParams( lh2b_core* core, const lh2abi::ViewPyramid& vie
 static void RotatePixelBuffers( lh2b_core* core )
 {
 	if (!core->copyPending[0]) return;
-	if (core->pixelsAlt.count < core->pixels.count) core->pixelsAlt.Resize( core->pixels.count );
+	if (core->pixelsAlt.count < core->pixels.count)
+	{
+		core->pixelsAlt.Resize( core->pixels.count );
+		CUDA_CHECK( cudaMemsetAsync( core->pixelsAlt.ptr, 0, core->pixelsAlt.count * sizeof( float4 ), core->stream ) );	// as SetTarget does for 'pixels' (the filter's present pass skips the border)
+	}
 	core->pixels.Swap( core->pixelsAlt );
 	std::swap( core->copyDone[0], core->copyDone[1] );
 	std::swap( core->copyPending[0], core->copyPending[1] );
@@ -257,11 +280,13 @@ static void RenderFrame( lh2b_core* core, const lh2abi::ViewPyramid& view )
 		core->accumulator.Swap( core->accumulatorAlt ), core->deltaDepth.Swap( core->deltaDepthAlt );
 		if (core->samplesTaken != 0)
 		{
-			// (only this rank's own rows - a contiguous band: the peers' rows of this frame may have arrived in the new set already)
-			const size_t px = (size_t)core->width * core->height, first = (size_t)BandY0( core ) * core->width, n = (size_t)(BandY1( core ) - BandY0( core )) * core->width * sizeof( float4 );
-			CUDA_CHECK( cudaMemcpyAsync( core->accumulator.ptr + first, core->accumulatorAlt.ptr + first, n, cudaMemcpyDeviceToDevice, s ) );
-			CUDA_CHECK( cudaMemcpyAsync( core->accumulator.ptr + px + first, core->accumulatorAlt.ptr + px + first, n, cudaMemcpyDeviceToDevice, s ) );
-			if (core->deltaDepth.count) CUDA_CHECK( cudaMemcpyAsync( core->deltaDepth.ptr + first, core->deltaDepthAlt.ptr + first, n, cudaMemcpyDeviceToDevice, s ) );
+			// (only this rank's own rows: the peers' rows of this frame may have arrived in the new set already)
+			const size_t px = (size_t)core->width * core->height, first = (size_t)BandY0( core ) * core->width, rowBytes = (size_t)core->width * sizeof( float4 );
+			auto own = [&]( float4* dst, const float4* src ) {
+				if (BandStep( core ) == 1) CUDA_CHECK( cudaMemcpyAsync( dst + first, src + first, (size_t)(BandY1( core ) - BandY0( core )) * rowBytes, cudaMemcpyDeviceToDevice, s ) );
+				else CUDA_CHECK( cudaMemcpy2DAsync( dst + first, (size_t)BandStep( core ) * 4 * rowBytes, src + first, (size_t)BandStep( core ) * 4 * rowBytes, 4 * rowBytes, BandTileRowsOf( core ), cudaMemcpyDeviceToDevice, s ) ); };
+			own( core->accumulator.ptr, core->accumulatorAlt.ptr ), own( core->accumulator.ptr + px, core->accumulatorAlt.ptr + px );
+			if (core->deltaDepth.count) own( core->deltaDepth.ptr, core->deltaDepthAlt.ptr );
 		}
 	}
 	if (core->samplesTaken == 0)
@@ -420,6 +445,8 @@ int lh2b_setting( lh2b_core* core, const char* name, float value )
 	// extensions of this core (the reference fixes these at compile time: core_settings.h:25, pathtracer.h:33)
 	else if (!strcmp( name, "maxPathLength" )) core->maxPathLength = value < 1 ? 1 : (value > LH2B_MAXPATHLENGTH ? LH2B_MAXPATHLENGTH : (int)value);
 	else if (!strcmp( name, "tileRootShare" )) core->tileRootShare = value < 0 ? 0 : (value > 1 ? 1 : value);	// read by lh2b_tile_create
+	else if (!strcmp( name, "tileFilterShard" )) core->tileFilterShard = value > 0 ? 1 : 0;	// read by lh2b_tile_create: every rank filters its own band (filter mode only)
+	else if (!strcmp( name, "tileInterleave" )) core->tileInterleave = value > 0 ? 1 : 0;	// read by lh2b_tile_create (with tileFilterShard): rendered rows interleaved over the ranks (1) or the filter band (0)
 	else if (!strcmp( name, "gatherMode" )) core->gatherMode = value > 0 ? 1 : 0;	// read by lh2b_gather_create
 	else if (!strcmp( name, "l2Persist" )) core->l2Persist = value > 0 ? 1 : 0;	// takes effect at the next FinalizeInstances
 	else if (!strcmp( name, "preciseMath" )) { const int m = value > 0 ? 1 : 0; if (m != core->preciseMath) core->preciseMath = m, core->samplesTaken = 0; }
@@ -620,6 +647,7 @@ int lh2b_read_pixels( lh2b_core* core, float* rgbaOut )
 {
 	API_BEGIN
 	FinishFrame( core );
+	if (core->tailEvent) CUDA_CHECK( cudaStreamWaitEvent( core->stream, core->tailEvent, 0 ) );	// sharded filter chain: the peers' bands of the image
 	CUDA_CHECK( cudaMemcpyAsync( rgbaOut, core->pixels.ptr, (size_t)core->width * core->height * sizeof( float4 ), cudaMemcpyDeviceToHost, core->stream ) );
 	CUDA_CHECK( cudaStreamSynchronize( core->stream ) );
 	API_END
@@ -631,6 +659,7 @@ int lh2b_read_pixels_async( lh2b_core* core, float* pinnedOut )
 	// the frame (finalize included) is already enqueued on the launch stream: order the copy behind it on the copy stream
 	CUDA_CHECK( cudaEventRecord( core->frameDone, core->stream ) );
 	CUDA_CHECK( cudaStreamWaitEvent( core->copyStream, core->frameDone, 0 ) );
+	if (core->tailEvent) CUDA_CHECK( cudaStreamWaitEvent( core->copyStream, core->tailEvent, 0 ) );
 	CUDA_CHECK( cudaMemcpyAsync( pinnedOut, core->pixels.ptr, (size_t)core->width * core->height * sizeof( float4 ), cudaMemcpyDeviceToHost, core->copyStream ) );
 	CUDA_CHECK( cudaEventRecord( core->copyDone[0], core->copyStream ) );
 	core->copyPending[0] = true;
@@ -783,6 +812,25 @@ int lh2b_read_filter_buffers( lh2b_core* core, uint32_t* features, float* worldP
 	if (worldPos) CUDA_CHECK( cudaMemcpyAsync( worldPos, core->worldPosBuf[cur].ptr, px * 16, cudaMemcpyDeviceToHost, s ) );
 	if (deltaDepth) CUDA_CHECK( cudaMemcpyAsync( deltaDepth, core->deltaDepth.ptr, px * 16, cudaMemcpyDeviceToHost, s ) );
 	if (accumulator2) CUDA_CHECK( cudaMemcpyAsync( accumulator2, core->accumulator.ptr, 2 * px * 16, cudaMemcpyDeviceToHost, s ) );
+	CUDA_CHECK( cudaStreamSynchronize( s ) );
+	API_END
+}
+
+/* Filter mode only: the outputs of the last frame's filter chain that the next frame reads as history (any pointer may be null;
+   float4[w*h] each, motion float2[w*h]): moments, phase-1 a-trous output, TAA image, phase-3 output, motion vectors. For tests / debugging. */
+int lh2b_read_filter_history( lh2b_core* core, float* moments, float* phase1, float* taa, float* phase3, float* motion )
+{
+	API_BEGIN
+	FinishFrame( core );
+	if (!core->filterEnabled || core->features.count == 0) throw CoreError( "read_filter_history: filter mode is off" );
+	const size_t px = (size_t)core->width * core->height;
+	const int cur = core->filterFlip ^ 1;	// the chain already rotated
+	cudaStream_t s = core->stream;
+	if (moments) CUDA_CHECK( cudaMemcpyAsync( moments, core->momentsBuf[cur].ptr, px * 16, cudaMemcpyDeviceToHost, s ) );
+	if (phase1) CUDA_CHECK( cudaMemcpyAsync( phase1, core->filteredBuf[cur ^ 1].ptr, px * 16, cudaMemcpyDeviceToHost, s ) );
+	if (taa) CUDA_CHECK( cudaMemcpyAsync( taa, core->taaBuf[cur].ptr, px * 16, cudaMemcpyDeviceToHost, s ) );
+	if (phase3) CUDA_CHECK( cudaMemcpyAsync( phase3, core->shading.ptr, px * 16, cudaMemcpyDeviceToHost, s ) );
+	if (motion) CUDA_CHECK( cudaMemcpyAsync( motion, core->motion.ptr, px * 8, cudaMemcpyDeviceToHost, s ) );
 	CUDA_CHECK( cudaStreamSynchronize( s ) );
 	API_END
 }

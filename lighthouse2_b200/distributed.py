@@ -165,17 +165,23 @@ class TileShardedRenderer:
     """Strong scaling of ONE frame (real-time mode, BASELINE.json configs[4]): rank r path-traces a band of rows, the bands are
     gathered on rank 0 over NVLink peer memory and rank 0 runs the frame's tail (SVGF / TAA chain or finalize) on the complete
     buffers (csrc/tile_gather.cu). Create after SetTarget and Setting("filter"). At 1 spp the frame equals the single-GPU frame
-    bit for bit.
+    bit for bit. filter_shard=1 (filter mode, up to 8 ranks): every rank also filters a band of the frame - history lookups go to the
+    owning rank over NVLink from inside the filter kernels - and rank 0 only collects the presented bands; interleave picks the
+    rendered rows of a rank (1: interleaved 4-row tile rows, 0: its filter band).
 
         frame(view, converge, host_out)   enqueue one frame on this rank (rank 0: the image goes to pinned host_out, or None)
         finish()                          wait for everything this rank has in flight
     """
 
-    def __init__(self, core, rank=None, world=None):
+    def __init__(self, core, rank=None, world=None, filter_shard=None, interleave=None):
         self.core = core
         self.rank = dist.get_rank() if rank is None else rank
         self.world = dist.get_world_size() if world is None else world
         core.Setting("pipeline", 1)
+        if filter_shard is not None:
+            core.Setting("tileFilterShard", int(filter_shard))
+        if interleave is not None:
+            core.Setting("tileInterleave", int(interleave))
         self.g = core.TileCreate(self.rank, self.world)
         handles = [None] * self.world
         dist.all_gather_object(handles, core.TileExport(self.g))

@@ -26,11 +26,20 @@ def make_core(dev, sd, spp):
 
 def tile_sharding(rank, world, local, sd):
     """Tile (row-band) sharded frames, plain and with the SVGF / TAA chain, moving camera: rank 0's image must equal the
-    single-GPU frame bit for bit (1 spp)."""
-    TW, TH = 192, 160
-    views = [scenes.view_pyramid((3 * k, 30, -80 + k), (0, 0, 0), 40, TW, TH) for k in range(5)]
+    single-GPU frame bit for bit (1 spp). Filter mode three ways: tail on rank 0; filter chain sharded too (every rank filters a
+    band, history rows read from their owners over NVLink) with interleaved and with contiguous rendered rows - those two also with
+    converging frames in the sequence."""
+    TW, TH = 192, 240
+    views = [scenes.view_pyramid((3 * k, 30, -80 + k), (0, 0, 0), 40, TW, TH) for k in range(6)]
     ok = True
-    for filt in (0, 1):
+    #        filter, filter_shard, interleave, converge flags
+    cases = [(0, 0, 1, [1] * 6), (1, 0, 1, [1] * 6), (1, 1, 1, [1] * 6), (1, 1, 0, [1] * 6), (1, 1, 1, [1, 1, 0, 0, 1, 0])]
+    if os.environ.get("LH2B_WORKER_CASE"):
+        cases = [cases[int(os.environ["LH2B_WORKER_CASE"])]]
+    for filt, shard, inter, conv in cases:
+        seq = []
+        for k, c in enumerate(conv):
+            seq.append(views[k] if c == 1 else seq[-1])     # a converging frame keeps the view of the frame before
         def make(spp=1):
             c = RenderCore(local)
             c.SetTarget(TW, TH, spp)
@@ -43,22 +52,28 @@ def tile_sharding(rank, world, local, sd):
         want = []
         if rank == 0:
             single = make()
-            for v in views:
-                single.Render(v, 1)
+            for v, c in zip(seq, conv):
+                single.Render(v, c)
                 want.append(single.ReadPixels().copy())
             single.Shutdown()
         core = make()
-        r = TileShardedRenderer(core, rank, world)
+        r = TileShardedRenderer(core, rank, world, filter_shard=shard, interleave=inter)
         outs = [torch.zeros((TH, TW, 4), dtype=torch.float32).pin_memory() for _ in views]
-        for k, v in enumerate(views):
-            r.frame(v, 1, outs[k])
+        for k, (v, c) in enumerate(zip(seq, conv)):
+            r.frame(v, c, outs[k])
         r.finish()
+        name = "plain" if not filt else ("filter, tail on rank 0" if not shard else f"filter, chain sharded, {'interleaved' if inter else 'contiguous'} rows, converge {conv}")
         if rank == 0:
             for k in range(len(views)):
                 same = np.array_equal(outs[k].numpy(), want[k])
                 err = np.abs(outs[k].numpy() - want[k]).max()
-                print(f"tile {'filter' if filt else 'plain'} frame {k}: rows {r.rows} identical={same} max abs err {err:.2e}", flush=True)
+                bad_rows = np.nonzero((outs[k].numpy() != want[k]).any(axis=(1, 2)))[0]
+                print(f"tile [{name}] frame {k}: rows {r.rows} identical={same} max abs err {err:.2e}" + (f" differing rows {bad_rows[:8]}..{bad_rows[-1]} ({len(bad_rows)})" if len(bad_rows) else ""), flush=True)
                 ok &= bool(same)
+                if not same and os.environ.get("LH2B_WORKER_VERBOSE"):
+                    ys, xs = np.nonzero((outs[k].numpy() != want[k]).any(axis=2))
+                    print(f"   {len(ys)} pixels differ; first: " + ", ".join(f"(y{y} x{x}: {outs[k].numpy()[y, x, :3]} vs {want[k][y, x, :3]})" for y, x in list(zip(ys, xs))[:6]), flush=True)
+                    print("   per row: " + " ".join(f"{y}:{int((ys == y).sum())}" for y in np.unique(ys)[:40]), flush=True)
         r.close()
         core.Shutdown()
         dist.barrier()
@@ -80,7 +95,7 @@ def main():
             want.append(single.ReadPixels().copy())
         single.Shutdown()
     ok = True
-    for kind in ("peer", "peer-reduce-scatter", "nccl"):
+    for kind in (() if os.environ.get("LH2B_WORKER_TILE_ONLY") else ("peer", "peer-reduce-scatter", "nccl")):
         core = make_core(local, sd, SPP)
         core.Setting("gatherMode", 1 if kind == "peer-reduce-scatter" else 0)
         r = PeerGatherRenderer(core, SPP, rank, world) if kind.startswith("peer") else PipelinedShardedRenderer(core, SPP, rank, world, f"cuda:{local}")
