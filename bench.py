@@ -553,8 +553,9 @@ def bench_c4(args, rank, world, local_rank):
 
 def bench_c5(args, rank, world, local_rank, barrier, reduce_max_sum):
     """BASELINE.json configs[4]: 4K, 1 spp, SVGF filter + TAA, moving camera, real-time frame-time mode. N GPUs: the frame is
-    tile-sharded (row bands rendered per rank, gathered on rank 0 over NVLink peer memory, filter chain on rank 0). The frame ends
-    in rank 0's device pixel buffer (what a display path consumes); reported as ms per frame."""
+    tile-sharded - rendering AND the filter chain (csrc/tile_gather.cu, Setting tileFilterShard): every rank path-traces interleaved
+    tile rows and filters a band, rank 0 collects the presented bands. The frame ends in rank 0's device pixel buffer (what a display
+    path consumes); reported as ms per frame."""
     import torch
     from lighthouse2_b200 import RenderCore, scenes
     from lighthouse2_b200.distributed import TileShardedRenderer
@@ -567,7 +568,7 @@ def bench_c5(args, rank, world, local_rank, barrier, reduce_max_sum):
     sd.upload(core)
     stream = torch.cuda.ExternalStream(core.Stream(), device=f"cuda:{local_rank}")
     view_of = lambda f: scenes.view_pyramid((0.2 * f, 30, -80 + 0.1 * f), (0, 0, 0), 40, W5, H5)
-    r = TileShardedRenderer(core, rank, world) if world > 1 else None
+    r = TileShardedRenderer(core, rank, world, filter_shard=1, interleave=1) if world > 1 else None
     if r is None:
         core.Setting("pipeline", 1)
 
@@ -598,7 +599,8 @@ def bench_c5(args, rank, world, local_rank, barrier, reduce_max_sum):
     return {"workload": "4K 1 spp + SVGF temporal / a-trous filter + TAA, moving camera, real-time frame-time mode (configs[4])", "n_gpus": world,
             "frames": frames, "ms_per_frame": ms / frames, "fps": frames / (ms * 1e-3), "stage_ms_rank0_last_frame": stages,
             "filter_gb_per_s_at_584_B_per_px": (px * 584 / (stages["filterMs"] * 1e-3) / 1e9) if (world == 1 and stages["filterMs"] > 0) else None,
-            "parallelism": "1 GPU" if world == 1 else f"tile-sharded x{world} (row bands), bands gathered on rank 0 over NVLink peer memory, filter chain on rank 0"}
+            "parallelism": "1 GPU" if world == 1 else f"tile-sharded x{world}: every rank path-traces interleaved 4-row tile rows and filters a band of the frame (band + 16 halo rows; "
+                           "history rows read from their owner over NVLink inside the filter kernels; the chain of frame k runs next to the path tracing of frame k + 1); rank 0 collects the presented bands"}
 
 
 def main():

@@ -102,6 +102,7 @@ struct lh2b_core
 	int tileFilterShard = 0, tileInterleave = 1;
 	const lh2b::FilterShard* filterShard = nullptr;		// set while attached: band, halo rows, phase2Out; RunFilter fills the history tables from shardHist
 	const float4* shardHist[4][2][LH2B_MAX_SHARDS] = {};	// [worldPos, moments, filtered, taa][flip][rank]: every rank's history buffers (peer mappings, own = local)
+	const float4** shardHistDev = nullptr;				// the same table in device memory (the filter kernels index it by the owner of a row)
 	float4* worldPosOverride = nullptr;				// the frame being rendered writes its world positions here (staging set of that frame) instead of worldPosBuf[filterFlip]
 	uint4* featuresOverride = nullptr;				// ... and its features here (its history-counter bits are then meaningless: the gatherer merges them into 'features')
 	cudaStream_t tailStream = nullptr;				// when set, the filter chain runs on this stream (next to the following frame's path tracing on 'stream')

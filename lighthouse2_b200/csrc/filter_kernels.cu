@@ -107,30 +107,34 @@ __device__ __forceinline__ float MitchellNetravali( const float v )
    serves both cases, because the sharded frame has to equal the single-GPU frame bit for bit and two instantiations of the same source
    need not round alike (measured: a second instantiation of the TAA kernel differed by 1-10 ulp where the 4x4 history footprint touches
    the left image edge - the compiler had versioned that loop differently). The price on one GPU is a compare and a select per history read. */
-struct HistBuf { const float4* p[LH2B_MAX_SHARDS]; const float4* local; int lo, hi; };	// rows [lo, hi) of this rank's own copy are valid (its band plus the halo rows it computes itself)
+struct HistBuf { const float4* local; const float4* const* perRank; int lo; uint32_t span; };	// rows [lo, lo + span) of this rank's own copy are valid (its band plus the halo rows
+																						// it computes itself); perRank: device table of every rank's buffer (null on one GPU)
 struct ShardMap { uint32_t magic; int last; };	// owner of row y: min( y / rowsPerBand, last ), the division as a multiplication by magic = 2^32 / rowsPerBand + 1
-__device__ __forceinline__ float4 HistAt( const HistBuf& b, const ShardMap& m, const int x, const int y, const int w )
+/* The common case - a row this rank holds itself - must stay as cheap as the plain load: measured on C5 (one GPU, where every row is
+   local), the owner arithmetic plus an indexed constant load in front of every gather cost 0.4 ms of the 3.3 ms chain, an out-of-line
+   call for the rare case 0.5 ms (the 16 gathers of a search step no longer overlap). Here the owner lookup sits under the predicate of
+   the rare case and reads its table from global memory; the local address needs one subtract and one compare. */
+/* row y of a history buffer (the test is per row: the lookups below fetch two to four texels from each row they touch) */
+__device__ __forceinline__ const float4* HistRow( const HistBuf& b, const ShardMap& m, const int y, const int w )
 {
 	// halo rows are computed on both sides of a band boundary with identical results: whatever this rank computed itself it reads locally
-	const float4* base = (uint32_t)(y - b.lo) < (uint32_t)(b.hi - b.lo) ? b.local : b.p[min( (int)__umulhi( (uint32_t)y, m.magic ), m.last )];
-	return __ldg( base + x + y * w );
+	const float4* base = b.local;
+	if ((uint32_t)(y - b.lo) >= b.span) base = (const float4*)__ldg( (const unsigned long long*)b.perRank + min( (int)__umulhi( (uint32_t)y, m.magic ), m.last ) );
+	return base + y * w;
 }
+__device__ __forceinline__ float4 HistAt( const HistBuf& b, const ShardMap& m, const int x, const int y, const int w ) { return __ldg( HistRow( b, m, y, w ) + x ); }
 
 /* sampling_shared.h:111-215 */
-__device__ __forceinline__ float4 ReadWorldPos( const HistBuf& buffer, const ShardMap& m, const int x, const int y, const int w, const int h )
-{
-	if (x >= 0 && y >= 0 && x < w && y < h) return HistAt( buffer, m, x, y, w );
-	return make_float4( 1e20f, 1e20f, 1e20f, __uint_as_float( 0 ) );
-}
 __device__ __forceinline__ float4 ReadTexelConsistent( const HistBuf& buffer, const HistBuf& prevWorldPos, const ShardMap& m, const float4 localPos,
 	const float3 localNormal, const float u, const float v, const int w, const int h )
 {
 	const int iu1 = (int)floorf( u ), iv1 = (int)floorf( v ), iu0 = max( 0, iu1 - 1 ), iv0 = max( 0, iv1 - 1 );
 	if (iu1 >= w || iv1 >= h || iu1 < 0 || iv1 < 0) return make_float4( -1, -1, -1, -1 );
 	const float fx = u - floorf( u ), fy = v - floorf( v );
-	const float4 p0 = HistAt( buffer, m, iu0, iv0, w ), p1 = HistAt( buffer, m, iu1, iv0, w ), p2 = HistAt( buffer, m, iu0, iv1, w ), p3 = HistAt( buffer, m, iu1, iv1, w );
-	const uint32_t n0 = __float_as_uint( HistAt( prevWorldPos, m, iu0, iv0, w ).w ), n1 = __float_as_uint( HistAt( prevWorldPos, m, iu1, iv0, w ).w );
-	const uint32_t n2 = __float_as_uint( HistAt( prevWorldPos, m, iu0, iv1, w ).w ), n3 = __float_as_uint( HistAt( prevWorldPos, m, iu1, iv1, w ).w );
+	const float4* b0 = HistRow( buffer, m, iv0, w ), * b1 = HistRow( buffer, m, iv1, w ), * q0 = HistRow( prevWorldPos, m, iv0, w ), * q1 = HistRow( prevWorldPos, m, iv1, w );
+	const float4 p0 = __ldg( b0 + iu0 ), p1 = __ldg( b0 + iu1 ), p2 = __ldg( b1 + iu0 ), p3 = __ldg( b1 + iu1 );
+	const uint32_t n0 = __float_as_uint( __ldg( q0 + iu0 ).w ), n1 = __float_as_uint( __ldg( q0 + iu1 ).w );
+	const uint32_t n2 = __float_as_uint( __ldg( q1 + iu0 ).w ), n3 = __float_as_uint( __ldg( q1 + iu1 ).w );
 	const uint32_t spec = __float_as_uint( localPos.w ) & 3;
 	float w0 = (1 - fx) * (1 - fy), w1 = fx * (1 - fy), w2 = (1 - fx) * fy, w3 = 1 - (w0 + w1 + w2);
 	if (dot( UnpackNormal2( n0 ), localNormal ) < 0.95f || (n0 & 3) != spec) w0 = 0;
@@ -148,9 +152,10 @@ __device__ __forceinline__ void ReadTexelConsistent2( const HistBuf& buffer, con
 	const int iu1 = (int)floorf( u ), iv1 = (int)floorf( v ), iu0 = max( 0, iu1 - 1 ), iv0 = max( 0, iv1 - 1 );
 	if (iu1 >= w || iv1 >= h || iu1 < 0 || iv1 < 0) return;
 	const float fx = u - floorf( u ), fy = v - floorf( v );
-	const float4 p0 = HistAt( buffer, m, iu0, iv0, w ), p1 = HistAt( buffer, m, iu1, iv0, w ), p2 = HistAt( buffer, m, iu0, iv1, w ), p3 = HistAt( buffer, m, iu1, iv1, w );
-	const uint32_t n0 = __float_as_uint( HistAt( prevWorldPos, m, iu0, iv0, w ).w ), n1 = __float_as_uint( HistAt( prevWorldPos, m, iu1, iv0, w ).w );
-	const uint32_t n2 = __float_as_uint( HistAt( prevWorldPos, m, iu0, iv1, w ).w ), n3 = __float_as_uint( HistAt( prevWorldPos, m, iu1, iv1, w ).w );
+	const float4* b0 = HistRow( buffer, m, iv0, w ), * b1 = HistRow( buffer, m, iv1, w ), * q0 = HistRow( prevWorldPos, m, iv0, w ), * q1 = HistRow( prevWorldPos, m, iv1, w );
+	const float4 p0 = __ldg( b0 + iu0 ), p1 = __ldg( b0 + iu1 ), p2 = __ldg( b1 + iu0 ), p3 = __ldg( b1 + iu1 );
+	const uint32_t n0 = __float_as_uint( __ldg( q0 + iu0 ).w ), n1 = __float_as_uint( __ldg( q0 + iu1 ).w );
+	const uint32_t n2 = __float_as_uint( __ldg( q1 + iu0 ).w ), n3 = __float_as_uint( __ldg( q1 + iu1 ).w );
 	const uint32_t spec = __float_as_uint( localPos.w ) & 3;
 	float w0 = (1 - fx) * (1 - fy), w1 = fx * (1 - fy), w2 = (1 - fx) * fy, w3 = 1 - (w0 + w1 + w2);
 	if (dot( UnpackNormal2( n0 ), localNormal ) < 0.975f || (n0 & 3) != spec) w0 = 0;
@@ -166,9 +171,10 @@ __device__ __forceinline__ void ReadTexelConsistent2( const HistBuf& buffer, con
 
 /* ---- prepare (finalize_shared.h:169-314) ------------------------------------------------------------------------ */
 /* curN = UnpackNormal2( cur.w ), unpacked once per pixel by the caller instead of once per texel (16 texels per search step) */
-__device__ __forceinline__ float WorldDistance( const int x, const int y, const float4 cur, const float3 curN, const HistBuf& prevWorldPos, const ShardMap& m, const int w, const int h )
+/* row: the texel's row of prevWorldPos, or null when that row lies outside the frame (ReadWorldPos then yields an invalid texel) */
+__device__ __forceinline__ float WorldDistance( const int x, const float4* __restrict__ row, const float4 cur, const float3 curN, const int w )
 {
-	const float4 p = ReadWorldPos( prevWorldPos, m, x, y, w, h );
+	const float4 p = (row != nullptr && x >= 0 && x < w) ? __ldg( row + x ) : make_float4( 1e20f, 1e20f, 1e20f, __uint_as_float( 0 ) );
 	if ((__float_as_uint( p.w ) & 3) != 1) return 1e21f;
 	if (dot( curN, UnpackNormal2( __float_as_uint( p.w ) ) ) < 0.85f) return 1e21f;
 	return sqrtf( sqrLen( make_float3( cur.x - p.x, cur.y - p.y, cur.z - p.z ) ) );
@@ -176,10 +182,11 @@ __device__ __forceinline__ float WorldDistance( const int x, const int y, const 
 __device__ __forceinline__ float FineWorldDistance( const float px, const float py, const float4 cur, const float3 curN, const HistBuf& prevWorldPos, const ShardMap& m, const int w, const int h )
 {
 	const int x0 = (int)px, y0 = (int)py;
+	const float4* r0 = (y0 >= 0 && y0 < h) ? HistRow( prevWorldPos, m, y0, w ) : nullptr, * r1 = (y0 + 1 >= 0 && y0 + 1 < h) ? HistRow( prevWorldPos, m, y0 + 1, w ) : nullptr;
+	const float d0 = WorldDistance( x0, r0, cur, curN, w ), d1 = WorldDistance( x0 + 1, r0, cur, curN, w );
+	const float d2 = WorldDistance( x0, r1, cur, curN, w ), d3 = WorldDistance( x0 + 1, r1, cur, curN, w );
 	const float fx = px - floorf( px ), fy = py - floorf( py );
 	const float w0 = (1 - fx) * (1 - fy), w1 = fx * (1 - fy), w2 = (1 - fx) * fy, w3 = fx * fy;
-	const float d0 = WorldDistance( x0, y0, cur, curN, prevWorldPos, m, w, h ), d1 = WorldDistance( x0 + 1, y0, cur, curN, prevWorldPos, m, w, h );
-	const float d2 = WorldDistance( x0, y0 + 1, cur, curN, prevWorldPos, m, w, h ), d3 = WorldDistance( x0 + 1, y0 + 1, cur, curN, prevWorldPos, m, w, h );
 	float totalWeight = 0, totalDist = 0;
 	if (d0 < 1e20f) totalDist += d0 * w0, totalWeight += w0;
 	if (d1 < 1e20f) totalDist += d1 * w1, totalWeight += w1;
@@ -313,7 +320,10 @@ template <bool DEFER> __global__ void __launch_bounds__( 256 ) prepareKernel( co
 /* Second pass: the diamond search for the queued pixels, persistent-thread style. The number of search iterations varies from
    7 to 25 per pixel, so a lane that finishes early takes the next queued pixel (one warp-aggregated atomicAdd once 8 lanes are
    idle) instead of idling until the slowest lane of its warp is done. The result (the reprojected position) is parked in the
-   motion buffer; prepareFinishKernel completes those pixels with full warps. counters: [0] = queue length, [1] = fetch cursor. */
+   motion buffer; prepareFinishKernel completes those pixels with full warps. counters: [0] = queue length, [1] = fetch cursor.
+   (r2, measured and dropped: keeping the distances of the 4 x 4 texels around the search centre in shared memory once the step is below
+   one pixel - the last five steps of every search revisit them - made the chain of C5 1.0 ms SLOWER: the centre changes its texel cell on
+   most improving steps, and a refill costs as much as the step it replaces.) */
 __global__ void __launch_bounds__( 256 ) prepareSearchKernel( const PrepareArgs a, const uint32_t* __restrict__ queue, uint32_t* __restrict__ counters )
 {
 	const uint32_t n = counters[0];
@@ -631,10 +641,14 @@ __global__ void __launch_bounds__( 256 ) taaKernel( const float4* __restrict__ p
 			const int x1 = (int)(pu - 2.0f), y1 = (int)(pv - 2.0f);
 			float totalWeight = 0;
 			float4 total = make_float4( 0, 0, 0, 0 );
-			for (int yy = y1; yy < y1 + 4; yy++) for (int xx = x1; xx < x1 + 4; xx++) if (xx >= 0 && yy > 0 && xx < w && yy < h)
+			for (int yy = y1; yy < y1 + 4; yy++) if (yy > 0 && yy < h)
 			{
-				const float weight = MitchellNetravali( (float)xx - pu ) * MitchellNetravali( (float)yy - pv );
-				total = total + HistAt( prevPixels, map, xx, yy, w ) * weight, totalWeight += weight;
+				const float4* row = HistRow( prevPixels, map, yy, w );
+				for (int xx = x1; xx < x1 + 4; xx++) if (xx >= 0 && xx < w)
+				{
+					const float weight = MitchellNetravali( (float)xx - pu ) * MitchellNetravali( (float)yy - pv );
+					total = total + __ldg( row + xx ) * weight, totalWeight += weight;
+				}
 			}
 			hist = xyz( total * (1.0f / totalWeight) );
 		}
@@ -710,10 +724,10 @@ static void FilterChainImpl( const FilterBuffers& b, const FilterSettings& s, cu
 	auto hist = [&]( const float4* local, const float4* const* perRank, const int margin ) {
 		HistBuf hb = {};
 		hb.local = local;
-		if (!sh) { hb.p[0] = local, hb.lo = 0, hb.hi = h; return hb; }	// one GPU: every row is local
-		for (int r = 0; r < sh->world; r++) hb.p[r] = perRank[r];
-		hb.lo = std::max( margin > 16 ? 0 : rowFirst, sh->presentFirst - margin ), hb.hi = std::min( margin > 16 ? h : rowEnd, sh->presentEnd + margin );
-		if (getenv( "LH2B_SHARD_NO_LOCAL" )) hb.lo = sh->presentFirst, hb.hi = sh->presentEnd;	// experiment: halo rows from their owner as well
+		if (!sh) { hb.lo = 0, hb.span = (uint32_t)h; return hb; }	// one GPU: every row is local
+		hb.perRank = perRank;
+		hb.lo = std::max( margin > 16 ? 0 : rowFirst, sh->presentFirst - margin );
+		hb.span = (uint32_t)(std::min( margin > 16 ? h : rowEnd, sh->presentEnd + margin ) - hb.lo);
 		return hb; };
 	// reprojection constants of the previous view (finalize_shared.h:301-313)
 	const float* pv = s.prevView;

@@ -30,7 +30,7 @@ struct FilterShard
 	int presentFirst, presentEnd;		// rows the present pass writes: the band
 	int worldPosMargin;				// rows beyond the band for which this rank holds last frame's world positions itself (the renderers send a wider strip of this
 									// input than the 16 halo rows: the diamond search of prepare wanders, and its dependent gathers should not cross NVLink)
-	const float4* prevWorldPos[LH2B_MAX_SHARDS], * prevMoments[LH2B_MAX_SHARDS], * filteredIN[LH2B_MAX_SHARDS], * prevPixels[LH2B_MAX_SHARDS];	// per rank; [own rank] = the local buffer
+	const float4* const* prevWorldPos, * const* prevMoments, * const* filteredIN, * const* prevPixels;	// DEVICE tables of 'world' pointers: every rank's buffer (peer mappings; [own rank] = the local buffer)
 	float4* phase2Out;				// output of the second a-trous pass (the single-GPU chain reuses filteredIN for it)
 };
 /* SVGF / TAA chain (filter_kernels.cu). Buffers are float4[w*h] unless noted. */

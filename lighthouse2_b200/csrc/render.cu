@@ -107,13 +107,8 @@ static void RunFilter( lh2b_core* core )
 	{
 		// this rank filters its band of the frame; history rows come from the rank that owns them (all ranks flip in step)
 		shard = *core->filterShard;
-		for (int r = 0; r < shard.world; r++)
-			shard.prevWorldPos[r] = core->shardHist[0][prev][r], shard.prevMoments[r] = core->shardHist[1][prev][r],
-			shard.filteredIN[r] = core->shardHist[2][cur][r], shard.prevPixels[r] = core->shardHist[3][prev][r];
-		if (getenv( "LH2B_SHARD_LOCAL_HIST" ))	// timing experiment only (wrong image): every history read stays on this GPU
-			for (int r = 0; r < shard.world; r++)
-				shard.prevWorldPos[r] = core->worldPosBuf[prev].ptr, shard.prevMoments[r] = core->momentsBuf[prev].ptr,
-				shard.filteredIN[r] = core->filteredBuf[cur].ptr, shard.prevPixels[r] = core->taaBuf[prev].ptr;
+		auto table = [&]( int kind, int flip ) { return (const float4* const*)(core->shardHistDev + (kind * 2 + flip) * LH2B_MAX_SHARDS); };
+		shard.prevWorldPos = table( 0, prev ), shard.prevMoments = table( 1, prev ), shard.filteredIN = table( 2, cur ), shard.prevPixels = table( 3, prev );
 		b.shard = &shard;
 		if (core->shardTarget) b.target = core->shardTarget;
 	}

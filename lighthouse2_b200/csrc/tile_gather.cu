@@ -221,7 +221,7 @@ static void ShardCreate( lh2b_tile_gather* g )
 	core->tileDouble = true, core->tileFrames = 0;
 	core->filterShard = &g->fs;
 	core->worldPosOverride = g->wpStage[0], core->featuresOverride = g->featStage[0];
-	core->tailStream = getenv( "LH2B_SHARD_NO_OVERLAP" ) ? core->stream : g->tail;
+	core->tailStream = getenv( "LH2B_SHARD_NO_OVERLAP" ) ? core->stream : g->tail;	// (the environment switch is for A/B measurements: chain behind the frame on one stream)
 	core->shardTarget = nullptr;
 	if (g->rank == 0) core->tailEvent = g->tailEvent;
 }
@@ -271,6 +271,9 @@ static void ShardImport( lh2b_tile_gather* g, const TileHandles* h )
 		}
 		if (r != g->rank) g->peerFlags[r] = (uint32_t*)open( h[r].flags );
 	}
+	// the filter kernels look a row's owner up in device memory
+	CUDA_CHECK( cudaMalloc( (void**)&c->shardHistDev, sizeof( c->shardHist ) ) );
+	CUDA_CHECK( cudaMemcpy( (void*)c->shardHistDev, c->shardHist, sizeof( c->shardHist ), cudaMemcpyHostToDevice ) );
 }
 
 static void ShardFrame( lh2b_tile_gather* g )
@@ -294,7 +297,7 @@ static void ShardFrame( lh2b_tile_gather* g )
 	// while the last connect pass runs; the accumulator halves follow when the frame is done
 	for (int round = 0; round < 2; round++)
 	{
-		CUDA_CHECK( cudaStreamWaitEvent( g->comm, (round == 0 && !getenv( "LH2B_SHARD_NO_EARLY" )) ? core->events[5 * core->maxPathLength + 3] : g->rendered, 0 ) );
+		CUDA_CHECK( cudaStreamWaitEvent( g->comm, round == 0 ? core->events[5 * core->maxPathLength + 3] : g->rendered, 0 ) );
 		for (int d = 0; d < g->world; d++)
 		{
 			if (d == me) continue;
@@ -400,6 +403,7 @@ static void ShardDestroy( lh2b_tile_gather* g )
 	cudaStreamSynchronize( g->tail );
 	core->filterShard = nullptr, core->worldPosOverride = nullptr, core->featuresOverride = nullptr, core->tailStream = nullptr, core->shardTarget = nullptr, core->tailEvent = nullptr;
 	memset( core->shardHist, 0, sizeof( core->shardHist ) );
+	if (core->shardHistDev) cudaFree( (void*)core->shardHistDev ), core->shardHistDev = nullptr;
 	for (void* m : g->maps) cudaIpcCloseMemHandle( m );
 	cudaFree( g->flags ), cudaFree( g->phase2 );
 	for (int i = 0; i < 2; i++) cudaFree( g->outStage[i] );

@@ -13,15 +13,23 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
 inter = int(sys.argv[1]) if len(sys.argv) > 1 else 1
-TW, TH = 192, 240
-sd = scenes.config2_scene(48, 32, n_materials=4, light_quads=2, floaters=200)
-views = [scenes.view_pyramid((3 * k, 30, -80 + k), (0, 0, 0), 40, TW, TH) for k in range(4)]
+if os.environ.get("SHARD_DEBUG_4K"):       # the C5 workload itself
+    TW, TH = 3840, 2160
+    sd = scenes.config2_scene(1000, 500, n_materials=64, light_quads=8)
+    views = [scenes.view_pyramid((0.2 * k, 30, -80 + 0.1 * k), (0, 0, 0), 40, TW, TH) for k in range(int(os.environ.get("SHARD_DEBUG_FRAMES", "5")))]
+else:
+    TW, TH = 192, 240
+    sd = scenes.config2_scene(48, 32, n_materials=4, light_quads=2, floaters=200)
+    views = [scenes.view_pyramid((3 * k, 30, -80 + k), (0, 0, 0), 40, TW, TH) for k in range(4)]
 
 
 def make():
     c = RenderCore(local)
     c.SetTarget(TW, TH, 1)
     c.Setting("epsilon", 1e-3), c.Setting("maxPathLength", 3), c.Setting("filter", 1), c.Setting("TAA", 1)
+    for key, val in os.environ.items():         # LH2B_SET_<setting>=<value>, e.g. bvhBuilder=1: the deterministic host builder gives every core the same tree
+        if key.startswith("LH2B_SET_"):
+            c.Setting(key[9:], float(val))
     sd.upload(c)
     return c
 
@@ -40,6 +48,15 @@ for k, v in enumerate(views):
     got = dict(zip(("features", "worldPos", "deltaDepth", "accumulator"), core.ReadFilterBuffers()))
     got.update(core.ReadFilterHistory())
     lines = []
+    img_single, img = single.ReadPixels(), None
+    if rank == 0:
+        img = core.ReadPixels()
+        d = (img.view(np.uint32) != img_single.view(np.uint32)).any(axis=2)
+        if d.any():
+            ys, xs = np.nonzero(d)
+            print(f"frame {k} FINAL IMAGE differs in {len(ys)} px, rows {ys.min()}..{ys.max()}; first (y{ys[0]} x{xs[0]}): {img[ys[0], xs[0]]} vs {img_single[ys[0], xs[0]]}", flush=True)
+        else:
+            print(f"frame {k} final image identical", flush=True)
     if k > 0 and (got["taa"][b0:b1].view(np.uint32) != want["taa"][b0:b1].view(np.uint32)).any():
         ys, xs = np.nonzero((got["taa"][b0:b1].view(np.uint32) != want["taa"][b0:b1].view(np.uint32)).any(axis=2))
         y, x = b0 + ys[0], xs[0]
