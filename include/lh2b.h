@@ -46,7 +46,10 @@ LH2B_API int lh2b_set_target( lh2b_core* core, int width, int height, int spp );
      frame scheduling               pipeline (1: Render( async ) enqueues frame k+1 behind frame k; statistics lag one frame),
                                     overlapConnect (1 default: connect( L ) runs next to extend( L + 1 ) on a second stream),
                                     gatherMode (read by lh2b_gather_create: 0 root gather default, 1 reduce-scatter),
-                                    tileRootShare (read by lh2b_tile_create: rank 0's band relative to an equal share, 0..1)
+                                    tileRootShare (read by lh2b_tile_create: rank 0's band relative to an equal share, 0..1),
+                                    tileFilterShard (read by lh2b_tile_create, filter mode, 2..8 ranks: 1 = every rank also filters a band
+                                    of the frame, see below; default 0 = the tail runs on rank 0), tileInterleave (with tileFilterShard:
+                                    1 default = rendered rows interleaved over the ranks, 0 = a rank renders its filter band)
      numerics                       preciseMath (1: the shade and filter stages run their IEEE / libm-accurate builds - no fast math, no FMA
                                     contraction; default 0 = the reference's -use_fast_math behaviour)
      kernel tuning (measurement)    wideBlocksPerSM, triThreshold, triThresholdShadow, refillThreshold */
@@ -132,7 +135,12 @@ LH2B_API int lh2b_host_bvh_build( const float* verts4, int triCount, void* nodes
    peers' rows into rank 0's buffers over NVLink and runs the filter chain / finalize there. Handles are exchanged like the
    gather's: lh2b_tile_handle_bytes() per rank, all-gathered in rank order. While a tile gatherer is attached only rank 0 presents:
    the peers' pixel buffers are not updated (their frames end after the last connect), and a probe pixel outside a rank's band is
-   not probed by that rank. */
+   not probed by that rank.
+   Setting "tileFilterShard" 1 (before lh2b_tile_create; filter mode): the SVGF / TAA chain is sharded as well - rank r filters the rows
+   [r * B, (r+1) * B) (B: an equal share rounded up to 16 rows) plus 16 halo rows, reads the history rows of other bands from their
+   owners over NVLink from inside the filter kernels, and presents its band into rank 0's image; the chain of frame k runs on its own
+   stream next to the path tracing of frame k + 1. Same calls, same result on rank 0 (bit-identical to one GPU at 1 spp); lh2b_read_pixels*
+   on rank 0 wait for the peers' bands. The frame height must be a multiple of 4 and give every rank a non-empty band. */
 typedef struct lh2b_tile_gather lh2b_tile_gather;
 LH2B_API int lh2b_set_row_band( lh2b_core* core, int y0, int y1 );
 LH2B_API int lh2b_set_row_band_strided( lh2b_core* core, int y0, int y1, int stepTileRows );	/* tile rows y0/4 + j * step below row y1 */
