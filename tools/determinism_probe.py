@@ -1,5 +1,5 @@
-"""Is a 4K filter-mode frame of the C5 workload reproducible bit for bit (a) on the same core, twice, (b) on a second core that built
-its own acceleration structure, (c) with another BVH builder? Prints the number of differing accumulator pixels.
+"""Is a 4K filter-mode frame of the C5 workload reproducible bit for bit on several core instances of one process (each builds its own
+acceleration structure; LH2B_SET_bvhBuilder=1 selects the deterministic host builder)? Prints the number of differing accumulator pixels.
     python tools/determinism_probe.py"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -39,9 +39,21 @@ def diff(a, b, what):
         print(f"{what}: frame {k}: {len(ys)} accumulator pixels differ" + (f", e.g. (y{ys[0]} x{xs[0]}): {x[:, ys[0], xs[0]].ravel()} vs {y[:, ys[0], xs[0]].ravel()}" if len(ys) else ""), flush=True)
 
 
-a = make()
-fa1 = frames(a)
-fa2 = frames(a)
-diff(fa1, fa2, "same core, run twice")
-b = make()
-diff(fa1, frames(b), "second core, own BVH build")
+mode = sys.argv[1] if len(sys.argv) > 1 else "order"
+if mode == "order":
+    a = make()
+    fa = frames(a)
+    b = make()
+    fb = frames(b)
+    c = make()
+    fc = frames(c)
+    diff(fa, fb, "first core vs second core")
+    diff(fb, fc, "second core vs third core")
+elif mode == "create-first":     # both cores exist before either renders
+    a, b = make(), make()
+    fa, fb = frames(a), frames(b)
+    diff(fa, fb, "created a, b; rendered a, then b")
+elif mode == "b-first":          # ... and the second one renders first
+    a, b = make(), make()
+    fb, fa = frames(b), frames(a)
+    diff(fa, fb, "created a, b; rendered b, then a")
