@@ -146,6 +146,10 @@ LH2B_API int lh2b_set_row_band( lh2b_core* core, int y0, int y1 );
 LH2B_API int lh2b_set_row_band_strided( lh2b_core* core, int y0, int y1, int stepTileRows );	/* tile rows y0/4 + j * step below row y1 */
 LH2B_API int lh2b_tile_handle_bytes( void );
 LH2B_API int lh2b_tile_layout( int height, int world, float rootShare, int rank, int* y0, int* y1, int* stepTileRows );	/* the band of a rank; needs no device */
+/* layout of the sharded filter chain (tileFilterShard; no device needed): band = { y0, y1, stepTileRows } rendered by 'rank', the rows it filters
+   and presents, those rows plus the 16 halo rows, and the strip of world positions it receives; and the tile rows of a band inside a row range */
+LH2B_API int lh2b_tile_shard_layout( int height, int world, int interleave, int rank, int* band3, int* filterBand2, int* withHalo2, int* worldPosStrip2 );
+LH2B_API int lh2b_tile_rows_inside( int y0, int y1, int stepTileRows, int e0, int e1, int* firstTileRow, int* count );
 LH2B_API int lh2b_tile_create( lh2b_core* core, int rank, int world, lh2b_tile_gather** out );
 LH2B_API int lh2b_tile_export( lh2b_tile_gather* g, void* handlesOut );
 LH2B_API int lh2b_tile_import( lh2b_tile_gather* g, const void* handlesOfAllRanks );

@@ -49,6 +49,8 @@ SIGNATURES = {
     "lh2b_set_row_band_strided": ([_vp, _ip, _ip, _ip], _ip),
     "lh2b_tile_handle_bytes": ([], _ip),
     "lh2b_tile_layout": ([_ip, _ip, _c.c_float, _ip, _c.POINTER(_ip), _c.POINTER(_ip), _c.POINTER(_ip)], _ip),
+    "lh2b_tile_shard_layout": ([_ip, _ip, _ip, _ip, _c.POINTER(_ip), _c.POINTER(_ip), _c.POINTER(_ip), _c.POINTER(_ip)], _ip),
+    "lh2b_tile_rows_inside": ([_ip, _ip, _ip, _ip, _ip, _c.POINTER(_ip), _c.POINTER(_ip)], _ip),
     "lh2b_tile_create": ([_vp, _ip, _ip, _c.POINTER(_vp)], _ip),
     "lh2b_tile_export": ([_vp, _vp], _ip),
     "lh2b_tile_import": ([_vp, _vp], _ip),

@@ -430,6 +430,32 @@ int lh2b_tile_layout( int height, int world, float rootShare, int rank, int* y0,
 	API_END
 }
 
+/* Layout of the sharded filter chain (Setting "tileFilterShard"; pure host arithmetic, no device needed): the rows a rank renders
+   (band: y0, y1, step in tile rows), the rows it filters and presents (filterBand), the rows every filter stage computes there
+   (withHalo = filterBand +- 16, clipped) and the strip of world positions it receives (worldPosStrip = filterBand +- 64, clipped). */
+int lh2b_tile_shard_layout( int height, int world, int interleave, int rank, int* band, int* filterBand, int* withHalo, int* worldPosStrip )
+{
+	API_BEGIN
+	if (world < 2 || world > LH2B_MAX_SHARDS || rank < 0 || rank >= world || height < 4 * world || (height & 3)) throw CoreError( "tile_shard_layout: arguments out of range" );
+	int rowsPerBand = 0;
+	ShardLayout( height, world, interleave, rank, band, withHalo, &rowsPerBand );
+	if ((world - 1) * rowsPerBand >= height) throw CoreError( "tile_shard_layout: frame too small for this many filter bands (16-row granularity)" );
+	filterBand[0] = rank * rowsPerBand, filterBand[1] = std::min( height, (rank + 1) * rowsPerBand );
+	worldPosStrip[0] = std::max( 0, filterBand[0] - WP_MARGIN ), worldPosStrip[1] = std::min( height, rank * rowsPerBand + rowsPerBand + WP_MARGIN );
+	API_END
+}
+
+/* The 4-row tile rows of the rendered band (y0, y1, step) that lie inside the rows [e0, e1): first tile row and count (what one
+   strided peer copy moves). */
+int lh2b_tile_rows_inside( int y0, int y1, int stepTileRows, int e0, int e1, int* firstTileRow, int* count )
+{
+	API_BEGIN
+	if (stepTileRows < 1 || (e0 & 3) || (y0 & 3)) throw CoreError( "tile_rows_inside: arguments out of range" );
+	const RowSpan r = BandInside( y0, y1, stepTileRows, e0, e1 );
+	*firstTileRow = r.tile0, *count = r.count;
+	API_END
+}
+
 int lh2b_tile_create( lh2b_core* core, int rank, int world, lh2b_tile_gather** out )
 {
 	API_BEGIN
