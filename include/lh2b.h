@@ -140,7 +140,9 @@ LH2B_API int lh2b_host_bvh_build( const float* verts4, int triCount, void* nodes
    [r * B, (r+1) * B) (B: an equal share rounded up to 16 rows) plus 16 halo rows, reads the history rows of other bands from their
    owners over NVLink from inside the filter kernels, and presents its band into rank 0's image; the chain of frame k runs on its own
    stream next to the path tracing of frame k + 1. Same calls, same result on rank 0 (bit-identical to one GPU at 1 spp); lh2b_read_pixels*
-   on rank 0 wait for the peers' bands. The frame height must be a multiple of 4 and give every rank a non-empty band. */
+   on rank 0 wait for the peers' bands. The frame height must be a multiple of 4 and give every rank a non-empty band. Every rank must
+   have finished its frames (lh2b_tile_wait, then a barrier of the caller's) before any rank calls lh2b_tile_destroy: the peers read this
+   rank's history buffers until their own chain is through. */
 typedef struct lh2b_tile_gather lh2b_tile_gather;
 LH2B_API int lh2b_set_row_band( lh2b_core* core, int y0, int y1 );
 LH2B_API int lh2b_set_row_band_strided( lh2b_core* core, int y0, int y1, int stepTileRows );	/* tile rows y0/4 + j * step below row y1 */

@@ -677,6 +677,7 @@ int lh2b_present_gl( lh2b_core* core, unsigned int glTextureId )
 	API_BEGIN
 	if (glTextureId == 0 || core->width <= 0) throw CoreError( "present_gl: no target" );
 	FinishFrame( core );
+	if (core->tailEvent) CUDA_CHECK( cudaStreamWaitEvent( core->stream, core->tailEvent, 0 ) );	// sharded filter chain: the peers' bands of the image
 	if (core->glResource && (core->glRegisteredTexture != glTextureId || core->glRegisteredW != core->width || core->glRegisteredH != core->height)) ReleaseGlTarget( core );
 	if (!core->glResource)
 	{
