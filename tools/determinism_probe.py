@@ -57,3 +57,17 @@ elif mode == "b-first":          # ... and the second one renders first
     a, b = make(), make()
     fb, fa = frames(b), frames(a)
     diff(fa, fb, "created a, b; rendered b, then a")
+elif mode == "geometry":         # do the two cores hold the same vertex / shading-triangle data after the upload?
+    a, b = make(), make()
+    for i, (v, t) in enumerate(sd.meshes):
+        n = np.asarray(v).reshape(-1, 4).shape[0] // 3
+        va, ta = a.ReadGeometry(i, n)
+        vb, tb = b.ReadGeometry(i, n)
+        same_v = np.array_equal(va.view(np.uint32), vb.view(np.uint32))
+        same_t = ta.tobytes() == tb.tobytes()
+        same_in = np.array_equal(va.view(np.uint32), np.ascontiguousarray(v, np.float32).reshape(-1, 4).view(np.uint32))
+        print(f"mesh {i}: {n} triangles, vertices identical {same_v} (and equal to the input: {same_in}), shading triangles identical {same_t}", flush=True)
+        if not same_t:
+            ba, bb = np.frombuffer(ta.tobytes(), np.uint32).reshape(n, -1), np.frombuffer(tb.tobytes(), np.uint32).reshape(n, -1)
+            tri, word = np.nonzero(ba != bb)
+            print(f"   {len(tri)} words differ; triangles {np.unique(tri)[:8]}, word offsets {np.unique(word)}", flush=True)
