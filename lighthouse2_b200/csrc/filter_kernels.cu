@@ -622,6 +622,8 @@ __device__ __forceinline__ void LoadTile34x10( float4 (*tile)[34], uint64_t* bar
 __global__ void __launch_bounds__( 256 ) taaKernel( const float4* __restrict__ pixelsIn, float4* __restrict__ pixelsOut, const __grid_constant__ HistBuf prevPixels, const __grid_constant__ ShardMap map,
 	const float2* __restrict__ motion, const int w, const int h, const int yBlock0 )
 {
+	// (r2, measured on the same box: reading the 3x3 neighbourhood straight from global memory instead of the staged tile: 0.291 vs 0.297 ms
+	// at 4K - the kernel's time is the 16 history gathers and the arithmetic, not the neighbourhood)
 	__shared__ __align__( 16 ) float4 tile[10][34];
 	__shared__ __align__( 8 ) uint64_t tileBar;
 	const int x0 = blockIdx.x * 32, y0 = (blockIdx.y + yBlock0) * 8;
