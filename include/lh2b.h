@@ -250,6 +250,9 @@ LH2B_API int lh2b_read_filter_buffers( lh2b_core* core, uint32_t* features, floa
 /* ... and what the chain of the last frame left for the next one (any pointer may be null; float4[w*h], motion float2[w*h]):
    luminance moments, phase-1 a-trous output, TAA image, phase-3 output, motion vectors. */
 LH2B_API int lh2b_read_filter_history( lh2b_core* core, float* moments, float* phase1, float* taa, float* phase3, float* motion );
+/* Debugging aid: one of the core's device tables (materials, triLights, pointLights, spotLights, dirLights, instDesc, blueNoise, sky, argb32,
+   argb128, nrm32, instTrav, nodes, tris) copied to host memory; *bytesOut = its size, at most maxBytes are copied (out may be null). */
+LH2B_API int lh2b_debug_read_table( lh2b_core* core, const char* name, void* out, size_t maxBytes, size_t* bytesOut );
 
 /* Presenting through CUDA-OpenGL interop, as the reference's InteropTexture does (lib/CUDA/shared_host_code/interoptexture.cpp:53-61:
    cudaGraphicsGLRegisterImage on GLTexture::ID, map, write, unmap): copies the finished frame from the core's linear RGBA32F

@@ -84,6 +84,7 @@ SIGNATURES = {
     "lh2b_shade_paths_time": ([_vp, _ip, _ip, _vp, _vp, _vp, _vp, _c.c_uint, _c.c_uint, _ip, _ip, _vp], _ip),
     "lh2b_read_filter_buffers": ([_vp, _vp, _vp, _vp, _vp], _ip),
     "lh2b_read_filter_history": ([_vp, _vp, _vp, _vp, _vp, _vp], _ip),
+    "lh2b_debug_read_table": ([_vp, _c.c_char_p, _vp, _c.c_size_t, _c.POINTER(_c.c_size_t)], _ip),
     "lh2b_shade_paths": ([_vp, _ip, _ip, _vp, _vp, _vp, _vp, _c.c_uint, _c.c_uint, _ip, _vp, _vp, _vp, _c.POINTER(_ip),
                           _vp, _vp, _vp, _c.POINTER(_ip), _vp], _ip),
     "CreateCore": ([], _vp),

@@ -314,6 +314,15 @@ class RenderCore:
         self._check(self._lib.lh2b_read_filter_history(self._h, *[_ptr(out[k]) for k in ("moments", "phase1", "taa", "phase3", "motion")]))
         return out
 
+    def DebugReadTable(self, name):
+        """One of the core's device tables as raw bytes (uint8 array); see lh2b_debug_read_table."""
+        n = ctypes.c_size_t()
+        self._check(self._lib.lh2b_debug_read_table(self._h, name.encode(), None, 0, ctypes.byref(n)))
+        out = np.zeros(n.value, np.uint8)
+        if n.value:
+            self._check(self._lib.lh2b_debug_read_table(self._h, name.encode(), _ptr(out), n.value, ctypes.byref(n)))
+        return out
+
     def FilterChain(self, io):
         """Parity hook (lh2b_filter_chain): io is a ctypes structure laid out like lh2b_filter_io."""
         self._check(self._lib.lh2b_filter_chain(self._h, ctypes.byref(io)))

@@ -831,6 +831,27 @@ int lh2b_read_filter_history( lh2b_core* core, float* moments, float* phase1, fl
 	API_END
 }
 
+/* Debugging aid: copy one of the core's device tables to host memory (at most maxBytes; *bytesOut = its size). Names: materials, triLights,
+   pointLights, spotLights, dirLights, instDesc, blueNoise, sky, argb32, argb128, nrm32, instTrav, nodes, tris. */
+int lh2b_debug_read_table( lh2b_core* core, const char* name, void* out, size_t maxBytes, size_t* bytesOut )
+{
+	API_BEGIN
+	FinishFrame( core );
+	const void* src = nullptr;
+	size_t bytes = 0;
+#define TABLE( NAME, BUF ) if (!strcmp( name, NAME )) src = core->BUF.ptr, bytes = core->BUF.count * sizeof( *core->BUF.ptr );
+	TABLE( "materials", materials ) TABLE( "triLights", triLights ) TABLE( "pointLights", pointLights ) TABLE( "spotLights", spotLights )
+	TABLE( "dirLights", dirLights ) TABLE( "instDesc", instDesc ) TABLE( "blueNoise", blueNoise ) TABLE( "sky", skyPixels )
+	TABLE( "argb32", argb32 ) TABLE( "argb128", argb128 ) TABLE( "nrm32", nrm32 ) TABLE( "instTrav", instTrav )
+#undef TABLE
+	if (!strcmp( name, "nodes" )) src = core->arenaNodes.ptr, bytes = (size_t)core->arenaNodeTop * CW_NODE_QUADS * sizeof( uint4 );
+	if (!strcmp( name, "tris" )) src = core->arenaTris.ptr, bytes = (size_t)core->arenaTriTop * 3 * sizeof( float4 );
+	if (!src && bytes == 0 && strcmp( name, "nodes" ) && strcmp( name, "tris" )) { bool known = false; for (const char* n : { "materials", "triLights", "pointLights", "spotLights", "dirLights", "instDesc", "blueNoise", "sky", "argb32", "argb128", "nrm32", "instTrav" }) known |= !strcmp( name, n ); if (!known) throw CoreError( "debug_read_table: unknown table" ); }
+	if (bytesOut) *bytesOut = bytes;
+	if (out && src && bytes) CUDA_CHECK( cudaMemcpy( out, src, std::min( bytes, maxBytes ), cudaMemcpyDeviceToHost ) );
+	API_END
+}
+
 int lh2b_filter_chain( lh2b_core* core, lh2b_filter_io* io )
 {
 	API_BEGIN

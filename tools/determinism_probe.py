@@ -71,3 +71,10 @@ elif mode == "geometry":         # do the two cores hold the same vertex / shadi
             ba, bb = np.frombuffer(ta.tobytes(), np.uint32).reshape(n, -1), np.frombuffer(tb.tobytes(), np.uint32).reshape(n, -1)
             tri, word = np.nonzero(ba != bb)
             print(f"   {len(tri)} words differ; triangles {np.unique(tri)[:8]}, word offsets {np.unique(word)}", flush=True)
+elif mode == "tables":           # ... and the same materials, lights, instance descriptors, sampler tables, sky, acceleration structure?
+    a, b = make(), make()
+    for name in ("materials", "triLights", "pointLights", "spotLights", "dirLights", "instDesc", "blueNoise", "sky", "argb32", "argb128", "nrm32", "instTrav", "nodes", "tris"):
+        ta, tb = a.DebugReadTable(name), b.DebugReadTable(name)
+        same = ta.shape == tb.shape and np.array_equal(ta, tb)
+        where = "" if same or ta.shape != tb.shape else f"; first differing byte {int(np.nonzero(ta != tb)[0][0])}, {int((ta != tb).sum())} bytes differ"
+        print(f"{name}: {ta.size} bytes, identical {same}{where}", flush=True)
