@@ -37,18 +37,23 @@
    from inside the filter kernels (filter_kernels.cu, SHARD = true). Rendering is sharded independently of that: interleaved 4-row tile
    rows (Setting "tileInterleave" 1, balanced) or the filter band itself (0).
 
-     rank r, frame k:  [core stream]  render its tile rows: accumulator / deltaDepth into set k & 1, world positions into staging set k & 1
-                       [comm stream]  for every rank d whose band + halo holds rows r rendered: wait( done[d] >= k-1 ) (d is through the chain of
-                                      frame k-2, which read set k & 1); copy those rows of accumulator x2, deltaDepth, features (staging), world
-                                      positions (staging) into d's set k & 1; d.arrived[r] = k+1
-                       [core stream]  wait( arrived[s] >= k+1 ) for every sender s; wait( done[s] >= k ) for EVERY s: all ranks are through the
-                                      chain of frame k-1, so its outputs - this frame's history - are complete everywhere and nobody reads the
-                                      history of frame k-2 any more, which this frame overwrites;
+     rank r, frame k:  [core stream]  render its tile rows: accumulator / deltaDepth into set k & 1, features and world positions into staging set
+                                      k & 1 (the next frame's rendering starts as soon as the chain and the pushes of frame k-1 are through: every
+                                      buffer a frame writes exists twice, by frame parity)
+                       [comm stream]  for every rank d whose band + halo (world positions: band + 64 rows) holds rows r rendered:
+                                      wait( done[d] >= k-1 ) (d is through the chain of frame k-2, which read set k & 1); copy those rows of
+                                      deltaDepth, features, world positions once the last shade pass is through, of the accumulator halves once
+                                      the frame is; d.arrived[r] = k+1
+                       [tail stream]  (high priority, next to the core stream) wait( arrived[s] >= k+1 ) for every sender s; wait( done[s] >= k )
+                                      for EVERY s: all ranks are through the chain of frame k-1, so its outputs - this frame's history - are
+                                      complete everywhere and nobody reads the history of frame k-2 any more, which this frame overwrites;
                                       merge the staged feature rows (history counter bits stay), staged world positions -> current buffer;
                                       the chain on band + halo; present: rank 0 into its pixel buffer, rank r > 0 with peer stores straight into
                                       rank 0's staging image k & 1 (after wait( outAck >= k-1 ));
                                       s.done[r] = k+1 for every s;  rank r > 0: rank0.outArrived[r] = k+1
-     rank 0            [2nd comm stream]  wait( outArrived[s] >= k+1 ) for every s; staging image -> pixel buffer (the peers' bands); s.outAck = k+1
+     rank 0            [2nd comm stream]  wait( outArrived[s] >= k+1 ) for every s; staging image -> pixel buffer (the peers' bands); s.outAck = k+1;
+                                      readers of the pixel buffer (lh2b_read_pixels*, lh2b_present_gl) wait for this copy
+   A converging frame (camera at rest) stores no features: its staging set is not merged and 'features' stays what the last restarted frame left.
    Every value a pixel depends on is computed by the same instructions from the same inputs as on one GPU (halo rows are computed twice,
    identically), so the frame is bit-identical to the single-GPU frame at 1 spp - checked by tests/multigpu_worker.py.
 */
