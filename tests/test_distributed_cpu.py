@@ -92,3 +92,84 @@ def test_sample_shard_partition():
                 assert total == world * spp
                 covered += list(range(first, first + spp))
             assert covered == list(range(world * spp))
+
+
+# ---- tile sharding (TileShardedRenderer): the host-side protocol over gloo with a stand-in core -----------------------------------------
+class _TileStubCore:
+    """Records what TileShardedRenderer asks of a core; handles are per-rank byte strings so that the exchange order can be checked."""
+
+    def __init__(self, rank):
+        self.rank, self.calls, self.settings, self.imported = rank, [], {}, None
+
+    def Setting(self, name, value):
+        self.settings[name] = value
+        self.calls.append(("Setting", name, value))
+
+    def TileCreate(self, rank, world):
+        self.calls.append(("TileCreate", rank, world))
+        return "gatherer"
+
+    def TileExport(self, g):
+        return bytes([0xA0 + self.rank]) * 8
+
+    def TileImport(self, g, blob):
+        self.imported = blob
+
+    def TileRows(self, g):
+        return (4 * self.rank, 240, 2)
+
+    def Render(self, view, converge, async_):
+        self.calls.append(("Render", converge, async_))
+
+    def TileFrame(self, g):
+        self.calls.append(("TileFrame",))
+
+    def ReadPixelsAsync(self, out):
+        self.calls.append(("ReadPixelsAsync",))
+
+    def WaitForRender(self):
+        self.calls.append(("WaitForRender",))
+
+    def TileWait(self, g):
+        self.calls.append(("TileWait",))
+
+    def WaitReadPixels(self):
+        self.calls.append(("WaitReadPixels",))
+
+    def TileDestroy(self, g):
+        self.calls.append(("TileDestroy",))
+
+
+def _tile_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from lighthouse2_b200.distributed import TileShardedRenderer
+    core = _TileStubCore(rank)
+    r = TileShardedRenderer(core, rank, world, filter_shard=1, interleave=1)
+    # the settings reach the core before the gatherer is created (lh2b_tile_create reads them), pipelined frames are switched on
+    names = [c[1] for c in core.calls if c[0] == "Setting"]
+    assert set(names) >= {"pipeline", "tileFilterShard", "tileInterleave"}
+    assert [c[0] for c in core.calls].index("TileCreate") > max(i for i, c in enumerate(core.calls) if c[0] == "Setting")
+    # every rank imports every rank's handles, concatenated in rank order
+    assert core.imported == b"".join(bytes([0xA0 + q]) * 8 for q in range(world))
+    assert r.rows == (4 * rank, 240, 2)
+    host = np.zeros((4, 4, 4), np.float32)
+    for conv in (1, 0):
+        r.frame("view", conv, host)
+    frame_calls = [c[0] for c in core.calls if c[0] in ("Render", "TileFrame", "ReadPixelsAsync")]
+    assert frame_calls == (["Render", "TileFrame", "ReadPixelsAsync"] * 2 if rank == 0 else ["Render", "TileFrame"] * 2)    # only rank 0 holds the frame
+    assert [c for c in core.calls if c[0] == "Render"] == [("Render", 1, True), ("Render", 0, True)]
+    r.close()
+    tail = [c[0] for c in core.calls][-4:] if rank == 0 else [c[0] for c in core.calls][-3:]
+    assert tail == (["WaitForRender", "TileWait", "WaitReadPixels", "TileDestroy"] if rank == 0 else ["WaitForRender", "TileWait", "TileDestroy"])
+    if rank == 0:
+        open(out, "w").write("ok")
+    dist.destroy_process_group()
+
+
+def test_two_rank_tile_sharding_host_protocol(tmp_path):
+    out = str(tmp_path / "tile_ok.txt")
+    port = 31500 + os.getpid() % 2000
+    mp.spawn(_tile_worker, args=(2, port, out), nprocs=2, join=True)
+    assert open(out).read() == "ok"
