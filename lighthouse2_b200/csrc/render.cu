@@ -30,8 +30,13 @@ static uint32_t RandomUInt( uint32_t& seed ) { seed ^= seed << 13, seed ^= seed 
 
 void InitRenderState( lh2b_core* core )
 {
-	// blue noise: three byte tables expanded to one uint per entry at offsets 0 / 65536 / 3*65536 (rendercore.cpp:247-254)
-	std::vector<uint32_t> bn( 65536 * 5, 0 );
+	// blue noise: three byte tables expanded to one uint per entry at offsets 0 / 65536 / 3*65536 (rendercore.cpp:247-254).
+	// The sampler (tools_shared.h:324-337, like Heitz's published code) indexes the ranking tile with the UNWRAPPED dimension: from the
+	// third path length on (dimensions 8..11) the four rank words of a pixel are those of the next tile pixel, and for tile pixel (127, 127)
+	// they lie up to 12 words past the end of the reference's buffer (undefined there). Here those words exist and are zero - without the
+	// padding the read returned whatever allocation followed the table: two core instances of one process disagreed in 1-4 pixels of a 4K
+	// frame (tools/determinism_probe.py).
+	std::vector<uint32_t> bn( 65536 * 5 + 16, 0 );
 	const unsigned char* b = lh2b_bluenoise_bytes;
 	for (int i = 0; i < 65536; i++) bn[i] = b[i];
 	for (int i = 0; i < 128 * 128 * 8; i++) bn[i + 65536] = b[65536 + i];
@@ -843,10 +848,14 @@ int lh2b_debug_read_table( lh2b_core* core, const char* name, void* out, size_t 
 	TABLE( "materials", materials ) TABLE( "triLights", triLights ) TABLE( "pointLights", pointLights ) TABLE( "spotLights", spotLights )
 	TABLE( "dirLights", dirLights ) TABLE( "instDesc", instDesc ) TABLE( "blueNoise", blueNoise ) TABLE( "sky", skyPixels )
 	TABLE( "argb32", argb32 ) TABLE( "argb128", argb128 ) TABLE( "nrm32", nrm32 ) TABLE( "instTrav", instTrav )
+	// wavefront state as the last frame left it: path0* / path1* = the two ping-pong path-state sets (O, D, T), hits, conn* = shadow rays
+	TABLE( "path0O", pathBuf[0][0] ) TABLE( "path0D", pathBuf[0][1] ) TABLE( "path0T", pathBuf[0][2] )
+	TABLE( "path1O", pathBuf[1][0] ) TABLE( "path1D", pathBuf[1][1] ) TABLE( "path1T", pathBuf[1][2] )
+	TABLE( "hits", hitBuf ) TABLE( "connO", connBuf[0] ) TABLE( "connD", connBuf[1] ) TABLE( "connE", connBuf[2] ) TABLE( "counters", counters )
 #undef TABLE
 	if (!strcmp( name, "nodes" )) src = core->arenaNodes.ptr, bytes = (size_t)core->arenaNodeTop * CW_NODE_QUADS * sizeof( uint4 );
 	if (!strcmp( name, "tris" )) src = core->arenaTris.ptr, bytes = (size_t)core->arenaTriTop * 3 * sizeof( float4 );
-	if (!src && bytes == 0 && strcmp( name, "nodes" ) && strcmp( name, "tris" )) { bool known = false; for (const char* n : { "materials", "triLights", "pointLights", "spotLights", "dirLights", "instDesc", "blueNoise", "sky", "argb32", "argb128", "nrm32", "instTrav" }) known |= !strcmp( name, n ); if (!known) throw CoreError( "debug_read_table: unknown table" ); }
+	if (!src && bytes == 0 && strcmp( name, "nodes" ) && strcmp( name, "tris" )) { bool known = false; for (const char* n : { "materials", "triLights", "pointLights", "spotLights", "dirLights", "instDesc", "blueNoise", "sky", "argb32", "argb128", "nrm32", "instTrav", "path0O", "path0D", "path0T", "path1O", "path1D", "path1T", "hits", "connO", "connD", "connE", "counters" }) known |= !strcmp( name, n ); if (!known) throw CoreError( "debug_read_table: unknown table" ); }
 	if (bytesOut) *bytesOut = bytes;
 	if (out && src && bytes) CUDA_CHECK( cudaMemcpy( out, src, std::min( bytes, maxBytes ), cudaMemcpyDeviceToHost ) );
 	API_END

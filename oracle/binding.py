@@ -318,7 +318,7 @@ def ref_shade_gpu(oracle, view, path_length, O4, D4, T4, hits, R0, shift, pass_,
     tc = np.array([len(t) for t in tris], np.int32)
     im = np.array([m for m, _ in sd.instances], np.int32)
     bn8 = np.fromfile(_BLUENOISE, dtype=np.uint8)
-    bn = np.zeros(65536 * 5, np.uint32)
+    bn = np.zeros(65536 * 5 + 16, np.uint32)     # + 16 zero words: the sampler reads past the ranking tile for tile pixel (127, 127) at dimensions >= 8
     bn[:65536] = bn8[:65536]; bn[65536:65536 + 131072] = bn8[65536:65536 + 131072]; bn[3 * 65536:3 * 65536 + 131072] = bn8[65536 + 131072:]
     lights = [np.ascontiguousarray(a) for a in (sd.tri_lights, sd.point_lights, sd.spot_lights, sd.dir_lights)]
     r = RefShadeIn()

@@ -180,7 +180,7 @@ static void SetupScene( const OrcFrameIn& in, FrameCtx& ctx )
 		for (int k = 0; k < 4; k++) o[k] = total[k] * (1.0f / (64 * 64));
 	}
 	memcpy( sc.worldToSky, in.worldToSky, sizeof( sc.worldToSky ) );
-	bn.assign( 65536 * 5, 0 );
+	bn.assign( 65536 * 5 + 16, 0 );	// 16 zero words behind the ranking tile: the sampler reads past it for tile pixel (127, 127) at dimensions >= 8 (as the reference does)
 	for (int i = 0; i < 65536; i++) bn[i] = in.blueNoiseBytes[i];
 	for (int i = 0; i < 128 * 128 * 8; i++) bn[i + 65536] = in.blueNoiseBytes[65536 + i], bn[i + 3 * 65536] = in.blueNoiseBytes[65536 + 131072 + i];
 	sc.blueNoise = bn.data();

@@ -117,7 +117,7 @@ extern "C" __attribute__( ( visibility( "default" ) ) ) int refshade_run( RefSha
 	float4* d128 = Up<float4>( in->argb128, (size_t)in->argb128Count * 16 ); owned.push_back( d128 );
 	uchar4* dN = Up<uchar4>( in->nrm32, (size_t)in->nrm32Count * 4 ); owned.push_back( dN );
 	float4* dSky = Up<float4>( in->skyPixels4, (size_t)in->skyPixelCount * 16 ); owned.push_back( dSky );
-	uint* dBN = Up<uint>( in->blueNoise, 65536 * 5 * 4 ); owned.push_back( dBN );
+	uint* dBN = Up<uint>( in->blueNoise, (65536 * 5 + 16) * 4 ); owned.push_back( dBN );	// 16 zero words of padding, see binding.py
 	const int4 lc = make_int4( in->triLightCount, in->pointLightCount, in->spotLightCount, in->dirLightCount );
 	mat4 w2s;
 	memcpy( &w2s, in->worldToSky, 64 );

@@ -78,3 +78,48 @@ elif mode == "tables":           # ... and the same materials, lights, instance 
         same = ta.shape == tb.shape and np.array_equal(ta, tb)
         where = "" if same or ta.shape != tb.shape else f"; first differing byte {int(np.nonzero(ta != tb)[0][0])}, {int((ta != tb).sum())} bytes differ"
         print(f"{name}: {ta.size} bytes, identical {same}{where}", flush=True)
+elif mode == "frame-state":      # the wavefront buffers as one frame (maximum path length 3) leaves them: where do the two cores part?
+    a, b = make(), make()
+    a.Render(views[0], 1), b.Render(views[0], 1)
+    ca, cb = a.DebugReadTable("counters").view(np.uint32), b.DebugReadTable("counters").view(np.uint32)
+    print("extension rays per path length", ca[:5], cb[:5], "shadow rays", ca[18:23], cb[18:23], flush=True)
+    n2, n3s = int(ca[2]), int(ca[18 + 3])           # rays shade( 2 ) emitted = paths of length 3; shadow rays of shade( 3 )
+
+    def rows(core, name, n):
+        return core.DebugReadTable(name).view(np.float32).reshape(-1, 4)[:n]
+
+    def cmp(what, xa, xb, key_a, key_b):
+        ia, ib = np.argsort(key_a, kind="stable"), np.argsort(key_b, kind="stable")
+        same_keys = np.array_equal(key_a[ia], key_b[ib])
+        d = (xa[ia].view(np.uint32) != xb[ib].view(np.uint32)).any(axis=1) if same_keys else None
+        print(f"{what}: {len(xa)} entries, same path set {same_keys}" + ("" if d is None else f", {int(d.sum())} entries differ" + (f", first key {int(key_a[ia][np.nonzero(d)[0][0]])}: {xa[ia][np.nonzero(d)[0][0]]} vs {xb[ib][np.nonzero(d)[0][0]]}" if d.any() else "")), flush=True)
+
+    # path length 3 reads set 0 (written by shade( 2 )): O.w carries the path index << 6 | flags
+    Oa, Ob = rows(a, "path0O", n2), rows(b, "path0O", n2)
+    ka, kb = Oa[:, 3].view(np.uint32) >> 6, Ob[:, 3].view(np.uint32) >> 6
+    for f in ("O", "D", "T"):
+        cmp(f"paths of length 3, {f} (output of shade 2)", rows(a, "path0" + f, n2), rows(b, "path0" + f, n2), ka, kb)
+    cmp("hits of extend 3", rows(a, "hits", n2), rows(b, "hits", n2), ka, kb)
+    bad_key = int(os.environ.get("PROBE_KEY", "5388903"))
+    for tag, O_, k_, core in (("first core", Oa, ka, a), ("second core", Ob, kb, b)):
+        i = np.nonzero(k_ == bad_key)[0]
+        if len(i):
+            h = rows(core, "hits", n2)[i[0]]
+            print(f"{tag}: path {bad_key} at slot {int(i[0])}: O {O_[i[0]]} flags {int(O_[i[0], 3].view(np.uint32)) & 63} D {rows(core, 'path0D', n2)[i[0]]} T {rows(core, 'path0T', n2)[i[0]]} "
+                  f"hit words {h.view(np.uint32)} (as float {h}, as int {h.view(np.int32)})", flush=True)
+    Ea, Eb = rows(a, "connE", n3s), rows(b, "connE", n3s)
+    for f in ("O", "D", "E"):
+        cmp(f"shadow rays of shade 3, {f}", rows(a, "conn" + f, n3s), rows(b, "conn" + f, n3s), Ea[:, 3].view(np.uint32), Eb[:, 3].view(np.uint32))
+elif mode == "tables-after":     # does a frame write into one of the read-only tables (a stray store into a neighbouring allocation)?
+    a, b = make(), make()
+    names = ("materials", "triLights", "pointLights", "spotLights", "dirLights", "instDesc", "blueNoise", "sky", "argb32", "argb128", "nrm32", "instTrav", "nodes", "tris")
+    before = {(c, n): c.DebugReadTable(n).copy() for c in (a, b) for n in names}
+    for v in views:
+        a.Render(v, 1), b.Render(v, 1)
+    for tag, c in (("first core", a), ("second core", b)):
+        for n in names:
+            now = c.DebugReadTable(n)
+            if not np.array_equal(now, before[(c, n)]):
+                idx = np.nonzero(now != before[(c, n)])[0]
+                print(f"{tag}: table {n} CHANGED during rendering: {len(idx)} bytes, first at byte {int(idx[0])} (of {now.size}): {before[(c, n)][idx[0]:idx[0] + 16]} -> {now[idx[0]:idx[0] + 16]}", flush=True)
+        print(f"{tag}: checked", flush=True)
